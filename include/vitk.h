@@ -1,0 +1,212 @@
+/*
+ * vitk.h -- C-ABI of libvitk.so: the B200 (sm_100a) kernels behind the ViT/DeiT training path.
+ *
+ * The reference (gogolB/thyroid-vit-cnn-comparison) is pure Python and has no FFI of its own
+ * (SURVEY.md section 8b): its "boundary" is the set of eager ATen call sites inside
+ * src/models/vit/vision_transformer_base.py, src/models/vit/deit_models.py and
+ * src/training/lightning_modules.py.  Each entry point below replaces one (or one fused group)
+ * of those call sites; the file:line it replaces is cited next to it.  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer into caller-owned memory
+ *     (torch storage in practice) unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs.
+ *   - return value: 0 on success, negative vitk_status on failure; vitk_last_error() gives text.
+ *   - bf16 buffers are passed as void* (uint16 storage, torch.bfloat16).
+ *   - the library never falls back to a CPU or library path: a missing GPU is an error.
+ */
+#ifndef VITK_H_
+#define VITK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITK_ABI_VERSION 1
+
+typedef enum {
+  VITK_OK = 0,
+  VITK_ERR_INVALID = -1,   /* bad shape / alignment / null pointer            */
+  VITK_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed             */
+  VITK_ERR_UNSUPPORTED = -3 /* shape outside what the sm_100a kernels cover    */
+} vitk_status;
+
+int vitk_abi_version(void);
+const char* vitk_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+int64_t vitk_launch_count(void);
+void vitk_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM on tcgen05 / TMEM fed by TMA.   D[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)
+ * replaces nn.Linear / nn.Conv2d(k=16,s=16) forward, dgrad and wgrad:
+ *   vision_transformer_base.py:95-101,136-138 (patch proj), :166,178 (qkv), :168,192 (proj),
+ *   :212-222 (fc1/fc2) and their autograd backward.
+ * Operand storage: a "K-major" operand is row-major [rows, K] (K contiguous, `ld` = row pitch
+ * in elements); an "MN-major" operand is row-major [K, rows] (rows contiguous).  The second
+ * form lets dgrad read W[N,K] and wgrad read dY[M,N] / X[M,K] without any transpose copy.
+ * ------------------------------------------------------------------------------------------ */
+typedef enum {
+  VITK_EPI_STORE = 0,      /* out = acc*alpha + bias + residual                               */
+  VITK_EPI_GELU = 1,       /* out = pre-activation (bf16), out2 = gelu_erf(pre) (bf16)        */
+  VITK_EPI_DGELU = 2,      /* out = acc * gelu_erf'(aux)  (aux = saved pre-activation, bf16)  */
+  VITK_EPI_ATOMIC_ADD = 3, /* out(fp32) += acc*alpha  (split-K wgrad, red.global.add.f32)     */
+  VITK_EPI_TOKENS = 4      /* patch rows -> token rows: out[b, prefix+p, :] = acc+bias+pos    */
+} vitk_epilogue;
+
+typedef struct {
+  const void* A;      /* bf16 */
+  const void* B;      /* bf16 */
+  int64_t lda, ldb;   /* row pitch in elements of the row-major storage described above */
+  int32_t a_mn_major; /* 0: A stored [M,K]; 1: A stored [K,M] */
+  int32_t b_mn_major; /* 0: B stored [N,K]; 1: B stored [K,N] */
+  int32_t M, N, K;
+  int32_t split_k;    /* >=1; >1 requires VITK_EPI_ATOMIC_ADD */
+  int32_t epilogue;   /* vitk_epilogue */
+  int32_t out_fp32;   /* 0: out is bf16, 1: out is fp32 */
+  float alpha;
+  const float* bias;      /* [N] fp32 or NULL */
+  const float* residual;  /* [M, ldr] fp32 or NULL (may alias out) */
+  int64_t ldr;
+  void* out;
+  int64_t ldo;
+  void* out2;             /* bf16 [M, ldo2] (GELU) */
+  int64_t ldo2;
+  const void* aux;        /* bf16 [M, ldaux] (DGELU) */
+  int64_t ldaux;
+  /* VITK_EPI_TOKENS: input row r = b*rows_per_img + p  ->  output row b*tokens_per_img + prefix + p,
+   * pos is fp32 [tokens_per_img, N] (pos_embed), added to the row it lands on. */
+  int32_t rows_per_img, tokens_per_img, prefix;
+  const float* pos;
+} vitk_gemm_args;
+
+int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm (eps 1e-5, affine) -- vision_transformer_base.py:263,273,377 (nn.LayerNorm)
+ * fwd: x fp32 [rows, dim] -> y bf16 [rows, dim], mean/rstd fp32 [rows]
+ * bwd: dx = (dres or 0) + LN'(dy);  dgamma/dbeta/dcolsum are ACCUMULATED (+=) into fp32 [dim].
+ *      dcolsum (optional) receives the column sum of the emitted dx -- that is the bias gradient
+ *      of the nn.Linear that produced the residual branch feeding this LayerNorm's input.
+ * ------------------------------------------------------------------------------------------ */
+int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                       float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
+                       void* stream);
+int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                       const float* gamma, const float* dres, float* dx, void* dx_bf16,
+                       float* dgamma, float* dbeta, float* dcolsum, int64_t rows, int32_t dim,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused softmax attention, dh = 64 -- vision_transformer_base.py:174-191 (Attention.forward:
+ * q@k^T * scale, softmax, attn@v) without materialising [B,H,N,N].
+ * qkv  bf16 [B, N, 3, H, 64]  (exactly the layout nn.Linear(D,3D) emits, :178)
+ * out  bf16 [B, N, H, 64]     (== (attn@v).transpose(1,2).reshape(B,N,C), :191)
+ * lse  fp32 [B, H, N]         natural-log sum-exp of the scaled scores (saved for backward)
+ * bwd recomputes P from q,k and lse; delta = rowsum(dout*out) is computed internally into
+ * `delta` (fp32 [B,H,N] scratch).
+ * probs (optional, eval only): fp32 [B,H,N,N] attention maps (:186-188 `attention_maps`).
+ * ------------------------------------------------------------------------------------------ */
+int vitk_attention_fwd(const void* qkv, void* out, float* lse, float* probs, int32_t B, int32_t N,
+                       int32_t H, float scale, void* stream);
+int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                       float* delta, void* dqkv, int32_t B, int32_t N, int32_t H, float scale,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch / token plumbing -- vision_transformer_base.py:120-143 (PatchEmbed.forward),
+ * deit_models.py:200-211 and vision_transformer_base.py:446-452 (cls/dist tokens + pos_embed).
+ * ------------------------------------------------------------------------------------------ */
+/* images fp32 NCHW [B,C,H,W] -> bf16 patch matrix [B*gh*gw, C*P*P] (k = c*P*P + ky*P + kx,
+ * the flattening order of Conv2d.weight[D,C,P,P]) */
+int vitk_patchify_bf16(const float* images, void* patches, int32_t B, int32_t C, int32_t H,
+                       int32_t W, int32_t P, void* stream);
+/* x[b, t, :] = tok_t + pos[t, :] for t < n_prefix (cls, dist) */
+int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos,
+                           int32_t B, int32_t tokens_per_img, int32_t dim, int32_t n_prefix,
+                           void* stream);
+/* dpos[t,:] += sum_b dx[b,t,:] ; dcls += sum_b dx[b,0,:] ; ddist += sum_b dx[b,1,:];
+ * dpatch_bf16 [B*rows_per_img, dim] = bf16(dx[b, n_prefix+p, :]) (the dY of the patch GEMM);
+ * dbias_patch[dim] += column sum over patch rows. */
+int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch_bf16,
+                    float* dbias_patch, int32_t B, int32_t tokens_per_img, int32_t dim,
+                    int32_t n_prefix, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Final norm + classification heads on the pooled rows only --
+ * deit_models.py:217,224-235 / vision_transformer_base.py:468-486 (norm, x[:,0], head, head_dist)
+ * x fp32 [B, tokens_per_img, dim]; for head h in [0,n_heads): row h of every image is
+ * LayerNorm'd and multiplied by W_h [C, dim] (+ b_h [C]) -> logits_h [B, C].
+ * bwd writes dx / dx_bf16 (ZERO outside the pooled rows), accumulates every parameter gradient
+ * and (optional) dcolsum[dim] += column sum of dx (bias gradient of the last block's fc2).
+ * ------------------------------------------------------------------------------------------ */
+int vitk_head_fwd(const float* x, const float* gamma, const float* beta, const float* W0,
+                  const float* b0, const float* W1, const float* b1, float* logits0,
+                  float* logits1, float* xhat, float* rstd, int32_t B, int32_t tokens_per_img,
+                  int32_t dim, int32_t C, int32_t n_heads, float eps, void* stream);
+int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat,
+                  const float* rstd, const float* gamma, const float* beta, const float* W0,
+                  const float* W1,
+                  float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dW0, float* db0,
+                  float* dW1, float* db1, float* dcolsum, int32_t B, int32_t tokens_per_img,
+                  int32_t dim, int32_t C, int32_t n_heads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused classification / distillation loss with gradient --
+ * lightning_modules.py:455-465 (0.5*CE(cls)+0.5*CE(dist) or CE), :959-974 (distillation:
+ * (1-alpha)*CE(cls,y) + alpha*KL(log_softmax(d/T) || softmax(t/T))*T^2 'batchmean', or hard CE
+ * on the teacher argmax), deit_models.py:461-480 (DistillationLoss), nn.CrossEntropyLoss
+ * label_smoothing (lightning_modules.py:345-350).
+ * mode 0: w_cls*CE(cls,y) [+ w_dist*CE(dist,y) if dist given]
+ * mode 1: w_cls*CE(cls,y) + w_dist*KL_soft(dist, teacher, T)
+ * mode 2: w_cls*CE(cls,y) + w_dist*CE(dist, argmax teacher)
+ * out_scalars fp32[8]: {loss, cls_loss, dist_loss, n_correct(cls vs y), n_agree(cls vs teacher), ...}
+ * dcls/ddist: fp32 [B,C] gradient of `loss` (already divided by B*grad_div; grad_div = world size
+ * under data parallel so that an all-reduce SUM yields the global-batch mean).
+ * ------------------------------------------------------------------------------------------ */
+int vitk_loss_fwd_bwd(const float* cls_logits, const float* dist_logits, const float* teacher_logits,
+                      const int64_t* labels, float* out_scalars, float* dcls, float* ddist,
+                      int32_t B, int32_t C, int32_t mode, float w_cls, float w_dist, float T,
+                      float label_smoothing, float grad_div, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer -- torch.optim.AdamW as configured at lightning_modules.py:599-604,1108-1113 plus
+ * Lightning's clip_grad_norm_(1.0) (configs/trainer/default.yaml:21,54).
+ * The parameters live in ONE flat fp32 buffer cut into chunks; chunk c covers
+ * [chunk_off[c], chunk_off[c]+chunk_len[c]) and uses lr*lr_scale[c], wd[c].
+ * state fp32[4] on device: {step, lr, grad_sqnorm, clip_coef}.
+ * ------------------------------------------------------------------------------------------ */
+int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, void* stream);
+int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    void* params_bf16, const int64_t* chunk_off, const int32_t* chunk_len,
+                    const float* chunk_lr_scale, const float* chunk_wd, int32_t n_chunks,
+                    float* state, float beta1, float beta2, float eps, float max_grad_norm,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small memory-bound helpers
+ * ------------------------------------------------------------------------------------------ */
+int vitk_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* out[dim] += column sums of a bf16 [rows, dim] matrix (bias gradients of qkv / fc1) */
+int vitk_colsum_bf16(const void* x_bf16, float* out, int64_t rows, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ensemble + attention rollout (config 5) --
+ * scripts/run_ensemble_kfold_evaluation.py:127-152 (sum_m w_m*softmax(logits_m) -> argmax),
+ * src/models/vit/attention_utils.py:129-145 (rollout; the reference body is `pass`: spec is
+ * Abnar & Zuidema 2020, see oracle/vit_oracle.py::attention_rollout).
+ * ------------------------------------------------------------------------------------------ */
+int vitk_ensemble_probs(const float* logits /*[F,B,C]*/, const float* weights /*[F]*/,
+                        float* probs /*[B,C]*/, int64_t* pred /*[B]*/, int32_t F, int32_t B,
+                        int32_t C, void* stream);
+/* probs fp32 [L,B,H,N,N] -> rollout fp32 [B,N,N]; fusion 0 mean, 1 max, 2 min */
+int vitk_attention_rollout(const float* probs, float* rollout, float* scratch, int32_t L,
+                           int32_t B, int32_t H, int32_t N, int32_t fusion, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITK_H_ */

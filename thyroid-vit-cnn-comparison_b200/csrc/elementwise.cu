@@ -1,0 +1,442 @@
+// elementwise.cu -- the memory-bound glue of the ViT/DeiT step: casts, patch gather, token
+// assembly and its backward, pooled final-norm + heads, bias-gradient column sums, ensemble
+// probabilities and attention rollout.  All kernels are coalesced and 128-bit vectorised; grids
+// are capped at a multiple of the SM count and grid-stride over the rest.
+#include "vitk_common.cuh"
+
+namespace vitk {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+inline int capped_grid(long long work_items, int threads, int ctas_per_sm) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16
+__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = ldg_f4(src + 8 * i), b = ldg_f4(src + 8 * i + 4);
+    *reinterpret_cast<uint4*>(dst + 8 * i) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+// ------------------------------------------------------------------ column sums of a bf16 matrix
+// block = 32 column-vectors (8 bf16 each) x 8 row lanes; grid.x = column chunk, grid.y = row slab
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long rows,
+                                                     int dim, int rows_per_block) {
+  __shared__ float red[8][32][8];
+  const int cv = blockIdx.x * 32 + threadIdx.x;  // column vector index
+  const int col = cv * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  if (col < dim) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 u = ldg_u4(x + r * dim + col);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && col < dim) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][j];
+      atomicAdd(out + col + j, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ patch gather (fp32 NCHW -> bf16 [B*gh*gw, C*P*P])
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int B, int C, int H, int W, int P) {
+  const int wv = W >> 3;
+  const long long total = (long long)B * C * H * wv;
+  const int gw = W / P, gh = H / P;
+  const int Kdim = C * P * P;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xv = int(i % wv);
+    long long r = i / wv;
+    const int y = int(r % H);
+    r /= H;
+    const int c = int(r % C);
+    const int b = int(r / C);
+    const float* src = img + (((long long)b * C + c) * H + y) * W + xv * 8;
+    const float4 a0 = ldg_f4(src), a1 = ldg_f4(src + 4);
+    const int x = xv * 8;
+    const int py = y / P, ky = y - py * P, px = x / P, kx = x - px * P;
+    bf16* dst = patches + ((long long)(b * gh + py) * gw + px) * Kdim + c * P * P + ky * P + kx;
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
+  }
+}
+
+// ------------------------------------------------------------------ cls / dist token rows
+__global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls_tok, const float* __restrict__ dist_tok,
+                                     const float* __restrict__ pos, int B, int T, int dim, int n_prefix) {
+  const int dv = dim >> 2;
+  const long long total = (long long)B * n_prefix * dv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % dv);
+    const int t = int((i / dv) % n_prefix);
+    const int b = int(i / ((long long)dv * n_prefix));
+    const float4 tk = ldg_f4((t == 0 ? cls_tok : dist_tok) + 4 * v);
+    const float4 ps = ldg_f4(pos + (long long)t * dim + 4 * v);
+    *reinterpret_cast<float4*>(x + ((long long)b * T + t) * dim + 4 * v) =
+        make_float4(tk.x + ps.x, tk.y + ps.y, tk.z + ps.z, tk.w + ps.w);
+  }
+}
+
+// ------------------------------------------------------------------ backward of token assembly
+// grid (T, ceil(B/IMGS)); blockDim = dim/4 threads (one float4 column each)
+constexpr int TOK_IMGS = 32;
+__global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, float* __restrict__ dcls,
+                                  float* __restrict__ ddist, bf16* __restrict__ dpatch, float* __restrict__ dbias, int B, int T,
+                                  int dim, int n_prefix) {
+  const int t = blockIdx.x;
+  const int b0 = blockIdx.y * TOK_IMGS;
+  const int b1 = min(B, b0 + TOK_IMGS);
+  const int rows_per_img = T - n_prefix;
+  for (int v = threadIdx.x; v < (dim >> 2); v += blockDim.x) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int b = b0; b < b1; ++b) {
+      const float4 g = ldg_f4(dx + ((long long)b * T + t) * dim + 4 * v);
+      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      if (t >= n_prefix && dpatch != nullptr)
+        *reinterpret_cast<uint2*>(dpatch + ((long long)b * rows_per_img + (t - n_prefix)) * dim + 4 * v) =
+            make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+    }
+    if (dpos != nullptr) {
+      float* p = dpos + (long long)t * dim + 4 * v;
+      atomicAdd(p, acc.x); atomicAdd(p + 1, acc.y); atomicAdd(p + 2, acc.z); atomicAdd(p + 3, acc.w);
+    }
+    float* extra = nullptr;
+    if (t == 0 && n_prefix >= 1) extra = dcls;
+    else if (t == 1 && n_prefix >= 2) extra = ddist;
+    else if (t >= n_prefix) extra = dbias;
+    if (extra != nullptr) {
+      float* p = extra + 4 * v;
+      atomicAdd(p, acc.x); atomicAdd(p + 1, acc.y); atomicAdd(p + 2, acc.z); atomicAdd(p + 3, acc.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pooled final norm + heads
+// one warp per (image, head)
+__global__ void head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ W1,
+                                const float* __restrict__ b1, float* __restrict__ logits0, float* __restrict__ logits1,
+                                float* __restrict__ xhat, float* __restrict__ rstd, int B, int T, int dim, int C, int n_heads,
+                                float eps) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * n_heads) return;
+  const int hd = w / B, b = w - hd * B;
+  const float* xr = x + ((long long)b * T + hd) * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s += xr[i];
+  const float mu = warp_sum(s) / float(dim);
+  float q = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float d = xr[i] - mu;
+    q += d * d;
+  }
+  const float rs = rsqrtf(warp_sum(q) / float(dim) + eps);
+  float* xh = xhat + ((long long)hd * B + b) * dim;
+  for (int i = lane; i < dim; i += 32) xh[i] = (xr[i] - mu) * rs;
+  if (lane == 0) rstd[hd * B + b] = rs;
+  __syncwarp();
+  const float* W = hd == 0 ? W0 : W1;
+  const float* bias = hd == 0 ? b0 : b1;
+  float* lg = (hd == 0 ? logits0 : logits1) + (long long)b * C;
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+    for (int i = lane; i < dim; i += 32) acc += (xh[i] * gamma[i] + beta[i]) * W[(long long)c * dim + i];
+    acc = warp_sum(acc);
+    if (lane == 0) lg[c] = acc + (bias != nullptr ? bias[c] : 0.f);
+  }
+}
+
+__global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __restrict__ dl1, const float* __restrict__ xhat,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ W0,
+                                const float* __restrict__ W1, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db0,
+                                float* __restrict__ db1, float* __restrict__ dcolsum, int B, int T, int dim, int C,
+                                int n_heads) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * n_heads) return;
+  const int hd = w / B, b = w - hd * B;
+  const float* dl = (hd == 0 ? dl0 : dl1) + (long long)b * C;
+  const float* W = hd == 0 ? W0 : W1;
+  float* dbh = hd == 0 ? db0 : db1;
+  const float* xh = xhat + ((long long)hd * B + b) * dim;
+  const float rs = rstd[hd * B + b];
+  // dxn = dl . W ; g = dxn * gamma ; LN backward on the single row
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    float dxn = 0.f;
+    for (int c = 0; c < C; ++c) dxn += dl[c] * W[(long long)c * dim + i];
+    const float g = dxn * gamma[i];
+    s1 += g;
+    s2 += g * xh[i];
+    atomicAdd(dgamma + i, dxn * xh[i]);
+    atomicAdd(dbeta + i, dxn);
+  }
+  const float m1 = warp_sum(s1) / float(dim), m2 = warp_sum(s2) / float(dim);
+  float* dxr = dx + ((long long)b * T + hd) * dim;
+  for (int i = lane; i < dim; i += 32) {
+    float dxn = 0.f;
+    for (int c = 0; c < C; ++c) dxn += dl[c] * W[(long long)c * dim + i];
+    const float g = dxn * gamma[i];
+    const float o = rs * (g - m1 - xh[i] * m2);
+    dxr[i] = o;
+    if (dx_bf16 != nullptr) dx_bf16[((long long)b * T + hd) * dim + i] = __float2bfloat16(o);
+    if (dcolsum != nullptr) atomicAdd(dcolsum + i, o);
+  }
+  if (dbh != nullptr)
+    for (int c = lane; c < C; c += 32) atomicAdd(dbh + c, dl[c]);
+}
+
+// dW_h[c, i] += sum_b dl_h[b, c] * (xhat_h[b, i] * gamma[i] + beta[i]); one thread per (h, c, i), loop over b
+__global__ void head_wgrad_kernel(const float* __restrict__ dl0, const float* __restrict__ dl1, const float* __restrict__ xhat,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dW0,
+                                  float* __restrict__ dW1, int B, int dim, int C, int n_heads) {
+  const long long total = (long long)n_heads * C * dim;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = int(idx % dim);
+    const int c = int((idx / dim) % C);
+    const int hd = int(idx / ((long long)dim * C));
+    const float* dl = hd == 0 ? dl0 : dl1;
+    const float* xh = xhat + (long long)hd * B * dim;
+    const float gm = gamma[i], bt = beta[i];
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dl[(long long)b * C + c] * (xh[(long long)b * dim + i] * gm + bt);
+    float* dW = hd == 0 ? dW0 : dW1;
+    dW[(long long)c * dim + i] += acc;
+  }
+}
+
+// ------------------------------------------------------------------ ensemble: sum_f w_f softmax(logits_f) -> argmax
+__global__ void ensemble_kernel(const float* __restrict__ logits, const float* __restrict__ weights, float* __restrict__ probs,
+                                long long* __restrict__ pred, int F, int B, int C) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* pr = probs + (long long)b * C;
+  for (int c = 0; c < C; ++c) pr[c] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    const float* lg = logits + ((long long)f * B + b) * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, lg[c]);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(lg[c] - mx);
+    const float wf = weights[f] / sum;
+    for (int c = 0; c < C; ++c) pr[c] += wf * expf(lg[c] - mx);
+  }
+  int best = 0;
+  float bv = pr[0];
+  for (int c = 1; c < C; ++c)
+    if (pr[c] > bv) {
+      bv = pr[c];
+      best = c;
+    }
+  pred[b] = best;
+}
+
+// ------------------------------------------------------------------ attention rollout
+// fused[b] = fuse_h(probs[l,b,h]); a = (fused + I)/2, rows renormalised; R <- a @ R  (R starts at I)
+__global__ void rollout_fuse_kernel(const float* __restrict__ probs, float* __restrict__ a, int l, int B, int H, int N, int fusion) {
+  const long long total = (long long)B * N;  // one thread-row per (b, i); threads of a warp stride over j
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total) return;
+  const int i = int(row % N);
+  const int b = int(row / N);
+  float sum = 0.f;
+  float* ar = a + row * N;
+  for (int j = lane; j < N; j += 32) {
+    float f = fusion == 0 ? 0.f : (fusion == 1 ? -INFINITY : INFINITY);
+    for (int h = 0; h < H; ++h) {
+      const float p = probs[((((long long)l * B + b) * H + h) * N + i) * N + j];
+      f = fusion == 0 ? f + p : (fusion == 1 ? fmaxf(f, p) : fminf(f, p));
+    }
+    if (fusion == 0) f /= float(H);
+    f = 0.5f * (f + (i == j ? 1.f : 0.f));
+    ar[j] = f;
+    sum += f;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < N; j += 32) ar[j] *= inv;
+}
+// Rout[b] = a[b] @ Rin[b]   (N x N fp32, N ~ 200: plain tiled loop, eval-only path)
+__global__ void rollout_matmul_kernel(const float* __restrict__ a, const float* __restrict__ rin, float* __restrict__ rout, int N) {
+  const int b = blockIdx.z;
+  const int i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const float* ar = a + ((long long)b * N + i) * N;
+  const float* r = rin + (long long)b * N * N;
+  float acc = 0.f;
+  for (int k = 0; k < N; ++k) acc += ar[k] * r[(long long)k * N + j];
+  rout[((long long)b * N + i) * N + j] = acc;
+}
+__global__ void rollout_eye_kernel(float* __restrict__ r, int B, int N) {
+  const long long total = (long long)B * N * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = int(idx % N);
+    const int i = int((idx / N) % N);
+    r[idx] = i == j ? 1.f : 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" int vitk_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  VITK_CHECK_ARG(src && dst && n >= 0, "vitk_cast_f32_to_bf16: bad args");
+  if (n == 0) return VITK_OK;
+  VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "vitk_cast_f32_to_bf16: pointers must be 16-byte aligned");
+  cast_kernel<<<capped_grid(n / 8 + 1, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<bf16*>(dst), n);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_colsum_bf16(const void* x, float* out, int64_t rows, int32_t dim, void* stream) {
+  VITK_CHECK_ARG(x && out && rows > 0 && dim > 0 && dim % 8 == 0, "vitk_colsum_bf16: dim=%d must be a multiple of 8", dim);
+  const int col_chunks = (dim / 8 + 31) / 32;
+  // aim for ~4 CTAs per SM in total
+  int slabs = (num_sms() * 4 + col_chunks - 1) / col_chunks;
+  if (slabs > (rows + 63) / 64) slabs = (int)((rows + 63) / 64);
+  if (slabs < 1) slabs = 1;
+  const int rpb = (int)((rows + slabs - 1) / slabs);
+  dim3 grid(col_chunks, (unsigned)((rows + rpb - 1) / rpb));
+  colsum_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), out, rows, dim, rpb);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_patchify_bf16(const float* images, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,
+                                  void* stream) {
+  VITK_CHECK_ARG(images && patches, "vitk_patchify_bf16: null pointer");
+  VITK_CHECK_ARG(B > 0 && C > 0 && P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0,
+                 "vitk_patchify_bf16: need P %% 8 == 0 and H, W divisible by P (B=%d C=%d H=%d W=%d P=%d)", B, C, H, W, P);
+  const long long total = (long long)B * C * H * (W / 8);
+  patchify_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      images, reinterpret_cast<bf16*>(patches), B, C, H, W, P);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos, int32_t B,
+                                      int32_t T, int32_t dim, int32_t n_prefix, void* stream) {
+  VITK_CHECK_ARG(x && pos && dim % 4 == 0 && n_prefix >= 0 && n_prefix <= 2, "vitk_prefix_tokens_fwd: bad args");
+  if (n_prefix == 0) return VITK_OK;
+  VITK_CHECK_ARG(cls_tok && (n_prefix < 2 || dist_tok), "vitk_prefix_tokens_fwd: missing token");
+  const long long total = (long long)B * n_prefix * (dim / 4);
+  prefix_tokens_kernel<<<capped_grid(total, 256, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cls_tok, dist_tok, pos, B, T,
+                                                                                                      dim, n_prefix);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch_bf16, float* dbias_patch,
+                               int32_t B, int32_t T, int32_t dim, int32_t n_prefix, void* stream) {
+  VITK_CHECK_ARG(dx && dim % 4 == 0 && n_prefix >= 0 && n_prefix <= 2 && T > n_prefix, "vitk_tokens_bwd: bad args");
+  int threads = dim / 4;
+  if (threads > 256) threads = 256;
+  threads = ((threads + 31) / 32) * 32;
+  dim3 grid(T, (B + TOK_IMGS - 1) / TOK_IMGS);
+  tokens_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dx, dpos, dcls, ddist, reinterpret_cast<bf16*>(dpatch_bf16), dbias_patch, B, T, dim, n_prefix);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_head_fwd(const float* x, const float* gamma, const float* beta, const float* W0, const float* b0,
+                             const float* W1, const float* b1, float* logits0, float* logits1, float* xhat, float* rstd,
+                             int32_t B, int32_t T, int32_t dim, int32_t C, int32_t n_heads, float eps, void* stream) {
+  VITK_CHECK_ARG(x && gamma && beta && W0 && logits0 && xhat && rstd, "vitk_head_fwd: null pointer");
+  VITK_CHECK_ARG(n_heads == 1 || (n_heads == 2 && W1 && logits1), "vitk_head_fwd: n_heads must be 1 or 2");
+  VITK_CHECK_ARG(T >= n_heads, "vitk_head_fwd: fewer tokens than heads");
+  const int warps = B * n_heads;
+  head_fwd_kernel<<<(warps + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gamma, beta, W0, b0, W1, b1, logits0, logits1,
+                                                                                      xhat, rstd, B, T, dim, C, n_heads, eps);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat, const float* rstd,
+                             const float* gamma, const float* beta, const float* W0, const float* W1, float* dx,
+                             void* dx_bf16, float* dgamma, float* dbeta, float* dW0, float* db0, float* dW1, float* db1,
+                             float* dcolsum, int32_t B, int32_t T, int32_t dim, int32_t C, int32_t n_heads, void* stream) {
+  VITK_CHECK_ARG(dlogits0 && xhat && rstd && gamma && beta && W0 && dx && dgamma && dbeta && dW0, "vitk_head_bwd: null pointer");
+  VITK_CHECK_ARG(n_heads == 1 || (n_heads == 2 && dlogits1 && W1 && dW1), "vitk_head_bwd: n_heads must be 1 or 2");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VITK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * T * dim * sizeof(float), st));
+  if (dx_bf16 != nullptr) VITK_CUDA(cudaMemsetAsync(dx_bf16, 0, (size_t)B * T * dim * 2, st));
+  const int warps = B * n_heads;
+  head_bwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(dlogits0, dlogits1, xhat, rstd, gamma, W0, W1, dx,
+                                                   reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, db0, db1, dcolsum, B, T,
+                                                   dim, C, n_heads);
+  VITK_LAUNCH_CHECK();
+  const long long total = (long long)n_heads * C * dim;
+  head_wgrad_kernel<<<capped_grid(total, 128, 4), 128, 0, st>>>(dlogits0, dlogits1, xhat, gamma, beta, dW0, dW1, B, dim, C,
+                                                               n_heads);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_ensemble_probs(const float* logits, const float* weights, float* probs, int64_t* pred, int32_t F, int32_t B,
+                                   int32_t C, void* stream) {
+  VITK_CHECK_ARG(logits && weights && probs && pred && F > 0 && B > 0 && C > 0, "vitk_ensemble_probs: bad args");
+  ensemble_kernel<<<(B + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, weights, probs,
+                                                                                      reinterpret_cast<long long*>(pred), F, B, C);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_attention_rollout(const float* probs, float* rollout, float* scratch, int32_t L, int32_t B, int32_t H,
+                                      int32_t N, int32_t fusion, void* stream) {
+  VITK_CHECK_ARG(probs && rollout && scratch && L > 0 && B > 0 && H > 0 && N > 0 && fusion >= 0 && fusion <= 2,
+                 "vitk_attention_rollout: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // scratch: [2][B,N,N] -> a (fused layer matrix) and the ping-pong partner of `rollout`
+  float* a = scratch;
+  float* other = scratch + (size_t)B * N * N;
+  float* cur = (L % 2 == 0) ? rollout : other;  // after L swaps the result lands in `rollout`
+  float* nxt = (L % 2 == 0) ? other : rollout;
+  rollout_eye_kernel<<<capped_grid((long long)B * N * N, 256, 4), 256, 0, st>>>(cur, B, N);
+  VITK_LAUNCH_CHECK();
+  for (int l = 0; l < L; ++l) {
+    const long long rows = (long long)B * N;
+    rollout_fuse_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(probs, a, l, B, H, N, fusion);
+    VITK_LAUNCH_CHECK();
+    dim3 grid((N + 127) / 128, N, B);
+    rollout_matmul_kernel<<<grid, 128, 0, st>>>(a, cur, nxt, N);
+    VITK_LAUNCH_CHECK();
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  return VITK_OK;
+}

@@ -1,0 +1,233 @@
+"""Tensor-level wrappers over the C-ABI (raw device pointers + the current CUDA stream).
+
+Every function enqueues kernels of libvitk.so on torch's current stream and returns torch
+tensors that merely own the memory.  No function here computes anything with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (libvitk has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+
+
+def launch_count() -> int:
+    return int(_lib.load().vitk_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().vitk_reset_launch_count()
+
+
+# --------------------------------------------------------------------------- GEMM
+def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
+         out: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         epilogue: int = _lib.EPI_STORE, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+         split_k: int = 1, alpha: float = 1.0, tokens: Optional[tuple] = None, pos: Optional[torch.Tensor] = None,
+         lda: Optional[int] = None, ldb: Optional[int] = None) -> torch.Tensor:
+    """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue (see include/vitk.h).
+
+    A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].
+    """
+    _req(A, bf16, "gemm A"); _req(B, bf16, "gemm B")
+    a = GemmArgs()
+    a.A, a.B = A.data_ptr(), B.data_ptr()
+    a.lda = lda if lda is not None else (M if a_mn else K)
+    a.ldb = ldb if ldb is not None else (N if b_mn else K)
+    a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
+    a.M, a.N, a.K = M, N, K
+    a.split_k, a.epilogue = split_k, epilogue
+    a.out_fp32 = int(out.dtype == f32)
+    a.alpha = alpha
+    if bias is not None:
+        _req(bias, f32, "gemm bias")
+    if residual is not None:
+        _req(residual, f32, "gemm residual")
+    a.bias, a.residual, a.ldr = _p(bias), _p(residual), N
+    a.out, a.ldo = out.data_ptr(), N
+    a.out2, a.ldo2 = _p(out2), N
+    a.aux, a.ldaux = _p(aux), N
+    if tokens is not None:
+        a.rows_per_img, a.tokens_per_img, a.prefix = tokens
+        a.pos = _p(pos)
+    check(_lib.load().vitk_gemm_bf16(C.byref(a), _stream()), "gemm")
+    return out
+
+
+# --------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=None):
+    _req(x, f32, "layernorm x")
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    y = torch.empty(x.shape, dtype=bf16, device=x.device) if y is None else y
+    mean = torch.empty(rows, dtype=f32, device=x.device) if mean is None else mean
+    rstd = torch.empty(rows, dtype=f32, device=x.device) if rstd is None else rstd
+    check(_lib.load().vitk_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                         rstd.data_ptr(), rows, dim, eps, _stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None, dx_bf16=None, dcolsum=None):
+    _req(dy, bf16, "layernorm dy"); _req(x, f32, "layernorm x")
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    dx = torch.empty_like(x) if dx is None else dx
+    check(_lib.load().vitk_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                         _p(dres), dx.data_ptr(), _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(),
+                                         _p(dcolsum), rows, dim, _stream()), "layernorm_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------- attention
+def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None):
+    _req(qkv, bf16, "attention qkv")
+    out = torch.empty(B, N, H * 64, dtype=bf16, device=qkv.device) if out is None else out
+    lse = torch.empty(B, H, N, dtype=f32, device=qkv.device) if lse is None else lse
+    check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), _p(probs), B, N, H, scale, _stream()),
+          "attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqkv=None, delta=None):
+    _req(qkv, bf16, "attention qkv"); _req(out, bf16, "attention out"); _req(dout, bf16, "attention dout")
+    dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
+    delta = torch.empty(B, H, N, dtype=f32, device=qkv.device) if delta is None else delta
+    check(_lib.load().vitk_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                         dqkv.data_ptr(), B, N, H, scale, _stream()), "attention_bwd")
+    return dqkv
+
+
+# --------------------------------------------------------------------------- tokens
+def patchify(images, P: int, out=None):
+    _req(images, f32, "patchify images")
+    B, Cc, H, W = images.shape
+    rows = B * (H // P) * (W // P)
+    out = torch.empty(rows, Cc * P * P, dtype=bf16, device=images.device) if out is None else out
+    check(_lib.load().vitk_patchify_bf16(images.data_ptr(), out.data_ptr(), B, Cc, H, W, P, _stream()), "patchify")
+    return out
+
+
+def prefix_tokens_fwd(x, cls_tok, dist_tok, pos, n_prefix: int):
+    B, T, dim = x.shape
+    check(_lib.load().vitk_prefix_tokens_fwd(x.data_ptr(), _p(cls_tok), _p(dist_tok), pos.data_ptr(), B, T, dim, n_prefix,
+                                             _stream()), "prefix_tokens_fwd")
+    return x
+
+
+def tokens_bwd(dx, dpos, dcls, ddist, dpatch_bf16, dbias, n_prefix: int):
+    B, T, dim = dx.shape
+    check(_lib.load().vitk_tokens_bwd(dx.data_ptr(), _p(dpos), _p(dcls), _p(ddist), _p(dpatch_bf16), _p(dbias), B, T, dim,
+                                      n_prefix, _stream()), "tokens_bwd")
+
+
+# --------------------------------------------------------------------------- heads
+def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5):
+    _req(x, f32, "head x")
+    B, T, dim = x.shape
+    Cc = W0.shape[0]
+    logits0 = torch.empty(B, Cc, dtype=f32, device=x.device)
+    logits1 = torch.empty(B, Cc, dtype=f32, device=x.device) if n_heads == 2 else None
+    xhat = torch.empty(n_heads, B, dim, dtype=f32, device=x.device)
+    rstd = torch.empty(n_heads, B, dtype=f32, device=x.device)
+    check(_lib.load().vitk_head_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), W0.data_ptr(), _p(b0), _p(W1), _p(b1),
+                                    logits0.data_ptr(), _p(logits1), xhat.data_ptr(), rstd.data_ptr(), B, T, dim, Cc, n_heads,
+                                    eps, _stream()), "head_fwd")
+    return logits0, logits1, xhat, rstd
+
+
+def head_bwd(dl0, dl1, xhat, rstd, gamma, beta, W0, W1, dx, dx_bf16, dgamma, dbeta, dW0, db0, dW1, db1, dcolsum,
+             T: int, n_heads: int):
+    B, Cc = dl0.shape
+    dim = W0.shape[1]
+    check(_lib.load().vitk_head_bwd(dl0.data_ptr(), _p(dl1), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                    W0.data_ptr(), _p(W1), dx.data_ptr(), _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(),
+                                    dW0.data_ptr(), _p(db0), _p(dW1), _p(db1), _p(dcolsum), B, T, dim, Cc, n_heads, _stream()),
+          "head_bwd")
+
+
+# --------------------------------------------------------------------------- loss
+def loss_fwd_bwd(cls_logits, dist_logits, teacher_logits, labels, *, mode: int, w_cls: float, w_dist: float, T: float = 1.0,
+                 label_smoothing: float = 0.0, grad_div: float = 1.0):
+    _req(cls_logits, f32, "loss cls_logits")
+    if labels.dtype != torch.int64:
+        raise RuntimeError("loss labels must be int64")
+    B, Cc = cls_logits.shape
+    out = torch.empty(8, dtype=f32, device=cls_logits.device)
+    dcls = torch.empty_like(cls_logits)
+    ddist = torch.empty_like(dist_logits) if dist_logits is not None else None
+    check(_lib.load().vitk_loss_fwd_bwd(cls_logits.data_ptr(), _p(dist_logits), _p(teacher_logits), labels.data_ptr(),
+                                        out.data_ptr(), dcls.data_ptr(), _p(ddist), B, Cc, mode, w_cls, w_dist, T,
+                                        label_smoothing, grad_div, _stream()), "loss_fwd_bwd")
+    return out, dcls, ddist
+
+
+# --------------------------------------------------------------------------- optimizer
+def grad_sqnorm(grads, state):
+    check(_lib.load().vitk_grad_sqnorm(grads.data_ptr(), grads.numel(), state.data_ptr(), _stream()), "grad_sqnorm")
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, chunk_off, chunk_len, chunk_lr_scale, chunk_wd, state,
+               beta1: float, beta2: float, eps: float, max_grad_norm: float):
+    check(_lib.load().vitk_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                      _p(params_bf16), chunk_off.data_ptr(), chunk_len.data_ptr(), chunk_lr_scale.data_ptr(),
+                                      chunk_wd.data_ptr(), chunk_off.numel(), state.data_ptr(), beta1, beta2, eps,
+                                      max_grad_norm, _stream()), "adamw_step")
+
+
+# --------------------------------------------------------------------------- helpers
+def cast_bf16(src, dst=None):
+    _req(src, f32, "cast src")
+    dst = torch.empty(src.shape, dtype=bf16, device=src.device) if dst is None else dst
+    check(_lib.load().vitk_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast")
+    return dst
+
+
+def colsum_bf16(x, out):
+    _req(x, bf16, "colsum x")
+    dim = x.shape[-1]
+    check(_lib.load().vitk_colsum_bf16(x.data_ptr(), out.data_ptr(), x.numel() // dim, dim, _stream()), "colsum")
+    return out
+
+
+def ensemble_probs(logits, weights):
+    _req(logits, f32, "ensemble logits")
+    F, B, Cc = logits.shape
+    probs = torch.empty(B, Cc, dtype=f32, device=logits.device)
+    pred = torch.empty(B, dtype=torch.int64, device=logits.device)
+    check(_lib.load().vitk_ensemble_probs(logits.data_ptr(), weights.data_ptr(), probs.data_ptr(), pred.data_ptr(), F, B, Cc,
+                                          _stream()), "ensemble_probs")
+    return probs, pred
+
+
+def attention_rollout(probs, fusion: str = "mean"):
+    _req(probs, f32, "rollout probs")
+    L, B, H, N, _ = probs.shape
+    fus = {"mean": 0, "max": 1, "min": 2}[fusion]
+    out = torch.empty(B, N, N, dtype=f32, device=probs.device)
+    scratch = torch.empty(2, B, N, N, dtype=f32, device=probs.device)
+    check(_lib.load().vitk_attention_rollout(probs.data_ptr(), out.data_ptr(), scratch.data_ptr(), L, B, H, N, fus, _stream()),
+          "attention_rollout")
+    return out
