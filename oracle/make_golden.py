@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/* by running the REFERENCE's own classes
+(imported unmodified from /root/reference via oracle/ref_loader.py) on seeded inputs.
+
+Run in the authoring container only:   python oracle/make_golden.py
+The fixtures it writes are committed; the GPU box never sees /root/reference.
+
+Fixtures
+  small_deit.pt / small_vit.pt   tiny configs (DeiT: embed 64, 1 head, depth 2; ViT: embed 128, 2 heads, depth 1; 64x64 image): inputs are
+                                 regenerated from seeds; stored = logits, loss, FULL gradients, parameters
+                                 after one clip+AdamW step, eval-mode logits, attention maps of layer 0.
+  deit_tiny_b4.pt / vit_base_b2.pt  full-size models: logits, loss, per-parameter gradient norm and the
+                                 gradient's projection on a seeded random direction (compact but sensitive).
+  param_groups_deit_tiny.json    get_parameter_groups() table (name, weight_decay, lr_scale) + named_parameters order.
+  distill_loss.pt                DistillationLoss / training_step arithmetic on random logits.
+  kfold_splits_7.json            the reference's committed data/splits/split_fold_{1..7}.json (known-answer vectors).
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_loader, vit_oracle as O  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+SMALL_DEIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=64, depth=2, num_heads=1, distilled=True, is_deit=True)
+SMALL_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=1, embed_dim=128, depth=1, num_heads=2, distilled=False, is_deit=False)
+
+
+def build_reference(cfg: O.VitConfig, seed: int):
+    base, vitm, deit = ref_loader.load()
+    kw = dict(img_size=cfg.img_size, patch_size=cfg.patch_size, in_chans=cfg.in_chans, num_classes=cfg.num_classes,
+              embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio)
+    if cfg.is_deit:
+        model = deit.DeiT(distilled=cfg.distilled, **kw)
+    else:
+        model = vitm.VisionTransformer(drop_path_rate=0.0, **kw)
+    sd = O.seeded_state_dict(cfg, seed)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return model
+
+
+def direction(name_idx: int, shape, seed: int = 1234):
+    g = torch.Generator().manual_seed(seed * 7 + name_idx)
+    return torch.randn(shape, generator=g)
+
+
+def run_case(cfg: O.VitConfig, batch: int, seed: int, full: bool):
+    torch.manual_seed(0)
+    model = build_reference(cfg, seed)
+    x, y = O.seeded_batch(cfg, batch, seed)
+    model.train()
+    out = model(x)
+    if isinstance(out, tuple):
+        loss = 0.5 * F.cross_entropy(out[0], y) + 0.5 * F.cross_entropy(out[1], y)   # lightning_modules.py:459-461
+        logits = [o.detach().clone() for o in out]
+    else:
+        loss = F.cross_entropy(out, y)
+        logits = [out.detach().clone()]
+    loss.backward()
+    names = [n for n, _ in model.named_parameters()]
+    rec = {"config": cfg.__dict__, "batch": batch, "seed": seed, "loss": loss.item(), "logits": logits,
+           "param_names": names}
+    grads = {n: (p.grad.detach().clone() if p.grad is not None else None) for n, p in model.named_parameters()}
+    rec["no_grad_params"] = [n for n, g in grads.items() if g is None]
+    rec["grad_norm"] = {n: g.norm().item() for n, g in grads.items() if g is not None}
+    rec["grad_proj"] = {n: (g * direction(i, g.shape)).sum().item() for i, (n, g) in enumerate(grads.items()) if g is not None}
+    if full:
+        rec["grads"] = {n: g for n, g in grads.items() if g is not None}
+        model.eval()                                                                       # eval path BEFORE the update
+        with torch.no_grad():
+            rec["eval_logits"] = model(x).detach().clone()
+        rec["attn_layer0"] = model.blocks[0].attn.attention_maps.clone()                   # vision_transformer_base.py:187-188
+        model.train()
+        # one optimizer step exactly as Lightning would run it: clip_grad_norm_(1.0) then AdamW
+        params = [p for p in model.parameters() if p.grad is not None]
+        groups_tbl = model.get_parameter_groups(weight_decay=0.05)
+        for gdict in groups_tbl:
+            gdict["lr"] = 1e-3 * gdict.get("lr_scale", 1.0)                                # lightning_modules.py:1101-1103
+        groups_tbl = [g for g in groups_tbl if g["params"][0].grad is not None]
+        opt = torch.optim.AdamW(groups_tbl, betas=(0.9, 0.999), weight_decay=0.05)           # :1108-1113
+        total_norm = torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        rec["total_grad_norm"] = total_norm.item()
+        rec["params_after_step"] = {n: p.detach().clone() for n, p in model.named_parameters()}
+    return rec
+
+
+def main():
+    assert ref_loader.available(), "run this where /root/reference is mounted"
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    torch.save(run_case(SMALL_DEIT, 3, 42, True), GOLD / "small_deit.pt")
+    torch.save(run_case(SMALL_VIT, 2, 43, True), GOLD / "small_vit.pt")
+    torch.save(run_case(O.DEIT_TINY, 4, 42, False), GOLD / "deit_tiny_b4.pt")
+    torch.save(run_case(O.VIT_BASE, 2, 42, False), GOLD / "vit_base_b2.pt")
+
+    # parameter-group table of the real DeiT-tiny (incl. the substring quirk)
+    model = build_reference(O.DEIT_TINY, 42)
+    tbl = [{"name": g["name"], "weight_decay": g["weight_decay"], "lr_scale": g["lr_scale"]}
+           for g in model.get_parameter_groups(weight_decay=0.05, layer_decay=0.75)]
+    (GOLD / "param_groups_deit_tiny.json").write_text(json.dumps(
+        {"named_parameters": [n for n, _ in model.named_parameters()], "groups": tbl,
+         "num_params": sum(p.numel() for p in model.parameters())}, indent=0))
+
+    # DistillationLoss on random logits (deit_models.py:461-480)
+    _, _, deit = ref_loader.load()
+    g = torch.Generator().manual_seed(7)
+    c, d, t = (torch.randn(16, 2, generator=g) for _ in range(3))
+    yy = torch.randint(0, 2, (16,), generator=g)
+    recs = {"cls": c, "dist": d, "teacher": t * 2, "labels": yy, "cases": []}
+    for kind in ("soft", "hard"):
+        for ls in (0.0, 0.1):
+            crit = deit.DistillationLoss(base_criterion=torch.nn.CrossEntropyLoss(label_smoothing=ls), distillation_type=kind,
+                                         alpha=0.7, tau=3.0)
+            recs["cases"].append({"type": kind, "label_smoothing": ls, "alpha": 0.7, "tau": 3.0,
+                                  "loss": crit((c, d), yy, t * 2).item()})
+    torch.save(recs, GOLD / "distill_loss.pt")
+
+    # fold known-answer vectors
+    folds = [json.loads((ref_loader.REF_ROOT / f"data/splits/split_fold_{i}.json").read_text()) for i in range(1, 8)]
+    (GOLD / "kfold_splits_7.json").write_text(json.dumps(
+        {"source": "reference data/splits/split_fold_{1..7}.json", "n": 450, "labels": "225 x 0 then 225 x 1",
+         "folds": [{k: f[k] for k in ("train", "val", "test")} for f in folds]}))
+    for f in sorted(GOLD.iterdir()):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+"""Pins the oracle (oracle/vit_oracle.py, the CPU restatement the CUDA path is judged against):
+  * against the committed golden fixtures generated from the reference's own classes
+    (oracle/make_golden.py), always;
+  * against the reference classes imported live from /root/reference, when that tree is mounted.
+CPU only."""
+import json
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import ref_loader, vit_oracle as O  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+
+def _cfg(d):
+    return O.VitConfig(**d)
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+@pytest.mark.parametrize("name", ["small_deit", "small_vit"])
+def test_oracle_matches_golden_small_full_gradients(name):
+    rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    cfg = _cfg(rec["config"])
+    p = O.seeded_state_dict(cfg, rec["seed"])
+    assert list(O.param_shapes(cfg)) == rec["param_names"]          # named_parameters() order of the reference
+    x, y = O.seeded_batch(cfg, rec["batch"], rec["seed"])
+    loss, out, grads = O.train_step(p, x, y, cfg)
+    outs = out if isinstance(out, tuple) else (out,)
+    for o, ref in zip(outs, rec["logits"]):
+        assert (o.detach() - ref).abs().max().item() < 1e-5
+    assert abs(loss.item() - rec["loss"]) < 1e-6
+    assert sorted(n for n, g in grads.items() if g is None) == sorted(rec["no_grad_params"])
+    for n, gref in rec["grads"].items():
+        assert _rel(grads[n], gref) < 1e-4, n
+    # one clip(1.0)+AdamW step with the reference's own parameter-group table
+    tbl = O.parameter_groups(list(p), cfg.depth, weight_decay=0.05)
+    wd = {g["name"]: g["weight_decay"] for g in tbl}
+    sc = {g["name"]: g["lr_scale"] for g in tbl}
+    params = {k: v.clone() for k, v in p.items()}
+    total = O.clip_and_adamw_step(params, grads, {}, lr=1e-3, weight_decay=wd, lr_scale=sc, max_grad_norm=1.0)
+    assert abs(total - rec["total_grad_norm"]) / rec["total_grad_norm"] < 1e-5
+    for n, pref in rec["params_after_step"].items():
+        assert (params[n] - pref).abs().max().item() < 2e-6, n
+    # eval path + attention maps
+    attn = []
+    ev = O.forward(p, x, cfg, training=False, attn_out=attn)
+    assert (ev - rec["eval_logits"]).abs().max().item() < 1e-5
+    assert (attn[0] - rec["attn_layer0"]).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("name,batch", [("deit_tiny_b4", 4), ("vit_base_b2", 2)])
+def test_oracle_matches_golden_full_size(name, batch):
+    rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    cfg = _cfg(rec["config"])
+    torch.set_num_threads(8)
+    p = O.seeded_state_dict(cfg, rec["seed"])
+    x, y = O.seeded_batch(cfg, batch, rec["seed"])
+    loss, out, grads = O.train_step(p, x, y, cfg)
+    outs = out if isinstance(out, tuple) else (out,)
+    for o, ref in zip(outs, rec["logits"]):
+        assert (o.detach() - ref).abs().max().item() < 2e-5
+    assert abs(loss.item() - rec["loss"]) < 1e-5
+    from oracle.make_golden import direction
+    for i, n in enumerate(rec["param_names"]):
+        if n in rec["no_grad_params"]:
+            assert grads[n] is None
+            continue
+        assert abs(grads[n].norm().item() - rec["grad_norm"][n]) <= 1e-3 * rec["grad_norm"][n] + 1e-9, n
+        proj = (grads[n] * direction(i, grads[n].shape)).sum().item()
+        assert abs(proj - rec["grad_proj"][n]) <= 2e-3 * rec["grad_norm"][n] * grads[n].numel() ** 0.5 + 1e-9, n
+
+
+def test_param_group_table_and_count():
+    rec = json.loads((GOLD / "param_groups_deit_tiny.json").read_text())
+    names = list(O.param_shapes(O.DEIT_TINY))
+    assert names == rec["named_parameters"]
+    assert sum(torch.Size(s).numel() for s in O.param_shapes(O.DEIT_TINY).values()) == rec["num_params"] == 5526501
+    tbl = O.parameter_groups(names, 12, weight_decay=0.05, layer_decay=0.75)
+    assert len(tbl) == len(rec["groups"])
+    for a, b in zip(tbl, rec["groups"]):
+        assert a["name"] == b["name"] and a["weight_decay"] == b["weight_decay"] and abs(a["lr_scale"] - b["lr_scale"]) < 1e-12
+    # the documented quirk: blocks.10 / blocks.11 inherit blocks.1's scale
+    sc = {g["name"]: g["lr_scale"] for g in tbl}
+    assert sc["blocks.11.mlp.fc2.weight"] == sc["blocks.1.mlp.fc2.weight"] == 0.75 ** 10
+
+
+def test_distillation_loss_golden():
+    rec = torch.load(GOLD / "distill_loss.pt", weights_only=False)
+    for c in rec["cases"]:
+        total, _, _ = O.distillation_loss((rec["cls"], rec["dist"]), rec["labels"], rec["teacher"], alpha=c["alpha"],
+                                          temperature=c["tau"], distillation_type=c["type"], label_smoothing=c["label_smoothing"])
+        assert abs(total.item() - c["loss"]) < 1e-6, c
+
+
+def test_kfold_known_answer():
+    rec = json.loads((GOLD / "kfold_splits_7.json").read_text())
+    labels = [0] * 225 + [1] * 225
+    got = O.kfold_splits(labels, k=7, seed=42)
+    assert got == rec["folds"]
+    # 5-fold variant (BASELINE.json config 5): partition + stratification properties
+    five = O.kfold_splits(labels, k=5, seed=42)
+    for f in five:
+        assert sorted(f["train"] + f["val"] + f["test"]) == list(range(450))
+        assert abs(sum(labels[i] for i in f["test"]) - len(f["test"]) / 2) <= 1
+
+
+def test_ensemble_and_rollout_properties():
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(5, 11, 2, generator=g)
+    probs, pred = O.ensemble_predict(logits, torch.full((5,), 0.2))
+    assert torch.allclose(probs.sum(1), torch.ones(11), atol=1e-6) and torch.equal(pred, probs.argmax(1))
+    maps = torch.randn(3, 2, 3, 10, 10, generator=g).softmax(-1)
+    for fusion in ("mean", "max", "min"):
+        r = O.attention_rollout(maps, fusion)
+        assert torch.allclose(r.sum(-1), torch.ones(2, 10), atol=1e-5)   # product of row-stochastic matrices
+    ident = torch.eye(10).expand(3, 2, 3, 10, 10)
+    assert torch.allclose(O.attention_rollout(ident), torch.eye(10).expand(2, 10, 10))
+    assert O.progressive_alpha(0.7, {0: 0.1, 5: 0.5}, 3) == 0.1 and O.progressive_alpha(0.7, None, 3) == 0.7
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_oracle_vs_live_reference_default_init():
+    """Reference's own random init (seed 42), ViT factory path, 1-channel 64px input."""
+    base, vitm, deit = ref_loader.load()
+    torch.manual_seed(42)
+    model = deit.create_deit_tiny(img_size=64, in_chans=1, distilled=True)
+    cfg = O.VitConfig(img_size=64, in_chans=1)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x = torch.rand(2, 1, 64, 64)
+    model.train()
+    c_ref, d_ref = model(x)
+    c, d = O.forward(p, x, cfg, training=True)
+    assert (c - c_ref).abs().max().item() < 1e-6 and (d - d_ref).abs().max().item() < 1e-6
+    model.eval()
+    assert (O.forward(p, x, cfg, training=False) - model(x)).abs().max().item() < 1e-6
+    with pytest.raises(AssertionError):
+        O.forward(p, torch.rand(1, 1, 32, 32), cfg)                 # tests/test_vit_models.py:401-412
+    torch.manual_seed(42)
+    vit = vitm.create_vit_tiny(img_size=64, in_chans=1, drop_path_rate=0.0)
+    cfgv = O.VitConfig(img_size=64, in_chans=1, distilled=False, is_deit=False)
+    pv = {k: v.detach().clone() for k, v in vit.state_dict().items()}
+    vit.train()
+    assert (O.forward(pv, x, cfgv) - vit(x)).abs().max().item() < 1e-6
+    assert list(O.param_shapes(cfgv)) == [n for n, _ in vit.named_parameters()]
