@@ -1,0 +1,207 @@
+"""End-to-end parity of the B200 path against the oracle (oracle/vit_oracle.py) and the committed
+golden fixtures, through the public model classes (which call libvitk.so through the C-ABI).
+
+Tolerances are BASELINE.json's: logits <= 2e-3 max-abs, per-parameter gradients <= 1e-2 relative L2,
+identical top-1 predictions."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import thyroid_vit_cnn_comparison_b200 as tv  # noqa: E402
+from thyroid_vit_cnn_comparison_b200 import vit as V, training as TR, optim as OPT  # noqa: E402
+from oracle import vit_oracle as O  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+LOGIT_TOL = 2e-3
+GRAD_TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def build(cfg: O.VitConfig, seed: int):
+    kw = dict(img_size=cfg.img_size, patch_size=cfg.patch_size, in_chans=cfg.in_chans, num_classes=cfg.num_classes,
+              embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio)
+    m = V.DeiT(distilled=cfg.distilled, **kw) if cfg.is_deit else V.VisionTransformer(drop_path_rate=0.0, **kw)
+    sd = O.seeded_state_dict(cfg, seed)
+    m.load_state_dict(sd, strict=True)          # state_dict keys are the reference's
+    return m.cuda(), sd
+
+
+def run_gpu(model, x, y):
+    model.train()
+    model.zero_grad()
+    out = model(x.cuda())
+    loss, _ = TR.fused_cross_entropy(out, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {n: (p.grad.detach().cpu().clone() if p.grad is not None else None) for n, p in model.named_parameters()}
+    outs = out if isinstance(out, tuple) else (out,)
+    return loss.item(), [o.detach().cpu() for o in outs], grads
+
+
+@pytest.mark.parametrize("name", ["small_deit", "small_vit"])
+def test_small_models_vs_golden(name):
+    rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    cfg = O.VitConfig(**rec["config"])
+    model, _ = build(cfg, rec["seed"])
+    assert [n for n, _ in model.named_parameters()] == rec["param_names"]
+    x, y = O.seeded_batch(cfg, rec["batch"], rec["seed"])
+    loss, outs, grads = run_gpu(model, x, y)
+    for o, ref in zip(outs, rec["logits"]):
+        assert (o - ref).abs().max().item() < LOGIT_TOL
+    assert abs(loss - rec["loss"]) < 2e-3
+    for n in rec["no_grad_params"]:
+        assert grads[n] is None                         # quality_score never receives a gradient (reference behaviour)
+    for n, gref in rec["grads"].items():
+        assert rel_l2(grads[n], gref) < GRAD_TOL, (n, rel_l2(grads[n], gref))
+    model.eval()
+    with torch.no_grad():
+        ev = model(x.cuda())
+    assert (ev.cpu() - rec["eval_logits"]).abs().max().item() < LOGIT_TOL
+    maps = model.blocks[0].attn.attention_maps
+    assert maps.shape == rec["attn_layer0"].shape and not maps.is_cuda
+    assert (maps - rec["attn_layer0"]).abs().max().item() < 5e-3
+    assert (maps.sum(-1) - 1).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("cfg,batch,gold", [(O.DEIT_TINY, 32, None), (O.DEIT_TINY, 4, "deit_tiny_b4"), (O.VIT_BASE, 2, "vit_base_b2")])
+def test_full_size_vs_oracle(cfg, batch, gold):
+    """Config 1 of BASELINE.json (DeiT-tiny, B=32, 224x224 synthetic tiles) and ViT-B/16, against the CPU oracle."""
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    model, sd = build(cfg, 42)
+    x, y = O.seeded_batch(cfg, batch, 42)
+    loss, outs, grads = run_gpu(model, x, y)
+    ref_loss, ref_out, ref_grads = O.train_step(sd, x, y, cfg)
+    ref_outs = ref_out if isinstance(ref_out, tuple) else (ref_out,)
+    for o, ref in zip(outs, ref_outs):
+        assert (o - ref.detach()).abs().max().item() < LOGIT_TOL
+        assert torch.equal(o.argmax(1), ref.detach().argmax(1))      # bit-identical top-1
+    assert abs(loss - ref_loss.item()) < 2e-3
+    worst = max((rel_l2(grads[n], g), n) for n, g in ref_grads.items() if g is not None)
+    assert worst[0] < GRAD_TOL, worst
+    if gold is not None:
+        rec = torch.load(GOLD / f"{gold}.pt", weights_only=False)
+        for o, ref in zip(outs, rec["logits"]):
+            assert (o - ref).abs().max().item() < LOGIT_TOL
+
+
+def _groups(model, base_lr, wd):
+    groups = model.get_parameter_groups(weight_decay=wd)
+    for g in groups:
+        g["lr"] = base_lr * g.get("lr_scale", 1.0)
+    return groups
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_matches_oracle_adamw(use_graph):
+    """TrainStep (fwd + fused loss + bwd + clip(1.0) + AdamW) for 3 steps vs oracle autograd + clip_and_adamw_step."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2)
+    model, sd = build(cfg, 7)
+    model.train()
+    opt = OPT.FusedAdamW(model, _groups(model, 1e-3, 0.05), lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+    step = TR.TrainStep(model, opt, 8, mode="ce", use_graph=use_graph)
+    names = list(O.param_shapes(cfg))
+    tbl = O.parameter_groups(names, cfg.depth, weight_decay=0.05)
+    wd = {g["name"]: g["weight_decay"] for g in tbl}
+    sc = {g["name"]: g["lr_scale"] for g in tbl}
+    params = {k: v.clone() for k, v in sd.items()}
+    state = {}
+    for it in range(3):
+        x, y = O.seeded_batch(cfg, 8, 100 + it)
+        stats = step(x.pin_memory(), y.pin_memory()).cpu()
+        ref_loss, _, ref_grads = O.train_step(params, x, y, cfg)
+        O.clip_and_adamw_step(params, ref_grads, state, lr=1e-3, weight_decay=wd, lr_scale=sc, max_grad_norm=1.0)
+        assert abs(stats[0].item() - ref_loss.item()) < 3e-3, (it, stats[0].item(), ref_loss.item())
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        if "quality_score" in n:
+            continue
+        # after 3 Adam steps of lr 1e-3 every weight moved by <= ~3e-3; compare the UPDATE, not the weight
+        upd, ref_upd = p.detach().cpu() - sd[n], params[n] - sd[n]
+        assert rel_l2(upd, ref_upd) < 5e-2, (n, rel_l2(upd, ref_upd))
+
+
+def test_distillation_step_matches_oracle():
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=2, num_heads=1)
+    model, sd = build(cfg, 11)
+    model.train()
+    x, y = O.seeded_batch(cfg, 6, 5)
+    teacher_logits = torch.randn(6, 2, generator=torch.Generator().manual_seed(3)) * 2
+    model.zero_grad()
+    out = model(x.cuda())
+    total, st = TR.fused_distillation_loss(out, y.cuda(), teacher_logits.cuda(), alpha=0.7, temperature=3.0)
+    total.backward()
+    torch.cuda.synchronize()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_total, ref_c, ref_d = O.distillation_loss(O.forward(leaves, x, cfg), y, teacher_logits, 0.7, 3.0, "soft")
+    ref_total.backward()
+    assert abs(total.item() - ref_total.item()) < 3e-3
+    assert abs(st["class_loss"].item() - ref_c.item()) < 3e-3 and abs(st["distill_loss"].item() - ref_d.item()) < 3e-3
+    for n, p in model.named_parameters():
+        if leaves[n].grad is None:
+            continue
+        assert rel_l2(p.grad, leaves[n].grad) < GRAD_TOL, n
+
+
+def test_gradient_accumulation_and_torch_optimizer_interop():
+    """reference tests/test_vit_models.py:450-478 (grad accumulation over micro-batches) + a stock torch optimizer."""
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=1, num_heads=1)
+    model, sd = build(cfg, 3)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    opt.zero_grad()
+    xs = [O.seeded_batch(cfg, 2, 20 + i) for i in range(3)]
+    for x, y in xs:
+        loss, _ = TR.fused_cross_entropy(model(x.cuda()), y.cuda())
+        (loss / 3).backward()
+    g_acc = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters() if p.grad is not None}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    for x, y in xs:
+        (O.classification_loss(O.forward(leaves, x, cfg), y) / 3).backward()
+    for n, g in g_acc.items():
+        assert rel_l2(g, leaves[n].grad) < GRAD_TOL, n
+        assert torch.isfinite(g).all() and g.abs().sum() > 0            # tests/test_vit_models.py:430-448
+    before = model.head.weight.detach().clone()
+    opt.step()
+    opt.zero_grad()                                                     # set_to_none=True: next backward must start from zero
+    assert not torch.equal(before, model.head.weight.detach())
+    x, y = xs[0]
+    loss, _ = TR.fused_cross_entropy(model(x.cuda()), y.cuda())
+    loss.backward()
+    sd2 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    leaves2 = {k: v.clone().requires_grad_(True) for k, v in sd2.items()}
+    O.classification_loss(O.forward(leaves2, x, cfg), y).backward()
+    assert rel_l2(model.head.weight.grad, leaves2["head.weight"].grad) < GRAD_TOL
+
+
+def test_api_surface_and_errors():
+    m = V.create_deit_tiny(img_size=224, in_chans=3, distilled=True)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == 5526501                                             # SURVEY.md section 6 [probed]
+    assert m.embed_dim == 192 and len(m.blocks) == 12 and m.blocks[0].attn.num_heads == 3
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 224, 224))                                     # CPU tensor/model: no fallback, loud failure
+    m = m.cuda()
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 3, 256, 256, device="cuda"))                      # tests/test_vit_models.py:401-412
+    m.train()
+    out = m(torch.rand(2, 3, 224, 224, device="cuda"))
+    assert isinstance(out, tuple) and out[0].shape == (2, 2) and out[1].shape == (2, 2)
+    m.eval()
+    with torch.no_grad():
+        ev = m(torch.rand(2, 3, 224, 224, device="cuda"))
+    assert ev.shape == (2, 2)
+    assert m.get_attention_maps().shape == (12, 2, 3, 198, 198)
+    with pytest.raises(ValueError):
+        V.get_vit_model("vit_invalid")
+    vb = V.get_vit_model("vit_base", img_size=224, in_chans=3, drop_path_rate=0.0)
+    assert abs(sum(p.numel() for p in vb.parameters()) - 86e6) < 2e6

@@ -1,0 +1,303 @@
+"""Host-side engine of the B200 ViT/DeiT path: owns the flat parameter / gradient buffers and the
+activation workspace, and sequences libvitk kernels for forward and backward.
+
+This is orchestration only -- every FLOP and every byte moved happens inside libvitk.so
+(include/vitk.h).  The kernel sequence restates, op for op, the reference's
+DeiT.forward / VisionTransformerBase.forward (deit_models.py:190-238,
+vision_transformer_base.py:120-143,174-195,217-223,282-285,440-486) and their autograd backward.
+
+Memory layout in HBM (per rank)
+  flat_params   fp32 [P]   all trainable tensors, each padded to 128 elements, in REVERSE execution order
+                            (heads, norm, blocks L-1..0, patch/pos/cls) so gradient buckets complete in order
+  flat_grads    fp32 [P]   same offsets; kernels ACCUMULATE into it (split-K red.add, column-sum atomics)
+  flat_bf16     bf16 [P]   tensor-core shadow of flat_params (written by the AdamW kernel / cast kernel)
+  residual x    fp32 [B*T, D] per block boundary (2L+1 buffers, saved for backward)
+  activations   bf16: LN outputs, qkv [B,T,3,H,64], attention out [B,T,H,64], fc1 pre/post GELU [B*T, 4D]
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+
+PAD = 128  # every tensor starts on a 128-element boundary (512 B fp32 / 256 B bf16: TMA + 128-bit safe)
+
+
+@dataclass
+class Dims:
+    img: int
+    patch: int
+    chans: int
+    dim: int
+    depth: int
+    heads: int
+    hidden: int
+    classes: int
+    n_prefix: int      # 1 (cls) or 2 (cls + dist)
+    n_out: int         # number of classification heads (2 for a distilled DeiT)
+
+    @property
+    def n_patches(self) -> int:
+        return (self.img // self.patch) ** 2
+
+    @property
+    def tokens(self) -> int:
+        return self.n_patches + self.n_prefix
+
+    @property
+    def kpatch(self) -> int:
+        return self.chans * self.patch * self.patch
+
+
+def execution_order(names: List[str], depth: int) -> List[str]:
+    """Reverse execution order: the order in which backward finishes each tensor's gradient."""
+    def key(n: str):
+        if n.startswith("head") or n.startswith("norm."):
+            return (0, 0)
+        if n.startswith("blocks."):
+            return (1, depth - 1 - int(n.split(".")[1]))
+        return (2, 0)
+    return sorted(names, key=lambda n: (key(n), names.index(n)))
+
+
+class FlatParams:
+    """One fp32 buffer for all trainable tensors + same-shape gradient and bf16 shadow buffers."""
+
+    def __init__(self, named: "OrderedDict[str, torch.Tensor]", depth: int, device):
+        order = execution_order(list(named), depth)
+        self.offsets: Dict[str, Tuple[int, torch.Size]] = {}
+        total = 0
+        for n in order:
+            self.offsets[n] = (total, named[n].shape)
+            total += (named[n].numel() + PAD - 1) // PAD * PAD
+        self.numel = total
+        self.order = order
+        self.params = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=device)
+        self.bf16 = torch.zeros(total, dtype=torch.bfloat16, device=device)
+        self._shadow_version = -1
+        for n in order:
+            self.view(self.params, n).copy_(named[n].detach().to(device=device, dtype=torch.float32))
+
+    def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        return buf[off:off + shape.numel()].view(shape)
+
+    def refresh_shadow(self) -> None:
+        """flat_params -> bf16 shadow (one vectorised cast kernel over the whole buffer)."""
+        ops.cast_bf16(self.params, self.bf16)
+
+    def bucket_slices(self, bucket_bytes: int) -> List[Tuple[int, int]]:
+        """Contiguous [start, end) element ranges of ~bucket_bytes, cut at tensor boundaries, in
+        gradient-completion order (used by the data-parallel all-reduce)."""
+        out, start, cur = [], 0, 0
+        for n in self.order:
+            off, shape = self.offsets[n]
+            end = off + (shape.numel() + PAD - 1) // PAD * PAD
+            cur = end
+            if (cur - start) * 4 >= bucket_bytes:
+                out.append((start, cur))
+                start = cur
+        if cur > start:
+            out.append((start, cur))
+        return out
+
+
+class Workspace:
+    """Activation + scratch buffers for one (batch, training?) shape; allocated once, reused every step."""
+
+    def __init__(self, d: Dims, B: int, train: bool, device):
+        self.B, self.train = B, train
+        T, D, H = d.tokens, d.dim, d.heads
+        M = B * T
+        f32, b16 = torch.float32, torch.bfloat16
+        e = lambda *s, dt=b16: torch.empty(*s, dtype=dt, device=device)
+        L = d.depth if train else 1
+        self.patches = e(B * d.n_patches, d.kpatch)
+        nres = 2 * d.depth + 1 if train else 3
+        self.x = [e(M, D, dt=f32) for _ in range(nres)]
+        self.xn1 = [e(M, D) for _ in range(L)]
+        self.xn2 = [e(M, D) for _ in range(L)]
+        self.stats = [e(4, M, dt=f32) for _ in range(L)]          # mean1, rstd1, mean2, rstd2
+        self.qkv = [e(M, 3 * D) for _ in range(L)]
+        self.ao = [e(M, D) for _ in range(L)]
+        self.lse = [e(B, H, T, dt=f32) for _ in range(L)]
+        self.pre = [e(M, d.hidden) for _ in range(L)]
+        self.act = [e(M, d.hidden) for _ in range(L)]
+        if train:
+            self.dx = [e(M, D, dt=f32) for _ in range(2)]
+            self.dxb = e(M, D)
+            self.dxn = e(M, D)
+            self.d_ao = e(M, D)
+            self.d_pre = e(M, d.hidden)
+            self.dqkv = e(M, 3 * D)
+            self.delta = e(B, H, T, dt=f32)
+            self.dpatch = e(B * d.n_patches, D)
+        self.head_saved = None
+
+
+class VitEngine:
+    """Forward / backward of the whole encoder for one model instance."""
+
+    def __init__(self, dims: Dims, named_params: "OrderedDict[str, torch.Tensor]", device):
+        if dims.dim % dims.heads != 0 or dims.dim // dims.heads != 64:
+            raise NotImplementedError(
+                f"libvitk attention kernels cover head_dim 64 (got dim={dims.dim}, heads={dims.heads}); "
+                "every ViT/DeiT tiny/small/base variant of the reference satisfies this")
+        if dims.dim % 8 or dims.hidden % 8 or dims.kpatch % 8 or dims.patch % 8:
+            raise NotImplementedError("embed_dim, mlp hidden and patch size must be multiples of 8")
+        _lib.load()
+        self.d = dims
+        self.device = torch.device(device)
+        self.flat = FlatParams(named_params, dims.depth, self.device)
+        self.flat.refresh_shadow()
+        self._ws: Dict[Tuple[int, bool], Workspace] = {}
+        self.scale = 64 ** -0.5
+        self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.grad_ready_hook = None   # callable(name_prefix) used by the data-parallel bucket launcher
+
+    # ------------------------------------------------------------------ helpers
+    def w(self, name: str) -> torch.Tensor:      # bf16 shadow view
+        return self.flat.view(self.flat.bf16, name)
+
+    def p(self, name: str) -> torch.Tensor:      # fp32 master view
+        return self.flat.view(self.flat.params, name)
+
+    def g(self, name: str) -> torch.Tensor:      # fp32 gradient view
+        return self.flat.view(self.flat.grads, name)
+
+    def workspace(self, B: int, train: bool) -> Workspace:
+        key = (B, train)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = Workspace(self.d, B, train, self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _split_k(self, m_out: int, n_out: int, k: int) -> int:
+        bn = 256 if n_out % 256 == 0 else 192 if n_out % 192 == 0 else 128 if n_out % 128 == 0 else 64
+        tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
+        nkb = (k + 63) // 64
+        return max(1, min(max(1, nkb // 2), (2 * self.sms + tiles - 1) // tiles))
+
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, rows: int) -> None:
+        """grad[wname][N_out, K_in] += dy[rows, N_out]^T @ x[rows, K_in] (both operands read MN-major)."""
+        gw = self.g(wname)
+        n_out = gw.shape[0]
+        k_in = gw.numel() // n_out
+        ops.gemm(dy, x, n_out, k_in, rows, a_mn=True, b_mn=True, out=gw, epilogue=_lib.EPI_ATOMIC_ADD,
+                 split_k=self._split_k(n_out, k_in, rows))
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, images: torch.Tensor, train: bool, attn_probs: Optional[List[torch.Tensor]] = None):
+        d = self.d
+        if images.dim() != 4 or images.shape[1] != d.chans:
+            raise ValueError(f"expected images [B,{d.chans},H,W], got {tuple(images.shape)}")
+        B = images.shape[0]
+        T, D = d.tokens, d.dim
+        M = B * T
+        ws = self.workspace(B, train)
+        images = images.contiguous()
+        if images.dtype != torch.float32:
+            images = images.float()
+        ops.patchify(images, d.patch, out=ws.patches)
+        x0 = ws.x[0]
+        ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
+                 bias=self.p("patch_embed.proj.bias"), epilogue=_lib.EPI_TOKENS,
+                 tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"))
+        ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token"),
+                              self.p("dist_token") if d.n_prefix == 2 else None, self.p("pos_embed"), d.n_prefix)
+        for l in range(d.depth):
+            s = l if train else 0
+            pre = f"blocks.{l}."
+            if train:
+                x_in, x_mid, x_out = ws.x[2 * l], ws.x[2 * l + 1], ws.x[2 * l + 2]
+            else:
+                x_in, x_mid, x_out = ws.x[(2 * l) % 3], ws.x[(2 * l + 1) % 3], ws.x[(2 * l + 2) % 3]
+            st = ws.stats[s]
+            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), y=ws.xn1[s], mean=st[0], rstd=st[1])
+            ops.gemm(ws.xn1[s], self.w(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
+            probs = None
+            if attn_probs is not None:
+                probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
+                attn_probs.append(probs)
+            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
+            ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
+            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
+            ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.pre[s], out2=ws.act[s],
+                     bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
+            ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
+        x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
+        two = d.n_out == 2
+        l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
+                                          self.p("head.weight"), self.p("head.bias"),
+                                          self.p("head_dist.weight") if two else None,
+                                          self.p("head_dist.bias") if two else None, d.n_out)
+        if train:
+            ws.head_saved = (xhat, rstd)
+        return l0, l1
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, B: int, dl0: torch.Tensor, dl1: Optional[torch.Tensor]) -> None:
+        """Accumulates every parameter gradient into flat.grads (input gradient is not produced)."""
+        d = self.d
+        T, D = d.tokens, d.dim
+        M = B * T
+        ws = self.workspace(B, True)
+        if ws.head_saved is None:
+            raise RuntimeError("backward() called without a preceding training forward()")
+        xhat, rstd = ws.head_saved
+        ws.head_saved = None
+        two = d.n_out == 2
+        dx, dx_alt = ws.dx[0], ws.dx[1]
+        last_fc2_bias = self.g(f"blocks.{d.depth - 1}.mlp.fc2.bias")
+        ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),
+                     self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dxb,
+                     self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
+                     self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
+                     last_fc2_bias, T, d.n_out)
+        self._notify("head")
+        for l in range(d.depth - 1, -1, -1):
+            pre = f"blocks.{l}."
+            st = ws.stats[l]
+            x_in, x_mid = ws.x[2 * l], ws.x[2 * l + 1]
+            # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
+            self._wgrad(ws.dxb, ws.act[l], pre + "mlp.fc2.weight", M)
+            ops.gemm(ws.dxb, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.pre[l],
+                     epilogue=_lib.EPI_DGELU)
+            ops.colsum_bf16(ws.d_pre, self.g(pre + "mlp.fc1.bias"))
+            self._wgrad(ws.d_pre, ws.xn2[l], pre + "mlp.fc1.weight", M)
+            ops.gemm(ws.d_pre, self.w(pre + "mlp.fc1.weight"), M, D, d.hidden, b_mn=True, out=ws.dxn)
+            ops.layernorm_bwd(ws.dxn, x_mid, st[2], st[3], self.p(pre + "norm2.weight"), self.g(pre + "norm2.weight"),
+                              self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx_bf16=ws.dxb,
+                              dcolsum=self.g(pre + "attn.proj.bias"))
+            dx, dx_alt = dx_alt, dx
+            # ---- attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
+            self._wgrad(ws.dxb, ws.ao[l], pre + "attn.proj.weight", M)
+            ops.gemm(ws.dxb, self.w(pre + "attn.proj.weight"), M, D, D, b_mn=True, out=ws.d_ao)
+            ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
+            ops.colsum_bf16(ws.dqkv, self.g(pre + "attn.qkv.bias"))
+            self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M)
+            ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
+            prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
+            ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),
+                              self.g(pre + "norm1.bias"), dres=dx, dx=dx_alt, dx_bf16=ws.dxb if l > 0 else None,
+                              dcolsum=prev_bias)
+            dx, dx_alt = dx_alt, dx
+            self._notify(pre)
+        ops.tokens_bwd(dx.view(B, T, D), self.g("pos_embed"), self.g("cls_token"),
+                       self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g("patch_embed.proj.bias"),
+                       d.n_prefix)
+        self._wgrad(ws.dpatch, ws.patches, "patch_embed.proj.weight", B * d.n_patches)
+        self._notify("embed")
+
+    def _notify(self, what: str) -> None:
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(what)
+
+    def zero_grad(self) -> None:
+        self.flat.grads.zero_()

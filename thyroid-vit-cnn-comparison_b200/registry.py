@@ -1,0 +1,148 @@
+"""ModelRegistry slot + wrapper classes -- the reference's drop-in boundary for models
+(src/models/registry.py:19-98, src/models/base.py:9-51, src/models/vit/{__init__,deit,vision_transformer}.py).
+
+`ModelRegistry` here has the reference's exact semantics (register decorator, create_model(config) ->
+cls(config=config), ValueError for unknown names).  `install_into(ref_registry)` registers the B200
+wrappers into the REFERENCE's own registry object (re-registration overwrites, registry.py:36-42), which is
+all it takes to make ThyroidViTModule / ThyroidDistillationModule of the reference build B200 models.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any
+
+import torch
+import torch.nn as nn
+
+from . import vit as V
+
+logger = logging.getLogger(__name__)
+
+
+class ModelRegistry:
+    _registry: dict = {}
+
+    @classmethod
+    def register(cls, names, model_type: str = "default"):
+        if not isinstance(names, list):
+            names = [names]
+
+        def decorator(model_class):
+            cls._registry.setdefault(model_type, {})
+            for name in names:
+                cls._registry[model_type][name] = model_class
+            return model_class
+        return decorator
+
+    @classmethod
+    def create_model(cls, config):
+        if not hasattr(config, "name"):
+            raise ValueError("Configuration for model creation must include a 'name' attribute.")
+        name = config.name
+        for _, models in cls._registry.items():
+            if name in models:
+                return models[name](config=config)
+        raise ValueError(f"Model '{name}' not found in registry. Available models: {cls.list_available_models()}")
+
+    @classmethod
+    def list_models(cls, model_type=None):
+        if model_type:
+            return list(cls._registry.get(model_type, {}).keys())
+        return [n for models in cls._registry.values() for n in models]
+
+    @classmethod
+    def list_available_models(cls):
+        return {t: list(m.keys()) for t, m in cls._registry.items()}
+
+
+class ModelBase(nn.Module):
+    """src/models/base.py:9-51."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = None
+
+    def _build_model(self):
+        raise NotImplementedError("Subclasses must implement _build_model.")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.model is None:
+            raise RuntimeError("The model has not been built yet. Ensure _build_model() is called in the subclass's "
+                               "__init__ and assigns to self.model.")
+        return self.model(x)
+
+
+def _get(cfg: Any, key: str, default=None):
+    if hasattr(cfg, "get"):
+        try:
+            v = cfg.get(key, default)
+            return default if v is None else v
+        except Exception:
+            pass
+    return getattr(cfg, key, default)
+
+
+def _common_kwargs(cfg) -> dict:
+    """Top-level keys the reference wrappers read (deit.py:26-32, vision_transformer.py:27-40) plus the YAML
+    `params:` block the hand-written constructors take (configs/model/vit/deit_tiny.yaml:11-33)."""
+    extra = _get(cfg, "extra_params", {}) or {}
+    in_chans = _get(extra, "in_chans", None) or _get(cfg, "in_channels", None) or _get(cfg, "channels", None) or 3
+    kw = dict(img_size=int(_get(cfg, "img_size", 224)), patch_size=int(_get(cfg, "patch_size", 16)),
+              in_chans=int(in_chans), num_classes=int(_get(cfg, "num_classes", 2)))
+    params = _get(cfg, "params", {}) or {}
+    for k in ("embed_dim", "depth", "num_heads", "mlp_ratio", "qkv_bias", "drop_rate", "attn_drop_rate", "drop_path_rate",
+              "distilled", "quality_aware", "store_attention"):
+        v = _get(params, k, None)
+        if v is not None:
+            kw[k] = v
+    return kw
+
+
+@ModelRegistry.register(["deit_tiny", "deit_small", "deit_base"], "vit")
+class DeiT(ModelBase):
+    """src/models/vit/deit.py:10-72.  The reference maps these names to timm's NON-distilled deit_*_patch16_224
+    (single logits tensor); `params.distilled: true` in the model YAML selects the hand-written distilled variant."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._build_model()
+
+    def _build_model(self):
+        name = self.config.name
+        factory = {"deit_tiny": V.create_deit_tiny, "deit_small": V.create_deit_small, "deit_base": V.create_deit_base}.get(name)
+        if factory is None:
+            raise ValueError(f"Unsupported DeiT model name: {name}")
+        kw = _common_kwargs(self.config)
+        kw.setdefault("distilled", False)
+        kw.setdefault("drop_path_rate", 0.0)
+        self.model = factory(pretrained=False, **kw)
+
+    def get_parameter_groups(self, *a, **k):
+        return self.model.get_parameter_groups(*a, **k)
+
+
+@ModelRegistry.register(["vit_tiny", "vit_small", "vit_base"], "vit")
+class VisionTransformer(ModelBase):
+    """src/models/vit/vision_transformer.py:10-92."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._build_model()
+
+    def _build_model(self):
+        name = self.config.name
+        if name not in V.VIT_MODEL_REGISTRY:
+            raise ValueError(f"Unsupported ViT model name: {name}")
+        kw = _common_kwargs(self.config)
+        kw.setdefault("drop_path_rate", 0.0)
+        self.model = V.VIT_MODEL_REGISTRY[name](**kw)
+
+    def get_parameter_groups(self, *a, **k):
+        return self.model.get_parameter_groups(*a, **k)
+
+
+def install_into(ref_registry) -> None:
+    """Overwrite the reference registry's vit_* / deit_* entries with the B200 wrappers."""
+    ref_registry.register(["deit_tiny", "deit_small", "deit_base"], "vit")(DeiT)
+    ref_registry.register(["vit_tiny", "vit_small", "vit_base"], "vit")(VisionTransformer)
