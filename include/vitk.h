@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 1
+#define VITK_ABI_VERSION 3
 
 typedef enum {
   VITK_OK = 0,
@@ -49,6 +49,8 @@ void vitk_reset_launch_count(void);
  * in elements); an "MN-major" operand is row-major [K, rows] (rows contiguous).  The second
  * form lets dgrad read W[N,K] and wgrad read dY[M,N] / X[M,K] without any transpose copy.
  * ------------------------------------------------------------------------------------------ */
+typedef enum { VITK_BF16 = 0, VITK_FP32 = 1, VITK_FP16 = 2 } vitk_dtype;
+
 typedef enum {
   VITK_EPI_STORE = 0,      /* out = acc*alpha + bias + residual                               */
   VITK_EPI_GELU = 1,       /* out = pre-activation (bf16), out2 = gelu_erf(pre) (bf16)        */
@@ -66,15 +68,19 @@ typedef struct {
   int32_t M, N, K;
   int32_t split_k;    /* >=1; >1 requires VITK_EPI_ATOMIC_ADD */
   int32_t epilogue;   /* vitk_epilogue */
-  int32_t out_fp32;   /* 0: out is bf16, 1: out is fp32 */
+  int32_t out_dtype;  /* vitk_dtype of out (and out2) */
+  int32_t a_dtype;    /* VITK_BF16 or VITK_FP16: element type of A (both are 16-bit tensor-core operands and */
+  int32_t b_dtype;    /* may be mixed: e.g. dY in bf16 (range) times saved activations in fp16 (precision))   */
+  int32_t aux_dtype;  /* element type of aux */
   float alpha;
   const float* bias;      /* [N] fp32 or NULL */
   const float* residual;  /* [M, ldr] fp32 or NULL (may alias out) */
   int64_t ldr;
   void* out;
   int64_t ldo;
-  void* out2;             /* bf16 [M, ldo2] (GELU) */
+  void* out2;             /* [M, ldo2], same dtype as out (GELU: the activation) */
   int64_t ldo2;
+  void* out3;             /* optional bf16 [M, ldo2] copy of out2 (GELU): the operand backward's wgrad reads */
   const void* aux;        /* bf16 [M, ldaux] (DGELU) */
   int64_t ldaux;
   /* VITK_EPI_TOKENS: input row r = b*rows_per_img + p  ->  output row b*tokens_per_img + prefix + p,
@@ -87,13 +93,13 @@ int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm (eps 1e-5, affine) -- vision_transformer_base.py:263,273,377 (nn.LayerNorm)
- * fwd: x fp32 [rows, dim] -> y bf16 [rows, dim], mean/rstd fp32 [rows]
+ * fwd: x fp32 [rows, dim] -> y (fp16 or bf16) [rows, dim] (+ optional bf16 copy y2), mean/rstd fp32 [rows]
  * bwd: dx = (dres or 0) + LN'(dy);  dgamma/dbeta/dcolsum are ACCUMULATED (+=) into fp32 [dim].
  *      dcolsum (optional) receives the column sum of the emitted dx -- that is the bias gradient
  *      of the nn.Linear that produced the residual branch feeding this LayerNorm's input.
  * ------------------------------------------------------------------------------------------ */
-int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16,
-                       float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
+int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
+                       void* y2_bf16, float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
                        void* stream);
 int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
                        const float* gamma, const float* dres, float* dx, void* dx_bf16,
@@ -104,14 +110,15 @@ int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, c
  * Fused softmax attention, dh = 64 -- vision_transformer_base.py:174-191 (Attention.forward:
  * q@k^T * scale, softmax, attn@v) without materialising [B,H,N,N].
  * qkv  bf16 [B, N, 3, H, 64]  (exactly the layout nn.Linear(D,3D) emits, :178)
- * out  bf16 [B, N, H, 64]     (== (attn@v).transpose(1,2).reshape(B,N,C), :191)
+ * out  fp16|bf16 [B, N, H, 64] (== (attn@v).transpose(1,2).reshape(B,N,C), :191); out2 = optional bf16 copy
+ *      (backward reads the bf16 one: `out` argument of vitk_attention_bwd)
  * lse  fp32 [B, H, N]         natural-log sum-exp of the scaled scores (saved for backward)
  * bwd recomputes P from q,k and lse; delta = rowsum(dout*out) is computed internally into
  * `delta` (fp32 [B,H,N] scratch).
  * probs (optional, eval only): fp32 [B,H,N,N] attention maps (:186-188 `attention_maps`).
  * ------------------------------------------------------------------------------------------ */
-int vitk_attention_fwd(const void* qkv, void* out, float* lse, float* probs, int32_t B, int32_t N,
-                       int32_t H, float scale, void* stream);
+int vitk_attention_fwd(const void* qkv, void* out, int32_t out_dtype, void* out2_bf16, float* lse,
+                       float* probs, int32_t B, int32_t N, int32_t H, float scale, void* stream);
 int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                        float* delta, void* dqkv, int32_t B, int32_t N, int32_t H, float scale,
                        void* stream);
@@ -120,10 +127,10 @@ int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const
  * Patch / token plumbing -- vision_transformer_base.py:120-143 (PatchEmbed.forward),
  * deit_models.py:200-211 and vision_transformer_base.py:446-452 (cls/dist tokens + pos_embed).
  * ------------------------------------------------------------------------------------------ */
-/* images fp32 NCHW [B,C,H,W] -> bf16 patch matrix [B*gh*gw, C*P*P] (k = c*P*P + ky*P + kx,
+/* images fp32 NCHW [B,C,H,W] -> fp16|bf16 patch matrix (+ optional bf16 copy) [B*gh*gw, C*P*P] (k = c*P*P + ky*P + kx,
  * the flattening order of Conv2d.weight[D,C,P,P]) */
-int vitk_patchify_bf16(const float* images, void* patches, int32_t B, int32_t C, int32_t H,
-                       int32_t W, int32_t P, void* stream);
+int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, void* patches2_bf16,
+                  int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* stream);
 /* x[b, t, :] = tok_t + pos[t, :] for t < n_prefix (cls, dist) */
 int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos,
                            int32_t B, int32_t tokens_per_img, int32_t dim, int32_t n_prefix,
@@ -181,7 +188,7 @@ int vitk_loss_fwd_bwd(const float* cls_logits, const float* dist_logits, const f
  * ------------------------------------------------------------------------------------------ */
 int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, void* stream);
 int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                    void* params_bf16, const int64_t* chunk_off, const int32_t* chunk_len,
+                    void* params_bf16, void* params_fp16, const int64_t* chunk_off, const int32_t* chunk_len,
                     const float* chunk_lr_scale, const float* chunk_wd, int32_t n_chunks,
                     float* state, float beta1, float beta2, float eps, float max_grad_norm,
                     void* stream);
@@ -189,7 +196,8 @@ int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 /* ------------------------------------------------------------------------------------------
  * Small memory-bound helpers
  * ------------------------------------------------------------------------------------------ */
-int vitk_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* fp32 -> 16-bit shadow(s): dst_bf16 and/or dst_fp16 (either may be NULL) */
+int vitk_cast_f32_to_16(const float* src, void* dst_bf16, void* dst_fp16, int64_t n, void* stream);
 /* out[dim] += column sums of a bf16 [rows, dim] matrix (bias gradients of qkv / fc1) */
 int vitk_colsum_bf16(const void* x_bf16, float* out, int64_t rows, int32_t dim, void* stream);
 

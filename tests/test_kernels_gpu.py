@@ -68,6 +68,14 @@ def test_gemm_gelu(M, N, K):
     torch.cuda.synchronize()
     assert rel_l2(pre, ref) < 6e-3
     assert rel_l2(act, torch.nn.functional.gelu(ref)) < 6e-3
+    # fp16 operands / outputs with the bf16 twin of the activation (the training forward's configuration)
+    Ah, Wh = A.to(torch.float16), W.to(torch.float16)
+    preh = torch.empty(M, N, dtype=torch.float16, device=DEV); acth = torch.empty_like(preh); twin = torch.empty_like(act)
+    ops.gemm(Ah, Wh, M, N, K, out=preh, out2=acth, out3=twin, bias=bias, epilogue=_lib.EPI_GELU)
+    refh = Ah.float() @ Wh.float().t() + bias
+    torch.cuda.synchronize()
+    assert rel_l2(preh, refh) < 6e-4 and rel_l2(acth, torch.nn.functional.gelu(refh)) < 6e-4
+    assert rel_l2(twin, torch.nn.functional.gelu(refh)) < 6e-3
 
 
 @pytest.mark.parametrize("M,N,K", [(6336, 768, 192), (6336, 192, 576), (333, 3072, 768), (130, 72, 136)])
@@ -131,6 +139,9 @@ def test_layernorm_fwd_bwd(rows, dim):
     y, mean, rstd = ops.layernorm_fwd(x, g, b)
     ref = torch.nn.functional.layer_norm(x, (dim,), g, b, 1e-5)
     assert rel_l2(y, ref) < 4e-3
+    twin = torch.empty(rows, dim, dtype=torch.bfloat16, device=DEV)
+    yh, _, _ = ops.layernorm_fwd(x, g, b, dtype=torch.float16, y2=twin)
+    assert rel_l2(yh, ref) < 5e-4 and torch.equal(twin, y)
     dy = _rand(rows, dim, dtype=torch.bfloat16, seed=4)
     dres = _rand(rows, dim, seed=5)
     dg = torch.zeros(dim, device=DEV); db = torch.zeros(dim, device=DEV); dc = torch.zeros(dim, device=DEV)
@@ -166,6 +177,10 @@ def test_attention_fwd_bwd(B, N, H):
     torch.cuda.synchronize()
     assert rel_l2(out, o_ref) < 8e-3
     assert (lse - lse_ref).abs().max().item() < 2e-3
+    outh = torch.empty(B, N, H * 64, dtype=torch.float16, device=DEV); twin = torch.empty_like(out)
+    ops.attention_fwd(qkv, B, N, H, scale, out=outh, out2=twin)
+    torch.cuda.synchronize()
+    assert torch.equal(twin, out) and rel_l2(outh, o_ref) < 8e-3
     dout = _rand(B, N, H * 64, dtype=torch.bfloat16, seed=2)
     dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale)
     o_ref.backward(dout.float())
@@ -193,6 +208,10 @@ def test_patchify(B, C, S, P):
     ref = torch.nn.functional.unfold(img, P, stride=P).transpose(1, 2).reshape(-1, C * P * P)
     torch.cuda.synchronize()
     assert torch.equal(out, ref.to(torch.bfloat16))
+    twin = torch.empty_like(out)
+    outh = ops.patchify(img, P, out2=twin, dtype=torch.float16)
+    torch.cuda.synchronize()
+    assert torch.equal(outh, ref.to(torch.float16)) and torch.equal(twin, out)
 
 
 def test_prefix_and_tokens_bwd():
@@ -294,6 +313,7 @@ def test_adamw_matches_torch(max_norm):
     flat_p = torch.zeros(total, device=DEV); flat_g = torch.zeros(total, device=DEV)
     m = torch.zeros(total, device=DEV); v = torch.zeros(total, device=DEV)
     p16 = torch.zeros(total, dtype=torch.bfloat16, device=DEV)
+    ph16 = torch.zeros(total, dtype=torch.float16, device=DEV)
     refs = []
     for i, (s, o) in enumerate(zip(sizes, offs)):
         n = math.prod(s)
@@ -319,12 +339,13 @@ def test_adamw_matches_torch(max_norm):
             torch.nn.utils.clip_grad_norm_(refs, max_norm)
             ops.grad_sqnorm(flat_g, state)
         opt.step()
-        ops.adamw_step(flat_p, flat_g, m, v, p16, chunk_off, chunk_len, c_scale, c_wd, state, 0.9, 0.999, 1e-8, max_norm)
+        ops.adamw_step(flat_p, flat_g, m, v, p16, ph16, chunk_off, chunk_len, c_scale, c_wd, state, 0.9, 0.999, 1e-8, max_norm)
     torch.cuda.synchronize()
     for r, s, o in zip(refs, sizes, offs):
         n = math.prod(s)
         assert (flat_p[o:o + n] - r.detach().flatten()).abs().max().item() < 2e-6
         assert torch.equal(p16[o:o + n], flat_p[o:o + n].to(torch.bfloat16))
+        assert torch.equal(ph16[o:o + n], flat_p[o:o + n].to(torch.float16))
     assert state[0].item() == 3.0
 
 
@@ -333,6 +354,7 @@ def test_cast_and_colsum():
     x = _rand(1000, 576, seed=1)
     xb = ops.cast_bf16(x)
     assert torch.equal(xb, x.to(torch.bfloat16))
+    assert torch.equal(ops.cast_fp16(x), x.to(torch.float16))
     out = torch.zeros(576, device=DEV)
     ops.colsum_bf16(xb, out)
     torch.cuda.synchronize()
@@ -360,3 +382,28 @@ def test_ensemble_and_rollout():
             R = a @ R
         torch.cuda.synchronize()
         assert (r - R).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------ mixed 16-bit operand formats
+@pytest.mark.parametrize("adt,bdt", [(torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16)])
+def test_gemm_operand_formats(adt, bdt):
+    """kind::f16 takes fp16 x fp16 or bf16 x bf16.  (Mixing the two in ONE tcgen05.mma was probed on B200 and raises
+    cudaErrorIllegalInstruction, so the engine keeps a bf16 twin of every forward operand for backward.)"""
+    M, N, K = 1000, 192, 320
+    A32, B32 = _rand(M, K, seed=1), _rand(N, K, scale=0.05, seed=2)
+    A, B = A32.to(adt), B32.to(bdt)
+    out = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(A, B, M, N, K, out=out)
+    torch.cuda.synchronize()
+    assert rel_l2(out, A.float() @ B.float().t()) < 1e-5
+    # dgrad layout (B MN-major) and wgrad layout (both MN-major, split-K) with mixed formats
+    Bt = _rand(K, N, scale=0.05, seed=3).to(bdt)
+    out16 = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    ops.gemm(A, Bt, M, N, K, b_mn=True, out=out16)
+    torch.cuda.synchronize()
+    assert rel_l2(out16, A.float() @ Bt.float()) < 1e-3
+    dY, X = _rand(M, N, seed=4).to(adt), _rand(M, K, seed=5).to(bdt)
+    dW = torch.zeros(N, K, device=DEV)
+    ops.gemm(dY, X, N, K, M, a_mn=True, b_mn=True, out=dW, split_k=4, epilogue=_lib.EPI_ATOMIC_ADD)
+    torch.cuda.synchronize()
+    assert rel_l2(dW, dY.float().t() @ X.float()) < 1e-4

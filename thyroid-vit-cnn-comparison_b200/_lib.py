@@ -14,6 +14,8 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
+ABI_VERSION = 3
+DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
 
@@ -23,11 +25,12 @@ class GemmArgs(C.Structure):
         ("lda", c_int64), ("ldb", c_int64),
         ("a_mn_major", c_int), ("b_mn_major", c_int),
         ("M", c_int), ("N", c_int), ("K", c_int),
-        ("split_k", c_int), ("epilogue", c_int), ("out_fp32", c_int),
+        ("split_k", c_int), ("epilogue", c_int), ("out_dtype", c_int),
+        ("a_dtype", c_int), ("b_dtype", c_int), ("aux_dtype", c_int),
         ("alpha", c_float),
         ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64),
         ("out", c_void_p), ("ldo", c_int64),
-        ("out2", c_void_p), ("ldo2", c_int64),
+        ("out2", c_void_p), ("ldo2", c_int64), ("out3", c_void_p),
         ("aux", c_void_p), ("ldaux", c_int64),
         ("rows_per_img", c_int), ("tokens_per_img", c_int), ("prefix", c_int),
         ("pos", c_void_p),
@@ -41,19 +44,19 @@ SIGNATURES = {
     "vitk_launch_count": (c_int64, []),
     "vitk_reset_launch_count": (None, []),
     "vitk_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
-    "vitk_layernorm_fwd": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_float, c_void_p]),
+    "vitk_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int64, c_int, c_float, c_void_p]),
     "vitk_layernorm_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_void_p]),
-    "vitk_attention_fwd": (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "vitk_attention_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 3 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vitk_attention_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_void_p]),
-    "vitk_patchify_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "vitk_patchify": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
     "vitk_prefix_tokens_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "vitk_tokens_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
     "vitk_head_fwd": (c_int, [c_void_p] * 11 + [c_int] * 5 + [c_float, c_void_p]),
     "vitk_head_bwd": (c_int, [c_void_p] * 17 + [c_int] * 5 + [c_void_p]),
     "vitk_loss_fwd_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int] + [c_float] * 5 + [c_void_p]),
     "vitk_grad_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    "vitk_adamw_step": (c_int, [c_void_p] * 9 + [c_int, c_void_p] + [c_float] * 4 + [c_void_p]),
-    "vitk_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "vitk_adamw_step": (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_float] * 4 + [c_void_p]),
+    "vitk_cast_f32_to_16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vitk_colsum_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vitk_ensemble_probs": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "vitk_attention_rollout": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
@@ -81,7 +84,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.vitk_abi_version() != 1:
+    if lib.vitk_abi_version() != ABI_VERSION:
         raise RuntimeError("libvitk.so ABI version mismatch")
     _lib = lib
     return lib

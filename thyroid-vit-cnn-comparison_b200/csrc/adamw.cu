@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
 
 __global__ void __launch_bounds__(256)
     adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 __nv_bfloat16* __restrict__ p16, const long long* __restrict__ chunk_off, const int* __restrict__ chunk_len,
+                 __nv_bfloat16* __restrict__ p16, __half* __restrict__ ph16, const long long* __restrict__ chunk_off, const int* __restrict__ chunk_len,
                  const float* __restrict__ chunk_lr_scale, const float* __restrict__ chunk_wd, const float* __restrict__ state,
                  float beta1, float beta2, float eps, float max_norm) {
   const int c = blockIdx.x;
@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(256)
     *reinterpret_cast<float4*>(m + e) = mv;
     *reinterpret_cast<float4*>(v + e) = vv;
     if (p16 != nullptr) *reinterpret_cast<uint2*>(p16 + e) = make_uint2(pack_bf16(pv.x, pv.y), pack_bf16(pv.z, pv.w));
+    if (ph16 != nullptr) {
+      __half2 h0 = __floats2half2_rn(pv.x, pv.y), h1 = __floats2half2_rn(pv.z, pv.w);
+      *reinterpret_cast<uint2*>(ph16 + e) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    }
   }
   for (int i = (len4 << 2) + threadIdx.x; i < len; i += blockDim.x) {
     const long long e = off + i;
@@ -87,6 +91,7 @@ __global__ void __launch_bounds__(256)
     const float pk = p[e] * decay - step_size * (mk / denom);
     p[e] = pk; m[e] = mk; v[e] = vk;
     if (p16 != nullptr) p16[e] = __float2bfloat16(pk);
+    if (ph16 != nullptr) ph16[e] = __float2half_rn(pk);
   }
 }
 
@@ -115,7 +120,7 @@ extern "C" int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, voi
 }
 
 extern "C" int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16,
-                               const int64_t* chunk_off, const int32_t* chunk_len, const float* chunk_lr_scale,
+                               void* params_fp16, const int64_t* chunk_off, const int32_t* chunk_len, const float* chunk_lr_scale,
                                const float* chunk_wd, int32_t n_chunks, float* state, float beta1, float beta2, float eps,
                                float max_grad_norm, void* stream) {
   VITK_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && chunk_off && chunk_len && chunk_lr_scale && chunk_wd && state,
@@ -123,7 +128,7 @@ extern "C" int vitk_adamw_step(float* params, const float* grads, float* exp_avg
   VITK_CHECK_ARG(n_chunks > 0, "vitk_adamw_step: n_chunks must be > 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   adamw_kernel<<<n_chunks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(params_bf16),
-                                         reinterpret_cast<const long long*>(chunk_off), chunk_len, chunk_lr_scale, chunk_wd,
+                                         reinterpret_cast<__half*>(params_fp16), reinterpret_cast<const long long*>(chunk_off), chunk_len, chunk_lr_scale, chunk_wd,
                                          state, beta1, beta2, eps, max_grad_norm);
   VITK_LAUNCH_CHECK();
   adamw_tick_kernel<<<1, 1, 0, st>>>(state, max_grad_norm);

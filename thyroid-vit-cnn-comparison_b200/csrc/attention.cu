@@ -125,8 +125,9 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                       float* __restrict__ lse, int N, int H, float scale_log2) {
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int out_fp16,
+                                                       bf16* __restrict__ out2, float* __restrict__ lse, int N, int H,
+                                                       float scale_log2) {
   __shared__ __align__(128) bf16 sQ[TILE * DH];
   __shared__ __align__(128) bf16 sK[2][TILE * DH];
   __shared__ __align__(128) bf16 sV[2][TILE * DH];
@@ -219,10 +220,19 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
     const int q = q0 + warp * 16 + g + r * 8;
     if (q >= N) continue;
     const float inv = 1.f / l_run[r];
-    bf16* orow = out + ((long long)(b * N + q) * H + h) * DH;
+    const long long ooff = ((long long)(b * N + q) * H + h) * DH;
+    bf16* orow = out + ooff;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-      *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = pack_bf16(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+    for (int nt = 0; nt < 8; ++nt) {
+      const float v0 = o[nt][2 * r] * inv, v1 = o[nt][2 * r + 1] * inv;
+      if (out_fp16) {
+        __half2 hh = __floats2half2_rn(v0, v1);
+        *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = *reinterpret_cast<uint32_t*>(&hh);
+      } else {
+        *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = pack_bf16(v0, v1);
+      }
+      if (out2 != nullptr) *reinterpret_cast<uint32_t*>(out2 + ooff + nt * 8 + 2 * t) = pack_bf16(v0, v1);
+    }
     if (t == 0) lse[((long long)b * H + h) * N + q] = m_run[r] * LN2 + logf(l_run[r]);
   }
 }
@@ -493,14 +503,16 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 
 using namespace vitk;
 
-extern "C" int vitk_attention_fwd(const void* qkv, void* out, float* lse, float* probs, int32_t B, int32_t N, int32_t H,
-                                  float scale, void* stream) {
+extern "C" int vitk_attention_fwd(const void* qkv, void* out, int32_t out_dtype, void* out2_bf16, float* lse, float* probs,
+                                  int32_t B, int32_t N, int32_t H, float scale, void* stream) {
   VITK_CHECK_ARG(qkv && out && lse, "vitk_attention_fwd: null pointer");
+  VITK_CHECK_ARG(out_dtype == VITK_BF16 || out_dtype == VITK_FP16, "vitk_attention_fwd: out must be bf16 or fp16");
   VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_fwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_fwd: grid limit");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  attn_fwd_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse, N, H,
+  attn_fwd_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out),
+                                        int(out_dtype == VITK_FP16), reinterpret_cast<bf16*>(out2_bf16), lse, N, H,
                                         scale * LOG2E);
   VITK_LAUNCH_CHECK();
   if (probs != nullptr) {

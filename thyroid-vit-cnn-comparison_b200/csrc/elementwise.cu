@@ -18,16 +18,26 @@ inline int capped_grid(long long work_items, int threads, int ctas_per_sm) {
 }
 
 // ------------------------------------------------------------------ fp32 -> bf16
-__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, __half* __restrict__ dsth, long long n) {
   const long long n8 = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     const float4 a = ldg_f4(src + 8 * i), b = ldg_f4(src + 8 * i + 4);
-    *reinterpret_cast<uint4*>(dst + 8 * i) =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    if (dst != nullptr)
+      *reinterpret_cast<uint4*>(dst + 8 * i) =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    if (dsth != nullptr)
+      *reinterpret_cast<uint4*>(dsth + 8 * i) =
+          make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
   }
-  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    dst[i] = __float2bfloat16(src[i]);
+  for (long long i = (n8 << 3) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (dst != nullptr) dst[i] = __float2bfloat16(src[i]);
+    if (dsth != nullptr) dsth[i] = __float2half_rn(src[i]);
+  }
 }
 
 // ------------------------------------------------------------------ column sums of a bf16 matrix
@@ -65,7 +75,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 }
 
 // ------------------------------------------------------------------ patch gather (fp32 NCHW -> bf16 [B*gh*gw, C*P*P])
-__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int B, int C, int H, int W, int P) {
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int fp16, bf16* __restrict__ patches2,
+                                int B, int C, int H, int W, int P) {
   const int wv = W >> 3;
   const long long total = (long long)B * C * H * wv;
   const int gw = W / P, gh = H / P;
@@ -82,9 +93,14 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
     const float4 a0 = ldg_f4(src), a1 = ldg_f4(src + 4);
     const int x = xv * 8;
     const int py = y / P, ky = y - py * P, px = x / P, kx = x - px * P;
-    bf16* dst = patches + ((long long)(b * gh + py) * gw + px) * Kdim + c * P * P + ky * P + kx;
-    *reinterpret_cast<uint4*>(dst) =
-        make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
+    const long long doff = ((long long)(b * gh + py) * gw + px) * Kdim + c * P * P + ky * P + kx;
+    const uint4 vb = make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
+    if (fp16)
+      *reinterpret_cast<uint4*>(patches + doff) =
+          make_uint4(pack_f16(a0.x, a0.y), pack_f16(a0.z, a0.w), pack_f16(a1.x, a1.y), pack_f16(a1.z, a1.w));
+    else
+      *reinterpret_cast<uint4*>(patches + doff) = vb;
+    if (patches2 != nullptr) *reinterpret_cast<uint4*>(patches2 + doff) = vb;
   }
 }
 
@@ -312,13 +328,14 @@ __global__ void rollout_eye_kernel(float* __restrict__ r, int B, int N) {
 
 using namespace vitk;
 
-extern "C" int vitk_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
-  VITK_CHECK_ARG(src && dst && n >= 0, "vitk_cast_f32_to_bf16: bad args");
+extern "C" int vitk_cast_f32_to_16(const float* src, void* dst_bf16, void* dst_fp16, int64_t n, void* stream) {
+  VITK_CHECK_ARG(src && (dst_bf16 || dst_fp16) && n >= 0, "vitk_cast_f32_to_16: bad args");
   if (n == 0) return VITK_OK;
-  VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
-                 "vitk_cast_f32_to_bf16: pointers must be 16-byte aligned");
+  VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dst_fp16) & 15) == 0,
+                 "vitk_cast_f32_to_16: pointers must be 16-byte aligned");
   cast_kernel<<<capped_grid(n / 8 + 1, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<bf16*>(dst), n);
+      src, reinterpret_cast<bf16*>(dst_bf16), reinterpret_cast<__half*>(dst_fp16), n);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -337,14 +354,16 @@ extern "C" int vitk_colsum_bf16(const void* x, float* out, int64_t rows, int32_t
   return VITK_OK;
 }
 
-extern "C" int vitk_patchify_bf16(const float* images, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P,
-                                  void* stream) {
-  VITK_CHECK_ARG(images && patches, "vitk_patchify_bf16: null pointer");
+extern "C" int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, void* patches2_bf16, int32_t B,
+                             int32_t C, int32_t H, int32_t W, int32_t P, void* stream) {
+  VITK_CHECK_ARG(images && patches, "vitk_patchify: null pointer");
+  VITK_CHECK_ARG(patches_dtype == VITK_BF16 || patches_dtype == VITK_FP16, "vitk_patchify: patches must be bf16 or fp16");
   VITK_CHECK_ARG(B > 0 && C > 0 && P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0,
-                 "vitk_patchify_bf16: need P %% 8 == 0 and H, W divisible by P (B=%d C=%d H=%d W=%d P=%d)", B, C, H, W, P);
+                 "vitk_patchify: need P %% 8 == 0 and H, W divisible by P (B=%d C=%d H=%d W=%d P=%d)", B, C, H, W, P);
   const long long total = (long long)B * C * H * (W / 8);
   patchify_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      images, reinterpret_cast<bf16*>(patches), B, C, H, W, P);
+      images, reinterpret_cast<bf16*>(patches), int(patches_dtype == VITK_FP16), reinterpret_cast<bf16*>(patches2_bf16), B, C, H,
+      W, P);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -33,7 +33,8 @@ struct GemmParams {
   int M, N, K;
   int num_kblocks;
   int kblocks_per_split;
-  int epilogue, out_fp32;
+  int epilogue, out_dtype, aux_dtype;
+  uint32_t idesc;
   float alpha;
   const float* bias;
   const float* residual;
@@ -42,6 +43,7 @@ struct GemmParams {
   long long ldo;
   void* out2;
   long long ldo2;
+  void* out3;
   const void* aux;
   long long ldaux;
   int rows_per_img, tokens_per_img, prefix;
@@ -154,11 +156,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
          (2ull << 61);
 }
 
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M = 128, N = BN.
-template <int BN, bool A_MN, bool B_MN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
-         (uint32_t(BN >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+// Instruction descriptor for kind::f16: {bf16|fp16} x {bf16|fp16} -> fp32, M = 128, N = bn.
+// a_format / b_format: 0 = F16, 1 = BF16 (may differ between A and B).
+inline uint32_t make_idesc(int bn, bool a_mn, bool b_mn, bool a_fp16, bool b_fp16) {
+  return (1u << 4) | (uint32_t(a_fp16 ? 0 : 1) << 7) | (uint32_t(b_fp16 ? 0 : 1) << 10) | (uint32_t(a_mn) << 15) |
+         (uint32_t(b_mn) << 16) | (uint32_t(bn >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+}
+
+// 16-bit packing in the output element type
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool fp16) {
+  if (fp16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, bool fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return unpack_bf16(u);
 }
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+    const uint32_t idesc = p.idesc;
     constexpr uint32_t a_adv = A_MN ? (2048u >> 4) : (32u >> 4);  // desc.lo step per UMMA_K
     constexpr uint32_t b_adv = B_MN ? (2048u >> 4) : (32u >> 4);
     for (int kb = 0; kb < nk; ++kb) {
@@ -326,33 +341,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               }
             }
           }
-          if (p.out_fp32) {
+          if (p.out_dtype == VITK_FP32) {
             float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (col0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
+            const bool h = p.out_dtype == VITK_FP16;
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
               if (col0 + j < p.N)
-                st_global_v4(o + j, pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                             pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                st_global_v4(o + j, pack16(f[j], f[j + 1], h), pack16(f[j + 2], f[j + 3], h),
+                             pack16(f[j + 4], f[j + 5], h), pack16(f[j + 6], f[j + 7], h));
           }
         } break;
         case VITK_EPI_GELU: {
+          const bool h = p.out_dtype == VITK_FP16;
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
           __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j < p.N) {
-              st_global_v4(o + j, pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                           pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+              st_global_v4(o + j, pack16(f[j], f[j + 1], h), pack16(f[j + 2], f[j + 3], h),
+                           pack16(f[j + 4], f[j + 5], h), pack16(f[j + 6], f[j + 7], h));
               float g[8];
 #pragma unroll
               for (int t = 0; t < 8; ++t) g[t] = gelu_erf(f[j + t]);
-              st_global_v4(o2 + j, pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]),
-                           pack_bf16(g[6], g[7]));
+              st_global_v4(o2 + j, pack16(g[0], g[1], h), pack16(g[2], g[3], h), pack16(g[4], g[5], h),
+                           pack16(g[6], g[7], h));
+              if (p.out3 != nullptr)
+                st_global_v4(reinterpret_cast<__nv_bfloat16*>(p.out3) + orow * p.ldo2 + col0 + j, pack_bf16(g[0], g[1]),
+                             pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
             }
           }
         } break;
@@ -363,13 +383,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j < p.N) {
               const uint4 a4 = ldg_u4(ax + j);
-              const float2 a0 = unpack_bf16(a4.x), a1 = unpack_bf16(a4.y), a2 = unpack_bf16(a4.z),
-                           a3 = unpack_bf16(a4.w);
+              const bool ah = p.aux_dtype == VITK_FP16;
+              const float2 a0 = unpack16(a4.x, ah), a1 = unpack16(a4.y, ah), a2 = unpack16(a4.z, ah),
+                           a3 = unpack16(a4.w, ah);
               const float g0 = f[j] * gelu_erf_grad(a0.x), g1 = f[j + 1] * gelu_erf_grad(a0.y);
               const float g2 = f[j + 2] * gelu_erf_grad(a1.x), g3 = f[j + 3] * gelu_erf_grad(a1.y);
               const float g4 = f[j + 4] * gelu_erf_grad(a2.x), g5 = f[j + 5] * gelu_erf_grad(a2.y);
               const float g6 = f[j + 6] * gelu_erf_grad(a3.x), g7 = f[j + 7] * gelu_erf_grad(a3.y);
-              st_global_v4(o + j, pack_bf16(g0, g1), pack_bf16(g2, g3), pack_bf16(g4, g5), pack_bf16(g6, g7));
+              const bool h = p.out_dtype == VITK_FP16;
+              st_global_v4(o + j, pack16(g0, g1, h), pack16(g2, g3, h), pack16(g4, g5, h), pack16(g6, g7, h));
             }
           }
         } break;
@@ -405,7 +427,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D bf16 tensor map over a row-major [outer, inner] matrix, 128B swizzle, zero OOB fill.
 int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
-                 uint32_t box_inner, uint32_t box_outer) {
+                 uint32_t box_inner, uint32_t box_outer, bool fp16) {
   auto fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -415,7 +437,7 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
   cuuint64_t strides[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -497,13 +519,19 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream) {
   VITK_CHECK_ARG(a->split_k == 1 || a->epilogue == VITK_EPI_ATOMIC_ADD,
                  "vitk_gemm_bf16: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
   VITK_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= VITK_EPI_TOKENS, "vitk_gemm_bf16: bad epilogue %d", a->epilogue);
-  if (a->epilogue == VITK_EPI_GELU) VITK_CHECK_ARG(a->out2 != nullptr && !a->out_fp32, "GELU epilogue needs bf16 out and out2");
-  if (a->epilogue == VITK_EPI_DGELU) VITK_CHECK_ARG(a->aux != nullptr && !a->out_fp32, "DGELU epilogue needs aux and bf16 out");
-  if (a->epilogue == VITK_EPI_ATOMIC_ADD) VITK_CHECK_ARG(a->out_fp32, "ATOMIC_ADD epilogue needs fp32 out");
+  VITK_CHECK_ARG(a->out_dtype >= VITK_BF16 && a->out_dtype <= VITK_FP16, "vitk_gemm_bf16: bad out_dtype %d", a->out_dtype);
+  VITK_CHECK_ARG((a->a_dtype == VITK_BF16 || a->a_dtype == VITK_FP16) && (a->b_dtype == VITK_BF16 || a->b_dtype == VITK_FP16),
+                 "vitk_gemm_bf16: operands must be bf16 or fp16");
+  const bool out_fp32 = a->out_dtype == VITK_FP32;
+  if (a->epilogue == VITK_EPI_GELU) VITK_CHECK_ARG(a->out2 != nullptr && !out_fp32, "GELU epilogue needs 16-bit out and out2");
+  if (a->epilogue == VITK_EPI_DGELU)
+    VITK_CHECK_ARG(a->aux != nullptr && !out_fp32 && (a->aux_dtype == VITK_BF16 || a->aux_dtype == VITK_FP16),
+                   "DGELU epilogue needs a 16-bit aux and 16-bit out");
+  if (a->epilogue == VITK_EPI_ATOMIC_ADD) VITK_CHECK_ARG(out_fp32, "ATOMIC_ADD epilogue needs fp32 out");
   if (a->epilogue == VITK_EPI_TOKENS)
     VITK_CHECK_ARG(a->pos != nullptr && a->rows_per_img > 0 && a->tokens_per_img >= a->rows_per_img + a->prefix,
                    "TOKENS epilogue needs pos / rows_per_img / tokens_per_img");
-  const int vec = a->out_fp32 ? 4 : 8;
+  const int vec = out_fp32 ? 4 : 8;
   VITK_CHECK_ARG(a->ldo % vec == 0, "vitk_gemm_bf16: ldo must keep rows 16-byte aligned");
 
   const int bn = pick_bn(a->N);
@@ -515,20 +543,21 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_kblocks = num_kblocks;
   p.kblocks_per_split = kpb;
-  p.epilogue = a->epilogue; p.out_fp32 = a->out_fp32;
+  p.epilogue = a->epilogue; p.out_dtype = a->out_dtype; p.aux_dtype = a->aux_dtype;
+  p.idesc = make_idesc(bn, a->a_mn_major != 0, a->b_mn_major != 0, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16);
   p.alpha = a->alpha;
   p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr;
-  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
+  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2; p.out3 = a->out3;
   p.aux = a->aux; p.ldaux = a->ldaux;
   p.rows_per_img = a->rows_per_img; p.tokens_per_img = a->tokens_per_img; p.prefix = a->prefix; p.pos = a->pos;
 
   CUtensorMap tmA, tmB;
   int rc;
-  if (!a->a_mn_major) rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M);
-  else                rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K);
+  if (!a->a_mn_major) rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M, a->a_dtype == VITK_FP16);
+  else                rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K, a->a_dtype == VITK_FP16);
   if (rc != VITK_OK) return rc;
-  if (!a->b_mn_major) rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn);
-  else                rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K);
+  if (!a->b_mn_major) rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, a->b_dtype == VITK_FP16);
+  else                rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, a->b_dtype == VITK_FP16);
   if (rc != VITK_OK) return rc;
 
   dim3 grid((a->M + BLOCK_M - 1) / BLOCK_M, (a->N + bn - 1) / bn, splits);

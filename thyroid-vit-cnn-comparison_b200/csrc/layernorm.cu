@@ -20,7 +20,8 @@ constexpr int LN_WARPS = 8;
 template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
-                                                               __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                                                               __nv_bfloat16* __restrict__ y, int y_fp16,
+                                                               __nv_bfloat16* __restrict__ y2, float* __restrict__ mean,
                                                                float* __restrict__ rstd, long long rows, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int nvec = dim >> 2;
@@ -63,7 +64,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
         const float b = (v[c].y - mu) * rs * gm[c].y + bt[c].y;
         const float cc = (v[c].z - mu) * rs * gm[c].z + bt[c].z;
         const float d = (v[c].w - mu) * rs * gm[c].w + bt[c].w;
-        *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(pack_bf16(a, b), pack_bf16(cc, d));
+        if (y_fp16) {
+          __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(cc, d);
+          *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        } else {
+          *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(pack_bf16(a, b), pack_bf16(cc, d));
+        }
+        if (y2 != nullptr) *reinterpret_cast<uint2*>(y2 + row * dim + 4 * i) = make_uint2(pack_bf16(a, b), pack_bf16(cc, d));
       }
     }
     if (lane == 0) {
@@ -190,14 +197,17 @@ static int ln_chunks(int dim) {
   return 99;
 }
 
-extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* mean,
-                                  float* rstd, int64_t rows, int32_t dim, float eps, void* stream) {
-  VITK_CHECK_ARG(x && gamma && beta && y_bf16 && mean && rstd, "vitk_layernorm_fwd: null pointer");
+extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
+                                  void* y2_bf16, float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
+                                  void* stream) {
+  VITK_CHECK_ARG(x && gamma && beta && y && mean && rstd, "vitk_layernorm_fwd: null pointer");
+  VITK_CHECK_ARG(y_dtype == VITK_BF16 || y_dtype == VITK_FP16, "vitk_layernorm_fwd: y must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_fwd: dim=%d must be a multiple of 4, <= 1024", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ch = ln_chunks(dim);
   LN_DISPATCH(ch, ln_fwd_kernel<C_><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(
-                      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), mean, rstd, rows, dim, eps));
+                      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16),
+                      reinterpret_cast<__nv_bfloat16*>(y2_bf16), mean, rstd, rows, dim, eps));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -10,9 +10,16 @@ Memory layout in HBM (per rank)
   flat_params   fp32 [P]   all trainable tensors, each padded to 128 elements, in REVERSE execution order
                             (heads, norm, blocks L-1..0, patch/pos/cls) so gradient buckets complete in order
   flat_grads    fp32 [P]   same offsets; kernels ACCUMULATE into it (split-K red.add, column-sum atomics)
-  flat_bf16     bf16 [P]   tensor-core shadow of flat_params (written by the AdamW kernel / cast kernel)
+  flat_fp16     fp16 [P]   forward tensor-core shadow of flat_params  } both written by the AdamW kernel
+  flat_bf16     bf16 [P]   backward (dgrad) tensor-core shadow         } (or the cast kernel)
   residual x    fp32 [B*T, D] per block boundary (2L+1 buffers, saved for backward)
-  activations   bf16: LN outputs, qkv [B,T,3,H,64], attention out [B,T,H,64], fc1 pre/post GELU [B*T, 4D]
+  activations   fp16 GEMM inputs of the forward (LN outputs, attention out, GELU out, patches) with a bf16 twin
+                saved for backward's wgrad; qkv [B,T,3,H,64] bf16; fc1 pre-activation fp16
+
+Operand formats: tcgen05 kind::f16 cannot mix fp16 and bf16 in one MMA (probed on B200: illegal instruction).
+Forward GEMMs run fp16 x fp16 -- 11-bit significands are what keeps the logits inside the 2e-3 parity bound
+(pure bf16 measured 1.1e-3 rms / 2.8e-3 max at B=32) -- while every gradient tensor is bf16 (fp32 exponent range,
+no loss scaling), so backward GEMMs run bf16 x bf16 against the bf16 twins.  Accumulation is always fp32.
 """
 from __future__ import annotations
 
@@ -79,6 +86,7 @@ class FlatParams:
         self.params = torch.zeros(total, dtype=torch.float32, device=device)
         self.grads = torch.zeros(total, dtype=torch.float32, device=device)
         self.bf16 = torch.zeros(total, dtype=torch.bfloat16, device=device)
+        self.fp16 = torch.zeros(total, dtype=torch.float16, device=device)
         self._shadow_version = -1
         for n in order:
             self.view(self.params, n).copy_(named[n].detach().to(device=device, dtype=torch.float32))
@@ -88,8 +96,8 @@ class FlatParams:
         return buf[off:off + shape.numel()].view(shape)
 
     def refresh_shadow(self) -> None:
-        """flat_params -> bf16 shadow (one vectorised cast kernel over the whole buffer)."""
-        ops.cast_bf16(self.params, self.bf16)
+        """flat_params -> fp16 + bf16 shadows (one vectorised cast kernel over the whole buffer)."""
+        ops.cast_shadows(self.params, self.bf16, self.fp16)
 
     def bucket_slices(self, bucket_bytes: int) -> List[Tuple[int, int]]:
         """Contiguous [start, end) element ranges of ~bucket_bytes, cut at tensor boundaries, in
@@ -114,20 +122,26 @@ class Workspace:
         self.B, self.train = B, train
         T, D, H = d.tokens, d.dim, d.heads
         M = B * T
-        f32, b16 = torch.float32, torch.bfloat16
+        f32, b16, h16 = torch.float32, torch.bfloat16, torch.float16
         e = lambda *s, dt=b16: torch.empty(*s, dtype=dt, device=device)
         L = d.depth if train else 1
-        self.patches = e(B * d.n_patches, d.kpatch)
+        self.patches = e(B * d.n_patches, d.kpatch, dt=h16)
+        self.patches_b = e(B * d.n_patches, d.kpatch) if train else None
         nres = 2 * d.depth + 1 if train else 3
         self.x = [e(M, D, dt=f32) for _ in range(nres)]
-        self.xn1 = [e(M, D) for _ in range(L)]
-        self.xn2 = [e(M, D) for _ in range(L)]
+        self.xn1 = [e(M, D, dt=h16) for _ in range(L)]
+        self.xn2 = [e(M, D, dt=h16) for _ in range(L)]
+        # bf16 twins of the forward GEMM inputs: what backward's wgrad GEMMs read
+        self.xn1_b = [e(M, D) for _ in range(L)] if train else [None]
+        self.xn2_b = [e(M, D) for _ in range(L)] if train else [None]
+        self.ao_b = [e(M, D) for _ in range(L)] if train else [None]
+        self.act_b = [e(M, d.hidden) for _ in range(L)] if train else [None]
         self.stats = [e(4, M, dt=f32) for _ in range(L)]          # mean1, rstd1, mean2, rstd2
         self.qkv = [e(M, 3 * D) for _ in range(L)]
-        self.ao = [e(M, D) for _ in range(L)]
+        self.ao = [e(M, D, dt=h16) for _ in range(L)]
         self.lse = [e(B, H, T, dt=f32) for _ in range(L)]
-        self.pre = [e(M, d.hidden) for _ in range(L)]
-        self.act = [e(M, d.hidden) for _ in range(L)]
+        self.pre = [e(M, d.hidden, dt=h16) for _ in range(L)]
+        self.act = [e(M, d.hidden, dt=h16) for _ in range(L)]
         if train:
             self.dx = [e(M, D, dt=f32) for _ in range(2)]
             self.dxb = e(M, D)
@@ -161,8 +175,11 @@ class VitEngine:
         self.grad_ready_hook = None   # callable(name_prefix) used by the data-parallel bucket launcher
 
     # ------------------------------------------------------------------ helpers
-    def w(self, name: str) -> torch.Tensor:      # bf16 shadow view
+    def w(self, name: str) -> torch.Tensor:      # bf16 shadow view (backward)
         return self.flat.view(self.flat.bf16, name)
+
+    def wh(self, name: str) -> torch.Tensor:     # fp16 shadow view (forward)
+        return self.flat.view(self.flat.fp16, name)
 
     def p(self, name: str) -> torch.Tensor:      # fp32 master view
         return self.flat.view(self.flat.params, name)
@@ -204,9 +221,9 @@ class VitEngine:
         images = images.contiguous()
         if images.dtype != torch.float32:
             images = images.float()
-        ops.patchify(images, d.patch, out=ws.patches)
+        ops.patchify(images, d.patch, out=ws.patches, out2=ws.patches_b)
         x0 = ws.x[0]
-        ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
+        ops.gemm(ws.patches, self.wh("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
                  bias=self.p("patch_embed.proj.bias"), epilogue=_lib.EPI_TOKENS,
                  tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"))
         ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token"),
@@ -219,18 +236,20 @@ class VitEngine:
             else:
                 x_in, x_mid, x_out = ws.x[(2 * l) % 3], ws.x[(2 * l + 1) % 3], ws.x[(2 * l + 2) % 3]
             st = ws.stats[s]
-            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), y=ws.xn1[s], mean=st[0], rstd=st[1])
-            ops.gemm(ws.xn1[s], self.w(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
+            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), y=ws.xn1[s], y2=ws.xn1_b[s],
+                              mean=st[0], rstd=st[1])
+            ops.gemm(ws.xn1[s], self.wh(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
             probs = None
             if attn_probs is not None:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
-            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
-            ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
-            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
-            ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.pre[s], out2=ws.act[s],
+            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], out2=ws.ao_b[s], lse=ws.lse[s], probs=probs)
+            ops.gemm(ws.ao[s], self.wh(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
+            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], y2=ws.xn2_b[s],
+                              mean=st[2], rstd=st[3])
+            ops.gemm(ws.xn2[s], self.wh(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.pre[s], out2=ws.act[s], out3=ws.act_b[s],
                      bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
-            ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
+            ops.gemm(ws.act[s], self.wh(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
         x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
         two = d.n_out == 2
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
@@ -266,22 +285,22 @@ class VitEngine:
             st = ws.stats[l]
             x_in, x_mid = ws.x[2 * l], ws.x[2 * l + 1]
             # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
-            self._wgrad(ws.dxb, ws.act[l], pre + "mlp.fc2.weight", M)
+            self._wgrad(ws.dxb, ws.act_b[l], pre + "mlp.fc2.weight", M)
             ops.gemm(ws.dxb, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.pre[l],
                      epilogue=_lib.EPI_DGELU)
             ops.colsum_bf16(ws.d_pre, self.g(pre + "mlp.fc1.bias"))
-            self._wgrad(ws.d_pre, ws.xn2[l], pre + "mlp.fc1.weight", M)
+            self._wgrad(ws.d_pre, ws.xn2_b[l], pre + "mlp.fc1.weight", M)
             ops.gemm(ws.d_pre, self.w(pre + "mlp.fc1.weight"), M, D, d.hidden, b_mn=True, out=ws.dxn)
             ops.layernorm_bwd(ws.dxn, x_mid, st[2], st[3], self.p(pre + "norm2.weight"), self.g(pre + "norm2.weight"),
                               self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx_bf16=ws.dxb,
                               dcolsum=self.g(pre + "attn.proj.bias"))
             dx, dx_alt = dx_alt, dx
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
-            self._wgrad(ws.dxb, ws.ao[l], pre + "attn.proj.weight", M)
+            self._wgrad(ws.dxb, ws.ao_b[l], pre + "attn.proj.weight", M)
             ops.gemm(ws.dxb, self.w(pre + "attn.proj.weight"), M, D, D, b_mn=True, out=ws.d_ao)
-            ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
+            ops.attention_bwd(ws.qkv[l], ws.ao_b[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
             ops.colsum_bf16(ws.dqkv, self.g(pre + "attn.qkv.bias"))
-            self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M)
+            self._wgrad(ws.dqkv, ws.xn1_b[l], pre + "attn.qkv.weight", M)
             ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
             prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
             ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),
@@ -292,7 +311,7 @@ class VitEngine:
         ops.tokens_bwd(dx.view(B, T, D), self.g("pos_embed"), self.g("cls_token"),
                        self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g("patch_embed.proj.bias"),
                        d.n_prefix)
-        self._wgrad(ws.dpatch, ws.patches, "patch_embed.proj.weight", B * d.n_patches)
+        self._wgrad(ws.dpatch, ws.patches_b, "patch_embed.proj.weight", B * d.n_patches)
         self._notify("embed")
 
     def _notify(self, what: str) -> None:

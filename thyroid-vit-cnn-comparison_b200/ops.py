@@ -14,7 +14,18 @@ from . import _lib
 from ._lib import GemmArgs, check
 
 bf16 = torch.bfloat16
+f16 = torch.float16
 f32 = torch.float32
+_DT = {bf16: _lib.DT_BF16, f32: _lib.DT_FP32, f16: _lib.DT_FP16}
+
+
+def _req16(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (libvitk has no CPU path)")
+    if t.dtype not in (bf16, f16):
+        raise RuntimeError(f"{name}: expected bfloat16 or float16, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
 
 
 def _stream() -> int:
@@ -46,21 +57,23 @@ def reset_launch_count() -> None:
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
          out: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          epilogue: int = _lib.EPI_STORE, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
-         split_k: int = 1, alpha: float = 1.0, tokens: Optional[tuple] = None, pos: Optional[torch.Tensor] = None,
+         out3: Optional[torch.Tensor] = None, split_k: int = 1, alpha: float = 1.0, tokens: Optional[tuple] = None, pos: Optional[torch.Tensor] = None,
          lda: Optional[int] = None, ldb: Optional[int] = None) -> torch.Tensor:
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue (see include/vitk.h).
 
     A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].
     """
-    _req(A, bf16, "gemm A"); _req(B, bf16, "gemm B")
+    _req16(A, "gemm A"); _req16(B, "gemm B")
     a = GemmArgs()
+    a.a_dtype, a.b_dtype = _DT[A.dtype], _DT[B.dtype]
+    a.aux_dtype = _DT[aux.dtype] if aux is not None else 0
     a.A, a.B = A.data_ptr(), B.data_ptr()
     a.lda = lda if lda is not None else (M if a_mn else K)
     a.ldb = ldb if ldb is not None else (N if b_mn else K)
     a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
     a.M, a.N, a.K = M, N, K
     a.split_k, a.epilogue = split_k, epilogue
-    a.out_fp32 = int(out.dtype == f32)
+    a.out_dtype = _DT[out.dtype]
     a.alpha = alpha
     if bias is not None:
         _req(bias, f32, "gemm bias")
@@ -69,6 +82,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     a.bias, a.residual, a.ldr = _p(bias), _p(residual), N
     a.out, a.ldo = out.data_ptr(), N
     a.out2, a.ldo2 = _p(out2), N
+    a.out3 = _p(out3)
     a.aux, a.ldaux = _p(aux), N
     if tokens is not None:
         a.rows_per_img, a.tokens_per_img, a.prefix = tokens
@@ -78,15 +92,18 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
 
 
 # --------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=None, y2=None, dtype=bf16):
+    """y = LayerNorm(x) in `dtype` (fp16 or bf16); y2: optional extra bf16 copy (what backward's wgrad reads)."""
     _req(x, f32, "layernorm x")
     dim = x.shape[-1]
     rows = x.numel() // dim
-    y = torch.empty(x.shape, dtype=bf16, device=x.device) if y is None else y
+    y = torch.empty(x.shape, dtype=dtype, device=x.device) if y is None else y
     mean = torch.empty(rows, dtype=f32, device=x.device) if mean is None else mean
     rstd = torch.empty(rows, dtype=f32, device=x.device) if rstd is None else rstd
-    check(_lib.load().vitk_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                         rstd.data_ptr(), rows, dim, eps, _stream()), "layernorm_fwd")
+    if y2 is not None:
+        _req(y2, bf16, "layernorm y2")
+    check(_lib.load().vitk_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _DT[y.dtype], _p(y2),
+                                         mean.data_ptr(), rstd.data_ptr(), rows, dim, eps, _stream()), "layernorm_fwd")
     return y, mean, rstd
 
 
@@ -102,12 +119,13 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None
 
 
 # --------------------------------------------------------------------------- attention
-def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None):
+def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None, out2=None):
+    """out in fp16 or bf16 (its dtype decides); out2: optional bf16 copy for backward."""
     _req(qkv, bf16, "attention qkv")
     out = torch.empty(B, N, H * 64, dtype=bf16, device=qkv.device) if out is None else out
     lse = torch.empty(B, H, N, dtype=f32, device=qkv.device) if lse is None else lse
-    check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), _p(probs), B, N, H, scale, _stream()),
-          "attention_fwd")
+    check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), _DT[out.dtype], _p(out2), lse.data_ptr(), _p(probs),
+                                         B, N, H, scale, _stream()), "attention_fwd")
     return out, lse
 
 
@@ -121,12 +139,13 @@ def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqk
 
 
 # --------------------------------------------------------------------------- tokens
-def patchify(images, P: int, out=None):
+def patchify(images, P: int, out=None, out2=None, dtype=bf16):
     _req(images, f32, "patchify images")
     B, Cc, H, W = images.shape
     rows = B * (H // P) * (W // P)
-    out = torch.empty(rows, Cc * P * P, dtype=bf16, device=images.device) if out is None else out
-    check(_lib.load().vitk_patchify_bf16(images.data_ptr(), out.data_ptr(), B, Cc, H, W, P, _stream()), "patchify")
+    out = torch.empty(rows, Cc * P * P, dtype=dtype, device=images.device) if out is None else out
+    check(_lib.load().vitk_patchify(images.data_ptr(), out.data_ptr(), _DT[out.dtype], _p(out2), B, Cc, H, W, P, _stream()),
+          "patchify")
     return out
 
 
@@ -189,10 +208,10 @@ def grad_sqnorm(grads, state):
     check(_lib.load().vitk_grad_sqnorm(grads.data_ptr(), grads.numel(), state.data_ptr(), _stream()), "grad_sqnorm")
 
 
-def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, chunk_off, chunk_len, chunk_lr_scale, chunk_wd, state,
+def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, params_fp16, chunk_off, chunk_len, chunk_lr_scale, chunk_wd, state,
                beta1: float, beta2: float, eps: float, max_grad_norm: float):
     check(_lib.load().vitk_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                                      _p(params_bf16), chunk_off.data_ptr(), chunk_len.data_ptr(), chunk_lr_scale.data_ptr(),
+                                      _p(params_bf16), _p(params_fp16), chunk_off.data_ptr(), chunk_len.data_ptr(), chunk_lr_scale.data_ptr(),
                                       chunk_wd.data_ptr(), chunk_off.numel(), state.data_ptr(), beta1, beta2, eps,
                                       max_grad_norm, _stream()), "adamw_step")
 
@@ -201,8 +220,21 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, chunk_off, chunk
 def cast_bf16(src, dst=None):
     _req(src, f32, "cast src")
     dst = torch.empty(src.shape, dtype=bf16, device=src.device) if dst is None else dst
-    check(_lib.load().vitk_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "cast")
+    check(_lib.load().vitk_cast_f32_to_16(src.data_ptr(), dst.data_ptr(), None, src.numel(), _stream()), "cast")
     return dst
+
+
+def cast_fp16(src, dst=None):
+    _req(src, f32, "cast src")
+    dst = torch.empty(src.shape, dtype=f16, device=src.device) if dst is None else dst
+    check(_lib.load().vitk_cast_f32_to_16(src.data_ptr(), None, dst.data_ptr(), src.numel(), _stream()), "cast")
+    return dst
+
+
+def cast_shadows(src, dst_bf16, dst_fp16):
+    """One pass over fp32 `src` writing both 16-bit shadows."""
+    _req(src, f32, "cast src")
+    check(_lib.load().vitk_cast_f32_to_16(src.data_ptr(), _p(dst_bf16), _p(dst_fp16), src.numel(), _stream()), "cast")
 
 
 def colsum_bf16(x, out):

@@ -92,7 +92,7 @@ class FusedAdamW(torch.optim.Optimizer):
         flat = self.engine.flat
         if self.max_grad_norm > 0:
             ops.grad_sqnorm(flat.grads, self.dev_state)
-        ops.adamw_step(flat.params, flat.grads, self.exp_avg, self.exp_avg_sq, flat.bf16, self.chunk_off, self.chunk_len,
+        ops.adamw_step(flat.params, flat.grads, self.exp_avg, self.exp_avg_sq, flat.bf16, flat.fp16, self.chunk_off, self.chunk_len,
                        self.chunk_lr, self.chunk_wd, self.dev_state, self.betas[0], self.betas[1], self.eps,
                        self.max_grad_norm)
 

@@ -1,0 +1,122 @@
+"""Data parallelism: one process per GPU, bucketed gradient all-reduce over NCCL (NVLink 5 / NVSwitch)
+overlapped with backward, plus fold-sharded ensemble inference.
+
+The reference has no distributed code at all (`strategy: auto, devices: 1`); the
+path shards naturally by batch, so the design is plain DP:
+  * every rank holds a full replica (flat fp32 params / grads, engine.FlatParams);
+  * the flat gradient buffer is laid out in REVERSE execution order, so as backward walks
+    head -> blocks L-1..0 -> embeddings, a growing PREFIX of the buffer is final;
+  * each time the engine reports a finished stage, every ~bucket_mb bucket that lies inside the final
+    prefix is all-reduced (SUM, fp32) asynchronously on NCCL's stream while backward continues;
+  * gradients were pre-divided by world_size in the fused loss kernel, so SUM == global-batch mean;
+  * the optimizer's grad-norm/clip runs AFTER the reduction: no extra scalar collective is needed.
+Works with any torch.distributed backend (gloo on CPU tensors is used by the unit tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* from the environment (torchrun). Returns (rank, world, local_rank)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend=backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def completed_prefix(order: List[str], offsets: dict, pad: int, stage: str, depth: int) -> int:
+    """End offset (elements) of the flat-gradient prefix that is final once `stage` has finished.
+    stage: 'head' | 'blocks.<l>.' | 'embed'."""
+    def end_of(name: str) -> int:
+        off, shape = offsets[name]
+        return off + (shape.numel() + pad - 1) // pad * pad
+
+    if stage == "embed":
+        return end_of(order[-1])
+    if stage == "head":
+        names = [n for n in order if n.startswith("head") or n.startswith("norm.")]
+        return max(end_of(n) for n in names)
+    blk = int(stage.split(".")[1])
+    names = [n for n in order if n.startswith("head") or n.startswith("norm.") or
+             (n.startswith("blocks.") and int(n.split(".")[1]) >= blk)]
+    return max(end_of(n) for n in names)
+
+
+class BucketedAllReduce:
+    """Gradient reducer attached to a VitEngine (see module docstring)."""
+
+    def __init__(self, process_group=None, bucket_mb: float = 25.0):
+        self.pg = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.engine = None
+        self.buckets: List[Tuple[int, int]] = []
+        self._next = 0
+        self._works = []
+        self.launched_log: List[Tuple[str, int]] = []   # (stage, bucket index) -- used by tests
+
+    def attach(self, engine) -> None:
+        from .engine import PAD
+        self.engine = engine
+        self._pad = PAD
+        self.buckets = engine.flat.bucket_slices(self.bucket_bytes)
+        engine.grad_ready_hook = self.on_stage_done
+        self._next = 0
+
+    def on_stage_done(self, stage: str) -> None:
+        if self.world_size == 1:
+            return
+        flat = self.engine.flat
+        done = completed_prefix(flat.order, flat.offsets, self._pad, stage, self.engine.d.depth)
+        while self._next < len(self.buckets) and self.buckets[self._next][1] <= done:
+            s, e = self.buckets[self._next]
+            self._works.append(dist.all_reduce(flat.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            self.launched_log.append((stage, self._next))
+            self._next += 1
+
+    def finish(self) -> None:
+        """Reduce whatever is left and make the current stream wait for all buckets (no host sync on NCCL)."""
+        if self.world_size > 1:
+            self.on_stage_done("embed")
+            for w in self._works:
+                w.wait()
+        self._works = []
+        self._next = 0
+
+
+def shard_folds(num_folds: int, rank: int, world: int) -> List[int]:
+    """Fold f runs on rank f mod world (folds are independent, no data-path collective)."""
+    return [f for f in range(num_folds) if f % world == rank]
+
+
+def gather_fold_logits(local_logits: torch.Tensor, local_folds: List[int], num_folds: int, process_group=None) -> torch.Tensor:
+    """All-gather per-fold logits [F_local,B,C] into [F,B,C] in fold order (tiny: B*C floats per fold)."""
+    if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
+        return local_logits
+    world = dist.get_world_size(process_group)
+    per_rank = (num_folds + world - 1) // world
+    B, C = local_logits.shape[1:]
+    buf = local_logits.new_zeros(per_rank, B, C)
+    buf[:local_logits.shape[0]] = local_logits
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=process_group)
+    full = local_logits.new_zeros(num_folds, B, C)
+    for r in range(world):
+        for i, f in enumerate(shard_folds(num_folds, r, world)):
+            full[f] = out[r][i]
+    return full

@@ -99,8 +99,8 @@ class PatchEmbed(nn.Module):
             assert H == self.img_size and W == self.img_size, \
                 f"Input size ({H}x{W}) doesn't match expected size ({self.img_size}x{self.img_size})"
         _require_cuda(x, "PatchEmbed")
-        patches = ops.patchify(x.float().contiguous(), self.patch_size)
-        w16 = ops.cast_bf16(self.proj.weight.detach().reshape(self.embed_dim, -1).contiguous())
+        patches = ops.patchify(x.float().contiguous(), self.patch_size, dtype=torch.float16)
+        w16 = ops.cast_fp16(self.proj.weight.detach().reshape(self.embed_dim, -1).contiguous())
         out = torch.empty(patches.shape[0], self.embed_dim, dtype=torch.float32, device=x.device)
         ops.gemm(patches, w16, patches.shape[0], self.embed_dim, patches.shape[1], out=out,
                  bias=self.proj.bias.detach() if self.proj.bias is not None else None)
