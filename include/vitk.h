@@ -15,6 +15,14 @@
  *   - return value: 0 on success, negative vitk_status on failure; vitk_last_error() gives text.
  *   - bf16 buffers are passed as void* (uint16 storage, torch.bfloat16).
  *   - the library never falls back to a CPU or library path: a missing GPU is an error.
+ *
+ * Numerics contract
+ *   - tensor-core operands are 16-bit (fp16 by default in the engine, bf16 supported everywhere), accumulation,
+ *     softmax/LayerNorm statistics, the residual stream and all PARAMETER gradients are fp32.
+ *   - activation gradients (dY tensors) are stored in 16 bits multiplied by a loss scale S that lives on the
+ *     device (amp_state[0]); kernels that emit parameter gradients multiply by 1/S (amp_state[1], passed as
+ *     `grad_unscale`) while accumulating, so the fp32 gradient buffer always holds TRUE gradients.
+ *   - amp_state fp32[8] = {S, 1/S, good_steps, skipped_steps, last_step_overflowed, -, -, -}.
  */
 #ifndef VITK_H_
 #define VITK_H_
@@ -25,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 3
+#define VITK_ABI_VERSION 4
 
 typedef enum {
   VITK_OK = 0,
@@ -73,6 +81,7 @@ typedef struct {
   int32_t b_dtype;    /* may be mixed: e.g. dY in bf16 (range) times saved activations in fp16 (precision))   */
   int32_t aux_dtype;  /* element type of aux */
   float alpha;
+  const float* alpha_dev; /* optional DEVICE scalar multiplied into alpha (1/loss-scale for wgrad) */
   const float* bias;      /* [N] fp32 or NULL */
   const float* residual;  /* [M, ldr] fp32 or NULL (may alias out) */
   int64_t ldr;
@@ -80,7 +89,6 @@ typedef struct {
   int64_t ldo;
   void* out2;             /* [M, ldo2], same dtype as out (GELU: the activation) */
   int64_t ldo2;
-  void* out3;             /* optional bf16 [M, ldo2] copy of out2 (GELU): the operand backward's wgrad reads */
   const void* aux;        /* bf16 [M, ldaux] (DGELU) */
   int64_t ldaux;
   /* VITK_EPI_TOKENS: input row r = b*rows_per_img + p  ->  output row b*tokens_per_img + prefix + p,
@@ -89,66 +97,67 @@ typedef struct {
   const float* pos;
 } vitk_gemm_args;
 
-int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);
+int vitk_gemm(const vitk_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm (eps 1e-5, affine) -- vision_transformer_base.py:263,273,377 (nn.LayerNorm)
- * fwd: x fp32 [rows, dim] -> y (fp16 or bf16) [rows, dim] (+ optional bf16 copy y2), mean/rstd fp32 [rows]
- * bwd: dx = (dres or 0) + LN'(dy);  dgamma/dbeta/dcolsum are ACCUMULATED (+=) into fp32 [dim].
- *      dcolsum (optional) receives the column sum of the emitted dx -- that is the bias gradient
- *      of the nn.Linear that produced the residual branch feeding this LayerNorm's input.
+ * fwd: x fp32 [rows, dim] -> y (fp16|bf16) [rows, dim], mean/rstd fp32 [rows]
+ * bwd: dx = (dres or 0) + LN'(dy) in fp32 (+ optional 16-bit copy dx16 for the next dgrad/wgrad GEMM);
+ *      dgamma/dbeta/dcolsum are ACCUMULATED (+=) into fp32 [dim], each multiplied by *grad_unscale when given.
+ *      dcolsum (optional) receives the column sum of the emitted dx -- the bias gradient of the nn.Linear
+ *      that produced the residual branch feeding this LayerNorm's input.
  * ------------------------------------------------------------------------------------------ */
 int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
-                       void* y2_bf16, float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
-                       void* stream);
-int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
-                       const float* gamma, const float* dres, float* dx, void* dx_bf16,
-                       float* dgamma, float* dbeta, float* dcolsum, int64_t rows, int32_t dim,
-                       void* stream);
+                       float* mean, float* rstd, int64_t rows, int32_t dim, float eps, void* stream);
+int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* mean,
+                       const float* rstd, const float* gamma, const float* dres, float* dx, void* dx16,
+                       int32_t dx16_dtype, float* dgamma, float* dbeta, float* dcolsum,
+                       const float* grad_unscale, int64_t rows, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused softmax attention, dh = 64 -- vision_transformer_base.py:174-191 (Attention.forward:
- * q@k^T * scale, softmax, attn@v) without materialising [B,H,N,N].
- * qkv  bf16 [B, N, 3, H, 64]  (exactly the layout nn.Linear(D,3D) emits, :178)
- * out  fp16|bf16 [B, N, H, 64] (== (attn@v).transpose(1,2).reshape(B,N,C), :191); out2 = optional bf16 copy
- *      (backward reads the bf16 one: `out` argument of vitk_attention_bwd)
- * lse  fp32 [B, H, N]         natural-log sum-exp of the scaled scores (saved for backward)
+ * q@k^T * scale, softmax, attn@v) without materialising [B,H,N,N].  One element type (`dtype`:
+ * fp16|bf16) for qkv / out / dout / dqkv.
+ * qkv  [B, N, 3, H, 64]  (exactly the layout nn.Linear(D,3D) emits, :178)
+ * out  [B, N, H, 64]     (== (attn@v).transpose(1,2).reshape(B,N,C), :191)
+ * lse  fp32 [B, H, N]    natural-log sum-exp of the scaled scores (saved for backward)
  * bwd recomputes P from q,k and lse; delta = rowsum(dout*out) is computed internally into
  * `delta` (fp32 [B,H,N] scratch).
  * probs (optional, eval only): fp32 [B,H,N,N] attention maps (:186-188 `attention_maps`).
  * ------------------------------------------------------------------------------------------ */
-int vitk_attention_fwd(const void* qkv, void* out, int32_t out_dtype, void* out2_bf16, float* lse,
-                       float* probs, int32_t B, int32_t N, int32_t H, float scale, void* stream);
+int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, float* lse, float* probs, int32_t B,
+                       int32_t N, int32_t H, float scale, void* stream);
 int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
-                       float* delta, void* dqkv, int32_t B, int32_t N, int32_t H, float scale,
-                       void* stream);
+                       float* delta, void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H,
+                       float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch / token plumbing -- vision_transformer_base.py:120-143 (PatchEmbed.forward),
  * deit_models.py:200-211 and vision_transformer_base.py:446-452 (cls/dist tokens + pos_embed).
  * ------------------------------------------------------------------------------------------ */
-/* images fp32 NCHW [B,C,H,W] -> fp16|bf16 patch matrix (+ optional bf16 copy) [B*gh*gw, C*P*P] (k = c*P*P + ky*P + kx,
+/* images fp32 NCHW [B,C,H,W] -> fp16|bf16 patch matrix [B*gh*gw, C*P*P] (k = c*P*P + ky*P + kx,
  * the flattening order of Conv2d.weight[D,C,P,P]) */
-int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, void* patches2_bf16,
-                  int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* stream);
+int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, int32_t B, int32_t C,
+                  int32_t H, int32_t W, int32_t P, void* stream);
 /* x[b, t, :] = tok_t + pos[t, :] for t < n_prefix (cls, dist) */
 int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos,
                            int32_t B, int32_t tokens_per_img, int32_t dim, int32_t n_prefix,
                            void* stream);
-/* dpos[t,:] += sum_b dx[b,t,:] ; dcls += sum_b dx[b,0,:] ; ddist += sum_b dx[b,1,:];
- * dpatch_bf16 [B*rows_per_img, dim] = bf16(dx[b, n_prefix+p, :]) (the dY of the patch GEMM);
- * dbias_patch[dim] += column sum over patch rows. */
-int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch_bf16,
-                    float* dbias_patch, int32_t B, int32_t tokens_per_img, int32_t dim,
-                    int32_t n_prefix, void* stream);
+/* dpos[t,:] += u*sum_b dx[b,t,:] ; dcls += u*sum_b dx[b,0,:] ; ddist += u*sum_b dx[b,1,:]  (u = *grad_unscale or 1);
+ * dpatch16 [B*rows_per_img, dim] = 16-bit copy of dx[b, n_prefix+p, :] (the dY of the patch GEMM, still scaled);
+ * dbias_patch[dim] += u * column sum over patch rows. */
+int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch16,
+                    int32_t dpatch_dtype, float* dbias_patch, const float* grad_unscale, int32_t B,
+                    int32_t tokens_per_img, int32_t dim, int32_t n_prefix, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Final norm + classification heads on the pooled rows only --
  * deit_models.py:217,224-235 / vision_transformer_base.py:468-486 (norm, x[:,0], head, head_dist)
  * x fp32 [B, tokens_per_img, dim]; for head h in [0,n_heads): row h of every image is
  * LayerNorm'd and multiplied by W_h [C, dim] (+ b_h [C]) -> logits_h [B, C].
- * bwd writes dx / dx_bf16 (ZERO outside the pooled rows), accumulates every parameter gradient
- * and (optional) dcolsum[dim] += column sum of dx (bias gradient of the last block's fc2).
+ * bwd takes TRUE dlogits, writes dx / dx16 = S * d(loss)/dx (S = *loss_scale or 1; ZERO outside the pooled
+ * rows), accumulates every (true) parameter gradient and (optional) dcolsum[dim] += column sum of the true dx
+ * (bias gradient of the last block's fc2).
  * ------------------------------------------------------------------------------------------ */
 int vitk_head_fwd(const float* x, const float* gamma, const float* beta, const float* W0,
                   const float* b0, const float* W1, const float* b1, float* logits0,
@@ -156,10 +165,10 @@ int vitk_head_fwd(const float* x, const float* gamma, const float* beta, const f
                   int32_t dim, int32_t C, int32_t n_heads, float eps, void* stream);
 int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat,
                   const float* rstd, const float* gamma, const float* beta, const float* W0,
-                  const float* W1,
-                  float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dW0, float* db0,
-                  float* dW1, float* db1, float* dcolsum, int32_t B, int32_t tokens_per_img,
-                  int32_t dim, int32_t C, int32_t n_heads, void* stream);
+                  const float* W1, float* dx, void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta,
+                  float* dW0, float* db0, float* dW1, float* db1, float* dcolsum,
+                  const float* loss_scale, int32_t B, int32_t tokens_per_img, int32_t dim, int32_t C,
+                  int32_t n_heads, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused classification / distillation loss with gradient --
@@ -187,10 +196,16 @@ int vitk_loss_fwd_bwd(const float* cls_logits, const float* dist_logits, const f
  * state fp32[4] on device: {step, lr, grad_sqnorm, clip_coef}.
  * ------------------------------------------------------------------------------------------ */
 int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, void* stream);
+/* If state[2] (the squared norm) is not finite the step is SKIPPED (fp16 overflow): nothing is written, and --
+ * when amp_state is given -- S is halved; otherwise S doubles after `growth_interval` clean steps. */
 int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                    void* params_bf16, void* params_fp16, const int64_t* chunk_off, const int32_t* chunk_len,
-                    const float* chunk_lr_scale, const float* chunk_wd, int32_t n_chunks,
-                    float* state, float beta1, float beta2, float eps, float max_grad_norm,
+                    void* params_bf16, void* params_fp16, const int64_t* chunk_off,
+                    const int32_t* chunk_len, const float* chunk_lr_scale, const float* chunk_wd,
+                    int32_t n_chunks, float* state, float* amp_state, float beta1, float beta2, float eps,
+                    float max_grad_norm, int32_t growth_interval, void* stream);
+/* Loss-scale bookkeeping for callers that run their OWN optimizer on the fp32 gradients (torch.optim.*):
+ * checks grads for inf/nan; on overflow zeroes them and halves S, else counts towards the next doubling. */
+int vitk_amp_update(float* grads, int64_t n, float* amp_state, float* scratch4, int32_t growth_interval,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -198,8 +213,9 @@ int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
  * ------------------------------------------------------------------------------------------ */
 /* fp32 -> 16-bit shadow(s): dst_bf16 and/or dst_fp16 (either may be NULL) */
 int vitk_cast_f32_to_16(const float* src, void* dst_bf16, void* dst_fp16, int64_t n, void* stream);
-/* out[dim] += column sums of a bf16 [rows, dim] matrix (bias gradients of qkv / fc1) */
-int vitk_colsum_bf16(const void* x_bf16, float* out, int64_t rows, int32_t dim, void* stream);
+/* out[dim] += u * column sums of a 16-bit [rows, dim] matrix (bias gradients of qkv / fc1), u = *grad_unscale or 1 */
+int vitk_colsum16(const void* x, int32_t dtype, float* out, const float* grad_unscale, int64_t rows,
+                  int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Ensemble + attention rollout (config 5) --

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -27,10 +27,10 @@ class GemmArgs(C.Structure):
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("split_k", c_int), ("epilogue", c_int), ("out_dtype", c_int),
         ("a_dtype", c_int), ("b_dtype", c_int), ("aux_dtype", c_int),
-        ("alpha", c_float),
+        ("alpha", c_float), ("alpha_dev", c_void_p),
         ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64),
         ("out", c_void_p), ("ldo", c_int64),
-        ("out2", c_void_p), ("ldo2", c_int64), ("out3", c_void_p),
+        ("out2", c_void_p), ("ldo2", c_int64),
         ("aux", c_void_p), ("ldaux", c_int64),
         ("rows_per_img", c_int), ("tokens_per_img", c_int), ("prefix", c_int),
         ("pos", c_void_p),
@@ -43,21 +43,22 @@ SIGNATURES = {
     "vitk_last_error": (C.c_char_p, []),
     "vitk_launch_count": (c_int64, []),
     "vitk_reset_launch_count": (None, []),
-    "vitk_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
-    "vitk_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_int64, c_int, c_float, c_void_p]),
-    "vitk_layernorm_bwd": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_void_p]),
-    "vitk_attention_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 3 + [c_int, c_int, c_int, c_float, c_void_p]),
-    "vitk_attention_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_void_p]),
-    "vitk_patchify": (c_int, [c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "vitk_gemm": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "vitk_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 2 + [c_int64, c_int, c_float, c_void_p]),
+    "vitk_layernorm_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 7 + [c_int] + [c_void_p] * 4 + [c_int64, c_int, c_void_p]),
+    "vitk_attention_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "vitk_attention_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]),
+    "vitk_patchify": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "vitk_prefix_tokens_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
-    "vitk_tokens_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
+    "vitk_tokens_bwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 4 + [c_void_p]),
     "vitk_head_fwd": (c_int, [c_void_p] * 11 + [c_int] * 5 + [c_float, c_void_p]),
-    "vitk_head_bwd": (c_int, [c_void_p] * 17 + [c_int] * 5 + [c_void_p]),
+    "vitk_head_bwd": (c_int, [c_void_p] * 10 + [c_int] + [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
     "vitk_loss_fwd_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int] + [c_float] * 5 + [c_void_p]),
     "vitk_grad_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    "vitk_adamw_step": (c_int, [c_void_p] * 10 + [c_int, c_void_p] + [c_float] * 4 + [c_void_p]),
+    "vitk_adamw_step": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p] + [c_float] * 4 + [c_int, c_void_p]),
+    "vitk_amp_update": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "vitk_cast_f32_to_16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "vitk_colsum_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vitk_colsum16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vitk_ensemble_probs": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "vitk_attention_rollout": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
 }

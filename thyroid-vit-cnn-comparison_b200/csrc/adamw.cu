@@ -1,5 +1,6 @@
 // adamw.cu -- multi-tensor AdamW over one flat parameter buffer, fused with Lightning's global
-// L2-norm gradient clipping and with the fp32 -> bf16 weight shadow the tensor-core GEMMs read.
+// L2-norm gradient clipping, with the fp32 -> 16-bit weight shadows the tensor-core GEMMs read, and with
+// the dynamic loss-scale bookkeeping of the fp16 gradient path.
 //
 // Restates torch.optim.AdamW(param_groups, lr, betas, eps=1e-8, weight_decay) as configured at
 // src/training/lightning_modules.py:599-604 (ViT) and :1108-1113 (distillation: one group per
@@ -9,9 +10,13 @@
 //     p <- p*(1 - lr*wd);  m <- b1*m + (1-b1)*g;  v <- b2*v + (1-b2)*g^2
 //     p <- p - (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 //
-// HBM roofline: 28 B/param without clipping (read p,g,m,v = 16 B; write p,m,v = 12 B) + 2 B bf16
-// shadow; the norm pass re-reads g (4 B/param).  state = {step, lr, grad_sqnorm, clip_coef} lives
-// on the device so the whole step replays inside a CUDA graph.
+// Loss scaling (torch.cuda.amp.GradScaler semantics, all on the device so the step replays from a CUDA
+// graph): activation gradients travel as fp16 multiplied by S; parameter gradients were already divided by
+// S by the kernels that produced them.  If ||g||^2 is not finite the step is skipped and S halves; after
+// `growth_interval` consecutive clean steps S doubles.
+//
+// HBM roofline: 28 B/param (read p,g,m,v = 16 B; write p,m,v = 12 B) + 2 B per 16-bit shadow; the norm
+// pass re-reads g (4 B/param).  state = {step, lr, grad_sqnorm, clip_coef}.
 #include "vitk_common.cuh"
 
 namespace vitk {
@@ -39,11 +44,15 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
   }
 }
 
+__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e+38f; }  // false for inf and nan
+
 __global__ void __launch_bounds__(256)
     adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 __nv_bfloat16* __restrict__ p16, __half* __restrict__ ph16, const long long* __restrict__ chunk_off, const int* __restrict__ chunk_len,
-                 const float* __restrict__ chunk_lr_scale, const float* __restrict__ chunk_wd, const float* __restrict__ state,
-                 float beta1, float beta2, float eps, float max_norm) {
+                 __nv_bfloat16* __restrict__ p16, __half* __restrict__ ph16, const long long* __restrict__ chunk_off,
+                 const int* __restrict__ chunk_len, const float* __restrict__ chunk_lr_scale,
+                 const float* __restrict__ chunk_wd, const float* __restrict__ state, float beta1, float beta2, float eps,
+                 float max_norm) {
+  if (!finite_f(state[2])) return;  // overflowed step: skip (every CTA sees the same value)
   const int c = blockIdx.x;
   const long long off = chunk_off[c];
   const int len = chunk_len[c];
@@ -77,10 +86,7 @@ __global__ void __launch_bounds__(256)
     *reinterpret_cast<float4*>(m + e) = mv;
     *reinterpret_cast<float4*>(v + e) = vv;
     if (p16 != nullptr) *reinterpret_cast<uint2*>(p16 + e) = make_uint2(pack_bf16(pv.x, pv.y), pack_bf16(pv.z, pv.w));
-    if (ph16 != nullptr) {
-      __half2 h0 = __floats2half2_rn(pv.x, pv.y), h1 = __floats2half2_rn(pv.z, pv.w);
-      *reinterpret_cast<uint2*>(ph16 + e) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-    }
+    if (ph16 != nullptr) *reinterpret_cast<uint2*>(ph16 + e) = make_uint2(pack_f16(pv.x, pv.y), pack_f16(pv.z, pv.w));
   }
   for (int i = (len4 << 2) + threadIdx.x; i < len; i += blockDim.x) {
     const long long e = off + i;
@@ -95,11 +101,50 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// after the update: step += 1, publish the clip coefficient, clear the norm accumulator
-__global__ void adamw_tick_kernel(float* state, float max_norm) {
-  state[3] = max_norm > 0.f ? fminf(1.f, max_norm / (sqrtf(state[2]) + 1e-6f)) : 1.f;
-  state[0] += 1.f;
+__device__ __forceinline__ void amp_bookkeeping(float* amp, bool overflow, int growth_interval) {
+  if (amp == nullptr) return;
+  if (overflow) {
+    amp[0] = fmaxf(amp[0] * 0.5f, 1.f);
+    amp[2] = 0.f;
+    amp[3] += 1.f;
+    amp[4] = 1.f;
+  } else {
+    amp[2] += 1.f;
+    amp[4] = 0.f;
+    if (growth_interval > 0 && amp[2] >= float(growth_interval)) {
+      amp[0] = fminf(amp[0] * 2.f, 16777216.f);
+      amp[2] = 0.f;
+    }
+  }
+  amp[1] = 1.f / amp[0];
+}
+
+// after the update: step += 1 (clean steps only), publish the clip coefficient, clear the norm accumulator
+__global__ void adamw_tick_kernel(float* state, float* amp, float max_norm, int growth_interval) {
+  const bool ok = finite_f(state[2]);
+  state[3] = (ok && max_norm > 0.f) ? fminf(1.f, max_norm / (sqrtf(state[2]) + 1e-6f)) : 1.f;
+  if (ok) state[0] += 1.f;
   state[2] = 0.f;
+  amp_bookkeeping(amp, !ok, growth_interval);
+}
+
+// compat path (external torch optimizer): zero the gradients of an overflowed step
+__global__ void amp_zero_if_overflow_kernel(float* __restrict__ g, long long n, const float* __restrict__ scratch) {
+  if (finite_f(scratch[2])) return;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] = 0.f;
+}
+__global__ void amp_tick_kernel(float* scratch, float* amp, int growth_interval) {
+  amp_bookkeeping(amp, !finite_f(scratch[2]), growth_interval);
+  scratch[2] = 0.f;
+}
+
+int sq_grid(long long n) {
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
 }
 
 }  // namespace
@@ -110,28 +155,38 @@ using namespace vitk;
 extern "C" int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, void* stream) {
   VITK_CHECK_ARG(grads && state && n > 0, "vitk_grad_sqnorm: bad args");
   VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "vitk_grad_sqnorm: grads must be 16-byte aligned");
-  long long blocks = (n / 4 + 255) / 256;
-  const long long cap = (long long)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  sqnorm_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(grads, n, state);
+  sqnorm_kernel<<<sq_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(grads, n, state);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
 extern "C" int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16,
-                               void* params_fp16, const int64_t* chunk_off, const int32_t* chunk_len, const float* chunk_lr_scale,
-                               const float* chunk_wd, int32_t n_chunks, float* state, float beta1, float beta2, float eps,
-                               float max_grad_norm, void* stream) {
+                               void* params_fp16, const int64_t* chunk_off, const int32_t* chunk_len,
+                               const float* chunk_lr_scale, const float* chunk_wd, int32_t n_chunks, float* state,
+                               float* amp_state, float beta1, float beta2, float eps, float max_grad_norm,
+                               int32_t growth_interval, void* stream) {
   VITK_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && chunk_off && chunk_len && chunk_lr_scale && chunk_wd && state,
                  "vitk_adamw_step: null pointer");
   VITK_CHECK_ARG(n_chunks > 0, "vitk_adamw_step: n_chunks must be > 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   adamw_kernel<<<n_chunks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(params_bf16),
-                                         reinterpret_cast<__half*>(params_fp16), reinterpret_cast<const long long*>(chunk_off), chunk_len, chunk_lr_scale, chunk_wd,
-                                         state, beta1, beta2, eps, max_grad_norm);
+                                         reinterpret_cast<__half*>(params_fp16), reinterpret_cast<const long long*>(chunk_off),
+                                         chunk_len, chunk_lr_scale, chunk_wd, state, beta1, beta2, eps, max_grad_norm);
   VITK_LAUNCH_CHECK();
-  adamw_tick_kernel<<<1, 1, 0, st>>>(state, max_grad_norm);
+  adamw_tick_kernel<<<1, 1, 0, st>>>(state, amp_state, max_grad_norm, growth_interval);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_amp_update(float* grads, int64_t n, float* amp_state, float* scratch4, int32_t growth_interval,
+                               void* stream) {
+  VITK_CHECK_ARG(grads && amp_state && scratch4 && n > 0, "vitk_amp_update: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sqnorm_kernel<<<sq_grid(n), 256, 0, st>>>(grads, n, scratch4);
+  VITK_LAUNCH_CHECK();
+  amp_zero_if_overflow_kernel<<<sq_grid(n), 256, 0, st>>>(grads, n, scratch4);
+  VITK_LAUNCH_CHECK();
+  amp_tick_kernel<<<1, 1, 0, st>>>(scratch4, amp_state, growth_interval);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

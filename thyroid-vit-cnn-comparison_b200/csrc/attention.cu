@@ -9,7 +9,10 @@
 // Layouts are the reference's own: qkv [B,N,3,H,64] is what nn.Linear(D,3D) emits (:178), the
 // output [B,N,H,64] is (attn@v).transpose(1,2).reshape(B,N,C) (:191) -- no permute copies.
 //
-// Round-1 implementation: warp-level mma.sync m16n8k16 bf16 (HMMA) with ldmatrix from
+// Element type: fp16 or bf16 for ALL of qkv / out / dout / dqkv of one call (template H16); the engine uses
+// fp16 (gradients are loss-scaled), bf16 stays available.  Softmax statistics and accumulators are fp32.
+//
+// Round-1 implementation: warp-level mma.sync m16n8k16 (HMMA) with ldmatrix from
 // XOR-swizzled shared tiles.  The tcgen05/TMEM version (S and P resident in TMEM, N<=256 in a
 // single tile) is the planned replacement; the C-ABI below is already the one it will keep.
 #include "vitk_common.cuh"
@@ -60,11 +63,32 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <bool H16>
+__device__ __forceinline__ void mma_16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (H16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+template <bool H16>
+__device__ __forceinline__ uint32_t pk(float lo, float hi) {
+  if (H16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(lo, hi);
+}
+template <bool H16>
+__device__ __forceinline__ float2 upk(uint32_t u) {
+  if (H16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return unpack_bf16(u);
 }
 
 // A-operand fragments (16 rows x 64 k) of rows [r0, r0+16) of a tile: 4 k16 steps.
@@ -86,6 +110,7 @@ __device__ __forceinline__ void load_b_kn(uint32_t (&f)[4], const bf16* tile, in
 }
 
 // acc[8][4] (16 x 64) += A(16 x 64 via frags) * X^T, X = tile rows as n
+template <bool H16>
 __device__ __forceinline__ void gemm_a_xt(float (&acc)[8][4], const uint32_t (&a)[4][4], const bf16* tile, int lane) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
@@ -93,26 +118,27 @@ __device__ __forceinline__ void gemm_a_xt(float (&acc)[8][4], const uint32_t (&a
     for (int np = 0; np < 4; ++np) {
       uint32_t b[4];
       load_b_nt(b, tile, np, ks, lane);
-      mma_bf16(acc[2 * np], a[ks], b[0], b[1]);
-      mma_bf16(acc[2 * np + 1], a[ks], b[2], b[3]);
+      mma_16<H16>(acc[2 * np], a[ks], b[0], b[1]);
+      mma_16<H16>(acc[2 * np + 1], a[ks], b[2], b[3]);
     }
   }
 }
 // acc[8][4] (16 x 64) += P(16 x 64, given as fp32 C-fragments, converted to bf16) * X, X = tile rows as k
+template <bool H16>
 __device__ __forceinline__ void gemm_p_x(float (&acc)[8][4], const float (&p)[8][4], const bf16* tile, int lane) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     uint32_t a[4];
-    a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
-    a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
-    a[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
-    a[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+    a[0] = pk<H16>(p[2 * ks][0], p[2 * ks][1]);
+    a[1] = pk<H16>(p[2 * ks][2], p[2 * ks][3]);
+    a[2] = pk<H16>(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+    a[3] = pk<H16>(p[2 * ks + 1][2], p[2 * ks + 1][3]);
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       uint32_t b[4];
       load_b_kn(b, tile, ks, np, lane);
-      mma_bf16(acc[2 * np], a, b[0], b[1]);
-      mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+      mma_16<H16>(acc[2 * np], a, b[0], b[1]);
+      mma_16<H16>(acc[2 * np + 1], a, b[2], b[3]);
     }
   }
 }
@@ -125,9 +151,9 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int out_fp16,
-                                                       bf16* __restrict__ out2, float* __restrict__ lse, int N, int H,
-                                                       float scale_log2) {
+template <bool H16>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                       float* __restrict__ lse, int N, int H, float scale_log2) {
   __shared__ __align__(128) bf16 sQ[TILE * DH];
   __shared__ __align__(128) bf16 sK[2][TILE * DH];
   __shared__ __align__(128) bf16 sV[2][TILE * DH];
@@ -164,7 +190,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 
     float s[8][4];
     zero_acc(s);
-    gemm_a_xt(s, qf, sK[buf], lane);
+    gemm_a_xt<H16>(s, qf, sK[buf], lane);
 
     // scale into log2 domain, mask keys >= N
     float mx[2] = {-INFINITY, -INFINITY};
@@ -206,7 +232,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
     for (int nt = 0; nt < 8; ++nt) {
       o[nt][0] *= corr[0]; o[nt][1] *= corr[0]; o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
     }
-    gemm_p_x(o, s, sV[buf], lane);
+    gemm_p_x<H16>(o, s, sV[buf], lane);
     __syncthreads();  // everyone done with buf before it is refilled two iterations later
   }
 
@@ -223,21 +249,14 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
     const long long ooff = ((long long)(b * N + q) * H + h) * DH;
     bf16* orow = out + ooff;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float v0 = o[nt][2 * r] * inv, v1 = o[nt][2 * r + 1] * inv;
-      if (out_fp16) {
-        __half2 hh = __floats2half2_rn(v0, v1);
-        *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = *reinterpret_cast<uint32_t*>(&hh);
-      } else {
-        *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = pack_bf16(v0, v1);
-      }
-      if (out2 != nullptr) *reinterpret_cast<uint32_t*>(out2 + ooff + nt * 8 + 2 * t) = pack_bf16(v0, v1);
-    }
+    for (int nt = 0; nt < 8; ++nt)
+      *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = pk<H16>(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
     if (t == 0) lse[((long long)b * H + h) * N + q] = m_run[r] * LN2 + logf(l_run[r]);
   }
 }
 
 // ------------------------------------------------------------------ backward: delta = rowsum(dO * O)
+template <bool H16>
 __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
                                   int B, int N, int H) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b, n, h)
@@ -246,7 +265,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   if (row >= total) return;
   const uint32_t a = *reinterpret_cast<const uint32_t*>(out + row * DH + lane * 2);
   const uint32_t d = *reinterpret_cast<const uint32_t*>(dout + row * DH + lane * 2);
-  const float2 af = unpack_bf16(a), df = unpack_bf16(d);
+  const float2 af = upk<H16>(a), df = upk<H16>(d);
   float v = warp_sum(af.x * df.x + af.y * df.y);
   if (lane == 0) {
     const int h = int(row % H);
@@ -268,6 +287,7 @@ struct BwdSmem {
   float delta[2][TILE];
 };
 
+template <bool H16>
 __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                             const float* __restrict__ lse, const float* __restrict__ delta,
                                                             bf16* __restrict__ dqkv, int N, int H, float scale,
@@ -323,7 +343,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
     // S^T (16 keys x 64 queries) = K_w Q^T
     float st[8][4];
     zero_acc(st);
-    gemm_a_xt(st, kf, sm.q[buf], lane);
+    gemm_a_xt<H16>(st, kf, sm.q[buf], lane);
     // P^T = exp(S^T*scale - lse[q])
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -335,11 +355,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
       }
     }
     // dV += P^T dO
-    gemm_p_x(dv, st, sm.d[buf], lane);
+    gemm_p_x<H16>(dv, st, sm.d[buf], lane);
     // dP^T = V_w dO^T
     float dp[8][4];
     zero_acc(dp);
-    gemm_a_xt(dp, vf, sm.d[buf], lane);
+    gemm_a_xt<H16>(dp, vf, sm.d[buf], lane);
     // dS^T = P^T * (dP^T - delta[q])
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
       }
     }
     // dK += dS^T Q
-    gemm_p_x(dk, dp, sm.q[buf], lane);
+    gemm_p_x<H16>(dk, dp, sm.q[buf], lane);
     __syncthreads();
   }
 
@@ -362,13 +382,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
     bf16* dvrow = dqkv + (((long long)(b * N + key) * 3 + 2) * H + h) * DH;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      *reinterpret_cast<uint32_t*>(dkrow + nt * 8 + 2 * t) = pack_bf16(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
-      *reinterpret_cast<uint32_t*>(dvrow + nt * 8 + 2 * t) = pack_bf16(dv[nt][2 * r], dv[nt][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(dkrow + nt * 8 + 2 * t) = pk<H16>(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
+      *reinterpret_cast<uint32_t*>(dvrow + nt * 8 + 2 * t) = pk<H16>(dv[nt][2 * r], dv[nt][2 * r + 1]);
     }
   }
 }
 
 // ------------------------------------------------------------------ backward: dQ
+template <bool H16>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                           const float* __restrict__ lse, const float* __restrict__ delta,
                                                           bf16* __restrict__ dqkv, int N, int H, float scale,
@@ -421,7 +442,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
     }
     float s[8][4];
     zero_acc(s);
-    gemm_a_xt(s, qf, sm.q[buf], lane);  // S = Q K^T
+    gemm_a_xt<H16>(s, qf, sm.q[buf], lane);  // S = Q K^T
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -432,13 +453,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
     }
     float dp[8][4];
     zero_acc(dp);
-    gemm_a_xt(dp, dof, sm.d[buf], lane);  // dP = dO V^T
+    gemm_a_xt<H16>(dp, dof, sm.d[buf], lane);  // dP = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) dp[nt][e] = s[nt][e] * (dp[nt][e] - del[e >> 1]);
     }
-    gemm_p_x(dq, dp, sm.q[buf], lane);  // dQ += dS K
+    gemm_p_x<H16>(dq, dp, sm.q[buf], lane);  // dQ += dS K
     __syncthreads();
   }
 
@@ -449,13 +470,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
     bf16* dqrow = dqkv + (((long long)(b * N + q) * 3 + 0) * H + h) * DH;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
-      *reinterpret_cast<uint32_t*>(dqrow + nt * 8 + 2 * t) = pack_bf16(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
+      *reinterpret_cast<uint32_t*>(dqrow + nt * 8 + 2 * t) = pk<H16>(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
   }
 }
 
 // ------------------------------------------------------------------ eval-only attention maps
 // probs[b,h,q,:] = softmax(q.k^T*scale) in fp32 -- the `attention_maps` the reference stores in
 // eval mode (vision_transformer_base.py:186-188).  One warp per (b,h,q) row; not on the train path.
+template <bool H16>
 __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restrict__ probs, int B, int N, int H, float scale) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b,h,q)
   const int lane = threadIdx.x & 31;
@@ -467,7 +489,7 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
   float qv[DH];
 #pragma unroll
   for (int d = 0; d < DH; d += 2) {
-    const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(qp + d));
+    const float2 f = upk<H16>(*reinterpret_cast<const uint32_t*>(qp + d));
     qv[d] = f.x; qv[d + 1] = f.y;
   }
   float* prow = probs + row * N;
@@ -478,7 +500,7 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 #pragma unroll
     for (int d = 0; d < DH; d += 8) {
       const uint4 u = ldg_u4(kp + d);
-      const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+      const float2 f0 = upk<H16>(u.x), f1 = upk<H16>(u.y), f2 = upk<H16>(u.z), f3 = upk<H16>(u.w);
       acc += qv[d] * f0.x + qv[d + 1] * f0.y + qv[d + 2] * f1.x + qv[d + 3] * f1.y + qv[d + 4] * f2.x +
              qv[d + 5] * f2.y + qv[d + 6] * f3.x + qv[d + 7] * f3.y;
     }
@@ -503,50 +525,64 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 
 using namespace vitk;
 
-extern "C" int vitk_attention_fwd(const void* qkv, void* out, int32_t out_dtype, void* out2_bf16, float* lse, float* probs,
-                                  int32_t B, int32_t N, int32_t H, float scale, void* stream) {
-  VITK_CHECK_ARG(qkv && out && lse, "vitk_attention_fwd: null pointer");
-  VITK_CHECK_ARG(out_dtype == VITK_BF16 || out_dtype == VITK_FP16, "vitk_attention_fwd: out must be bf16 or fp16");
-  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_fwd: bad shape B=%d N=%d H=%d", B, N, H);
-  VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_fwd: grid limit");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+template <bool H16>
+static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* probs, int B, int N, int H, float scale,
+                              cudaStream_t st) {
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  attn_fwd_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out),
-                                        int(out_dtype == VITK_FP16), reinterpret_cast<bf16*>(out2_bf16), lse, N, H,
-                                        scale * LOG2E);
+  attn_fwd_kernel<H16><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse, N, H,
+                                             scale * LOG2E);
   VITK_LAUNCH_CHECK();
   if (probs != nullptr) {
     const long long rows = (long long)B * H * N;
-    attn_probs_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), probs, B, N, H, scale);
+    attn_probs_kernel<H16><<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), probs, B, N, H, scale);
     VITK_LAUNCH_CHECK();
   }
   return VITK_OK;
 }
 
-extern "C" int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
-                                  void* dqkv, int32_t B, int32_t N, int32_t H, float scale, void* stream) {
-  VITK_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "vitk_attention_bwd: null pointer");
-  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_bwd: bad shape B=%d N=%d H=%d", B, N, H);
-  VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_bwd: grid limit");
+extern "C" int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, float* lse, float* probs, int32_t B, int32_t N,
+                                  int32_t H, float scale, void* stream) {
+  VITK_CHECK_ARG(qkv && out && lse, "vitk_attention_fwd: null pointer");
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_fwd: dtype must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_fwd: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_fwd: grid limit");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == VITK_FP16 ? attention_fwd_impl<true>(qkv, out, lse, probs, B, N, H, scale, st)
+                            : attention_fwd_impl<false>(qkv, out, lse, probs, B, N, H, scale, st);
+}
+
+template <bool H16>
+static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                              int B, int N, int H, float scale, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
     configured = true;
   }
   const long long rows = (long long)B * N * H;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
-                                                                reinterpret_cast<const bf16*>(dout), delta, B, N, H);
+  attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
+                                                                     reinterpret_cast<const bf16*>(dout), delta, B, N, H);
   VITK_LAUNCH_CHECK();
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  attn_bwd_dkdv_kernel<<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
-                                                           reinterpret_cast<const bf16*>(dout), lse, delta,
-                                                           reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E);
+  attn_bwd_dkdv_kernel<H16><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                                reinterpret_cast<const bf16*>(dout), lse, delta,
+                                                                reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E);
   VITK_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
-                                                         reinterpret_cast<const bf16*>(dout), lse, delta,
-                                                         reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E);
+  attn_bwd_dq_kernel<H16><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                              reinterpret_cast<const bf16*>(dout), lse, delta,
+                                                              reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
+}
+
+extern "C" int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                                  void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H, float scale, void* stream) {
+  VITK_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "vitk_attention_bwd: null pointer");
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_bwd: dtype must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_bwd: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_bwd: grid limit");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == VITK_FP16 ? attention_bwd_impl<true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st)
+                            : attention_bwd_impl<false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st);
 }

@@ -18,10 +18,6 @@ inline int capped_grid(long long work_items, int threads, int ctas_per_sm) {
 }
 
 // ------------------------------------------------------------------ fp32 -> bf16
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 __global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, __half* __restrict__ dsth, long long n) {
   const long long n8 = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -42,8 +38,9 @@ __global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ ds
 
 // ------------------------------------------------------------------ column sums of a bf16 matrix
 // block = 32 column-vectors (8 bf16 each) x 8 row lanes; grid.x = column chunk, grid.y = row slab
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long rows,
-                                                     int dim, int rows_per_block) {
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int fp16, float* __restrict__ out,
+                                                     const float* __restrict__ unscale, long long rows, int dim,
+                                                     int rows_per_block) {
   __shared__ float red[8][32][8];
   const int cv = blockIdx.x * 32 + threadIdx.x;  // column vector index
   const int col = cv * 8;
@@ -55,7 +52,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   if (col < dim) {
     for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
       const uint4 u = ldg_u4(x + r * dim + col);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      const float2 a = unpack16(u.x, fp16), b = unpack16(u.y, fp16), c = unpack16(u.z, fp16), d = unpack16(u.w, fp16);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
       acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
     }
@@ -64,19 +61,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
   __syncthreads();
   if (threadIdx.y == 0 && col < dim) {
+    const float u = unscale != nullptr ? __ldg(unscale) : 1.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float s = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][j];
-      atomicAdd(out + col + j, s);
+      atomicAdd(out + col + j, s * u);
     }
   }
 }
 
 // ------------------------------------------------------------------ patch gather (fp32 NCHW -> bf16 [B*gh*gw, C*P*P])
-__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int fp16, bf16* __restrict__ patches2,
-                                int B, int C, int H, int W, int P) {
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int fp16, int B, int C, int H, int W,
+                                int P) {
   const int wv = W >> 3;
   const long long total = (long long)B * C * H * wv;
   const int gw = W / P, gh = H / P;
@@ -94,13 +92,8 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
     const int x = xv * 8;
     const int py = y / P, ky = y - py * P, px = x / P, kx = x - px * P;
     const long long doff = ((long long)(b * gh + py) * gw + px) * Kdim + c * P * P + ky * P + kx;
-    const uint4 vb = make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
-    if (fp16)
-      *reinterpret_cast<uint4*>(patches + doff) =
-          make_uint4(pack_f16(a0.x, a0.y), pack_f16(a0.z, a0.w), pack_f16(a1.x, a1.y), pack_f16(a1.z, a1.w));
-    else
-      *reinterpret_cast<uint4*>(patches + doff) = vb;
-    if (patches2 != nullptr) *reinterpret_cast<uint4*>(patches2 + doff) = vb;
+    *reinterpret_cast<uint4*>(patches + doff) = make_uint4(pack16(a0.x, a0.y, fp16), pack16(a0.z, a0.w, fp16),
+                                                           pack16(a1.x, a1.y, fp16), pack16(a1.z, a1.w, fp16));
   }
 }
 
@@ -124,8 +117,9 @@ __global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restr
 // grid (T, ceil(B/IMGS)); blockDim = dim/4 threads (one float4 column each)
 constexpr int TOK_IMGS = 32;
 __global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, float* __restrict__ dcls,
-                                  float* __restrict__ ddist, bf16* __restrict__ dpatch, float* __restrict__ dbias, int B, int T,
-                                  int dim, int n_prefix) {
+                                  float* __restrict__ ddist, bf16* __restrict__ dpatch, int fp16, float* __restrict__ dbias,
+                                  const float* __restrict__ unscale, int B, int T, int dim, int n_prefix) {
+  const float u = unscale != nullptr ? __ldg(unscale) : 1.f;
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * TOK_IMGS;
   const int b1 = min(B, b0 + TOK_IMGS);
@@ -137,8 +131,9 @@ __global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restric
       acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
       if (t >= n_prefix && dpatch != nullptr)
         *reinterpret_cast<uint2*>(dpatch + ((long long)b * rows_per_img + (t - n_prefix)) * dim + 4 * v) =
-            make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+            make_uint2(pack16(g.x, g.y, fp16), pack16(g.z, g.w, fp16));
     }
+    acc.x *= u; acc.y *= u; acc.z *= u; acc.w *= u;
     if (dpos != nullptr) {
       float* p = dpos + (long long)t * dim + 4 * v;
       atomicAdd(p, acc.x); atomicAdd(p + 1, acc.y); atomicAdd(p + 2, acc.z); atomicAdd(p + 3, acc.w);
@@ -192,10 +187,11 @@ __global__ void head_fwd_kernel(const float* __restrict__ x, const float* __rest
 
 __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __restrict__ dl1, const float* __restrict__ xhat,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ W0,
-                                const float* __restrict__ W1, float* __restrict__ dx, bf16* __restrict__ dx_bf16,
+                                const float* __restrict__ W1, float* __restrict__ dx, bf16* __restrict__ dx16, int fp16,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db0,
-                                float* __restrict__ db1, float* __restrict__ dcolsum, int B, int T, int dim, int C,
-                                int n_heads) {
+                                float* __restrict__ db1, float* __restrict__ dcolsum, const float* __restrict__ loss_scale,
+                                int B, int T, int dim, int C, int n_heads) {
+  const float S = loss_scale != nullptr ? __ldg(loss_scale) : 1.f;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * n_heads) return;
@@ -223,8 +219,11 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __re
     for (int c = 0; c < C; ++c) dxn += dl[c] * W[(long long)c * dim + i];
     const float g = dxn * gamma[i];
     const float o = rs * (g - m1 - xh[i] * m2);
-    dxr[i] = o;
-    if (dx_bf16 != nullptr) dx_bf16[((long long)b * T + hd) * dim + i] = __float2bfloat16(o);
+    dxr[i] = o * S;
+    if (dx16 != nullptr) {
+      if (fp16) reinterpret_cast<__half*>(dx16)[((long long)b * T + hd) * dim + i] = __float2half_rn(o * S);
+      else dx16[((long long)b * T + hd) * dim + i] = __float2bfloat16(o * S);
+    }
     if (dcolsum != nullptr) atomicAdd(dcolsum + i, o);
   }
   if (dbh != nullptr)
@@ -340,8 +339,10 @@ extern "C" int vitk_cast_f32_to_16(const float* src, void* dst_bf16, void* dst_f
   return VITK_OK;
 }
 
-extern "C" int vitk_colsum_bf16(const void* x, float* out, int64_t rows, int32_t dim, void* stream) {
-  VITK_CHECK_ARG(x && out && rows > 0 && dim > 0 && dim % 8 == 0, "vitk_colsum_bf16: dim=%d must be a multiple of 8", dim);
+extern "C" int vitk_colsum16(const void* x, int32_t dtype, float* out, const float* grad_unscale, int64_t rows, int32_t dim,
+                             void* stream) {
+  VITK_CHECK_ARG(x && out && rows > 0 && dim > 0 && dim % 8 == 0, "vitk_colsum16: dim=%d must be a multiple of 8", dim);
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_colsum16: dtype must be bf16 or fp16");
   const int col_chunks = (dim / 8 + 31) / 32;
   // aim for ~4 CTAs per SM in total
   int slabs = (num_sms() * 4 + col_chunks - 1) / col_chunks;
@@ -349,21 +350,21 @@ extern "C" int vitk_colsum_bf16(const void* x, float* out, int64_t rows, int32_t
   if (slabs < 1) slabs = 1;
   const int rpb = (int)((rows + slabs - 1) / slabs);
   dim3 grid(col_chunks, (unsigned)((rows + rpb - 1) / rpb));
-  colsum_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), out, rows, dim, rpb);
+  colsum_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), int(dtype == VITK_FP16), out, grad_unscale, rows, dim, rpb);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
-extern "C" int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, void* patches2_bf16, int32_t B,
-                             int32_t C, int32_t H, int32_t W, int32_t P, void* stream) {
+extern "C" int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, int32_t B, int32_t C, int32_t H,
+                             int32_t W, int32_t P, void* stream) {
   VITK_CHECK_ARG(images && patches, "vitk_patchify: null pointer");
   VITK_CHECK_ARG(patches_dtype == VITK_BF16 || patches_dtype == VITK_FP16, "vitk_patchify: patches must be bf16 or fp16");
   VITK_CHECK_ARG(B > 0 && C > 0 && P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0,
                  "vitk_patchify: need P %% 8 == 0 and H, W divisible by P (B=%d C=%d H=%d W=%d P=%d)", B, C, H, W, P);
   const long long total = (long long)B * C * H * (W / 8);
   patchify_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      images, reinterpret_cast<bf16*>(patches), int(patches_dtype == VITK_FP16), reinterpret_cast<bf16*>(patches2_bf16), B, C, H,
-      W, P);
+      images, reinterpret_cast<bf16*>(patches), int(patches_dtype == VITK_FP16), B, C, H, W, P);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -380,15 +381,17 @@ extern "C" int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const floa
   return VITK_OK;
 }
 
-extern "C" int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch_bf16, float* dbias_patch,
-                               int32_t B, int32_t T, int32_t dim, int32_t n_prefix, void* stream) {
+extern "C" int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch16, int32_t dpatch_dtype,
+                               float* dbias_patch, const float* grad_unscale, int32_t B, int32_t T, int32_t dim,
+                               int32_t n_prefix, void* stream) {
   VITK_CHECK_ARG(dx && dim % 4 == 0 && n_prefix >= 0 && n_prefix <= 2 && T > n_prefix, "vitk_tokens_bwd: bad args");
   int threads = dim / 4;
   if (threads > 256) threads = 256;
   threads = ((threads + 31) / 32) * 32;
   dim3 grid(T, (B + TOK_IMGS - 1) / TOK_IMGS);
   tokens_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      dx, dpos, dcls, ddist, reinterpret_cast<bf16*>(dpatch_bf16), dbias_patch, B, T, dim, n_prefix);
+      dx, dpos, dcls, ddist, reinterpret_cast<bf16*>(dpatch16), int(dpatch_dtype == VITK_FP16), dbias_patch, grad_unscale, B, T,
+      dim, n_prefix);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -408,17 +411,18 @@ extern "C" int vitk_head_fwd(const float* x, const float* gamma, const float* be
 
 extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat, const float* rstd,
                              const float* gamma, const float* beta, const float* W0, const float* W1, float* dx,
-                             void* dx_bf16, float* dgamma, float* dbeta, float* dW0, float* db0, float* dW1, float* db1,
-                             float* dcolsum, int32_t B, int32_t T, int32_t dim, int32_t C, int32_t n_heads, void* stream) {
+                             void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta, float* dW0, float* db0, float* dW1,
+                             float* db1, float* dcolsum, const float* loss_scale, int32_t B, int32_t T, int32_t dim, int32_t C,
+                             int32_t n_heads, void* stream) {
   VITK_CHECK_ARG(dlogits0 && xhat && rstd && gamma && beta && W0 && dx && dgamma && dbeta && dW0, "vitk_head_bwd: null pointer");
   VITK_CHECK_ARG(n_heads == 1 || (n_heads == 2 && dlogits1 && W1 && dW1), "vitk_head_bwd: n_heads must be 1 or 2");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VITK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * T * dim * sizeof(float), st));
-  if (dx_bf16 != nullptr) VITK_CUDA(cudaMemsetAsync(dx_bf16, 0, (size_t)B * T * dim * 2, st));
+  if (dx16 != nullptr) VITK_CUDA(cudaMemsetAsync(dx16, 0, (size_t)B * T * dim * 2, st));
   const int warps = B * n_heads;
   head_bwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(dlogits0, dlogits1, xhat, rstd, gamma, W0, W1, dx,
-                                                   reinterpret_cast<bf16*>(dx_bf16), dgamma, dbeta, db0, db1, dcolsum, B, T,
-                                                   dim, C, n_heads);
+                                                   reinterpret_cast<bf16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, db0,
+                                                   db1, dcolsum, loss_scale, B, T, dim, C, n_heads);
   VITK_LAUNCH_CHECK();
   const long long total = (long long)n_heads * C * dim;
   head_wgrad_kernel<<<capped_grid(total, 128, 4), 128, 0, st>>>(dlogits0, dlogits1, xhat, gamma, beta, dW0, dW1, B, dim, C,

@@ -36,6 +36,7 @@ struct GemmParams {
   int epilogue, out_dtype, aux_dtype;
   uint32_t idesc;
   float alpha;
+  const float* alpha_dev;
   const float* bias;
   const float* residual;
   long long ldr;
@@ -43,7 +44,6 @@ struct GemmParams {
   long long ldo;
   void* out2;
   long long ldo2;
-  void* out3;
   const void* aux;
   long long ldaux;
   int rows_per_img, tokens_per_img, prefix;
@@ -161,19 +161,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 inline uint32_t make_idesc(int bn, bool a_mn, bool b_mn, bool a_fp16, bool b_fp16) {
   return (1u << 4) | (uint32_t(a_fp16 ? 0 : 1) << 7) | (uint32_t(b_fp16 ? 0 : 1) << 10) | (uint32_t(a_mn) << 15) |
          (uint32_t(b_mn) << 16) | (uint32_t(bn >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
-}
-
-// 16-bit packing in the output element type
-__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool fp16) {
-  if (fp16) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  return pack_bf16(lo, hi);
-}
-__device__ __forceinline__ float2 unpack16(uint32_t u, bool fp16) {
-  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&u));
-  return unpack_bf16(u);
 }
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -308,8 +295,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
       if (!row_ok) continue;
       float f[32];
+      const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
       if (p.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -370,9 +358,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               for (int t = 0; t < 8; ++t) g[t] = gelu_erf(f[j + t]);
               st_global_v4(o2 + j, pack16(g[0], g[1], h), pack16(g[2], g[3], h), pack16(g[4], g[5], h),
                            pack16(g[6], g[7], h));
-              if (p.out3 != nullptr)
-                st_global_v4(reinterpret_cast<__nv_bfloat16*>(p.out3) + orow * p.ldo2 + col0 + j, pack_bf16(g[0], g[1]),
-                             pack_bf16(g[2], g[3]), pack_bf16(g[4], g[5]), pack_bf16(g[6], g[7]));
             }
           }
         } break;
@@ -507,21 +492,24 @@ int pick_bn(int N) {
 
 using namespace vitk;
 
-extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream) {
-  VITK_CHECK_ARG(a != nullptr, "vitk_gemm_bf16: null args");
-  VITK_CHECK_ARG(a->A && a->B && a->out, "vitk_gemm_bf16: null operand");
-  VITK_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "vitk_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
-  VITK_CHECK_ARG(a->N % 8 == 0, "vitk_gemm_bf16: N=%d must be a multiple of 8", a->N);
-  VITK_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vitk_gemm_bf16: lda/ldb must be multiples of 8 (16-byte TMA pitch)");
+extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
+  VITK_CHECK_ARG(a != nullptr, "vitk_gemm: null args");
+  VITK_CHECK_ARG(a->A && a->B && a->out, "vitk_gemm: null operand");
+  VITK_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "vitk_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  VITK_CHECK_ARG(a->N % 8 == 0, "vitk_gemm: N=%d must be a multiple of 8", a->N);
+  VITK_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vitk_gemm: lda/ldb must be multiples of 8 (16-byte TMA pitch)");
   VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
-                 "vitk_gemm_bf16: operands must be 16-byte aligned");
-  VITK_CHECK_ARG(a->split_k >= 1, "vitk_gemm_bf16: split_k must be >= 1");
+                 "vitk_gemm: operands must be 16-byte aligned");
+  VITK_CHECK_ARG(a->split_k >= 1, "vitk_gemm: split_k must be >= 1");
   VITK_CHECK_ARG(a->split_k == 1 || a->epilogue == VITK_EPI_ATOMIC_ADD,
-                 "vitk_gemm_bf16: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
-  VITK_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= VITK_EPI_TOKENS, "vitk_gemm_bf16: bad epilogue %d", a->epilogue);
-  VITK_CHECK_ARG(a->out_dtype >= VITK_BF16 && a->out_dtype <= VITK_FP16, "vitk_gemm_bf16: bad out_dtype %d", a->out_dtype);
+                 "vitk_gemm: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
+  VITK_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= VITK_EPI_TOKENS, "vitk_gemm: bad epilogue %d", a->epilogue);
+  VITK_CHECK_ARG(a->out_dtype >= VITK_BF16 && a->out_dtype <= VITK_FP16, "vitk_gemm: bad out_dtype %d", a->out_dtype);
   VITK_CHECK_ARG((a->a_dtype == VITK_BF16 || a->a_dtype == VITK_FP16) && (a->b_dtype == VITK_BF16 || a->b_dtype == VITK_FP16),
-                 "vitk_gemm_bf16: operands must be bf16 or fp16");
+                 "vitk_gemm: operands must be bf16 or fp16");
+  VITK_CHECK_ARG(a->a_dtype == a->b_dtype,
+                 "vitk_gemm: A and B must share one element type (tcgen05 kind::f16 with mixed fp16/bf16 operands is an "
+                 "illegal instruction on sm_100a)");
   const bool out_fp32 = a->out_dtype == VITK_FP32;
   if (a->epilogue == VITK_EPI_GELU) VITK_CHECK_ARG(a->out2 != nullptr && !out_fp32, "GELU epilogue needs 16-bit out and out2");
   if (a->epilogue == VITK_EPI_DGELU)
@@ -532,7 +520,7 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream) {
     VITK_CHECK_ARG(a->pos != nullptr && a->rows_per_img > 0 && a->tokens_per_img >= a->rows_per_img + a->prefix,
                    "TOKENS epilogue needs pos / rows_per_img / tokens_per_img");
   const int vec = out_fp32 ? 4 : 8;
-  VITK_CHECK_ARG(a->ldo % vec == 0, "vitk_gemm_bf16: ldo must keep rows 16-byte aligned");
+  VITK_CHECK_ARG(a->ldo % vec == 0, "vitk_gemm: ldo must keep rows 16-byte aligned");
 
   const int bn = pick_bn(a->N);
   const int num_kblocks = (a->K + BLOCK_K - 1) / BLOCK_K;
@@ -545,9 +533,9 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream) {
   p.kblocks_per_split = kpb;
   p.epilogue = a->epilogue; p.out_dtype = a->out_dtype; p.aux_dtype = a->aux_dtype;
   p.idesc = make_idesc(bn, a->a_mn_major != 0, a->b_mn_major != 0, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16);
-  p.alpha = a->alpha;
+  p.alpha = a->alpha; p.alpha_dev = a->alpha_dev;
   p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr;
-  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2; p.out3 = a->out3;
+  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.aux = a->aux; p.ldaux = a->ldaux;
   p.rows_per_img = a->rows_per_img; p.tokens_per_img = a->tokens_per_img; p.prefix = a->prefix; p.pos = a->pos;
 

@@ -21,7 +21,7 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
                                                                __nv_bfloat16* __restrict__ y, int y_fp16,
-                                                               __nv_bfloat16* __restrict__ y2, float* __restrict__ mean,
+                                                               float* __restrict__ mean,
                                                                float* __restrict__ rstd, long long rows, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int nvec = dim >> 2;
@@ -64,13 +64,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
         const float b = (v[c].y - mu) * rs * gm[c].y + bt[c].y;
         const float cc = (v[c].z - mu) * rs * gm[c].z + bt[c].z;
         const float d = (v[c].w - mu) * rs * gm[c].w + bt[c].w;
-        if (y_fp16) {
-          __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(cc, d);
-          *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        } else {
-          *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(pack_bf16(a, b), pack_bf16(cc, d));
-        }
-        if (y2 != nullptr) *reinterpret_cast<uint2*>(y2 + row * dim + 4 * i) = make_uint2(pack_bf16(a, b), pack_bf16(cc, d));
+        *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(pack16(a, b, y_fp16), pack16(cc, d, y_fp16));
       }
     }
     if (lane == 0) {
@@ -82,10 +76,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
 
 template <int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-    ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
-                  float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta, float* __restrict__ dcolsum, long long rows, int dim) {
+                  float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, int dx_fp16, float* __restrict__ dgamma,
+                  float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale, long long rows,
+                  int dim) {
   extern __shared__ float red[];  // [3][dim]
   const int lane = threadIdx.x & 31;
   const int nvec = dim >> 2;
@@ -113,7 +108,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
       if (i < nvec) {
         const float4 xv = ldg_f4(xr + 4 * i);
         const uint2 dyu = ldg_u2(dyr + 4 * i);
-        const float2 d01 = unpack_bf16(dyu.x), d23 = unpack_bf16(dyu.y);
+        const float2 d01 = unpack16(dyu.x, dy_fp16), d23 = unpack16(dyu.y, dy_fp16);
         xh[c] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         g[c] = make_float4(d01.x * gm[c].x, d01.y * gm[c].y, d23.x * gm[c].z, d23.y * gm[c].w);
         dg[c].x += d01.x * xh[c].x; dg[c].y += d01.y * xh[c].y; dg[c].z += d23.x * xh[c].z; dg[c].w += d23.y * xh[c].w;
@@ -139,7 +134,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
         }
         *reinterpret_cast<float4*>(dxr + 4 * i) = o;
         if (dx_bf16 != nullptr)
-          *reinterpret_cast<uint2*>(dx_bf16 + row * dim + 4 * i) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+          *reinterpret_cast<uint2*>(dx_bf16 + row * dim + 4 * i) = make_uint2(pack16(o.x, o.y, dx_fp16), pack16(o.z, o.w, dx_fp16));
         dc[c].x += o.x; dc[c].y += o.y; dc[c].z += o.z; dc[c].w += o.w;
       }
     }
@@ -160,10 +155,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     }
   }
   __syncthreads();
+  const float u = unscale != nullptr ? __ldg(unscale) : 1.f;
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[dim + i]);
-    if (dcolsum != nullptr) atomicAdd(dcolsum + i, red[2 * dim + i]);
+    atomicAdd(dgamma + i, red[i] * u);
+    atomicAdd(dbeta + i, red[dim + i] * u);
+    if (dcolsum != nullptr) atomicAdd(dcolsum + i, red[2 * dim + i] * u);
   }
 }
 
@@ -198,24 +194,25 @@ static int ln_chunks(int dim) {
 }
 
 extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
-                                  void* y2_bf16, float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
-                                  void* stream) {
+                                  float* mean, float* rstd, int64_t rows, int32_t dim, float eps, void* stream) {
   VITK_CHECK_ARG(x && gamma && beta && y && mean && rstd, "vitk_layernorm_fwd: null pointer");
   VITK_CHECK_ARG(y_dtype == VITK_BF16 || y_dtype == VITK_FP16, "vitk_layernorm_fwd: y must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_fwd: dim=%d must be a multiple of 4, <= 1024", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ch = ln_chunks(dim);
   LN_DISPATCH(ch, ln_fwd_kernel<C_><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(
-                      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16),
-                      reinterpret_cast<__nv_bfloat16*>(y2_bf16), mean, rstd, rows, dim, eps));
+                      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, rows, dim, eps));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
-extern "C" int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
-                                  const float* gamma, const float* dres, float* dx, void* dx_bf16, float* dgamma,
-                                  float* dbeta, float* dcolsum, int64_t rows, int32_t dim, void* stream) {
-  VITK_CHECK_ARG(dy_bf16 && x && mean && rstd && gamma && dx && dgamma && dbeta, "vitk_layernorm_bwd: null pointer");
+extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, const float* dres, float* dx, void* dx16, int32_t dx16_dtype,
+                                  float* dgamma, float* dbeta, float* dcolsum, const float* grad_unscale, int64_t rows,
+                                  int32_t dim, void* stream) {
+  VITK_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "vitk_layernorm_bwd: null pointer");
+  VITK_CHECK_ARG((dy_dtype == VITK_BF16 || dy_dtype == VITK_FP16) && (dx16_dtype == VITK_BF16 || dx16_dtype == VITK_FP16),
+                 "vitk_layernorm_bwd: dy / dx16 must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_bwd: dim=%d must be a multiple of 4, <= 1024", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int ch = ln_chunks(dim);
@@ -226,8 +223,9 @@ extern "C" int vitk_layernorm_bwd(const void* dy_bf16, const float* x, const flo
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   LN_DISPATCH(ch, ln_bwd_kernel<C_><<<(int)blocks, LN_WARPS * 32, smem, st>>>(
-                      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), x, mean, rstd, gamma, dres, dx,
-                      reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dcolsum, rows, dim));
+                      reinterpret_cast<const __nv_bfloat16*>(dy), int(dy_dtype == VITK_FP16), x, mean, rstd, gamma, dres, dx,
+                      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum,
+                      grad_unscale, rows, dim));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

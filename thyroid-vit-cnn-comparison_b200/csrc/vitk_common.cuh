@@ -81,6 +81,17 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 16-bit pair in the runtime-selected element type (fp16 or bf16)
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool fp16) { return fp16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+__device__ __forceinline__ float2 unpack16(uint32_t u, bool fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return unpack_bf16(u);
+}
+
 // exact (erf) GELU, as nn.GELU() default (vision_transformer_base.py:212-219)
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));

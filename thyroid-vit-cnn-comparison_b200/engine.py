@@ -9,17 +9,20 @@ vision_transformer_base.py:120-143,174-195,217-223,282-285,440-486) and their au
 Memory layout in HBM (per rank)
   flat_params   fp32 [P]   all trainable tensors, each padded to 128 elements, in REVERSE execution order
                             (heads, norm, blocks L-1..0, patch/pos/cls) so gradient buckets complete in order
-  flat_grads    fp32 [P]   same offsets; kernels ACCUMULATE into it (split-K red.add, column-sum atomics)
-  flat_fp16     fp16 [P]   forward tensor-core shadow of flat_params  } both written by the AdamW kernel
-  flat_bf16     bf16 [P]   backward (dgrad) tensor-core shadow         } (or the cast kernel)
+  flat_grads    fp32 [P]   same offsets, TRUE (unscaled) gradients; kernels ACCUMULATE into it
+                            (split-K red.add, column-sum atomics)
+  flat_16       fp16 [P]   tensor-core shadow of flat_params (written by the AdamW kernel / cast kernel)
   residual x    fp32 [B*T, D] per block boundary (2L+1 buffers, saved for backward)
-  activations   fp16 GEMM inputs of the forward (LN outputs, attention out, GELU out, patches) with a bf16 twin
-                saved for backward's wgrad; qkv [B,T,3,H,64] bf16; fc1 pre-activation fp16
+  activations   fp16: LN outputs, qkv [B,T,3,H,64], attention out [B,T,H,64], fc1 pre/post GELU [B*T,4D], patches
+  amp_state     fp32 [8]   {S, 1/S, good_steps, skipped, overflowed, ...}: dynamic loss scale, device resident
 
-Operand formats: tcgen05 kind::f16 cannot mix fp16 and bf16 in one MMA (probed on B200: illegal instruction).
-Forward GEMMs run fp16 x fp16 -- 11-bit significands are what keeps the logits inside the 2e-3 parity bound
-(pure bf16 measured 1.1e-3 rms / 2.8e-3 max at B=32) -- while every gradient tensor is bf16 (fp32 exponent range,
-no loss scaling), so backward GEMMs run bf16 x bf16 against the bf16 twins.  Accumulation is always fp32.
+Numerics.  tcgen05 kind::f16 cannot mix fp16 with bf16 operands in one MMA (probed on B200: illegal
+instruction) and pure bf16 operands miss BASELINE.json's parity bounds (measured: logits 1.1e-3 rms / 2.8e-3
+max at B=32, gradients 0.6-1.7 % rel-L2).  So every tensor-core operand is fp16 (11-bit significand), with
+fp32 accumulation, fp32 LN/softmax statistics, an fp32 residual stream and fp32 master weights; activation
+GRADIENTS are stored as fp16 times a dynamic loss scale S (GradScaler semantics, bookkeeping on the device),
+and every kernel that emits a parameter gradient multiplies by 1/S on the fly.  `dtype=torch.bfloat16` is
+kept as a constructor option (S fixed at 1).
 """
 from __future__ import annotations
 
@@ -31,7 +34,7 @@ import torch
 
 from . import _lib, ops
 
-PAD = 128  # every tensor starts on a 128-element boundary (512 B fp32 / 256 B bf16: TMA + 128-bit safe)
+PAD = 128  # every tensor starts on a 128-element boundary (512 B fp32 / 256 B 16-bit: TMA + 128-bit safe)
 
 
 @dataclass
@@ -72,9 +75,9 @@ def execution_order(names: List[str], depth: int) -> List[str]:
 
 
 class FlatParams:
-    """One fp32 buffer for all trainable tensors + same-shape gradient and bf16 shadow buffers."""
+    """One fp32 buffer for all trainable tensors + same-layout gradient and 16-bit shadow buffers."""
 
-    def __init__(self, named: "OrderedDict[str, torch.Tensor]", depth: int, device):
+    def __init__(self, named: "OrderedDict[str, torch.Tensor]", depth: int, device, dtype16=torch.float16):
         order = execution_order(list(named), depth)
         self.offsets: Dict[str, Tuple[int, torch.Size]] = {}
         total = 0
@@ -83,11 +86,10 @@ class FlatParams:
             total += (named[n].numel() + PAD - 1) // PAD * PAD
         self.numel = total
         self.order = order
+        self.dtype16 = dtype16
         self.params = torch.zeros(total, dtype=torch.float32, device=device)
         self.grads = torch.zeros(total, dtype=torch.float32, device=device)
-        self.bf16 = torch.zeros(total, dtype=torch.bfloat16, device=device)
-        self.fp16 = torch.zeros(total, dtype=torch.float16, device=device)
-        self._shadow_version = -1
+        self.w16 = torch.zeros(total, dtype=dtype16, device=device)
         for n in order:
             self.view(self.params, n).copy_(named[n].detach().to(device=device, dtype=torch.float32))
 
@@ -96,8 +98,11 @@ class FlatParams:
         return buf[off:off + shape.numel()].view(shape)
 
     def refresh_shadow(self) -> None:
-        """flat_params -> fp16 + bf16 shadows (one vectorised cast kernel over the whole buffer)."""
-        ops.cast_shadows(self.params, self.bf16, self.fp16)
+        """flat_params -> 16-bit shadow (one vectorised cast kernel over the whole buffer)."""
+        if self.dtype16 == torch.float16:
+            ops.cast_fp16(self.params, self.w16)
+        else:
+            ops.cast_bf16(self.params, self.w16)
 
     def bucket_slices(self, bucket_bytes: int) -> List[Tuple[int, int]]:
         """Contiguous [start, end) element ranges of ~bucket_bytes, cut at tensor boundaries, in
@@ -118,33 +123,27 @@ class FlatParams:
 class Workspace:
     """Activation + scratch buffers for one (batch, training?) shape; allocated once, reused every step."""
 
-    def __init__(self, d: Dims, B: int, train: bool, device):
+    def __init__(self, d: Dims, B: int, train: bool, device, dt16):
         self.B, self.train = B, train
         T, D, H = d.tokens, d.dim, d.heads
         M = B * T
-        f32, b16, h16 = torch.float32, torch.bfloat16, torch.float16
-        e = lambda *s, dt=b16: torch.empty(*s, dtype=dt, device=device)
+        f32 = torch.float32
+        e = lambda *s, dt=dt16: torch.empty(*s, dtype=dt, device=device)
         L = d.depth if train else 1
-        self.patches = e(B * d.n_patches, d.kpatch, dt=h16)
-        self.patches_b = e(B * d.n_patches, d.kpatch) if train else None
+        self.patches = e(B * d.n_patches, d.kpatch)
         nres = 2 * d.depth + 1 if train else 3
         self.x = [e(M, D, dt=f32) for _ in range(nres)]
-        self.xn1 = [e(M, D, dt=h16) for _ in range(L)]
-        self.xn2 = [e(M, D, dt=h16) for _ in range(L)]
-        # bf16 twins of the forward GEMM inputs: what backward's wgrad GEMMs read
-        self.xn1_b = [e(M, D) for _ in range(L)] if train else [None]
-        self.xn2_b = [e(M, D) for _ in range(L)] if train else [None]
-        self.ao_b = [e(M, D) for _ in range(L)] if train else [None]
-        self.act_b = [e(M, d.hidden) for _ in range(L)] if train else [None]
+        self.xn1 = [e(M, D) for _ in range(L)]
+        self.xn2 = [e(M, D) for _ in range(L)]
         self.stats = [e(4, M, dt=f32) for _ in range(L)]          # mean1, rstd1, mean2, rstd2
         self.qkv = [e(M, 3 * D) for _ in range(L)]
-        self.ao = [e(M, D, dt=h16) for _ in range(L)]
+        self.ao = [e(M, D) for _ in range(L)]
         self.lse = [e(B, H, T, dt=f32) for _ in range(L)]
-        self.pre = [e(M, d.hidden, dt=h16) for _ in range(L)]
-        self.act = [e(M, d.hidden, dt=h16) for _ in range(L)]
+        self.pre = [e(M, d.hidden) for _ in range(L)]
+        self.act = [e(M, d.hidden) for _ in range(L)]
         if train:
             self.dx = [e(M, D, dt=f32) for _ in range(2)]
-            self.dxb = e(M, D)
+            self.dx16 = e(M, D)
             self.dxn = e(M, D)
             self.d_ao = e(M, D)
             self.d_pre = e(M, d.hidden)
@@ -153,11 +152,22 @@ class Workspace:
             self.dpatch = e(B * d.n_patches, D)
         self.head_saved = None
 
+    def nbytes(self) -> int:
+        tot = 0
+        for v in self.__dict__.values():
+            for t in (v if isinstance(v, list) else [v]):
+                if isinstance(t, torch.Tensor):
+                    tot += t.numel() * t.element_size()
+        return tot
+
 
 class VitEngine:
     """Forward / backward of the whole encoder for one model instance."""
 
-    def __init__(self, dims: Dims, named_params: "OrderedDict[str, torch.Tensor]", device):
+    INIT_LOSS_SCALE = 65536.0
+    GROWTH_INTERVAL = 2000
+
+    def __init__(self, dims: Dims, named_params: "OrderedDict[str, torch.Tensor]", device, dtype16=torch.float16):
         if dims.dim % dims.heads != 0 or dims.dim // dims.heads != 64:
             raise NotImplementedError(
                 f"libvitk attention kernels cover head_dim 64 (got dim={dims.dim}, heads={dims.heads}); "
@@ -167,19 +177,22 @@ class VitEngine:
         _lib.load()
         self.d = dims
         self.device = torch.device(device)
-        self.flat = FlatParams(named_params, dims.depth, self.device)
+        self.dt16 = dtype16
+        self.flat = FlatParams(named_params, dims.depth, self.device, dtype16)
         self.flat.refresh_shadow()
         self._ws: Dict[Tuple[int, bool], Workspace] = {}
         self.scale = 64 ** -0.5
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        self.grad_ready_hook = None   # callable(name_prefix) used by the data-parallel bucket launcher
+        self.grad_ready_hook = None   # callable(stage) used by the data-parallel bucket launcher
+        self.generation = 0
+        s0 = self.INIT_LOSS_SCALE if dtype16 == torch.float16 else 1.0
+        self.amp = torch.tensor([s0, 1.0 / s0, 0, 0, 0, 0, 0, 0], dtype=torch.float32, device=self.device)
+        self.amp_scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.growth_interval = self.GROWTH_INTERVAL if dtype16 == torch.float16 else 0
 
     # ------------------------------------------------------------------ helpers
-    def w(self, name: str) -> torch.Tensor:      # bf16 shadow view (backward)
-        return self.flat.view(self.flat.bf16, name)
-
-    def wh(self, name: str) -> torch.Tensor:     # fp16 shadow view (forward)
-        return self.flat.view(self.flat.fp16, name)
+    def w(self, name: str) -> torch.Tensor:      # 16-bit shadow view
+        return self.flat.view(self.flat.w16, name)
 
     def p(self, name: str) -> torch.Tensor:      # fp32 master view
         return self.flat.view(self.flat.params, name)
@@ -187,11 +200,19 @@ class VitEngine:
     def g(self, name: str) -> torch.Tensor:      # fp32 gradient view
         return self.flat.view(self.flat.grads, name)
 
+    @property
+    def loss_scale(self) -> torch.Tensor:        # device scalar S
+        return self.amp[0:1]
+
+    @property
+    def grad_unscale(self) -> torch.Tensor:      # device scalar 1/S
+        return self.amp[1:2]
+
     def workspace(self, B: int, train: bool) -> Workspace:
         key = (B, train)
         ws = self._ws.get(key)
         if ws is None:
-            ws = Workspace(self.d, B, train, self.device)
+            ws = Workspace(self.d, B, train, self.device, self.dt16)
             self._ws[key] = ws
         return ws
 
@@ -202,12 +223,12 @@ class VitEngine:
         return max(1, min(max(1, nkb // 2), (2 * self.sms + tiles - 1) // tiles))
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, rows: int) -> None:
-        """grad[wname][N_out, K_in] += dy[rows, N_out]^T @ x[rows, K_in] (both operands read MN-major)."""
+        """grad[wname][N_out, K_in] += (1/S) * dy[rows, N_out]^T @ x[rows, K_in] (both operands read MN-major)."""
         gw = self.g(wname)
         n_out = gw.shape[0]
         k_in = gw.numel() // n_out
         ops.gemm(dy, x, n_out, k_in, rows, a_mn=True, b_mn=True, out=gw, epilogue=_lib.EPI_ATOMIC_ADD,
-                 split_k=self._split_k(n_out, k_in, rows))
+                 split_k=self._split_k(n_out, k_in, rows), alpha_dev=self.grad_unscale)
 
     # ------------------------------------------------------------------ forward
     def forward(self, images: torch.Tensor, train: bool, attn_probs: Optional[List[torch.Tensor]] = None):
@@ -221,9 +242,9 @@ class VitEngine:
         images = images.contiguous()
         if images.dtype != torch.float32:
             images = images.float()
-        ops.patchify(images, d.patch, out=ws.patches, out2=ws.patches_b)
+        ops.patchify(images, d.patch, out=ws.patches)
         x0 = ws.x[0]
-        ops.gemm(ws.patches, self.wh("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
+        ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
                  bias=self.p("patch_embed.proj.bias"), epilogue=_lib.EPI_TOKENS,
                  tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"))
         ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token"),
@@ -236,20 +257,18 @@ class VitEngine:
             else:
                 x_in, x_mid, x_out = ws.x[(2 * l) % 3], ws.x[(2 * l + 1) % 3], ws.x[(2 * l + 2) % 3]
             st = ws.stats[s]
-            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), y=ws.xn1[s], y2=ws.xn1_b[s],
-                              mean=st[0], rstd=st[1])
-            ops.gemm(ws.xn1[s], self.wh(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
+            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), y=ws.xn1[s], mean=st[0], rstd=st[1])
+            ops.gemm(ws.xn1[s], self.w(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
             probs = None
             if attn_probs is not None:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
-            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], out2=ws.ao_b[s], lse=ws.lse[s], probs=probs)
-            ops.gemm(ws.ao[s], self.wh(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
-            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], y2=ws.xn2_b[s],
-                              mean=st[2], rstd=st[3])
-            ops.gemm(ws.xn2[s], self.wh(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.pre[s], out2=ws.act[s], out3=ws.act_b[s],
+            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
+            ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
+            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
+            ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.pre[s], out2=ws.act[s],
                      bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
-            ops.gemm(ws.act[s], self.wh(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
+            ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
         x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
         two = d.n_out == 2
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
@@ -262,7 +281,8 @@ class VitEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self, B: int, dl0: torch.Tensor, dl1: Optional[torch.Tensor]) -> None:
-        """Accumulates every parameter gradient into flat.grads (input gradient is not produced)."""
+        """Takes TRUE dlogits; accumulates every TRUE parameter gradient into flat.grads (no input gradient).
+        Activation gradients in between are S-scaled 16-bit tensors."""
         d = self.d
         T, D = d.tokens, d.dim
         M = B * T
@@ -272,46 +292,47 @@ class VitEngine:
         xhat, rstd = ws.head_saved
         ws.head_saved = None
         two = d.n_out == 2
+        u = self.grad_unscale
         dx, dx_alt = ws.dx[0], ws.dx[1]
         last_fc2_bias = self.g(f"blocks.{d.depth - 1}.mlp.fc2.bias")
         ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),
-                     self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dxb,
+                     self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dx16,
                      self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
                      self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
-                     last_fc2_bias, T, d.n_out)
+                     last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale)
         self._notify("head")
         for l in range(d.depth - 1, -1, -1):
             pre = f"blocks.{l}."
             st = ws.stats[l]
             x_in, x_mid = ws.x[2 * l], ws.x[2 * l + 1]
             # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
-            self._wgrad(ws.dxb, ws.act_b[l], pre + "mlp.fc2.weight", M)
-            ops.gemm(ws.dxb, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.pre[l],
+            self._wgrad(ws.dx16, ws.act[l], pre + "mlp.fc2.weight", M)
+            ops.gemm(ws.dx16, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.pre[l],
                      epilogue=_lib.EPI_DGELU)
-            ops.colsum_bf16(ws.d_pre, self.g(pre + "mlp.fc1.bias"))
-            self._wgrad(ws.d_pre, ws.xn2_b[l], pre + "mlp.fc1.weight", M)
+            ops.colsum16(ws.d_pre, self.g(pre + "mlp.fc1.bias"), unscale=u)
+            self._wgrad(ws.d_pre, ws.xn2[l], pre + "mlp.fc1.weight", M)
             ops.gemm(ws.d_pre, self.w(pre + "mlp.fc1.weight"), M, D, d.hidden, b_mn=True, out=ws.dxn)
             ops.layernorm_bwd(ws.dxn, x_mid, st[2], st[3], self.p(pre + "norm2.weight"), self.g(pre + "norm2.weight"),
-                              self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx_bf16=ws.dxb,
-                              dcolsum=self.g(pre + "attn.proj.bias"))
+                              self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16,
+                              dcolsum=self.g(pre + "attn.proj.bias"), unscale=u)
             dx, dx_alt = dx_alt, dx
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
-            self._wgrad(ws.dxb, ws.ao_b[l], pre + "attn.proj.weight", M)
-            ops.gemm(ws.dxb, self.w(pre + "attn.proj.weight"), M, D, D, b_mn=True, out=ws.d_ao)
-            ops.attention_bwd(ws.qkv[l], ws.ao_b[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
-            ops.colsum_bf16(ws.dqkv, self.g(pre + "attn.qkv.bias"))
-            self._wgrad(ws.dqkv, ws.xn1_b[l], pre + "attn.qkv.weight", M)
+            self._wgrad(ws.dx16, ws.ao[l], pre + "attn.proj.weight", M)
+            ops.gemm(ws.dx16, self.w(pre + "attn.proj.weight"), M, D, D, b_mn=True, out=ws.d_ao)
+            ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
+            ops.colsum16(ws.dqkv, self.g(pre + "attn.qkv.bias"), unscale=u)
+            self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M)
             ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
             prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
             ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),
-                              self.g(pre + "norm1.bias"), dres=dx, dx=dx_alt, dx_bf16=ws.dxb if l > 0 else None,
-                              dcolsum=prev_bias)
+                              self.g(pre + "norm1.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16 if l > 0 else None,
+                              dcolsum=prev_bias, unscale=u)
             dx, dx_alt = dx_alt, dx
             self._notify(pre)
         ops.tokens_bwd(dx.view(B, T, D), self.g("pos_embed"), self.g("cls_token"),
                        self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g("patch_embed.proj.bias"),
-                       d.n_prefix)
-        self._wgrad(ws.dpatch, ws.patches_b, "patch_embed.proj.weight", B * d.n_patches)
+                       d.n_prefix, unscale=u)
+        self._wgrad(ws.dpatch, ws.patches, "patch_embed.proj.weight", B * d.n_patches)
         self._notify("embed")
 
     def _notify(self, what: str) -> None:
@@ -320,3 +341,8 @@ class VitEngine:
 
     def zero_grad(self) -> None:
         self.flat.grads.zero_()
+
+    def amp_update(self) -> None:
+        """Loss-scale bookkeeping when an EXTERNAL optimizer consumes flat.grads (see vitk_amp_update)."""
+        if self.dt16 == torch.float16:
+            ops.amp_update(self.flat.grads, self.amp, self.amp_scratch, self.growth_interval)

@@ -2,6 +2,7 @@
 
 Every function enqueues kernels of libvitk.so on torch's current stream and returns torch
 tensors that merely own the memory.  No function here computes anything with torch ops.
+16-bit tensors may be torch.float16 or torch.bfloat16; the wrapper passes the matching vitk_dtype.
 """
 from __future__ import annotations
 
@@ -17,15 +18,6 @@ bf16 = torch.bfloat16
 f16 = torch.float16
 f32 = torch.float32
 _DT = {bf16: _lib.DT_BF16, f32: _lib.DT_FP32, f16: _lib.DT_FP16}
-
-
-def _req16(t: torch.Tensor, name: str) -> None:
-    if not t.is_cuda:
-        raise RuntimeError(f"{name}: expected a CUDA tensor (libvitk has no CPU path)")
-    if t.dtype not in (bf16, f16):
-        raise RuntimeError(f"{name}: expected bfloat16 or float16, got {t.dtype}")
-    if not t.is_contiguous():
-        raise RuntimeError(f"{name}: expected a contiguous tensor")
 
 
 def _stream() -> int:
@@ -45,6 +37,15 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
         raise RuntimeError(f"{name}: expected a contiguous tensor")
 
 
+def _req16(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (libvitk has no CPU path)")
+    if t.dtype not in (bf16, f16):
+        raise RuntimeError(f"{name}: expected bfloat16 or float16, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+
+
 def launch_count() -> int:
     return int(_lib.load().vitk_launch_count())
 
@@ -57,13 +58,15 @@ def reset_launch_count() -> None:
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False,
          out: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          epilogue: int = _lib.EPI_STORE, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
-         out3: Optional[torch.Tensor] = None, split_k: int = 1, alpha: float = 1.0, tokens: Optional[tuple] = None, pos: Optional[torch.Tensor] = None,
-         lda: Optional[int] = None, ldb: Optional[int] = None) -> torch.Tensor:
+         split_k: int = 1, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, tokens: Optional[tuple] = None,
+         pos: Optional[torch.Tensor] = None, lda: Optional[int] = None, ldb: Optional[int] = None) -> torch.Tensor:
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue (see include/vitk.h).
 
-    A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].
-    """
+    A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].  A and B must share one
+    16-bit element type (tcgen05 kind::f16 cannot mix fp16 with bf16)."""
     _req16(A, "gemm A"); _req16(B, "gemm B")
+    if A.dtype != B.dtype:
+        raise RuntimeError(f"gemm: A ({A.dtype}) and B ({B.dtype}) must have the same 16-bit element type")
     a = GemmArgs()
     a.a_dtype, a.b_dtype = _DT[A.dtype], _DT[B.dtype]
     a.aux_dtype = _DT[aux.dtype] if aux is not None else 0
@@ -75,6 +78,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     a.split_k, a.epilogue = split_k, epilogue
     a.out_dtype = _DT[out.dtype]
     a.alpha = alpha
+    a.alpha_dev = _p(alpha_dev)
     if bias is not None:
         _req(bias, f32, "gemm bias")
     if residual is not None:
@@ -82,70 +86,69 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     a.bias, a.residual, a.ldr = _p(bias), _p(residual), N
     a.out, a.ldo = out.data_ptr(), N
     a.out2, a.ldo2 = _p(out2), N
-    a.out3 = _p(out3)
     a.aux, a.ldaux = _p(aux), N
     if tokens is not None:
         a.rows_per_img, a.tokens_per_img, a.prefix = tokens
         a.pos = _p(pos)
-    check(_lib.load().vitk_gemm_bf16(C.byref(a), _stream()), "gemm")
+    check(_lib.load().vitk_gemm(C.byref(a), _stream()), "gemm")
     return out
 
 
 # --------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=None, y2=None, dtype=bf16):
-    """y = LayerNorm(x) in `dtype` (fp16 or bf16); y2: optional extra bf16 copy (what backward's wgrad reads)."""
+def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=None, dtype=f16):
     _req(x, f32, "layernorm x")
     dim = x.shape[-1]
     rows = x.numel() // dim
     y = torch.empty(x.shape, dtype=dtype, device=x.device) if y is None else y
     mean = torch.empty(rows, dtype=f32, device=x.device) if mean is None else mean
     rstd = torch.empty(rows, dtype=f32, device=x.device) if rstd is None else rstd
-    if y2 is not None:
-        _req(y2, bf16, "layernorm y2")
-    check(_lib.load().vitk_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _DT[y.dtype], _p(y2),
+    check(_lib.load().vitk_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _DT[y.dtype],
                                          mean.data_ptr(), rstd.data_ptr(), rows, dim, eps, _stream()), "layernorm_fwd")
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None, dx_bf16=None, dcolsum=None):
-    _req(dy, bf16, "layernorm dy"); _req(x, f32, "layernorm x")
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None, dx16=None, dcolsum=None, unscale=None):
+    """dx = dres + LN'(dy); dgamma/dbeta/dcolsum += (*unscale) * column sums."""
+    _req16(dy, "layernorm dy"); _req(x, f32, "layernorm x")
     dim = x.shape[-1]
     rows = x.numel() // dim
     dx = torch.empty_like(x) if dx is None else dx
-    check(_lib.load().vitk_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                         _p(dres), dx.data_ptr(), _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(),
-                                         _p(dcolsum), rows, dim, _stream()), "layernorm_bwd")
+    check(_lib.load().vitk_layernorm_bwd(dy.data_ptr(), _DT[dy.dtype], x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                         gamma.data_ptr(), _p(dres), dx.data_ptr(), _p(dx16),
+                                         _DT[dx16.dtype] if dx16 is not None else _DT[dy.dtype], dgamma.data_ptr(),
+                                         dbeta.data_ptr(), _p(dcolsum), _p(unscale), rows, dim, _stream()), "layernorm_bwd")
     return dx
 
 
 # --------------------------------------------------------------------------- attention
-def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None, out2=None):
-    """out in fp16 or bf16 (its dtype decides); out2: optional bf16 copy for backward."""
-    _req(qkv, bf16, "attention qkv")
-    out = torch.empty(B, N, H * 64, dtype=bf16, device=qkv.device) if out is None else out
+def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None):
+    _req16(qkv, "attention qkv")
+    out = torch.empty(B, N, H * 64, dtype=qkv.dtype, device=qkv.device) if out is None else out
+    if out.dtype != qkv.dtype:
+        raise RuntimeError("attention: qkv and out must share one element type")
     lse = torch.empty(B, H, N, dtype=f32, device=qkv.device) if lse is None else lse
-    check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), _DT[out.dtype], _p(out2), lse.data_ptr(), _p(probs),
-                                         B, N, H, scale, _stream()), "attention_fwd")
+    check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], lse.data_ptr(), _p(probs), B, N, H,
+                                         scale, _stream()), "attention_fwd")
     return out, lse
 
 
 def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqkv=None, delta=None):
-    _req(qkv, bf16, "attention qkv"); _req(out, bf16, "attention out"); _req(dout, bf16, "attention dout")
+    _req16(qkv, "attention qkv")
+    _req(out, qkv.dtype, "attention out"); _req(dout, qkv.dtype, "attention dout")
     dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
     delta = torch.empty(B, H, N, dtype=f32, device=qkv.device) if delta is None else delta
     check(_lib.load().vitk_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-                                         dqkv.data_ptr(), B, N, H, scale, _stream()), "attention_bwd")
+                                         dqkv.data_ptr(), _DT[qkv.dtype], B, N, H, scale, _stream()), "attention_bwd")
     return dqkv
 
 
 # --------------------------------------------------------------------------- tokens
-def patchify(images, P: int, out=None, out2=None, dtype=bf16):
+def patchify(images, P: int, out=None, dtype=f16):
     _req(images, f32, "patchify images")
     B, Cc, H, W = images.shape
     rows = B * (H // P) * (W // P)
     out = torch.empty(rows, Cc * P * P, dtype=dtype, device=images.device) if out is None else out
-    check(_lib.load().vitk_patchify(images.data_ptr(), out.data_ptr(), _DT[out.dtype], _p(out2), B, Cc, H, W, P, _stream()),
-          "patchify")
+    check(_lib.load().vitk_patchify(images.data_ptr(), out.data_ptr(), _DT[out.dtype], B, Cc, H, W, P, _stream()), "patchify")
     return out
 
 
@@ -156,9 +159,10 @@ def prefix_tokens_fwd(x, cls_tok, dist_tok, pos, n_prefix: int):
     return x
 
 
-def tokens_bwd(dx, dpos, dcls, ddist, dpatch_bf16, dbias, n_prefix: int):
+def tokens_bwd(dx, dpos, dcls, ddist, dpatch16, dbias, n_prefix: int, unscale=None):
     B, T, dim = dx.shape
-    check(_lib.load().vitk_tokens_bwd(dx.data_ptr(), _p(dpos), _p(dcls), _p(ddist), _p(dpatch_bf16), _p(dbias), B, T, dim,
+    check(_lib.load().vitk_tokens_bwd(dx.data_ptr(), _p(dpos), _p(dcls), _p(ddist), _p(dpatch16),
+                                      _DT[dpatch16.dtype] if dpatch16 is not None else 0, _p(dbias), _p(unscale), B, T, dim,
                                       n_prefix, _stream()), "tokens_bwd")
 
 
@@ -177,14 +181,15 @@ def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5):
     return logits0, logits1, xhat, rstd
 
 
-def head_bwd(dl0, dl1, xhat, rstd, gamma, beta, W0, W1, dx, dx_bf16, dgamma, dbeta, dW0, db0, dW1, db1, dcolsum,
-             T: int, n_heads: int):
+def head_bwd(dl0, dl1, xhat, rstd, gamma, beta, W0, W1, dx, dx16, dgamma, dbeta, dW0, db0, dW1, db1, dcolsum,
+             T: int, n_heads: int, loss_scale=None):
+    """dx / dx16 = S * dLoss/dx (S = *loss_scale), parameter gradients are true (unscaled)."""
     B, Cc = dl0.shape
     dim = W0.shape[1]
     check(_lib.load().vitk_head_bwd(dl0.data_ptr(), _p(dl1), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                    W0.data_ptr(), _p(W1), dx.data_ptr(), _p(dx_bf16), dgamma.data_ptr(), dbeta.data_ptr(),
-                                    dW0.data_ptr(), _p(db0), _p(dW1), _p(db1), _p(dcolsum), B, T, dim, Cc, n_heads, _stream()),
-          "head_bwd")
+                                    W0.data_ptr(), _p(W1), dx.data_ptr(), _p(dx16), _DT[dx16.dtype] if dx16 is not None else 0,
+                                    dgamma.data_ptr(), dbeta.data_ptr(), dW0.data_ptr(), _p(db0), _p(dW1), _p(db1), _p(dcolsum),
+                                    _p(loss_scale), B, T, dim, Cc, n_heads, _stream()), "head_bwd")
 
 
 # --------------------------------------------------------------------------- loss
@@ -203,17 +208,22 @@ def loss_fwd_bwd(cls_logits, dist_logits, teacher_logits, labels, *, mode: int, 
     return out, dcls, ddist
 
 
-# --------------------------------------------------------------------------- optimizer
+# --------------------------------------------------------------------------- optimizer / loss scale
 def grad_sqnorm(grads, state):
     check(_lib.load().vitk_grad_sqnorm(grads.data_ptr(), grads.numel(), state.data_ptr(), _stream()), "grad_sqnorm")
 
 
-def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, params_fp16, chunk_off, chunk_len, chunk_lr_scale, chunk_wd, state,
-               beta1: float, beta2: float, eps: float, max_grad_norm: float):
+def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, params_fp16, chunk_off, chunk_len, chunk_lr_scale, chunk_wd,
+               state, amp_state, beta1: float, beta2: float, eps: float, max_grad_norm: float, growth_interval: int = 2000):
     check(_lib.load().vitk_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                                      _p(params_bf16), _p(params_fp16), chunk_off.data_ptr(), chunk_len.data_ptr(), chunk_lr_scale.data_ptr(),
-                                      chunk_wd.data_ptr(), chunk_off.numel(), state.data_ptr(), beta1, beta2, eps,
-                                      max_grad_norm, _stream()), "adamw_step")
+                                      _p(params_bf16), _p(params_fp16), chunk_off.data_ptr(), chunk_len.data_ptr(),
+                                      chunk_lr_scale.data_ptr(), chunk_wd.data_ptr(), chunk_off.numel(), state.data_ptr(),
+                                      _p(amp_state), beta1, beta2, eps, max_grad_norm, growth_interval, _stream()), "adamw_step")
+
+
+def amp_update(grads, amp_state, scratch4, growth_interval: int = 2000):
+    check(_lib.load().vitk_amp_update(grads.data_ptr(), grads.numel(), amp_state.data_ptr(), scratch4.data_ptr(),
+                                      growth_interval, _stream()), "amp_update")
 
 
 # --------------------------------------------------------------------------- helpers
@@ -231,16 +241,11 @@ def cast_fp16(src, dst=None):
     return dst
 
 
-def cast_shadows(src, dst_bf16, dst_fp16):
-    """One pass over fp32 `src` writing both 16-bit shadows."""
-    _req(src, f32, "cast src")
-    check(_lib.load().vitk_cast_f32_to_16(src.data_ptr(), _p(dst_bf16), _p(dst_fp16), src.numel(), _stream()), "cast")
-
-
-def colsum_bf16(x, out):
-    _req(x, bf16, "colsum x")
+def colsum16(x, out, unscale=None):
+    _req16(x, "colsum x")
     dim = x.shape[-1]
-    check(_lib.load().vitk_colsum_bf16(x.data_ptr(), out.data_ptr(), x.numel() // dim, dim, _stream()), "colsum")
+    check(_lib.load().vitk_colsum16(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _p(unscale), x.numel() // dim, dim, _stream()),
+          "colsum")
     return out
 
 

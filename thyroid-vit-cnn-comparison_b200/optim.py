@@ -1,6 +1,7 @@
 """FusedAdamW: torch.optim.AdamW semantics (lightning_modules.py:599-604, :1108-1113) executed by ONE
 multi-tensor libvitk kernel over the model's flat parameter buffer, with Lightning's
-clip_grad_norm_(max_norm) (configs/trainer/default.yaml:21,54) and the bf16 weight shadow fused in.
+clip_grad_norm_(max_norm) (configs/trainer/default.yaml:21,54), the 16-bit weight shadow and the dynamic
+loss-scale bookkeeping (skip the step and halve S on fp16 overflow) fused in.
 
 It is a torch.optim.Optimizer (param_groups / state_dict / lr schedulers such as CosineAnnealingLR
 keep working: group['lr'] is re-read every step), but step() never touches torch arithmetic.
@@ -90,11 +91,14 @@ class FusedAdamW(torch.optim.Optimizer):
     def launch(self) -> None:
         """Enqueue norm + update kernels (CUDA-graph capturable: no host reads, hyper-parameters on device)."""
         flat = self.engine.flat
-        if self.max_grad_norm > 0:
-            ops.grad_sqnorm(flat.grads, self.dev_state)
-        ops.adamw_step(flat.params, flat.grads, self.exp_avg, self.exp_avg_sq, flat.bf16, flat.fp16, self.chunk_off, self.chunk_len,
-                       self.chunk_lr, self.chunk_wd, self.dev_state, self.betas[0], self.betas[1], self.eps,
-                       self.max_grad_norm)
+        # the squared norm doubles as the fp16 overflow detector, so it is always computed
+        ops.grad_sqnorm(flat.grads, self.dev_state)
+        eng = self.engine
+        fp16 = flat.dtype16 == torch.float16
+        ops.adamw_step(flat.params, flat.grads, self.exp_avg, self.exp_avg_sq, None if fp16 else flat.w16,
+                       flat.w16 if fp16 else None, self.chunk_off, self.chunk_len, self.chunk_lr, self.chunk_wd,
+                       self.dev_state, eng.amp if fp16 else None, self.betas[0], self.betas[1], self.eps,
+                       self.max_grad_norm, eng.growth_interval)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.engine.zero_grad()

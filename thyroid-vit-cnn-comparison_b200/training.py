@@ -439,12 +439,12 @@ class TrainStep:
 
     def _snapshot(self):
         f, o = self.eng.flat, self.opt
-        return (f.params.clone(), f.bf16.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.dev_state.clone(), f.fp16.clone())
+        return (f.params.clone(), f.w16.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.dev_state.clone(), self.eng.amp.clone())
 
     def _restore(self, snap) -> None:
         f, o = self.eng.flat, self.opt
-        f.params.copy_(snap[0]); f.bf16.copy_(snap[1]); o.exp_avg.copy_(snap[2]); o.exp_avg_sq.copy_(snap[3])
-        o.dev_state.copy_(snap[4]); f.fp16.copy_(snap[5])
+        f.params.copy_(snap[0]); f.w16.copy_(snap[1]); o.exp_avg.copy_(snap[2]); o.exp_avg_sq.copy_(snap[3])
+        o.dev_state.copy_(snap[4]); self.eng.amp.copy_(snap[5])
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """Public step: copies the batch in, runs the step, returns the device tensor of step statistics

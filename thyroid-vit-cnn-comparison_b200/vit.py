@@ -99,7 +99,7 @@ class PatchEmbed(nn.Module):
             assert H == self.img_size and W == self.img_size, \
                 f"Input size ({H}x{W}) doesn't match expected size ({self.img_size}x{self.img_size})"
         _require_cuda(x, "PatchEmbed")
-        patches = ops.patchify(x.float().contiguous(), self.patch_size, dtype=torch.float16)
+        patches = ops.patchify(x.float().contiguous(), self.patch_size)
         w16 = ops.cast_fp16(self.proj.weight.detach().reshape(self.embed_dim, -1).contiguous())
         out = torch.empty(patches.shape[0], self.embed_dim, dtype=torch.float32, device=x.device)
         ops.gemm(patches, w16, patches.shape[0], self.embed_dim, patches.shape[1], out=out,
@@ -200,6 +200,7 @@ class _EncoderFn(torch.autograd.Function):
         dl0 = grads[0].contiguous().float()
         dl1 = grads[1].contiguous().float() if ctx.two else None
         eng.backward(ctx.B, dl0, dl1)
+        eng.amp_update()     # an external optimizer will read param.grad: overflow check + loss-scale bookkeeping
         return None, None, None
 
 
@@ -329,8 +330,8 @@ class VisionTransformerBase(_Base):
                         dim=self.embed_dim, depth=len(self.blocks), heads=blk.attn.num_heads,
                         hidden=blk.mlp.fc1.out_features, classes=self.num_classes, n_prefix=self._n_prefix(),
                         n_out=self._n_out())
-            eng = VitEngine(dims, OrderedDict((n, p.data) for n, p in named.items()), first.device)
-            eng.generation = 0
+            eng = VitEngine(dims, OrderedDict((n, p.data) for n, p in named.items()), first.device,
+                            dtype16=self._vitk_hparams.get("compute_dtype", torch.float16))
             for n, p in named.items():        # re-point the module's parameters at the flat buffers
                 p.data = eng.flat.view(eng.flat.params, n)
                 p.grad = None
