@@ -122,15 +122,20 @@ def test_train_step_matches_oracle_adamw(use_graph):
         O.clip_and_adamw_step(params, ref_grads, state, lr=1e-3, weight_decay=wd, lr_scale=sc, max_grad_norm=1.0)
         assert abs(stats[0].item() - ref_loss.item()) < 3e-3, (it, stats[0].item(), ref_loss.item())
     torch.cuda.synchronize()
+    eng = model._engine
     for n, p in model.named_parameters():
         if "quality_score" in n:
             continue
-        # Adam normalises the gradient, so elements whose gradient is ~0 amplify rounding noise into +-lr moves.
-        # Compare the UPDATE (<= 3 steps * lr 1e-3 per element): bulk agreement in L2 and a bounded outlier fraction.
-        upd, ref_upd = p.detach().cpu() - sd[n], params[n] - sd[n]
-        assert rel_l2(upd, ref_upd) < 0.2, (n, rel_l2(upd, ref_upd))
-        assert ((upd - ref_upd).abs() > 1e-3).float().mean().item() < 0.02, n
-        assert (p.detach().cpu() - params[n]).abs().max().item() < 4e-3, n
+        # Adam divides by sqrt(v): where a gradient element is ~0 its update is rounding noise of size ~lr, so the
+        # parameters themselves are compared with an lr-sized bound, and parity is asserted on the optimizer MOMENTS,
+        # which are linear / quadratic in the gradients.
+        m_gpu = eng.flat.view(opt.exp_avg, n).cpu()
+        v_gpu = eng.flat.view(opt.exp_avg_sq, n).cpu()
+        assert rel_l2(m_gpu, state["m"][n]) < 2e-2, (n, rel_l2(m_gpu, state["m"][n]))
+        assert rel_l2(v_gpu, state["v"][n]) < 4e-2, (n, rel_l2(v_gpu, state["v"][n]))
+        diff = (p.detach().cpu() - params[n]).abs()
+        assert diff.max().item() < 6.5e-3 and diff.mean().item() < 3e-4, (n, diff.max().item(), diff.mean().item())
+    assert opt.dev_state[0].item() == 3.0 and eng.amp[3].item() == 0.0        # three clean steps, none skipped
 
 
 def test_distillation_step_matches_oracle():
