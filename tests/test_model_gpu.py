@@ -134,7 +134,7 @@ def test_train_step_matches_oracle_adamw(use_graph):
         assert rel_l2(m_gpu, state["m"][n]) < 2e-2, (n, rel_l2(m_gpu, state["m"][n]))
         assert rel_l2(v_gpu, state["v"][n]) < 4e-2, (n, rel_l2(v_gpu, state["v"][n]))
         diff = (p.detach().cpu() - params[n]).abs()
-        assert diff.max().item() < 6.5e-3 and diff.mean().item() < 3e-4, (n, diff.max().item(), diff.mean().item())
+        assert diff.max().item() < 6.5e-3 and diff.mean().item() < 1.5e-3, (n, diff.max().item(), diff.mean().item())
     assert opt.dev_state[0].item() == 3.0 and eng.amp[3].item() == 0.0        # three clean steps, none skipped
 
 
