@@ -1,4 +1,4 @@
-// gemm_tcgen05.cu -- bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// gemm_tcgen05.cu -- 16-bit GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
 // operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring.
 //
 //   D[M,N] = A[M,K] * B[N,K]^T   with a fused epilogue (bias / residual / GELU / dGELU /
@@ -12,10 +12,15 @@
 //   dgrad    dX = dY * W        A = dY [M,N]  K-major     B = W  [N,K]  read MN-major
 //   wgrad    dW = dY^T * X      A = dY [M,N]  MN-major    B = X  [M,K]  MN-major (split-K)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quadrant each).  One 128 x BN output tile per CTA; the
-// shallow-pipeline variants fit two CTAs per SM so one CTA's epilogue overlaps the other's
-// mainloop (DeiT-tiny GEMMs have K = 192: three k-blocks, epilogue-dominated).
+// Structure (v2): PERSISTENT, one CTA per SM, 192 threads:
+//   warp 0      TMA producer   -- runs ahead over tiles, STAGES-deep smem ring (full/empty mbarriers)
+//   warp 1      MMA issuer     -- one elected lane issues tcgen05.mma; owns the TMEM allocation
+//   warps 2..5  epilogue       -- one TMEM lane quadrant each
+// TMEM holds TWO accumulator stages (2 x BN fp32 columns), so the MMAs of tile i+1 overlap the epilogue of
+// tile i.  The epilogue transposes each 32x32 fp32 chunk through shared memory so that every global access
+// of a warp covers whole 64/128-byte row segments (residual reads, 16-bit / fp32 stores, vector reductions).
+// DeiT-tiny GEMMs (K = 192) are HBM-bound: what matters is bytes in flight (the ring) and coalescing;
+// ViT-B GEMMs (K = 768/3072) are tensor-bound: what matters is that the MMA warp never waits for the epilogue.
 #include <cudaTypedefs.h>
 
 #include "vitk_common.cuh"
@@ -25,14 +30,16 @@ namespace vitk {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
+constexpr int EPI_PITCH = 36;  // floats per staged row (32 + 4 pad: conflict-free 128-bit rows)
 
 struct GemmParams {
   int M, N, K;
   int num_kblocks;
   int kblocks_per_split;
+  int num_m_tiles, num_n_tiles, num_splits;
   int epilogue, out_dtype, aux_dtype;
   uint32_t idesc;
   float alpha;
@@ -55,9 +62,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -80,48 +88,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     if ((++spins & 0x3ff) == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 2000000000ull) {  // 2 s
-        printf("vitk gemm: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
-               blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      if (t1 - t0 > 4000000000ull) {  // 4 s
+        printf("vitk gemm: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
         __trap();
       }
     }
   }
 }
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar,
-                                            int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
-      "%4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(slot)),
-               "r"(ncols)
-               : "memory");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -134,71 +129,113 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128B swizzle.
-//   K-major : rows of 128 B (64 bf16 of K), 8-row groups 1024 B apart        -> SBO = 1024
-//   MN-major: rows of 128 B (64 bf16 of M/N) per k, 8-k groups 1024 B apart   -> SBO = 1024,
-//             next 64-wide M/N block one whole TMA box (64 k * 128 B) further -> LBO = 8192
+//   K-major : rows of 128 B (64 elements of K), 8-row groups 1024 B apart       -> SBO = 1024
+//   MN-major: rows of 128 B (64 elements of M/N) per k, 8-k groups 1024 B apart  -> SBO = 1024,
+//             next 64-wide M/N block one whole TMA box (64 k * 128 B) further    -> LBO = 8192
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   constexpr uint64_t lbo = MN_MAJOR ? (8192u >> 4) : 1u;
   constexpr uint64_t sbo = 1024u >> 4;
-  return static_cast<uint64_t>((saddr >> 4) & 0x3fffu) | (lbo << 16) | (sbo << 32) | (1ull << 46) |
-         (2ull << 61);
+  return static_cast<uint64_t>((saddr >> 4) & 0x3fffu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// Instruction descriptor for kind::f16: {bf16|fp16} x {bf16|fp16} -> fp32, M = 128, N = bn.
-// a_format / b_format: 0 = F16, 1 = BF16 (may differ between A and B).
+// Instruction descriptor for kind::f16: {bf16|fp16} x same -> fp32, M = 128, N = bn.  a/b_format: 0 = F16, 1 = BF16.
 inline uint32_t make_idesc(int bn, bool a_mn, bool b_mn, bool a_fp16, bool b_fp16) {
   return (1u << 4) | (uint32_t(a_fp16 ? 0 : 1) << 7) | (uint32_t(b_fp16 ? 0 : 1) << 10) | (uint32_t(a_mn) << 15) |
          (uint32_t(b_mn) << 16) | (uint32_t(bn >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+constexpr int tmem_cols_for(int bn) {
+  return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
 }
 
-template <int BN>
-constexpr int tmem_cols() {
-  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+// ------------------------------------------------------------------ epilogue on one float4 (row, 4 consecutive columns)
+__device__ __forceinline__ void epilogue_vec(const GemmParams& p, float4 f, int row, int col, float alpha, const float4& bias4) {
+  f.x = f.x * alpha + bias4.x; f.y = f.y * alpha + bias4.y; f.z = f.z * alpha + bias4.z; f.w = f.w * alpha + bias4.w;
+  long long orow = row;
+  switch (p.epilogue) {
+    case VITK_EPI_TOKENS: {
+      const int b = row / p.rows_per_img;
+      const int pi = row - b * p.rows_per_img;
+      orow = (long long)b * p.tokens_per_img + p.prefix + pi;
+      const float4 q = ldg_f4(p.pos + (long long)(p.prefix + pi) * p.N + col);
+      f.x += q.x; f.y += q.y; f.z += q.z; f.w += q.w;
+    }  // fallthrough
+    case VITK_EPI_STORE: {
+      if (p.residual != nullptr) {
+        const float4 r = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
+        f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
+      }
+      if (p.out_dtype == VITK_FP32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = f;
+      } else {
+        const bool h = p.out_dtype == VITK_FP16;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col) =
+            make_uint2(pack16(f.x, f.y, h), pack16(f.z, f.w, h));
+      }
+    } break;
+    case VITK_EPI_GELU: {
+      const bool h = p.out_dtype == VITK_FP16;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col) =
+          make_uint2(pack16(f.x, f.y, h), pack16(f.z, f.w, h));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col) =
+          make_uint2(pack16(gelu_erf(f.x), gelu_erf(f.y), h), pack16(gelu_erf(f.z), gelu_erf(f.w), h));
+    } break;
+    case VITK_EPI_DGELU: {
+      const bool ah = p.aux_dtype == VITK_FP16, h = p.out_dtype == VITK_FP16;
+      const uint2 a = ldg_u2(reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col);
+      const float2 a0 = unpack16(a.x, ah), a1 = unpack16(a.y, ah);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col) =
+          make_uint2(pack16(f.x * gelu_erf_grad(a0.x), f.y * gelu_erf_grad(a0.y), h),
+                     pack16(f.z * gelu_erf_grad(a1.x), f.w * gelu_erf_grad(a1.y), h));
+    } break;
+    case VITK_EPI_ATOMIC_ADD:
+      red_add_v4(reinterpret_cast<float*>(p.out) + orow * p.ldo + col, f);
+      break;
+    default:
+      break;
+  }
 }
 
 // ------------------------------------------------------------------ the kernel
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                        const GemmParams p) {
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = tmem_cols<BN>();
+  constexpr int TMEM_COLS = tmem_cols_for(BN);
+  constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * p.kblocks_per_split;
-  const int kb_end = min(p.num_kblocks, kb_begin + p.kblocks_per_split);
-  const int nk = kb_end - kb_begin;
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int total_tiles = tiles_mn * p.num_splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -207,7 +244,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -216,179 +256,127 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> (m, n, split): n fastest (CTAs running together share the A rows through L2), split slowest
+  auto decode = [&](int tile, int& m0, int& n0, int& kb0, int& nk) {
+    const int split = tile / tiles_mn;
+    const int r = tile - split * tiles_mn;
+    const int mt = r / p.num_n_tiles;
+    const int nt = r - mt * p.num_n_tiles;
+    m0 = mt * BLOCK_M;
+    n0 = nt * BN;
+    kb0 = split * p.kblocks_per_split;
+    const int kb1 = min(p.num_kblocks, kb0 + p.kblocks_per_split);
+    nk = kb1 - kb0;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1, 1);
-      if (lane == 0) {
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int kc = (kb_begin + kb) * BLOCK_K;
-        uint8_t* a_dst = sA + s * A_BYTES;
-        uint8_t* b_dst = sB + s * B_BYTES;
-        if (!A_MN) {
-          tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
-        } else {
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m0, n0, kb0, nk;
+      decode(tile, m0, n0, kb0, nk);
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        if (lane == 0) {
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int kc = (kb0 + kb) * BLOCK_K;
+          uint8_t* a_dst = sA + s * A_BYTES;
+          uint8_t* b_dst = sB + s * B_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kc);
-        }
-        if (!B_MN) {
-          tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0);
-        } else {
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kc);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_dst + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kc);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_dst + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kc);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = p.idesc;
     constexpr uint32_t a_adv = A_MN ? (2048u >> 4) : (32u >> 4);  // desc.lo step per UMMA_K
     constexpr uint32_t b_adv = B_MN ? (2048u >> 4) : (32u >> 4);
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph, 2);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      int m0, n0, kb0, nk;
+      decode(tile, m0, n0, kb0, nk);
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator stage
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint64_t adesc = make_smem_desc<A_MN>(smem_u32(sA + s * A_BYTES));
-        const uint64_t bdesc = make_smem_desc<B_MN>(smem_u32(sB + s * B_BYTES));
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph, 2);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_smem_desc<A_MN>(smem_u32(sA + s * A_BYTES));
+          const uint64_t bdesc = make_smem_desc<B_MN>(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          umma_bf16(tmem_base, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (kb == nk - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&empty_bar[s]);
-        if (kb == nk - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int row = m0 + quad * 32 + lane;
-    const bool row_ok = row < p.M;
-    if (nk > 0) {
-      mbar_wait(tmem_full_bar, 0, 3);
+    float* stage = sEpi + quad * 32 * EPI_PITCH;
+    const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+    const int c4 = lane & 7;     // float4 column slot of this lane inside a 32-column chunk
+    const int rsub = lane >> 3;  // row (mod 4) this lane handles when reading the staged chunk back
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      int m0, n0, kb0, nk;
+      decode(tile, m0, n0, kb0, nk);
+      const uint32_t acc = tcount & 1;
+      mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
       tcgen05_fence_after();
-    }
-    long long orow = row;
-    const float* pos_row = nullptr;
-    if (p.epilogue == VITK_EPI_TOKENS && row_ok) {
-      const int b = row / p.rows_per_img;
-      const int pi = row - b * p.rows_per_img;
-      orow = (long long)b * p.tokens_per_img + p.prefix + pi;
-      pos_row = p.pos + (long long)(p.prefix + pi) * p.N;
-    }
+      const uint32_t t_addr = tmem_base + acc * BN + (uint32_t(quad * 32) << 16);
+      const int row_base = m0 + quad * 32;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      const int col0 = n0 + c0;
-      if (col0 >= p.N) break;  // warp-uniform
-      uint32_t v[32];
-      if (nk > 0) {
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), v);
-      } else {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_addr + uint32_t(c0), v);
+        // transpose through smem: lane = row on the way in, lane = (row mod 4, float4 column) on the way out
+        float* wr = stage + lane * EPI_PITCH;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      if (!row_ok) continue;
-      float f[32];
-      const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(wr + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+        const int col = col0 + c4 * 4;
+        if (col < p.N) {
+          const float4 bias4 = p.bias != nullptr ? ldg_f4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (col0 + j < p.N) {
-            const float4 b4 = ldg_f4(p.bias + col0 + j);
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            const int row = row_base + r;
+            if (row < p.M) {
+              const float4 f = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + c4 * 4);
+              epilogue_vec(p, f, row, col, alpha, bias4);
+            }
           }
         }
+        __syncwarp();
       }
-      switch (p.epilogue) {
-        case VITK_EPI_STORE:
-        case VITK_EPI_TOKENS: {
-          if (p.epilogue == VITK_EPI_TOKENS) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.N) {
-                const float4 q4 = ldg_f4(pos_row + col0 + j);
-                f[j] += q4.x; f[j + 1] += q4.y; f[j + 2] += q4.z; f[j + 3] += q4.w;
-              }
-            }
-          }
-          if (p.residual != nullptr) {
-            const float* r = p.residual + orow * p.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.N) {
-                const float4 r4 = *reinterpret_cast<const float4*>(r + j);
-                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-              }
-            }
-          }
-          if (p.out_dtype == VITK_FP32) {
-            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (col0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            const bool h = p.out_dtype == VITK_FP16;
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              if (col0 + j < p.N)
-                st_global_v4(o + j, pack16(f[j], f[j + 1], h), pack16(f[j + 2], f[j + 3], h),
-                             pack16(f[j + 4], f[j + 5], h), pack16(f[j + 6], f[j + 7], h));
-          }
-        } break;
-        case VITK_EPI_GELU: {
-          const bool h = p.out_dtype == VITK_FP16;
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-          __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              st_global_v4(o + j, pack16(f[j], f[j + 1], h), pack16(f[j + 2], f[j + 3], h),
-                           pack16(f[j + 4], f[j + 5], h), pack16(f[j + 6], f[j + 7], h));
-              float g[8];
-#pragma unroll
-              for (int t = 0; t < 8; ++t) g[t] = gelu_erf(f[j + t]);
-              st_global_v4(o2 + j, pack16(g[0], g[1], h), pack16(g[2], g[3], h), pack16(g[4], g[5], h),
-                           pack16(g[6], g[7], h));
-            }
-          }
-        } break;
-        case VITK_EPI_DGELU: {
-          const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col0;
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              const uint4 a4 = ldg_u4(ax + j);
-              const bool ah = p.aux_dtype == VITK_FP16;
-              const float2 a0 = unpack16(a4.x, ah), a1 = unpack16(a4.y, ah), a2 = unpack16(a4.z, ah),
-                           a3 = unpack16(a4.w, ah);
-              const float g0 = f[j] * gelu_erf_grad(a0.x), g1 = f[j + 1] * gelu_erf_grad(a0.y);
-              const float g2 = f[j + 2] * gelu_erf_grad(a1.x), g3 = f[j + 3] * gelu_erf_grad(a1.y);
-              const float g4 = f[j + 4] * gelu_erf_grad(a2.x), g5 = f[j + 5] * gelu_erf_grad(a2.y);
-              const float g6 = f[j + 6] * gelu_erf_grad(a3.x), g7 = f[j + 7] * gelu_erf_grad(a3.y);
-              const bool h = p.out_dtype == VITK_FP16;
-              st_global_v4(o + j, pack16(g0, g1, h), pack16(g2, g3, h), pack16(g4, g5, h), pack16(g6, g7, h));
-            }
-          }
-        } break;
-        case VITK_EPI_ATOMIC_ADD: {
-          float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) atomicAdd(o + j, f[j]);
-        } break;
-        default:
-          break;
-      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator stage
+      tcgen05_fence_before();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -410,9 +398,9 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [outer, inner] matrix, 128B swizzle, zero OOB fill.
-int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
-                 uint32_t box_inner, uint32_t box_outer, bool fp16) {
+// 2-D 16-bit tensor map over a row-major [outer, inner] matrix, 128B swizzle, zero OOB fill.
+int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
+                 uint32_t box_outer, bool fp16) {
   auto fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -422,21 +410,21 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
   cuuint64_t strides[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed: CUresult %d (base=%p inner=%llu outer=%llu pitch=%llu box=%ux%u)",
-              (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
-              (unsigned long long)pitch_elems, box_inner, box_outer);
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (base=%p inner=%llu outer=%llu pitch=%llu box=%ux%u)", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems, box_inner, box_outer);
     return VITK_ERR_CUDA;
   }
   return VITK_OK;
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 4 * 32 * EPI_PITCH * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(SMEM <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
   if (!configured) {
@@ -449,21 +437,12 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_gemm(int bn, bool deep, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid,
-                  cudaStream_t st) {
+int dispatch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
   switch (bn) {
-    case 64:
-      return deep ? launch_gemm<64, 8, A_MN, B_MN>(tmA, tmB, p, grid, st)
-                  : launch_gemm<64, 4, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 128:
-      return deep ? launch_gemm<128, 6, A_MN, B_MN>(tmA, tmB, p, grid, st)
-                  : launch_gemm<128, 3, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 192:
-      return deep ? launch_gemm<192, 5, A_MN, B_MN>(tmA, tmB, p, grid, st)
-                  : launch_gemm<192, 2, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 256:
-      return deep ? launch_gemm<256, 4, A_MN, B_MN>(tmA, tmB, p, grid, st)
-                  : launch_gemm<256, 2, A_MN, B_MN>(tmA, tmB, p, grid, st);
+    case 64:  return launch_gemm<64, 8, A_MN, B_MN>(tmA, tmB, p, grid, st);
+    case 128: return launch_gemm<128, 6, A_MN, B_MN>(tmA, tmB, p, grid, st);
+    case 192: return launch_gemm<192, 5, A_MN, B_MN>(tmA, tmB, p, grid, st);
+    case 256: return launch_gemm<256, 4, A_MN, B_MN>(tmA, tmB, p, grid, st);
     default:
       set_error("unsupported BLOCK_N %d", bn);
       return VITK_ERR_UNSUPPORTED;
@@ -501,8 +480,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
                  "vitk_gemm: operands must be 16-byte aligned");
   VITK_CHECK_ARG(a->split_k >= 1, "vitk_gemm: split_k must be >= 1");
-  VITK_CHECK_ARG(a->split_k == 1 || a->epilogue == VITK_EPI_ATOMIC_ADD,
-                 "vitk_gemm: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
+  VITK_CHECK_ARG(a->split_k == 1 || a->epilogue == VITK_EPI_ATOMIC_ADD, "vitk_gemm: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
   VITK_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= VITK_EPI_TOKENS, "vitk_gemm: bad epilogue %d", a->epilogue);
   VITK_CHECK_ARG(a->out_dtype >= VITK_BF16 && a->out_dtype <= VITK_FP16, "vitk_gemm: bad out_dtype %d", a->out_dtype);
   VITK_CHECK_ARG((a->a_dtype == VITK_BF16 || a->a_dtype == VITK_FP16) && (a->b_dtype == VITK_BF16 || a->b_dtype == VITK_FP16),
@@ -519,18 +497,24 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   if (a->epilogue == VITK_EPI_TOKENS)
     VITK_CHECK_ARG(a->pos != nullptr && a->rows_per_img > 0 && a->tokens_per_img >= a->rows_per_img + a->prefix,
                    "TOKENS epilogue needs pos / rows_per_img / tokens_per_img");
-  const int vec = out_fp32 ? 4 : 8;
-  VITK_CHECK_ARG(a->ldo % vec == 0, "vitk_gemm: ldo must keep rows 16-byte aligned");
+  VITK_CHECK_ARG(a->ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+                 "vitk_gemm: out rows must stay 8/16-byte aligned (ldo %% 4 == 0, 16-byte aligned base)");
+  if (a->residual)
+    VITK_CHECK_ARG(a->ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0, "vitk_gemm: residual alignment");
+  if (a->bias) VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "vitk_gemm: bias must be 16-byte aligned");
 
   const int bn = pick_bn(a->N);
   const int num_kblocks = (a->K + BLOCK_K - 1) / BLOCK_K;
-  int kpb = (num_kblocks + a->split_k - 1) / a->split_k;
+  const int kpb = (num_kblocks + a->split_k - 1) / a->split_k;
   const int splits = (num_kblocks + kpb - 1) / kpb;
 
   GemmParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_kblocks = num_kblocks;
   p.kblocks_per_split = kpb;
+  p.num_m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (a->N + bn - 1) / bn;
+  p.num_splits = splits;
   p.epilogue = a->epilogue; p.out_dtype = a->out_dtype; p.aux_dtype = a->aux_dtype;
   p.idesc = make_idesc(bn, a->a_mn_major != 0, a->b_mn_major != 0, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16);
   p.alpha = a->alpha; p.alpha_dev = a->alpha_dev;
@@ -541,18 +525,19 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
 
   CUtensorMap tmA, tmB;
   int rc;
-  if (!a->a_mn_major) rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M, a->a_dtype == VITK_FP16);
-  else                rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K, a->a_dtype == VITK_FP16);
+  const bool ah = a->a_dtype == VITK_FP16, bh = a->b_dtype == VITK_FP16;
+  if (!a->a_mn_major) rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M, ah);
+  else                rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K, ah);
   if (rc != VITK_OK) return rc;
-  if (!a->b_mn_major) rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, a->b_dtype == VITK_FP16);
-  else                rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, a->b_dtype == VITK_FP16);
+  if (!a->b_mn_major) rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, bh);
+  else                rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, bh);
   if (rc != VITK_OK) return rc;
 
-  dim3 grid((a->M + BLOCK_M - 1) / BLOCK_M, (a->N + bn - 1) / bn, splits);
-  const bool deep = kpb >= 6;
+  const long long total_tiles = (long long)p.num_m_tiles * p.num_n_tiles * splits;
+  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, deep, tmA, tmB, p, grid, st);
-  if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, deep, tmA, tmB, p, grid, st);
-  if (a->a_mn_major && a->b_mn_major) return dispatch_gemm<true, true>(bn, deep, tmA, tmB, p, grid, st);
-  return dispatch_gemm<true, false>(bn, deep, tmA, tmB, p, grid, st);
+  if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, tmA, tmB, p, grid, st);
+  if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, tmA, tmB, p, grid, st);
+  if (a->a_mn_major && a->b_mn_major) return dispatch_gemm<true, true>(bn, tmA, tmB, p, grid, st);
+  return dispatch_gemm<true, false>(bn, tmA, tmB, p, grid, st);
 }
