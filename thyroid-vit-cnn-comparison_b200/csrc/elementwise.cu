@@ -50,7 +50,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
   if (col < dim) {
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+    long long r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {  // four independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ldg_u4(x + (r + 8 * k) * dim + col);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack16(u[k].x, fp16), b = unpack16(u[k].y, fp16), c = unpack16(u[k].z, fp16), d = unpack16(u[k].w, fp16);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+    for (; r < r1; r += 8) {
       const uint4 u = ldg_u4(x + r * dim + col);
       const float2 a = unpack16(u.x, fp16), b = unpack16(u.y, fp16), c = unpack16(u.z, fp16), d = unpack16(u.w, fp16);
       acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;

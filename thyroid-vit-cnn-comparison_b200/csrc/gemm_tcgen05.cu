@@ -15,7 +15,8 @@
 // Structure (v2): PERSISTENT, one CTA per SM, 192 threads:
 //   warp 0      TMA producer   -- runs ahead over tiles, STAGES-deep smem ring (full/empty mbarriers)
 //   warp 1      MMA issuer     -- one elected lane issues tcgen05.mma; owns the TMEM allocation
-//   warps 2..5  epilogue       -- one TMEM lane quadrant each
+//   warps 2..9  epilogue       -- two warps per TMEM lane quadrant (alternating 32-column chunks): the exact-erf
+//                                 GELU / dGELU epilogues are ALU work that needs the extra warps to hide latency
 // TMEM holds TWO accumulator stages (2 x BN fp32 columns), so the MMAs of tile i+1 overlap the epilogue of
 // tile i.  The epilogue transposes each 32x32 fp32 chunk through shared memory so that every global access
 // of a warp covers whole 64/128-byte row segments (residual reads, 16-bit / fp32 stores, vector reductions).
@@ -32,8 +33,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_PITCH = 36;  // floats per staged row (32 + 4 pad: conflict-free 128-bit rows)
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_PITCH = 20;  // floats per staged row (16 + 4 pad: conflict-free 128-bit accesses)
+constexpr int EPI_STAGE_FLOATS = 32 * EPI_PITCH;
 
 struct GemmParams {
   int M, N, K;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = tmem_cols_for(BN);
-  constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+  constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -331,12 +334,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    float* stage = sEpi + quad * 32 * EPI_PITCH;
+    // ===================== epilogue (warps 2..) =====================
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may read
+    const int group = (warp - 2) >> 2;        // which of the EPI_WARPS/4 warps sharing that quadrant
+    float* stage = sEpi + (warp - 2) * EPI_STAGE_FLOATS;
     const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
-    const int c4 = lane & 7;     // float4 column slot of this lane inside a 32-column chunk
-    const int rsub = lane >> 3;  // row (mod 4) this lane handles when reading the staged chunk back
+    const int c4 = lane & 3;     // float4 column slot of this lane inside a 16-column half chunk
+    const int rsub = lane >> 2;  // row (mod 8) this lane handles when reading the staged half chunk back
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       int m0, n0, kb0, nk;
@@ -347,32 +351,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t t_addr = tmem_base + acc * BN + (uint32_t(quad * 32) << 16);
       const int row_base = m0 + quad * 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = group * 32; c0 < BN; c0 += 32 * (EPI_WARPS / 4)) {
         const int col0 = n0 + c0;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(t_addr + uint32_t(c0), v);
-        // transpose through smem: lane = row on the way in, lane = (row mod 4, float4 column) on the way out
-        float* wr = stage + lane * EPI_PITCH;
+        // transpose through smem in two 16-column halves: lane = row on the way in,
+        // lane = (row mod 8, float4 column) on the way out -> every global access covers whole 32/64-byte row segments
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(wr + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        __syncwarp();
-        const int col = col0 + c4 * 4;
-        if (col < p.N) {
-          const float4 bias4 = p.bias != nullptr ? ldg_f4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          float* wr = stage + lane * EPI_PITCH;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rsub;
-            const int row = row_base + r;
-            if (row < p.M) {
-              const float4 f = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + c4 * 4);
-              epilogue_vec(p, f, row, col, alpha, bias4);
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(wr + j) =
+                make_float4(__uint_as_float(v[hlf * 16 + j]), __uint_as_float(v[hlf * 16 + j + 1]),
+                            __uint_as_float(v[hlf * 16 + j + 2]), __uint_as_float(v[hlf * 16 + j + 3]));
+          __syncwarp();
+          const int col = col0 + hlf * 16 + c4 * 4;
+          if (col < p.N) {
+            const float4 bias4 = p.bias != nullptr ? ldg_f4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + rsub;
+              const int row = row_base + r;
+              if (row < p.M) {
+                const float4 f = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + c4 * 4);
+                epilogue_vec(p, f, row, col, alpha, bias4);
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator stage
       tcgen05_fence_before();
@@ -423,7 +432,7 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + 4 * 32 * EPI_PITCH * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;

@@ -1,15 +1,15 @@
-// layernorm.cu -- LayerNorm forward / backward, one warp per token row, 128-bit accesses,
-// shuffle reductions.  Replaces nn.LayerNorm(dim) (eps 1e-5, affine) at
+// layernorm.cu -- LayerNorm forward / backward: a group of LPR lanes (8/16/32) owns one token row, 128-bit
+// accesses, shuffle reductions inside the group.  Replaces nn.LayerNorm(dim) (eps 1e-5, affine) at
 // vision_transformer_base.py:263,273 (norm1/norm2 of every Block).
 //
-// The residual stream stays fp32 (x in, dx out); the normalised activations feeding the
-// tensor-core GEMMs are emitted as bf16.  Backward also folds in the residual gradient
-// (dx = dres + LN'(dy)), emits the bf16 copy the next dgrad/wgrad GEMM consumes and the column
-// sum of dx (= bias gradient of the Linear that wrote the residual branch), so the residual
-// gradient is read once and written once per LayerNorm.
+// The residual stream stays fp32 (x in, dx out); the normalised activations feeding the tensor-core GEMMs are
+// emitted in 16 bits.  Backward also folds in the residual gradient (dx = dres + LN'(dy)), emits the 16-bit copy
+// the next dgrad/wgrad GEMM consumes and the column sum of dx (= bias gradient of the Linear that wrote the
+// residual branch), so the residual gradient is read once and written once per LayerNorm.
 //
-// HBM roofline (algorithmic bytes per row, D = dim):
-//   fwd: 4D (x) + 2D (y) + 8 (stats)            bwd: 2D (dy) + 4D (x) + 4D (dres) + 4D (dx) + 2D (dx bf16)
+// Lane mapping: dim/4 float4 vectors per row are spread over LPR lanes x CHUNKS; D=192 -> 16 lanes x 3 (two rows
+// per warp, every lane busy), D=768 -> 32 lanes x 6.  HBM roofline (algorithmic bytes per row, D = dim):
+//   fwd: 4D (x) + 2D (y) + 8 (stats)            bwd: 2D (dy) + 4D (x) + 4D (dres) + 4D (dx) + 2D (dx16)
 #include "vitk_common.cuh"
 
 namespace vitk {
@@ -17,48 +17,59 @@ namespace {
 
 constexpr int LN_WARPS = 8;
 
-template <int CHUNKS>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta,
-                                                               __nv_bfloat16* __restrict__ y, int y_fp16,
-                                                               float* __restrict__ mean,
-                                                               float* __restrict__ rstd, long long rows, int dim, float eps) {
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  __nv_bfloat16* __restrict__ y, int y_fp16, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
+                  int dim, float eps) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, gl = lane % LPR;
   const int nvec = dim >> 2;
   const float inv_dim = 1.f / float(dim);
   float4 gm[CHUNKS], bt[CHUNKS];
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
-    const int i = lane + 32 * c;
+    const int i = gl + LPR * c;
     gm[c] = i < nvec ? ldg_f4(gamma + 4 * i) : make_float4(0, 0, 0, 0);
     bt[c] = i < nvec ? ldg_f4(beta + 4 * i) : make_float4(0, 0, 0, 0);
   }
-  for (long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows;
-       row += (long long)gridDim.x * LN_WARPS) {
-    const float* xr = x + row * dim;
+  const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
+  for (long long row0 = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += stride) {
+    const long long row = row0 + sub;
+    const bool ok = row < rows;
+    const float* xr = x + (ok ? row : 0) * dim;
     float4 v[CHUNKS];
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      const int i = lane + 32 * c;
-      v[c] = i < nvec ? ldg_f4(xr + 4 * i) : make_float4(0, 0, 0, 0);
+      const int i = gl + LPR * c;
+      v[c] = (ok && i < nvec) ? ldg_f4(xr + 4 * i) : make_float4(0, 0, 0, 0);
       s += v[c].x + v[c].y + v[c].z + v[c].w;
     }
-    const float mu = warp_sum(s) * inv_dim;
+    const float mu = group_sum<LPR>(s) * inv_dim;
     float q = 0.f;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      const int i = lane + 32 * c;
+      const int i = gl + LPR * c;
       if (i < nvec) {
         const float a = v[c].x - mu, b = v[c].y - mu, cc = v[c].z - mu, d = v[c].w - mu;
         q += a * a + b * b + cc * cc + d * d;
       }
     }
-    const float rs = rsqrtf(warp_sum(q) * inv_dim + eps);
+    const float rs = rsqrtf(group_sum<LPR>(q) * inv_dim + eps);
+    if (!ok) continue;
     __nv_bfloat16* yr = y + row * dim;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      const int i = lane + 32 * c;
+      const int i = gl + LPR * c;
       if (i < nvec) {
         const float a = (v[c].x - mu) * rs * gm[c].x + bt[c].x;
         const float b = (v[c].y - mu) * rs * gm[c].y + bt[c].y;
@@ -67,22 +78,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
         *reinterpret_cast<uint2*>(yr + 4 * i) = make_uint2(pack16(a, b, y_fp16), pack16(cc, d, y_fp16));
       }
     }
-    if (lane == 0) {
+    if (gl == 0) {
       mean[row] = mu;
       rstd[row] = rs;
     }
   }
 }
 
-template <int CHUNKS>
+template <int LPR, int CHUNKS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
     ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
-                  float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_bf16, int dx_fp16, float* __restrict__ dgamma,
+                  float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
                   float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale, long long rows,
                   int dim) {
+  constexpr int RPW = 32 / LPR;
   extern __shared__ float red[];  // [3][dim]
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, gl = lane % LPR;
   const int nvec = dim >> 2;
   const float inv_dim = 1.f / float(dim);
   for (int i = threadIdx.x; i < 3 * dim; i += blockDim.x) red[i] = 0.f;
@@ -91,58 +104,64 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
   float4 gm[CHUNKS], dg[CHUNKS], db[CHUNKS], dc[CHUNKS];
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
-    const int i = lane + 32 * c;
+    const int i = gl + LPR * c;
     gm[c] = i < nvec ? ldg_f4(gamma + 4 * i) : make_float4(0, 0, 0, 0);
     dg[c] = db[c] = dc[c] = make_float4(0, 0, 0, 0);
   }
-  for (long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows;
-       row += (long long)gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    const float* xr = x + row * dim;
-    const __nv_bfloat16* dyr = dy + row * dim;
+  const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
+  for (long long row0 = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += stride) {
+    const long long row = row0 + sub;
+    const bool ok = row < rows;
+    const long long rr = ok ? row : 0;
+    const float mu = mean[rr], rs = rstd[rr];
+    const float* xr = x + rr * dim;
+    const __nv_bfloat16* dyr = dy + rr * dim;
+    // issue every load of the row before any arithmetic (memory-level parallelism)
+    float4 xv[CHUNKS], rv[CHUNKS];
+    uint2 dyu[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int i = gl + LPR * c;
+      const bool act = ok && i < nvec;
+      xv[c] = act ? ldg_f4(xr + 4 * i) : make_float4(0, 0, 0, 0);
+      dyu[c] = act ? ldg_u2(dyr + 4 * i) : make_uint2(0, 0);
+      rv[c] = (act && dres != nullptr) ? ldg_f4(dres + rr * dim + 4 * i) : make_float4(0, 0, 0, 0);
+    }
     float4 xh[CHUNKS], g[CHUNKS];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      const int i = lane + 32 * c;
-      if (i < nvec) {
-        const float4 xv = ldg_f4(xr + 4 * i);
-        const uint2 dyu = ldg_u2(dyr + 4 * i);
-        const float2 d01 = unpack16(dyu.x, dy_fp16), d23 = unpack16(dyu.y, dy_fp16);
-        xh[c] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[c] = make_float4(d01.x * gm[c].x, d01.y * gm[c].y, d23.x * gm[c].z, d23.y * gm[c].w);
-        dg[c].x += d01.x * xh[c].x; dg[c].y += d01.y * xh[c].y; dg[c].z += d23.x * xh[c].z; dg[c].w += d23.y * xh[c].w;
-        db[c].x += d01.x; db[c].y += d01.y; db[c].z += d23.x; db[c].w += d23.y;
-        s1 += g[c].x + g[c].y + g[c].z + g[c].w;
-        s2 += g[c].x * xh[c].x + g[c].y * xh[c].y + g[c].z * xh[c].z + g[c].w * xh[c].w;
-      } else {
-        xh[c] = g[c] = make_float4(0, 0, 0, 0);
-      }
+      const float2 d01 = unpack16(dyu[c].x, dy_fp16), d23 = unpack16(dyu[c].y, dy_fp16);
+      xh[c] = make_float4((xv[c].x - mu) * rs, (xv[c].y - mu) * rs, (xv[c].z - mu) * rs, (xv[c].w - mu) * rs);
+      const int i = gl + LPR * c;
+      if (!(ok && i < nvec)) xh[c] = make_float4(0, 0, 0, 0);
+      g[c] = make_float4(d01.x * gm[c].x, d01.y * gm[c].y, d23.x * gm[c].z, d23.y * gm[c].w);
+      dg[c].x += d01.x * xh[c].x; dg[c].y += d01.y * xh[c].y; dg[c].z += d23.x * xh[c].z; dg[c].w += d23.y * xh[c].w;
+      db[c].x += d01.x; db[c].y += d01.y; db[c].z += d23.x; db[c].w += d23.y;
+      s1 += g[c].x + g[c].y + g[c].z + g[c].w;
+      s2 += g[c].x * xh[c].x + g[c].y * xh[c].y + g[c].z * xh[c].z + g[c].w * xh[c].w;
     }
-    const float m1 = warp_sum(s1) * inv_dim;
-    const float m2 = warp_sum(s2) * inv_dim;
+    const float m1 = group_sum<LPR>(s1) * inv_dim;
+    const float m2 = group_sum<LPR>(s2) * inv_dim;
+    if (!ok) continue;
     float* dxr = dx + row * dim;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      const int i = lane + 32 * c;
+      const int i = gl + LPR * c;
       if (i < nvec) {
-        float4 o = make_float4(rs * (g[c].x - m1 - xh[c].x * m2), rs * (g[c].y - m1 - xh[c].y * m2),
-                               rs * (g[c].z - m1 - xh[c].z * m2), rs * (g[c].w - m1 - xh[c].w * m2));
-        if (dres != nullptr) {
-          const float4 r = ldg_f4(dres + row * dim + 4 * i);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        const float4 o = make_float4(rs * (g[c].x - m1 - xh[c].x * m2) + rv[c].x, rs * (g[c].y - m1 - xh[c].y * m2) + rv[c].y,
+                                     rs * (g[c].z - m1 - xh[c].z * m2) + rv[c].z, rs * (g[c].w - m1 - xh[c].w * m2) + rv[c].w);
         *reinterpret_cast<float4*>(dxr + 4 * i) = o;
-        if (dx_bf16 != nullptr)
-          *reinterpret_cast<uint2*>(dx_bf16 + row * dim + 4 * i) = make_uint2(pack16(o.x, o.y, dx_fp16), pack16(o.z, o.w, dx_fp16));
+        if (dx16 != nullptr)
+          *reinterpret_cast<uint2*>(dx16 + row * dim + 4 * i) = make_uint2(pack16(o.x, o.y, dx_fp16), pack16(o.z, o.w, dx_fp16));
         dc[c].x += o.x; dc[c].y += o.y; dc[c].z += o.z; dc[c].w += o.w;
       }
     }
   }
-  // block reduction of the three column sums, then one atomic per column per block
+  // block reduction of the three column sums (shared atomics), then one global atomic per column per block
 #pragma unroll
   for (int c = 0; c < CHUNKS; ++c) {
-    const int i = lane + 32 * c;
+    const int i = gl + LPR * c;
     if (i < nvec) {
       float* r0 = red + 4 * i;
       atomicAdd(r0 + 0, dg[c].x); atomicAdd(r0 + 1, dg[c].y); atomicAdd(r0 + 2, dg[c].z); atomicAdd(r0 + 3, dg[c].w);
@@ -163,10 +182,27 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
   }
 }
 
-int ln_grid(long long rows) {
-  const long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-  const long long cap = (long long)num_sms() * 8;  // multiple of the SM count, 8 resident CTAs / SM
-  return (int)(blocks < cap ? blocks : cap);
+struct LnCfg {
+  int lpr, chunks;
+};
+// smallest lane group that covers the row with <= 8 float4 per lane, preferring full lane utilisation
+LnCfg ln_config(int dim) {
+  const int nvec = dim / 4;
+  const int lprs[3] = {8, 16, 32};
+  for (int lpr : lprs) {
+    const int ch = (nvec + lpr - 1) / lpr;
+    if (ch <= 4) return {lpr, ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 3 ? 3 : 4};
+  }
+  const int ch = (nvec + 31) / 32;
+  return {32, ch <= 6 ? 6 : 8};
+}
+
+int ln_grid(long long rows, int rows_per_block, int ctas_per_sm) {
+  long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+  const long long cap = (long long)num_sms() * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
 }
 
 }  // namespace
@@ -174,34 +210,35 @@ int ln_grid(long long rows) {
 
 using namespace vitk;
 
-#define LN_DISPATCH(CH, ...)            \
-  switch (CH) {                         \
-    case 1: { constexpr int C_ = 1; __VA_ARGS__; } break; \
-    case 2: { constexpr int C_ = 2; __VA_ARGS__; } break; \
-    case 3: { constexpr int C_ = 3; __VA_ARGS__; } break; \
-    case 4: { constexpr int C_ = 4; __VA_ARGS__; } break; \
-    case 6: { constexpr int C_ = 6; __VA_ARGS__; } break; \
-    case 8: { constexpr int C_ = 8; __VA_ARGS__; } break; \
-    default: set_error("layernorm: dim too large"); return VITK_ERR_UNSUPPORTED; \
+#define LN_CASE(L, C, ...)                      \
+  if (cfg.lpr == L && cfg.chunks == C) {        \
+    constexpr int L_ = L, C_ = C;               \
+    __VA_ARGS__;                                \
+    launched = true;                            \
+  }
+#define LN_DISPATCH(...)                                                                                       \
+  {                                                                                                            \
+    bool launched = false;                                                                                     \
+    LN_CASE(8, 1, __VA_ARGS__) LN_CASE(8, 2, __VA_ARGS__) LN_CASE(8, 3, __VA_ARGS__) LN_CASE(8, 4, __VA_ARGS__) \
+    LN_CASE(16, 1, __VA_ARGS__) LN_CASE(16, 2, __VA_ARGS__) LN_CASE(16, 3, __VA_ARGS__) LN_CASE(16, 4, __VA_ARGS__) \
+    LN_CASE(32, 1, __VA_ARGS__) LN_CASE(32, 2, __VA_ARGS__) LN_CASE(32, 3, __VA_ARGS__) LN_CASE(32, 4, __VA_ARGS__) \
+    LN_CASE(32, 6, __VA_ARGS__) LN_CASE(32, 8, __VA_ARGS__)                                                     \
+    if (!launched) {                                                                                           \
+      set_error("layernorm: unsupported dim");                                                                 \
+      return VITK_ERR_UNSUPPORTED;                                                                             \
+    }                                                                                                          \
   }
 
-static int ln_chunks(int dim) {
-  const int c = (dim / 4 + 31) / 32;
-  if (c <= 4) return c;
-  if (c <= 6) return 6;
-  if (c <= 8) return 8;
-  return 99;
-}
-
-extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
-                                  float* mean, float* rstd, int64_t rows, int32_t dim, float eps, void* stream) {
+extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype, float* mean,
+                                  float* rstd, int64_t rows, int32_t dim, float eps, void* stream) {
   VITK_CHECK_ARG(x && gamma && beta && y && mean && rstd, "vitk_layernorm_fwd: null pointer");
   VITK_CHECK_ARG(y_dtype == VITK_BF16 || y_dtype == VITK_FP16, "vitk_layernorm_fwd: y must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_fwd: dim=%d must be a multiple of 4, <= 1024", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int ch = ln_chunks(dim);
-  LN_DISPATCH(ch, ln_fwd_kernel<C_><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(
-                      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, rows, dim, eps));
+  const LnCfg cfg = ln_config(dim);
+  const int rpb = LN_WARPS * (32 / cfg.lpr);
+  LN_DISPATCH((ln_fwd_kernel<L_, C_><<<ln_grid(rows, rpb, 8), LN_WARPS * 32, 0, st>>>(
+      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, rows, dim, eps)));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -215,17 +252,13 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
                  "vitk_layernorm_bwd: dy / dx16 must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_bwd: dim=%d must be a multiple of 4, <= 1024", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int ch = ln_chunks(dim);
+  const LnCfg cfg = ln_config(dim);
   const size_t smem = 3 * (size_t)dim * sizeof(float);
-  // fewer, fatter blocks than forward: each block ends with 3*dim global atomics
-  long long blocks = (rows + LN_WARPS * 4 - 1) / (LN_WARPS * 4);
-  const long long cap = (long long)num_sms() * 4;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  LN_DISPATCH(ch, ln_bwd_kernel<C_><<<(int)blocks, LN_WARPS * 32, smem, st>>>(
-                      reinterpret_cast<const __nv_bfloat16*>(dy), int(dy_dtype == VITK_FP16), x, mean, rstd, gamma, dres, dx,
-                      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum,
-                      grad_unscale, rows, dim));
+  // each CTA should sweep several rows per lane group so the closing 3*dim global atomics are amortised
+  const int rpb = LN_WARPS * (32 / cfg.lpr) * 4;
+  LN_DISPATCH((ln_bwd_kernel<L_, C_><<<ln_grid(rows, rpb, 6), LN_WARPS * 32, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), int(dy_dtype == VITK_FP16), x, mean, rstd, gamma, dres, dx,
+      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum, grad_unscale, rows, dim)));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -92,14 +92,28 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, bool fp16) {
   return unpack_bf16(u);
 }
 
+// erf with |abs error| <= ~3e-7 (Abramowitz & Stegun 7.1.26 in fp32; exp and reciprocal run on the SFU pipe).
+// The CUDA libm erff costs ~3x more instructions; at 4 x D GELU evaluations per token the exact-erf epilogue would
+// otherwise be ISSUE-bound rather than HBM-bound.  Returns erf(x) and e = exp(-x*x) (reused by the derivative).
+__device__ __forceinline__ float erf_fast(float x, float& e) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  e = __expf(-ax * ax);
+  return copysignf(fmaf(-poly * t, e, 1.0f), x);
+}
 // exact (erf) GELU, as nn.GELU() default (vision_transformer_base.py:212-219)
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  float e;
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f, e));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;  // = exp(-x*x/2)
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f, e));
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 // streaming 128-bit global accesses
