@@ -140,9 +140,9 @@ class KernelProfile:
     """Brackets every libvitk launch group of an EAGER step with CUDA events on the launching stream and aggregates
     device time, algorithmic FLOPs and algorithmic bytes per kernel class."""
 
-    def __init__(self, ops_mod):
+    def __init__(self, ops_mod, by_shape: bool = False):
         import torch
-        self.torch, self.ops, self.records, self._orig = torch, ops_mod, [], {}
+        self.torch, self.ops, self.records, self._orig, self.by_shape = torch, ops_mod, [], {}, by_shape
 
     def _wrap(self, name, meta_fn):
         orig = getattr(self.ops, name)
@@ -173,6 +173,8 @@ class KernelProfile:
                 nbytes += 2 * M * N
             if k.get("aux") is not None:
                 nbytes += 2 * M * N
+            if self.by_shape:
+                return f"gemm_tcgen05[{kind}] {M}x{N}x{K} epi{k.get('epilogue', 0)}", 2.0 * M * N * K, float(nbytes)
             return f"gemm_tcgen05[{kind}]", 2.0 * M * N * K, float(nbytes)
 
         def attn_f(qkv, B, N, H, scale, **k):
@@ -317,7 +319,7 @@ def run_ours(args):
     if rank == 0:
         saved_graph, step.use_graph = step.use_graph, False
         nprof = 3
-        with KernelProfile(ops) as prof:
+        with KernelProfile(ops, by_shape=args.by_shape) as prof:
             for _ in range(nprof):
                 step.run()
             tab = prof.table()
@@ -388,6 +390,7 @@ def main():
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--by-shape", action="store_true", help="split the GEMM rows of the kernel profile by shape")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,10 +12,10 @@
 //   dgrad    dX = dY * W        A = dY [M,N]  K-major     B = W  [N,K]  read MN-major
 //   wgrad    dW = dY^T * X      A = dY [M,N]  MN-major    B = X  [M,K]  MN-major (split-K)
 //
-// Structure (v2): PERSISTENT, one CTA per SM, 192 threads:
+// Structure (v2): PERSISTENT, one CTA per SM, 64 + 32*EPI_WARPS threads:
 //   warp 0      TMA producer   -- runs ahead over tiles, STAGES-deep smem ring (full/empty mbarriers)
 //   warp 1      MMA issuer     -- one elected lane issues tcgen05.mma; owns the TMEM allocation
-//   warps 2..9  epilogue       -- two warps per TMEM lane quadrant (alternating 32-column chunks): the exact-erf
+//   warps 2..13 epilogue       -- three warps per TMEM lane quadrant (interleaved 32-column chunks): the exact-erf
 //                                 GELU / dGELU epilogues are ALU work that needs the extra warps to hide latency
 // TMEM holds TWO accumulator stages (2 x BN fp32 columns), so the MMAs of tile i+1 overlap the epilogue of
 // tile i.  The epilogue transposes each 32x32 fp32 chunk through shared memory so that every global access
@@ -33,7 +33,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr int EPI_WARPS = 12;  // three warps per TMEM lane quadrant, interleaved over the 32-column chunks
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_PITCH = 20;  // floats per staged row (16 + 4 pad: conflict-free 128-bit accesses)
 constexpr int EPI_STAGE_FLOATS = 32 * EPI_PITCH;
@@ -166,22 +166,35 @@ constexpr int tmem_cols_for(int bn) {
 }
 
 // ------------------------------------------------------------------ epilogue on one float4 (row, 4 consecutive columns)
-__device__ __forceinline__ void epilogue_vec(const GemmParams& p, float4 f, int row, int col, float alpha, const float4& bias4) {
-  f.x = f.x * alpha + bias4.x; f.y = f.y * alpha + bias4.y; f.z = f.z * alpha + bias4.z; f.w = f.w * alpha + bias4.w;
-  long long orow = row;
+// Split in two phases so that a warp first ISSUES the global loads of all its rows (residual / pos_embed / saved
+// pre-activation) and only then does arithmetic and stores: `out` may alias `residual`, so the compiler cannot hoist
+// those loads across the stores by itself, and a serialised load->math->store chain exposes HBM latency per row.
+__device__ __forceinline__ long long epilogue_out_row(const GemmParams& p, int row) {
+  if (p.epilogue != VITK_EPI_TOKENS) return row;
+  const int b = row / p.rows_per_img;
+  return (long long)b * p.tokens_per_img + p.prefix + (row - b * p.rows_per_img);
+}
+__device__ __forceinline__ float4 epilogue_load(const GemmParams& p, int row, long long orow, int col) {
+  float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.epilogue == VITK_EPI_TOKENS) {
+    const int b = row / p.rows_per_img;
+    e = ldg_f4(p.pos + (long long)(p.prefix + row - b * p.rows_per_img) * p.N + col);
+  } else if (p.epilogue == VITK_EPI_STORE) {
+    if (p.residual != nullptr) e = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
+  } else if (p.epilogue == VITK_EPI_DGELU) {
+    const uint2 a = ldg_u2(reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col);
+    e.x = __uint_as_float(a.x);
+    e.y = __uint_as_float(a.y);
+  }
+  return e;
+}
+__device__ __forceinline__ void epilogue_apply(const GemmParams& p, float4 f, const float4& e, long long orow, int col, float alpha,
+                                               const float4& bias4) {
+  f.x = fmaf(f.x, alpha, bias4.x); f.y = fmaf(f.y, alpha, bias4.y); f.z = fmaf(f.z, alpha, bias4.z); f.w = fmaf(f.w, alpha, bias4.w);
   switch (p.epilogue) {
-    case VITK_EPI_TOKENS: {
-      const int b = row / p.rows_per_img;
-      const int pi = row - b * p.rows_per_img;
-      orow = (long long)b * p.tokens_per_img + p.prefix + pi;
-      const float4 q = ldg_f4(p.pos + (long long)(p.prefix + pi) * p.N + col);
-      f.x += q.x; f.y += q.y; f.z += q.z; f.w += q.w;
-    }  // fallthrough
+    case VITK_EPI_TOKENS:
     case VITK_EPI_STORE: {
-      if (p.residual != nullptr) {
-        const float4 r = *reinterpret_cast<const float4*>(p.residual + orow * p.ldr + col);
-        f.x += r.x; f.y += r.y; f.z += r.z; f.w += r.w;
-      }
+      f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
       if (p.out_dtype == VITK_FP32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = f;
       } else {
@@ -199,8 +212,7 @@ __device__ __forceinline__ void epilogue_vec(const GemmParams& p, float4 f, int 
     } break;
     case VITK_EPI_DGELU: {
       const bool ah = p.aux_dtype == VITK_FP16, h = p.out_dtype == VITK_FP16;
-      const uint2 a = ldg_u2(reinterpret_cast<const __nv_bfloat16*>(p.aux) + orow * p.ldaux + col);
-      const float2 a0 = unpack16(a.x, ah), a1 = unpack16(a.y, ah);
+      const float2 a0 = unpack16(__float_as_uint(e.x), ah), a1 = unpack16(__float_as_uint(e.y), ah);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col) =
           make_uint2(pack16(f.x * gelu_erf_grad(a0.x), f.y * gelu_erf_grad(a0.y), h),
                      pack16(f.z * gelu_erf_grad(a1.x), f.w * gelu_erf_grad(a1.y), h));
@@ -370,13 +382,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const int col = col0 + hlf * 16 + c4 * 4;
           if (col < p.N) {
             const float4 bias4 = p.bias != nullptr ? ldg_f4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ex[4];
+            long long orow[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 4; ++i) {  // phase 1: every global load of this half chunk in flight
+              const int row = row_base + i * 8 + rsub;
+              orow[i] = row < p.M ? epilogue_out_row(p, row) : 0;
+              ex[i] = row < p.M ? epilogue_load(p, row, orow[i], col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // phase 2: arithmetic + stores
               const int r = i * 8 + rsub;
-              const int row = row_base + r;
-              if (row < p.M) {
+              if (row_base + r < p.M) {
                 const float4 f = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + c4 * 4);
-                epilogue_vec(p, f, row, col, alpha, bias4);
+                epilogue_apply(p, f, ex[i], orow[i], col, alpha, bias4);
               }
             }
           }
@@ -450,7 +469,7 @@ int dispatch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   switch (bn) {
     case 64:  return launch_gemm<64, 8, A_MN, B_MN>(tmA, tmB, p, grid, st);
     case 128: return launch_gemm<128, 6, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 192: return launch_gemm<192, 5, A_MN, B_MN>(tmA, tmB, p, grid, st);
+    case 192: return launch_gemm<192, 4, A_MN, B_MN>(tmA, tmB, p, grid, st);
     case 256: return launch_gemm<256, 4, A_MN, B_MN>(tmA, tmB, p, grid, st);
     default:
       set_error("unsupported BLOCK_N %d", bn);

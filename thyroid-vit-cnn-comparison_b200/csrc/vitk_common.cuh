@@ -97,7 +97,7 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, bool fp16) {
 // otherwise be ISSUE-bound rather than HBM-bound.  Returns erf(x) and e = exp(-x*x) (reused by the derivative).
 __device__ __forceinline__ float erf_fast(float x, float& e) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
