@@ -1,0 +1,206 @@
+"""CPU-only checks of the host side: the C-ABI library exports exactly what include/vitk.h declares (no compute
+calls -- there is no GPU here), the drop-in classes keep the reference's API surface / state_dict keys, the
+product path fails LOUDLY without CUDA, the registry and config plumbing, and the data-parallel bucket logic
+(world_size-2 gloo processes)."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import thyroid_vit_cnn_comparison_b200 as tv  # noqa: E402
+from thyroid_vit_cnn_comparison_b200 import _lib, engine, parallel, registry, training, vit  # noqa: E402
+from oracle import vit_oracle as O  # noqa: E402
+
+
+def _header_functions():
+    h = (ROOT / "include" / "vitk.h").read_text()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|void|int64_t|const char\*)\s+(vitk_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    lib = _lib.load()                      # loads (and if needed builds) libvitk.so; no GPU required
+    decl = _header_functions()
+    assert set(decl) == set(_lib.SIGNATURES), set(decl) ^ set(_lib.SIGNATURES)
+    for name, nargs in decl.items():
+        assert hasattr(lib, name), name
+        assert len(_lib.SIGNATURES[name][1]) == nargs, name
+    assert lib.vitk_abi_version() == _lib.ABI_VERSION
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (vitk_\w+)", nm))
+    assert exported == set(decl), exported ^ set(decl)
+
+
+def test_no_cpu_fallback_and_loud_failure():
+    m = vit.create_deit_tiny(img_size=224, in_chans=3, distilled=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 224, 224))
+    from thyroid_vit_cnn_comparison_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.layernorm_fwd(torch.zeros(4, 64), torch.ones(64), torch.zeros(64))
+    # the product package must not import the oracle
+    for f in (ROOT / "thyroid-vit-cnn-comparison_b200").glob("*.py"):
+        assert "oracle" not in f.read_text().replace("# oracle", ""), f
+
+
+def test_state_dict_keys_and_param_order_match_reference():
+    for cfg, model in [(O.DEIT_TINY, vit.create_deit_tiny(img_size=224, in_chans=3, distilled=True)),
+                       (O.VIT_BASE, vit.create_vit_base(img_size=224, in_chans=3, drop_path_rate=0.0))]:
+        assert [n for n, _ in model.named_parameters()] == list(O.param_shapes(cfg))
+        assert {n: tuple(p.shape) for n, p in model.named_parameters()} == {n: tuple(s) for n, s in O.param_shapes(cfg).items()}
+        model.load_state_dict(O.seeded_state_dict(cfg, 1), strict=True)
+    m = vit.create_deit_tiny(img_size=224, in_chans=3)
+    assert sum(p.numel() for p in m.parameters()) == 5526501
+    assert m.hparams.depth == 12 and m.hparams.get("num_heads") == 3 and m.embed_dim == 192
+    assert m.patch_embed.num_patches == 196 and m.pos_embed.shape == (1, 198, 192)
+    assert isinstance(m.blocks[0].drop_path, torch.nn.Identity)
+
+
+def test_parameter_groups_reproduce_reference_table():
+    import json
+    rec = json.loads((ROOT / "tests/golden/param_groups_deit_tiny.json").read_text())
+    m = vit.create_deit_tiny(img_size=224, in_chans=3, distilled=True)
+    groups = m.get_parameter_groups(weight_decay=0.05, layer_decay=0.75)
+    assert [(g["name"], g["weight_decay"], round(g["lr_scale"], 12)) for g in groups] == \
+        [(g["name"], g["weight_decay"], round(g["lr_scale"], 12)) for g in rec["groups"]]
+
+
+def test_factories_registry_and_errors():
+    with pytest.raises(ValueError):
+        vit.get_vit_model("vit_invalid")                       # reference tests/test_vit_models.py:334-337
+    with pytest.raises(ValueError):
+        vit.create_deit_model("deit_huge")
+    assert set(vit.VIT_MODEL_REGISTRY) == {"vit_tiny", "vit_small", "vit_base"}
+    small = vit.get_vit_model("vit_small", img_size=224, in_chans=3, drop_path_rate=0.0)
+    assert small.embed_dim == 384 and small.blocks[0].attn.num_heads == 6
+
+    class Cfg:                                                 # tests/unit/test_models.py:10-22 config contract
+        def __init__(self, **k):
+            self.__dict__.update(k)
+
+        def get(self, k, d=None):
+            return getattr(self, k, d)
+
+    w = registry.ModelRegistry.create_model(Cfg(name="deit_tiny", pretrained=False, num_classes=2, img_size=224))
+    assert w.model is not None and list(w.state_dict())[0] == "model.cls_token"
+    w2 = registry.ModelRegistry.create_model(Cfg(name="vit_base", num_classes=10, img_size=224, extra_params={"in_chans": 1}))
+    assert w2.model.head.out_features == 10 and w2.model.patch_embed.proj.in_channels == 1
+    with pytest.raises(ValueError):
+        registry.ModelRegistry.create_model(Cfg(name="resnet18"))
+    with pytest.raises(ValueError):
+        registry.ModelRegistry.create_model(object())
+    assert set(registry.ModelRegistry.list_models("vit")) >= {"deit_tiny", "vit_base"}
+
+    class FakeRefRegistry:                                     # install_into overwrites the reference registry slots
+        store = {}
+
+        @classmethod
+        def register(cls, names, model_type="default"):
+            def deco(c):
+                for n in names:
+                    cls.store[n] = c
+                return c
+            return deco
+    registry.install_into(FakeRefRegistry)
+    assert FakeRefRegistry.store["deit_tiny"] is registry.DeiT and FakeRefRegistry.store["vit_small"] is registry.VisionTransformer
+
+
+def test_unsupported_options_fail_loudly():
+    m = vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, pool_type="gap")
+    with pytest.raises(NotImplementedError):
+        m._check_supported()
+    m = vit.create_vit_tiny(img_size=64, in_chans=3)           # factory default drop_path_rate=0.1
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m._check_supported()
+    m.eval()
+    m._check_supported()                                       # identity in eval
+
+
+def test_flat_layout_and_completed_prefix():
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=3, num_heads=1)
+    names = [n for n in O.param_shapes(cfg) if "quality" not in n]
+    order = engine.execution_order(names, cfg.depth)
+    assert order[0].startswith("norm") or order[0].startswith("head")
+    assert [n.split(".")[1] for n in order if n.startswith("blocks.")][0] == "2"       # last block first
+    assert order[-1] in ("patch_embed.proj.bias", "patch_embed.proj.weight", "pos_embed", "cls_token", "dist_token")
+    offsets, total = {}, 0
+    shapes = O.param_shapes(cfg)
+    for n in order:
+        offsets[n] = (total, torch.Size(shapes[n]))
+        total += (torch.Size(shapes[n]).numel() + engine.PAD - 1) // engine.PAD * engine.PAD
+    ends = [parallel.completed_prefix(order, offsets, engine.PAD, s, cfg.depth) for s in ("head", "blocks.2.", "blocks.1.", "blocks.0.", "embed")]
+    assert ends == sorted(ends) and ends[-1] == total and ends[0] > 0
+
+
+def _dp_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeFlat:
+        def __init__(self):
+            self.order = ["head.weight", "blocks.1.w", "blocks.0.w", "pos_embed"]
+            sizes = [256, 4096, 4096, 512]
+            self.offsets, off = {}, 0
+            for n, s in zip(self.order, sizes):
+                self.offsets[n] = (off, torch.Size([s]))
+                off += s
+            self.grads = torch.full((off,), float(rank + 1))
+
+        def bucket_slices(self, nbytes):
+            return engine.FlatParams.bucket_slices(self, nbytes)
+
+    class FakeDims:
+        depth = 2
+
+    class FakeEngine:
+        flat, d, grad_ready_hook = FakeFlat(), FakeDims(), None
+
+    eng = FakeEngine()
+    red = parallel.BucketedAllReduce(bucket_mb=8192 * 4 / (1 << 20))     # ~2 tensors per bucket
+    red.attach(eng)
+    for stage in ("head", "blocks.1.", "blocks.0.", "embed"):
+        eng.grad_ready_hook(stage)
+    red.finish()
+    expect = float(sum(r + 1 for r in range(world)))
+    ok = bool(torch.all(eng.flat.grads == expect))
+    overlapped = any(stage != "embed" for stage, _ in red.launched_log)       # some bucket left before backward ended
+    folds = parallel.shard_folds(5, rank, world)
+    logits = torch.stack([torch.full((3, 2), float(f)) for f in folds]) if folds else torch.zeros(0, 3, 2)
+    full = parallel.gather_fold_logits(logits, folds, 5)
+    ok_folds = bool(all(torch.all(full[f] == f) for f in range(5)))
+    Path(tmp, f"r{rank}.txt").write_text(f"{ok} {overlapped} {ok_folds} {len(red.buckets)}")
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_and_fold_sharding_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        ok, overlapped, ok_folds, nb = (tmp_path / f"r{r}.txt").read_text().split()
+        assert ok == "True" and overlapped == "True" and ok_folds == "True" and int(nb) >= 2
+
+
+def test_cfg_get_and_label_handling():
+    assert training.cfg_get({"a": 1}, "a") == 1 and training.cfg_get(None, "a", 5) == 5
+
+    class C:
+        x = 3
+
+        def get(self, k, d=None):
+            return {"y": 4}.get(k, d)
+    assert training.cfg_get(C(), "x") == 3 and training.cfg_get(C(), "y") == 4 and training.cfg_get(C(), "z", 9) == 9
+    assert training._labels(torch.tensor([[1], [0]], dtype=torch.int32)).tolist() == [1, 0]
+    assert parallel.shard_folds(5, 1, 8) == [1] and parallel.shard_folds(5, 0, 2) == [0, 2, 4]
