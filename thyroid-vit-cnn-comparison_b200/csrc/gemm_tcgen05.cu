@@ -44,6 +44,7 @@ struct GemmParams {
   int kblocks_per_split;
   int num_m_tiles, num_n_tiles, num_splits;
   int epilogue, out_dtype, aux_dtype;
+  int epi16;  // 16-bit output without residual: row-per-thread math, swizzled 16-bit staging, TMA store
   uint32_t idesc;
   float alpha;
   const float* alpha_dev;
@@ -140,6 +141,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -225,10 +235,29 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float4 f, co
   }
 }
 
+// 32 rows x 32 16-bit columns (64-byte rows) staged in the TMA SWIZZLE_64B layout: 16-byte chunk c of row r lives at
+// r*64 + ((c ^ ((r >> 1) & 3)) << 4)  -- conflict-free for row-per-lane 128-bit accesses.
+__device__ __forceinline__ uint32_t swz64(int r, int c) { return uint32_t(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+// Stage one packed 32x32 16-bit chunk (h[16] = this lane's row) and hand it to the TMA store engine.
+__device__ __forceinline__ void stage_and_store(uint8_t* sbuf, const uint32_t (&h)[16], const CUtensorMap* tm, int col0, int row0,
+                                                int lane) {
+  if (lane == 0) tma_store_wait_read();  // the previous store issued from this buffer has finished READING it
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(sbuf + swz64(lane, c)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) tma_store_2d(tm, sbuf, col0, row0);
+}
+
 // ------------------------------------------------------------------ the kernel
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                        const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -245,7 +274,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;         // [EPI_WARPS] per-warp TMA-load barrier (dGELU pre-activation chunk)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -263,6 +293,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
     }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -353,7 +384,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
     const int c4 = lane & 3;     // float4 column slot of this lane inside a 16-column half chunk
     const int rsub = lane >> 2;  // row (mod 8) this lane handles when reading the staged half chunk back
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, aux_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       int m0, n0, kb0, nk;
       decode(tile, m0, n0, kb0, nk);
@@ -366,6 +397,55 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int c0 = group * 32; c0 < BN; c0 += 32 * (EPI_WARPS / 4)) {
         const int col0 = n0 + c0;
         if (col0 >= p.N) break;  // warp-uniform
+        if (p.epi16) {
+          // ---- 16-bit outputs: math in the row-per-lane TMEM layout, swizzled 16-bit staging, TMA store ----
+          uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage);
+          const bool h16 = p.out_dtype == VITK_FP16;
+          if (p.epilogue == VITK_EPI_DGELU && lane == 0) {  // fetch the saved pre-activation chunk while TMEM is read
+            tma_store_wait_read();
+            mbar_expect_tx(&aux_bar[warp - 2], 32 * 64);
+            tma_load_2d(sbuf, &tmAux, &aux_bar[warp - 2], col0, row_base);
+          }
+          uint32_t v[32];
+          tmem_ld32(t_addr + uint32_t(c0), v);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < p.N) {
+                const float4 b4 = ldg_f4(p.bias + col0 + j);  // warp-uniform address: one broadcast wavefront
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            }
+          }
+          uint32_t h[16];
+          if (p.epilogue == VITK_EPI_DGELU) {
+            const bool ah = p.aux_dtype == VITK_FP16;
+            mbar_wait(&aux_bar[warp - 2], aux_phase, 5);
+            aux_phase ^= 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 a = *reinterpret_cast<const uint4*>(sbuf + swz64(lane, c));
+              const float2 a0 = unpack16(a.x, ah), a1 = unpack16(a.y, ah), a2 = unpack16(a.z, ah), a3 = unpack16(a.w, ah);
+              f[8 * c + 0] *= gelu_erf_grad(a0.x); f[8 * c + 1] *= gelu_erf_grad(a0.y);
+              f[8 * c + 2] *= gelu_erf_grad(a1.x); f[8 * c + 3] *= gelu_erf_grad(a1.y);
+              f[8 * c + 4] *= gelu_erf_grad(a2.x); f[8 * c + 5] *= gelu_erf_grad(a2.y);
+              f[8 * c + 6] *= gelu_erf_grad(a3.x); f[8 * c + 7] *= gelu_erf_grad(a3.y);
+            }
+            __syncwarp();  // every lane has read its pre-activation row before the buffer is reused for the output
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = pack16(f[2 * j], f[2 * j + 1], h16);
+          stage_and_store(sbuf, h, &tmOut, col0, row_base, lane);
+          if (p.epilogue == VITK_EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = pack16(gelu_erf(f[2 * j]), gelu_erf(f[2 * j + 1]), h16);
+            stage_and_store(sbuf, h, &tmOut2, col0, row_base, lane);
+          }
+          continue;
+        }
         uint32_t v[32];
         tmem_ld32(t_addr + uint32_t(c0), v);
         // transpose through smem in two 16-column halves: lane = row on the way in,
@@ -406,6 +486,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) tma_store_wait_all();  // outstanding TMA stores must complete before the CTA (and its smem) goes away
   }
 
   tcgen05_fence_before();
@@ -428,7 +509,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D 16-bit tensor map over a row-major [outer, inner] matrix, 128B swizzle, zero OOB fill.
 int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
-                 uint32_t box_outer, bool fp16) {
+                 uint32_t box_outer, bool fp16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -439,7 +520,7 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (base=%p inner=%llu outer=%llu pitch=%llu box=%ux%u)", (int)r, base,
@@ -450,8 +531,8 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 + (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
@@ -459,18 +540,18 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  kfn<<<grid, GEMM_THREADS, SMEM, st>>>(tmA, tmB, p);
+  kfn<<<grid, GEMM_THREADS, SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+int dispatch_gemm(int bn, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
   switch (bn) {
-    case 64:  return launch_gemm<64, 8, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 128: return launch_gemm<128, 6, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 192: return launch_gemm<192, 4, A_MN, B_MN>(tmA, tmB, p, grid, st);
-    case 256: return launch_gemm<256, 4, A_MN, B_MN>(tmA, tmB, p, grid, st);
+    case 64:  return launch_gemm<64, 8, A_MN, B_MN>(tm, p, grid, st);
+    case 128: return launch_gemm<128, 6, A_MN, B_MN>(tm, p, grid, st);
+    case 192: return launch_gemm<192, 4, A_MN, B_MN>(tm, p, grid, st);
+    case 256: return launch_gemm<256, 4, A_MN, B_MN>(tm, p, grid, st);
     default:
       set_error("unsupported BLOCK_N %d", bn);
       return VITK_ERR_UNSUPPORTED;
@@ -551,21 +632,42 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.aux = a->aux; p.ldaux = a->ldaux;
   p.rows_per_img = a->rows_per_img; p.tokens_per_img = a->tokens_per_img; p.prefix = a->prefix; p.pos = a->pos;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tm[5];  // A, B, out, out2, aux
   int rc;
   const bool ah = a->a_dtype == VITK_FP16, bh = a->b_dtype == VITK_FP16;
-  if (!a->a_mn_major) rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M, ah);
-  else                rc = make_tmap_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K, ah);
+  if (!a->a_mn_major) rc = make_tmap_2d(&tm[0], a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M, ah);
+  else                rc = make_tmap_2d(&tm[0], a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K, ah);
   if (rc != VITK_OK) return rc;
-  if (!a->b_mn_major) rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, bh);
-  else                rc = make_tmap_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, bh);
+  if (!a->b_mn_major) rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, bh);
+  else                rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, bh);
   if (rc != VITK_OK) return rc;
+  // 16-bit outputs without a residual go out through TMA stores of 32x32 chunks (64-byte rows, SWIZZLE_64B)
+  p.epi16 = (!out_fp32 && a->residual == nullptr &&
+             (a->epilogue == VITK_EPI_STORE || a->epilogue == VITK_EPI_GELU || a->epilogue == VITK_EPI_DGELU) &&
+             a->ldo % 8 == 0 && (a->epilogue != VITK_EPI_GELU || (a->ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0)) &&
+             (a->epilogue != VITK_EPI_DGELU || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)))
+                ? 1 : 0;
+  tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];
+  if (p.epi16) {
+    const bool oh = a->out_dtype == VITK_FP16;
+    rc = make_tmap_2d(&tm[2], a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, oh, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != VITK_OK) return rc;
+    if (a->epilogue == VITK_EPI_GELU) {
+      rc = make_tmap_2d(&tm[3], a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo2, 32, 32, oh, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != VITK_OK) return rc;
+    }
+    if (a->epilogue == VITK_EPI_DGELU) {
+      rc = make_tmap_2d(&tm[4], a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldaux, 32, 32, a->aux_dtype == VITK_FP16,
+                        CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != VITK_OK) return rc;
+    }
+  }
 
   const long long total_tiles = (long long)p.num_m_tiles * p.num_n_tiles * splits;
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, tmA, tmB, p, grid, st);
-  if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, tmA, tmB, p, grid, st);
-  if (a->a_mn_major && a->b_mn_major) return dispatch_gemm<true, true>(bn, tmA, tmB, p, grid, st);
-  return dispatch_gemm<true, false>(bn, tmA, tmB, p, grid, st);
+  if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, tm, p, grid, st);
+  if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, tm, p, grid, st);
+  if (a->a_mn_major && a->b_mn_major) return dispatch_gemm<true, true>(bn, tm, p, grid, st);
+  return dispatch_gemm<true, false>(bn, tm, p, grid, st);
 }
