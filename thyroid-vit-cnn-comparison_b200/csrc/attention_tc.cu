@@ -1,0 +1,564 @@
+// attention_tc.cu -- fused softmax attention on the 5th-gen tensor cores (tcgen05.mma, S / P / O and every backward
+// accumulator resident in TMEM, operands staged by TMA), head_dim 64, sequences of up to 256 tokens
+// (every 224x224 / 256x256... configuration of the reference with N = 197 / 198; longer sequences use attention.cu).
+//
+// Replaces Attention.forward's q@k^T*scale -> softmax -> attn@v (vision_transformer_base.py:182-191) and its autograd
+// backward.  Layouts are the reference's own: qkv [B,N,3,H,64] as nn.Linear(D,3D) emits it (:178), out [B,N,H,64] =
+// (attn@v).transpose(1,2).reshape(B,N,C) (:191).  The [B,H,N,N] score tensor never exists in HBM.
+//
+// Forward  (one CTA per (128-query tile, head, image); 4 softmax warps + 1 TMA/MMA warp; 256 TMEM columns, 2 CTAs/SM)
+//   S[128 x KP] = Q K^T            tcgen05.mma SS, fp32 in TMEM columns [0, KP)
+//   P = exp2(S*c - max*c)          one thread per query row (tcgen05.ld), written back IN PLACE as 16-bit (tcgen05.st)
+//   O[128 x 64] = P V              tcgen05.mma TS (A = P from TMEM, B = V MN-major from smem), TMEM columns [128, 192)
+//   out = O / rowsum               TMEM -> registers -> swizzled smem -> TMA store (rows >= N clipped by the tensor map)
+//
+// Backward (one CTA per (head, image); 8 math warps + 1 TMA/MMA warp; all 512 TMEM columns).  For every 128-key tile j
+// and every <=128-query chunk c:
+//   S^T = K_j Q_c^T, dP^T = V_j dO_c^T             (SS)  columns [0,128), [128,256); lane = key, column = query
+//   P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - delta)   16-bit, written IN PLACE over the half of the columns each
+//                                                   warp consumed; dS is also staged MN-major in smem (A operand of dQ)
+//   dV_j += P^T dO_c, dK_j += dS^T Q_c             (TS)  columns [256,320), [320,384)
+//   dQ_c += dS K_j                                 (SS)  columns [384,448) / [448,512), accumulated over j
+// so K, V, Q, dO are read from HBM exactly once and nothing is recomputed or reduced through global memory.
+#include "tc_common.cuh"
+
+namespace vitk {
+namespace {
+
+using namespace tc;
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int DH = 64;
+constexpr int O_COL = 128;  // forward: TMEM column of the O accumulator (P occupies [0, KP/2) <= 128)
+
+template <bool H16>
+__device__ __forceinline__ uint32_t pk16(float lo, float hi) {
+  if (H16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ================================================================================================ forward
+constexpr int FWD_THREADS = 160;
+
+template <bool H16>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+    attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                       const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KP, float scale,
+                       float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                       // [128][64] 16-bit, later the output staging tile
+  uint8_t* sK = sQ + 128 * 128;             // [KP][64]
+  uint8_t* sV = sK + KP * 128;              // [KP][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KP * 128);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmKV);
+      prefetch_tmap(&tmO);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      mbar_init_fence();
+      mbar_expect_tx(bar_qk, (128 + KP) * 128);
+      tma_load_3d(sQ, &tmQ, bar_qk, h * DH, q0, b);
+      tma_load_3d(sK, &tmKV, bar_qk, (H + h) * DH, 0, b);
+      mbar_expect_tx(bar_v, KP * 128);
+      tma_load_3d(sV, &tmKV, bar_v, (2 * H + h) * DH, 0, b);
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== MMA issuer =====================
+    mbar_wait(bar_qk, 0, 1);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc_s = idesc_f16(KP, false, false, H16);
+      const uint64_t adesc = smem_desc_kmajor(smem_u32(sQ));
+      const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(tb, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_p, 0, 2);
+    mbar_wait(bar_v, 0, 3);
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc_o = idesc_f16(DH, false, true, H16);
+      const uint64_t vdesc = smem_desc_mnmajor(smem_u32(sV), 8192);
+      const int steps = KP >> 4;
+      for (int s = 0; s < steps; ++s)
+        umma_ts(tb + O_COL, tb + uint32_t(8 * s), vdesc + uint64_t(s * (2048 >> 4)), idesc_o, s > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue: one thread per query row =====================
+    const int row = warp * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t trow = tb + (uint32_t(warp * 32) << 16);
+    mbar_wait(bar_s, 0, 4);
+    tc_fence_after();
+    // pass 1: row maximum over the valid keys
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < KP; c0 += 32) {
+      uint32_t v[32];
+      if (KP - c0 >= 32) {
+        tmem_ld32_nowait(trow + uint32_t(c0), v);
+      } else {
+        tmem_ld16_nowait(trow + uint32_t(c0), v);
+#pragma unroll
+        for (int j = 16; j < 32; ++j) v[j] = 0xff800000u;  // -inf
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c0 + j < N) ? __uint_as_float(v[j]) : -INFINITY);
+    }
+    // pass 2: P = exp2((S - max) * scale * log2e), 16-bit, in place
+    const float msc = mx * scale_log2;
+    float sum = 0.f;
+    for (int c0 = 0; c0 < KP; c0 += 32) {
+      uint32_t v[32];
+      const bool full = KP - c0 >= 32;
+      if (full) {
+        tmem_ld32_nowait(trow + uint32_t(c0), v);
+      } else {
+        tmem_ld16_nowait(trow + uint32_t(c0), v);
+#pragma unroll
+        for (int j = 16; j < 32; ++j) v[j] = 0u;
+      }
+      tmem_ld_wait();
+      uint32_t ph[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = (c0 + j < N) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2, -msc)) : 0.f;
+        const float p1 = (c0 + j + 1 < N) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2, -msc)) : 0.f;
+        sum += p0 + p1;
+        ph[j >> 1] = pk16<H16>(p0, p1);
+      }
+      if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
+      else tmem_st8_nowait(trow + uint32_t(c0 >> 1), ph);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    if (q < N) lse[((long long)b * H + h) * N + q] = fmaf(mx, scale, logf(sum));
+    const float inv = 1.f / sum;
+    // epilogue: O / rowsum -> 16-bit -> swizzled staging (the Q tile is dead once S exists) -> TMA store
+    mbar_wait(bar_o, 0, 5);
+    tc_fence_after();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];
+      tmem_ld32_nowait(trow + uint32_t(O_COL + 32 * hh), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o;
+        o.x = pk16<H16>(__uint_as_float(v[8 * c + 0]) * inv, __uint_as_float(v[8 * c + 1]) * inv);
+        o.y = pk16<H16>(__uint_as_float(v[8 * c + 2]) * inv, __uint_as_float(v[8 * c + 3]) * inv);
+        o.z = pk16<H16>(__uint_as_float(v[8 * c + 4]) * inv, __uint_as_float(v[8 * c + 5]) * inv);
+        o.w = pk16<H16>(__uint_as_float(v[8 * c + 6]) * inv, __uint_as_float(v[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(sQ + swz128(row, 4 * hh + c)) = o;
+      }
+    }
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmO, sQ, h * DH, q0, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tb);
+}
+
+// ================================================================================================ backward
+constexpr int BWD_THREADS = 288;  // 8 math warps + 1 control warp
+constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+// One 32- or 16-column group of the backward math: thread = key lane, columns = queries g0 .. g0+W-1 of chunk c.
+template <bool H16, int W>
+__device__ __forceinline__ void bwd_math_group(uint32_t trow, int g0, int pcol, const float* __restrict__ s_lse2,
+                                               const float* __restrict__ s_delta, int qbase, float scale_log2, bool keyvalid,
+                                               uint8_t* sDS, int keyrow) {
+  uint32_t sv[W], dv[W];
+  if constexpr (W == 32) {
+    tmem_ld32_nowait(trow + uint32_t(TM_S + g0), sv);
+    tmem_ld32_nowait(trow + uint32_t(TM_DP + g0), dv);
+  } else {
+    tmem_ld16_nowait(trow + uint32_t(TM_S + g0), sv);
+    tmem_ld16_nowait(trow + uint32_t(TM_DP + g0), dv);
+  }
+  tmem_ld_wait();
+  uint32_t ph[W / 2], dh[W / 2];
+#pragma unroll
+  for (int e = 0; e < W; e += 4) {
+    const float4 l4 = *reinterpret_cast<const float4*>(s_lse2 + qbase + g0 + e);   // warp-uniform address: broadcast
+    const float4 d4 = *reinterpret_cast<const float4*>(s_delta + qbase + g0 + e);
+    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e + 0]), scale_log2, -l4.x));
+    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), scale_log2, -l4.y));
+    const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e + 2]), scale_log2, -l4.z));
+    const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e + 3]), scale_log2, -l4.w));
+    const float s0 = p0 * (__uint_as_float(dv[e + 0]) - d4.x);
+    const float s1 = p1 * (__uint_as_float(dv[e + 1]) - d4.y);
+    const float s2 = p2 * (__uint_as_float(dv[e + 2]) - d4.z);
+    const float s3 = p3 * (__uint_as_float(dv[e + 3]) - d4.w);
+    ph[(e >> 1) + 0] = pk16<H16>(p0, p1);
+    ph[(e >> 1) + 1] = pk16<H16>(p2, p3);
+    dh[(e >> 1) + 0] = pk16<H16>(s0, s1);
+    dh[(e >> 1) + 1] = pk16<H16>(s2, s3);
+  }
+  if (!keyvalid) {  // padded key lane (its S / dP rows are garbage, possibly non-finite): contributes exactly zero
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) ph[i] = dh[i] = 0u;
+  }
+  if constexpr (W == 32) {
+    tmem_st16_nowait(trow + uint32_t(TM_S + pcol), ph);
+    tmem_st16_nowait(trow + uint32_t(TM_DP + pcol), dh);
+  } else {
+    tmem_st8_nowait(trow + uint32_t(TM_S + pcol), ph);
+    tmem_st8_nowait(trow + uint32_t(TM_DP + pcol), dh);
+  }
+  // dS, MN-major A operand of dQ = dS K: 64-query blocks of [128 key rows][128 B], 128B swizzle
+#pragma unroll
+  for (int ch = 0; ch < W / 8; ++ch) {
+    const int ql = g0 + 8 * ch;  // query index inside the chunk
+    *reinterpret_cast<uint4*>(sDS + (ql >> 6) * 16384 + swz128(keyrow, (ql & 63) >> 3)) =
+        make_uint4(dh[4 * ch], dh[4 * ch + 1], dh[4 * ch + 2], dh[4 * ch + 3]);
+  }
+}
+
+template <bool H16>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+    attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                       const __grid_constant__ CUtensorMap tmDQKV, const float* __restrict__ lse, const float* __restrict__ delta,
+                       int N, int H, int QP, float scale, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int tile_bytes = QP * 128;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + tile_bytes;
+  uint8_t* sV = sK + tile_bytes;
+  uint8_t* sDO = sV + tile_bytes;
+  uint8_t* sDS = sDO + tile_bytes;   // 2 x [128][128 B]
+  uint8_t* sOut = sDS + 32768;       // 2 x [128][128 B]
+  float* s_lse2 = reinterpret_cast<float*>(sOut + 32768);  // [256]
+  float* s_delta = s_lse2 + 256;                            // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+  uint64_t* bar_load = bars + 0;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;
+  uint64_t* bar_m2 = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int NJ = (N + 127) >> 7;   // 128-key tiles
+  const int NC = NJ;               // <=128-query chunks
+  const int T = NJ * NC;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQKV);
+      prefetch_tmap(&tmDO);
+      prefetch_tmap(&tmDQKV);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_m2, 1);
+      mbar_init_fence();
+      mbar_expect_tx(bar_load, 4 * tile_bytes);
+      tma_load_3d(sK, &tmQKV, bar_load, (H + h) * DH, 0, b);
+      tma_load_3d(sQ, &tmQKV, bar_load, h * DH, 0, b);
+      tma_load_3d(sV, &tmQKV, bar_load, (2 * H + h) * DH, 0, b);
+      tma_load_3d(sDO, &tmDO, bar_load, h * DH, 0, b);
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else {
+    // per-query statistics: lse in the log2 domain (+inf masks the padded queries: P = exp2(-inf) = 0), delta
+    const float* lse_b = lse + ((long long)b * H + h) * N;
+    const float* del_b = delta + ((long long)b * H + h) * N;
+    const int i = threadIdx.x;  // 0..255
+    s_lse2[i] = i < N ? lse_b[i] * LOG2E : INFINITY;
+    s_delta[i] = i < N ? del_b[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== MMA issuer =====================
+    mbar_wait(bar_load, 0, 1);
+    tc_fence_after();
+    const uint32_t idesc64_ts = idesc_f16(DH, false, true, H16);   // A from TMEM (K-major), B MN-major
+    const uint32_t idesc64_mn = idesc_f16(DH, true, true, H16);    // A, B MN-major from smem
+    auto issue_g1 = [&](int j, int c) {
+      const int QC = min(128, QP - 128 * c);
+      const uint32_t idesc_s = idesc_f16(QC, false, false, H16);
+      const uint64_t kd = smem_desc_kmajor(smem_u32(sK + j * 16384));
+      const uint64_t qd = smem_desc_kmajor(smem_u32(sQ + c * 16384));
+      const uint64_t vd = smem_desc_kmajor(smem_u32(sV + j * 16384));
+      const uint64_t dd = smem_desc_kmajor(smem_u32(sDO + c * 16384));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(tb + TM_S, kd + uint64_t(2 * k), qd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(tb + TM_DP, vd + uint64_t(2 * k), dd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    };
+    if (lane == 0) issue_g1(0, 0);
+    __syncwarp();
+    int t = 0;
+    for (int j = 0; j < NJ; ++j) {
+      for (int c = 0; c < NC; ++c, ++t) {
+        mbar_wait(bar_p, t & 1, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const int QC = min(128, QP - 128 * c);
+          const int HB = ((QC >> 1) + 15) & ~15;
+          const int KJ = min(128, QP - 128 * j);
+          const int qsteps = QC >> 4;
+          for (int s = 0; s < qsteps; ++s) {   // dV_j += P^T dO_c
+            const int qo = 16 * s;
+            const int acol = qo < HB ? (qo >> 1) : HB + ((qo - HB) >> 1);
+            const uint64_t bd = smem_desc_mnmajor(smem_u32(sDO + (c * 128 + qo) * 128), 8192);
+            umma_ts(tb + TM_DV, tb + uint32_t(TM_S + acol), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
+          }
+          for (int s = 0; s < qsteps; ++s) {   // dK_j += dS^T Q_c
+            const int qo = 16 * s;
+            const int acol = qo < HB ? (qo >> 1) : HB + ((qo - HB) >> 1);
+            const uint64_t bd = smem_desc_mnmajor(smem_u32(sQ + (c * 128 + qo) * 128), 8192);
+            umma_ts(tb + TM_DK, tb + uint32_t(TM_DP + acol), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
+          }
+          const int ksteps = KJ >> 4;
+          for (int s = 0; s < ksteps; ++s) {   // dQ_c += dS K_j
+            const uint64_t ad = smem_desc_mnmajor(smem_u32(sDS + s * 2048), 16384);
+            const uint64_t bd = smem_desc_mnmajor(smem_u32(sK + (j * 128 + 16 * s) * 128), 8192);
+            umma_ss(tb + uint32_t(TM_DQ + 64 * c), ad, bd, idesc64_mn, (j > 0 || s > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_m2);
+          if (t + 1 < T) {
+            const int c1 = (c + 1 == NC) ? 0 : c + 1;
+            const int j1 = (c + 1 == NC) ? j + 1 : j;
+            issue_g1(j1, c1);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== math warps: lane quadrant = warp % 4, column half = warp / 4 =====================
+    const int quad = warp & 3, half = warp >> 2;
+    const int keyrow = quad * 32 + lane;
+    const uint32_t trow = tb + (uint32_t(quad * 32) << 16);
+    const int tid = threadIdx.x;  // 0..255
+    int t = 0;
+    for (int j = 0; j < NJ; ++j) {
+      const bool keyvalid = (j * 128 + keyrow) < N;
+      for (int c = 0; c < NC; ++c, ++t) {
+        const int QC = min(128, QP - 128 * c);
+        const int HB = ((QC >> 1) + 15) & ~15;
+        const int cbeg = half == 0 ? 0 : HB, cend = half == 0 ? HB : QC;
+        mbar_wait(bar_s, t & 1, 3);
+        tc_fence_after();
+        int g0 = cbeg;
+        for (; g0 + 32 <= cend; g0 += 32)
+          bwd_math_group<H16, 32>(trow, g0, cbeg + ((g0 - cbeg) >> 1), s_lse2, s_delta, c * 128, scale_log2, keyvalid, sDS, keyrow);
+        if (g0 < cend)
+          bwd_math_group<H16, 16>(trow, g0, cbeg + ((g0 - cbeg) >> 1), s_lse2, s_delta, c * 128, scale_log2, keyvalid, sDS, keyrow);
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(bar_p);
+        if (c == NC - 1) {
+          // ---- key tile j is complete: dV_j (half 0) / dK_j (half 1) -> 16-bit -> staging -> TMA store
+          mbar_wait(bar_m2, t & 1, 4);
+          tc_fence_after();
+          if (tid == 0) tma_store_wait_read();  // earlier stores have finished reading sOut
+          named_bar_sync(1, 256);
+          const float mul = half == 0 ? 1.f : scale;
+          uint8_t* dst = sOut + half * 16384;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32_nowait(trow + uint32_t((half == 0 ? TM_DV : TM_DK) + 32 * hh), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 o;
+              o.x = pk16<H16>(__uint_as_float(v[8 * cc + 0]) * mul, __uint_as_float(v[8 * cc + 1]) * mul);
+              o.y = pk16<H16>(__uint_as_float(v[8 * cc + 2]) * mul, __uint_as_float(v[8 * cc + 3]) * mul);
+              o.z = pk16<H16>(__uint_as_float(v[8 * cc + 4]) * mul, __uint_as_float(v[8 * cc + 5]) * mul);
+              o.w = pk16<H16>(__uint_as_float(v[8 * cc + 6]) * mul, __uint_as_float(v[8 * cc + 7]) * mul);
+              *reinterpret_cast<uint4*>(dst + swz128(keyrow, 4 * hh + cc)) = o;
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          named_bar_sync(1, 256);
+          if (tid == 0) {
+            tma_store_3d(&tmDQKV, sOut, (2 * H + h) * DH, j * 128, b);          // dV_j
+            tma_store_3d(&tmDQKV, sOut + 16384, (H + h) * DH, j * 128, b);      // dK_j
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    // ---- dQ chunks (accumulated over all key tiles): half c handles chunk c
+    if (tid == 0) tma_store_wait_read();
+    named_bar_sync(1, 256);
+    if (half < NC) {
+      uint8_t* dst = sOut + half * 16384;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32_nowait(trow + uint32_t(TM_DQ + 64 * half + 32 * hh), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 o;
+          o.x = pk16<H16>(__uint_as_float(v[8 * cc + 0]) * scale, __uint_as_float(v[8 * cc + 1]) * scale);
+          o.y = pk16<H16>(__uint_as_float(v[8 * cc + 2]) * scale, __uint_as_float(v[8 * cc + 3]) * scale);
+          o.z = pk16<H16>(__uint_as_float(v[8 * cc + 4]) * scale, __uint_as_float(v[8 * cc + 5]) * scale);
+          o.w = pk16<H16>(__uint_as_float(v[8 * cc + 6]) * scale, __uint_as_float(v[8 * cc + 7]) * scale);
+          *reinterpret_cast<uint4*>(dst + swz128(keyrow, 4 * hh + cc)) = o;
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    named_bar_sync(1, 256);
+    if (tid == 0) {
+      for (int c = 0; c < NC; ++c) tma_store_3d(&tmDQKV, sOut + c * 16384, h * DH, c * 128, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tb);
+}
+
+// ------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// 3-D 16-bit tensor map over [B][N][width] (row-major), box = 1 x box_rows x 64 columns, 128B swizzle.  Rows >= N are
+// zero-filled on load and clipped on store, so ragged sequences (197 / 198 tokens) need no masking in the data path.
+int make_tmap_3d(CUtensorMap* tm, const void* base, int width, int N, int B, int box_rows, bool fp16) {
+  auto fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return VITK_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)N * width * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d (base=%p width=%d N=%d B=%d box_rows=%d)", (int)r, base, width, N, B,
+              box_rows);
+    return VITK_ERR_CUDA;
+  }
+  return VITK_OK;
+}
+
+}  // namespace
+
+// Forward for N <= 256.  Returns VITK_OK or an error; the caller (attention.cu) owns argument validation.
+template <bool H16>
+int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st) {
+  const int KP = (N + 15) & ~15;
+  CUtensorMap tmQ, tmKV, tmO;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KP, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  const int smem = 128 * 128 + 2 * KP * 128 + 64 + 1024;
+  auto kfn = attn_fwd_tc_kernel<H16>;
+  static int configured = 0;
+  if (configured < smem) {
+    VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 + 2 * 256 * 128 + 64 + 1024));
+    configured = 128 * 128 + 2 * 256 * 128 + 64 + 1024;
+  }
+  dim3 grid((N + 127) / 128, H, B);
+  kfn<<<grid, FWD_THREADS, smem, st>>>(tmQ, tmKV, tmO, lse, N, H, KP, scale, scale * LOG2E);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+template <bool H16>
+int attention_bwd_tc_impl(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
+                          float scale, cudaStream_t st) {
+  const int QP = (N + 15) & ~15;
+  CUtensorMap tmQKV, tmDO, tmDQKV;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQKV, qkv, 3 * H * DH, N, B, QP, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmDO, dout, H * DH, N, B, QP, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmDQKV, dqkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  const int smem = 4 * QP * 128 + 65536 + 2048 + 64 + 1024;
+  const int smem_max = 4 * 256 * 128 + 65536 + 2048 + 64 + 1024;
+  auto kfn = attn_bwd_tc_kernel<H16>;
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    configured = true;
+  }
+  dim3 grid(H, B);
+  kfn<<<grid, BWD_THREADS, smem, st>>>(tmQKV, tmDO, tmDQKV, lse, delta, N, H, QP, scale, scale * LOG2E);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {
+  return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, st)
+              : attention_fwd_tc_impl<false>(qkv, out, lse, B, N, H, scale, st);
+}
+int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
+                     float scale, bool fp16, cudaStream_t st) {
+  return fp16 ? attention_bwd_tc_impl<true>(qkv, dout, lse, delta, dqkv, B, N, H, scale, st)
+              : attention_bwd_tc_impl<false>(qkv, dout, lse, delta, dqkv, B, N, H, scale, st);
+}
+
+}  // namespace vitk
