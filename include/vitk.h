@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 4
+#define VITK_ABI_VERSION 5
 
 typedef enum {
   VITK_OK = 0,
@@ -61,8 +61,9 @@ typedef enum { VITK_BF16 = 0, VITK_FP32 = 1, VITK_FP16 = 2 } vitk_dtype;
 
 typedef enum {
   VITK_EPI_STORE = 0,      /* out = acc*alpha + bias + residual                               */
-  VITK_EPI_GELU = 1,       /* out = pre-activation (bf16), out2 = gelu_erf(pre) (bf16)        */
-  VITK_EPI_DGELU = 2,      /* out = acc * gelu_erf'(aux)  (aux = saved pre-activation, bf16)  */
+  VITK_EPI_GELU = 1,       /* pre = acc*alpha + bias: out = gelu_erf'(pre), out2 = gelu_erf(pre) (16-bit): the    */
+                           /* derivative is all backward needs, and one erf evaluation yields both               */
+  VITK_EPI_DGELU = 2,      /* out = acc * aux  (aux = the derivative saved by VITK_EPI_GELU, 16-bit)              */
   VITK_EPI_ATOMIC_ADD = 3, /* out(fp32) += acc*alpha  (split-K wgrad, red.global.add.f32)     */
   VITK_EPI_TOKENS = 4      /* patch rows -> token rows: out[b, prefix+p, :] = acc+bias+pos    */
 } vitk_epilogue;
@@ -89,7 +90,7 @@ typedef struct {
   int64_t ldo;
   void* out2;             /* [M, ldo2], same dtype as out (GELU: the activation) */
   int64_t ldo2;
-  const void* aux;        /* bf16 [M, ldaux] (DGELU) */
+  const void* aux;        /* 16-bit [M, ldaux] (DGELU: saved gelu'(pre)) */
   int64_t ldaux;
   /* VITK_EPI_TOKENS: input row r = b*rows_per_img + p  ->  output row b*tokens_per_img + prefix + p,
    * pos is fp32 [tokens_per_img, N] (pos_embed), added to the row it lands on. */

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -80,7 +80,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         mod.build()
-    lib = C.CDLL(str(LIB_PATH))
+    # VITK_LIB: load another build of the same C-ABI (e.g. the profiling build of tools/build_dbg.py)
+    lib = C.CDLL(os.environ.get("VITK_LIB") or str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == header / library mismatch
         fn.restype = res

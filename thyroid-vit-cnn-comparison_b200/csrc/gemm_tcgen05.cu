@@ -26,6 +26,30 @@
 
 #include "vitk_common.cuh"
 
+#ifdef VITK_GEMM_KNOBS
+#include <stdlib.h>
+#define KNOB(x) ((p.knobs & (x)) != 0)
+// per-tile timeline of CTA 0 (profiling build only): [role][tile][event] SM clock stamps
+__device__ long long g_vitk_dbg[3 * 64 * 4];
+#define DBG_STAMP(role, t, ev)                                                              \
+  do {                                                                                      \
+    if (KNOB(64) && blockIdx.x == 0 && (t) < 64) g_vitk_dbg[((role) * 64 + (t)) * 4 + (ev)] = clock64(); \
+  } while (0)
+__device__ long long g_vitk_dbg2[8 * 4 * 8];  // [tile][unit][event] of epilogue warp 2
+#define DBG_UNIT(t, u, ev)                                                                                   \
+  do {                                                                                                       \
+    if (KNOB(64) && blockIdx.x == 0 && warp == 2 && lane == 0 && (t) < 8 && (u) < 4) g_vitk_dbg2[((t) * 4 + (u)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define KNOB(x) false
+#define DBG_UNIT(t, u, ev) \
+  do {                     \
+  } while (0)
+#define DBG_STAMP(role, t, ev) \
+  do {                         \
+  } while (0)
+#endif
+
 namespace vitk {
 
 namespace {
@@ -36,15 +60,22 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 12;  // three warps per TMEM lane quadrant, interleaved over the 32-column chunks
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_PITCH = 20;  // floats per staged row (16 + 4 pad: conflict-free 128-bit accesses)
-constexpr int EPI_STAGE_FLOATS = 32 * EPI_PITCH;
+constexpr int EPI_STAGE_FLOATS = 1024;  // per warp: 32 x EPI_PITCH floats (fp32 path) or two 2 KB TMA-store buffers (16-bit path)
+static_assert(EPI_STAGE_FLOATS >= 32 * EPI_PITCH, "staging buffer too small");
+constexpr int MAX_BIAS_SMEM = 3328;  // floats (13 KB): bias of every supported layer (N <= 3072, rounded up to the N tile)
 
 struct GemmParams {
   int M, N, K;
   int num_kblocks;
   int kblocks_per_split;
   int num_m_tiles, num_n_tiles, num_splits;
+  int step_split, step_mt, step_nt;  // mixed-radix digits of the grid size over (split, m tile, n tile)
   int epilogue, out_dtype, aux_dtype;
-  int epi16;  // 16-bit output without residual: row-per-thread math, swizzled 16-bit staging, TMA store
+  int tma_epi;     // STORE / GELU / DGELU epilogues: row-per-lane math, 2 KB swizzled staging units, TMA loads (residual / saved
+                   // derivative) and TMA stores -- no per-thread global access in the epilogue
+  int knobs;  // profiling only (-DVITK_GEMM_KNOBS build, tools/build_dbg.py): 1 no TMA stores, 2 no epilogue math/stores,
+              // 4 B operand loaded for the first tile of a CTA only, 8 A operand likewise, 16 epilogue does not even read TMEM,
+              // 32 no MMAs issued (results are then wrong)
   uint32_t idesc;
   float alpha;
   const float* alpha_dev;
@@ -100,6 +131,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// true in exactly one (converged) lane of the warp; lets ptxas issue the uniform-datapath TMA / MMA instructions
+// without the per-instruction "waterfall" loops it emits around `if (lane == 0)`
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -141,6 +183,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_u32(smem_src)),
                "r"(c0), "r"(c1)
@@ -148,6 +200,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
@@ -215,17 +268,18 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float4 f, co
     } break;
     case VITK_EPI_GELU: {
       const bool h = p.out_dtype == VITK_FP16;
+      float4 g, d;
+      gelu_erf_both(f.x, g.x, d.x); gelu_erf_both(f.y, g.y, d.y); gelu_erf_both(f.z, g.z, d.z); gelu_erf_both(f.w, g.w, d.w);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col) =
-          make_uint2(pack16(f.x, f.y, h), pack16(f.z, f.w, h));
+          make_uint2(pack16(d.x, d.y, h), pack16(d.z, d.w, h));
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col) =
-          make_uint2(pack16(gelu_erf(f.x), gelu_erf(f.y), h), pack16(gelu_erf(f.z), gelu_erf(f.w), h));
+          make_uint2(pack16(g.x, g.y, h), pack16(g.z, g.w, h));
     } break;
     case VITK_EPI_DGELU: {
       const bool ah = p.aux_dtype == VITK_FP16, h = p.out_dtype == VITK_FP16;
       const float2 a0 = unpack16(__float_as_uint(e.x), ah), a1 = unpack16(__float_as_uint(e.y), ah);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col) =
-          make_uint2(pack16(f.x * gelu_erf_grad(a0.x), f.y * gelu_erf_grad(a0.y), h),
-                     pack16(f.z * gelu_erf_grad(a1.x), f.w * gelu_erf_grad(a1.y), h));
+          make_uint2(pack16(f.x * a0.x, f.y * a0.y, h), pack16(f.z * a1.x, f.w * a1.y, h));
     } break;
     case VITK_EPI_ATOMIC_ADD:
       red_add_v4(reinterpret_cast<float*>(p.out) + orow * p.ldo + col, f);
@@ -239,17 +293,45 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float4 f, co
 // r*64 + ((c ^ ((r >> 1) & 3)) << 4)  -- conflict-free for row-per-lane 128-bit accesses.
 __device__ __forceinline__ uint32_t swz64(int r, int c) { return uint32_t(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
-// Stage one packed 32x32 16-bit chunk (h[16] = this lane's row) and hand it to the TMA store engine.
+// Stage one packed 32x32 16-bit chunk (h[16] = this lane's row) and hand it to the TMA store engine.  Every warp
+// alternates between two 2 KB buffers, so "at most one newer store still reading" means this buffer is free.
 __device__ __forceinline__ void stage_and_store(uint8_t* sbuf, const uint32_t (&h)[16], const CUtensorMap* tm, int col0, int row0,
-                                                int lane) {
-  if (lane == 0) tma_store_wait_read();  // the previous store issued from this buffer has finished READING it
-  __syncwarp();
+                                                int lane, bool wait_free = true, bool no_store = false) {
+  if (wait_free) {
+    if (elect_one()) tma_store_wait_read1();  // bulk groups are per thread: the elected lane issues AND waits
+    __syncwarp();
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c)
     *reinterpret_cast<uint4*>(sbuf + swz64(lane, c)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) tma_store_2d(tm, sbuf, col0, row0);
+  if (elect_one() && !no_store) tma_store_2d(tm, sbuf, col0, row0);
+}
+
+// 32 accumulator values of one row x 32 saved-derivative values (a[4] = 32 x 16-bit) -> 16 packed 16-bit pairs
+template <bool AUX_H16>
+__device__ __forceinline__ void mul_pack(uint32_t (&h)[16], const float (&f)[32], const uint4 (&a)[4], bool h16) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float2 a0 = unpack16(a[c].x, AUX_H16), a1 = unpack16(a[c].y, AUX_H16), a2 = unpack16(a[c].z, AUX_H16),
+                 a3 = unpack16(a[c].w, AUX_H16);
+    h[4 * c + 0] = pack16(f[8 * c + 0] * a0.x, f[8 * c + 1] * a0.y, h16);
+    h[4 * c + 1] = pack16(f[8 * c + 2] * a1.x, f[8 * c + 3] * a1.y, h16);
+    h[4 * c + 2] = pack16(f[8 * c + 4] * a2.x, f[8 * c + 5] * a2.y, h16);
+    h[4 * c + 3] = pack16(f[8 * c + 6] * a3.x, f[8 * c + 7] * a3.y, h16);
+  }
+}
+// hd = gelu'(f), hg = gelu(f), packed 16-bit pairs
+template <bool H16>
+__device__ __forceinline__ void gelu_pack(uint32_t (&hd)[16], uint32_t (&hg)[16], const float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float2 g, d;
+    gelu_erf_both2(make_float2(f[2 * j], f[2 * j + 1]), g, d);
+    hd[j] = H16 ? pack_f16(d.x, d.y) : pack_bf16(d.x, d.y);
+    hg[j] = H16 ? pack_f16(g.x, g.y) : pack_bf16(g.x, g.y);
+  }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -270,7 +352,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   float* sEpi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  float* sBias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES + MAX_BIAS_SMEM * 4);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained by the epilogue
@@ -297,83 +380,127 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (p.tma_epi) {  // bias of every column tile (zeros when there is none), zero-padded to the tile grid
+    const int n_up = p.num_n_tiles * BN;
+    for (int i = threadIdx.x; i < n_up; i += GEMM_THREADS) sBias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (m, n, split): n fastest (CTAs running together share the A rows through L2), split slowest
-  auto decode = [&](int tile, int& m0, int& n0, int& kb0, int& nk) {
-    const int split = tile / tiles_mn;
-    const int r = tile - split * tiles_mn;
-    const int mt = r / p.num_n_tiles;
-    const int nt = r - mt * p.num_n_tiles;
-    m0 = mt * BLOCK_M;
-    n0 = nt * BN;
-    kb0 = split * p.kblocks_per_split;
+  // tile -> (m, n, split): n fastest (CTAs running together share the A rows through L2), split slowest.  Every role
+  // walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: the (split, mt, nt) counter advances in mixed radix by the
+  // host-computed digits of gridDim.x, so no role pays integer divisions per tile.
+  struct TileIter {
+    int split, mt, nt;
+  };
+  auto tile_first = [&]() {
+    TileIter t;
+    t.split = (int)blockIdx.x / tiles_mn;
+    const int r = (int)blockIdx.x - t.split * tiles_mn;
+    t.mt = r / p.num_n_tiles;
+    t.nt = r - t.mt * p.num_n_tiles;
+    return t;
+  };
+  auto tile_next = [&](TileIter& t) {
+    t.nt += p.step_nt;
+    t.mt += p.step_mt;
+    t.split += p.step_split;
+    if (t.nt >= p.num_n_tiles) {
+      t.nt -= p.num_n_tiles;
+      ++t.mt;
+    }
+    if (t.mt >= p.num_m_tiles) {
+      t.mt -= p.num_m_tiles;
+      ++t.split;
+    }
+  };
+  auto decode = [&](const TileIter& t, int& m0, int& n0, int& kb0, int& nk) {
+    m0 = t.mt * BLOCK_M;
+    n0 = t.nt * BN;
+    kb0 = t.split * p.kblocks_per_split;
     const int kb1 = min(p.num_kblocks, kb0 + p.kblocks_per_split);
     nk = kb1 - kb0;
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int m0, n0, kb0, nk;
-      decode(tile, m0, n0, kb0, nk);
-      for (int kb = 0; kb < nk; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 1);
-        if (lane == 0) {
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+    // ===================== TMA producer (one elected thread) =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      TileIter ti = tile_first();
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_next(ti)) {
+        int m0, n0, kb0, nk;
+        decode(ti, m0, n0, kb0, nk);
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 1);
+          if (kb == 0) DBG_STAMP(0, (tile - (int)blockIdx.x) / (int)gridDim.x, 0);
+          const bool skip_a = KNOB(8) && tile != (int)blockIdx.x, skip_b = KNOB(4) && tile != (int)blockIdx.x;
+          mbar_expect_tx(&full_bar[s], (skip_a ? 0 : A_BYTES) + (skip_b ? 0 : B_BYTES));
           const int kc = (kb0 + kb) * BLOCK_K;
           uint8_t* a_dst = sA + s * A_BYTES;
           uint8_t* b_dst = sB + s * B_BYTES;
-          if (!A_MN) {
+          if (skip_a) {
+          } else if (!A_MN) {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
           } else {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kc);
           }
-          if (!B_MN) {
+          if (skip_b) {
+          } else if (!B_MN) {
             tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_dst + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kc);
           }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = p.idesc;
-    constexpr uint32_t a_adv = A_MN ? (2048u >> 4) : (32u >> 4);  // desc.lo step per UMMA_K
-    constexpr uint32_t b_adv = B_MN ? (2048u >> 4) : (32u >> 4);
-    uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      int m0, n0, kb0, nk;
-      decode(tile, m0, n0, kb0, nk);
-      const uint32_t acc = tcount & 1;
-      mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator stage
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < nk; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph, 2);
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      const uint32_t idesc = p.idesc;
+      constexpr uint32_t a_adv = A_MN ? (2048u >> 4) : (32u >> 4);  // desc.lo step per UMMA_K
+      constexpr uint32_t b_adv = B_MN ? (2048u >> 4) : (32u >> 4);
+      const uint64_t adesc0 = make_smem_desc<A_MN>(smem_u32(sA));
+      const uint64_t bdesc0 = make_smem_desc<B_MN>(smem_u32(sB));
+      int s = 0;
+      uint32_t ph = 0, tcount = 0;
+      TileIter ti = tile_first();
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount, tile_next(ti)) {
+        int m0, n0, kb0, nk;
+        decode(ti, m0, n0, kb0, nk);
+        const uint32_t acc = tcount & 1;
+        DBG_STAMP(1, tcount, 0);
+        mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_smem_desc<A_MN>(smem_u32(sA + s * A_BYTES));
-          const uint64_t bdesc = make_smem_desc<B_MN>(smem_u32(sB + s * B_BYTES));
+        DBG_STAMP(1, tcount, 1);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full_bar[s], ph, 2);
+          tcgen05_fence_after();
+          if (kb == 0) DBG_STAMP(1, tcount, 2);
+          const uint64_t adesc = adesc0 + uint64_t(s * (A_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + uint64_t(s * (B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_f16(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (!KNOB(32)) umma_f16(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
-          if (kb == nk - 1) umma_commit(&tfull_bar[acc]);
+          if (kb == nk - 1) {
+            umma_commit(&tfull_bar[acc]);
+            DBG_STAMP(1, tcount, 3);
+          }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
-        __syncwarp();
       }
     }
   } else {
@@ -384,68 +511,154 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
     const int c4 = lane & 3;     // float4 column slot of this lane inside a 16-column half chunk
     const int rsub = lane >> 2;  // row (mod 8) this lane handles when reading the staged half chunk back
-    uint32_t tcount = 0, aux_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t tcount = 0, aux_phase = 0, sbuf_idx = 0;
+    TileIter ti = tile_first();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount, tile_next(ti)) {
       int m0, n0, kb0, nk;
-      decode(tile, m0, n0, kb0, nk);
+      decode(ti, m0, n0, kb0, nk);
       const uint32_t acc = tcount & 1;
-      mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
-      tcgen05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (uint32_t(quad * 32) << 16);
       const int row_base = m0 + quad * 32;
+      if (p.tma_epi) {
+        // ---- STORE / GELU / DGELU: units of 2 KB (32 rows x 32 16-bit columns, or 32 rows x 16 fp32 columns) ----
+        // Math happens in the row-per-lane TMEM layout; the saved derivative / fp32 residual unit arrives by TMA into the
+        // staging buffer the result will leave from (issued one unit ahead, the first one before the accumulator is even
+        // ready), results leave by TMA store; two buffers per warp alternate so a store overlaps the next unit.
+        const bool out32 = p.out_dtype == VITK_FP32, h16 = p.out_dtype == VITK_FP16;
+        const int UC = out32 ? 16 : 32;
+        const int ustride = UC * (EPI_WARPS / 4);
+        const bool has_aux = p.epilogue == VITK_EPI_DGELU || p.residual != nullptr;
+        uint8_t* const sbase = reinterpret_cast<uint8_t*>(stage);
+        auto issue_aux = [&](int c0) {
+          if (elect_one()) {
+            tma_store_wait_read1();
+            mbar_expect_tx(&aux_bar[warp - 2], 2048);
+            tma_load_2d(sbase + (sbuf_idx & 1) * 2048, &tmAux, &aux_bar[warp - 2], n0 + c0, row_base);
+          }
+        };
+        int c0 = group * UC;
+        bool more = c0 < BN && n0 + c0 < p.N;
+        if (has_aux && more) issue_aux(c0);
+        if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 0);
+        mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
+        tcgen05_fence_after();
+        if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 1);
+        int ucount = -1;
+        while (more) {
+          ++ucount;
+          const int col0 = n0 + c0;
+          uint8_t* sbuf = sbase + (sbuf_idx & 1) * 2048;
+          ++sbuf_idx;
+          if (KNOB(16)) {
+          } else if (out32) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + uint32_t(c0), v);
+            float4 b4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) b4[c] = *reinterpret_cast<const float4*>(sBias + col0 + 4 * c);
+            float f[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              f[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), alpha, b4[c].x);
+              f[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), alpha, b4[c].y);
+              f[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), alpha, b4[c].z);
+              f[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), alpha, b4[c].w);
+            }
+            if (has_aux) {
+              mbar_wait(&aux_bar[warp - 2], aux_phase, 5);
+              aux_phase ^= 1;
+              float4 r[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) r[c] = *reinterpret_cast<const float4*>(sbuf + swz64(lane, c));
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                f[4 * c + 0] += r[c].x; f[4 * c + 1] += r[c].y; f[4 * c + 2] += r[c].z; f[4 * c + 3] += r[c].w;
+              }
+            } else {
+              if (elect_one()) tma_store_wait_read1();
+            }
+            __syncwarp();  // residual rows read by every lane / buffer free: it may now be overwritten with the result
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<float4*>(sbuf + swz64(lane, c)) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (elect_one() && !KNOB(1)) tma_store_2d(&tmOut, sbuf, col0, row_base);
+          } else {
+            uint32_t v[32];
+            DBG_UNIT(tcount, ucount, 0);
+            tmem_ld32(t_addr + uint32_t(c0), v);
+            DBG_UNIT(tcount, ucount, 1);
+            float4 b4[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) b4[c] = *reinterpret_cast<const float4*>(sBias + col0 + 4 * c);
+            float f[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              f[4 * c + 0] = fmaf(__uint_as_float(v[4 * c + 0]), alpha, b4[c].x);
+              f[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), alpha, b4[c].y);
+              f[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), alpha, b4[c].z);
+              f[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), alpha, b4[c].w);
+            }
+            uint32_t h[16];
+            if (KNOB(2)) {
+            } else if (p.epilogue == VITK_EPI_DGELU) {
+              mbar_wait(&aux_bar[warp - 2], aux_phase, 5);
+              aux_phase ^= 1;
+              uint4 a[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) a[c] = *reinterpret_cast<const uint4*>(sbuf + swz64(lane, c));
+              __syncwarp();  // every lane has read its derivative row before the buffer is reused for the output
+              if (p.aux_dtype == VITK_FP16) mul_pack<true>(h, f, a, h16);
+              else mul_pack<false>(h, f, a, h16);
+              stage_and_store(sbuf, h, &tmOut, col0, row_base, lane, false, KNOB(1));
+            } else if (p.epilogue == VITK_EPI_GELU) {
+              // out = gelu'(pre) (all the backward needs), out2 = gelu(pre): one erf evaluation serves both
+              uint32_t h2[16];
+              if (h16) gelu_pack<true>(h, h2, f);
+              else gelu_pack<false>(h, h2, f);
+              stage_and_store(sbuf, h, &tmOut, col0, row_base, lane, true, KNOB(1));
+              uint8_t* sbuf2 = sbase + (sbuf_idx & 1) * 2048;
+              ++sbuf_idx;
+              stage_and_store(sbuf2, h2, &tmOut2, col0, row_base, lane, true, KNOB(1));
+            } else {
+              if (h16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h[j] = pack_f16(f[2 * j], f[2 * j + 1]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+              }
+              DBG_UNIT(tcount, ucount, 2);
+              if (elect_one()) tma_store_wait_read1();
+              __syncwarp();
+              DBG_UNIT(tcount, ucount, 3);
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(sbuf + swz64(lane, c)) = make_uint4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              DBG_UNIT(tcount, ucount, 4);
+              if (elect_one() && !KNOB(1)) tma_store_2d(&tmOut, sbuf, col0, row_base);
+              DBG_UNIT(tcount, ucount, 5);
+            }
+          }
+          c0 += ustride;
+          more = c0 < BN && n0 + c0 < p.N;
+          if (has_aux && more) issue_aux(c0);
+        }
+        tcgen05_fence_before();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
+        continue;
+      }
+      mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
+      tcgen05_fence_after();
 #pragma unroll 1
       for (int c0 = group * 32; c0 < BN; c0 += 32 * (EPI_WARPS / 4)) {
         const int col0 = n0 + c0;
         if (col0 >= p.N) break;  // warp-uniform
-        if (p.epi16) {
-          // ---- 16-bit outputs: math in the row-per-lane TMEM layout, swizzled 16-bit staging, TMA store ----
-          uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage);
-          const bool h16 = p.out_dtype == VITK_FP16;
-          if (p.epilogue == VITK_EPI_DGELU && lane == 0) {  // fetch the saved pre-activation chunk while TMEM is read
-            tma_store_wait_read();
-            mbar_expect_tx(&aux_bar[warp - 2], 32 * 64);
-            tma_load_2d(sbuf, &tmAux, &aux_bar[warp - 2], col0, row_base);
-          }
-          uint32_t v[32];
-          tmem_ld32(t_addr + uint32_t(c0), v);
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.N) {
-                const float4 b4 = ldg_f4(p.bias + col0 + j);  // warp-uniform address: one broadcast wavefront
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
-            }
-          }
-          uint32_t h[16];
-          if (p.epilogue == VITK_EPI_DGELU) {
-            const bool ah = p.aux_dtype == VITK_FP16;
-            mbar_wait(&aux_bar[warp - 2], aux_phase, 5);
-            aux_phase ^= 1;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 a = *reinterpret_cast<const uint4*>(sbuf + swz64(lane, c));
-              const float2 a0 = unpack16(a.x, ah), a1 = unpack16(a.y, ah), a2 = unpack16(a.z, ah), a3 = unpack16(a.w, ah);
-              f[8 * c + 0] *= gelu_erf_grad(a0.x); f[8 * c + 1] *= gelu_erf_grad(a0.y);
-              f[8 * c + 2] *= gelu_erf_grad(a1.x); f[8 * c + 3] *= gelu_erf_grad(a1.y);
-              f[8 * c + 4] *= gelu_erf_grad(a2.x); f[8 * c + 5] *= gelu_erf_grad(a2.y);
-              f[8 * c + 6] *= gelu_erf_grad(a3.x); f[8 * c + 7] *= gelu_erf_grad(a3.y);
-            }
-            __syncwarp();  // every lane has read its pre-activation row before the buffer is reused for the output
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = pack16(f[2 * j], f[2 * j + 1], h16);
-          stage_and_store(sbuf, h, &tmOut, col0, row_base, lane);
-          if (p.epilogue == VITK_EPI_GELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = pack16(gelu_erf(f[2 * j]), gelu_erf(f[2 * j + 1]), h16);
-            stage_and_store(sbuf, h, &tmOut2, col0, row_base, lane);
-          }
-          continue;
-        }
+        if (KNOB(16)) continue;
         uint32_t v[32];
         tmem_ld32(t_addr + uint32_t(c0), v);
         // transpose through smem in two 16-column halves: lane = row on the way in,
@@ -486,7 +699,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (lane == 0) tma_store_wait_all();  // outstanding TMA stores must complete before the CTA (and its smem) goes away
+    if (elect_one()) tma_store_wait_all();  // outstanding TMA stores must complete before the CTA (and its smem) goes away
   }
 
   tcgen05_fence_before();
@@ -509,17 +722,18 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D 16-bit tensor map over a row-major [outer, inner] matrix, 128B swizzle, zero OOB fill.
 int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
-                 uint32_t box_outer, bool fp16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                 uint32_t box_outer, bool fp16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool fp32 = false) {
   auto fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return VITK_ERR_CUDA;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint64_t strides[1] = {pitch_elems * (fp32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+  CUresult r = fn(tm, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -532,7 +746,8 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 + (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 + MAX_BIAS_SMEM * 4 +
+                       (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   static bool configured = false;
   auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
@@ -548,10 +763,10 @@ int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream
 template <bool A_MN, bool B_MN>
 int dispatch_gemm(int bn, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
   switch (bn) {
-    case 64:  return launch_gemm<64, 8, A_MN, B_MN>(tm, p, grid, st);
-    case 128: return launch_gemm<128, 6, A_MN, B_MN>(tm, p, grid, st);
+    case 64:  return launch_gemm<64, 6, A_MN, B_MN>(tm, p, grid, st);
+    case 128: return launch_gemm<128, 5, A_MN, B_MN>(tm, p, grid, st);
     case 192: return launch_gemm<192, 4, A_MN, B_MN>(tm, p, grid, st);
-    case 256: return launch_gemm<256, 4, A_MN, B_MN>(tm, p, grid, st);
+    case 256: return launch_gemm<256, 3, A_MN, B_MN>(tm, p, grid, st);
     default:
       set_error("unsupported BLOCK_N %d", bn);
       return VITK_ERR_UNSUPPORTED;
@@ -579,6 +794,15 @@ int pick_bn(int N) {
 }  // namespace vitk
 
 using namespace vitk;
+
+#ifdef VITK_GEMM_KNOBS
+extern "C" int vitk_debug_read(long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, g_vitk_dbg, sizeof(g_vitk_dbg));
+}
+extern "C" int vitk_debug_read2(long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, g_vitk_dbg2, sizeof(g_vitk_dbg2));
+}
+#endif
 
 extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   VITK_CHECK_ARG(a != nullptr, "vitk_gemm: null args");
@@ -618,6 +842,12 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   const int splits = (num_kblocks + kpb - 1) / kpb;
 
   GemmParams p{};
+#ifdef VITK_GEMM_KNOBS
+  {
+    const char* kn = getenv("VITK_GEMM_KNOBS");
+    p.knobs = kn ? atoi(kn) : 0;
+  }
+#endif
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_kblocks = num_kblocks;
   p.kblocks_per_split = kpb;
@@ -641,16 +871,21 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   if (!a->b_mn_major) rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, bh);
   else                rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, bh);
   if (rc != VITK_OK) return rc;
-  // 16-bit outputs without a residual go out through TMA stores of 32x32 chunks (64-byte rows, SWIZZLE_64B)
-  p.epi16 = (!out_fp32 && a->residual == nullptr &&
-             (a->epilogue == VITK_EPI_STORE || a->epilogue == VITK_EPI_GELU || a->epilogue == VITK_EPI_DGELU) &&
-             a->ldo % 8 == 0 && (a->epilogue != VITK_EPI_GELU || (a->ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0)) &&
-             (a->epilogue != VITK_EPI_DGELU || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)))
-                ? 1 : 0;
+  // STORE / GELU / DGELU epilogues run on 2 KB TMA units (32x32 16-bit or 32x16 fp32 boxes, 64-byte rows, SWIZZLE_64B);
+  // the only combination left on the per-thread path is a 16-bit output with an fp32 residual (its residual unit would be 4 KB)
+  const bool store_like = a->epilogue == VITK_EPI_STORE || a->epilogue == VITK_EPI_GELU || a->epilogue == VITK_EPI_DGELU;
+  const int oalign = out_fp32 ? 4 : 8;
+  p.tma_epi = (store_like && (a->residual == nullptr || out_fp32) && a->ldo % oalign == 0 &&
+               (a->residual == nullptr || (a->ldr % 4 == 0)) &&
+               (a->epilogue != VITK_EPI_GELU || (a->ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0)) &&
+               (a->epilogue != VITK_EPI_DGELU || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)))
+                  ? 1 : 0;
+  if (p.num_n_tiles * bn > MAX_BIAS_SMEM) p.tma_epi = 0;  // the TMA epilogue keeps the whole bias vector in shared memory
   tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];
-  if (p.epi16) {
+  if (p.tma_epi) {
     const bool oh = a->out_dtype == VITK_FP16;
-    rc = make_tmap_2d(&tm[2], a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, 32, 32, oh, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_2d(&tm[2], a->out, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo, out_fp32 ? 16 : 32, 32, oh,
+                      CU_TENSOR_MAP_SWIZZLE_64B, out_fp32);
     if (rc != VITK_OK) return rc;
     if (a->epilogue == VITK_EPI_GELU) {
       rc = make_tmap_2d(&tm[3], a->out2, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldo2, 32, 32, oh, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -660,11 +895,22 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
       rc = make_tmap_2d(&tm[4], a->aux, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldaux, 32, 32, a->aux_dtype == VITK_FP16,
                         CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc != VITK_OK) return rc;
+    } else if (a->residual != nullptr) {
+      rc = make_tmap_2d(&tm[4], a->residual, (uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->ldr, 16, 32, false,
+                        CU_TENSOR_MAP_SWIZZLE_64B, true);
+      if (rc != VITK_OK) return rc;
     }
   }
 
   const long long total_tiles = (long long)p.num_m_tiles * p.num_n_tiles * splits;
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  {
+    const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+    p.step_split = grid / tiles_mn;
+    const int r = grid - p.step_split * tiles_mn;
+    p.step_mt = r / p.num_n_tiles;
+    p.step_nt = r - p.step_mt * p.num_n_tiles;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, tm, p, grid, st);
   if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, tm, p, grid, st);

@@ -92,28 +92,63 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, bool fp16) {
   return unpack_bf16(u);
 }
 
-// erf with |abs error| <= ~3e-7 (Abramowitz & Stegun 7.1.26 in fp32; exp and reciprocal run on the SFU pipe).
-// The CUDA libm erff costs ~3x more instructions; at 4 x D GELU evaluations per token the exact-erf epilogue would
-// otherwise be ISSUE-bound rather than HBM-bound.  Returns erf(x) and e = exp(-x*x) (reused by the derivative).
-__device__ __forceinline__ float erf_fast(float x, float& e) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  e = __expf(-ax * ax);
-  return copysignf(fmaf(-poly * t, e, 1.0f), x);
+// Exact-erf GELU (nn.GELU() default, vision_transformer_base.py:212-219) and its derivative in one pass:
+//   gelu(x) = x * Phi(x),  gelu'(x) = Phi(x) + x * phi(x),  Phi(x) = 0.5 * erfc(-x / sqrt2).
+// erfc(|u|) = (a1 t + ... + a5 t^5) exp(-u^2), t = 1 / (1 + p |u|)  (Abramowitz & Stegun 7.1.26, |abs error| <= 1.5e-7);
+// the reciprocal and the exponential are single MUFU instructions (approx.ftz: no denormal slow paths), the 0.5 is folded
+// into the coefficients.  ~17 FP32 instructions + 2 MUFU per element: at 4 x D evaluations per token the libm erff
+// (3x the instructions) made the fc1 epilogue issue-bound instead of HBM-bound.
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-// exact (erf) GELU, as nn.GELU() default (vision_transformer_base.py:212-219)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_erf_both(float x, float& g, float& dg) {
+  const float t = rcp_ftz(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float e = ex2_ftz(x * x * (-0.5f * 1.4426950408889634f));  // exp(-x^2 / 2)
+  const float h = poly * t * e;                                     // 0.5 * erfc(|x| / sqrt2) = Phi(-|x|)
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  g = x * cdf;
+  dg = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+// Two elements at a time on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2, sm_100): half the issue slots of the scalar
+// version for the polynomial, the products and the final combine; the two MUFUs per element stay scalar.
+__device__ __forceinline__ void gelu_erf_both2(float2 x, float2& g, float2& dg) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), ax,
+                                make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_ftz(den.x), rcp_ftz(den.y));
+  float2 poly = __ffma2_rn(t, make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  poly = __ffma2_rn(poly, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  poly = __ffma2_rn(poly, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  poly = __ffma2_rn(poly, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  const float2 q = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  const float2 e = make_float2(ex2_ftz(q.x), ex2_ftz(q.y));           // exp(-x^2 / 2)
+  const float2 h = __fmul2_rn(__fmul2_rn(poly, t), e);                  // Phi(-|x|)
+  // Phi(x) = 0.5 + copysign(0.5 - h, x)
+  const float2 w = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-h.x, -h.y));
+  const float2 cdf = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(copysignf(w.x, x.x), copysignf(w.y, x.y)));
+  g = __fmul2_rn(x, cdf);
+  dg = __ffma2_rn(__fmul2_rn(x, make_float2(0.3989422804014327f, 0.3989422804014327f)), e, cdf);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  float e;
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f, e));
+  float g, dg;
+  gelu_erf_both(x, g, dg);
+  return g;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float e;  // = exp(-x*x/2)
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f, e));
-  return fmaf(x * 0.3989422804014327f, e, cdf);
+  float g, dg;
+  gelu_erf_both(x, g, dg);
+  return dg;
 }
 
 // streaming 128-bit global accesses

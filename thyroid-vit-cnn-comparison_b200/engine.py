@@ -13,7 +13,7 @@ Memory layout in HBM (per rank)
                             (split-K red.add, column-sum atomics)
   flat_16       fp16 [P]   tensor-core shadow of flat_params (written by the AdamW kernel / cast kernel)
   residual x    fp32 [B*T, D] per block boundary (2L+1 buffers, saved for backward)
-  activations   fp16: LN outputs, qkv [B,T,3,H,64], attention out [B,T,H,64], fc1 pre/post GELU [B*T,4D], patches
+  activations   fp16: LN outputs, qkv [B,T,3,H,64], attention out [B,T,H,64], fc1 GELU output and GELU derivative [B*T,4D], patches
   amp_state     fp32 [8]   {S, 1/S, good_steps, skipped, overflowed, ...}: dynamic loss scale, device resident
 
 Numerics.  tcgen05 kind::f16 cannot mix fp16 with bf16 operands in one MMA (probed on B200: illegal
@@ -139,7 +139,7 @@ class Workspace:
         self.qkv = [e(M, 3 * D) for _ in range(L)]
         self.ao = [e(M, D) for _ in range(L)]
         self.lse = [e(B, H, T, dt=f32) for _ in range(L)]
-        self.pre = [e(M, d.hidden) for _ in range(L)]
+        self.dact = [e(M, d.hidden) for _ in range(L)]
         self.act = [e(M, d.hidden) for _ in range(L)]
         if train:
             self.dx = [e(M, D, dt=f32) for _ in range(2)]
@@ -266,7 +266,7 @@ class VitEngine:
             ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
             ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
             ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
-            ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.pre[s], out2=ws.act[s],
+            ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.dact[s], out2=ws.act[s],
                      bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
             ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
         x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
@@ -307,7 +307,7 @@ class VitEngine:
             x_in, x_mid = ws.x[2 * l], ws.x[2 * l + 1]
             # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
             self._wgrad(ws.dx16, ws.act[l], pre + "mlp.fc2.weight", M)
-            ops.gemm(ws.dx16, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.pre[l],
+            ops.gemm(ws.dx16, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.dact[l],
                      epilogue=_lib.EPI_DGELU)
             ops.colsum16(ws.d_pre, self.g(pre + "mlp.fc1.bias"), unscale=u)
             self._wgrad(ws.d_pre, ws.xn2[l], pre + "mlp.fc1.weight", M)
