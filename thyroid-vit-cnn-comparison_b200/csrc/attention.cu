@@ -525,8 +525,8 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 // tcgen05 / TMEM kernels for sequences of up to 256 tokens (attention_tc.cu)
 constexpr int TC_MAX_TOKENS = 256;
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
-int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
-                     float scale, bool fp16, cudaStream_t st);
+int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
+                     int H, float scale, bool fp16, cudaStream_t st);
 }  // namespace vitk
 
 using namespace vitk;
@@ -571,11 +571,11 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
     configured = true;
   }
+  if (N <= TC_MAX_TOKENS) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, H16, st);  // delta fused
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
                                                                      reinterpret_cast<const bf16*>(dout), delta, B, N, H);
   VITK_LAUNCH_CHECK();
-  if (N <= TC_MAX_TOKENS) return attention_bwd_tc(qkv, dout, lse, delta, dqkv, B, N, H, scale, H16, st);
   dim3 grid((N + TILE - 1) / TILE, H, B);
   attn_bwd_dkdv_kernel<H16><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
                                                                 reinterpret_cast<const bf16*>(dout), lse, delta,

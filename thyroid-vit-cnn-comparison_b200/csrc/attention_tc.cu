@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       prefetch_tmap(&tmQ);
       prefetch_tmap(&tmKV);
       prefetch_tmap(&tmO);
@@ -92,22 +92,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   const uint32_t tb = *tmem_slot;
 
   if (warp == 4) {
-    // ===================== MMA issuer =====================
-    mbar_wait(bar_qk, 0, 1);
-    tc_fence_after();
-    if (lane == 0) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      mbar_wait(bar_qk, 0, 1);
+      tc_fence_after();
       const uint32_t idesc_s = idesc_f16(KP, false, false, H16);
       const uint64_t adesc = smem_desc_kmajor(smem_u32(sQ));
       const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK));
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss(tb, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
       umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_p, 0, 2);
-    mbar_wait(bar_v, 0, 3);
-    tc_fence_after();
-    if (lane == 0) {
+      mbar_wait(bar_p, 0, 2);
+      mbar_wait(bar_v, 0, 3);
+      tc_fence_after();
       const uint32_t idesc_o = idesc_f16(DH, false, true, H16);
       const uint64_t vdesc = smem_desc_mnmajor(smem_u32(sV), 8192);
       const int steps = KP >> 4;
@@ -188,7 +185,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     }
     fence_proxy_async();
     named_bar_sync(1, 128);
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       tma_store_3d(&tmO, sQ, h * DH, q0, b);
       tma_store_commit();
       tma_store_wait_all();
@@ -258,8 +255,9 @@ __device__ __forceinline__ void bwd_math_group(uint32_t trow, int g0, int pcol, 
 template <bool H16>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
     attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                       const __grid_constant__ CUtensorMap tmDQKV, const float* __restrict__ lse, const float* __restrict__ delta,
-                       int N, int H, int QP, float scale, float scale_log2) {
+                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQKV,
+                       const float* __restrict__ lse, float* __restrict__ delta, int N, int H, int QP, float scale,
+                       float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -277,7 +275,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   uint64_t* bar_s = bars + 1;
   uint64_t* bar_p = bars + 2;
   uint64_t* bar_m2 = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -286,30 +285,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   const int T = NJ * NC;
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {
       prefetch_tmap(&tmQKV);
       prefetch_tmap(&tmDO);
+      prefetch_tmap(&tmO);
       prefetch_tmap(&tmDQKV);
       mbar_init(bar_load, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_p, 256);
       mbar_init(bar_m2, 1);
+      mbar_init(bar_o, 1);
       mbar_init_fence();
       mbar_expect_tx(bar_load, 4 * tile_bytes);
       tma_load_3d(sK, &tmQKV, bar_load, (H + h) * DH, 0, b);
       tma_load_3d(sQ, &tmQKV, bar_load, h * DH, 0, b);
       tma_load_3d(sV, &tmQKV, bar_load, (2 * H + h) * DH, 0, b);
       tma_load_3d(sDO, &tmDO, bar_load, h * DH, 0, b);
+      mbar_expect_tx(bar_o, tile_bytes);            // O parks in the (still unused) output staging buffer
+      tma_load_3d(sOut, &tmO, bar_o, h * DH, 0, b);
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
   } else {
-    // per-query statistics: lse in the log2 domain (+inf masks the padded queries: P = exp2(-inf) = 0), delta
+    // lse in the log2 domain (+inf masks the padded queries: P = exp2(-inf) = 0)
     const float* lse_b = lse + ((long long)b * H + h) * N;
-    const float* del_b = delta + ((long long)b * H + h) * N;
     const int i = threadIdx.x;  // 0..255
     s_lse2[i] = i < N ? lse_b[i] * LOG2E : INFINITY;
-    s_delta[i] = i < N ? del_b[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -317,32 +318,31 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   const uint32_t tb = *tmem_slot;
 
   if (warp == 8) {
-    // ===================== MMA issuer =====================
-    mbar_wait(bar_load, 0, 1);
-    tc_fence_after();
-    const uint32_t idesc64_ts = idesc_f16(DH, false, true, H16);   // A from TMEM (K-major), B MN-major
-    const uint32_t idesc64_mn = idesc_f16(DH, true, true, H16);    // A, B MN-major from smem
-    auto issue_g1 = [&](int j, int c) {
-      const int QC = min(128, QP - 128 * c);
-      const uint32_t idesc_s = idesc_f16(QC, false, false, H16);
-      const uint64_t kd = smem_desc_kmajor(smem_u32(sK + j * 16384));
-      const uint64_t qd = smem_desc_kmajor(smem_u32(sQ + c * 16384));
-      const uint64_t vd = smem_desc_kmajor(smem_u32(sV + j * 16384));
-      const uint64_t dd = smem_desc_kmajor(smem_u32(sDO + c * 16384));
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      mbar_wait(bar_load, 0, 1);
+      tc_fence_after();
+      const uint32_t idesc64_ts = idesc_f16(DH, false, true, H16);   // A from TMEM (K-major), B MN-major
+      const uint32_t idesc64_mn = idesc_f16(DH, true, true, H16);    // A, B MN-major from smem
+      auto issue_g1 = [&](int j, int c) {
+        const int QC = min(128, QP - 128 * c);
+        const uint32_t idesc_s = idesc_f16(QC, false, false, H16);
+        const uint64_t kd = smem_desc_kmajor(smem_u32(sK + j * 16384));
+        const uint64_t qd = smem_desc_kmajor(smem_u32(sQ + c * 16384));
+        const uint64_t vd = smem_desc_kmajor(smem_u32(sV + j * 16384));
+        const uint64_t dd = smem_desc_kmajor(smem_u32(sDO + c * 16384));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tb + TM_S, kd + uint64_t(2 * k), qd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_ss(tb + TM_S, kd + uint64_t(2 * k), qd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tb + TM_DP, vd + uint64_t(2 * k), dd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(bar_s);
-    };
-    if (lane == 0) issue_g1(0, 0);
-    __syncwarp();
-    int t = 0;
-    for (int j = 0; j < NJ; ++j) {
-      for (int c = 0; c < NC; ++c, ++t) {
-        mbar_wait(bar_p, t & 1, 2);
-        tc_fence_after();
-        if (lane == 0) {
+        for (int k = 0; k < 4; ++k) umma_ss(tb + TM_DP, vd + uint64_t(2 * k), dd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      };
+      issue_g1(0, 0);
+      int t = 0;
+      for (int j = 0; j < NJ; ++j) {
+        for (int c = 0; c < NC; ++c, ++t) {
+          mbar_wait(bar_p, t & 1, 2);
+          tc_fence_after();
           const int QC = min(128, QP - 128 * c);
           const int HB = ((QC >> 1) + 15) & ~15;
           const int KJ = min(128, QP - 128 * j);
@@ -372,15 +372,39 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             issue_g1(j1, c1);
           }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // ===================== math warps: lane quadrant = warp % 4, column half = warp / 4 =====================
     const int quad = warp & 3, half = warp >> 2;
     const int keyrow = quad * 32 + lane;
     const uint32_t trow = tb + (uint32_t(quad * 32) << 16);
     const int tid = threadIdx.x;  // 0..255
+    {
+      // delta[q] = sum_d dO[q,d] * O[q,d] (the softmax-backward row term), one query row per thread, straight from the
+      // TMA-staged dO and O tiles -- no separate pass over HBM
+      mbar_wait(bar_load, 0, 5);
+      mbar_wait(bar_o, 0, 6);
+      float dsum = 0.f;
+      if (tid < N) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = *reinterpret_cast<const uint4*>(sDO + swz128(tid, c));
+          const uint4 o = *reinterpret_cast<const uint4*>(sOut + swz128(tid, c));
+          const uint32_t au[4] = {a.x, a.y, a.z, a.w}, ou[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack16(au[e], H16), y = unpack16(ou[e], H16);
+            dsum = fmaf(x.x, y.x, dsum);
+            dsum = fmaf(x.y, y.y, dsum);
+          }
+        }
+        delta[((long long)b * H + h) * N + tid] = dsum;
+      }
+      s_delta[tid] = dsum;
+      named_bar_sync(1, 256);
+    }
     int t = 0;
     for (int j = 0; j < NJ; ++j) {
       const bool keyvalid = (j * 128 + keyrow) < N;
@@ -403,7 +427,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           // ---- key tile j is complete: dV_j (half 0) / dK_j (half 1) -> 16-bit -> staging -> TMA store
           mbar_wait(bar_m2, t & 1, 4);
           tc_fence_after();
-          if (tid == 0) tma_store_wait_read();  // earlier stores have finished reading sOut
+          if (warp == 0 && elect_one()) tma_store_wait_read();  // earlier stores have finished reading sOut
           named_bar_sync(1, 256);
           const float mul = half == 0 ? 1.f : scale;
           uint8_t* dst = sOut + half * 16384;
@@ -425,7 +449,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
           tc_fence_before();
           fence_proxy_async();
           named_bar_sync(1, 256);
-          if (tid == 0) {
+          if (warp == 0 && elect_one()) {
             tma_store_3d(&tmDQKV, sOut, (2 * H + h) * DH, j * 128, b);          // dV_j
             tma_store_3d(&tmDQKV, sOut + 16384, (H + h) * DH, j * 128, b);      // dK_j
             tma_store_commit();
@@ -434,7 +458,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       }
     }
     // ---- dQ chunks (accumulated over all key tiles): half c handles chunk c
-    if (tid == 0) tma_store_wait_read();
+    if (warp == 0 && elect_one()) tma_store_wait_read();
     named_bar_sync(1, 256);
     if (half < NC) {
       uint8_t* dst = sOut + half * 16384;
@@ -457,7 +481,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     tc_fence_before();
     fence_proxy_async();
     named_bar_sync(1, 256);
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       for (int c = 0; c < NC; ++c) tma_store_3d(&tmDQKV, sOut + c * 16384, h * DH, c * 128, b);
       tma_store_commit();
       tma_store_wait_all();
@@ -529,13 +553,14 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
 }
 
 template <bool H16>
-int attention_bwd_tc_impl(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
-                          float scale, cudaStream_t st) {
+int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
+                          int H, float scale, cudaStream_t st) {
   const int QP = (N + 15) & ~15;
-  CUtensorMap tmQKV, tmDO, tmDQKV;
+  CUtensorMap tmQKV, tmDO, tmO, tmDQKV;
   int rc;
   if ((rc = make_tmap_3d(&tmQKV, qkv, 3 * H * DH, N, B, QP, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmDO, dout, H * DH, N, B, QP, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, QP, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmDQKV, dqkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
   const int smem = 4 * QP * 128 + 65536 + 2048 + 64 + 1024;
   const int smem_max = 4 * 256 * 128 + 65536 + 2048 + 64 + 1024;
@@ -546,7 +571,7 @@ int attention_bwd_tc_impl(const void* qkv, const void* dout, const float* lse, c
     configured = true;
   }
   dim3 grid(H, B);
-  kfn<<<grid, BWD_THREADS, smem, st>>>(tmQKV, tmDO, tmDQKV, lse, delta, N, H, QP, scale, scale * LOG2E);
+  kfn<<<grid, BWD_THREADS, smem, st>>>(tmQKV, tmDO, tmO, tmDQKV, lse, delta, N, H, QP, scale, scale * LOG2E);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -555,10 +580,10 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H
   return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, st)
               : attention_fwd_tc_impl<false>(qkv, out, lse, B, N, H, scale, st);
 }
-int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
-                     float scale, bool fp16, cudaStream_t st) {
-  return fp16 ? attention_bwd_tc_impl<true>(qkv, dout, lse, delta, dqkv, B, N, H, scale, st)
-              : attention_bwd_tc_impl<false>(qkv, dout, lse, delta, dqkv, B, N, H, scale, st);
+int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
+                     int H, float scale, bool fp16, cudaStream_t st) {
+  return fp16 ? attention_bwd_tc_impl<true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st)
+              : attention_bwd_tc_impl<false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st);
 }
 
 }  // namespace vitk

@@ -366,16 +366,30 @@ class TrainStep:
         self.eng = model._ensure_engine()
         d = self.eng.d
         dev = self.eng.device
-        self.images = torch.zeros(batch_size, d.chans, d.img, d.img, dtype=torch.float32, device=dev)
-        self.labels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        # two input slots: the pinned-host -> HBM copy of step i+1 runs on its own stream (copy engine) while step i computes
+        self._images = [torch.zeros(batch_size, d.chans, d.img, d.img, dtype=torch.float32, device=dev) for _ in range(2)]
+        self._labels = [torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.slot = 0
         self.stats = torch.zeros(8, dtype=torch.float32, device=dev)
         self.teacher_dtype = teacher_dtype
-        self.graph = None
+        self.graphs = [None, None]
         self.use_graph = use_graph
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._copied = [torch.cuda.Event() for _ in range(2)]     # slot filled (recorded on the copy stream)
+        self._consumed = [torch.cuda.Event() for _ in range(2)]   # slot no longer read (recorded on the compute stream)
+        self._pending_copy = False
         if mode == "distill" and teacher is None:
             raise ValueError("mode='distill' needs a teacher module")
         if reducer is not None:
             reducer.attach(self.eng)
+
+    @property
+    def images(self) -> torch.Tensor:
+        return self._images[self.slot]
+
+    @property
+    def labels(self) -> torch.Tensor:
+        return self._labels[self.slot]
 
     def _device_step(self) -> None:
         eng = self.eng
@@ -410,19 +424,39 @@ class TrainStep:
         self.opt.launch()
 
     def load(self, images: torch.Tensor, labels: torch.Tensor) -> None:
-        """Host (ideally pinned) or device tensors -> the step's static device buffers."""
-        self.images.copy_(images, non_blocking=True)
-        self.labels.copy_(labels, non_blocking=True)
+        """Host (ideally pinned) or device tensors -> the next input slot.  Host batches are copied on a dedicated
+        stream: the copy starts as soon as the slot's previous reader (two steps back) is done, i.e. it overlaps the
+        step that is still computing; run() makes the compute stream wait for it."""
+        self.slot ^= 1
+        s = self.slot
+        cur = torch.cuda.current_stream()
+        if images.is_cuda:
+            self._images[s].copy_(images, non_blocking=True)
+            self._labels[s].copy_(labels, non_blocking=True)
+            self._pending_copy = False
+            return
+        cs = self._copy_stream
+        cs.wait_event(self._consumed[s])
+        with torch.cuda.stream(cs):
+            self._images[s].copy_(images, non_blocking=True)
+            self._labels[s].copy_(labels, non_blocking=True)
+            self._copied[s].record(cs)
+        self._pending_copy = True
 
     def run(self) -> None:
         """Enqueue one step on the current stream (no host sync)."""
         model = self.model
         model._shadow_version = model._param_version()
         self.opt._refresh_hyper()
+        cur = torch.cuda.current_stream()
+        if self._pending_copy:
+            cur.wait_event(self._copied[self.slot])
+            self._pending_copy = False
         if not self.use_graph:
             self._device_step()
+            self._consumed[self.slot].record(cur)
             return
-        if self.graph is None:
+        if self.graphs[self.slot] is None:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):           # warm-up outside capture (lazy inits, workspace allocation)
@@ -431,11 +465,13 @@ class TrainStep:
                 self._restore(snapshot)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            g = torch.cuda.CUDAGraph()            # one graph per input slot (the slot's buffers are baked into it)
+            with torch.cuda.graph(g):
                 self._device_step()
+            self.graphs[self.slot] = g
             self._restore(snapshot)               # capture does not execute, but keep state exact anyway
-        self.graph.replay()
+        self.graphs[self.slot].replay()
+        self._consumed[self.slot].record(cur)
 
     def _snapshot(self):
         f, o = self.eng.flat, self.opt
