@@ -199,6 +199,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// TMA reduction: global[box] += smem[box] (fp32 add performed at the L2, one bulk request instead of 512 per-lane REDs)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -583,7 +590,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               *reinterpret_cast<float4*>(sbuf + swz64(lane, c)) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (elect_one() && !KNOB(1)) tma_store_2d(&tmOut, sbuf, col0, row_base);
+            if (elect_one() && !KNOB(1)) {
+              if (p.epilogue == VITK_EPI_ATOMIC_ADD) tma_reduce_add_2d(&tmOut, sbuf, col0, row_base);  // split-K partial tile
+              else tma_store_2d(&tmOut, sbuf, col0, row_base);
+            }
           } else {
             uint32_t v[32];
             DBG_UNIT(tcount, ucount, 0);
@@ -652,8 +662,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
         continue;
       }
+      if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 0);
       mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
       tcgen05_fence_after();
+      if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 1);
 #pragma unroll 1
       for (int c0 = group * 32; c0 < BN; c0 += 32 * (EPI_WARPS / 4)) {
         const int col0 = n0 + c0;
@@ -698,6 +710,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator stage
       tcgen05_fence_before();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
     }
     if (elect_one()) tma_store_wait_all();  // outstanding TMA stores must complete before the CTA (and its smem) goes away
   }
@@ -873,7 +886,8 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   if (rc != VITK_OK) return rc;
   // STORE / GELU / DGELU epilogues run on 2 KB TMA units (32x32 16-bit or 32x16 fp32 boxes, 64-byte rows, SWIZZLE_64B);
   // the only combination left on the per-thread path is a 16-bit output with an fp32 residual (its residual unit would be 4 KB)
-  const bool store_like = a->epilogue == VITK_EPI_STORE || a->epilogue == VITK_EPI_GELU || a->epilogue == VITK_EPI_DGELU;
+  const bool store_like = a->epilogue == VITK_EPI_STORE || a->epilogue == VITK_EPI_GELU || a->epilogue == VITK_EPI_DGELU ||
+                          (a->epilogue == VITK_EPI_ATOMIC_ADD && a->bias == nullptr && a->residual == nullptr);
   const int oalign = out_fp32 ? 4 : 8;
   p.tma_epi = (store_like && (a->residual == nullptr || out_fp32) && a->ldo % oalign == 0 &&
                (a->residual == nullptr || (a->ldr % 4 == 0)) &&

@@ -12,16 +12,28 @@ from thyroid_vit_cnn_comparison_b200 import _lib, ops
 F16 = torch.float16
 M, N, K = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 mode = sys.argv[4] if len(sys.argv) > 4 else "store"
-A = torch.randn(M, K, device="cuda").to(F16)
-W = (torch.randn(N, K, device="cuda") * .05).to(F16)
-bias = torch.randn(N, device="cuda")
-out = torch.empty(M, N, dtype=F16, device="cuda")
-out2 = torch.empty(M, N, dtype=F16, device="cuda")
-o32, r32 = torch.empty(M, N, device="cuda"), torch.randn(M, N, device="cuda")
+if mode != "wgrad":
+    A = torch.randn(M, K, device="cuda").to(F16)
+    W = (torch.randn(N, K, device="cuda") * .05).to(F16)
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, dtype=F16, device="cuda")
+    out2 = torch.empty(M, N, dtype=F16, device="cuda")
+    o32, r32 = torch.empty(M, N, device="cuda"), torch.randn(M, N, device="cuda")
 if mode == "store":
     fn = lambda: ops.gemm(A, W, M, N, K, out=out, bias=bias)
 elif mode == "gelu":
     fn = lambda: ops.gemm(A, W, M, N, K, out=out, out2=out2, bias=bias, epilogue=_lib.EPI_GELU)
+elif mode == "wgrad":   # dW[M=N_out, N=K_in] += dY^T X over K = tokens;  argv: N_out K_in tokens
+    dY = torch.randn(K, M, device="cuda").to(F16)
+    X = torch.randn(K, N, device="cuda").to(F16)
+    gw = torch.zeros(M, N, device="cuda")
+    one = torch.ones(1, device="cuda")
+    bn = 256 if N % 256 == 0 else 192 if N % 192 == 0 else 128 if N % 128 == 0 else 64
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    nkb = (K + 63) // 64
+    split = int(os.environ.get("SPLIT", "0")) or max(1, min(max(1, nkb // 2), (2 * 148 + tiles - 1) // tiles))
+    print("split_k", split)
+    fn = lambda: ops.gemm(dY, X, M, N, K, a_mn=True, b_mn=True, out=gw, epilogue=_lib.EPI_ATOMIC_ADD, split_k=split, alpha_dev=one)
 else:
     fn = lambda: ops.gemm(A, W, M, N, K, out=o32, bias=bias, residual=r32)
 for _ in range(3):
