@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 5
+#define VITK_ABI_VERSION 6
 
 typedef enum {
   VITK_OK = 0,
@@ -96,6 +96,10 @@ typedef struct {
    * pos is fp32 [tokens_per_img, N] (pos_embed), added to the row it lands on. */
   int32_t rows_per_img, tokens_per_img, prefix;
   const float* pos;
+  /* VITK_EPI_ATOMIC_ADD only (optional): colsum_out[m] += alpha * sum_k A[m,k], fp32 [M].  In wgrad (A = dY read
+   * MN-major) this is the bias gradient of the same nn.Linear; it falls out of one extra N=16 tensor-core MMA per
+   * k-step against a tile of ones, so dY is not read a second time. */
+  float* colsum_out;
 } vitk_gemm_args;
 
 int vitk_gemm(const vitk_gemm_args* args, void* stream);

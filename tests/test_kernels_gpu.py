@@ -124,6 +124,22 @@ def test_gemm_wgrad_mn_mn_splitk(Mc, No, Ko, split):
     assert rel_l2(out, ref) < 1e-4
 
 
+@pytest.mark.parametrize("Mc,No,Ko,split", [(6336, 576, 192, 8), (6336, 768, 192, 5), (50688, 2304, 768, 2), (1000, 136, 72, 3)])
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_gemm_wgrad_with_bias_grad(Mc, No, Ko, split, dt):
+    """The bias gradient (column sums of dY) falls out of the wgrad GEMM: one extra N=16 MMA per k-step against ones."""
+    dY = _rand(Mc, No, dtype=dt, seed=1)
+    X = _rand(Mc, Ko, dtype=dt, seed=2)
+    out = torch.zeros(No, Ko, dtype=torch.float32, device=DEV)
+    db = torch.full((No,), 0.5, dtype=torch.float32, device=DEV)      # accumulates (+=)
+    u = torch.tensor([0.25], device=DEV)
+    ops.gemm(dY, X, No, Ko, Mc, a_mn=True, b_mn=True, out=out, split_k=split, epilogue=_lib.EPI_ATOMIC_ADD, alpha_dev=u,
+             colsum_out=db)
+    torch.cuda.synchronize()
+    assert rel_l2(out, 0.25 * (dY.float().t() @ X.float())) < {F16: 1e-4, BF16: 1e-4}[dt]
+    assert rel_l2(db, 0.5 + 0.25 * dY.float().sum(0)) < 1e-4
+
+
 def test_gemm_tokens_epilogue():
     B, P, T, prefix, D, K = 5, 196, 198, 2, 192, 768
     A = _rand(B * P, K, dtype=F16, seed=1)

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("aux", c_void_p), ("ldaux", c_int64),
         ("rows_per_img", c_int), ("tokens_per_img", c_int), ("prefix", c_int),
         ("pos", c_void_p),
+        ("colsum_out", c_void_p),
     ]
 
 

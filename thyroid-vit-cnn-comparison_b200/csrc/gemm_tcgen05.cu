@@ -62,6 +62,7 @@ constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_PITCH = 20;  // floats per staged row (16 + 4 pad: conflict-free 128-bit accesses)
 constexpr int EPI_STAGE_FLOATS = 1024;  // per warp: 32 x EPI_PITCH floats (fp32 path) or two 2 KB TMA-store buffers (16-bit path)
 static_assert(EPI_STAGE_FLOATS >= 32 * EPI_PITCH, "staging buffer too small");
+constexpr int ONES_OFFSET = 2816;   // floats: the last 2 KB of the bias region hold the ones tile of the column-sum MMA
 constexpr int MAX_BIAS_SMEM = 3328;  // floats (13 KB): bias of every supported layer (N <= 3072, rounded up to the N tile)
 
 struct GemmParams {
@@ -70,6 +71,10 @@ struct GemmParams {
   int kblocks_per_split;
   int num_m_tiles, num_n_tiles, num_splits;
   int step_split, step_mt, step_nt;  // mixed-radix digits of the grid size over (split, m tile, n tile)
+  float* colsum;     // optional [M]: += alpha * sum_k A[m, k], from one extra N=16 MMA per k-step against a tile of ones
+  int acc_stride;    // TMEM columns per accumulator stage (BN, or BN + 16 with colsum)
+  int tmem_cols;     // TMEM allocation (power of two >= 2 * acc_stride)
+  uint32_t idesc_ones;
   int epilogue, out_dtype, aux_dtype;
   int tma_epi;     // STORE / GELU / DGELU epilogues: row-per-lane math, 2 KB swizzled staging units, TMA loads (residual / saved
                    // derivative) and TMA stores -- no per-thread global access in the epilogue
@@ -182,6 +187,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return v;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -350,7 +361,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = tmem_cols_for(BN);
   constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
 
   extern __shared__ uint8_t smem_raw[];
@@ -386,7 +396,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (p.colsum != nullptr) {  // 16 k-rows x 128 B of ones (B operand of the column-sum MMA) in the tail of the bias region
+    const uint32_t one2 = (p.idesc & (1u << 7)) ? 0x3f803f80u : 0x3c003c00u;  // bf16 / fp16 1.0 pairs
+    for (int i = threadIdx.x; i < 2048 / 4; i += GEMM_THREADS) reinterpret_cast<uint32_t*>(sBias + ONES_OFFSET)[i] = one2;
+    fence_proxy_async();
+  }
   if (p.tma_epi) {  // bias of every column tile (zeros when there is none), zero-padded to the tile grid
     const int n_up = p.num_n_tiles * BN;
     for (int i = threadIdx.x; i < n_up; i += GEMM_THREADS) sBias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
@@ -488,7 +503,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         DBG_STAMP(1, tcount, 1);
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+        const bool do_colsum = p.colsum != nullptr && n0 == 0;
+        const uint64_t ones_desc = make_smem_desc<true>(smem_u32(sBias + ONES_OFFSET));
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full_bar[s], ph, 2);
           tcgen05_fence_after();
@@ -498,6 +515,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             if (!KNOB(32)) umma_f16(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (do_colsum) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16(d_tmem + BN, adesc + uint64_t(k * a_adv), ones_desc, p.idesc_ones, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[s]);
           if (kb == nk - 1) {
             umma_commit(&tfull_bar[acc]);
@@ -524,7 +546,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int m0, n0, kb0, nk;
       decode(ti, m0, n0, kb0, nk);
       const uint32_t acc = tcount & 1;
-      const uint32_t t_addr = tmem_base + acc * BN + (uint32_t(quad * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t(quad * 32) << 16);
       const int row_base = m0 + quad * 32;
       if (p.tma_epi) {
         // ---- STORE / GELU / DGELU: units of 2 KB (32 rows x 32 16-bit columns, or 32 rows x 16 fp32 columns) ----
@@ -657,6 +679,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           more = c0 < BN && n0 + c0 < p.N;
           if (has_aux && more) issue_aux(c0);
         }
+        if (p.colsum != nullptr && n0 == 0 && group == 0) {  // row sums of A over this K range: one fp32 RED per row
+          const float v = __uint_as_float(tmem_ld1(t_addr + uint32_t(BN)));
+          if (row_base + lane < p.M) atomicAdd(p.colsum + row_base + lane, v * alpha);
+        }
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
@@ -717,7 +743,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------ host side
@@ -787,11 +813,12 @@ int dispatch_gemm(int bn, const CUtensorMap* tm, const GemmParams& p, int grid, 
 }
 
 // Pick the N tile: the widest of {256,192,128,64} that tiles N with the least padding.
-int pick_bn(int N) {
+int pick_bn(int N, bool with_colsum) {
   const int cands[4] = {256, 192, 128, 64};
   int best = 64;
   long best_cost = -1;
   for (int c : cands) {
+    if (with_colsum && c > 240) continue;  // two accumulator stages of BN + 16 columns must fit the 512 TMEM columns
     const long tiles = (N + c - 1) / c;
     const long cost = tiles * c;  // padded width; ties -> wider tile (listed first)
     if (best_cost < 0 || cost < best_cost) {
@@ -848,8 +875,11 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   if (a->residual)
     VITK_CHECK_ARG(a->ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0, "vitk_gemm: residual alignment");
   if (a->bias) VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "vitk_gemm: bias must be 16-byte aligned");
+  if (a->colsum_out)
+    VITK_CHECK_ARG(a->epilogue == VITK_EPI_ATOMIC_ADD && out_fp32 && a->bias == nullptr && a->residual == nullptr && a->ldo % 4 == 0,
+                   "vitk_gemm: colsum_out needs the split-K accumulate epilogue (fp32 out, no bias / residual)");
 
-  const int bn = pick_bn(a->N);
+  const int bn = pick_bn(a->N, a->colsum_out != nullptr);
   const int num_kblocks = (a->K + BLOCK_K - 1) / BLOCK_K;
   const int kpb = (num_kblocks + a->split_k - 1) / a->split_k;
   const int splits = (num_kblocks + kpb - 1) / kpb;
@@ -873,6 +903,10 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr;
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.aux = a->aux; p.ldaux = a->ldaux;
+  p.colsum = a->colsum_out;
+  p.acc_stride = bn + (a->colsum_out != nullptr ? 16 : 0);
+  p.tmem_cols = 2 * p.acc_stride <= 32 ? 32 : 2 * p.acc_stride <= 64 ? 64 : 2 * p.acc_stride <= 128 ? 128 : 2 * p.acc_stride <= 256 ? 256 : 512;
+  p.idesc_ones = make_idesc(16, a->a_mn_major != 0, true, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16);
   p.rows_per_img = a->rows_per_img; p.tokens_per_img = a->tokens_per_img; p.prefix = a->prefix; p.pos = a->pos;
 
   CUtensorMap tm[5];  // A, B, out, out2, aux
@@ -895,6 +929,8 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
                (a->epilogue != VITK_EPI_DGELU || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)))
                   ? 1 : 0;
   if (p.num_n_tiles * bn > MAX_BIAS_SMEM) p.tma_epi = 0;  // the TMA epilogue keeps the whole bias vector in shared memory
+  if (a->colsum_out != nullptr)
+    VITK_CHECK_ARG(p.tma_epi && p.num_n_tiles * bn <= ONES_OFFSET, "vitk_gemm: colsum_out supports N <= %d", ONES_OFFSET);
   tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];
   if (p.tma_epi) {
     const bool oh = a->out_dtype == VITK_FP16;

@@ -182,6 +182,108 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
   }
 }
 
+
+// ------------------------------------------------------------------ backward, "column owner" layout
+// A CTA of 192 threads covers 192 / V rows at a time (V = dim / 4 float4 columns per row: 48 for D = 192, 192 for D = 768):
+// every thread owns ONE float4 column, so the three column-sum accumulators (dgamma, dbeta, bias gradient) cost 12
+// registers instead of 12 per chunk per lane, and R rows per thread are in flight at once (R x 40 bytes of loads per
+// thread, 24+ resident warps per SM).  Row statistics are reduced inside G-lane groups by shuffles and across groups
+// through a double-buffered shared-memory table (one __syncthreads per batch of R x slots rows).
+template <int V, int R>
+__global__ void __launch_bounds__(192, 5)
+    ln_bwd_cols_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
+                       const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
+                       float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale, long long rows) {
+  constexpr int T = 192;
+  constexpr int SLOTS = T / V;                 // rows processed side by side
+  constexpr int G = (V % 32 == 0) ? 32 : 16;   // lanes per shuffle group (never straddles two rows)
+  constexpr int GPR = V / G;                   // groups per row
+  constexpr int DIM = V * 4;
+  __shared__ float2 part[2][R][SLOTS][GPR];
+  __shared__ float4 fin[3][SLOTS][V];
+  const int tid = threadIdx.x;
+  const int slot = tid / V, cv = tid - slot * V;
+  const int grp = cv / G, gl = cv % G;
+  const float inv_dim = 1.f / float(DIM);
+  const float4 gm = ldg_f4(gamma + 4 * cv);
+  float4 dg = make_float4(0, 0, 0, 0), db = dg, dc = dg;
+  const long long batch = (long long)SLOTS * R;
+  int it = 0;
+  for (long long base = (long long)blockIdx.x * batch; base < rows; base += (long long)gridDim.x * batch, ++it) {
+    float4 xv[R], rv[R];
+    uint2 dyu[R];
+    float mu[R], rs[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // every load of the batch in flight before any arithmetic
+      const long long row = base + r * SLOTS + slot;
+      const bool ok = row < rows;
+      const long long rr = ok ? row : 0;
+      xv[r] = ok ? ldg_f4(x + rr * DIM + 4 * cv) : make_float4(0, 0, 0, 0);
+      dyu[r] = ok ? ldg_u2(dy + rr * DIM + 4 * cv) : make_uint2(0, 0);
+      rv[r] = (ok && dres != nullptr) ? ldg_f4(dres + rr * DIM + 4 * cv) : make_float4(0, 0, 0, 0);
+      mu[r] = __ldg(mean + rr);
+      rs[r] = __ldg(rstd + rr);
+    }
+    float4 xh[R], g[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = base + r * SLOTS + slot;
+      const float2 d01 = unpack16(dyu[r].x, dy_fp16), d23 = unpack16(dyu[r].y, dy_fp16);
+      xh[r] = make_float4((xv[r].x - mu[r]) * rs[r], (xv[r].y - mu[r]) * rs[r], (xv[r].z - mu[r]) * rs[r], (xv[r].w - mu[r]) * rs[r]);
+      if (row >= rows) xh[r] = make_float4(0, 0, 0, 0);
+      g[r] = make_float4(d01.x * gm.x, d01.y * gm.y, d23.x * gm.z, d23.y * gm.w);
+      dg.x += d01.x * xh[r].x; dg.y += d01.y * xh[r].y; dg.z += d23.x * xh[r].z; dg.w += d23.y * xh[r].w;
+      db.x += d01.x; db.y += d01.y; db.z += d23.x; db.w += d23.y;
+      float s1 = g[r].x + g[r].y + g[r].z + g[r].w;
+      float s2 = g[r].x * xh[r].x + g[r].y * xh[r].y + g[r].z * xh[r].z + g[r].w * xh[r].w;
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (gl == 0) part[it & 1][r][slot][grp] = make_float2(s1, s2);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = base + r * SLOTS + slot;
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < GPR; ++k) {
+        const float2 pp = part[it & 1][r][slot][k];
+        m1 += pp.x;
+        m2 += pp.y;
+      }
+      m1 *= inv_dim;
+      m2 *= inv_dim;
+      if (row < rows) {
+        const float4 o = make_float4(rs[r] * (g[r].x - m1 - xh[r].x * m2) + rv[r].x, rs[r] * (g[r].y - m1 - xh[r].y * m2) + rv[r].y,
+                                     rs[r] * (g[r].z - m1 - xh[r].z * m2) + rv[r].z, rs[r] * (g[r].w - m1 - xh[r].w * m2) + rv[r].w);
+        *reinterpret_cast<float4*>(dx + row * DIM + 4 * cv) = o;
+        if (dx16 != nullptr)
+          *reinterpret_cast<uint2*>(dx16 + row * DIM + 4 * cv) = make_uint2(pack16(o.x, o.y, dx_fp16), pack16(o.z, o.w, dx_fp16));
+        dc.x += o.x; dc.y += o.y; dc.z += o.z; dc.w += o.w;
+      }
+    }
+  }
+  // column sums: combine the SLOTS partial owners of each column, then one global atomic per column per CTA
+  fin[0][slot][cv] = dg;
+  fin[1][slot][cv] = db;
+  fin[2][slot][cv] = dc;
+  __syncthreads();
+  const float u = unscale != nullptr ? __ldg(unscale) : 1.f;
+  for (int i = tid; i < 3 * DIM; i += T) {
+    const int which = i / DIM, c = i - which * DIM;
+    if (which == 2 && dcolsum == nullptr) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) acc += reinterpret_cast<const float*>(&fin[which][sl][0])[c];
+    float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dcolsum;
+    atomicAdd(dst + c, acc * u);
+  }
+}
+
 struct LnCfg {
   int lpr, chunks;
 };
@@ -252,6 +354,28 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
                  "vitk_layernorm_bwd: dy / dx16 must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_bwd: dim=%d must be a multiple of 4, <= 1024", dim);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // dims whose float4 column count divides 192 take the column-owner kernel (every ViT/DeiT width: 192, 384, 768; and 128)
+    const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+    __nv_bfloat16* dx16p = reinterpret_cast<__nv_bfloat16*>(dx16);
+    const int f_dy = int(dy_dtype == VITK_FP16), f_dx = int(dx16_dtype == VITK_FP16);
+#define LN_COLS(V_, R_)                                                                                                    \
+  {                                                                                                                        \
+    const long long batch = (long long)(192 / V_) * R_;                                                                    \
+    long long blocks = (rows + batch - 1) / batch;                                                                         \
+    const long long cap = (long long)num_sms() * 5;                                                                        \
+    if (blocks > cap) blocks = cap;                                                                                        \
+    ln_bwd_cols_kernel<V_, R_><<<(unsigned)blocks, 192, 0, st>>>(dyp, f_dy, x, mean, rstd, gamma, dres, dx, dx16p, f_dx, dgamma, \
+                                                                 dbeta, dcolsum, grad_unscale, rows);                    \
+    VITK_LAUNCH_CHECK();                                                                                                   \
+    return VITK_OK;                                                                                                        \
+  }
+    if (dim == 768) LN_COLS(192, 2)
+    if (dim == 384) LN_COLS(96, 2)
+    if (dim == 192) LN_COLS(48, 2)
+    if (dim == 128) LN_COLS(32, 2)
+#undef LN_COLS
+  }
   const LnCfg cfg = ln_config(dim);
   const size_t smem = 3 * (size_t)dim * sizeof(float);
   // each CTA should sweep several rows per lane group so the closing 3*dim global atomics are amortised

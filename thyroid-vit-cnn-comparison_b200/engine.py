@@ -216,19 +216,21 @@ class VitEngine:
             self._ws[key] = ws
         return ws
 
-    def _split_k(self, m_out: int, n_out: int, k: int) -> int:
-        bn = 256 if n_out % 256 == 0 else 192 if n_out % 192 == 0 else 128 if n_out % 128 == 0 else 64
+    def _split_k(self, m_out: int, n_out: int, k: int, colsum: bool = False) -> int:
+        bn = 256 if (n_out % 256 == 0 and not colsum) else 192 if n_out % 192 == 0 else 128 if n_out % 128 == 0 else 64
         tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
         nkb = (k + 63) // 64
         return max(1, min(max(1, nkb // 2), (2 * self.sms + tiles - 1) // tiles))
 
-    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, rows: int) -> None:
-        """grad[wname][N_out, K_in] += (1/S) * dy[rows, N_out]^T @ x[rows, K_in] (both operands read MN-major)."""
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, rows: int, bias_name: Optional[str] = None) -> None:
+        """grad[wname][N_out, K_in] += (1/S) * dy[rows, N_out]^T @ x[rows, K_in] (both operands read MN-major);
+        with `bias_name`, grad[bias][N_out] += (1/S) * column sums of dy from the same pass over dy."""
         gw = self.g(wname)
         n_out = gw.shape[0]
         k_in = gw.numel() // n_out
         ops.gemm(dy, x, n_out, k_in, rows, a_mn=True, b_mn=True, out=gw, epilogue=_lib.EPI_ATOMIC_ADD,
-                 split_k=self._split_k(n_out, k_in, rows), alpha_dev=self.grad_unscale)
+                 split_k=self._split_k(n_out, k_in, rows, bias_name is not None), alpha_dev=self.grad_unscale,
+                 colsum_out=self.g(bias_name) if bias_name is not None else None)
 
     # ------------------------------------------------------------------ forward
     def forward(self, images: torch.Tensor, train: bool, attn_probs: Optional[List[torch.Tensor]] = None):
@@ -309,8 +311,7 @@ class VitEngine:
             self._wgrad(ws.dx16, ws.act[l], pre + "mlp.fc2.weight", M)
             ops.gemm(ws.dx16, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.dact[l],
                      epilogue=_lib.EPI_DGELU)
-            ops.colsum16(ws.d_pre, self.g(pre + "mlp.fc1.bias"), unscale=u)
-            self._wgrad(ws.d_pre, ws.xn2[l], pre + "mlp.fc1.weight", M)
+            self._wgrad(ws.d_pre, ws.xn2[l], pre + "mlp.fc1.weight", M, bias_name=pre + "mlp.fc1.bias")
             ops.gemm(ws.d_pre, self.w(pre + "mlp.fc1.weight"), M, D, d.hidden, b_mn=True, out=ws.dxn)
             ops.layernorm_bwd(ws.dxn, x_mid, st[2], st[3], self.p(pre + "norm2.weight"), self.g(pre + "norm2.weight"),
                               self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16,
@@ -320,8 +321,7 @@ class VitEngine:
             self._wgrad(ws.dx16, ws.ao[l], pre + "attn.proj.weight", M)
             ops.gemm(ws.dx16, self.w(pre + "attn.proj.weight"), M, D, D, b_mn=True, out=ws.d_ao)
             ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
-            ops.colsum16(ws.dqkv, self.g(pre + "attn.qkv.bias"), unscale=u)
-            self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M)
+            self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M, bias_name=pre + "attn.qkv.bias")
             ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
             prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
             ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),

@@ -59,7 +59,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
          out: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          epilogue: int = _lib.EPI_STORE, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          split_k: int = 1, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, tokens: Optional[tuple] = None,
-         pos: Optional[torch.Tensor] = None, lda: Optional[int] = None, ldb: Optional[int] = None) -> torch.Tensor:
+         pos: Optional[torch.Tensor] = None, lda: Optional[int] = None, ldb: Optional[int] = None,
+         colsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue (see include/vitk.h).
 
     A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].  A and B must share one
@@ -90,6 +91,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     if tokens is not None:
         a.rows_per_img, a.tokens_per_img, a.prefix = tokens
         a.pos = _p(pos)
+    if colsum_out is not None:
+        _req(colsum_out, f32, "gemm colsum_out")
+    a.colsum_out = _p(colsum_out)
     check(_lib.load().vitk_gemm(C.byref(a), _stream()), "gemm")
     return out
 
