@@ -251,7 +251,7 @@ def run_ours(args):
         for p in teacher.parameters():
             p.requires_grad = False
     reducer = parallel.BucketedAllReduce(bucket_mb=args.bucket_mb) if world > 1 else None
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or args.dp_graph)
     step = training.TrainStep(model, opt, args.batch, mode=args.mode, teacher=teacher, reducer=reducer, use_graph=use_graph)
 
     g = torch.Generator().manual_seed(1234 + rank)
@@ -316,9 +316,16 @@ def run_ours(args):
     # live per-kernel profile (eager, CUDA events on the launching stream)
     roof, kernels = None, None
     pk, pk_src = peaks()
+    nprof = 3
+    if rank != 0:
+        # the eager profile steps issue gradient all-reduces: every rank has to take part in them
+        saved_graph, step.use_graph = step.use_graph, False
+        for _ in range(nprof):
+            step.run()
+        step.use_graph = saved_graph
+        torch.cuda.synchronize()
     if rank == 0:
         saved_graph, step.use_graph = step.use_graph, False
-        nprof = 3
         with KernelProfile(ops, by_shape=args.by_shape) as prof:
             for _ in range(nprof):
                 step.run()
@@ -374,7 +381,16 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # teardown must never hold the box: drop captured graphs (they pin NCCL work), then leave; a watchdog ends the
+        # process if the communicator teardown itself blocks (the result line is already out)
+        def _bail():
+            time.sleep(20)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        step.graphs = [None, None]
+        torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -389,6 +405,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dp-graph", action="store_true", help="N > 1: capture the step (NCCL all-reduces included) in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--by-shape", action="store_true", help="split the GEMM rows of the kernel profile by shape")
     args = ap.parse_args()

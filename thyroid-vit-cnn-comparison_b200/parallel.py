@@ -29,11 +29,14 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        import datetime
+        # a mismatched collective must fail within minutes, not hold a multi-GPU box for the default 10
+        timeout = datetime.timedelta(seconds=int(os.environ.get("VITK_DIST_TIMEOUT_S", "120")))
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group(backend=backend, device_id=torch.device("cuda", local))
+            dist.init_process_group(backend=backend, device_id=torch.device("cuda", local), timeout=timeout)
         else:
-            dist.init_process_group(backend=backend)
+            dist.init_process_group(backend=backend, timeout=timeout)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, world, local
