@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "vitk_common.cuh"
 
@@ -18,6 +19,14 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VITK_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
 
 }  // namespace vitk
 

@@ -523,7 +523,8 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 }  // namespace
 
 // tcgen05 / TMEM kernels for sequences of up to 256 tokens (attention_tc.cu)
-constexpr int TC_MAX_TOKENS = 256;
+constexpr int TC_MAX_TOKENS = 256;      // forward
+constexpr int TC_MAX_TOKENS_BWD = 240;  // backward (shared-memory budget of the pipelined kernel)
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
                      int H, float scale, bool fp16, cudaStream_t st);
@@ -571,7 +572,7 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
     configured = true;
   }
-  if (N <= TC_MAX_TOKENS) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, H16, st);  // delta fused
+  if (N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, H16, st);  // delta fused
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
                                                                      reinterpret_cast<const bf16*>(dout), delta, B, N, H);

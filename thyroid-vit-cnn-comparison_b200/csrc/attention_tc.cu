@@ -12,15 +12,29 @@
 //   O[128 x 64] = P V              tcgen05.mma TS (A = P from TMEM, B = V MN-major from smem), TMEM columns [128, 192)
 //   out = O / rowsum               TMEM -> registers -> swizzled smem -> TMA store (rows >= N clipped by the tensor map)
 //
-// Backward (one CTA per (head, image); 8 math warps + 1 TMA/MMA warp; all 512 TMEM columns).  For every 128-key tile j
-// and every <=128-query chunk c:
-//   S^T = K_j Q_c^T, dP^T = V_j dO_c^T             (SS)  columns [0,128), [128,256); lane = key, column = query
-//   P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - delta)   16-bit, written IN PLACE over the half of the columns each
-//                                                   warp consumed; dS is also staged MN-major in smem (A operand of dQ)
+// Backward (one CTA per (head, image); 8 math warps + 1 TMA/MMA warp; all 512 TMEM columns; N <= 240).  For every
+// 128-key tile j and every 64-query chunk c (software-pipelined: the MMAs of chunk t run while chunk t+1 is computed):
+//   S^T = K_j Q_c^T, dP^T = V_j dO_c^T             (SS)  columns [0,64), [64,128); lane = key, column = query
+//   P^T = exp2(S^T*c - lse), dS^T = P^T o (dP^T - delta)   16-bit, double-buffered in columns [128,256); dS is also
+//                                                   staged MN-major in smem (A operand of dQ); delta = rowsum(dO o O)
+//                                                   is computed in the kernel from the TMA-staged dO and O tiles
 //   dV_j += P^T dO_c, dK_j += dS^T Q_c             (TS)  columns [256,320), [320,384)
-//   dQ_c += dS K_j                                 (SS)  columns [384,448) / [448,512), accumulated over j
-// so K, V, Q, dO are read from HBM exactly once and nothing is recomputed or reduced through global memory.
+//   dQ_i += dS K_j  (128-query tile i = 2 chunks)  (SS)  columns [384,448) / [448,512), accumulated over j
+// so K, V, Q, dO, O are read from HBM exactly once and nothing is recomputed or reduced through global memory.
 #include "tc_common.cuh"
+
+#ifdef VITK_GEMM_KNOBS
+// profiling build only: SM clock stamps of CTA (0,0) -- [0..63] MMA thread, [64..] math warp 0 lane 0
+__device__ long long g_attn_dbg[256];
+#define ASTAMP(i)                                                                   \
+  do {                                                                              \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < 256) g_attn_dbg[i] = clock64(); \
+  } while (0)
+#else
+#define ASTAMP(i) \
+  do {            \
+  } while (0)
+#endif
 
 namespace vitk {
 namespace {
@@ -48,7 +62,7 @@ template <bool H16>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KP, float scale,
-                       float scale_log2) {
+                       float scale_log2, int wave_ctas) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -77,15 +91,26 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       mbar_init(bar_p, 128);
       mbar_init(bar_o, 1);
       mbar_init_fence();
+      pdl_wait();  // qkv is the previous kernel's output
       mbar_expect_tx(bar_qk, (128 + KP) * 128);
       tma_load_3d(sQ, &tmQ, bar_qk, h * DH, q0, b);
       tma_load_3d(sK, &tmKV, bar_qk, (H + h) * DH, 0, b);
       mbar_expect_tx(bar_v, KP * 128);
       tma_load_3d(sV, &tmKV, bar_v, (2 * H + h) * DH, 0, b);
+      // operands of the CTA that runs one wave later -> L2
+      const long long nxt = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + wave_ctas;
+      if (nxt < (long long)gridDim.x * gridDim.y * gridDim.z) {
+        const int nq = int(nxt % gridDim.x), nh = int((nxt / gridDim.x) % gridDim.y), nb = int(nxt / ((long long)gridDim.x * gridDim.y));
+        tma_prefetch_3d(&tmQ, nh * DH, nq * 128, nb);
+        tma_prefetch_3d(&tmKV, (H + nh) * DH, 0, nb);
+        tma_prefetch_3d(&tmKV, (2 * H + nh) * DH, 0, nb);
+      }
     }
     __syncwarp();
     tmem_alloc<256>(tmem_slot);
   }
+  pdl_trigger();
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -118,11 +143,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     const int row = warp * 32 + lane;
     const int q = q0 + row;
     const uint32_t trow = tb + (uint32_t(warp * 32) << 16);
+    // a warp whose 32 query rows are all padding (second tile of a 197/198-token sequence) only keeps the barriers moving;
+    // its P / O rows are garbage that no valid row depends on and the TMA store clips
+    const bool warp_valid = q0 + warp * 32 < N;
     mbar_wait(bar_s, 0, 4);
     tc_fence_after();
     // pass 1: row maximum over the valid keys
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < KP; c0 += 32) {
+    for (int c0 = 0; warp_valid && c0 < KP; c0 += 32) {
       uint32_t v[32];
       if (KP - c0 >= 32) {
         tmem_ld32_nowait(trow + uint32_t(c0), v);
@@ -137,8 +165,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     }
     // pass 2: P = exp2((S - max) * scale * log2e), 16-bit, in place
     const float msc = mx * scale_log2;
-    float sum = 0.f;
-    for (int c0 = 0; c0 < KP; c0 += 32) {
+    float2 sum2 = make_float2(0.f, 0.f);
+    for (int c0 = 0; warp_valid && c0 < KP; c0 += 32) {
       uint32_t v[32];
       const bool full = KP - c0 >= 32;
       if (full) {
@@ -150,16 +178,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       }
       tmem_ld_wait();
       uint32_t ph[16];
+      const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-msc, -msc);
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float p0 = (c0 + j < N) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2, -msc)) : 0.f;
-        const float p1 = (c0 + j + 1 < N) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2, -msc)) : 0.f;
-        sum += p0 + p1;
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nm2);
+        const float p0 = (c0 + j < N) ? ex2_approx(x.x) : 0.f;
+        const float p1 = (c0 + j + 1 < N) ? ex2_approx(x.y) : 0.f;
+        sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
         ph[j >> 1] = pk16<H16>(p0, p1);
       }
       if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
       else tmem_st8_nowait(trow + uint32_t(c0 >> 1), ph);
     }
+    const float sum = sum2.x + sum2.y;
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(bar_p);
@@ -170,6 +201,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     tc_fence_after();
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
+      if (!warp_valid) break;
       uint32_t v[32];
       tmem_ld32_nowait(trow + uint32_t(O_COL + 32 * hh), v);
       tmem_ld_wait();
@@ -188,7 +220,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     if (warp == 0 && elect_one()) {
       tma_store_3d(&tmO, sQ, h * DH, q0, b);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();   // shared memory must outlive the reads; the writes complete asynchronously
     }
   }
   tc_fence_before();
@@ -198,58 +230,49 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
 
 // ================================================================================================ backward
 constexpr int BWD_THREADS = 288;  // 8 math warps + 1 control warp
-constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+// TMEM map (all 512 columns).  S^T / dP^T hold one 64-query chunk (fp32, lane = key); P^T / dS^T are their 16-bit
+// versions (A operands of dV / dK), double-buffered so that the MMAs of chunk t run while chunk t+1 is being computed.
+constexpr int TM_S = 0, TM_DP = 64, TM_PT = 128 /* +64*buf */, TM_DS = 160 /* +64*buf */, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
-// One 32- or 16-column group of the backward math: thread = key lane, columns = queries g0 .. g0+W-1 of chunk c.
+// Math of one chunk for one thread: W (32 or 16) query columns starting at column g0 of the chunk, key lane = this thread.
 template <bool H16, int W>
-__device__ __forceinline__ void bwd_math_group(uint32_t trow, int g0, int pcol, const float* __restrict__ s_lse2,
-                                               const float* __restrict__ s_delta, int qbase, float scale_log2, bool keyvalid,
-                                               uint8_t* sDS, int keyrow) {
-  uint32_t sv[W], dv[W];
-  if constexpr (W == 32) {
-    tmem_ld32_nowait(trow + uint32_t(TM_S + g0), sv);
-    tmem_ld32_nowait(trow + uint32_t(TM_DP + g0), dv);
-  } else {
-    tmem_ld16_nowait(trow + uint32_t(TM_S + g0), sv);
-    tmem_ld16_nowait(trow + uint32_t(TM_DP + g0), dv);
-  }
-  tmem_ld_wait();
+__device__ __forceinline__ void bwd_math(const uint32_t (&sv)[32], const uint32_t (&dv)[32], uint32_t trow, int g0, int buf,
+                                         const float* __restrict__ s_lse2, const float* __restrict__ s_delta, int qbase,
+                                         float scale_log2, bool keyvalid, uint8_t* sDSblk, int keyrow) {
   uint32_t ph[W / 2], dh[W / 2];
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
 #pragma unroll
   for (int e = 0; e < W; e += 4) {
+    // s_lse2 / s_delta hold the NEGATED statistics (-lse*log2e, -delta): everything below is packed fp32x2 math
     const float4 l4 = *reinterpret_cast<const float4*>(s_lse2 + qbase + g0 + e);   // warp-uniform address: broadcast
     const float4 d4 = *reinterpret_cast<const float4*>(s_delta + qbase + g0 + e);
-    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e + 0]), scale_log2, -l4.x));
-    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e + 1]), scale_log2, -l4.y));
-    const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e + 2]), scale_log2, -l4.z));
-    const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e + 3]), scale_log2, -l4.w));
-    const float s0 = p0 * (__uint_as_float(dv[e + 0]) - d4.x);
-    const float s1 = p1 * (__uint_as_float(dv[e + 1]) - d4.y);
-    const float s2 = p2 * (__uint_as_float(dv[e + 2]) - d4.z);
-    const float s3 = p3 * (__uint_as_float(dv[e + 3]) - d4.w);
-    ph[(e >> 1) + 0] = pk16<H16>(p0, p1);
-    ph[(e >> 1) + 1] = pk16<H16>(p2, p3);
-    dh[(e >> 1) + 0] = pk16<H16>(s0, s1);
-    dh[(e >> 1) + 1] = pk16<H16>(s2, s3);
+    const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), sc2, make_float2(l4.x, l4.y));
+    const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sc2, make_float2(l4.z, l4.w));
+    const float2 p01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
+    const float2 p23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
+    const float2 t01 = __fadd2_rn(make_float2(__uint_as_float(dv[e + 0]), __uint_as_float(dv[e + 1])), make_float2(d4.x, d4.y));
+    const float2 t23 = __fadd2_rn(make_float2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), make_float2(d4.z, d4.w));
+    const float2 s01 = __fmul2_rn(p01, t01), s23 = __fmul2_rn(p23, t23);
+    ph[(e >> 1) + 0] = pk16<H16>(p01.x, p01.y);
+    ph[(e >> 1) + 1] = pk16<H16>(p23.x, p23.y);
+    dh[(e >> 1) + 0] = pk16<H16>(s01.x, s01.y);
+    dh[(e >> 1) + 1] = pk16<H16>(s23.x, s23.y);
   }
   if (!keyvalid) {  // padded key lane (its S / dP rows are garbage, possibly non-finite): contributes exactly zero
 #pragma unroll
     for (int i = 0; i < W / 2; ++i) ph[i] = dh[i] = 0u;
   }
   if constexpr (W == 32) {
-    tmem_st16_nowait(trow + uint32_t(TM_S + pcol), ph);
-    tmem_st16_nowait(trow + uint32_t(TM_DP + pcol), dh);
+    tmem_st16_nowait(trow + uint32_t(TM_PT + 64 * buf + (g0 >> 1)), ph);
+    tmem_st16_nowait(trow + uint32_t(TM_DS + 64 * buf + (g0 >> 1)), dh);
   } else {
-    tmem_st8_nowait(trow + uint32_t(TM_S + pcol), ph);
-    tmem_st8_nowait(trow + uint32_t(TM_DP + pcol), dh);
+    tmem_st8_nowait(trow + uint32_t(TM_PT + 64 * buf + (g0 >> 1)), ph);
+    tmem_st8_nowait(trow + uint32_t(TM_DS + 64 * buf + (g0 >> 1)), dh);
   }
-  // dS, MN-major A operand of dQ = dS K: 64-query blocks of [128 key rows][128 B], 128B swizzle
+  // dS, MN-major A operand of dQ = dS K: [128 key rows][64 queries = 128 B], 128B swizzle
 #pragma unroll
-  for (int ch = 0; ch < W / 8; ++ch) {
-    const int ql = g0 + 8 * ch;  // query index inside the chunk
-    *reinterpret_cast<uint4*>(sDS + (ql >> 6) * 16384 + swz128(keyrow, (ql & 63) >> 3)) =
-        make_uint4(dh[4 * ch], dh[4 * ch + 1], dh[4 * ch + 2], dh[4 * ch + 3]);
-  }
+  for (int ch = 0; ch < W / 8; ++ch)
+    *reinterpret_cast<uint4*>(sDSblk + swz128(keyrow, (g0 >> 3) + ch)) = make_uint4(dh[4 * ch], dh[4 * ch + 1], dh[4 * ch + 2], dh[4 * ch + 3]);
 }
 
 template <bool H16>
@@ -257,7 +280,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQKV,
                        const float* __restrict__ lse, float* __restrict__ delta, int N, int H, int QP, float scale,
-                       float scale_log2) {
+                       float scale_log2, int wave_ctas) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -266,23 +289,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   uint8_t* sK = sQ + tile_bytes;
   uint8_t* sV = sK + tile_bytes;
   uint8_t* sDO = sV + tile_bytes;
-  uint8_t* sDS = sDO + tile_bytes;   // 2 x [128][128 B]
-  uint8_t* sOut = sDS + 32768;       // 2 x [128][128 B]
+  uint8_t* sDS = sDO + tile_bytes;   // 2 buffers (one per 128-query tile in flight) x 2 chunks x [128][128 B]
+  uint8_t* sOut = sDS + 65536;       // 2 x [128][128 B]: O at start-up, output staging afterwards
   float* s_lse2 = reinterpret_cast<float*>(sOut + 32768);  // [256]
   float* s_delta = s_lse2 + 256;                            // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
-  uint64_t* bar_load = bars + 0;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_p = bars + 2;
-  uint64_t* bar_m2 = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_kq = bars + 0;      // K, Q landed
+  uint64_t* bar_vdo = bars + 1;     // V, dO landed
+  uint64_t* bar_o = bars + 2;       // O landed
+  uint64_t* bar_s = bars + 3;       // S^T, dP^T of chunk t complete
+  uint64_t* bar_ld = bars + 4;      // every math thread has S^T, dP^T of chunk t in registers
+  uint64_t* bar_p = bars + 5;       // P^T, dS^T (TMEM + staging) of chunk t written
+  uint64_t* bar_m2 = bars + 6;      // [2] dV / dK / dQ MMAs that read P/dS buffer (t & 1) complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int NJ = (N + 127) >> 7;   // 128-key tiles
-  const int NC = NJ;               // <=128-query chunks
-  const int T = NJ * NC;
+  const int NJ = (N + 127) >> 7;    // 128-key tiles
+  const int NCH = (QP + 63) >> 6;   // 64-query chunks
+  const int T = NJ * NCH;
 
   if (warp == 8) {
     if (elect_one()) {
@@ -290,28 +315,46 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       prefetch_tmap(&tmDO);
       prefetch_tmap(&tmO);
       prefetch_tmap(&tmDQKV);
-      mbar_init(bar_load, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 256);
-      mbar_init(bar_m2, 1);
+      mbar_init(bar_kq, 1);
+      mbar_init(bar_vdo, 1);
       mbar_init(bar_o, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_ld, 256);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_m2 + 0, 1);
+      mbar_init(bar_m2 + 1, 1);
       mbar_init_fence();
-      mbar_expect_tx(bar_load, 4 * tile_bytes);
-      tma_load_3d(sK, &tmQKV, bar_load, (H + h) * DH, 0, b);
-      tma_load_3d(sQ, &tmQKV, bar_load, h * DH, 0, b);
-      tma_load_3d(sV, &tmQKV, bar_load, (2 * H + h) * DH, 0, b);
-      tma_load_3d(sDO, &tmDO, bar_load, h * DH, 0, b);
+      pdl_wait();  // qkv / dO / O are earlier kernels' outputs
+      mbar_expect_tx(bar_kq, 2 * tile_bytes);
+      tma_load_3d(sK, &tmQKV, bar_kq, (H + h) * DH, 0, b);
+      tma_load_3d(sQ, &tmQKV, bar_kq, h * DH, 0, b);
+      mbar_expect_tx(bar_vdo, 2 * tile_bytes);
+      tma_load_3d(sV, &tmQKV, bar_vdo, (2 * H + h) * DH, 0, b);
+      tma_load_3d(sDO, &tmDO, bar_vdo, h * DH, 0, b);
       mbar_expect_tx(bar_o, tile_bytes);            // O parks in the (still unused) output staging buffer
       tma_load_3d(sOut, &tmO, bar_o, h * DH, 0, b);
+      // operands of the CTA that runs one wave later -> L2 (HBM streams while this wave computes)
+      const int nxt = blockIdx.y * gridDim.x + blockIdx.x + wave_ctas;
+      if (nxt < (int)(gridDim.x * gridDim.y)) {
+        const int nh = nxt % gridDim.x, nb = nxt / gridDim.x;
+        tma_prefetch_3d(&tmQKV, (H + nh) * DH, 0, nb);
+        tma_prefetch_3d(&tmQKV, nh * DH, 0, nb);
+        tma_prefetch_3d(&tmQKV, (2 * H + nh) * DH, 0, nb);
+        tma_prefetch_3d(&tmDO, nh * DH, 0, nb);
+        tma_prefetch_3d(&tmO, nh * DH, 0, nb);
+      }
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
+    pdl_wait();
   } else {
-    // lse in the log2 domain (+inf masks the padded queries: P = exp2(-inf) = 0)
+    pdl_wait();
+    // -lse in the log2 domain (-inf masks the padded queries: P = exp2(-inf) = 0)
     const float* lse_b = lse + ((long long)b * H + h) * N;
     const int i = threadIdx.x;  // 0..255
-    s_lse2[i] = i < N ? lse_b[i] * LOG2E : INFINITY;
+    s_lse2[i] = i < N ? -lse_b[i] * LOG2E : -INFINITY;   // negated (see bwd_math)
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -320,57 +363,75 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   if (warp == 8) {
     // ===================== MMA issuer (one elected thread) =====================
     if (elect_one()) {
-      mbar_wait(bar_load, 0, 1);
-      tc_fence_after();
       const uint32_t idesc64_ts = idesc_f16(DH, false, true, H16);   // A from TMEM (K-major), B MN-major
       const uint32_t idesc64_mn = idesc_f16(DH, true, true, H16);    // A, B MN-major from smem
-      auto issue_g1 = [&](int j, int c) {
-        const int QC = min(128, QP - 128 * c);
+      auto issue_s = [&](int j, int c) {      // S^T = K_j Q_c^T
+        const int QC = min(64, QP - 64 * c);
         const uint32_t idesc_s = idesc_f16(QC, false, false, H16);
         const uint64_t kd = smem_desc_kmajor(smem_u32(sK + j * 16384));
-        const uint64_t qd = smem_desc_kmajor(smem_u32(sQ + c * 16384));
-        const uint64_t vd = smem_desc_kmajor(smem_u32(sV + j * 16384));
-        const uint64_t dd = smem_desc_kmajor(smem_u32(sDO + c * 16384));
+        const uint64_t qd = smem_desc_kmajor(smem_u32(sQ + c * 8192));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tb + TM_S, kd + uint64_t(2 * k), qd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+      };
+      auto issue_dp = [&](int j, int c) {     // dP^T = V_j dO_c^T
+        const int QC = min(64, QP - 64 * c);
+        const uint32_t idesc_s = idesc_f16(QC, false, false, H16);
+        const uint64_t vd = smem_desc_kmajor(smem_u32(sV + j * 16384));
+        const uint64_t dd = smem_desc_kmajor(smem_u32(sDO + c * 8192));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tb + TM_DP, vd + uint64_t(2 * k), dd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
       };
-      issue_g1(0, 0);
+      ASTAMP(0);
+      mbar_wait(bar_kq, 0, 1);
+      tc_fence_after();
+      ASTAMP(1);
+      issue_s(0, 0);
+      mbar_wait(bar_vdo, 0, 2);
+      tc_fence_after();
+      ASTAMP(2);
+      issue_dp(0, 0);
+      umma_commit(bar_s);
       int t = 0;
       for (int j = 0; j < NJ; ++j) {
-        for (int c = 0; c < NC; ++c, ++t) {
-          mbar_wait(bar_p, t & 1, 2);
+        for (int c = 0; c < NCH; ++c, ++t) {
+          // the math warps hold chunk t in registers: S^T / dP^T may be overwritten by chunk t+1 right away
+          mbar_wait(bar_ld, t & 1, 3);
           tc_fence_after();
-          const int QC = min(128, QP - 128 * c);
-          const int HB = ((QC >> 1) + 15) & ~15;
-          const int KJ = min(128, QP - 128 * j);
+          ASTAMP(4 + 4 * t);
+          if (t + 1 < T) {
+            const int c1 = (c + 1 == NCH) ? 0 : c + 1;
+            const int j1 = (c + 1 == NCH) ? j + 1 : j;
+            issue_s(j1, c1);
+            issue_dp(j1, c1);
+            umma_commit(bar_s);
+          }
+          mbar_wait(bar_p, t & 1, 4);
+          tc_fence_after();
+          ASTAMP(5 + 4 * t);
+          const int buf = t & 1;
+          const int QC = min(64, QP - 64 * c);
           const int qsteps = QC >> 4;
           for (int s = 0; s < qsteps; ++s) {   // dV_j += P^T dO_c
-            const int qo = 16 * s;
-            const int acol = qo < HB ? (qo >> 1) : HB + ((qo - HB) >> 1);
-            const uint64_t bd = smem_desc_mnmajor(smem_u32(sDO + (c * 128 + qo) * 128), 8192);
-            umma_ts(tb + TM_DV, tb + uint32_t(TM_S + acol), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
+            const uint64_t bd = smem_desc_mnmajor(smem_u32(sDO + (c * 64 + 16 * s) * 128), 8192);
+            umma_ts(tb + TM_DV, tb + uint32_t(TM_PT + 64 * buf + 8 * s), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
           }
           for (int s = 0; s < qsteps; ++s) {   // dK_j += dS^T Q_c
-            const int qo = 16 * s;
-            const int acol = qo < HB ? (qo >> 1) : HB + ((qo - HB) >> 1);
-            const uint64_t bd = smem_desc_mnmajor(smem_u32(sQ + (c * 128 + qo) * 128), 8192);
-            umma_ts(tb + TM_DK, tb + uint32_t(TM_DP + acol), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
+            const uint64_t bd = smem_desc_mnmajor(smem_u32(sQ + (c * 64 + 16 * s) * 128), 8192);
+            umma_ts(tb + TM_DK, tb + uint32_t(TM_DS + 64 * buf + 8 * s), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
           }
-          const int ksteps = KJ >> 4;
-          for (int s = 0; s < ksteps; ++s) {   // dQ_c += dS K_j
-            const uint64_t ad = smem_desc_mnmajor(smem_u32(sDS + s * 2048), 16384);
-            const uint64_t bd = smem_desc_mnmajor(smem_u32(sK + (j * 128 + 16 * s) * 128), 8192);
-            umma_ss(tb + uint32_t(TM_DQ + 64 * c), ad, bd, idesc64_mn, (j > 0 || s > 0) ? 1u : 0u);
+          if ((c & 1) || c == NCH - 1) {       // the 128-query tile c/2 is staged completely: dQ += dS K_j
+            const int qt = c >> 1;
+            const int u = j * ((NCH + 1) >> 1) + qt;
+            const int KJ = min(128, QP - 128 * j);
+            const int ksteps = KJ >> 4;
+            for (int s = 0; s < ksteps; ++s) {
+              const uint64_t ad = smem_desc_mnmajor(smem_u32(sDS + (u & 1) * 32768 + s * 2048), 16384);
+              const uint64_t bd = smem_desc_mnmajor(smem_u32(sK + (j * 128 + 16 * s) * 128), 8192);
+              umma_ss(tb + uint32_t(TM_DQ + 64 * qt), ad, bd, idesc64_mn, (j > 0 || s > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(bar_m2);
-          if (t + 1 < T) {
-            const int c1 = (c + 1 == NC) ? 0 : c + 1;
-            const int j1 = (c + 1 == NC) ? j + 1 : j;
-            issue_g1(j1, c1);
-          }
+          umma_commit(bar_m2 + buf);
+          ASTAMP(6 + 4 * t);
         }
       }
     }
@@ -384,7 +445,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     {
       // delta[q] = sum_d dO[q,d] * O[q,d] (the softmax-backward row term), one query row per thread, straight from the
       // TMA-staged dO and O tiles -- no separate pass over HBM
-      mbar_wait(bar_load, 0, 5);
+      mbar_wait(bar_vdo, 0, 5);
       mbar_wait(bar_o, 0, 6);
       float dsum = 0.f;
       if (tid < N) {
@@ -402,30 +463,50 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         }
         delta[((long long)b * H + h) * N + tid] = dsum;
       }
-      s_delta[tid] = dsum;
+      s_delta[tid] = -dsum;   // negated (see bwd_math)
       named_bar_sync(1, 256);
     }
+    if (tid == 0) ASTAMP(64);
     int t = 0;
     for (int j = 0; j < NJ; ++j) {
       const bool keyvalid = (j * 128 + keyrow) < N;
-      for (int c = 0; c < NC; ++c, ++t) {
-        const int QC = min(128, QP - 128 * c);
-        const int HB = ((QC >> 1) + 15) & ~15;
-        const int cbeg = half == 0 ? 0 : HB, cend = half == 0 ? HB : QC;
-        mbar_wait(bar_s, t & 1, 3);
+      for (int c = 0; c < NCH; ++c, ++t) {
+        const int QC = min(64, QP - 64 * c);
+        const int g0 = half * 32;                       // this warp's columns: [g0, min(g0 + 32, QC))
+        const int w = min(32, QC - g0);                 // 32, 16 or <= 0 (QC is a multiple of 16)
+        const int buf = t & 1;
+        const int u = j * ((NCH + 1) >> 1) + (c >> 1);
+        uint8_t* sDSblk = sDS + (u & 1) * 32768 + (c & 1) * 16384;
+        if (tid == 0) ASTAMP(68 + 8 * t);
+        mbar_wait(bar_s, t & 1, 7);
         tc_fence_after();
-        int g0 = cbeg;
-        for (; g0 + 32 <= cend; g0 += 32)
-          bwd_math_group<H16, 32>(trow, g0, cbeg + ((g0 - cbeg) >> 1), s_lse2, s_delta, c * 128, scale_log2, keyvalid, sDS, keyrow);
-        if (g0 < cend)
-          bwd_math_group<H16, 16>(trow, g0, cbeg + ((g0 - cbeg) >> 1), s_lse2, s_delta, c * 128, scale_log2, keyvalid, sDS, keyrow);
+        if (tid == 0) ASTAMP(69 + 8 * t);
+        uint32_t sv[32], dv[32];
+        if (w == 32) {
+          tmem_ld32_nowait(trow + uint32_t(TM_S + g0), sv);
+          tmem_ld32_nowait(trow + uint32_t(TM_DP + g0), dv);
+        } else if (w == 16) {
+          tmem_ld16_nowait(trow + uint32_t(TM_S + g0), sv);
+          tmem_ld16_nowait(trow + uint32_t(TM_DP + g0), dv);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_ld);                            // S^T / dP^T are free for chunk t+1
+        if (tid == 0) ASTAMP(70 + 8 * t);
+        // the P/dS buffer and the staging block were last read by the MMAs committed two chunks ago
+        if (t >= 2) mbar_wait(bar_m2 + buf, ((t >> 1) - 1) & 1, 8);
+        tc_fence_after();
+        if (tid == 0) ASTAMP(71 + 8 * t);
+        if (w == 32) bwd_math<H16, 32>(sv, dv, trow, g0, buf, s_lse2, s_delta, c * 64, scale_log2, keyvalid, sDSblk, keyrow);
+        else if (w == 16) bwd_math<H16, 16>(sv, dv, trow, g0, buf, s_lse2, s_delta, c * 64, scale_log2, keyvalid, sDSblk, keyrow);
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
         mbar_arrive(bar_p);
-        if (c == NC - 1) {
+        if (tid == 0) ASTAMP(72 + 8 * t);
+        if (c == NCH - 1) {
           // ---- key tile j is complete: dV_j (half 0) / dK_j (half 1) -> 16-bit -> staging -> TMA store
-          mbar_wait(bar_m2, t & 1, 4);
+          mbar_wait(bar_m2 + buf, (t >> 1) & 1, 9);
           tc_fence_after();
           if (warp == 0 && elect_one()) tma_store_wait_read();  // earlier stores have finished reading sOut
           named_bar_sync(1, 256);
@@ -454,13 +535,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             tma_store_3d(&tmDQKV, sOut + 16384, (H + h) * DH, j * 128, b);      // dK_j
             tma_store_commit();
           }
+          if (tid == 0) ASTAMP(73 + 8 * t);
         }
       }
     }
-    // ---- dQ chunks (accumulated over all key tiles): half c handles chunk c
+    // ---- dQ tiles (accumulated over all key tiles; every MMA is complete: the last bar_m2 wait above covered them)
+    const int NQT = (NCH + 1) >> 1;
     if (warp == 0 && elect_one()) tma_store_wait_read();
     named_bar_sync(1, 256);
-    if (half < NC) {
+    if (half < NQT) {
       uint8_t* dst = sOut + half * 16384;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -482,10 +565,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     fence_proxy_async();
     named_bar_sync(1, 256);
     if (warp == 0 && elect_one()) {
-      for (int c = 0; c < NC; ++c) tma_store_3d(&tmDQKV, sOut + c * 16384, h * DH, c * 128, b);
+      for (int qt = 0; qt < NQT; ++qt) tma_store_3d(&tmDQKV, sOut + qt * 16384, h * DH, qt * 128, b);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();   // shared memory must outlive the reads; the writes themselves complete asynchronously
     }
+    if (tid == 0) ASTAMP(65);
   }
   tc_fence_before();
   __syncthreads();
@@ -547,7 +631,8 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
     configured = 128 * 128 + 2 * 256 * 128 + 64 + 1024;
   }
   dim3 grid((N + 127) / 128, H, B);
-  kfn<<<grid, FWD_THREADS, smem, st>>>(tmQ, tmKV, tmO, lse, N, H, KP, scale, scale * LOG2E);
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, lse, N, H, KP, scale, scale * LOG2E,
+                       2 * num_sms()));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -562,8 +647,8 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
   if ((rc = make_tmap_3d(&tmDO, dout, H * DH, N, B, QP, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, QP, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmDQKV, dqkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
-  const int smem = 4 * QP * 128 + 65536 + 2048 + 64 + 1024;
-  const int smem_max = 4 * 256 * 128 + 65536 + 2048 + 64 + 1024;
+  const int smem = 4 * QP * 128 + 98304 + 2048 + 128 + 1024;
+  const int smem_max = 4 * 240 * 128 + 98304 + 2048 + 128 + 1024;
   auto kfn = attn_bwd_tc_kernel<H16>;
   static bool configured = false;
   if (!configured) {
@@ -571,10 +656,15 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
     configured = true;
   }
   dim3 grid(H, B);
-  kfn<<<grid, BWD_THREADS, smem, st>>>(tmQKV, tmDO, tmO, tmDQKV, lse, delta, N, H, QP, scale, scale * LOG2E);
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(BWD_THREADS), (size_t)smem, st, tmQKV, tmDO, tmO, tmDQKV, lse, delta, N, H, QP, scale,
+                       scale * LOG2E, num_sms()));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
+
+#ifdef VITK_GEMM_KNOBS
+extern "C" int vitk_debug_read_attn(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_attn_dbg, sizeof(g_attn_dbg)); }
+#endif
 
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {
   return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, st)

@@ -397,6 +397,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  // everything above is independent of the previous kernel's output: under programmatic dependent launch it overlaps that
+  // kernel's tail.  From here on global memory is touched: wait for the previous grid, and let the next one start launching.
+  pdl_trigger();
+  pdl_wait();
   if (p.colsum != nullptr) {  // 16 k-rows x 128 B of ones (B operand of the column-sum MMA) in the tail of the bias region
     const uint32_t one2 = (p.idesc & (1u << 7)) ? 0x3f803f80u : 0x3c003c00u;  // bf16 / fp16 1.0 pairs
     for (int i = threadIdx.x; i < 2048 / 4; i += GEMM_THREADS) reinterpret_cast<uint32_t*>(sBias + ONES_OFFSET)[i] = one2;
@@ -794,7 +798,7 @@ int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  kfn<<<grid, GEMM_THREADS, SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+  VITK_CUDA(launch_pdl(kfn, dim3(grid), dim3(GEMM_THREADS), SMEM, st, tm[0], tm[1], tm[2], tm[3], tm[4], p));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
                   __nv_bfloat16* __restrict__ y, int y_fp16, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
                   int dim, float eps) {
   constexpr int RPW = 32 / LPR;  // rows per warp
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, gl = lane % LPR;
   const int nvec = dim >> 2;
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(192, 5)
   constexpr int DIM = V * 4;
   __shared__ float2 part[2][R][SLOTS][GPR];
   __shared__ float4 fin[3][SLOTS][V];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int slot = tid / V, cv = tid - slot * V;
   const int grp = cv / G, gl = cv % G;
@@ -339,8 +343,9 @@ extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const LnCfg cfg = ln_config(dim);
   const int rpb = LN_WARPS * (32 / cfg.lpr);
-  LN_DISPATCH((ln_fwd_kernel<L_, C_><<<ln_grid(rows, rpb, 8), LN_WARPS * 32, 0, st>>>(
-      x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, rows, dim, eps)));
+  LN_DISPATCH(VITK_CUDA(launch_pdl(ln_fwd_kernel<L_, C_>, dim3(ln_grid(rows, rpb, 8)), dim3(LN_WARPS * 32), 0, st, x, gamma, beta,
+                                   reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, (long long)rows, dim,
+                                   eps)));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -365,8 +370,8 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
     long long blocks = (rows + batch - 1) / batch;                                                                         \
     const long long cap = (long long)num_sms() * 5;                                                                        \
     if (blocks > cap) blocks = cap;                                                                                        \
-    ln_bwd_cols_kernel<V_, R_><<<(unsigned)blocks, 192, 0, st>>>(dyp, f_dy, x, mean, rstd, gamma, dres, dx, dx16p, f_dx, dgamma, \
-                                                                 dbeta, dcolsum, grad_unscale, rows);                    \
+    VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, gamma,   \
+                         dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, (long long)rows));                  \
     VITK_LAUNCH_CHECK();                                                                                                   \
     return VITK_OK;                                                                                                        \
   }

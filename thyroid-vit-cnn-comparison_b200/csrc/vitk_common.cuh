@@ -54,8 +54,35 @@ inline int num_sms() {
   return sms;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Kernels launched through launch_pdl() may begin (prologue: barrier init, TMEM allocation, descriptor prefetch) while the
+// previous kernel of the stream is still draining; they call pdl_wait() before touching any global memory, which blocks
+// until the previous grid has completed and its writes are visible.  pdl_trigger() lets the NEXT kernel start launching.
+// Inside a captured CUDA graph these become programmatic dependency edges.  VITK_PDL=0 falls back to plain launches.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
