@@ -242,7 +242,8 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __re
     for (int c = lane; c < C; c += 32) atomicAdd(dbh + c, dl[c]);
 }
 
-// dW_h[c, i] += sum_b dl_h[b, c] * (xhat_h[b, i] * gamma[i] + beta[i]); one thread per (h, c, i), loop over b
+// dW_h[c, i] += sum_b dl_h[b, c] * (xhat_h[b, i] * gamma[i] + beta[i]); one thread per (h, c, i) and batch slab
+// (blockIdx.y): the batch loop is split over 16-sample slabs so the kernel is not one long dependent-load chain
 __global__ void head_wgrad_kernel(const float* __restrict__ dl0, const float* __restrict__ dl1, const float* __restrict__ xhat,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dW0,
                                   float* __restrict__ dW1, int B, int dim, int C, int n_heads) {
@@ -255,9 +256,11 @@ __global__ void head_wgrad_kernel(const float* __restrict__ dl0, const float* __
     const float* xh = xhat + (long long)hd * B * dim;
     const float gm = gamma[i], bt = beta[i];
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += dl[(long long)b * C + c] * (xh[(long long)b * dim + i] * gm + bt);
+    const int b0 = blockIdx.y * 16, b1 = min(B, b0 + 16);
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) acc += __ldg(dl + (long long)b * C + c) * (__ldg(xh + (long long)b * dim + i) * gm + bt);
     float* dW = hd == 0 ? dW0 : dW1;
-    dW[(long long)c * dim + i] += acc;
+    atomicAdd(dW + (long long)c * dim + i, acc);
   }
 }
 
@@ -437,8 +440,8 @@ extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const
                                                    db1, dcolsum, loss_scale, B, T, dim, C, n_heads);
   VITK_LAUNCH_CHECK();
   const long long total = (long long)n_heads * C * dim;
-  head_wgrad_kernel<<<capped_grid(total, 128, 4), 128, 0, st>>>(dlogits0, dlogits1, xhat, gamma, beta, dW0, dW1, B, dim, C,
-                                                               n_heads);
+  head_wgrad_kernel<<<dim3(capped_grid(total, 128, 4), (B + 15) / 16), 128, 0, st>>>(dlogits0, dlogits1, xhat, gamma, beta, dW0, dW1,
+                                                                                    B, dim, C, n_heads);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

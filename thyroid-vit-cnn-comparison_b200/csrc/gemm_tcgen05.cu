@@ -188,6 +188,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t v;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
@@ -338,6 +351,20 @@ __device__ __forceinline__ void mul_pack(uint32_t (&h)[16], const float (&f)[32]
     h[4 * c + 1] = pack16(f[8 * c + 2] * a1.x, f[8 * c + 3] * a1.y, h16);
     h[4 * c + 2] = pack16(f[8 * c + 4] * a2.x, f[8 * c + 5] * a2.y, h16);
     h[4 * c + 3] = pack16(f[8 * c + 6] * a3.x, f[8 * c + 7] * a3.y, h16);
+  }
+}
+// 32 accumulators of one row -> *alpha + bias -> 16 packed 16-bit pairs
+__device__ __forceinline__ void bias_pack(uint32_t (&h)[16], const uint32_t (&v)[32], const float* __restrict__ sbias, float alpha,
+                                          bool h16) {
+  float4 b4[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) b4[c] = *reinterpret_cast<const float4*>(sbias + 4 * c);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float f0 = fmaf(__uint_as_float(v[4 * c + 0]), alpha, b4[c].x), f1 = fmaf(__uint_as_float(v[4 * c + 1]), alpha, b4[c].y);
+    const float f2 = fmaf(__uint_as_float(v[4 * c + 2]), alpha, b4[c].z), f3 = fmaf(__uint_as_float(v[4 * c + 3]), alpha, b4[c].w);
+    h[2 * c + 0] = h16 ? pack_f16(f0, f1) : pack_bf16(f0, f1);
+    h[2 * c + 1] = h16 ? pack_f16(f2, f3) : pack_bf16(f2, f3);
   }
 }
 // hd = gelu'(f), hg = gelu(f), packed 16-bit pairs
