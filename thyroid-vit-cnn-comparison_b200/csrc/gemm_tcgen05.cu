@@ -23,6 +23,7 @@
 // DeiT-tiny GEMMs (K = 192) are HBM-bound: what matters is bytes in flight (the ring) and coalescing;
 // ViT-B GEMMs (K = 768/3072) are tensor-bound: what matters is that the MMA warp never waits for the epilogue.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "vitk_common.cuh"
 
@@ -134,6 +135,56 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       }
     }
   }
+}
+
+// ---- CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA holds 128 accumulator rows and
+// stages its own A rows plus HALF of the B tile; the leader CTA issues the MMAs for both.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is counted on a barrier that may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives (once all earlier MMAs of this thread are complete) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // true in exactly one (converged) lane of the warp; lets ptxas issue the uniform-datapath TMA / MMA instructions
@@ -250,9 +301,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // Instruction descriptor for kind::f16: {bf16|fp16} x same -> fp32, M = 128, N = bn.  a/b_format: 0 = F16, 1 = BF16.
-inline uint32_t make_idesc(int bn, bool a_mn, bool b_mn, bool a_fp16, bool b_fp16) {
+inline uint32_t make_idesc(int bn, bool a_mn, bool b_mn, bool a_fp16, bool b_fp16, int m = BLOCK_M) {
   return (1u << 4) | (uint32_t(a_fp16 ? 0 : 1) << 7) | (uint32_t(b_fp16 ? 0 : 1) << 10) | (uint32_t(a_mn) << 15) |
-         (uint32_t(b_mn) << 16) | (uint32_t(bn >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+         (uint32_t(b_mn) << 16) | (uint32_t(bn >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
 constexpr int tmem_cols_for(int bn) {
@@ -380,15 +431,22 @@ __device__ __forceinline__ void gelu_pack(uint32_t (&hd)[16], uint32_t (&hg)[16]
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                         const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  constexpr int NCTA = CTA2 ? 2 : 1;
+  constexpr int BN_LOCAL = BN / NCTA;             // rows of the B tile this CTA stages
+  constexpr int TILE_M = BLOCK_M * NCTA;          // output rows per tile (per CTA pair in 2-CTA mode)
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr int B_BYTES = BN * BLOCK_K * 2;
+  constexpr int B_BYTES = BN_LOCAL * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int EPI_BYTES = EPI_WARPS * EPI_STAGE_FLOATS * 4;
+  static_assert(!CTA2 || !B_MN || BN_LOCAL % 64 == 0, "MN-major B halves must be whole 64-column boxes");
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const int unit_id = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // tile-walk position (per pair)
+  const int unit_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -418,12 +476,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], EPI_WARPS * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&aux_bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   // everything above is independent of the previous kernel's output: under programmatic dependent launch it overlaps that
   // kernel's tail.  From here on global memory is touched: wait for the previous grid, and let the next one start launching.
   pdl_trigger();
@@ -439,6 +500,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -450,8 +512,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   };
   auto tile_first = [&]() {
     TileIter t;
-    t.split = (int)blockIdx.x / tiles_mn;
-    const int r = (int)blockIdx.x - t.split * tiles_mn;
+    t.split = unit_id / tiles_mn;
+    const int r = unit_id - t.split * tiles_mn;
     t.mt = r / p.num_n_tiles;
     t.nt = r - t.mt * p.num_n_tiles;
     return t;
@@ -470,7 +532,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   };
   auto decode = [&](const TileIter& t, int& m0, int& n0, int& kb0, int& nk) {
-    m0 = t.mt * BLOCK_M;
+    m0 = t.mt * TILE_M + (int)cta_rank * BLOCK_M;   // this CTA's 128 rows of the tile
     n0 = t.nt * BN;
     kb0 = t.split * p.kblocks_per_split;
     const int kb1 = min(p.num_kblocks, kb0 + p.kblocks_per_split);
@@ -483,30 +545,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int s = 0;
       uint32_t ph = 0;
       TileIter ti = tile_first();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tile_next(ti)) {
+      for (int tile = unit_id; tile < total_tiles; tile += unit_stride, tile_next(ti)) {
         int m0, n0, kb0, nk;
         decode(ti, m0, n0, kb0, nk);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 1);
-          if (kb == 0) DBG_STAMP(0, (tile - (int)blockIdx.x) / (int)gridDim.x, 0);
-          const bool skip_a = KNOB(8) && tile != (int)blockIdx.x, skip_b = KNOB(4) && tile != (int)blockIdx.x;
-          mbar_expect_tx(&full_bar[s], (skip_a ? 0 : A_BYTES) + (skip_b ? 0 : B_BYTES));
+          if (kb == 0) DBG_STAMP(0, (tile - unit_id) / unit_stride, 0);
           const int kc = (kb0 + kb) * BLOCK_K;
           uint8_t* a_dst = sA + s * A_BYTES;
           uint8_t* b_dst = sB + s * B_BYTES;
-          if (skip_a) {
-          } else if (!A_MN) {
-            tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
-          } else {
+          if (!CTA2) {
+            const bool skip_a = KNOB(8) && tile != unit_id, skip_b = KNOB(4) && tile != unit_id;
+            mbar_expect_tx(&full_bar[s], (skip_a ? 0 : A_BYTES) + (skip_b ? 0 : B_BYTES));
+            if (skip_a) {
+            } else if (!A_MN) {
+              tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kc);
-          }
-          if (skip_b) {
-          } else if (!B_MN) {
-            tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0);
-          } else {
+              for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full_bar[s], m0 + 64 * i, kc);
+            }
+            if (skip_b) {
+            } else if (!B_MN) {
+              tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_dst + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kc);
+              for (int i = 0; i < BN / 64; ++i) tma_load_2d(b_dst + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, kc);
+            }
+          } else {
+            // both CTAs' loads are counted on the LEADER's full barrier (it expects the bytes of the whole pair)
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            const int nb0 = n0 + (int)cta_rank * BN_LOCAL;   // this CTA's half of the B tile
+            if (!A_MN) {
+              tma_load_2d_pair(a_dst, &tmA, bar, kc, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_pair(a_dst + i * 8192, &tmA, bar, m0 + 64 * i, kc);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(b_dst, &tmB, bar, kc, nb0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN_LOCAL / 64; ++i) tma_load_2d_pair(b_dst + i * 8192, &tmB, bar, nb0 + 64 * i, kc);
+            }
           }
           if (++s == STAGES) {
             s = 0;
@@ -516,8 +597,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one elected thread) =====================
-    if (elect_one()) {
+    // ===================== MMA issuer (one elected thread; in 2-CTA mode the leader CTA issues for the pair) ==========
+    if (elect_one() && cta_rank == 0) {
       const uint32_t idesc = p.idesc;
       constexpr uint32_t a_adv = A_MN ? (2048u >> 4) : (32u >> 4);  // desc.lo step per UMMA_K
       constexpr uint32_t b_adv = B_MN ? (2048u >> 4) : (32u >> 4);
@@ -526,7 +607,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       int s = 0;
       uint32_t ph = 0, tcount = 0;
       TileIter ti = tile_first();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount, tile_next(ti)) {
+      for (int tile = unit_id; tile < total_tiles; tile += unit_stride, ++tcount, tile_next(ti)) {
         int m0, n0, kb0, nk;
         decode(ti, m0, n0, kb0, nk);
         const uint32_t acc = tcount & 1;
@@ -545,15 +626,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const uint64_t bdesc = bdesc0 + uint64_t(s * (B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            if (!KNOB(32)) umma_f16(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (!KNOB(32)) {
+              if (CTA2) umma_f16_pair(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(d_tmem, adesc + uint64_t(k * a_adv), bdesc + uint64_t(k * b_adv), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           if (do_colsum) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16(d_tmem + BN, adesc + uint64_t(k * a_adv), ones_desc, p.idesc_ones, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if (CTA2) umma_f16_pair(d_tmem + BN, adesc + uint64_t(k * a_adv), ones_desc, p.idesc_ones, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16(d_tmem + BN, adesc + uint64_t(k * a_adv), ones_desc, p.idesc_ones, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[s]);
+          if (CTA2) umma_commit_pair(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
           if (kb == nk - 1) {
-            umma_commit(&tfull_bar[acc]);
+            if (CTA2) umma_commit_pair(&tfull_bar[acc]);
+            else umma_commit(&tfull_bar[acc]);
             DBG_STAMP(1, tcount, 3);
           }
           if (++s == STAGES) {
@@ -573,7 +661,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int rsub = lane >> 2;  // row (mod 8) this lane handles when reading the staged half chunk back
     uint32_t tcount = 0, aux_phase = 0, sbuf_idx = 0;
     TileIter ti = tile_first();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount, tile_next(ti)) {
+    for (int tile = unit_id; tile < total_tiles; tile += unit_stride, ++tcount, tile_next(ti)) {
       int m0, n0, kb0, nk;
       decode(ti, m0, n0, kb0, nk);
       const uint32_t acc = tcount & 1;
@@ -715,7 +803,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           if (row_base + lane < p.M) atomicAdd(p.colsum + row_base + lane, v * alpha);
         }
         tcgen05_fence_before();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+          else mbar_arrive(&tempty_bar[acc]);
+        }
         if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
         continue;
       }
@@ -766,7 +857,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator stage
       tcgen05_fence_before();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
     }
     if (elect_one()) tma_store_wait_all();  // outstanding TMA stores must complete before the CTA (and its smem) goes away
@@ -774,7 +868,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if (CTA2) cluster_sync_all();  // the peer may still be reading this CTA's B half / arriving on its barriers
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -814,33 +912,50 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
   return VITK_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2>
 int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 + MAX_BIAS_SMEM * 4 +
-                       (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024;
+  constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + (BN / (CTA2 ? 2 : 1)) * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 +
+                       MAX_BIAS_SMEM * 4 + (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   static bool configured = false;
-  auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN, CTA2>;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  VITK_CUDA(launch_pdl(kfn, dim3(grid), dim3(GEMM_THREADS), SMEM, st, tm[0], tm[1], tm[2], tm[3], tm[4], p));
+  VITK_CUDA(launch_pdl_cluster(kfn, dim3(grid), dim3(GEMM_THREADS), SMEM, st, CTA2 ? 2 : 1, tm[0], tm[1], tm[2], tm[3], tm[4], p));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch_gemm(int bn, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+int dispatch_gemm(int bn, bool cta2, const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+  if (cta2) {  // CTA pairs: 256 x BN tiles, half of B per CTA -> deeper rings in the same shared memory
+    switch (bn) {
+      case 128: return launch_gemm<128, 6, A_MN, B_MN, true>(tm, p, grid, st);
+      case 256: return launch_gemm<256, 5, A_MN, B_MN, true>(tm, p, grid, st);
+      default: break;
+    }
+    set_error("2-CTA mode supports BLOCK_N 128 / 256 (got %d)", bn);
+    return VITK_ERR_UNSUPPORTED;
+  }
   switch (bn) {
-    case 64:  return launch_gemm<64, 6, A_MN, B_MN>(tm, p, grid, st);
-    case 128: return launch_gemm<128, 5, A_MN, B_MN>(tm, p, grid, st);
-    case 192: return launch_gemm<192, 4, A_MN, B_MN>(tm, p, grid, st);
-    case 256: return launch_gemm<256, 3, A_MN, B_MN>(tm, p, grid, st);
+    case 64:  return launch_gemm<64, 6, A_MN, B_MN, false>(tm, p, grid, st);
+    case 128: return launch_gemm<128, 5, A_MN, B_MN, false>(tm, p, grid, st);
+    case 192: return launch_gemm<192, 4, A_MN, B_MN, false>(tm, p, grid, st);
+    case 256: return launch_gemm<256, 3, A_MN, B_MN, false>(tm, p, grid, st);
     default:
       set_error("unsupported BLOCK_N %d", bn);
       return VITK_ERR_UNSUPPORTED;
   }
+}
+
+bool pair_mode_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VITK_GEMM_2CTA");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 // Pick the N tile: the widest of {256,192,128,64} that tiles N with the least padding.
@@ -915,6 +1030,12 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   const int kpb = (num_kblocks + a->split_k - 1) / a->split_k;
   const int splits = (num_kblocks + kpb - 1) / kpb;
 
+  // CTA pairs (tcgen05 cta_group::2): each SM reads its A tile and only half of the B tile from shared memory per MMA
+  // -- 64 instead of 96 B/clk of operand reads, and a third less TMA write traffic, through the 128 B/clk shared memory.  It
+  // pays when the tile is MMA-bound (long K); short-K tiles are epilogue-bound and only suffer the cross-CTA handshakes.
+  const bool long_k = kpb >= 24 || (kpb >= 8 && !out_fp32);
+  const bool cta2 = pair_mode_enabled() && (bn == 256 || bn == 128) && a->M >= 256 && (num_sms() % 2 == 0) && long_k;
+  const int tile_m = cta2 ? 2 * BLOCK_M : BLOCK_M;
   GemmParams p{};
 #ifdef VITK_GEMM_KNOBS
   {
@@ -925,11 +1046,11 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.num_kblocks = num_kblocks;
   p.kblocks_per_split = kpb;
-  p.num_m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_tiles = (a->M + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + bn - 1) / bn;
   p.num_splits = splits;
   p.epilogue = a->epilogue; p.out_dtype = a->out_dtype; p.aux_dtype = a->aux_dtype;
-  p.idesc = make_idesc(bn, a->a_mn_major != 0, a->b_mn_major != 0, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16);
+  p.idesc = make_idesc(bn, a->a_mn_major != 0, a->b_mn_major != 0, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16, tile_m);
   p.alpha = a->alpha; p.alpha_dev = a->alpha_dev;
   p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr;
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
@@ -937,7 +1058,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.colsum = a->colsum_out;
   p.acc_stride = bn + (a->colsum_out != nullptr ? 16 : 0);
   p.tmem_cols = 2 * p.acc_stride <= 32 ? 32 : 2 * p.acc_stride <= 64 ? 64 : 2 * p.acc_stride <= 128 ? 128 : 2 * p.acc_stride <= 256 ? 256 : 512;
-  p.idesc_ones = make_idesc(16, a->a_mn_major != 0, true, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16);
+  p.idesc_ones = make_idesc(16, a->a_mn_major != 0, true, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16, tile_m);
   p.rows_per_img = a->rows_per_img; p.tokens_per_img = a->tokens_per_img; p.prefix = a->prefix; p.pos = a->pos;
 
   CUtensorMap tm[5];  // A, B, out, out2, aux
@@ -946,7 +1067,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   if (!a->a_mn_major) rc = make_tmap_2d(&tm[0], a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BLOCK_K, BLOCK_M, ah);
   else                rc = make_tmap_2d(&tm[0], a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, BLOCK_K, ah);
   if (rc != VITK_OK) return rc;
-  if (!a->b_mn_major) rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)bn, bh);
+  if (!a->b_mn_major) rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, BLOCK_K, (uint32_t)(cta2 ? bn / 2 : bn), bh);
   else                rc = make_tmap_2d(&tm[1], a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, BLOCK_K, bh);
   if (rc != VITK_OK) return rc;
   // STORE / GELU / DGELU epilogues run on 2 KB TMA units (32x32 16-bit or 32x16 fp32 boxes, 64-byte rows, SWIZZLE_64B);
@@ -984,17 +1105,19 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   }
 
   const long long total_tiles = (long long)p.num_m_tiles * p.num_n_tiles * splits;
-  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  const int max_units = cta2 ? num_sms() / 2 : num_sms();                 // CTA pairs, or CTAs
+  const int units = (int)(total_tiles < max_units ? total_tiles : max_units);
+  const int grid = cta2 ? 2 * units : units;
   {
     const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
-    p.step_split = grid / tiles_mn;
-    const int r = grid - p.step_split * tiles_mn;
+    p.step_split = units / tiles_mn;
+    const int r = units - p.step_split * tiles_mn;
     p.step_mt = r / p.num_n_tiles;
     p.step_nt = r - p.step_mt * p.num_n_tiles;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, tm, p, grid, st);
-  if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, tm, p, grid, st);
-  if (a->a_mn_major && a->b_mn_major) return dispatch_gemm<true, true>(bn, tm, p, grid, st);
-  return dispatch_gemm<true, false>(bn, tm, p, grid, st);
+  if (!a->a_mn_major && !a->b_mn_major) return dispatch_gemm<false, false>(bn, cta2, tm, p, grid, st);
+  if (!a->a_mn_major && a->b_mn_major) return dispatch_gemm<false, true>(bn, cta2, tm, p, grid, st);
+  if (a->a_mn_major && a->b_mn_major) return dispatch_gemm<true, true>(bn, cta2, tm, p, grid, st);
+  return dispatch_gemm<true, false>(bn, cta2, tm, p, grid, st);
 }
