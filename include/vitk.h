@@ -75,7 +75,7 @@ typedef struct {
   int32_t a_mn_major; /* 0: A stored [M,K]; 1: A stored [K,M] */
   int32_t b_mn_major; /* 0: B stored [N,K]; 1: B stored [K,N] */
   int32_t M, N, K;
-  int32_t split_k;    /* >=1; >1 requires VITK_EPI_ATOMIC_ADD */
+  int32_t split_k;    /* >=1 (>1 requires VITK_EPI_ATOMIC_ADD), or 0: chosen by the library */
   int32_t epilogue;   /* vitk_epilogue */
   int32_t out_dtype;  /* vitk_dtype of out (and out2) */
   int32_t a_dtype;    /* VITK_BF16 or VITK_FP16: element type of A (both are 16-bit tensor-core operands and */

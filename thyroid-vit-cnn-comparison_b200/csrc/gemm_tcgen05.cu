@@ -74,6 +74,7 @@ struct GemmParams {
   int step_split, step_mt, step_nt;  // mixed-radix digits of the grid size over (split, m tile, n tile)
   float* colsum;     // optional [M]: += alpha * sum_k A[m, k], from one extra N=16 MMA per k-step against a tile of ones
   int acc_stride;    // TMEM columns per accumulator stage (BN, or BN + 16 with colsum)
+  int nacc;          // accumulator stages: 2 (MMAs of tile i+1 overlap epilogue i), or 1 when 2 x acc_stride > 512 columns
   int tmem_cols;     // TMEM allocation (power of two >= 2 * acc_stride)
   uint32_t idesc_ones;
   int epilogue, out_dtype, aux_dtype;
@@ -610,9 +611,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       for (int tile = unit_id; tile < total_tiles; tile += unit_stride, ++tcount, tile_next(ti)) {
         int m0, n0, kb0, nk;
         decode(ti, m0, n0, kb0, nk);
-        const uint32_t acc = tcount & 1;
+        const uint32_t acc = p.nacc == 2 ? (tcount & 1) : 0u;
+        const uint32_t acc_ph = p.nacc == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
         DBG_STAMP(1, tcount, 0);
-        mbar_wait(&tempty_bar[acc], ((tcount >> 1) & 1) ^ 1, 4);  // epilogue has drained this accumulator stage
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1, 4);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         DBG_STAMP(1, tcount, 1);
         const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
@@ -664,7 +666,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     for (int tile = unit_id; tile < total_tiles; tile += unit_stride, ++tcount, tile_next(ti)) {
       int m0, n0, kb0, nk;
       decode(ti, m0, n0, kb0, nk);
-      const uint32_t acc = tcount & 1;
+      const uint32_t acc = p.nacc == 2 ? (tcount & 1) : 0u;
+      const uint32_t acc_ph = p.nacc == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
       const uint32_t t_addr = tmem_base + acc * p.acc_stride + (uint32_t(quad * 32) << 16);
       const int row_base = m0 + quad * 32;
       if (p.tma_epi) {
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         bool more = c0 < BN && n0 + c0 < p.N;
         if (has_aux && more) issue_aux(c0);
         if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 0);
-        mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
+        mbar_wait(&tfull_bar[acc], acc_ph, 3);
         tcgen05_fence_after();
         if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 1);
         int ucount = -1;
@@ -811,7 +814,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         continue;
       }
       if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 0);
-      mbar_wait(&tfull_bar[acc], (tcount >> 1) & 1, 3);
+      mbar_wait(&tfull_bar[acc], acc_ph, 3);
       tcgen05_fence_after();
       if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 1);
 #pragma unroll 1
@@ -964,7 +967,7 @@ int pick_bn(int N, bool with_colsum) {
   int best = 64;
   long best_cost = -1;
   for (int c : cands) {
-    if (with_colsum && c > 240) continue;  // two accumulator stages of BN + 16 columns must fit the 512 TMEM columns
+    (void)with_colsum;  // BN = 256 with the 16 column-sum columns runs on a single accumulator stage (272 of 512 columns)
     const long tiles = (N + c - 1) / c;
     const long cost = tiles * c;  // padded width; ties -> wider tile (listed first)
     if (best_cost < 0 || cost < best_cost) {
@@ -998,8 +1001,8 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   VITK_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "vitk_gemm: lda/ldb must be multiples of 8 (16-byte TMA pitch)");
   VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
                  "vitk_gemm: operands must be 16-byte aligned");
-  VITK_CHECK_ARG(a->split_k >= 1, "vitk_gemm: split_k must be >= 1");
-  VITK_CHECK_ARG(a->split_k == 1 || a->epilogue == VITK_EPI_ATOMIC_ADD, "vitk_gemm: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
+  VITK_CHECK_ARG(a->split_k >= 0, "vitk_gemm: split_k must be >= 1 (or 0: chosen by the library)");
+  VITK_CHECK_ARG(a->split_k <= 1 || a->epilogue == VITK_EPI_ATOMIC_ADD, "vitk_gemm: split_k > 1 needs VITK_EPI_ATOMIC_ADD");
   VITK_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= VITK_EPI_TOKENS, "vitk_gemm: bad epilogue %d", a->epilogue);
   VITK_CHECK_ARG(a->out_dtype >= VITK_BF16 && a->out_dtype <= VITK_FP16, "vitk_gemm: bad out_dtype %d", a->out_dtype);
   VITK_CHECK_ARG((a->a_dtype == VITK_BF16 || a->a_dtype == VITK_FP16) && (a->b_dtype == VITK_BF16 || a->b_dtype == VITK_FP16),
@@ -1027,14 +1030,30 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
 
   const int bn = pick_bn(a->N, a->colsum_out != nullptr);
   const int num_kblocks = (a->K + BLOCK_K - 1) / BLOCK_K;
-  const int kpb = (num_kblocks + a->split_k - 1) / a->split_k;
+  int split_k = a->split_k;
+  bool pair_ok = pair_mode_enabled() && (bn == 256 || bn == 128) && a->M >= 256 && (num_sms() % 2 == 0);
+  if (split_k == 0) {
+    // split_k = 0: the library picks the K split of an accumulate GEMM -- about two work units per CTA (or CTA pair), at least
+    // 8 k-blocks each, so that every SM is busy and the epilogue of one unit overlaps the MMAs of the next
+    if (a->epilogue != VITK_EPI_ATOMIC_ADD) {
+      split_k = 1;
+    } else {
+      const bool pair = pair_ok && num_kblocks >= 48;
+      const int tile_rows = pair ? 2 * BLOCK_M : BLOCK_M;
+      const long tiles = (long)((a->M + tile_rows - 1) / tile_rows) * ((a->N + bn - 1) / bn);
+      const long units = pair ? num_sms() / 2 : num_sms();
+      long want = (2 * units + tiles - 1) / tiles;
+      const long cap = num_kblocks / 8 > 0 ? num_kblocks / 8 : 1;
+      split_k = (int)(want < 1 ? 1 : want > cap ? cap : want);
+    }
+  }
+  const int kpb = (num_kblocks + split_k - 1) / split_k;
   const int splits = (num_kblocks + kpb - 1) / kpb;
-
   // CTA pairs (tcgen05 cta_group::2): each SM reads its A tile and only half of the B tile from shared memory per MMA
   // -- 64 instead of 96 B/clk of operand reads, and a third less TMA write traffic, through the 128 B/clk shared memory.  It
   // pays when the tile is MMA-bound (long K); short-K tiles are epilogue-bound and only suffer the cross-CTA handshakes.
   const bool long_k = kpb >= 24 || (kpb >= 8 && !out_fp32);
-  const bool cta2 = pair_mode_enabled() && (bn == 256 || bn == 128) && a->M >= 256 && (num_sms() % 2 == 0) && long_k;
+  const bool cta2 = pair_ok && long_k;
   const int tile_m = cta2 ? 2 * BLOCK_M : BLOCK_M;
   GemmParams p{};
 #ifdef VITK_GEMM_KNOBS
@@ -1057,7 +1076,11 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.aux = a->aux; p.ldaux = a->ldaux;
   p.colsum = a->colsum_out;
   p.acc_stride = bn + (a->colsum_out != nullptr ? 16 : 0);
-  p.tmem_cols = 2 * p.acc_stride <= 32 ? 32 : 2 * p.acc_stride <= 64 ? 64 : 2 * p.acc_stride <= 128 ? 128 : 2 * p.acc_stride <= 256 ? 256 : 512;
+  p.nacc = 2 * p.acc_stride <= 512 ? 2 : 1;
+  {
+    const int need = p.nacc * p.acc_stride;
+    p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  }
   p.idesc_ones = make_idesc(16, a->a_mn_major != 0, true, a->a_dtype == VITK_FP16, a->b_dtype == VITK_FP16, tile_m);
   p.rows_per_img = a->rows_per_img; p.tokens_per_img = a->tokens_per_img; p.prefix = a->prefix; p.pos = a->pos;
 

@@ -229,7 +229,7 @@ class VitEngine:
         n_out = gw.shape[0]
         k_in = gw.numel() // n_out
         ops.gemm(dy, x, n_out, k_in, rows, a_mn=True, b_mn=True, out=gw, epilogue=_lib.EPI_ATOMIC_ADD,
-                 split_k=self._split_k(n_out, k_in, rows, bias_name is not None), alpha_dev=self.grad_unscale,
+                 split_k=0, alpha_dev=self.grad_unscale,       # 0: the library picks the K split (tile shape / CTA pairs)
                  colsum_out=self.g(bias_name) if bias_name is not None else None)
 
     # ------------------------------------------------------------------ forward
