@@ -251,7 +251,7 @@ def run_ours(args):
         for p in teacher.parameters():
             p.requires_grad = False
     reducer = parallel.BucketedAllReduce(bucket_mb=args.bucket_mb) if world > 1 else None
-    use_graph = not args.no_graph and (world == 1 or args.dp_graph)
+    use_graph = not args.no_graph and (world == 1 or not args.dp_eager)
     step = training.TrainStep(model, opt, args.batch, mode=args.mode, teacher=teacher, reducer=reducer, use_graph=use_graph)
 
     g = torch.Generator().manual_seed(1234 + rank)
@@ -405,7 +405,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--dp-graph", action="store_true", help="N > 1: capture the step (NCCL all-reduces included) in a CUDA graph")
+    ap.add_argument("--dp-graph", action="store_true", help="(default) N > 1: the step, NCCL all-reduces included, is one CUDA graph")
+    ap.add_argument("--dp-eager", action="store_true", help="N > 1: launch the step eagerly instead of replaying a captured graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--by-shape", action="store_true", help="split the GEMM rows of the kernel profile by shape")
     args = ap.parse_args()
