@@ -135,6 +135,25 @@ def workload_config(args, cpu: bool = False):
             "l2": "no flush needed: the step's working set (activations > 3 GB) is far larger than the 126 MB L2"}
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, profiles/): label of the
+# live per-kernel profile -> case name of tools/kbench.py the capture was taken with (DeiT-tiny shapes, batch 256)
+NCU_CASES = {
+    "attention_bwd": "attn_bwd", "attention_fwd": "attn_fwd", "layernorm_bwd": "ln_bwd", "layernorm_fwd": "ln_fwd",
+    "gemm_tcgen05[fwd] 50688x768x192 epi1": "gemm_gelu", "gemm_tcgen05[fwd] 50688x576x192 epi0": "gemm_qkv",
+    "gemm_tcgen05[fwd] 50688x192x192 epi0": "gemm_proj", "gemm_tcgen05[dgrad] 50688x768x192 epi2": "dgrad_dgelu",
+    "gemm_tcgen05[wgrad] 768x192x50688 epi3": "wgrad_fc1",
+}
+
+
+def ncu_traffic(model: str, label: str):
+    f = ROOT / "profiles" / "r01_ncu_traffic_deit_tiny.json"
+    case = NCU_CASES.get(label)
+    if model != "deit_tiny" or case is None or not f.exists():
+        return None, None
+    ent = json.loads(f.read_text()).get(case)
+    return (ent["dram_bytes"], f"profiles/{f.name}:{case}") if ent else (None, None)
+
+
 # ------------------------------------------------------------------------------------------- per-kernel live profile
 class KernelProfile:
     """Brackets every libvitk launch group of an EAGER step with CUDA events on the launching stream and aggregates
@@ -326,11 +345,18 @@ def run_ours(args):
         torch.cuda.synchronize()
     if rank == 0:
         saved_graph, step.use_graph = step.use_graph, False
-        with KernelProfile(ops, by_shape=args.by_shape) as prof:
+        with KernelProfile(ops, by_shape=True) as prof:
             for _ in range(nprof):
                 step.run()
-            tab = prof.table()
+            tab_shape = prof.table()
         step.use_graph = saved_graph
+        # per-class table (GEMMs of all shapes folded into fwd / dgrad / wgrad) unless --by-shape asks for the detail
+        tab = {}
+        for label, v in tab_shape.items():
+            key = label if args.by_shape else label.split(" ")[0]
+            d = tab.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            for k2 in d:
+                d[k2] += v[k2]
         total_ms = sum(v["ms"] for v in tab.values())
         kernels = {}
         ridge = pk["bf16_tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
@@ -344,15 +370,19 @@ def run_ours(args):
             ent["frac_hbm_peak"] = ent["gbs"] / pk["hbm_gbs"]
             ent["intensity_flop_per_byte"] = (v["flops"] / v["bytes"]) if v["bytes"] else None
             kernels[label] = ent
-        top_label = next(iter(kernels))
-        top = kernels[top_label]
-        tv_ = tab[top_label]
+        # the roofline object describes the single dominant kernel (one shape), not a class of launches
+        top_label, tv_ = max(tab_shape.items(), key=lambda kv: kv[1]["ms"])
+        sec_ = tv_["ms"] / 1e3
+        top = {"share": tv_["ms"] / total_ms, "gbs": tv_["bytes"] / sec_ / 1e9,
+               "tflops": tv_["flops"] / sec_ / 1e12 if tv_["flops"] else 0.0,
+               "intensity_flop_per_byte": (tv_["flops"] / tv_["bytes"]) if tv_["bytes"] else None}
         if top.get("intensity_flop_per_byte") and top["intensity_flop_per_byte"] > ridge:
             roof = {"kernel": top_label, "bound": "tensor", "achieved": top["tflops"], "peak": pk["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": top["tflops"] / pk["bf16_tflops_sustained"], "traffic": None}
         else:
             roof = {"kernel": top_label, "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": top["gbs"] / pk["hbm_gbs"], "traffic": None}
+        roof["traffic"], roof["traffic_source"] = ncu_traffic(args.model, top_label)
         roof["peak_source"] = f"{pk_src} (MEASURED_PEAKS.json sustained figures: the kernel is timed inside a long step)"
         roof["avg_launch_ms"] = tv_["ms"] / tv_["launches"]
         roof["algorithmic_per_launch"] = {"flops": tv_["flops"] / tv_["launches"], "bytes": tv_["bytes"] / tv_["launches"]}
