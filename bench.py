@@ -265,6 +265,7 @@ def run_ours(args):
     teacher = None
     if args.mode == "distill":
         import torchvision
+        torch.backends.cudnn.benchmark = True   # the teacher is ~170 small convolutions: let cuDNN pick per-shape algorithms
         teacher = torchvision.models.densenet169(weights=None, num_classes=2).to(dev).eval().to(torch.bfloat16)
         teacher = teacher.to(memory_format=torch.channels_last)
         for p in teacher.parameters():

@@ -375,6 +375,7 @@ class TrainStep:
         self.graphs = [None, None]
         self.use_graph = use_graph
         self._copy_stream = torch.cuda.Stream(device=dev)
+        self._teacher_stream = torch.cuda.Stream(device=dev)
         self._copied = [torch.cuda.Event() for _ in range(2)]     # slot filled (recorded on the copy stream)
         self._consumed = [torch.cuda.Event() for _ in range(2)]   # slot no longer read (recorded on the compute stream)
         self._pending_copy = False
@@ -396,7 +397,12 @@ class TrainStep:
         model = self.model
         teacher_logits = None
         if self.mode == "distill":
-            with torch.no_grad():
+            # the frozen teacher (cuDNN, reference: lightning_modules.py:943-947) only feeds the loss: it runs on a side stream,
+            # concurrently with the student's forward (a parallel branch of the captured graph), and is joined before the loss
+            cur = torch.cuda.current_stream()
+            side = self._teacher_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), torch.no_grad():
                 x = self.images
                 if self.teacher_dtype is not None and self.teacher_dtype != torch.float32:
                     x = x.to(self.teacher_dtype).contiguous(memory_format=torch.channels_last)
@@ -404,6 +410,8 @@ class TrainStep:
         eng.zero_grad()
         l0, l1 = eng.forward(self.images, train=True)
         eng.generation += 1
+        if self.mode == "distill":
+            torch.cuda.current_stream().wait_stream(self._teacher_stream)
         if self.mode == "ce":
             if l1 is not None:
                 out, d0, d1 = ops.loss_fwd_bwd(l0, l1, None, self.labels, mode=0, w_cls=0.5, w_dist=0.5,
