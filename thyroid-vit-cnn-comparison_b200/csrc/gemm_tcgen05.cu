@@ -1031,18 +1031,18 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   const int bn = pick_bn(a->N, a->colsum_out != nullptr);
   const int num_kblocks = (a->K + BLOCK_K - 1) / BLOCK_K;
   int split_k = a->split_k;
-  bool pair_ok = pair_mode_enabled() && (bn == 256 || bn == 128) && a->M >= 256 && (num_sms() % 2 == 0);
+  bool pair_ok = pair_mode_enabled() && (bn == 256 || bn == 128) && a->M > BLOCK_M && (num_sms() % 2 == 0);
   if (split_k == 0) {
     // split_k = 0: the library picks the K split of an accumulate GEMM -- about two work units per CTA (or CTA pair), at least
     // 8 k-blocks each, so that every SM is busy and the epilogue of one unit overlaps the MMAs of the next
     if (a->epilogue != VITK_EPI_ATOMIC_ADD) {
       split_k = 1;
     } else {
-      const bool pair = pair_ok && num_kblocks >= 48;
+      const bool pair = pair_ok && num_kblocks >= 32;
       const int tile_rows = pair ? 2 * BLOCK_M : BLOCK_M;
       const long tiles = (long)((a->M + tile_rows - 1) / tile_rows) * ((a->N + bn - 1) / bn);
       const long units = pair ? num_sms() / 2 : num_sms();
-      long want = (2 * units + tiles - 1) / tiles;
+      long want = (2 * units) / tiles;   // floor: never a third, partial round of work units
       const long cap = num_kblocks / 8 > 0 ? num_kblocks / 8 : 1;
       split_k = (int)(want < 1 ? 1 : want > cap ? cap : want);
     }
@@ -1052,7 +1052,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   // CTA pairs (tcgen05 cta_group::2): each SM reads its A tile and only half of the B tile from shared memory per MMA
   // -- 64 instead of 96 B/clk of operand reads, and a third less TMA write traffic, through the 128 B/clk shared memory.  It
   // pays when the tile is MMA-bound (long K); short-K tiles are epilogue-bound and only suffer the cross-CTA handshakes.
-  const bool long_k = kpb >= 24 || (kpb >= 8 && !out_fp32);
+  const bool long_k = kpb >= 24 || (kpb >= 8 && (!out_fp32 || a->epilogue == VITK_EPI_ATOMIC_ADD));
   const bool cta2 = pair_ok && long_k;
   const int tile_m = cta2 ? 2 * BLOCK_M : BLOCK_M;
   GemmParams p{};

@@ -84,13 +84,13 @@ def main():
         "dgrad_qkv": (lambda: ops.gemm(qkv, w_qkv, M, D, 3 * D, b_mn=True, out=o16), 4 * E, 2 * M * 3 * D * D),
         "dgrad_proj": (lambda: ops.gemm(x16, w_proj, M, D, D, b_mn=True, out=o16), 2 * E, 2 * M * D * D),
         "wgrad_fc2": (lambda: ops.gemm(x16, h16, D, HID, M, a_mn=True, b_mn=True, out=gw_fc2, epilogue=_lib.EPI_ATOMIC_ADD,
-                                       split_k=splitk(D, HID, M), alpha_dev=one), (R + 1) * E, 2 * M * HID * D),
+                                       split_k=0, alpha_dev=one), (R + 1) * E, 2 * M * HID * D),
         "wgrad_fc1": (lambda: ops.gemm(h16, x16, HID, D, M, a_mn=True, b_mn=True, out=gw_fc1, epilogue=_lib.EPI_ATOMIC_ADD,
-                                       split_k=splitk(HID, D, M), alpha_dev=one), (R + 1) * E, 2 * M * HID * D),
+                                       split_k=0, alpha_dev=one), (R + 1) * E, 2 * M * HID * D),
         "wgrad_qkv": (lambda: ops.gemm(qkv, x16, 3 * D, D, M, a_mn=True, b_mn=True, out=gw_qkv, epilogue=_lib.EPI_ATOMIC_ADD,
-                                       split_k=splitk(3 * D, D, M), alpha_dev=one), 4 * E, 2 * M * 3 * D * D),
+                                       split_k=0, alpha_dev=one), 4 * E, 2 * M * 3 * D * D),
         "wgrad_proj": (lambda: ops.gemm(x16, o16b, D, D, M, a_mn=True, b_mn=True, out=gw_proj, epilogue=_lib.EPI_ATOMIC_ADD,
-                                        split_k=splitk(D, D, M), alpha_dev=one), 2 * E, 2 * M * D * D),
+                                        split_k=0, alpha_dev=one), 2 * E, 2 * M * D * D),
         "attn_fwd": (lambda: ops.attention_fwd(qkv, B, T, H, scale, out=o16b, lse=lse), 4 * E, 4 * B * H * T * T * 64),
         "attn_bwd": (lambda: ops.attention_bwd(qkv, o16b, x16, lse, B, T, H, scale, dqkv=dqkv, delta=delta), 9 * E,
                      10 * B * H * T * T * 64),
