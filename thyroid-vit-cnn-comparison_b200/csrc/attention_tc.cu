@@ -24,11 +24,11 @@
 #include "tc_common.cuh"
 
 #ifdef VITK_GEMM_KNOBS
-// profiling build only: SM clock stamps of CTA (0,0) -- [0..63] MMA thread, [64..] math warp 0 lane 0
+// profiling build only: SM clock stamps of one CTA of a later wave (head 0, image 100) -- [0..63] MMA thread, [64..] math warp 0
 __device__ long long g_attn_dbg[256];
 #define ASTAMP(i)                                                                   \
   do {                                                                              \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < 256) g_attn_dbg[i] = clock64(); \
+    if (blockIdx.x == 0 && blockIdx.y == (gridDim.y > 100 ? 100 : 0) && (i) < 256) g_attn_dbg[i] = clock64(); \
   } while (0)
 #else
 #define ASTAMP(i) \
