@@ -213,3 +213,59 @@ def test_api_surface_and_errors():
         V.get_vit_model("vit_invalid")
     vb = V.get_vit_model("vit_base", img_size=224, in_chans=3, drop_path_rate=0.0)
     assert abs(sum(p.numel() for p in vb.parameters()) - 86e6) < 2e6
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes: size-independent properties
+def test_full_batch_256_properties():
+    """DeiT-tiny at the bench size (batch 256, 3x224x224), where the oracle is too slow to be the checker:
+    * batch independence: the logits of images 0..31 inside the 256-batch are BIT-identical to those of the same 32 images
+      run alone (every kernel is row / image local; tile boundaries must not leak);
+    * determinism: two forwards give bit-identical logits;
+    * linearity of the mean-reduced gradient: grad(256) == mean of the gradients of the 8 sub-batches of 32
+      (checked per parameter, relative L2; split-K / atomics order is the only difference);
+    * oracle parity of the first 32 images' logits and identical top-1 (BASELINE tolerances)."""
+    cfg = O.DEIT_TINY
+    model, sd = build(cfg, 42)
+    x, y = O.seeded_batch(cfg, 256, 42)
+    loss, outs, grads = run_gpu(model, x, y)
+    _, outs2, _ = run_gpu(model, x, y)
+    for a, b in zip(outs, outs2):
+        assert torch.equal(a, b)
+    _, outs32, _ = run_gpu(model, x[:32], y[:32])
+    for a, b in zip(outs, outs32):
+        assert torch.equal(a[:32], b)
+    acc = {n: torch.zeros_like(g) for n, g in grads.items() if g is not None}
+    for k in range(8):
+        _, _, g = run_gpu(model, x[32 * k:32 * k + 32], y[32 * k:32 * k + 32])
+        for n in acc:
+            acc[n] += g[n] / 8
+    worst = max(rel_l2(grads[n], acc[n]) for n in acc)
+    assert worst < 2e-3, worst
+    _, ref_out, _ = O.train_step(sd, x[:32], y[:32], cfg)
+    ref = ref_out if isinstance(ref_out, (tuple, list)) else (ref_out,)
+    for a, r in zip(outs, ref):
+        assert (a[:32] - r).abs().max().item() < LOGIT_TOL
+        assert torch.equal(a[:32].argmax(1), r.argmax(1))
+
+
+def test_train_step_input_slots_and_graph_replay():
+    """TrainStep alternates two input slots (host batches are copied on a side stream while the previous step computes) and
+    replays one captured graph per slot: five steps from pinned host batches must equal five eager steps from device
+    batches, statistic for statistic."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2)
+    stats = []
+    for mode in ("host+graph", "device+eager"):
+        model, _ = build(cfg, 11)
+        model.train()
+        opt = OPT.FusedAdamW(model, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+        step = TR.TrainStep(model, opt, 8, mode="ce", use_graph=(mode == "host+graph"))
+        rows = []
+        for it in range(5):
+            x, y = O.seeded_batch(cfg, 8, 300 + it)
+            if mode == "host+graph":
+                rows.append(step(x.pin_memory(), y.pin_memory()).cpu().clone())
+            else:
+                rows.append(step(x.cuda(), y.cuda()).cpu().clone())
+        torch.cuda.synchronize()
+        stats.append(torch.stack(rows))
+    assert torch.allclose(stats[0], stats[1], rtol=1e-4, atol=1e-5), (stats[0][:, 0], stats[1][:, 0])
