@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 6
+#define VITK_ABI_VERSION 7
 
 typedef enum {
   VITK_OK = 0,
@@ -100,6 +100,9 @@ typedef struct {
    * MN-major) this is the bias gradient of the same nn.Linear; it falls out of one extra N=16 tensor-core MMA per
    * k-step against a tile of ones, so dY is not read a second time. */
   float* colsum_out;
+  /* VITK_EPI_STORE with an fp32 residual (optional): out = residual + row_scale[m] * (acc*alpha + bias), fp32 [M] --
+   * the per-sample stochastic-depth factor floor(keep + u) / keep of DropPath (vision_transformer_base.py:56-64, :283-284). */
+  const float* row_scale;
 } vitk_gemm_args;
 
 int vitk_gemm(const vitk_gemm_args* args, void* stream);
@@ -111,13 +114,15 @@ int vitk_gemm(const vitk_gemm_args* args, void* stream);
  *      dgamma/dbeta/dcolsum are ACCUMULATED (+=) into fp32 [dim], each multiplied by *grad_unscale when given.
  *      dcolsum (optional) receives the column sum of the emitted dx -- the bias gradient of the nn.Linear
  *      that produced the residual branch feeding this LayerNorm's input.
+ *      branch_scale (optional, fp32 [rows]): stochastic-depth factor of that residual branch; dx16 and dcolsum are the
+ *      gradient ENTERING the branch, i.e. dx * branch_scale[row] (dx itself, the residual-stream gradient, is unscaled).
  * ------------------------------------------------------------------------------------------ */
 int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
                        float* mean, float* rstd, int64_t rows, int32_t dim, float eps, void* stream);
 int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* mean,
                        const float* rstd, const float* gamma, const float* dres, float* dx, void* dx16,
                        int32_t dx16_dtype, float* dgamma, float* dbeta, float* dcolsum,
-                       const float* grad_unscale, int64_t rows, int32_t dim, void* stream);
+                       const float* grad_unscale, const float* branch_scale, int64_t rows, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused softmax attention, dh = 64 -- vision_transformer_base.py:174-191 (Attention.forward:
@@ -172,8 +177,13 @@ int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xha
                   const float* rstd, const float* gamma, const float* beta, const float* W0,
                   const float* W1, float* dx, void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta,
                   float* dW0, float* db0, float* dW1, float* db1, float* dcolsum,
-                  const float* loss_scale, int32_t B, int32_t tokens_per_img, int32_t dim, int32_t C,
-                  int32_t n_heads, void* stream);
+                  const float* loss_scale, const float* branch_scale, int32_t B, int32_t tokens_per_img, int32_t dim,
+                  int32_t C, int32_t n_heads, void* stream);
+
+/* Stochastic depth (DropPath.forward, vision_transformer_base.py:56-64): scale[br, b*T + t] = floor(keep + u[br,b]) / keep
+ * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */
+int vitk_droppath_scale(const float* uniform, const float* drop_prob, float* scale, int32_t branches, int32_t B,
+                        int32_t tokens_per_img, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused classification / distillation loss with gradient --

@@ -140,6 +140,32 @@ def test_gemm_wgrad_with_bias_grad(Mc, No, Ko, split, dt):
     assert rel_l2(db, 0.5 + 0.25 * dY.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(6336, 192, 192), (1000, 768, 3072)])
+def test_gemm_residual_row_scale(M, N, K):
+    """out = residual + row_scale[m] * (A W^T + bias): stochastic depth in the residual epilogue (DropPath, :56-64, :283-284)."""
+    A = _rand(M, K, dtype=F16, seed=1)
+    W = _rand(N, K, scale=0.05, dtype=F16, seed=2)
+    bias, res = _rand(N, seed=3), _rand(M, N, seed=4)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    rs = (torch.floor(0.8 + torch.rand(M, generator=g)) / 0.8).to(DEV)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, M, N, K, out=out, bias=bias, residual=res, row_scale=rs)
+    ref = res + rs[:, None] * (A.float() @ W.float().t() + bias)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5
+    assert torch.equal(out[rs == 0], res[rs == 0])          # dropped samples keep the residual bit for bit
+
+
+def test_droppath_scale_kernel():
+    nb, B, T = 6, 64, 198
+    u = torch.rand(nb, B, device=DEV)
+    p = torch.tensor([0.0, 0.02, 0.1, 0.25, 0.5, 0.9], device=DEV)
+    s = ops.droppath_scale(u, p, T)
+    ref = (torch.floor((1 - p)[:, None] + u) / (1 - p)[:, None])[:, :, None].expand(nb, B, T).reshape(nb, B * T)
+    torch.cuda.synchronize()
+    assert torch.equal(s, ref)
+
+
 def test_gemm_tokens_epilogue():
     B, P, T, prefix, D, K = 5, 196, 198, 2, 192, 768
     A = _rand(B * P, K, dtype=F16, seed=1)
@@ -181,6 +207,15 @@ def test_layernorm_fwd_bwd(rows, dim, dt):
     assert rel_l2(dg, gr.grad) < 1e-4
     assert rel_l2(db, br.grad) < 1e-4
     assert rel_l2(dc, ref_dx.sum(0)) < 1e-4
+    # stochastic depth: the 16-bit copy and the column sum carry dx * branch_scale[row]; dx itself is unscaled
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    bs = (torch.floor(0.7 + torch.rand(rows, generator=gen)) / 0.7).to(DEV)
+    dg.zero_(); db.zero_(); dc.zero_()
+    dx2 = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, dres=dres_true * S, dx16=dx16, dcolsum=dc, unscale=u, branch_scale=bs)
+    torch.cuda.synchronize()
+    assert torch.equal(dx2, dx)
+    assert rel_l2(dx16.float() / S, ref_dx * bs[:, None]) < OUT_TOL[dt]
+    assert rel_l2(dc, (ref_dx * bs[:, None]).sum(0)) < 1e-4
 
 
 # ------------------------------------------------------------------ attention

@@ -269,3 +269,63 @@ def test_train_step_input_slots_and_graph_replay():
         torch.cuda.synchronize()
         stats.append(torch.stack(rows))
     assert torch.allclose(stats[0], stats[1], rtol=1e-4, atol=1e-5), (stats[0][:, 0], stats[1][:, 0])
+
+
+def test_stochastic_depth_matches_oracle_with_replayed_masks():
+    """DropPath (vision_transformer_base.py:56-64) in training mode: the GPU path draws one Bernoulli per (branch, sample);
+    torch's CPU stream cannot reproduce the same draws, so the drawn factors are replayed into the oracle and logits /
+    gradients must then agree within BASELINE tolerances; eval mode is the identity; the drop frequency follows the rate."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=4, num_heads=2, is_deit=False, distilled=False)
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=4, num_heads=2, mlp_ratio=4.0)
+    m = V.VisionTransformer(drop_path_rate=0.3, **kw)
+    sd = O.seeded_state_dict(cfg, 3)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    rates = [getattr(b.drop_path, "drop_prob", 0.0) for b in m.blocks]
+    assert rates[0] == 0.0 and abs(rates[-1] - 0.3) < 1e-6                    # linspace(0, dpr, depth), vit_models.py:73
+    x, y = O.seeded_batch(cfg, 16, 3)
+    torch.manual_seed(123)
+    loss, outs, grads = run_gpu(m, x, y)
+    scales = m._engine.last_drop_scale.cpu().clone()                           # [2L, B]
+    assert scales.shape == (8, 16)
+    for i, r in enumerate(rates):                                              # factors are 0 or 1/keep
+        vals = set(scales[2 * i].tolist()) | set(scales[2 * i + 1].tolist())
+        assert all(abs(v) < 1e-6 or abs(v - 1 / (1 - r)) < 1e-5 for v in vals)
+    ref_loss, ref_out, ref_grads = O.train_step(sd, x, y, cfg, drop_scales=scales)
+    assert (outs[0] - ref_out).abs().max().item() < LOGIT_TOL
+    assert abs(loss - ref_loss.item()) < 2e-3
+    for n, g in ref_grads.items():
+        if g is None or "quality_score" in n:
+            continue
+        assert rel_l2(grads[n], g) < GRAD_TOL, (n, rel_l2(grads[n], g))
+    # eval mode: identity (no draws)
+    m.eval()
+    with torch.no_grad():
+        e = m(x.cuda()).cpu()
+    assert (e - O.forward(sd, x, cfg, training=False)).abs().max().item() < LOGIT_TOL
+    # frequency: 4000 draws at rate 0.3 on the last block
+    m.train()
+    drops, n = 0, 0
+    for _ in range(125):
+        m(x.cuda())
+        sc = m._engine.last_drop_scale[-2:]
+        drops += int((sc == 0).sum().item()); n += sc.numel()
+    assert abs(drops / n - 0.3) < 0.03, drops / n
+
+
+def test_stochastic_depth_inside_captured_graph():
+    """The uniforms come from torch's graph-safe CUDA generator: every replay of the captured step must draw new masks."""
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=4, num_heads=2, mlp_ratio=4.0)
+    m = V.VisionTransformer(drop_path_rate=0.5, **kw).cuda().train()
+    opt = OPT.FusedAdamW(m, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    step = TR.TrainStep(m, opt, 32, mode="ce", use_graph=True)
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=4, num_heads=2, is_deit=False, distilled=False)
+    x, y = O.seeded_batch(cfg, 32, 1)
+    seen = []
+    for _ in range(6):
+        step(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        seen.append(m._engine.last_drop_scale.cpu().clone())
+    assert all(torch.isfinite(s).all() for s in seen)
+    distinct = {tuple(s.flatten().tolist()) for s in seen}
+    assert len(distinct) >= 5, len(distinct)

@@ -202,7 +202,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __re
                                 const float* __restrict__ W1, float* __restrict__ dx, bf16* __restrict__ dx16, int fp16,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db0,
                                 float* __restrict__ db1, float* __restrict__ dcolsum, const float* __restrict__ loss_scale,
-                                int B, int T, int dim, int C, int n_heads) {
+                                const float* __restrict__ branch_scale, int B, int T, int dim, int C, int n_heads) {
   const float S = loss_scale != nullptr ? __ldg(loss_scale) : 1.f;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -226,17 +226,19 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __re
   }
   const float m1 = warp_sum(s1) / float(dim), m2 = warp_sum(s2) / float(dim);
   float* dxr = dx + ((long long)b * T + hd) * dim;
+  const float bs = branch_scale != nullptr ? __ldg(branch_scale + (long long)b * T + hd) : 1.f;
   for (int i = lane; i < dim; i += 32) {
     float dxn = 0.f;
     for (int c = 0; c < C; ++c) dxn += dl[c] * W[(long long)c * dim + i];
     const float g = dxn * gamma[i];
     const float o = rs * (g - m1 - xh[i] * m2);
     dxr[i] = o * S;
+    const float ob = o * bs;   // gradient entering the last MLP branch (stochastic depth)
     if (dx16 != nullptr) {
-      if (fp16) reinterpret_cast<__half*>(dx16)[((long long)b * T + hd) * dim + i] = __float2half_rn(o * S);
-      else dx16[((long long)b * T + hd) * dim + i] = __float2bfloat16(o * S);
+      if (fp16) reinterpret_cast<__half*>(dx16)[((long long)b * T + hd) * dim + i] = __float2half_rn(ob * S);
+      else dx16[((long long)b * T + hd) * dim + i] = __float2bfloat16(ob * S);
     }
-    if (dcolsum != nullptr) atomicAdd(dcolsum + i, o);
+    if (dcolsum != nullptr) atomicAdd(dcolsum + i, ob);
   }
   if (dbh != nullptr)
     for (int c = lane; c < C; c += 32) atomicAdd(dbh + c, dl[c]);
@@ -261,6 +263,20 @@ __global__ void head_wgrad_kernel(const float* __restrict__ dl0, const float* __
     for (int b = b0; b < b1; ++b) acc += __ldg(dl + (long long)b * C + c) * (__ldg(xh + (long long)b * dim + i) * gm + bt);
     float* dW = hd == 0 ? dW0 : dW1;
     atomicAdd(dW + (long long)c * dim + i, acc);
+  }
+}
+
+// ------------------------------------------------------------------ stochastic depth (DropPath, vision_transformer_base.py:56-64)
+// scale[br, b*T + t] = floor(keep + u[br, b]) / keep, keep = 1 - drop_prob[br]: one Bernoulli draw per (branch, sample),
+// expanded to the token rows so that GEMM epilogues / LayerNorm backward read one float per row
+__global__ void droppath_scale_kernel(const float* __restrict__ u, const float* __restrict__ drop_prob, float* __restrict__ scale,
+                                      int branches, int B, int T) {
+  const long long total = (long long)branches * B * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long sb = i / T;                 // branch * B + sample
+    const int br = int(sb / B);
+    const float keep = 1.f - drop_prob[br];
+    scale[i] = floorf(keep + u[sb]) / keep;
   }
 }
 
@@ -427,8 +443,8 @@ extern "C" int vitk_head_fwd(const float* x, const float* gamma, const float* be
 extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat, const float* rstd,
                              const float* gamma, const float* beta, const float* W0, const float* W1, float* dx,
                              void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta, float* dW0, float* db0, float* dW1,
-                             float* db1, float* dcolsum, const float* loss_scale, int32_t B, int32_t T, int32_t dim, int32_t C,
-                             int32_t n_heads, void* stream) {
+                             float* db1, float* dcolsum, const float* loss_scale, const float* branch_scale, int32_t B, int32_t T,
+                             int32_t dim, int32_t C, int32_t n_heads, void* stream) {
   VITK_CHECK_ARG(dlogits0 && xhat && rstd && gamma && beta && W0 && dx && dgamma && dbeta && dW0, "vitk_head_bwd: null pointer");
   VITK_CHECK_ARG(n_heads == 1 || (n_heads == 2 && dlogits1 && W1 && dW1), "vitk_head_bwd: n_heads must be 1 or 2");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -437,11 +453,21 @@ extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const
   const int warps = B * n_heads;
   head_bwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(dlogits0, dlogits1, xhat, rstd, gamma, W0, W1, dx,
                                                    reinterpret_cast<bf16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, db0,
-                                                   db1, dcolsum, loss_scale, B, T, dim, C, n_heads);
+                                                   db1, dcolsum, loss_scale, branch_scale, B, T, dim, C, n_heads);
   VITK_LAUNCH_CHECK();
   const long long total = (long long)n_heads * C * dim;
   head_wgrad_kernel<<<dim3(capped_grid(total, 128, 4), (B + 15) / 16), 128, 0, st>>>(dlogits0, dlogits1, xhat, gamma, beta, dW0, dW1,
                                                                                     B, dim, C, n_heads);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_droppath_scale(const float* uniform, const float* drop_prob, float* scale, int32_t branches, int32_t B, int32_t T,
+                                   void* stream) {
+  VITK_CHECK_ARG(uniform && drop_prob && scale && branches > 0 && B > 0 && T > 0, "vitk_droppath_scale: bad args");
+  const long long total = (long long)branches * B * T;
+  droppath_scale_kernel<<<capped_grid(total, 256, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(uniform, drop_prob, scale,
+                                                                                                       branches, B, T);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -72,6 +72,7 @@ struct GemmParams {
   int kblocks_per_split;
   int num_m_tiles, num_n_tiles, num_splits;
   int step_split, step_mt, step_nt;  // mixed-radix digits of the grid size over (split, m tile, n tile)
+  const float* row_scale;  // optional [M]: out = residual + row_scale[m] * (acc*alpha + bias)  (stochastic depth)
   float* colsum;     // optional [M]: += alpha * sum_k A[m, k], from one extra N=16 MMA per k-step against a tile of ones
   int acc_stride;    // TMEM columns per accumulator stage (BN, or BN + 16 with colsum)
   int nacc;          // accumulator stages: 2 (MMAs of tile i+1 overlap epilogue i), or 1 when 2 x acc_stride > 512 columns
@@ -715,6 +716,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               f[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), alpha, b4[c].z);
               f[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), alpha, b4[c].w);
             }
+            if (p.row_scale != nullptr) {   // per-sample stochastic-depth factor of this residual branch
+              const float rsc = (row_base + lane) < p.M ? __ldg(p.row_scale + row_base + lane) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] *= rsc;
+            }
             if (has_aux) {
               mbar_wait(&aux_bar[warp - 2], aux_phase, 5);
               aux_phase ^= 1;
@@ -1075,6 +1081,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.aux = a->aux; p.ldaux = a->ldaux;
   p.colsum = a->colsum_out;
+  p.row_scale = a->row_scale;
   p.acc_stride = bn + (a->colsum_out != nullptr ? 16 : 0);
   p.nacc = 2 * p.acc_stride <= 512 ? 2 : 1;
   {
@@ -1104,6 +1111,8 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
                (a->epilogue != VITK_EPI_DGELU || (a->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0)))
                   ? 1 : 0;
   if (p.num_n_tiles * bn > MAX_BIAS_SMEM) p.tma_epi = 0;  // the TMA epilogue keeps the whole bias vector in shared memory
+  if (a->row_scale != nullptr)
+    VITK_CHECK_ARG(p.tma_epi && out_fp32 && a->epilogue == VITK_EPI_STORE, "vitk_gemm: row_scale needs the fp32 STORE epilogue");
   if (a->colsum_out != nullptr)
     VITK_CHECK_ARG(p.tma_epi && p.num_n_tiles * bn <= ONES_OFFSET, "vitk_gemm: colsum_out supports N <= %d", ONES_OFFSET);
   tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                   float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale, long long rows,
-                  int dim) {
+                  float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale,
+                  const float* __restrict__ branch_scale, long long rows, int dim) {
   constexpr int RPW = 32 / LPR;
   extern __shared__ float red[];  // [3][dim]
   const int lane = threadIdx.x & 31;
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     const float m2 = group_sum<LPR>(s2) * inv_dim;
     if (!ok) continue;
     float* dxr = dx + row * dim;
+    const float bs = branch_scale != nullptr ? __ldg(branch_scale + row) : 1.f;   // stochastic-depth scale of the branch below
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       const int i = gl + LPR * c;
@@ -154,9 +155,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
         const float4 o = make_float4(rs * (g[c].x - m1 - xh[c].x * m2) + rv[c].x, rs * (g[c].y - m1 - xh[c].y * m2) + rv[c].y,
                                      rs * (g[c].z - m1 - xh[c].z * m2) + rv[c].z, rs * (g[c].w - m1 - xh[c].w * m2) + rv[c].w);
         *reinterpret_cast<float4*>(dxr + 4 * i) = o;
+        const float4 ob = make_float4(o.x * bs, o.y * bs, o.z * bs, o.w * bs);
         if (dx16 != nullptr)
-          *reinterpret_cast<uint2*>(dx16 + row * dim + 4 * i) = make_uint2(pack16(o.x, o.y, dx_fp16), pack16(o.z, o.w, dx_fp16));
-        dc[c].x += o.x; dc[c].y += o.y; dc[c].z += o.z; dc[c].w += o.w;
+          *reinterpret_cast<uint2*>(dx16 + row * dim + 4 * i) = make_uint2(pack16(ob.x, ob.y, dx_fp16), pack16(ob.z, ob.w, dx_fp16));
+        dc[c].x += ob.x; dc[c].y += ob.y; dc[c].z += ob.z; dc[c].w += ob.w;
       }
     }
   }
@@ -196,7 +198,8 @@ __global__ void __launch_bounds__(192, 5)
     ln_bwd_cols_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
                        const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale, long long rows) {
+                       float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale,
+                       const float* __restrict__ branch_scale, long long rows) {
   constexpr int T = 192;
   constexpr int SLOTS = T / V;                 // rows processed side by side
   constexpr int G = (V % 32 == 0) ? 32 : 16;   // lanes per shuffle group (never straddles two rows)
@@ -265,9 +268,12 @@ __global__ void __launch_bounds__(192, 5)
         const float4 o = make_float4(rs[r] * (g[r].x - m1 - xh[r].x * m2) + rv[r].x, rs[r] * (g[r].y - m1 - xh[r].y * m2) + rv[r].y,
                                      rs[r] * (g[r].z - m1 - xh[r].z * m2) + rv[r].z, rs[r] * (g[r].w - m1 - xh[r].w * m2) + rv[r].w);
         *reinterpret_cast<float4*>(dx + row * DIM + 4 * cv) = o;
+        // the 16-bit copy and the bias gradient belong to the residual BRANCH below: scaled by its stochastic-depth factor
+        const float bs = branch_scale != nullptr ? __ldg(branch_scale + row) : 1.f;
+        const float4 ob = make_float4(o.x * bs, o.y * bs, o.z * bs, o.w * bs);
         if (dx16 != nullptr)
-          *reinterpret_cast<uint2*>(dx16 + row * DIM + 4 * cv) = make_uint2(pack16(o.x, o.y, dx_fp16), pack16(o.z, o.w, dx_fp16));
-        dc.x += o.x; dc.y += o.y; dc.z += o.z; dc.w += o.w;
+          *reinterpret_cast<uint2*>(dx16 + row * DIM + 4 * cv) = make_uint2(pack16(ob.x, ob.y, dx_fp16), pack16(ob.z, ob.w, dx_fp16));
+        dc.x += ob.x; dc.y += ob.y; dc.z += ob.z; dc.w += ob.w;
       }
     }
   }
@@ -352,8 +358,8 @@ extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const floa
 
 extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* mean, const float* rstd,
                                   const float* gamma, const float* dres, float* dx, void* dx16, int32_t dx16_dtype,
-                                  float* dgamma, float* dbeta, float* dcolsum, const float* grad_unscale, int64_t rows,
-                                  int32_t dim, void* stream) {
+                                  float* dgamma, float* dbeta, float* dcolsum, const float* grad_unscale,
+                                  const float* branch_scale, int64_t rows, int32_t dim, void* stream) {
   VITK_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "vitk_layernorm_bwd: null pointer");
   VITK_CHECK_ARG((dy_dtype == VITK_BF16 || dy_dtype == VITK_FP16) && (dx16_dtype == VITK_BF16 || dx16_dtype == VITK_FP16),
                  "vitk_layernorm_bwd: dy / dx16 must be bf16 or fp16");
@@ -371,7 +377,7 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
     const long long cap = (long long)num_sms() * 5;                                                                        \
     if (blocks > cap) blocks = cap;                                                                                        \
     VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, gamma,   \
-                         dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, (long long)rows));                  \
+                         dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, branch_scale, (long long)rows));                  \
     VITK_LAUNCH_CHECK();                                                                                                   \
     return VITK_OK;                                                                                                        \
   }
@@ -387,7 +393,8 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
   const int rpb = LN_WARPS * (32 / cfg.lpr) * 4;
   LN_DISPATCH((ln_bwd_kernel<L_, C_><<<ln_grid(rows, rpb, 6), LN_WARPS * 32, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), int(dy_dtype == VITK_FP16), x, mean, rstd, gamma, dres, dx,
-      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum, grad_unscale, rows, dim)));
+      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum, grad_unscale, branch_scale, rows,
+      dim)));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

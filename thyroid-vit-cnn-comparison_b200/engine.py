@@ -189,6 +189,18 @@ class VitEngine:
         self.amp = torch.tensor([s0, 1.0 / s0, 0, 0, 0, 0, 0, 0], dtype=torch.float32, device=self.device)
         self.amp_scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.growth_interval = self.GROWTH_INTERVAL if dtype16 == torch.float16 else 0
+        # stochastic depth (DropPath, vision_transformer_base.py:56-64, rates linspace(0, dpr, L) per block, vit_models.py:73):
+        # branch 2l = attention branch of block l, branch 2l+1 = its MLP branch; one Bernoulli draw per (branch, sample)
+        self.drop_path = [0.0] * (2 * dims.depth)
+        self._dp_prob_dev = None
+        self.last_drop_scale = None     # [2L, B] factors of the latest training forward (tests / debugging)
+
+    def set_drop_path(self, per_block_rates) -> None:
+        rates = [float(r) for r in per_block_rates]
+        if len(rates) != self.d.depth or any(not (0.0 <= r < 1.0) for r in rates):
+            raise ValueError("set_drop_path: one rate in [0, 1) per block expected")
+        self.drop_path = [r for r in rates for _ in range(2)]
+        self._dp_prob_dev = torch.tensor(self.drop_path, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ helpers
     def w(self, name: str) -> torch.Tensor:      # 16-bit shadow view
@@ -244,6 +256,17 @@ class VitEngine:
         images = images.contiguous()
         if images.dtype != torch.float32:
             images = images.float()
+        dp = None
+        if train and any(r > 0.0 for r in self.drop_path):
+            # uniforms come from torch's CUDA generator (seedable, CUDA-graph safe); the mask arithmetic is libvitk's
+            u = torch.rand(2 * d.depth, B, dtype=torch.float32, device=self.device)
+            if getattr(ws, "dp", None) is None:
+                ws.dp = torch.empty(2 * d.depth, M, dtype=torch.float32, device=self.device)
+            ops.droppath_scale(u, self._dp_prob_dev, T, out=ws.dp)
+            dp = ws.dp
+            self.last_drop_scale = ws.dp[:, ::T]
+        ws.dp_active = dp is not None
+        rs = lambda i: dp[i] if (dp is not None and self.drop_path[i] > 0.0) else None
         ops.patchify(images, d.patch, out=ws.patches)
         x0 = ws.x[0]
         ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
@@ -266,11 +289,13 @@ class VitEngine:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
             ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
-            ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in)
+            ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in,
+                     row_scale=rs(2 * l))
             ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
             ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.dact[s], out2=ws.act[s],
                      bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
-            ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid)
+            ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid,
+                     row_scale=rs(2 * l + 1))
         x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
         two = d.n_out == 2
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
@@ -295,13 +320,15 @@ class VitEngine:
         ws.head_saved = None
         two = d.n_out == 2
         u = self.grad_unscale
+        dp = ws.dp if getattr(ws, "dp_active", False) else None
+        rs = lambda i: dp[i] if (dp is not None and i >= 0 and self.drop_path[i] > 0.0) else None
         dx, dx_alt = ws.dx[0], ws.dx[1]
         last_fc2_bias = self.g(f"blocks.{d.depth - 1}.mlp.fc2.bias")
         ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),
                      self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dx16,
                      self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
                      self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
-                     last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale)
+                     last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale, branch_scale=rs(2 * d.depth - 1))
         self._notify("head")
         for l in range(d.depth - 1, -1, -1):
             pre = f"blocks.{l}."
@@ -315,7 +342,7 @@ class VitEngine:
             ops.gemm(ws.d_pre, self.w(pre + "mlp.fc1.weight"), M, D, d.hidden, b_mn=True, out=ws.dxn)
             ops.layernorm_bwd(ws.dxn, x_mid, st[2], st[3], self.p(pre + "norm2.weight"), self.g(pre + "norm2.weight"),
                               self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16,
-                              dcolsum=self.g(pre + "attn.proj.bias"), unscale=u)
+                              dcolsum=self.g(pre + "attn.proj.bias"), unscale=u, branch_scale=rs(2 * l))
             dx, dx_alt = dx_alt, dx
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
             self._wgrad(ws.dx16, ws.ao[l], pre + "attn.proj.weight", M)
@@ -326,7 +353,7 @@ class VitEngine:
             prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
             ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),
                               self.g(pre + "norm1.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16 if l > 0 else None,
-                              dcolsum=prev_bias, unscale=u)
+                              dcolsum=prev_bias, unscale=u, branch_scale=rs(2 * l - 1))
             dx, dx_alt = dx_alt, dx
             self._notify(pre)
         ops.tokens_bwd(dx.view(B, T, D), self.g("pos_embed"), self.g("cls_token"),

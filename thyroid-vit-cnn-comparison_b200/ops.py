@@ -60,7 +60,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
          epilogue: int = _lib.EPI_STORE, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          split_k: int = 1, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, tokens: Optional[tuple] = None,
          pos: Optional[torch.Tensor] = None, lda: Optional[int] = None, ldb: Optional[int] = None,
-         colsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         colsum_out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue (see include/vitk.h).
 
     A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].  A and B must share one
@@ -94,6 +94,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     if colsum_out is not None:
         _req(colsum_out, f32, "gemm colsum_out")
     a.colsum_out = _p(colsum_out)
+    if row_scale is not None:
+        _req(row_scale, f32, "gemm row_scale")
+    a.row_scale = _p(row_scale)
     check(_lib.load().vitk_gemm(C.byref(a), _stream()), "gemm")
     return out
 
@@ -111,8 +114,10 @@ def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=Non
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None, dx16=None, dcolsum=None, unscale=None):
-    """dx = dres + LN'(dy); dgamma/dbeta/dcolsum += (*unscale) * column sums."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None, dx16=None, dcolsum=None, unscale=None,
+                  branch_scale=None):
+    """dx = dres + LN'(dy); dgamma/dbeta/dcolsum += (*unscale) * column sums.  With `branch_scale` ([rows], stochastic depth)
+    dx16 and dcolsum carry dx * branch_scale[row]."""
     _req16(dy, "layernorm dy"); _req(x, f32, "layernorm x")
     dim = x.shape[-1]
     rows = x.numel() // dim
@@ -120,7 +125,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None
     check(_lib.load().vitk_layernorm_bwd(dy.data_ptr(), _DT[dy.dtype], x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                          gamma.data_ptr(), _p(dres), dx.data_ptr(), _p(dx16),
                                          _DT[dx16.dtype] if dx16 is not None else _DT[dy.dtype], dgamma.data_ptr(),
-                                         dbeta.data_ptr(), _p(dcolsum), _p(unscale), rows, dim, _stream()), "layernorm_bwd")
+                                         dbeta.data_ptr(), _p(dcolsum), _p(unscale), _p(branch_scale), rows, dim, _stream()),
+          "layernorm_bwd")
     return dx
 
 
@@ -186,14 +192,24 @@ def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5):
 
 
 def head_bwd(dl0, dl1, xhat, rstd, gamma, beta, W0, W1, dx, dx16, dgamma, dbeta, dW0, db0, dW1, db1, dcolsum,
-             T: int, n_heads: int, loss_scale=None):
+             T: int, n_heads: int, loss_scale=None, branch_scale=None):
     """dx / dx16 = S * dLoss/dx (S = *loss_scale), parameter gradients are true (unscaled)."""
     B, Cc = dl0.shape
     dim = W0.shape[1]
     check(_lib.load().vitk_head_bwd(dl0.data_ptr(), _p(dl1), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                     W0.data_ptr(), _p(W1), dx.data_ptr(), _p(dx16), _DT[dx16.dtype] if dx16 is not None else 0,
                                     dgamma.data_ptr(), dbeta.data_ptr(), dW0.data_ptr(), _p(db0), _p(dW1), _p(db1), _p(dcolsum),
-                                    _p(loss_scale), B, T, dim, Cc, n_heads, _stream()), "head_bwd")
+                                    _p(loss_scale), _p(branch_scale), B, T, dim, Cc, n_heads, _stream()), "head_bwd")
+
+
+def droppath_scale(uniform, drop_prob, T: int, out=None):
+    """[branches, B] uniforms + [branches] drop probabilities -> [branches, B*T] per-row stochastic-depth factors."""
+    _req(uniform, f32, "droppath uniform"); _req(drop_prob, f32, "droppath drop_prob")
+    nb, B = uniform.shape
+    out = torch.empty(nb, B * T, dtype=f32, device=uniform.device) if out is None else out
+    check(_lib.load().vitk_droppath_scale(uniform.data_ptr(), drop_prob.data_ptr(), out.data_ptr(), nb, B, T, _stream()),
+          "droppath_scale")
+    return out
 
 
 # --------------------------------------------------------------------------- loss

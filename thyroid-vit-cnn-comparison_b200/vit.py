@@ -64,6 +64,8 @@ class DropPath(nn.Module):
         self.drop_prob = drop_prob
 
     def forward(self, x):
+        # inside a model the engine applies stochastic depth in the residual epilogue of the branch's last GEMM
+        # (VitEngine.set_drop_path); called stand-alone on a tensor only the identity cases are served
         if self.drop_prob == 0.0 or not self.training:
             return x
         raise NotImplementedError("DropPath with drop_prob > 0 in training mode is not implemented in the sm_100a path yet")
@@ -311,9 +313,9 @@ class VisionTransformerBase(_Base):
             raise NotImplementedError("representation_size / pre_logits is not implemented in the sm_100a path")
         if not isinstance(getattr(self, "pos_embed", None), nn.Parameter):
             raise NotImplementedError("sinusoidal position embeddings are not implemented in the sm_100a path")
-        if self.training and (hp.get("drop_rate", 0.0) or hp.get("attn_drop_rate", 0.0) or hp.get("drop_path_rate", 0.0)):
-            raise NotImplementedError("dropout / attention dropout / stochastic depth > 0 are not implemented in the "
-                                      "sm_100a training path yet (parity configuration uses 0, SURVEY.md section 7)")
+        if self.training and (hp.get("drop_rate", 0.0) or hp.get("attn_drop_rate", 0.0)):
+            raise NotImplementedError("dropout / attention dropout > 0 are not implemented in the sm_100a training path "
+                                      "(stochastic depth is; parity configuration uses 0, SURVEY.md section 7)")
 
     def _engine_params(self) -> "OrderedDict[str, nn.Parameter]":
         skip = ("patch_embed.quality_score",)
@@ -335,6 +337,7 @@ class VisionTransformerBase(_Base):
             for n, p in named.items():        # re-point the module's parameters at the flat buffers
                 p.data = eng.flat.view(eng.flat.params, n)
                 p.grad = None
+            eng.set_drop_path([float(getattr(b.drop_path, "drop_prob", 0.0)) for b in self.blocks])
             self._engine = eng
             named = self._engine_params()
             first = next(iter(named.values()))
