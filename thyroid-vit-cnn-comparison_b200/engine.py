@@ -228,12 +228,6 @@ class VitEngine:
             self._ws[key] = ws
         return ws
 
-    def _split_k(self, m_out: int, n_out: int, k: int, colsum: bool = False) -> int:
-        bn = 256 if (n_out % 256 == 0 and not colsum) else 192 if n_out % 192 == 0 else 128 if n_out % 128 == 0 else 64
-        tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
-        nkb = (k + 63) // 64
-        return max(1, min(max(1, nkb // 2), (2 * self.sms + tiles - 1) // tiles))
-
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, rows: int, bias_name: Optional[str] = None) -> None:
         """grad[wname][N_out, K_in] += (1/S) * dy[rows, N_out]^T @ x[rows, K_in] (both operands read MN-major);
         with `bias_name`, grad[bias][N_out] += (1/S) * column sums of dy from the same pass over dy."""
