@@ -30,7 +30,14 @@ __device__ long long g_attn_dbg[256];
   do {                                                                              \
     if (blockIdx.x == 0 && blockIdx.y == (gridDim.y > 100 ? 100 : 0) && (i) < 256) g_attn_dbg[i] = clock64(); \
   } while (0)
+#define FSTAMP(i)                                                                                                   \
+  do {                                                                                                              \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == (gridDim.z > 100 ? 100 : 0)) g_attn_dbg[200 + (i)] = clock64(); \
+  } while (0)
 #else
+#define FSTAMP(i) \
+  do {            \
+  } while (0)
 #define ASTAMP(i) \
   do {            \
   } while (0)
@@ -119,8 +126,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   if (warp == 4) {
     // ===================== MMA issuer (one elected thread) =====================
     if (elect_one()) {
+      FSTAMP(0);
       mbar_wait(bar_qk, 0, 1);
       tc_fence_after();
+      FSTAMP(1);
       const uint32_t idesc_s = idesc_f16(KP, false, false, H16);
       const uint64_t adesc = smem_desc_kmajor(smem_u32(sQ));
       const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK));
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       mbar_wait(bar_p, 0, 2);
       mbar_wait(bar_v, 0, 3);
       tc_fence_after();
+      FSTAMP(2);
       const uint32_t idesc_o = idesc_f16(DH, false, true, H16);
       const uint64_t vdesc = smem_desc_mnmajor(smem_u32(sV), 8192);
       const int steps = KP >> 4;
@@ -148,24 +158,47 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     const bool warp_valid = q0 + warp * 32 < N;
     mbar_wait(bar_s, 0, 4);
     tc_fence_after();
-    // pass 1: row maximum over the valid keys
-    float mx = -INFINITY;
-    for (int c0 = 0; warp_valid && c0 < KP; c0 += 32) {
-      uint32_t v[32];
-      if (KP - c0 >= 32) {
-        tmem_ld32_nowait(trow + uint32_t(c0), v);
-      } else {
-        tmem_ld16_nowait(trow + uint32_t(c0), v);
+    if (threadIdx.x == 0) FSTAMP(3);
+    // pass 1: row maximum over the valid keys.  Four independent running maxima (a single fmaxf chain over 208 columns is
+    // ~1000 cycles of pure dependency latency) and the next chunk's TMEM load in flight while this one is reduced.
+    float mx;
+    {
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      uint32_t va[32], vb[32];
+      const int nch = (KP + 31) >> 5;
+      auto load_chunk = [&](int c, uint32_t (&v)[32]) {
+        if (KP - 32 * c >= 32) tmem_ld32_nowait(trow + uint32_t(32 * c), v);
+        else tmem_ld16_nowait(trow + uint32_t(32 * c), v);
+      };
+      auto reduce_chunk = [&](int c, const uint32_t (&v)[32]) {
+        const int c0 = 32 * c;
+        if (c0 + 32 <= N) {        // whole chunk valid: no per-element masking
 #pragma unroll
-        for (int j = 16; j < 32; ++j) v[j] = 0xff800000u;  // -inf
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], (c0 + j < N) ? __uint_as_float(v[j]) : -INFINITY);
+        }
+      };
+      if (warp_valid) {
+        load_chunk(0, va);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) load_chunk(c + 1, vb);
+          reduce_chunk(c, va);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) load_chunk(c + 2, va);
+            reduce_chunk(c + 1, vb);
+          }
+        }
       }
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c0 + j < N) ? __uint_as_float(v[j]) : -INFINITY);
+      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     }
     // pass 2: P = exp2((S - max) * scale * log2e), 16-bit, in place
+    if (threadIdx.x == 0) FSTAMP(4);
     const float msc = mx * scale_log2;
-    float2 sum2 = make_float2(0.f, 0.f);
+    float2 sum2 = make_float2(0.f, 0.f), sum2b = make_float2(0.f, 0.f);
     for (int c0 = 0; warp_valid && c0 < KP; c0 += 32) {
       uint32_t v[32];
       const bool full = KP - c0 >= 32;
@@ -179,26 +212,39 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       tmem_ld_wait();
       uint32_t ph[16];
       const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-msc, -msc);
+      if (c0 + 32 <= N) {          // whole chunk valid
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nm2);
-        const float p0 = (c0 + j < N) ? ex2_approx(x.x) : 0.f;
-        const float p1 = (c0 + j + 1 < N) ? ex2_approx(x.y) : 0.f;
-        sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
-        ph[j >> 1] = pk16<H16>(p0, p1);
+        for (int j = 0; j < 32; j += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nm2);
+          const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          if (j & 2) sum2b = __fadd2_rn(sum2b, pp);
+          else sum2 = __fadd2_rn(sum2, pp);
+          ph[j >> 1] = pk16<H16>(pp.x, pp.y);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nm2);
+          const float p0 = (c0 + j < N) ? ex2_approx(x.x) : 0.f;
+          const float p1 = (c0 + j + 1 < N) ? ex2_approx(x.y) : 0.f;
+          sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
+          ph[j >> 1] = pk16<H16>(p0, p1);
+        }
       }
       if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
       else tmem_st8_nowait(trow + uint32_t(c0 >> 1), ph);
     }
-    const float sum = sum2.x + sum2.y;
+    const float sum = (sum2.x + sum2.y) + (sum2b.x + sum2b.y);
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(bar_p);
+    if (threadIdx.x == 0) FSTAMP(5);
     if (q < N) lse[((long long)b * H + h) * N + q] = fmaf(mx, scale, logf(sum));
     const float inv = 1.f / sum;
     // epilogue: O / rowsum -> 16-bit -> swizzled staging (the Q tile is dead once S exists) -> TMA store
     mbar_wait(bar_o, 0, 5);
     tc_fence_after();
+    if (threadIdx.x == 0) FSTAMP(6);
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       if (!warp_valid) break;
@@ -222,6 +268,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       tma_store_commit();
       tma_store_wait_read();   // shared memory must outlive the reads; the writes complete asynchronously
     }
+    if (threadIdx.x == 0) FSTAMP(7);
   }
   tc_fence_before();
   __syncthreads();

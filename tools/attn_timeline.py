@@ -30,3 +30,9 @@ for t in range(NT):
     w = [v[68 + 8 * t + i] - t0 for i in range(6)]
     print(f"{t:2d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} | {w[0]:7d} {w[1]:7d} {w[2]:7d} {w[3]:7d} {w[4]:7d} {w[5] if w[5] > 0 else 0:7d}")
 print("math: delta done", v[64] - t0, "| all done", v[65] - t0)
+
+f = [v[200 + i] for i in range(8)]
+f0 = f[0]
+print("forward CTA (tile 0, head 0, image 100), cycles from the MMA thread's start:")
+print("  Q,K landed", f[1] - f0, "| S ready (softmax starts)", f[3] - f0, "| max pass done", f[4] - f0, "| P written", f[5] - f0,
+      "| PV issued", f[2] - f0, "| O ready", f[6] - f0, "| stored", f[7] - f0)
