@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 7
+#define VITK_ABI_VERSION 8
 
 typedef enum {
   VITK_OK = 0,
@@ -171,8 +171,9 @@ int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, voi
  * ------------------------------------------------------------------------------------------ */
 int vitk_head_fwd(const float* x, const float* gamma, const float* beta, const float* W0,
                   const float* b0, const float* W1, const float* b1, float* logits0,
-                  float* logits1, float* xhat, float* rstd, int32_t B, int32_t tokens_per_img,
-                  int32_t dim, int32_t C, int32_t n_heads, float eps, void* stream);
+                  float* logits1, float* xhat, float* rstd, float* pooled, int32_t B,
+                  int32_t tokens_per_img, int32_t dim, int32_t C, int32_t n_heads, float eps,
+                  void* stream);
 int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat,
                   const float* rstd, const float* gamma, const float* beta, const float* W0,
                   const float* W1, float* dx, void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta,

@@ -329,3 +329,65 @@ def test_stochastic_depth_inside_captured_graph():
     assert all(torch.isfinite(s).all() for s in seen)
     distinct = {tuple(s.flatten().tolist()) for s in seen}
     assert len(distinct) >= 5, len(distinct)
+
+
+def test_sinusoidal_pos_embed_is_a_fixed_buffer():
+    """pos_embed_type='sinusoidal' (vision_transformer_base.py:352-356, 404-413): the table is a buffer, takes part in the
+    forward like the learnable one, never receives an optimizer update, and round-trips through state_dict."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2, is_deit=False, distilled=False)
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.0)
+    m = V.VisionTransformer(pos_embed_type="sinusoidal", **kw)
+    assert "pos_embed" in dict(m.named_buffers()) and "pos_embed" not in dict(m.named_parameters())
+    pos = torch.arange(17, dtype=torch.float64)[:, None]
+    i2 = torch.arange(0, 128, 2, dtype=torch.float64)[None, :]
+    ang = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), i2 / 128)
+    assert (m.pos_embed[0, :, 0::2].double() - ang.sin()).abs().max() < 1e-5
+    assert (m.pos_embed[0, :, 1::2].double() - ang.cos()).abs().max() < 1e-5
+    sd = O.seeded_state_dict(cfg, 5)
+    sd["pos_embed"] = m.pos_embed.detach().clone()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x, y = O.seeded_batch(cfg, 8, 5)
+    loss, outs, grads = run_gpu(m, x, y)
+    ref_loss, ref_out, ref_grads = O.train_step(sd, x, y, cfg)
+    assert (outs[0] - ref_out).abs().max().item() < LOGIT_TOL
+    assert abs(loss - ref_loss.item()) < 2e-3
+    for n, g in ref_grads.items():
+        if g is None or "quality_score" in n or n == "pos_embed":
+            continue
+        assert rel_l2(grads[n], g) < GRAD_TOL, (n, rel_l2(grads[n], g))
+    opt = OPT.FusedAdamW(m, lr=1e-2, weight_decay=0.1, max_grad_norm=1.0)
+    before = {n: t.detach().clone() for n, t in m.state_dict().items()}
+    opt.step()
+    torch.cuda.synchronize()
+    after = m.state_dict()
+    assert torch.equal(after["pos_embed"], before["pos_embed"])               # fixed table
+    assert not torch.equal(after["cls_token"], before["cls_token"])           # everything else trains
+    assert (after["pos_embed"].cpu() - sd["pos_embed"]).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("name", ["small_deit", "small_vit"])
+def test_forward_features_matches_oracle(name):
+    """forward_features / extract_features (vision_transformer_base.py:440-479,494-497; deit_models.py:190-218)."""
+    rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
+    cfg = O.VitConfig(**rec["config"])
+    model, sd = build(cfg, rec["seed"])
+    x, _ = O.seeded_batch(cfg, rec["batch"], rec["seed"])
+    ref = O.forward_tokens(sd, x, cfg)                                        # normalised tokens [B,T,D]
+    model.eval()
+    with torch.no_grad():
+        f = model.forward_features(x.cuda())
+        e = model.extract_features(x.cuda())
+    if cfg.is_deit:
+        assert f.shape == ref.shape
+        assert (f.cpu() - ref).abs().max().item() < 1e-2 and rel_l2(f.cpu(), ref) < 2e-3
+    else:
+        feats, quality = f
+        assert quality is None and feats.shape == (rec["batch"], cfg.embed_dim)
+        assert (feats.cpu() - ref[:, 0]).abs().max().item() < 1e-2 and rel_l2(feats.cpu(), ref[:, 0]) < 2e-3
+    assert e.shape == (rec["batch"], cfg.embed_dim)
+    assert rel_l2(e.cpu(), ref[:, 0]) < 2e-3
+    assert model.blocks[0].attn.attention_maps is not None                   # eval-mode maps are stored here too (:455-466)
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model.forward_features(x.cuda())                                     # training goes through forward()

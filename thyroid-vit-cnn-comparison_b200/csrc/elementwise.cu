@@ -166,8 +166,8 @@ __global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restric
 __global__ void head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ W1,
                                 const float* __restrict__ b1, float* __restrict__ logits0, float* __restrict__ logits1,
-                                float* __restrict__ xhat, float* __restrict__ rstd, int B, int T, int dim, int C, int n_heads,
-                                float eps) {
+                                float* __restrict__ xhat, float* __restrict__ rstd, float* __restrict__ pooled, int B, int T,
+                                int dim, int C, int n_heads, float eps) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * n_heads) return;
@@ -183,7 +183,11 @@ __global__ void head_fwd_kernel(const float* __restrict__ x, const float* __rest
   }
   const float rs = rsqrtf(warp_sum(q) / float(dim) + eps);
   float* xh = xhat + ((long long)hd * B + b) * dim;
-  for (int i = lane; i < dim; i += 32) xh[i] = (xr[i] - mu) * rs;
+  for (int i = lane; i < dim; i += 32) {
+    const float v = (xr[i] - mu) * rs;
+    xh[i] = v;
+    if (pooled != nullptr) pooled[((long long)hd * B + b) * dim + i] = v * gamma[i] + beta[i];   // norm(x)[:, hd] (forward_features)
+  }
   if (lane == 0) rstd[hd * B + b] = rs;
   __syncwarp();
   const float* W = hd == 0 ? W0 : W1;
@@ -429,13 +433,13 @@ extern "C" int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float*
 
 extern "C" int vitk_head_fwd(const float* x, const float* gamma, const float* beta, const float* W0, const float* b0,
                              const float* W1, const float* b1, float* logits0, float* logits1, float* xhat, float* rstd,
-                             int32_t B, int32_t T, int32_t dim, int32_t C, int32_t n_heads, float eps, void* stream) {
+                             float* pooled, int32_t B, int32_t T, int32_t dim, int32_t C, int32_t n_heads, float eps, void* stream) {
   VITK_CHECK_ARG(x && gamma && beta && W0 && logits0 && xhat && rstd, "vitk_head_fwd: null pointer");
   VITK_CHECK_ARG(n_heads == 1 || (n_heads == 2 && W1 && logits1), "vitk_head_fwd: n_heads must be 1 or 2");
   VITK_CHECK_ARG(T >= n_heads, "vitk_head_fwd: fewer tokens than heads");
   const int warps = B * n_heads;
   head_fwd_kernel<<<(warps + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gamma, beta, W0, b0, W1, b1, logits0, logits1,
-                                                                                      xhat, rstd, B, T, dim, C, n_heads, eps);
+                                                                                      xhat, rstd, pooled, B, T, dim, C, n_heads, eps);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -239,7 +239,10 @@ class VitEngine:
                  colsum_out=self.g(bias_name) if bias_name is not None else None)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, images: torch.Tensor, train: bool, attn_probs: Optional[List[torch.Tensor]] = None):
+    def forward(self, images: torch.Tensor, train: bool, attn_probs: Optional[List[torch.Tensor]] = None,
+                features: Optional[dict] = None):
+        """features (inference only): a dict that receives 'pooled' = norm(x)[:, :n_out] as fp32 [n_out,B,D] and
+        'x_last' = the final residual stream fp32 [B,T,D] (a workspace view: copy or consume before the next call)."""
         d = self.d
         if images.dim() != 4 or images.shape[1] != d.chans:
             raise ValueError(f"expected images [B,{d.chans},H,W], got {tuple(images.shape)}")
@@ -292,10 +295,15 @@ class VitEngine:
                      row_scale=rs(2 * l + 1))
         x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
         two = d.n_out == 2
+        pooled = None
+        if features is not None:
+            pooled = torch.empty(d.n_out, B, D, dtype=torch.float32, device=self.device)
+            features["pooled"] = pooled
+            features["x_last"] = x_last.view(B, T, D)
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
                                           self.p("head.weight"), self.p("head.bias"),
                                           self.p("head_dist.weight") if two else None,
-                                          self.p("head_dist.bias") if two else None, d.n_out)
+                                          self.p("head_dist.bias") if two else None, d.n_out, pooled=pooled)
         if train:
             ws.head_saved = (xhat, rstd)
         return l0, l1

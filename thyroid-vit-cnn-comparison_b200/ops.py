@@ -177,7 +177,8 @@ def tokens_bwd(dx, dpos, dcls, ddist, dpatch16, dbias, n_prefix: int, unscale=No
 
 
 # --------------------------------------------------------------------------- heads
-def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5):
+def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5, pooled=None):
+    """pooled (optional, fp32 [n_heads,B,dim]) receives norm(x)[:, h] -- the reference's forward_features output."""
     _req(x, f32, "head x")
     B, T, dim = x.shape
     Cc = W0.shape[0]
@@ -186,8 +187,8 @@ def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5):
     xhat = torch.empty(n_heads, B, dim, dtype=f32, device=x.device)
     rstd = torch.empty(n_heads, B, dtype=f32, device=x.device)
     check(_lib.load().vitk_head_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), W0.data_ptr(), _p(b0), _p(W1), _p(b1),
-                                    logits0.data_ptr(), _p(logits1), xhat.data_ptr(), rstd.data_ptr(), B, T, dim, Cc, n_heads,
-                                    eps, _stream()), "head_fwd")
+                                    logits0.data_ptr(), _p(logits1), xhat.data_ptr(), rstd.data_ptr(), _p(pooled), B, T, dim, Cc,
+                                    n_heads, eps, _stream()), "head_fwd")
     return logits0, logits1, xhat, rstd
 
 

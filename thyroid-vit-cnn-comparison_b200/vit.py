@@ -273,12 +273,10 @@ class VisionTransformerBase(_Base):
             pass
 
     def _create_sinusoidal_embedding(self, num_positions: int, embed_dim: int) -> torch.Tensor:
-        position = torch.arange(num_positions).unsqueeze(1)
-        div_term = torch.exp(torch.arange(0, embed_dim, 2) * (-math.log(10000.0) / embed_dim))
-        pe = torch.zeros(1, num_positions, embed_dim)
-        pe[0, :, 0::2] = torch.sin(position * div_term)
-        pe[0, :, 1::2] = torch.cos(position * div_term)
-        return pe
+        """Fixed sin/cos table, interleaved (even columns sin, odd columns cos) -- vision_transformer_base.py:404-413."""
+        inv_freq = torch.exp(torch.arange(0, embed_dim, 2) * (-math.log(10000.0) / embed_dim))
+        angles = torch.outer(torch.arange(num_positions).float(), inv_freq)            # [positions, D/2]
+        return torch.stack((angles.sin(), angles.cos()), dim=-1).reshape(1, num_positions, embed_dim)
 
     def _init_weights(self):
         """trunc_normal(0.02) linears, unit LayerNorms, He-style patch conv (vision_transformer_base.py:415-438)."""
@@ -311,8 +309,6 @@ class VisionTransformerBase(_Base):
             raise NotImplementedError("the sm_100a path implements class-token pooling (pool_type='cls')")
         if not isinstance(self.pre_logits, nn.Identity):
             raise NotImplementedError("representation_size / pre_logits is not implemented in the sm_100a path")
-        if not isinstance(getattr(self, "pos_embed", None), nn.Parameter):
-            raise NotImplementedError("sinusoidal position embeddings are not implemented in the sm_100a path")
         if self.training and (hp.get("drop_rate", 0.0) or hp.get("attn_drop_rate", 0.0)):
             raise NotImplementedError("dropout / attention dropout > 0 are not implemented in the sm_100a training path "
                                       "(stochastic depth is; parity configuration uses 0, SURVEY.md section 7)")
@@ -321,8 +317,17 @@ class VisionTransformerBase(_Base):
         skip = ("patch_embed.quality_score",)
         return OrderedDict((n, p) for n, p in self.named_parameters() if not n.startswith(skip))
 
-    def _ensure_engine(self) -> VitEngine:
+    def _engine_tensors(self) -> "OrderedDict[str, torch.Tensor]":
+        """Everything that lives in the engine's flat buffer: the trainable parameters plus a fixed (sinusoidal)
+        `pos_embed` buffer, which gets a slot but never an optimizer group (its learning rate stays 0)."""
         named = self._engine_params()
+        pe = getattr(self, "pos_embed", None)
+        if pe is not None and not isinstance(pe, nn.Parameter):
+            named["pos_embed"] = pe
+        return named
+
+    def _ensure_engine(self) -> VitEngine:
+        named = self._engine_tensors()
         first = next(iter(named.values()))
         _require_cuda(first, type(self).__name__)
         key = (first.device, tuple((n, p.data_ptr()) for n, p in list(named.items())[:3]))
@@ -336,7 +341,8 @@ class VisionTransformerBase(_Base):
                             dtype16=self._vitk_hparams.get("compute_dtype", torch.float16))
             for n, p in named.items():        # re-point the module's parameters at the flat buffers
                 p.data = eng.flat.view(eng.flat.params, n)
-                p.grad = None
+                if isinstance(p, nn.Parameter):
+                    p.grad = None
             eng.set_drop_path([float(getattr(b.drop_path, "drop_prob", 0.0)) for b in self.blocks])
             self._engine = eng
             named = self._engine_params()
@@ -346,7 +352,7 @@ class VisionTransformerBase(_Base):
         return self._engine
 
     def _param_version(self) -> int:
-        return sum(p._version for p in self._engine_params().values())
+        return sum(p._version for p in self._engine_tensors().values())
 
     def _sync_shadow(self) -> None:
         """Re-cast the bf16 tensor-core shadow when a parameter was modified through torch (optimizer.step(),
@@ -396,9 +402,28 @@ class VisionTransformerBase(_Base):
         return (l0, l1) if l1 is not None else l0
 
     # ------------------------------------------------------------------ reference API
+    def _features(self, x: torch.Tensor) -> dict:
+        """Inference-only encoder pass that also returns the pre-head features (no autograd graph)."""
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("forward_features is inference-only in the sm_100a path (call it under "
+                                      "torch.no_grad() or model.eval()); training goes through forward()")
+        self._check_supported()
+        eng = self._ensure_engine()
+        _require_cuda(x, type(self).__name__)
+        self._sync_shadow()
+        probs = [] if (self.store_attention and not self.training) else None
+        feats: dict = {}
+        eng.forward(x, train=False, attn_probs=probs, features=feats)
+        if probs is not None:
+            self._attention_storage = probs
+            for blk, pm in zip(self.blocks, probs):
+                blk.attn.attention_maps = pm
+        return feats
+
     def forward_features(self, x: torch.Tensor):
-        raise NotImplementedError("forward_features (pre-head pooled features) is not exposed by the fused sm_100a head "
-                                  "kernel yet; use forward()")
+        """vision_transformer_base.py:440-479: (norm(x)[:, 0] as [B, D], quality_scores).  The quality branch is dead
+        code in the reference's forward (its scores never reach the tokens), so None is returned for it."""
+        return self._features(x)["pooled"][0], None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """vision_transformer_base.py:482-486."""
@@ -411,7 +436,8 @@ class VisionTransformerBase(_Base):
         return torch.stack([m.detach().cpu() for m in self._attention_storage])
 
     def extract_features(self, x: torch.Tensor) -> torch.Tensor:
-        return self.forward_features(x)
+        """vision_transformer_base.py:494-497."""
+        return self._features(x)["pooled"][0]
 
     def training_step(self, batch, batch_idx):
         from .training import fused_cross_entropy
@@ -630,6 +656,14 @@ class DeiT(VisionTransformer):
         """The reference's DeiT override forgets to fill the storage and returns None (SURVEY.md section 3.5);
         per-block `attn.attention_maps` is the documented access path and is populated.  We return the stack."""
         return super().get_attention_maps()
+
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        """deit_models.py:190-218: the normalised token sequence [B, T, D] (inference-only here)."""
+        x_last = self._features(x)["x_last"]
+        B, T, D = x_last.shape
+        y, _, _ = ops.layernorm_fwd(x_last.reshape(B * T, D), self.norm.weight.detach(), self.norm.bias.detach(),
+                                    dtype=self._engine.dt16)
+        return y.float().view(B, T, D)       # 16-bit rounding of the normalised tokens (operand precision of the path)
 
     def forward(self, x: torch.Tensor):
         """deit_models.py:220-238: (cls, dist) logits in training, their mean in eval."""
