@@ -132,6 +132,7 @@ def workload_config(args, cpu: bool = False):
                         f"batch {args.batch}/GPU, random-init weights",
             "model": args.model, "per_gpu_batch": args.batch, "global_batch": args.batch * max(1, args.gpus), "image": "3x224x224",
             "parallelism": f"dp{max(1, args.gpus)}", "mode": args.mode,
+            "drop_rate": args.drop_rate, "drop_path_rate": args.drop_path_rate,
             "l2": "no flush needed: the step's working set (activations > 3 GB) is far larger than the 126 MB L2"}
 
 
@@ -257,9 +258,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.manual_seed(42)
     if args.model == "deit_tiny":
-        model = vit.create_deit_tiny(img_size=224, patch_size=16, in_chans=3, num_classes=2, distilled=True)
+        model = vit.create_deit_tiny(img_size=224, patch_size=16, in_chans=3, num_classes=2, distilled=True,
+                                     drop_rate=args.drop_rate, drop_path_rate=args.drop_path_rate)
     else:
-        model = vit.create_vit_base(img_size=224, patch_size=16, in_chans=3, num_classes=2, drop_path_rate=0.0)
+        model = vit.create_vit_base(img_size=224, patch_size=16, in_chans=3, num_classes=2, drop_rate=args.drop_rate,
+                                    drop_path_rate=args.drop_path_rate)
     model = model.to(dev).train()
     opt = optim.FusedAdamW(model, lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
     teacher = None
@@ -439,6 +442,8 @@ def main():
     ap.add_argument("--dp-graph", action="store_true", help="(default) N > 1: the step, NCCL all-reduces included, is one CUDA graph")
     ap.add_argument("--dp-eager", action="store_true", help="N > 1: launch the step eagerly instead of replaying a captured graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--drop-rate", type=float, default=0.0, help="nn.Dropout rate (BASELINE.json's workload: 0)")
+    ap.add_argument("--drop-path-rate", type=float, default=0.0, help="stochastic depth rate (BASELINE.json's workload: 0)")
     ap.add_argument("--by-shape", action="store_true", help="split the GEMM rows of the kernel profile by shape")
     args = ap.parse_args()
     if args.impl == "reference":

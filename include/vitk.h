@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 8
+#define VITK_ABI_VERSION 9
 
 typedef enum {
   VITK_OK = 0,
@@ -67,6 +67,20 @@ typedef enum {
   VITK_EPI_ATOMIC_ADD = 3, /* out(fp32) += acc*alpha  (split-K wgrad, red.global.add.f32)     */
   VITK_EPI_TOKENS = 4      /* patch rows -> token rows: out[b, prefix+p, :] = acc+bias+pos    */
 } vitk_epilogue;
+
+/* nn.Dropout with drop_rate > 0 -- pos_drop (vision_transformer_base.py:371,452), Attention.proj_drop (:169,193),
+ * Mlp.drop after the activation and after fc2 (:213,219-222).  Masks are never stored: the keep/drop decision of element
+ * (row, col) of one Dropout call ("site") is a pure function of (*seed, site, row * cols + col) (Philox4x32-7, 16-bit
+ * uniforms, dropped when uniform < round(p * 65536), kept values scaled by 1/(1-p)), so the forward epilogue and the
+ * backward kernel that needs the same mask both recompute it.  `seed` is a DEVICE scalar the caller redraws every
+ * training step (a captured CUDA graph therefore draws fresh masks on every replay).  cols must be a multiple of 8. */
+typedef struct {
+  const uint64_t* seed; /* device pointer; NULL (or p == 0) disables the dropout */
+  float p;              /* drop probability, 0 <= p < 1 */
+  int32_t site;         /* any id that is unique per Dropout call within one step */
+} vitk_dropout;
+/* factors fp32 [rows, cols] = 0 or 1/(1-p): the mask the fused kernels derive for `drop` (tests / debugging). */
+int vitk_dropout_mask(const vitk_dropout* drop, float* factors, int64_t rows, int32_t cols, void* stream);
 
 typedef struct {
   const void* A;      /* bf16 */
@@ -103,6 +117,14 @@ typedef struct {
   /* VITK_EPI_STORE with an fp32 residual (optional): out = residual + row_scale[m] * (acc*alpha + bias), fp32 [M] --
    * the per-sample stochastic-depth factor floor(keep + u) / keep of DropPath (vision_transformer_base.py:56-64, :283-284). */
   const float* row_scale;
+  /* Optional dropout of the epilogue result (see vitk_dropout above; element index = out_row * N + col):
+   *   fp32 VITK_EPI_STORE with residual: out = residual + row_scale * mask * (acc*alpha + bias)   (proj_drop / Mlp.drop #2)
+   *   VITK_EPI_GELU: out = mask * gelu'(pre), out2 = mask * gelu(pre)   (Mlp.drop #1; the saved derivative carries the mask
+   *                  into the backward VITK_EPI_DGELU for free)
+   *   VITK_EPI_TOKENS: out = mask * (acc + bias + pos)   (pos_drop; vitk_prefix_tokens_fwd covers the cls/dist rows) */
+  const uint64_t* drop_seed;
+  float drop_p;
+  int32_t drop_site;
 } vitk_gemm_args;
 
 int vitk_gemm(const vitk_gemm_args* args, void* stream);
@@ -116,13 +138,16 @@ int vitk_gemm(const vitk_gemm_args* args, void* stream);
  *      that produced the residual branch feeding this LayerNorm's input.
  *      branch_scale (optional, fp32 [rows]): stochastic-depth factor of that residual branch; dx16 and dcolsum are the
  *      gradient ENTERING the branch, i.e. dx * branch_scale[row] (dx itself, the residual-stream gradient, is unscaled).
+ *      branch_drop (optional): the dropout applied to that branch's output in forward; dx16 / dcolsum are additionally
+ *      multiplied by its mask.
  * ------------------------------------------------------------------------------------------ */
 int vitk_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int32_t y_dtype,
                        float* mean, float* rstd, int64_t rows, int32_t dim, float eps, void* stream);
 int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* mean,
                        const float* rstd, const float* gamma, const float* dres, float* dx, void* dx16,
                        int32_t dx16_dtype, float* dgamma, float* dbeta, float* dcolsum,
-                       const float* grad_unscale, const float* branch_scale, int64_t rows, int32_t dim, void* stream);
+                       const float* grad_unscale, const float* branch_scale, const vitk_dropout* branch_drop,
+                       int64_t rows, int32_t dim, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused softmax attention, dh = 64 -- vision_transformer_base.py:174-191 (Attention.forward:
@@ -149,16 +174,17 @@ int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const
  * the flattening order of Conv2d.weight[D,C,P,P]) */
 int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, int32_t B, int32_t C,
                   int32_t H, int32_t W, int32_t P, void* stream);
-/* x[b, t, :] = tok_t + pos[t, :] for t < n_prefix (cls, dist) */
+/* x[b, t, :] = drop(tok_t + pos[t, :]) for t < n_prefix (cls, dist); drop = pos_drop (optional) */
 int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos,
                            int32_t B, int32_t tokens_per_img, int32_t dim, int32_t n_prefix,
-                           void* stream);
+                           const vitk_dropout* drop, void* stream);
 /* dpos[t,:] += u*sum_b dx[b,t,:] ; dcls += u*sum_b dx[b,0,:] ; ddist += u*sum_b dx[b,1,:]  (u = *grad_unscale or 1);
  * dpatch16 [B*rows_per_img, dim] = 16-bit copy of dx[b, n_prefix+p, :] (the dY of the patch GEMM, still scaled);
- * dbias_patch[dim] += u * column sum over patch rows. */
+ * dbias_patch[dim] += u * column sum over patch rows.  With `drop` (pos_drop) every dx element is first multiplied by the
+ * mask the forward applied to that token element. */
 int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch16,
                     int32_t dpatch_dtype, float* dbias_patch, const float* grad_unscale, int32_t B,
-                    int32_t tokens_per_img, int32_t dim, int32_t n_prefix, void* stream);
+                    int32_t tokens_per_img, int32_t dim, int32_t n_prefix, const vitk_dropout* drop, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Final norm + classification heads on the pooled rows only --
@@ -178,8 +204,8 @@ int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xha
                   const float* rstd, const float* gamma, const float* beta, const float* W0,
                   const float* W1, float* dx, void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta,
                   float* dW0, float* db0, float* dW1, float* db1, float* dcolsum,
-                  const float* loss_scale, const float* branch_scale, int32_t B, int32_t tokens_per_img, int32_t dim,
-                  int32_t C, int32_t n_heads, void* stream);
+                  const float* loss_scale, const float* branch_scale, const vitk_dropout* branch_drop, int32_t B,
+                  int32_t tokens_per_img, int32_t dim, int32_t C, int32_t n_heads, void* stream);
 
 /* Stochastic depth (DropPath.forward, vision_transformer_base.py:56-64): scale[br, b*T + t] = floor(keep + u[br,b]) / keep
  * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */

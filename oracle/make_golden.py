@@ -10,6 +10,9 @@ Fixtures
                                  after one clip+AdamW step, eval-mode logits, attention maps of layer 0.
   deit_tiny_b4.pt / vit_base_b2.pt  full-size models: logits, loss, per-parameter gradient norm and the
                                  gradient's projection on a seeded random direction (compact but sensitive).
+  small_vit_dropout.pt           ViT (embed 128, 2 heads, depth 2) with drop_rate = 0.1 in training mode: the keep masks every
+                                 nn.Dropout call drew (forward hooks, site order pos_drop, then per block proj_drop, Mlp.drop #1,
+                                 Mlp.drop #2), logits, loss, full gradients -- pins WHERE the reference applies dropout.
   param_groups_deit_tiny.json    get_parameter_groups() table (name, weight_decay, lr_scale) + named_parameters order.
   distill_loss.pt                DistillationLoss / training_step arithmetic on random logits.
   kfold_splits_7.json            the reference's committed data/splits/split_fold_{1..7}.json (known-answer vectors).
@@ -94,12 +97,49 @@ def run_case(cfg: O.VitConfig, batch: int, seed: int, full: bool):
     return rec
 
 
+DROP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=128, depth=2, num_heads=2, distilled=False, is_deit=False)
+
+
+def run_dropout_case(cfg: O.VitConfig, batch: int, seed: int, drop_rate: float):
+    base, vitm, deit = ref_loader.load()
+    kw = dict(img_size=cfg.img_size, patch_size=cfg.patch_size, in_chans=cfg.in_chans, num_classes=cfg.num_classes,
+              embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio)
+    model = vitm.VisionTransformer(drop_path_rate=0.0, drop_rate=drop_rate, **kw)
+    sd = O.seeded_state_dict(cfg, seed)
+    model.load_state_dict(sd, strict=True)
+    calls = {}
+
+    def hook(name):
+        def fn(mod, inp, out):
+            assert inp[0].ne(0).all()                 # so `out != 0` is exactly the keep mask
+            calls.setdefault(name, []).append(out.detach().ne(0).to(torch.uint8))
+        return fn
+    model.pos_drop.register_forward_hook(hook("pos"))
+    for i, blk in enumerate(model.blocks):
+        blk.attn.proj_drop.register_forward_hook(hook(f"proj{i}"))
+        blk.mlp.drop.register_forward_hook(hook(f"mlp{i}"))
+    x, y = O.seeded_batch(cfg, batch, seed)
+    torch.manual_seed(seed)
+    model.train()
+    out = model(x)
+    loss = F.cross_entropy(out, y)
+    loss.backward()
+    masks = [calls["pos"][0]]
+    for i in range(cfg.depth):
+        assert len(calls[f"proj{i}"]) == 1 and len(calls[f"mlp{i}"]) == 2
+        masks += [calls[f"proj{i}"][0], calls[f"mlp{i}"][0], calls[f"mlp{i}"][1]]
+    return {"config": cfg.__dict__, "batch": batch, "seed": seed, "drop_rate": drop_rate, "keep_masks": masks,
+            "loss": loss.item(), "logits": out.detach().clone(),
+            "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}}
+
+
 def main():
     assert ref_loader.available(), "run this where /root/reference is mounted"
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     torch.save(run_case(SMALL_DEIT, 3, 42, True), GOLD / "small_deit.pt")
     torch.save(run_case(SMALL_VIT, 2, 43, True), GOLD / "small_vit.pt")
+    torch.save(run_dropout_case(DROP_VIT, 4, 44, 0.1), GOLD / "small_vit_dropout.pt")
     torch.save(run_case(O.DEIT_TINY, 4, 42, False), GOLD / "deit_tiny_b4.pt")
     torch.save(run_case(O.VIT_BASE, 2, 42, False), GOLD / "vit_base_b2.pt")
 

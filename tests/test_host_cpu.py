@@ -122,9 +122,12 @@ def test_unsupported_options_fail_loudly():
     m = vit.create_vit_tiny(img_size=64, in_chans=3)           # factory default drop_path_rate=0.1: stochastic depth is
     m.train()                                                  # served by the engine (GPU test test_stochastic_depth_*)
     m._check_supported()
-    m = vit.create_vit_tiny(img_size=64, in_chans=3, drop_rate=0.1)
+    m = vit.create_vit_tiny(img_size=64, in_chans=3, drop_rate=0.1)   # vit_base.yaml / vit_small.yaml: fused dropout
+    m.train()                                                         # (GPU test test_dropout_training_step_*)
+    m._check_supported()
+    m = vit.create_vit_tiny(img_size=64, in_chans=3, attn_drop_rate=0.1)
     m.train()
-    with pytest.raises(NotImplementedError):                   # dropout on activations / attention probabilities is not
+    with pytest.raises(NotImplementedError):                   # dropout on attention probabilities is not
         m._check_supported()
     m.eval()
     m._check_supported()                                       # identity in eval

@@ -473,3 +473,152 @@ def test_ensemble_and_rollout():
             R = a @ R
         torch.cuda.synchronize()
         assert (r - R).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------ nn.Dropout (drop_rate > 0): counter-based masks
+def _seed(v: int):
+    return torch.tensor([v], dtype=torch.int64, device=DEV)
+
+
+def test_dropout_mask_is_a_pure_function_of_seed_and_site():
+    s1, s2 = _seed(1234567), _seed(1234568)
+    m = ops.dropout_mask(s1, 0.1, 3, 5000, 192)
+    assert torch.equal(m, ops.dropout_mask(s1, 0.1, 3, 5000, 192))                    # deterministic
+    vals = set(m.unique().tolist())
+    assert len(vals) == 2 and 0.0 in vals and abs(max(vals) - 1 / 0.9) < 1e-6        # 0 or 1/(1-p)
+    assert abs((m == 0).float().mean().item() - 0.1) < 3e-3                          # ~1M draws
+    for other in (ops.dropout_mask(s2, 0.1, 3, 5000, 192), ops.dropout_mask(s1, 0.1, 4, 5000, 192)):
+        agree = ((other == 0) == (m == 0)).float().mean().item()                     # independent masks agree on 0.82 of elements
+        assert abs(agree - 0.82) < 5e-3
+    # a row-major [rows, cols] view of the element counter: the same elements for a different column count
+    assert torch.equal(m.view(-1), ops.dropout_mask(s1, 0.1, 3, 1250, 768).view(-1))
+    # no visible structure along rows or columns
+    dropped = (m == 0).float()
+    assert (dropped.mean(0) - 0.1).abs().max().item() < 0.03 and (dropped.mean(1) - 0.1).abs().max().item() < 0.12
+    assert torch.equal(ops.dropout_mask(s1, 0.0, 3, 64, 64), torch.ones(64, 64, device=DEV))
+    for p in (0.05, 0.5, 0.9):
+        assert abs((ops.dropout_mask(s1, p, 0, 4096, 256) == 0).float().mean().item() - p) < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(6336, 192, 192), (1000, 768, 3072)])
+def test_gemm_residual_dropout(M, N, K):
+    """out = residual + row_scale * mask * (A W^T + bias): proj_drop / Mlp.drop fused into the residual epilogue."""
+    A = _rand(M, K, dtype=F16, seed=1)
+    W = _rand(N, K, scale=0.05, dtype=F16, seed=2)
+    bias, res = _rand(N, seed=3), _rand(M, N, seed=4)
+    seed = _seed(99)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, M, N, K, out=out, bias=bias, residual=res, drop=(seed, 0.1, 7))
+    mask = ops.dropout_mask(seed, 0.1, 7, M, N)
+    ref = res + mask * (A.float() @ W.float().t() + bias)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 1e-5
+    assert torch.equal(out[mask == 0], res[mask == 0])
+    rs = (torch.floor(0.7 + torch.rand(M, device=DEV)) / 0.7)
+    ops.gemm(A, W, M, N, K, out=out, bias=bias, residual=res, row_scale=rs, drop=(seed, 0.25, 8))
+    ref = res + rs[:, None] * ops.dropout_mask(seed, 0.25, 8, M, N) * (A.float() @ W.float().t() + bias)
+    assert rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("M,N,K", [(6336, 768, 192), (777, 3072, 768)])
+def test_gemm_gelu_dropout(M, N, K, dt):
+    """Mlp.drop after the activation: out2 = mask * gelu(pre) and the saved derivative out = mask * gelu'(pre)."""
+    A = _rand(M, K, dtype=dt, seed=1)
+    W = _rand(N, K, scale=0.1, dtype=dt, seed=2)
+    bias = _rand(N, seed=3)
+    seed = _seed(5)
+    dact = torch.empty(M, N, dtype=dt, device=DEV)
+    act = torch.empty(M, N, dtype=dt, device=DEV)
+    ops.gemm(A, W, M, N, K, out=dact, out2=act, bias=bias, epilogue=_lib.EPI_GELU, drop=(seed, 0.1, 2))
+    mask = ops.dropout_mask(seed, 0.1, 2, M, N)
+    pre = (A.float() @ W.float().t() + bias).requires_grad_(True)
+    ref_act = torch.nn.functional.gelu(pre) * mask
+    ref_act.sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(act, ref_act) < OUT_TOL[dt] and rel_l2(dact, pre.grad) < OUT_TOL[dt]
+    assert act[mask == 0].abs().max().item() == 0 and dact[mask == 0].abs().max().item() == 0
+
+
+def test_tokens_dropout_fwd_bwd():
+    """pos_drop over the assembled token matrix: patch rows in the GEMM epilogue, cls/dist rows in the prefix kernel,
+    and the same mask on the gradient in the token-assembly backward."""
+    B, P, T, prefix, D, K = 5, 196, 198, 2, 192, 768
+    A = _rand(B * P, K, dtype=F16, seed=1)
+    W = _rand(D, K, scale=0.05, dtype=F16, seed=2)
+    bias, pos = _rand(D, seed=3), _rand(T, D, seed=4)
+    cls, dist = _rand(D, seed=5), _rand(D, seed=6)
+    seed = _seed(31)
+    x = torch.zeros(B, T, D, dtype=torch.float32, device=DEV)
+    ops.gemm(A, W, B * P, D, K, out=x, bias=bias, epilogue=_lib.EPI_TOKENS, tokens=(P, T, prefix), pos=pos, drop=(seed, 0.2, 0))
+    ops.prefix_tokens_fwd(x, cls, dist, pos, prefix, drop=(seed, 0.2, 0))
+    mask = ops.dropout_mask(seed, 0.2, 0, B * T, D).view(B, T, D)
+    ref = torch.empty_like(x)
+    ref[:, prefix:] = (A.float() @ W.float().t() + bias).view(B, P, D) + pos[prefix:]
+    ref[:, 0] = cls + pos[0]
+    ref[:, 1] = dist + pos[1]
+    ref = ref * mask
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 1e-3 and x[mask == 0].abs().max().item() == 0
+    dx = _rand(B, T, D, seed=7)
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    dpos, dcls, ddist, dbias = z(T, D), z(D), z(D), z(D)
+    dpatch = torch.empty(B * P, D, dtype=F16, device=DEV)
+    ops.tokens_bwd(dx, dpos, dcls, ddist, dpatch, dbias, prefix, drop=(seed, 0.2, 0))
+    g = dx * mask
+    torch.cuda.synchronize()
+    assert rel_l2(dpos, g.sum(0)) < 1e-5 and rel_l2(dcls, g[:, 0].sum(0)) < 1e-5 and rel_l2(ddist, g[:, 1].sum(0)) < 1e-5
+    assert rel_l2(dbias, g[:, prefix:].sum((0, 1))) < 1e-5
+    assert rel_l2(dpatch.float(), g[:, prefix:].reshape(B * P, D)) < 1e-3
+
+
+@pytest.mark.parametrize("rows,dim", [(6336, 192), (197 * 3, 768), (333, 256)])
+def test_layernorm_bwd_branch_dropout(rows, dim):
+    """dx16 / dcolsum = dx * branch_scale * dropout mask of the branch below; the fp32 residual-stream dx is untouched."""
+    x = _rand(rows, dim, seed=1)
+    gamma = _rand(dim, seed=2) * 0.1 + 1
+    beta = _rand(dim, seed=3) * 0.1
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
+    dy = _rand(rows, dim, dtype=F16, seed=4)
+    dres = _rand(rows, dim, seed=5)
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    seed = _seed(77)
+    outs = []
+    for drop in (None, (seed, 0.1, 11)):
+        dg, db, dcs = z(dim), z(dim), z(dim)
+        dx16 = torch.empty(rows, dim, dtype=F16, device=DEV)
+        bs = torch.floor(0.8 + torch.rand(rows, generator=torch.Generator().manual_seed(1))).to(DEV) / 0.8
+        dx = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg, db, dres=dres, dx16=dx16, dcolsum=dcs, branch_scale=bs,
+                               branch_drop=drop)
+        outs.append((dx.clone(), dx16.float(), dcs, dg, db, bs))
+    mask = ops.dropout_mask(seed, 0.1, 11, rows, dim)
+    (dx0, h0, c0, g0, b0, bs), (dx1, h1, c1, g1, b1, _) = outs
+    torch.cuda.synchronize()
+    assert rel_l2(g0, g1) < 1e-5 and rel_l2(b0, b1) < 1e-5       # dgamma / dbeta do not see the branch mask
+    assert torch.equal(dx0, dx1)
+    ref16 = dx0 * bs[:, None] * mask
+    assert rel_l2(h1, ref16) < 1e-3 and h1[mask == 0].abs().max().item() == 0
+    assert rel_l2(c1, ref16.sum(0)) < 1e-4
+
+
+def test_head_bwd_branch_dropout():
+    B, T, D, C = 19, 198, 192, 2
+    x = _rand(B, T, D, seed=1)
+    g = _rand(D, seed=2) * 0.1 + 1; b = _rand(D, seed=3) * 0.1
+    W0 = _rand(C, D, scale=0.02, seed=4); b0 = _rand(C, seed=5) * 0.1
+    l0, _, xhat, rstd = ops.head_fwd(x, g, b, W0, b0, None, None, 1)
+    dl0 = _rand(B, C, seed=8)
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    seed = _seed(3)
+    res = []
+    for drop in (None, (seed, 0.3, 6)):
+        dx = torch.empty(B, T, D, device=DEV); dx16 = torch.empty(B, T, D, dtype=F16, device=DEV)
+        dcs = z(D)
+        ops.head_bwd(dl0, None, xhat, rstd, g, b, W0, None, dx, dx16, z(D), z(D), z(C, D), z(C), None, None, dcs, T, 1,
+                     branch_drop=drop)
+        res.append((dx.clone(), dx16.float(), dcs))
+    mask = ops.dropout_mask(seed, 0.3, 6, B * T, D).view(B, T, D)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][0], res[1][0])
+    assert rel_l2(res[1][1], res[0][0] * mask) < 1e-3
+    assert rel_l2(res[1][2], (res[0][0] * mask).sum((0, 1))) < 1e-4

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import thyroid_vit_cnn_comparison_b200 as tv  # noqa: E402
-from thyroid_vit_cnn_comparison_b200 import vit as V, training as TR, optim as OPT  # noqa: E402
+from thyroid_vit_cnn_comparison_b200 import vit as V, training as TR, optim as OPT, ops  # noqa: E402
 from oracle import vit_oracle as O  # noqa: E402
 
 GOLD = ROOT / "tests" / "golden"
@@ -391,3 +391,74 @@ def test_forward_features_matches_oracle(name):
     model.train()
     with pytest.raises(NotImplementedError):
         model.forward_features(x.cuda())                                     # training goes through forward()
+
+
+def _gpu_drop_masks(m, B):
+    """The masks the kernels derived for the engine's current seed, in the oracle's site order."""
+    eng = m._engine
+    d = eng.d
+    M = B * d.tokens
+    cols = [d.dim] + [d.dim, d.hidden, d.dim] * d.depth
+    return [ops.dropout_mask(eng.drop_seed, eng.drop_rate, site, M, c).view(B, d.tokens, c).cpu() for site, c in enumerate(cols)]
+
+
+@pytest.mark.parametrize("deit", [False, True])
+def test_dropout_training_step_matches_oracle_with_replayed_masks(deit):
+    """drop_rate > 0 (configs/model/vit/vit_base.yaml, vit_small.yaml: 0.1): pos_drop, proj_drop and both Mlp.drop calls are
+    fused into the GEMM epilogues and re-derived in backward.  The masks the GPU drew are replayed into the oracle (whose
+    dropout placement is pinned to the reference by tests/golden/small_vit_dropout.pt)."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=3, num_heads=2, is_deit=deit, distilled=deit)
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=3, num_heads=2, mlp_ratio=4.0)
+    m = V.DeiT(distilled=True, drop_rate=0.2, **kw) if deit else V.VisionTransformer(drop_rate=0.2, drop_path_rate=0.2, **kw)
+    sd = O.seeded_state_dict(cfg, 9)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    B = 16
+    x, y = O.seeded_batch(cfg, B, 9)
+    torch.manual_seed(5)
+    loss, outs, grads = run_gpu(m, x, y)
+    masks = _gpu_drop_masks(m, B)
+    for mk in masks:
+        assert abs((mk == 0).float().mean().item() - 0.2) < 0.02
+    scales = m._engine.last_drop_scale.cpu().clone() if not deit else None
+    ref_loss, ref_out, ref_grads = O.train_step(sd, x, y, cfg, drop_scales=scales, drop_masks=masks)
+    ref_outs = ref_out if isinstance(ref_out, tuple) else (ref_out,)
+    for o, r in zip(outs, ref_outs):
+        assert (o - r).abs().max().item() < LOGIT_TOL
+    assert abs(loss - ref_loss.item()) < 2e-3
+    for n, g in ref_grads.items():
+        if g is None or "quality_score" in n:
+            continue
+        assert rel_l2(grads[n], g) < GRAD_TOL, (n, rel_l2(grads[n], g))
+    # a second step draws different masks; eval mode is the identity
+    first = masks[1].clone()
+    run_gpu(m, x, y)
+    assert not torch.equal(_gpu_drop_masks(m, B)[1], first)
+    m.eval()
+    with torch.no_grad():
+        e = m(x.cuda()).cpu()
+    assert (e - O.forward(sd, x, cfg, training=False)).abs().max().item() < LOGIT_TOL
+
+
+def test_dropout_inside_captured_graph_draws_fresh_masks():
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.0)
+    m = V.VisionTransformer(drop_rate=0.1, **kw).cuda().train()
+    opt = OPT.FusedAdamW(m, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    step = TR.TrainStep(m, opt, 32, mode="ce", use_graph=True)
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2, is_deit=False, distilled=False)
+    x, y = O.seeded_batch(cfg, 32, 1)
+    seeds, stats = [], []
+    for _ in range(6):
+        st = step(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        seeds.append(int(m._engine.drop_seed.item()))
+        stats.append(st.detach().cpu().clone())
+    assert len(set(seeds)) == len(seeds), seeds            # every replay redraws the device seed
+    assert all(torch.isfinite(s).all() for s in stats)
+
+
+def test_attention_dropout_still_fails_loudly():
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=1, num_heads=2, mlp_ratio=4.0)
+    m = V.VisionTransformer(attn_drop_rate=0.1, **kw).cuda().train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(2, 3, 64, 64, device="cuda"))

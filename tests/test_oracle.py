@@ -151,3 +151,23 @@ def test_oracle_vs_live_reference_default_init():
     vit.train()
     assert (O.forward(pv, x, cfgv) - vit(x)).abs().max().item() < 1e-6
     assert list(O.param_shapes(cfgv)) == [n for n, _ in vit.named_parameters()]
+
+
+def test_oracle_dropout_sites_match_reference_with_replayed_masks():
+    """drop_rate = 0.1: the fixture holds the keep masks every nn.Dropout call of the REFERENCE drew (pos_drop, proj_drop,
+    Mlp.drop twice per block); replaying them must reproduce the reference's logits, loss and gradients exactly."""
+    rec = torch.load(GOLD / "small_vit_dropout.pt", weights_only=False)
+    cfg = _cfg(rec["config"])
+    assert len(rec["keep_masks"]) == 1 + 3 * cfg.depth
+    sd = O.seeded_state_dict(cfg, rec["seed"])
+    x, y = O.seeded_batch(cfg, rec["batch"], rec["seed"])
+    masks = [m.float() / (1.0 - rec["drop_rate"]) for m in rec["keep_masks"]]
+    loss, out, grads = O.train_step(sd, x, y, cfg, drop_masks=masks)
+    assert abs(loss.item() - rec["loss"]) < 1e-6
+    assert (out - rec["logits"]).abs().max().item() < 1e-5
+    for n, g in rec["grads"].items():
+        assert _rel(grads[n], g) < 1e-5, n
+    # moving a mask to the wrong site must be visible (the test has teeth)
+    wrong = list(masks)
+    wrong[1], wrong[3] = wrong[3], wrong[1]
+    assert (O.forward(sd, x, cfg, drop_masks=wrong) - rec["logits"]).abs().max().item() > 1e-4

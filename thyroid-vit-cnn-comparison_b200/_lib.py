@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -36,7 +36,13 @@ class GemmArgs(C.Structure):
         ("pos", c_void_p),
         ("colsum_out", c_void_p),
         ("row_scale", c_void_p),
+        ("drop_seed", c_void_p), ("drop_p", c_float), ("drop_site", c_int),
     ]
+
+
+class Dropout(C.Structure):
+    """vitk_dropout: (device seed pointer, drop probability, site id)."""
+    _fields_ = [("seed", c_void_p), ("p", c_float), ("site", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/vitk.h declares
@@ -47,14 +53,15 @@ SIGNATURES = {
     "vitk_reset_launch_count": (None, []),
     "vitk_gemm": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "vitk_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 2 + [c_int64, c_int, c_float, c_void_p]),
-    "vitk_layernorm_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 7 + [c_int] + [c_void_p] * 5 + [c_int64, c_int, c_void_p]),
+    "vitk_layernorm_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 7 + [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_void_p]),
     "vitk_attention_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vitk_attention_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]),
     "vitk_patchify": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
-    "vitk_prefix_tokens_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
-    "vitk_tokens_bwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 4 + [c_void_p]),
+    "vitk_prefix_tokens_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "vitk_tokens_bwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
     "vitk_head_fwd": (c_int, [c_void_p] * 12 + [c_int] * 5 + [c_float, c_void_p]),
-    "vitk_head_bwd": (c_int, [c_void_p] * 10 + [c_int] + [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
+    "vitk_head_bwd": (c_int, [c_void_p] * 10 + [c_int] + [c_void_p] * 10 + [c_int] * 5 + [c_void_p]),
+    "vitk_dropout_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vitk_droppath_scale": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
     "vitk_loss_fwd_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int] + [c_float] * 5 + [c_void_p]),
     "vitk_grad_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

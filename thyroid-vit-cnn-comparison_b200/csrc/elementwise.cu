@@ -111,17 +111,22 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
 
 // ------------------------------------------------------------------ cls / dist token rows
 __global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls_tok, const float* __restrict__ dist_tok,
-                                     const float* __restrict__ pos, int B, int T, int dim, int n_prefix) {
+                                     const float* __restrict__ pos, int B, int T, int dim, int n_prefix, DropSpec drop) {
   const int dv = dim >> 2;
   const long long total = (long long)B * n_prefix * dv;
+  const unsigned long long dseed = drop.seed != nullptr ? __ldg(drop.seed) : 0ull;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = int(i % dv);
     const int t = int((i / dv) % n_prefix);
     const int b = int(i / ((long long)dv * n_prefix));
     const float4 tk = ldg_f4((t == 0 ? cls_tok : dist_tok) + 4 * v);
     const float4 ps = ldg_f4(pos + (long long)t * dim + 4 * v);
-    *reinterpret_cast<float4*>(x + ((long long)b * T + t) * dim + 4 * v) =
-        make_float4(tk.x + ps.x, tk.y + ps.y, tk.z + ps.z, tk.w + ps.w);
+    float4 o = make_float4(tk.x + ps.x, tk.y + ps.y, tk.z + ps.z, tk.w + ps.w);
+    if (drop.seed != nullptr) {   // pos_drop (vision_transformer_base.py:452): same site / indexing as the patch-token epilogue
+      const float4 m = drop_factors4(drop, dseed, (((unsigned long long)b * T + t) * dim + 4 * v) >> 2);
+      o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+    }
+    *reinterpret_cast<float4*>(x + ((long long)b * T + t) * dim + 4 * v) = o;
   }
 }
 
@@ -130,8 +135,9 @@ __global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restr
 constexpr int TOK_IMGS = 32;
 __global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, float* __restrict__ dcls,
                                   float* __restrict__ ddist, bf16* __restrict__ dpatch, int fp16, float* __restrict__ dbias,
-                                  const float* __restrict__ unscale, int B, int T, int dim, int n_prefix) {
+                                  const float* __restrict__ unscale, int B, int T, int dim, int n_prefix, DropSpec drop) {
   const float u = unscale != nullptr ? __ldg(unscale) : 1.f;
+  const unsigned long long dseed = drop.seed != nullptr ? __ldg(drop.seed) : 0ull;
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * TOK_IMGS;
   const int b1 = min(B, b0 + TOK_IMGS);
@@ -139,7 +145,11 @@ __global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restric
   for (int v = threadIdx.x; v < (dim >> 2); v += blockDim.x) {
     float4 acc = make_float4(0, 0, 0, 0);
     for (int b = b0; b < b1; ++b) {
-      const float4 g = ldg_f4(dx + ((long long)b * T + t) * dim + 4 * v);
+      float4 g = ldg_f4(dx + ((long long)b * T + t) * dim + 4 * v);
+      if (drop.seed != nullptr) {   // gradient through pos_drop: the mask the forward applied to this token element
+        const float4 m = drop_factors4(drop, dseed, (((unsigned long long)b * T + t) * dim + 4 * v) >> 2);
+        g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+      }
       acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
       if (t >= n_prefix && dpatch != nullptr)
         *reinterpret_cast<uint2*>(dpatch + ((long long)b * rows_per_img + (t - n_prefix)) * dim + 4 * v) =
@@ -206,8 +216,9 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __re
                                 const float* __restrict__ W1, float* __restrict__ dx, bf16* __restrict__ dx16, int fp16,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ db0,
                                 float* __restrict__ db1, float* __restrict__ dcolsum, const float* __restrict__ loss_scale,
-                                const float* __restrict__ branch_scale, int B, int T, int dim, int C, int n_heads) {
+                                const float* __restrict__ branch_scale, DropSpec drop, int B, int T, int dim, int C, int n_heads) {
   const float S = loss_scale != nullptr ? __ldg(loss_scale) : 1.f;
+  const unsigned long long dseed = drop.seed != nullptr ? __ldg(drop.seed) : 0ull;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * n_heads) return;
@@ -237,7 +248,14 @@ __global__ void head_bwd_kernel(const float* __restrict__ dl0, const float* __re
     const float g = dxn * gamma[i];
     const float o = rs * (g - m1 - xh[i] * m2);
     dxr[i] = o * S;
-    const float ob = o * bs;   // gradient entering the last MLP branch (stochastic depth)
+    float ob = o * bs;   // gradient entering the last MLP branch (stochastic depth, then that branch's dropout mask)
+    if (drop.seed != nullptr) {
+      const unsigned long long e = ((unsigned long long)b * T + hd) * dim + i;
+      const uint4 bits = drop_bits8(dseed, drop.site, e >> 3);
+      const int j = int(e & 7);
+      const uint32_t w = j < 2 ? bits.x : j < 4 ? bits.y : j < 6 ? bits.z : bits.w;
+      ob *= (((j & 1) ? (w >> 16) : (w & 0xffffu)) >= drop.thresh) ? drop.inv_keep : 0.f;
+    }
     if (dx16 != nullptr) {
       if (fp16) reinterpret_cast<__half*>(dx16)[((long long)b * T + hd) * dim + i] = __float2half_rn(ob * S);
       else dx16[((long long)b * T + hd) * dim + i] = __float2bfloat16(ob * S);
@@ -273,6 +291,13 @@ __global__ void head_wgrad_kernel(const float* __restrict__ dl0, const float* __
 // ------------------------------------------------------------------ stochastic depth (DropPath, vision_transformer_base.py:56-64)
 // scale[br, b*T + t] = floor(keep + u[br, b]) / keep, keep = 1 - drop_prob[br]: one Bernoulli draw per (branch, sample),
 // expanded to the token rows so that GEMM epilogues / LayerNorm backward read one float per row
+// factors[r, c] = 0 or 1/(1-p): the mask every fused kernel derives for (seed, site) -- exported for tests / debugging
+__global__ void dropout_mask_kernel(float* __restrict__ factors, long long n4, DropSpec drop) {
+  const unsigned long long dseed = __ldg(drop.seed);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    *reinterpret_cast<float4*>(factors + 4 * i) = drop_factors4(drop, dseed, (unsigned long long)i);
+}
+
 __global__ void droppath_scale_kernel(const float* __restrict__ u, const float* __restrict__ drop_prob, float* __restrict__ scale,
                                       int branches, int B, int T) {
   const long long total = (long long)branches * B * T;
@@ -404,29 +429,39 @@ extern "C" int vitk_patchify(const float* images, void* patches, int32_t patches
   return VITK_OK;
 }
 
+static DropSpec spec_of(const vitk_dropout* d) {
+  return d != nullptr ? make_drop_spec(d->seed, d->p, d->site) : make_drop_spec(nullptr, 0.f, 0);
+}
+#define VITK_CHECK_DROP(d, spec, dim, who) \
+  VITK_CHECK_ARG((spec).seed == nullptr || ((d)->p < 1.f && (dim) % 8 == 0), who ": dropout needs p < 1 and dim %% 8 == 0")
+
 extern "C" int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos, int32_t B,
-                                      int32_t T, int32_t dim, int32_t n_prefix, void* stream) {
+                                      int32_t T, int32_t dim, int32_t n_prefix, const vitk_dropout* drop, void* stream) {
   VITK_CHECK_ARG(x && pos && dim % 4 == 0 && n_prefix >= 0 && n_prefix <= 2, "vitk_prefix_tokens_fwd: bad args");
+  const DropSpec ds = spec_of(drop);
+  VITK_CHECK_DROP(drop, ds, dim, "vitk_prefix_tokens_fwd");
   if (n_prefix == 0) return VITK_OK;
   VITK_CHECK_ARG(cls_tok && (n_prefix < 2 || dist_tok), "vitk_prefix_tokens_fwd: missing token");
   const long long total = (long long)B * n_prefix * (dim / 4);
   prefix_tokens_kernel<<<capped_grid(total, 256, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cls_tok, dist_tok, pos, B, T,
-                                                                                                      dim, n_prefix);
+                                                                                                      dim, n_prefix, ds);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
 extern "C" int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch16, int32_t dpatch_dtype,
                                float* dbias_patch, const float* grad_unscale, int32_t B, int32_t T, int32_t dim,
-                               int32_t n_prefix, void* stream) {
+                               int32_t n_prefix, const vitk_dropout* drop, void* stream) {
   VITK_CHECK_ARG(dx && dim % 4 == 0 && n_prefix >= 0 && n_prefix <= 2 && T > n_prefix, "vitk_tokens_bwd: bad args");
+  const DropSpec ds = spec_of(drop);
+  VITK_CHECK_DROP(drop, ds, dim, "vitk_tokens_bwd");
   int threads = dim / 4;
   if (threads > 256) threads = 256;
   threads = ((threads + 31) / 32) * 32;
   dim3 grid(T, (B + TOK_IMGS - 1) / TOK_IMGS);
   tokens_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       dx, dpos, dcls, ddist, reinterpret_cast<bf16*>(dpatch16), int(dpatch_dtype == VITK_FP16), dbias_patch, grad_unscale, B, T,
-      dim, n_prefix);
+      dim, n_prefix, ds);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -447,9 +482,12 @@ extern "C" int vitk_head_fwd(const float* x, const float* gamma, const float* be
 extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xhat, const float* rstd,
                              const float* gamma, const float* beta, const float* W0, const float* W1, float* dx,
                              void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta, float* dW0, float* db0, float* dW1,
-                             float* db1, float* dcolsum, const float* loss_scale, const float* branch_scale, int32_t B, int32_t T,
-                             int32_t dim, int32_t C, int32_t n_heads, void* stream) {
+                             float* db1, float* dcolsum, const float* loss_scale, const float* branch_scale,
+                             const vitk_dropout* branch_drop, int32_t B, int32_t T, int32_t dim, int32_t C, int32_t n_heads,
+                             void* stream) {
   VITK_CHECK_ARG(dlogits0 && xhat && rstd && gamma && beta && W0 && dx && dgamma && dbeta && dW0, "vitk_head_bwd: null pointer");
+  const DropSpec ds = spec_of(branch_drop);
+  VITK_CHECK_DROP(branch_drop, ds, dim, "vitk_head_bwd");
   VITK_CHECK_ARG(n_heads == 1 || (n_heads == 2 && dlogits1 && W1 && dW1), "vitk_head_bwd: n_heads must be 1 or 2");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VITK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * T * dim * sizeof(float), st));
@@ -457,11 +495,22 @@ extern "C" int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const
   const int warps = B * n_heads;
   head_bwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(dlogits0, dlogits1, xhat, rstd, gamma, W0, W1, dx,
                                                    reinterpret_cast<bf16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, db0,
-                                                   db1, dcolsum, loss_scale, branch_scale, B, T, dim, C, n_heads);
+                                                   db1, dcolsum, loss_scale, branch_scale, ds, B, T, dim, C, n_heads);
   VITK_LAUNCH_CHECK();
   const long long total = (long long)n_heads * C * dim;
   head_wgrad_kernel<<<dim3(capped_grid(total, 128, 4), (B + 15) / 16), 128, 0, st>>>(dlogits0, dlogits1, xhat, gamma, beta, dW0, dW1,
                                                                                     B, dim, C, n_heads);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_dropout_mask(const vitk_dropout* drop, float* factors, int64_t rows, int32_t cols, void* stream) {
+  VITK_CHECK_ARG(drop && drop->seed && factors && rows > 0 && cols > 0 && cols % 8 == 0 && drop->p >= 0.f && drop->p < 1.f,
+                 "vitk_dropout_mask: bad args (cols %% 8 == 0, 0 <= p < 1)");
+  DropSpec ds = make_drop_spec(drop->seed, drop->p, drop->site);
+  ds.seed = static_cast<const unsigned long long*>(static_cast<const void*>(drop->seed));   // p == 0 still yields the all-ones mask
+  const long long n4 = rows * (long long)(cols / 4);
+  dropout_mask_kernel<<<capped_grid(n4, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(factors, n4, ds);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -73,6 +73,7 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles, num_splits;
   int step_split, step_mt, step_nt;  // mixed-radix digits of the grid size over (split, m tile, n tile)
   const float* row_scale;  // optional [M]: out = residual + row_scale[m] * (acc*alpha + bias)  (stochastic depth)
+  DropSpec drop;           // optional nn.Dropout on the linear's output (after GELU for the GELU epilogue); seed == nullptr: off
   float* colsum;     // optional [M]: += alpha * sum_k A[m, k], from one extra N=16 MMA per k-step against a tile of ones
   int acc_stride;    // TMEM columns per accumulator stage (BN, or BN + 16 with colsum)
   int nacc;          // accumulator stages: 2 (MMAs of tile i+1 overlap epilogue i), or 1 when 2 x acc_stride > 512 columns
@@ -335,13 +336,18 @@ __device__ __forceinline__ float4 epilogue_load(const GemmParams& p, int row, lo
   }
   return e;
 }
+template <bool DROP>
 __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float4 f, const float4& e, long long orow, int col, float alpha,
-                                               const float4& bias4) {
+                                               const float4& bias4, unsigned long long dseed) {
   f.x = fmaf(f.x, alpha, bias4.x); f.y = fmaf(f.y, alpha, bias4.y); f.z = fmaf(f.z, alpha, bias4.z); f.w = fmaf(f.w, alpha, bias4.w);
   switch (p.epilogue) {
     case VITK_EPI_TOKENS:
     case VITK_EPI_STORE: {
       f.x += e.x; f.y += e.y; f.z += e.z; f.w += e.w;
+      if (DROP && p.drop.seed != nullptr) {  // pos_drop: dropout of (patch embedding + pos_embed); host admits it for TOKENS only
+        const float4 m = drop_factors4(p.drop, dseed, ((unsigned long long)orow * p.N + col) >> 2);
+        f.x *= m.x; f.y *= m.y; f.z *= m.z; f.w *= m.w;
+      }
       if (p.out_dtype == VITK_FP32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = f;
       } else {
@@ -431,9 +437,42 @@ __device__ __forceinline__ void gelu_pack(uint32_t (&hd)[16], uint32_t (&hg)[16]
     hg[j] = H16 ? pack_f16(g.x, g.y) : pack_bf16(g.x, g.y);
   }
 }
+// same with nn.Dropout applied to the activation: gelu(pre) * m and gelu'(pre) * m (the saved derivative then carries the mask
+// into the backward DGELU epilogue for free); blk0 = index of the first 8-element mask block of this row chunk
+template <bool H16>
+__device__ __forceinline__ void gelu_pack_drop(uint32_t (&hd)[16], uint32_t (&hg)[16], const float (&f)[32], const DropSpec& ds,
+                                               unsigned long long dseed, unsigned long long blk0) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 bits = drop_bits8(dseed, ds.site, blk0 + c);
+    const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = 4 * c + q;
+      float2 g, d;
+      gelu_erf_both2(make_float2(f[2 * j], f[2 * j + 1]), g, d);
+      const float2 m = drop_pair(w[q], ds.thresh, ds.inv_keep);
+      g = __fmul2_rn(g, m);
+      d = __fmul2_rn(d, m);
+      hd[j] = H16 ? pack_f16(d.x, d.y) : pack_bf16(d.x, d.y);
+      hg[j] = H16 ? pack_f16(g.x, g.y) : pack_bf16(g.x, g.y);
+    }
+  }
+}
+// f[0..8) *= mask factors of one 8-element block
+__device__ __forceinline__ void drop_apply8(float* f, const DropSpec& ds, unsigned long long dseed, unsigned long long blk) {
+  const uint4 bits = drop_bits8(dseed, ds.site, blk);
+  const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 m = drop_pair(w[q], ds.thresh, ds.inv_keep);
+    f[2 * q] *= m.x;
+    f[2 * q + 1] *= m.y;
+  }
+}
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, bool DROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -660,6 +699,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const int group = (warp - 2) >> 2;        // which of the EPI_WARPS/4 warps sharing that quadrant
     float* stage = sEpi + (warp - 2) * EPI_STAGE_FLOATS;
     const float alpha = p.alpha_dev != nullptr ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+    // DROP is a template flag (forward, K-major instantiations only) so the dropout code costs the other kernels no registers
+    const unsigned long long dseed = (DROP && p.drop.seed != nullptr) ? __ldg(p.drop.seed) : 0ull;
     const int c4 = lane & 3;     // float4 column slot of this lane inside a 16-column half chunk
     const int rsub = lane >> 2;  // row (mod 8) this lane handles when reading the staged half chunk back
     uint32_t tcount = 0, aux_phase = 0, sbuf_idx = 0;
@@ -715,6 +756,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               f[4 * c + 1] = fmaf(__uint_as_float(v[4 * c + 1]), alpha, b4[c].y);
               f[4 * c + 2] = fmaf(__uint_as_float(v[4 * c + 2]), alpha, b4[c].z);
               f[4 * c + 3] = fmaf(__uint_as_float(v[4 * c + 3]), alpha, b4[c].w);
+            }
+            if (DROP && p.drop.seed != nullptr) {   // proj_drop / Mlp.drop on the branch output, before it joins the residual stream
+              const unsigned long long blk = ((unsigned long long)(row_base + lane) * p.N + col0) >> 3;
+              drop_apply8(f, p.drop, dseed, blk);
+              drop_apply8(f + 8, p.drop, dseed, blk + 1);
             }
             if (p.row_scale != nullptr) {   // per-sample stochastic-depth factor of this residual branch
               const float rsc = (row_base + lane) < p.M ? __ldg(p.row_scale + row_base + lane) : 0.f;
@@ -775,7 +821,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             } else if (p.epilogue == VITK_EPI_GELU) {
               // out = gelu'(pre) (all the backward needs), out2 = gelu(pre): one erf evaluation serves both
               uint32_t h2[16];
-              if (h16) gelu_pack<true>(h, h2, f);
+              if (DROP && p.drop.seed != nullptr) {
+                const unsigned long long blk = ((unsigned long long)(row_base + lane) * p.N + col0) >> 3;
+                if (h16) gelu_pack_drop<true>(h, h2, f, p.drop, dseed, blk);
+                else gelu_pack_drop<false>(h, h2, f, p.drop, dseed, blk);
+              } else if (h16) gelu_pack<true>(h, h2, f);
               else gelu_pack<false>(h, h2, f);
               stage_and_store(sbuf, h, &tmOut, col0, row_base, lane, true, KNOB(1));
               uint8_t* sbuf2 = sbase + (sbuf_idx & 1) * 2048;
@@ -857,7 +907,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               const int r = i * 8 + rsub;
               if (row_base + r < p.M) {
                 const float4 f = *reinterpret_cast<const float4*>(stage + r * EPI_PITCH + c4 * 4);
-                epilogue_apply(p, f, ex[i], orow[i], col, alpha, bias4);
+                epilogue_apply<DROP>(p, f, ex[i], orow[i], col, alpha, bias4, dseed);
               }
             }
           }
@@ -921,13 +971,16 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
   return VITK_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, bool DROP = false>
 int launch_gemm(const CUtensorMap* tm, const GemmParams& p, int grid, cudaStream_t st) {
+  if constexpr (!DROP && !A_MN && !B_MN) {   // forward linears: the dropout-capable instantiation when a mask is requested
+    if (p.drop.seed != nullptr) return launch_gemm<BN, STAGES, A_MN, B_MN, CTA2, true>(tm, p, grid, st);
+  }
   constexpr int SMEM = STAGES * (BLOCK_M * BLOCK_K * 2 + (BN / (CTA2 ? 2 : 1)) * BLOCK_K * 2) + EPI_WARPS * EPI_STAGE_FLOATS * 4 +
                        MAX_BIAS_SMEM * 4 + (2 * STAGES + 4 + EPI_WARPS) * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget exceeded");
   static bool configured = false;
-  auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN, CTA2>;
+  auto kfn = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN, CTA2, DROP>;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
@@ -1082,6 +1135,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   p.aux = a->aux; p.ldaux = a->ldaux;
   p.colsum = a->colsum_out;
   p.row_scale = a->row_scale;
+  p.drop = make_drop_spec(a->drop_seed, a->drop_p, a->drop_site);
   p.acc_stride = bn + (a->colsum_out != nullptr ? 16 : 0);
   p.nacc = 2 * p.acc_stride <= 512 ? 2 : 1;
   {
@@ -1113,6 +1167,13 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
   if (p.num_n_tiles * bn > MAX_BIAS_SMEM) p.tma_epi = 0;  // the TMA epilogue keeps the whole bias vector in shared memory
   if (a->row_scale != nullptr)
     VITK_CHECK_ARG(p.tma_epi && out_fp32 && a->epilogue == VITK_EPI_STORE, "vitk_gemm: row_scale needs the fp32 STORE epilogue");
+  if (p.drop.seed != nullptr) {
+    VITK_CHECK_ARG(a->drop_p < 1.f && a->N % 8 == 0 && !a->a_mn_major && !a->b_mn_major,
+                   "vitk_gemm: dropout needs p < 1, N %% 8 == 0 and K-major operands (a forward linear)");
+    VITK_CHECK_ARG(a->epilogue == VITK_EPI_TOKENS || (p.tma_epi && (a->epilogue == VITK_EPI_GELU ||
+                                                                   (a->epilogue == VITK_EPI_STORE && out_fp32))),
+                   "vitk_gemm: dropout is fused into the TOKENS, GELU and fp32 STORE epilogues only");
+  }
   if (a->colsum_out != nullptr)
     VITK_CHECK_ARG(p.tma_epi && p.num_n_tiles * bn <= ONES_OFFSET, "vitk_gemm: colsum_out supports N <= %d", ONES_OFFSET);
   tm[2] = tm[0]; tm[3] = tm[0]; tm[4] = tm[0];

@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                   float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
                   float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale,
-                  const float* __restrict__ branch_scale, long long rows, int dim) {
+                  const float* __restrict__ branch_scale, DropSpec drop, long long rows, int dim) {
   constexpr int RPW = 32 / LPR;
+  const unsigned long long dseed = drop.seed != nullptr ? __ldg(drop.seed) : 0ull;
   extern __shared__ float red[];  // [3][dim]
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, gl = lane % LPR;
@@ -155,7 +156,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
         const float4 o = make_float4(rs * (g[c].x - m1 - xh[c].x * m2) + rv[c].x, rs * (g[c].y - m1 - xh[c].y * m2) + rv[c].y,
                                      rs * (g[c].z - m1 - xh[c].z * m2) + rv[c].z, rs * (g[c].w - m1 - xh[c].w * m2) + rv[c].w);
         *reinterpret_cast<float4*>(dxr + 4 * i) = o;
-        const float4 ob = make_float4(o.x * bs, o.y * bs, o.z * bs, o.w * bs);
+        float4 ob = make_float4(o.x * bs, o.y * bs, o.z * bs, o.w * bs);
+        if (drop.seed != nullptr) {   // dropout mask of the branch output this gradient enters
+          const float4 m = drop_factors4(drop, dseed, ((unsigned long long)row * dim + 4 * i) >> 2);
+          ob.x *= m.x; ob.y *= m.y; ob.z *= m.z; ob.w *= m.w;
+        }
         if (dx16 != nullptr)
           *reinterpret_cast<uint2*>(dx16 + row * dim + 4 * i) = make_uint2(pack16(ob.x, ob.y, dx_fp16), pack16(ob.z, ob.w, dx_fp16));
         dc[c].x += ob.x; dc[c].y += ob.y; dc[c].z += ob.z; dc[c].w += ob.w;
@@ -193,13 +198,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 // registers instead of 12 per chunk per lane, and R rows per thread are in flight at once (R x 40 bytes of loads per
 // thread, 24+ resident warps per SM).  Row statistics are reduced inside G-lane groups by shuffles and across groups
 // through a double-buffered shared-memory table (one __syncthreads per batch of R x slots rows).
-template <int V, int R>
+template <int V, int R, bool DROP>
 __global__ void __launch_bounds__(192, 5)
     ln_bwd_cols_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
                        const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float* __restrict__ dcolsum, const float* __restrict__ unscale,
-                       const float* __restrict__ branch_scale, long long rows) {
+                       const float* __restrict__ branch_scale, DropSpec drop, long long rows) {
   constexpr int T = 192;
   constexpr int SLOTS = T / V;                 // rows processed side by side
   constexpr int G = (V % 32 == 0) ? 32 : 16;   // lanes per shuffle group (never straddles two rows)
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(192, 5)
   const int grp = cv / G, gl = cv % G;
   const float inv_dim = 1.f / float(DIM);
   const float4 gm = ldg_f4(gamma + 4 * cv);
+  const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;   // DROP: compile-time, so the plain kernel pays no registers
   float4 dg = make_float4(0, 0, 0, 0), db = dg, dc = dg;
   const long long batch = (long long)SLOTS * R;
   int it = 0;
@@ -270,7 +276,11 @@ __global__ void __launch_bounds__(192, 5)
         *reinterpret_cast<float4*>(dx + row * DIM + 4 * cv) = o;
         // the 16-bit copy and the bias gradient belong to the residual BRANCH below: scaled by its stochastic-depth factor
         const float bs = branch_scale != nullptr ? __ldg(branch_scale + row) : 1.f;
-        const float4 ob = make_float4(o.x * bs, o.y * bs, o.z * bs, o.w * bs);
+        float4 ob = make_float4(o.x * bs, o.y * bs, o.z * bs, o.w * bs);
+        if (DROP) {   // ... and by the dropout mask of that branch's output (recomputed, never stored)
+          const float4 m = drop_factors4(drop, dseed, ((unsigned long long)row * DIM + 4 * cv) >> 2);
+          ob.x *= m.x; ob.y *= m.y; ob.z *= m.z; ob.w *= m.w;
+        }
         if (dx16 != nullptr)
           *reinterpret_cast<uint2*>(dx16 + row * DIM + 4 * cv) = make_uint2(pack16(ob.x, ob.y, dx_fp16), pack16(ob.z, ob.w, dx_fp16));
         dc.x += ob.x; dc.y += ob.y; dc.z += ob.z; dc.w += ob.w;
@@ -359,8 +369,12 @@ extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const floa
 extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* mean, const float* rstd,
                                   const float* gamma, const float* dres, float* dx, void* dx16, int32_t dx16_dtype,
                                   float* dgamma, float* dbeta, float* dcolsum, const float* grad_unscale,
-                                  const float* branch_scale, int64_t rows, int32_t dim, void* stream) {
+                                  const float* branch_scale, const vitk_dropout* branch_drop, int64_t rows, int32_t dim,
+                                  void* stream) {
   VITK_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "vitk_layernorm_bwd: null pointer");
+  const DropSpec drop = branch_drop != nullptr ? make_drop_spec(branch_drop->seed, branch_drop->p, branch_drop->site)
+                                               : make_drop_spec(nullptr, 0.f, 0);
+  VITK_CHECK_ARG(drop.seed == nullptr || (branch_drop->p < 1.f && dim % 8 == 0), "vitk_layernorm_bwd: dropout needs p < 1, dim %% 8 == 0");
   VITK_CHECK_ARG((dy_dtype == VITK_BF16 || dy_dtype == VITK_FP16) && (dx16_dtype == VITK_BF16 || dx16_dtype == VITK_FP16),
                  "vitk_layernorm_bwd: dy / dx16 must be bf16 or fp16");
   VITK_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024, "vitk_layernorm_bwd: dim=%d must be a multiple of 4, <= 1024", dim);
@@ -376,8 +390,12 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
     long long blocks = (rows + batch - 1) / batch;                                                                         \
     const long long cap = (long long)num_sms() * 5;                                                                        \
     if (blocks > cap) blocks = cap;                                                                                        \
-    VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, gamma,   \
-                         dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, branch_scale, (long long)rows));                  \
+    if (drop.seed != nullptr)                                                                                              \
+      VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_, true>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, \
+                           gamma, dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, branch_scale, drop, (long long)rows)); \
+    else                                                                                                                   \
+      VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_, false>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, \
+                           gamma, dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, branch_scale, drop, (long long)rows)); \
     VITK_LAUNCH_CHECK();                                                                                                   \
     return VITK_OK;                                                                                                        \
   }
@@ -393,8 +411,8 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
   const int rpb = LN_WARPS * (32 / cfg.lpr) * 4;
   LN_DISPATCH((ln_bwd_kernel<L_, C_><<<ln_grid(rows, rpb, 6), LN_WARPS * 32, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), int(dy_dtype == VITK_FP16), x, mean, rstd, gamma, dres, dx,
-      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum, grad_unscale, branch_scale, rows,
-      dim)));
+      reinterpret_cast<__nv_bfloat16*>(dx16), int(dx16_dtype == VITK_FP16), dgamma, dbeta, dcolsum, grad_unscale, branch_scale, drop,
+      rows, dim)));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -194,6 +194,50 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return dg;
 }
 
+// ------------------------------------------------------------------ dropout masks (nn.Dropout of the reference, drop_rate > 0)
+// Counter-based: the keep / drop decision of element (row, col) of dropout site `site` is a pure function of
+// (seed, site, row * ld + col), so no mask is ever stored -- forward epilogues and the backward kernels that need the
+// same mask simply recompute it.  One Philox4x32-7 call yields 8 x 16-bit uniforms for 8 consecutive elements
+// (ld % 8 == 0); an element is dropped when its uniform < thresh = round(p * 65536), kept values are scaled by 1/(1-p).
+struct DropSpec {
+  const unsigned long long* seed;  // device scalar drawn per step (nullptr = dropout off)
+  uint32_t thresh;
+  float inv_keep;
+  uint32_t site;
+};
+__host__ inline DropSpec make_drop_spec(const void* seed, float p, int site) {
+  DropSpec d;
+  d.seed = (seed != nullptr && p > 0.f) ? static_cast<const unsigned long long*>(seed) : nullptr;
+  d.thresh = uint32_t(p * 65536.f + 0.5f);
+  d.inv_keep = 1.f / (1.f - p);
+  d.site = uint32_t(site);
+  return d;
+}
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// uniforms of elements [8 * blk, 8 * blk + 8): element j sits in 16-bit half (j & 1) of word (j >> 1)
+__device__ __forceinline__ uint4 drop_bits8(unsigned long long seed, uint32_t site, unsigned long long blk) {
+  return philox4x32_7(make_uint4(uint32_t(blk), uint32_t(blk >> 32), site, 0x5eedu), make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+}
+__device__ __forceinline__ float2 drop_pair(uint32_t word, uint32_t thresh, float inv_keep) {
+  return make_float2((word & 0xffffu) >= thresh ? inv_keep : 0.f, (word >> 16) >= thresh ? inv_keep : 0.f);
+}
+// factors of the 4 elements [4 * q4, 4 * q4 + 4) (q4 = element index / 4) -- for kernels that own one float4 per thread
+__device__ __forceinline__ float4 drop_factors4(const DropSpec& d, unsigned long long seed, unsigned long long q4) {
+  const uint4 b = drop_bits8(seed, d.site, q4 >> 1);
+  const float2 lo = drop_pair((q4 & 1) ? b.z : b.x, d.thresh, d.inv_keep), hi = drop_pair((q4 & 1) ? b.w : b.y, d.thresh, d.inv_keep);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // streaming 128-bit global accesses
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -185,6 +185,7 @@ class VitEngine:
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.grad_ready_hook = None   # callable(stage) used by the data-parallel bucket launcher
         self.generation = 0
+        self._drop_on = False
         s0 = self.INIT_LOSS_SCALE if dtype16 == torch.float16 else 1.0
         self.amp = torch.tensor([s0, 1.0 / s0, 0, 0, 0, 0, 0, 0], dtype=torch.float32, device=self.device)
         self.amp_scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
@@ -194,6 +195,11 @@ class VitEngine:
         self.drop_path = [0.0] * (2 * dims.depth)
         self._dp_prob_dev = None
         self.last_drop_scale = None     # [2L, B] factors of the latest training forward (tests / debugging)
+        # nn.Dropout(drop_rate) sites (pos_drop, proj_drop, Mlp.drop x2): counter-based masks recomputed from one device
+        # seed per step (include/vitk.h `vitk_dropout`); site 0 = pos_drop, block l: 1+3l proj, 2+3l after GELU, 3+3l after fc2
+        self.drop_rate = 0.0
+        self.drop_seed = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.frozen = set()             # flat-buffer entries that are not trained (a sinusoidal pos_embed buffer)
 
     def set_drop_path(self, per_block_rates) -> None:
         rates = [float(r) for r in per_block_rates]
@@ -201,6 +207,15 @@ class VitEngine:
             raise ValueError("set_drop_path: one rate in [0, 1) per block expected")
         self.drop_path = [r for r in rates for _ in range(2)]
         self._dp_prob_dev = torch.tensor(self.drop_path, dtype=torch.float32, device=self.device)
+
+    def set_dropout(self, rate: float) -> None:
+        if not (0.0 <= float(rate) < 1.0):
+            raise ValueError("set_dropout: rate in [0, 1) expected")
+        self.drop_rate = float(rate)
+
+    def _site(self, site: int):
+        """(seed, p, site) of one Dropout call, or None when dropout is off for this pass."""
+        return (self.drop_seed, self.drop_rate, site) if self._drop_on else None
 
     # ------------------------------------------------------------------ helpers
     def w(self, name: str) -> torch.Tensor:      # 16-bit shadow view
@@ -263,14 +278,19 @@ class VitEngine:
             dp = ws.dp
             self.last_drop_scale = ws.dp[:, ::T]
         ws.dp_active = dp is not None
+        self._drop_on = bool(train and self.drop_rate > 0.0)
+        ws.drop_on = self._drop_on
+        if self._drop_on:
+            self.drop_seed.random_(0, 1 << 62)      # torch's CUDA generator: seedable and CUDA-graph safe (fresh per replay)
         rs = lambda i: dp[i] if (dp is not None and self.drop_path[i] > 0.0) else None
         ops.patchify(images, d.patch, out=ws.patches)
         x0 = ws.x[0]
         ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
                  bias=self.p("patch_embed.proj.bias"), epilogue=_lib.EPI_TOKENS,
-                 tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"))
+                 tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"), drop=self._site(0))
         ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token"),
-                              self.p("dist_token") if d.n_prefix == 2 else None, self.p("pos_embed"), d.n_prefix)
+                              self.p("dist_token") if d.n_prefix == 2 else None, self.p("pos_embed"), d.n_prefix,
+                              drop=self._site(0))
         for l in range(d.depth):
             s = l if train else 0
             pre = f"blocks.{l}."
@@ -287,12 +307,12 @@ class VitEngine:
                 attn_probs.append(probs)
             ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
             ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in,
-                     row_scale=rs(2 * l))
+                     row_scale=rs(2 * l), drop=self._site(1 + 3 * l))
             ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
             ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.dact[s], out2=ws.act[s],
-                     bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
+                     bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU, drop=self._site(2 + 3 * l))
             ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid,
-                     row_scale=rs(2 * l + 1))
+                     row_scale=rs(2 * l + 1), drop=self._site(3 + 3 * l))
         x_last = ws.x[2 * d.depth] if train else ws.x[(2 * d.depth) % 3]
         two = d.n_out == 2
         pooled = None
@@ -323,6 +343,7 @@ class VitEngine:
         two = d.n_out == 2
         u = self.grad_unscale
         dp = ws.dp if getattr(ws, "dp_active", False) else None
+        self._drop_on = bool(getattr(ws, "drop_on", False))
         rs = lambda i: dp[i] if (dp is not None and i >= 0 and self.drop_path[i] > 0.0) else None
         dx, dx_alt = ws.dx[0], ws.dx[1]
         last_fc2_bias = self.g(f"blocks.{d.depth - 1}.mlp.fc2.bias")
@@ -330,7 +351,8 @@ class VitEngine:
                      self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dx16,
                      self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
                      self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
-                     last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale, branch_scale=rs(2 * d.depth - 1))
+                     last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale, branch_scale=rs(2 * d.depth - 1),
+                     branch_drop=self._site(3 + 3 * (d.depth - 1)))
         self._notify("head")
         for l in range(d.depth - 1, -1, -1):
             pre = f"blocks.{l}."
@@ -344,7 +366,8 @@ class VitEngine:
             ops.gemm(ws.d_pre, self.w(pre + "mlp.fc1.weight"), M, D, d.hidden, b_mn=True, out=ws.dxn)
             ops.layernorm_bwd(ws.dxn, x_mid, st[2], st[3], self.p(pre + "norm2.weight"), self.g(pre + "norm2.weight"),
                               self.g(pre + "norm2.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16,
-                              dcolsum=self.g(pre + "attn.proj.bias"), unscale=u, branch_scale=rs(2 * l))
+                              dcolsum=self.g(pre + "attn.proj.bias"), unscale=u, branch_scale=rs(2 * l),
+                              branch_drop=self._site(1 + 3 * l))
             dx, dx_alt = dx_alt, dx
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
             self._wgrad(ws.dx16, ws.ao[l], pre + "attn.proj.weight", M)
@@ -355,12 +378,13 @@ class VitEngine:
             prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
             ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),
                               self.g(pre + "norm1.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16 if l > 0 else None,
-                              dcolsum=prev_bias, unscale=u, branch_scale=rs(2 * l - 1))
+                              dcolsum=prev_bias, unscale=u, branch_scale=rs(2 * l - 1),
+                              branch_drop=self._site(3 * l) if l > 0 else None)
             dx, dx_alt = dx_alt, dx
             self._notify(pre)
-        ops.tokens_bwd(dx.view(B, T, D), self.g("pos_embed"), self.g("cls_token"),
+        ops.tokens_bwd(dx.view(B, T, D), None if "pos_embed" in self.frozen else self.g("pos_embed"), self.g("cls_token"),
                        self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g("patch_embed.proj.bias"),
-                       d.n_prefix, unscale=u)
+                       d.n_prefix, unscale=u, drop=self._site(0))
         self._wgrad(ws.dpatch, ws.patches, "patch_embed.proj.weight", B * d.n_patches)
         self._notify("embed")
 

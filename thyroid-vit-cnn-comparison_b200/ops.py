@@ -28,6 +28,16 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _drop(d):
+    """(seed int64[1] CUDA tensor, p, site) -> vitk_dropout passed by reference (None: no dropout)."""
+    if d is None:
+        return None
+    seed, p, site = d
+    if seed.dtype != torch.int64 or not seed.is_cuda:
+        raise TypeError("dropout seed must be a CUDA int64 tensor")
+    return C.byref(_lib.Dropout(seed.data_ptr(), float(p), int(site)))
+
+
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (libvitk has no CPU path)")
@@ -60,7 +70,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
          epilogue: int = _lib.EPI_STORE, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          split_k: int = 1, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, tokens: Optional[tuple] = None,
          pos: Optional[torch.Tensor] = None, lda: Optional[int] = None, ldb: Optional[int] = None,
-         colsum_out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+         colsum_out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None, drop=None) -> torch.Tensor:
     """D[M,N] = A[M,K] @ B[N,K]^T with a fused epilogue (see include/vitk.h).
 
     A is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); B is stored [N,K] or [K,N].  A and B must share one
@@ -97,6 +107,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
     if row_scale is not None:
         _req(row_scale, f32, "gemm row_scale")
     a.row_scale = _p(row_scale)
+    if drop is not None:       # (seed, p, site): nn.Dropout fused into the epilogue (include/vitk.h)
+        a.drop_seed, a.drop_p, a.drop_site = drop[0].data_ptr(), float(drop[1]), int(drop[2])
     check(_lib.load().vitk_gemm(C.byref(a), _stream()), "gemm")
     return out
 
@@ -115,9 +127,9 @@ def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, y=None, mean=None, rstd=Non
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None, dx16=None, dcolsum=None, unscale=None,
-                  branch_scale=None):
+                  branch_scale=None, branch_drop=None):
     """dx = dres + LN'(dy); dgamma/dbeta/dcolsum += (*unscale) * column sums.  With `branch_scale` ([rows], stochastic depth)
-    dx16 and dcolsum carry dx * branch_scale[row]."""
+    dx16 and dcolsum carry dx * branch_scale[row]; with `branch_drop` ((seed, p, site)) also the dropout mask of that branch."""
     _req16(dy, "layernorm dy"); _req(x, f32, "layernorm x")
     dim = x.shape[-1]
     rows = x.numel() // dim
@@ -125,7 +137,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None
     check(_lib.load().vitk_layernorm_bwd(dy.data_ptr(), _DT[dy.dtype], x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                          gamma.data_ptr(), _p(dres), dx.data_ptr(), _p(dx16),
                                          _DT[dx16.dtype] if dx16 is not None else _DT[dy.dtype], dgamma.data_ptr(),
-                                         dbeta.data_ptr(), _p(dcolsum), _p(unscale), _p(branch_scale), rows, dim, _stream()),
+                                         dbeta.data_ptr(), _p(dcolsum), _p(unscale), _p(branch_scale), _drop(branch_drop), rows, dim,
+                                         _stream()),
           "layernorm_bwd")
     return dx
 
@@ -162,18 +175,18 @@ def patchify(images, P: int, out=None, dtype=f16):
     return out
 
 
-def prefix_tokens_fwd(x, cls_tok, dist_tok, pos, n_prefix: int):
+def prefix_tokens_fwd(x, cls_tok, dist_tok, pos, n_prefix: int, drop=None):
     B, T, dim = x.shape
     check(_lib.load().vitk_prefix_tokens_fwd(x.data_ptr(), _p(cls_tok), _p(dist_tok), pos.data_ptr(), B, T, dim, n_prefix,
-                                             _stream()), "prefix_tokens_fwd")
+                                             _drop(drop), _stream()), "prefix_tokens_fwd")
     return x
 
 
-def tokens_bwd(dx, dpos, dcls, ddist, dpatch16, dbias, n_prefix: int, unscale=None):
+def tokens_bwd(dx, dpos, dcls, ddist, dpatch16, dbias, n_prefix: int, unscale=None, drop=None):
     B, T, dim = dx.shape
     check(_lib.load().vitk_tokens_bwd(dx.data_ptr(), _p(dpos), _p(dcls), _p(ddist), _p(dpatch16),
                                       _DT[dpatch16.dtype] if dpatch16 is not None else 0, _p(dbias), _p(unscale), B, T, dim,
-                                      n_prefix, _stream()), "tokens_bwd")
+                                      n_prefix, _drop(drop), _stream()), "tokens_bwd")
 
 
 # --------------------------------------------------------------------------- heads
@@ -193,14 +206,22 @@ def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5, po
 
 
 def head_bwd(dl0, dl1, xhat, rstd, gamma, beta, W0, W1, dx, dx16, dgamma, dbeta, dW0, db0, dW1, db1, dcolsum,
-             T: int, n_heads: int, loss_scale=None, branch_scale=None):
+             T: int, n_heads: int, loss_scale=None, branch_scale=None, branch_drop=None):
     """dx / dx16 = S * dLoss/dx (S = *loss_scale), parameter gradients are true (unscaled)."""
     B, Cc = dl0.shape
     dim = W0.shape[1]
     check(_lib.load().vitk_head_bwd(dl0.data_ptr(), _p(dl1), xhat.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                     W0.data_ptr(), _p(W1), dx.data_ptr(), _p(dx16), _DT[dx16.dtype] if dx16 is not None else 0,
                                     dgamma.data_ptr(), dbeta.data_ptr(), dW0.data_ptr(), _p(db0), _p(dW1), _p(db1), _p(dcolsum),
-                                    _p(loss_scale), _p(branch_scale), B, T, dim, Cc, n_heads, _stream()), "head_bwd")
+                                    _p(loss_scale), _p(branch_scale), _drop(branch_drop), B, T, dim, Cc, n_heads, _stream()),
+          "head_bwd")
+
+
+def dropout_mask(seed, p: float, site: int, rows: int, cols: int):
+    """fp32 [rows, cols] factors (0 or 1/(1-p)) the fused kernels derive for (seed, site) -- tests / debugging."""
+    out = torch.empty(rows, cols, dtype=f32, device=seed.device)
+    check(_lib.load().vitk_dropout_mask(_drop((seed, p, site)), out.data_ptr(), rows, cols, _stream()), "dropout_mask")
+    return out
 
 
 def droppath_scale(uniform, drop_prob, T: int, out=None):

@@ -309,9 +309,9 @@ class VisionTransformerBase(_Base):
             raise NotImplementedError("the sm_100a path implements class-token pooling (pool_type='cls')")
         if not isinstance(self.pre_logits, nn.Identity):
             raise NotImplementedError("representation_size / pre_logits is not implemented in the sm_100a path")
-        if self.training and (hp.get("drop_rate", 0.0) or hp.get("attn_drop_rate", 0.0)):
-            raise NotImplementedError("dropout / attention dropout > 0 are not implemented in the sm_100a training path "
-                                      "(stochastic depth is; parity configuration uses 0, SURVEY.md section 7)")
+        if self.training and hp.get("attn_drop_rate", 0.0):
+            raise NotImplementedError("attention-probability dropout > 0 is not implemented in the sm_100a training path "
+                                      "(drop_rate and stochastic depth are; every ViT/DeiT config of the reference uses 0)")
 
     def _engine_params(self) -> "OrderedDict[str, nn.Parameter]":
         skip = ("patch_embed.quality_score",)
@@ -344,6 +344,9 @@ class VisionTransformerBase(_Base):
                 if isinstance(p, nn.Parameter):
                     p.grad = None
             eng.set_drop_path([float(getattr(b.drop_path, "drop_prob", 0.0)) for b in self.blocks])
+            eng.set_dropout(float(self.pos_drop.p))       # pos_drop, proj_drop and Mlp.drop all carry drop_rate
+            if not isinstance(self.pos_embed, nn.Parameter):
+                eng.frozen.add("pos_embed")
             self._engine = eng
             named = self._engine_params()
             first = next(iter(named.values()))
