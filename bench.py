@@ -108,9 +108,50 @@ def cpu_reference_run(model_name: str, steps: int, warmup: int, batch: int = 32)
     return batch / sec, sec, cores
 
 
+def gpu_eager_reference_run(model_name: str, steps: int, warmup: int, batch: int, precision: str):
+    """Context number, NOT the reference arm the driver scores (that is the CPU run above): the same oracle port of the
+    reference's arithmetic executed by PyTorch eager (ATen / cuBLAS / cuDNN kernels) on cuda:0 at the full per-GPU batch --
+    SURVEY.md section 8(d) config 2 "compare against PyTorch eager of the reference class on the same GPU".
+    precision: fp32 (true fp32 matmuls), tf32, or bf16 (torch.autocast).  Returns (images/s, seconds/step)."""
+    import torch
+    from oracle import vit_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = precision == "tf32"
+    cfg = O.DEIT_TINY if model_name == "deit_tiny" else O.VIT_BASE
+    params = {k: v.to(dev) for k, v in O.seeded_state_dict(cfg, 42).items()}
+    x, y = O.seeded_batch(cfg, batch, 42)
+    x, y = x.to(dev), y.to(dev)
+    state = {}
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=precision == "bf16"):
+            _, _, grads = O.train_step(params, x, y, cfg)
+        O.clip_and_adamw_step(params, grads, state, lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / steps
+    return batch / sec, sec
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.ref_device == "cuda":
+        ips, sec = gpu_eager_reference_run(args.model, args.steps, max(3, args.warmup), args.batch, args.ref_precision)
+        print(json.dumps({"impl": "reference", "reference_device": "cuda (PyTorch eager, oracle port)", "precision": args.ref_precision,
+                          "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": sec * 1e3, "higher_is_better": True, "data": "synthetic",
+                          "config": workload_config(args, cpu=True)}), flush=True)
         return
     batch = 32 if args.model == "deit_tiny" else 8
     ips, sec, cores = cpu_reference_run(args.model, args.steps, max(1, args.warmup), batch)
@@ -444,6 +485,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--drop-rate", type=float, default=0.0, help="nn.Dropout rate (BASELINE.json's workload: 0)")
     ap.add_argument("--drop-path-rate", type=float, default=0.0, help="stochastic depth rate (BASELINE.json's workload: 0)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the scored reference arm; cuda = PyTorch-eager context number on the same GPU")
+    ap.add_argument("--ref-precision", default="fp32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--by-shape", action="store_true", help="split the GEMM rows of the kernel profile by shape")
     args = ap.parse_args()
     if args.impl == "reference":
