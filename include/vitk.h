@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 9
+#define VITK_ABI_VERSION 10
 
 typedef enum {
   VITK_OK = 0,
@@ -211,6 +211,22 @@ int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xha
  * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */
 int vitk_droppath_scale(const float* uniform, const float* drop_prob, float* scale, int32_t branches, int32_t B,
                         int32_t tokens_per_img, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * On-device classification metrics -- the torchmetrics objects of lightning_modules.py:358-374 and their per-step
+ * updates (:496-516 validation, :542-560 test, :902-920 distillation module).
+ * update: confusion[label * C + argmax(logits)] += 1 (int64 [C*C + 1]; the last slot counts labels outside [0, C));
+ *   for C == 2 and scores != NULL the positive-class probability softmax(logits)[:, 1] (:493-495) and the label are
+ *   appended at position *count (device scalar, advanced by B; samples past `capacity` are dropped but still counted).
+ *   Accuracy / F1 / specificity / sensitivity / PPV / NPV / StatScores are functions of the four binary counters.
+ * binary_auroc: AUROC(task='binary', thresholds=None) over the first min(*count, capacity) samples = (pairs with
+ *   score_pos > score_neg + ties / 2) / (P * N), counted in integers; out (float64 [4]) = {auroc (0 when a class is
+ *   absent, as torchmetrics), P, N, ties}; scratch int64 [4].
+ * ------------------------------------------------------------------------------------------ */
+int vitk_metrics_update(const float* logits, const int64_t* labels, int32_t B, int32_t C, int64_t* confusion,
+                        float* scores, uint8_t* score_labels, int64_t* count, int64_t capacity, void* stream);
+int vitk_binary_auroc(const float* scores, const uint8_t* score_labels, const int64_t* count, int64_t capacity,
+                      int64_t* scratch, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused classification / distillation loss with gradient --

@@ -622,3 +622,67 @@ def test_head_bwd_branch_dropout():
     assert torch.equal(res[0][0], res[1][0])
     assert rel_l2(res[1][1], res[0][0] * mask) < 1e-3
     assert rel_l2(res[1][2], (res[0][0] * mask).sum((0, 1))) < 1e-4
+
+
+# ------------------------------------------------------------------ on-device validation / test metrics
+@pytest.mark.parametrize("quant", [None, 4])
+def test_metrics_counters_and_auroc_match_oracle(quant):
+    """Confusion counters and the pairwise AUROC against the oracle's restatement of torchmetrics (pinned to scikit-learn
+    in tests/test_oracle.py); batches of ragged sizes are appended across several update launches."""
+    from oracle import vit_oracle as O
+    from thyroid_vit_cnn_comparison_b200.metrics import ClassificationMetrics
+    g = torch.Generator().manual_seed(11)
+    met = ClassificationMetrics(2, capacity=8192)
+    all_logits, all_y = [], []
+    for B in (256, 37, 1, 450, 1000, 3):
+        logits = torch.randn(B, 2, generator=g) * 2
+        if quant is not None:
+            logits = torch.round(logits * quant) / quant             # tied scores: the ties/2 term matters
+        y = torch.randint(0, 2, (B,), generator=g)
+        met.update(logits.to(DEV), y.to(DEV))
+        all_logits.append(logits); all_y.append(y)
+    logits, y = torch.cat(all_logits), torch.cat(all_y)
+    got = met.compute()
+    tp, fp, tn, fn = O.binary_stat_scores(logits.argmax(1), y)
+    ref = O.binary_metrics(tp, fp, tn, fn)
+    assert got["stat_scores"] == ref["stat_scores"]                  # integer counters: exact
+    for k in ("acc", "f1", "specificity", "sensitivity", "ppv", "npv"):
+        assert got[k] == ref[k], k
+    ref_auc = O.binary_auroc(torch.softmax(logits, 1)[:, 1], y)
+    assert abs(got["auc"] - ref_auc) < (1e-12 if quant is not None else 2e-6), (got["auc"], ref_auc)
+    assert int(met.count.item()) == logits.shape[0]
+    met.reset()
+    met.update(logits[:5].to(DEV), torch.ones(5, dtype=torch.long, device=DEV))
+    assert met.compute()["auc"] == 0.0                               # a class is absent
+    met.reset()
+    met.update(logits[:4].to(DEV), torch.tensor([0, 1, 2, 1], device=DEV))
+    with pytest.raises(ValueError):
+        met.compute()                                                # label outside [0, C)
+    small = ClassificationMetrics(2, capacity=16)
+    small.update(logits[:32].to(DEV), y[:32].to(DEV))
+    with pytest.raises(RuntimeError):
+        small.compute()                                              # AUROC buffer overflow is loud
+
+
+def test_metrics_large_split_auroc_and_multiclass_confusion():
+    from oracle import vit_oracle as O
+    from thyroid_vit_cnn_comparison_b200.metrics import ClassificationMetrics
+    g = torch.Generator().manual_seed(5)
+    n = 50000
+    y = torch.randint(0, 2, (n,), generator=g)
+    logits = torch.randn(n, 2, generator=g) + torch.stack([-0.5 * y.float(), 0.5 * y.float()], 1)   # informative scores
+    met = ClassificationMetrics(2, capacity=1 << 16)
+    for i in range(0, n, 4096):
+        met.update(logits[i:i + 4096].to(DEV), y[i:i + 4096].to(DEV))
+    got = met.compute()
+    ref_auc = O.binary_auroc(torch.softmax(logits, 1)[:, 1], y)
+    assert 0.6 < ref_auc < 0.9 and abs(got["auc"] - ref_auc) < 2e-6
+    mc = ClassificationMetrics(5)
+    lg = torch.randn(999, 5, generator=g)
+    yy = torch.randint(0, 5, (999,), generator=g)
+    mc.update(lg.to(DEV), yy.to(DEV))
+    cm = mc.compute()["confusion"]
+    ref = torch.zeros(5, 5, dtype=torch.int64)
+    for t, p in zip(yy.tolist(), lg.argmax(1).tolist()):
+        ref[t, p] += 1
+    assert torch.equal(cm, ref)

@@ -462,3 +462,33 @@ def test_attention_dropout_still_fails_loudly():
     m = V.VisionTransformer(attn_drop_rate=0.1, **kw).cuda().train()
     with pytest.raises(NotImplementedError):
         m(torch.zeros(2, 3, 64, 64, device="cuda"))
+
+
+def test_eval_steps_accumulate_device_metrics():
+    """validation_step / test_step of the Lightning-module counterparts (lightning_modules.py:474-570, :990-1082): metric
+    updates are one device launch per step; epoch-end values equal the oracle's on the concatenated eval logits."""
+    class Cfg(dict):
+        __getattr__ = dict.get
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2, is_deit=True, distilled=True)
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.0)
+    m = V.DeiT(distilled=True, **kw)
+    sd = O.seeded_state_dict(cfg, 21)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    mod = TR.ThyroidViTModule(Cfg(dataset=Cfg(num_classes=2), training=Cfg()), optimizer_params={"lr": 1e-3}, model=m)
+    logits, ys = [], []
+    with torch.no_grad():
+        for seed in (1, 2, 3):
+            x, y = O.seeded_batch(cfg, 24, seed)
+            out = mod.validation_step((x.cuda(), y.cuda()), 0)
+            mod.test_step((x.cuda(), y.cuda().view(-1, 1)), 0)            # [B,1] labels are squeezed (:479-482)
+            logits.append(O.forward(sd, x, cfg, training=False)); ys.append(y)
+            assert abs(float(out["val_loss"]) - torch.nn.functional.cross_entropy(logits[-1], y).item()) < 2e-3
+    logits, ys = torch.cat(logits), torch.cat(ys)
+    got = mod.split_metrics("val").compute()
+    tp, fp, tn, fn = O.binary_stat_scores(logits.argmax(1), ys)
+    margin = (logits[:, 1] - logits[:, 0]).abs().min().item()
+    if margin > 2 * LOGIT_TOL:                                           # no sample sits on the decision boundary
+        assert got["stat_scores"] == [tp, fp, tn, fn, tp + fn]
+    assert abs(got["auc"] - O.binary_auroc(torch.softmax(logits, 1)[:, 1], ys)) < 0.02
+    assert mod.split_metrics("test").compute()["stat_scores"] == got["stat_scores"]

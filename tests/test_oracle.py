@@ -171,3 +171,28 @@ def test_oracle_dropout_sites_match_reference_with_replayed_masks():
     wrong = list(masks)
     wrong[1], wrong[3] = wrong[3], wrong[1]
     assert (O.forward(sd, x, cfg, drop_masks=wrong) - rec["logits"]).abs().max().item() > 1e-4
+
+
+def test_oracle_metrics_match_sklearn():
+    """torchmetrics is not installed here (requirements.txt:171 pins 1.7.2): its binary definitions restated in the oracle are
+    pinned against scikit-learn's implementations of the same quantities, ties and degenerate splits included."""
+    from sklearn import metrics as SK
+    g = torch.Generator().manual_seed(3)
+    for n, quant in [(450, None), (1000, 8), (64, 2)]:
+        logits = torch.randn(n, 2, generator=g)
+        if quant is not None:
+            logits = torch.round(logits * quant) / quant              # many tied scores
+        y = torch.randint(0, 2, (n,), generator=g)
+        preds = logits.argmax(1)
+        probs = torch.softmax(logits, 1)[:, 1]
+        tp, fp, tn, fn = O.binary_stat_scores(preds, y)
+        assert [[tn, fp], [fn, tp]] == SK.confusion_matrix(y.numpy(), preds.numpy(), labels=[0, 1]).tolist()
+        m = O.binary_metrics(tp, fp, tn, fn)
+        assert abs(m["acc"] - SK.accuracy_score(y, preds)) < 1e-12
+        assert abs(m["f1"] - SK.f1_score(y, preds)) < 1e-12
+        assert abs(m["ppv"] - SK.precision_score(y, preds)) < 1e-12
+        assert abs(m["sensitivity"] - SK.recall_score(y, preds)) < 1e-12
+        assert abs(m["specificity"] - SK.recall_score(1 - y, 1 - preds)) < 1e-12
+        assert abs(O.binary_auroc(probs, y) - SK.roc_auc_score(y.numpy(), probs.double().numpy())) < 1e-12
+    assert O.binary_auroc(torch.rand(10), torch.ones(10, dtype=torch.long)) == 0.0      # a class is absent -> 0 (torchmetrics)
+    assert O.binary_metrics(0, 0, 5, 0)["f1"] == 0.0 and O.binary_metrics(0, 0, 5, 0)["ppv"] == 0.0

@@ -310,3 +310,24 @@ def attention_rollout(probs, fusion: str = "mean"):
     check(_lib.load().vitk_attention_rollout(probs.data_ptr(), out.data_ptr(), scratch.data_ptr(), L, B, H, N, fus, _stream()),
           "attention_rollout")
     return out
+
+
+# --------------------------------------------------------------------------- on-device metrics
+def metrics_update(logits, labels, confusion, scores=None, score_labels=None, count=None):
+    """confusion (int64 [C*C+1]) += this batch; optionally appends softmax(logits)[:, 1] / labels at *count (binary AUROC)."""
+    _req(logits, f32, "metrics logits")
+    B, Cc = logits.shape
+    if labels.dtype != torch.int64 or not labels.is_cuda or confusion.dtype != torch.int64 or confusion.numel() != Cc * Cc + 1:
+        raise TypeError("metrics_update: labels int64 CUDA [B], confusion int64 [C*C+1]")
+    cap = scores.numel() if scores is not None else 0
+    check(_lib.load().vitk_metrics_update(logits.data_ptr(), labels.data_ptr(), B, Cc, confusion.data_ptr(), _p(scores),
+                                          _p(score_labels), _p(count), cap, _stream()), "metrics_update")
+
+
+def binary_auroc(scores, score_labels, count, scratch=None, out=None):
+    """float64 [4] = {auroc, P, N, ties} over the first min(*count, capacity) appended samples."""
+    scratch = torch.empty(4, dtype=torch.int64, device=scores.device) if scratch is None else scratch
+    out = torch.empty(4, dtype=torch.float64, device=scores.device) if out is None else out
+    check(_lib.load().vitk_binary_auroc(scores.data_ptr(), score_labels.data_ptr(), count.data_ptr(), scores.numel(),
+                                        scratch.data_ptr(), out.data_ptr(), _stream()), "binary_auroc")
+    return out

@@ -136,6 +136,31 @@ def cfg_get(cfg: Any, key: str, default=None):
     return default
 
 
+def _split_metrics(module, split: str):
+    from .metrics import ClassificationMetrics
+    store = module.__dict__.setdefault("_metrics", {})
+    if split not in store:
+        num_classes = int(cfg_get(cfg_get(module.config, "dataset"), "num_classes", 2) or 2)
+        store[split] = ClassificationMetrics(num_classes)
+    return store[split]
+
+
+def _eval_step(module, model, batch, split: str):
+    """validation_step / test_step of both Lightning modules: loss + the metric updates that torchmetrics does on the
+    host in the reference, here one libvitk launch on device counters (metrics.ClassificationMetrics).  The running
+    values the reference logs every step (`self.log('val_acc', self.val_acc, ...)`) are exposed through
+    `split_metrics(split).compute()` at epoch end instead, so the step itself never synchronises with the host."""
+    images, labels = batch
+    outputs = model(images)
+    if isinstance(outputs, tuple):
+        outputs = outputs[0]
+    loss, stats = fused_cross_entropy(outputs, labels, getattr(module, "label_smoothing", 0.0))
+    _split_metrics(module, split).update(outputs, _labels(labels))
+    module.log(f"{split}_loss", loss, on_step=False, on_epoch=True, prog_bar=True)
+    module.log(f"{split}_acc", stats["acc"], on_step=False, on_epoch=True, prog_bar=True)
+    return {f"{split}_loss": loss, f"{split}_acc": stats["acc"], "preds": outputs.argmax(dim=1)}
+
+
 class ThyroidViTModule(_Base):
     """Counterpart of lightning_modules.py:310-731 for the B200 path."""
 
@@ -157,6 +182,7 @@ class ThyroidViTModule(_Base):
         self.num_classes = cfg_get(cfg_get(config, "dataset"), "num_classes", 2)
         self.max_grad_norm = float(cfg_get(cfg_get(config, "trainer"), "gradient_clip_val", 0.0) or 0.0)
         self.logged: Dict[str, Any] = {}
+        self._metrics: Dict[str, Any] = {}
 
     def _create_model(self) -> nn.Module:                                         # :379-400
         from .registry import ModelRegistry
@@ -180,15 +206,15 @@ class ThyroidViTModule(_Base):
         self.log("train_acc", stats["acc"], on_step=True, on_epoch=True, prog_bar=True)
         return loss
 
-    def validation_step(self, batch, batch_idx):
-        images, labels = batch
-        outputs = self.model(images)
-        if isinstance(outputs, tuple):
-            outputs = outputs[0]
-        loss, stats = fused_cross_entropy(outputs, labels, self.label_smoothing)
-        self.log("val_loss", loss, on_step=False, on_epoch=True, prog_bar=True)
-        self.log("val_acc", stats["acc"], on_step=False, on_epoch=True, prog_bar=True)
-        return {"val_loss": loss, "val_acc": stats["acc"]}
+    def validation_step(self, batch, batch_idx):                                  # :474-520
+        return _eval_step(self, self.model, batch, "val")
+
+    def test_step(self, batch, batch_idx):                                        # :522-570
+        return _eval_step(self, self.model, batch, "test")
+
+    def split_metrics(self, split: str = "val"):
+        """The on-device accumulator of one split (metrics.ClassificationMetrics); compute() / reset() at epoch end."""
+        return _split_metrics(self, split)
 
     def _inner(self):
         m = self.model
@@ -310,15 +336,20 @@ class ThyroidDistillationModule(_Base):
         self.log("teacher_agreement", st["teacher_agreement"], on_step=False, on_epoch=True)
         return total
 
-    def validation_step(self, batch, batch_idx):
-        images, labels = batch
-        outputs = self.student(images)
-        if isinstance(outputs, tuple):
-            outputs = outputs[0]
-        loss, st = fused_cross_entropy(outputs, labels, self.label_smoothing)
-        self.log("val_loss", loss, on_step=False, on_epoch=True, prog_bar=True)
-        self.log("val_acc", st["acc"], on_step=False, on_epoch=True, prog_bar=True)
-        return {"val_loss": loss, "val_acc": st["acc"]}
+    def validation_step(self, batch, batch_idx):                                            # :990-1040
+        out = _eval_step(self, self.student, batch, "val")
+        images, _ = batch
+        teacher_preds = self.get_teacher_outputs(images).argmax(dim=1)
+        agreement = (out["preds"] == teacher_preds).float().mean()                          # :1022-1024
+        self.log("val_teacher_agreement", agreement, on_step=False, on_epoch=True)
+        out["val_teacher_agreement"] = agreement
+        return out
+
+    def test_step(self, batch, batch_idx):                                                  # :1042-1082
+        return _eval_step(self, self.student, batch, "test")
+
+    def split_metrics(self, split: str = "val"):
+        return _split_metrics(self, split)
 
     def configure_optimizers(self):                                                         # :1084-1147
         tr = cfg_get(self.config, "training")
