@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 10
+#define VITK_ABI_VERSION 11
 
 typedef enum {
   VITK_OK = 0,
@@ -211,6 +211,26 @@ int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xha
  * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */
 int vitk_droppath_scale(const float* uniform, const float* drop_prob, float* scale, int32_t branches, int32_t B,
                         int32_t tokens_per_img, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GPU-side input pipeline (the step right before the hot path) for raw single-channel uint16
+ * tiles already in device memory:
+ *   vitk_resize_u16        dataset.py:533-551 `_preprocess_image`: cv2.resize(INTER_LINEAR) on uint16 (skipped when the size
+ *                          already matches), result rounded to the uint16 grid, / 65535 -> gray fp32 [B, H, W]
+ *   vitk_percentile_bounds quality_preprocessing.py:306-318 AdaptiveNormalization('percentile'): per image
+ *                          (torch.quantile(x, q_lo), torch.quantile(x, q_hi)), default linear interpolation, exact order
+ *                          statistics by radix select -> bounds fp32 [B, 2]
+ *   vitk_finish_tiles      clamp to the bounds and (x - lo) / (hi - lo + 1e-8) (:314-316, optional); gray -> C channels
+ *                          and T.Normalize(mean, std) (vit_transforms.py:381-393; mean/std are HOST arrays [C], NULL = none);
+ *                          then MixUp (cutmix = 0: lam*a + (1-lam)*b, b = image perm[b]) or CutMix (cutmix = 1: image perm[b]
+ *                          inside the box rows [y1,y2) x columns [x1,x2)) -- vit_transforms.py:396-462; perm NULL = no mix.
+ *                          out fp32 [B, C, H, W], W % 4 == 0, out must not alias gray.
+ * ------------------------------------------------------------------------------------------ */
+int vitk_resize_u16(const uint16_t* raw, float* gray, int32_t B, int32_t Hs, int32_t Ws, int32_t H, int32_t W, void* stream);
+int vitk_percentile_bounds(const float* x, int32_t B, int64_t n, float q_lo, float q_hi, float* bounds, void* stream);
+int vitk_finish_tiles(const float* gray, const float* bounds, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                      const float* mean, const float* stdv, const int32_t* perm, int32_t cutmix, float lam, int32_t x1,
+                      int32_t y1, int32_t x2, int32_t y2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * On-device classification metrics -- the torchmetrics objects of lightning_modules.py:358-374 and their per-step

@@ -13,6 +13,9 @@ Fixtures
   small_vit_dropout.pt           ViT (embed 128, 2 heads, depth 2) with drop_rate = 0.1 in training mode: the keep masks every
                                  nn.Dropout call drew (forward hooks, site order pos_drop, then per block proj_drop, Mlp.drop #1,
                                  Mlp.drop #2), logits, loss, full gradients -- pins WHERE the reference applies dropout.
+  ingest.pt                      input pipeline: raw uint16 tiles -> CARSThyroidDataset._preprocess_image (cv2.resize + /65535),
+                                 AdaptiveNormalization('percentile'), MixUp / CutMix with recorded host draws -- outputs of the
+                                 reference's own classes (src/data/{dataset,quality_preprocessing,vit_transforms}.py).
   param_groups_deit_tiny.json    get_parameter_groups() table (name, weight_decay, lr_scale) + named_parameters order.
   distill_loss.pt                DistillationLoss / training_step arithmetic on random logits.
   kfold_splits_7.json            the reference's committed data/splits/split_fold_{1..7}.json (known-answer vectors).
@@ -133,6 +136,74 @@ def run_dropout_case(cfg: O.VitConfig, batch: int, seed: int, drop_rate: float):
             "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}}
 
 
+def _load_ref_file(rel: str, name: str):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, ref_loader.REF_ROOT / rel)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_ingest_case():
+    """Runs the reference's own input-pipeline code on seeded raw tiles and records inputs + outputs."""
+    import types
+    import numpy as np
+    stubs = str(ROOT / "oracle" / "_stubs")                     # tifffile (file I/O only) is absent here
+    if stubs not in sys.path:
+        sys.path.insert(0, stubs)
+    qp = _load_ref_file("src/data/quality_preprocessing.py", "ref_quality_preprocessing")
+    vt = _load_ref_file("src/data/vit_transforms.py", "ref_vit_transforms")
+    # dataset.py imports src.config.schemas: resolve the reference's `src` package for this one import, then drop the
+    # placeholder packages ref_loader may have installed under the same names
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "src" or k.startswith("src.")}
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, str(ref_loader.REF_ROOT))
+    try:
+        import importlib
+        ds = importlib.import_module("src.data.dataset")
+    finally:
+        sys.path.remove(str(ref_loader.REF_ROOT))
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    rng = np.random.default_rng(7)
+    raws = []
+    for (h, w) in [(300, 277), (224, 224), (256, 256), (100, 120)]:
+        base = rng.integers(0, 65536, (h // 4 + 1, w // 4 + 1)).astype(np.float32)          # smooth-ish texture + noise
+        img = np.kron(base, np.ones((4, 4), np.float32))[:h, :w] * 0.7 + rng.integers(0, 20000, (h, w))
+        raws.append(np.clip(img, 0, 65535).astype(np.uint16))
+    fake_self = types.SimpleNamespace(config=types.SimpleNamespace(img_size=224, channels=1))
+    pre = [ds.CARSThyroidDataset._preprocess_image(fake_self, r.copy()) for r in raws]       # [1,224,224] float32 each
+    batch = torch.stack(pre)                                                                 # [4,1,224,224]
+    adaptive = qp.AdaptiveNormalization(method="percentile", percentiles=(1, 99))(batch.clone())
+    u16 = torch.round(batch * 65535.0)
+    assert torch.equal(u16 / 65535.0, batch)                                                 # exactly k / 65535: store k
+    rec = {"raw": [torch.from_numpy(r.view(np.int16).copy()) for r in raws],                 # uint16 bit patterns
+           "preprocessed_u16": torch.from_numpy(u16.to(torch.int32).numpy().astype(np.uint16).view(np.int16).copy()),
+           "adaptive": adaptive}
+    # MixUp / CutMix on a seeded normalised batch (regenerated from the seed by the tests); the host RNG is replayed so
+    # that the draws can be recorded next to the outputs
+    g = torch.Generator().manual_seed(99)
+    images = torch.randn(4, 3, 64, 64, generator=g)
+    labels = torch.tensor([0, 1, 1, 0])
+    rec["mix_seed"], rec["labels"] = 99, labels
+    np.random.seed(123); torch.manual_seed(123)
+    lam = float(np.random.beta(0.8, 0.8)); index = torch.randperm(4)
+    np.random.seed(123); torch.manual_seed(123)
+    mixed, la, lb, lam_out = vt.MixUp(alpha=0.8)(images.clone(), labels)
+    assert lam_out == lam and torch.equal(lb, labels[index])
+    rec["mixup"] = {"lam": lam, "index": index, "out": mixed}
+    np.random.seed(321); torch.manual_seed(321)
+    lam_c = float(np.random.beta(1.0, 1.0)); index_c = torch.randperm(4)
+    cx, cy = int(np.random.randint(64)), int(np.random.randint(64))
+    np.random.seed(321); torch.manual_seed(321)
+    cut, la, lb, lam_adj = vt.CutMix(alpha=1.0)(images.clone(), labels)
+    assert torch.equal(lb, labels[index_c])
+    rec["cutmix"] = {"lam_drawn": lam_c, "index": index_c, "cx": cx, "cy": cy, "out": cut, "lam": float(lam_adj)}
+    return rec
+
+
 def main():
     assert ref_loader.available(), "run this where /root/reference is mounted"
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -140,6 +211,7 @@ def main():
     torch.save(run_case(SMALL_DEIT, 3, 42, True), GOLD / "small_deit.pt")
     torch.save(run_case(SMALL_VIT, 2, 43, True), GOLD / "small_vit.pt")
     torch.save(run_dropout_case(DROP_VIT, 4, 44, 0.1), GOLD / "small_vit_dropout.pt")
+    torch.save(run_ingest_case(), GOLD / "ingest.pt")
     torch.save(run_case(O.DEIT_TINY, 4, 42, False), GOLD / "deit_tiny_b4.pt")
     torch.save(run_case(O.VIT_BASE, 2, 42, False), GOLD / "vit_base_b2.pt")
 

@@ -686,3 +686,87 @@ def test_metrics_large_split_auroc_and_multiclass_confusion():
     for t, p in zip(yy.tolist(), lg.argmax(1).tolist()):
         ref[t, p] += 1
     assert torch.equal(cm, ref)
+
+
+# ------------------------------------------------------------------ GPU-side input pipeline
+def _u16_cuda(a):
+    import numpy as np
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.uint16).to(DEV)
+
+
+def test_ingest_resize_matches_oracle_and_reference_fixture():
+    """Bit-exact against the oracle's restatement of cv2's INTER_LINEAR loop (same fp32 operations, no FMA contraction);
+    within 2 units of the uint16 grid of the reference's own cv2 output stored in tests/golden/ingest.pt."""
+    import numpy as np
+    from pathlib import Path
+    from oracle import ingest_oracle as IO
+    rec = torch.load(Path(__file__).parent / "golden" / "ingest.pt", weights_only=False)
+    pre = rec["preprocessed_u16"].numpy().view(np.uint16).astype(np.int64)
+    for i, raw in enumerate(rec["raw"]):
+        img = raw.numpy().view(np.uint16)
+        got = ops.resize_u16(_u16_cuda(img)[None], 224, 224).cpu()[0]
+        assert torch.equal(got, IO.preprocess_image(img, 224)[0])
+        k = torch.round(got * 65535.0).numpy().astype(np.int64)
+        assert np.abs(k - pre[i, 0]).max() <= 2
+    # a ragged batch of identical-size tiles, up- and down-scaling, odd sizes
+    rng = np.random.default_rng(3)
+    for (hs, ws, h) in [(61, 450, 224), (1000, 333, 256), (224, 224, 224), (7, 9, 64)]:
+        raw = rng.integers(0, 65536, (3, hs, ws)).astype(np.uint16)
+        got = ops.resize_u16(_u16_cuda(raw), h, h).cpu()
+        ref = torch.stack([IO.preprocess_image(raw[b], h)[0] for b in range(3)])
+        assert torch.equal(got, ref), (hs, ws, h)
+
+
+@pytest.mark.parametrize("n,B", [(224 * 224, 5), (1000, 3), (7, 2), (65536, 2)])
+def test_percentile_bounds_match_torch_quantile(n, B):
+    from oracle import ingest_oracle as IO
+    g = torch.Generator().manual_seed(n)
+    x = torch.rand(B, n, generator=g) ** 2
+    x[0, : n // 3] = 0.25                                  # heavy ties around a quantile
+    if B > 1:
+        x[1] = torch.round(x[1] * 50) / 50                 # few distinct values
+    for q in [(1, 99), (0, 100), (50, 50), (12.5, 87.5)]:
+        got = ops.percentile_bounds(x.to(DEV), q[0] / 100, q[1] / 100).cpu()
+        ref = IO.percentile_bounds(x, q)
+        assert (got - ref).abs().max().item() <= 1e-6, (q, got, ref)
+    neg = torch.randn(2, 999, generator=g)                 # negative values: the key transform must keep the order
+    assert (ops.percentile_bounds(neg.to(DEV), 0.01, 0.99).cpu() - IO.percentile_bounds(neg, (1, 99))).abs().max().item() <= 1e-6
+
+
+def test_finish_tiles_pipeline_and_mixing_match_reference_fixture():
+    import numpy as np
+    from pathlib import Path
+    from oracle import ingest_oracle as IO
+    from thyroid_vit_cnn_comparison_b200 import ingest as ING
+    rec = torch.load(Path(__file__).parent / "golden" / "ingest.pt", weights_only=False)
+    pre = rec["preprocessed_u16"].numpy().view(np.uint16)
+    batch = torch.from_numpy(pre.astype(np.float32) / np.float32(65535.0))                # [4,1,224,224]: the reference's own output
+    # AdaptiveNormalization -> 3 channels -> Normalize, against the reference's recorded `adaptive`
+    bounds = ops.percentile_bounds(batch.to(DEV), 0.01, 0.99)
+    got = ops.finish_tiles(batch[:, 0].contiguous().to(DEV), 3, bounds=bounds, mean=ING.IMAGENET_MEAN, std=ING.IMAGENET_STD).cpu()
+    ref = IO.to_channels_and_normalize(rec["adaptive"], 3, ING.IMAGENET_MEAN, ING.IMAGENET_STD)
+    assert (got - ref).abs().max().item() < 2e-6
+    plain = ops.finish_tiles(batch[:, 0].contiguous().to(DEV), 1).cpu()
+    assert torch.equal(plain, batch)
+    # MixUp / CutMix with the reference's recorded host draws
+    images = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(rec["mix_seed"]))
+    m, c = rec["mixup"], rec["cutmix"]
+    assert torch.equal(ING._mix_planes(images.to(DEV), m["index"], lam=m["lam"]).cpu(), m["out"])
+    box = IO.rand_bbox(images.shape, c["lam_drawn"], c["cx"], c["cy"])
+    assert torch.equal(ING._mix_planes(images.to(DEV), c["index"], cutmix=True, box=box).cpu(), c["out"])
+    # the drop-in classes replay the same host RNG stream as the reference's classes
+    np.random.seed(123); torch.manual_seed(123)
+    mixed, la, lb, lam = ING.MixUp(alpha=0.8)(images.to(DEV), rec["labels"].to(DEV))
+    assert torch.equal(mixed.cpu(), m["out"]) and lam == m["lam"] and torch.equal(lb.cpu(), rec["labels"][m["index"]])
+    np.random.seed(321); torch.manual_seed(321)
+    cut, la, lb, lam = ING.CutMix(alpha=1.0)(images.to(DEV), rec["labels"].to(DEV))
+    assert torch.equal(cut.cpu(), c["out"]) and abs(lam - c["lam"]) < 1e-12
+    # whole pipeline object on raw tiles, MixUp folded into the last pass
+    raw = rec["raw"][1].numpy().view(np.uint16)                                          # 224 x 224: no resize ambiguity
+    tiles = np.stack([raw, raw[::-1].copy(), raw[:, ::-1].copy()])
+    ing = ING.TileIngest(224, 3, percentiles=(1, 99))
+    perm = torch.tensor([2, 0, 1])
+    out = ing(_u16_cuda(tiles), mix={"perm": perm, "lam": 0.3}).cpu()
+    x = torch.stack([IO.preprocess_image(t, 224) for t in tiles])
+    x = IO.to_channels_and_normalize(IO.adaptive_normalization(x), 3, ING.IMAGENET_MEAN, ING.IMAGENET_STD)
+    assert (out - IO.mixup(x, perm, 0.3)).abs().max().item() < 5e-6

@@ -196,3 +196,29 @@ def test_oracle_metrics_match_sklearn():
         assert abs(O.binary_auroc(probs, y) - SK.roc_auc_score(y.numpy(), probs.double().numpy())) < 1e-12
     assert O.binary_auroc(torch.rand(10), torch.ones(10, dtype=torch.long)) == 0.0      # a class is absent -> 0 (torchmetrics)
     assert O.binary_metrics(0, 0, 5, 0)["f1"] == 0.0 and O.binary_metrics(0, 0, 5, 0)["ppv"] == 0.0
+
+
+def test_ingest_oracle_matches_reference_fixture():
+    """oracle/ingest_oracle.py against tests/golden/ingest.pt = outputs of the reference's own _preprocess_image (cv2),
+    AdaptiveNormalization, MixUp and CutMix (oracle/make_golden.py:run_ingest_case)."""
+    import numpy as np
+    from oracle import ingest_oracle as IO
+    rec = torch.load(GOLD / "ingest.pt", weights_only=False)
+    pre = rec["preprocessed_u16"].numpy().view(np.uint16).astype(np.int64)               # [4,1,224,224], k of k/65535
+    for i, raw in enumerate(rec["raw"]):
+        img = raw.numpy().view(np.uint16)
+        mine = torch.round(IO.preprocess_image(img, 224) * 65535.0).numpy().astype(np.int64)[0]
+        diff = np.abs(mine - pre[i, 0])
+        assert diff.max() <= 2, diff.max()            # cv2's SIMD/IPP path vs the published loop: <= 2 units of the uint16 grid
+        assert (diff > 0).mean() < 0.08
+        if img.shape == (224, 224):
+            assert diff.max() == 0                    # no resize: exact
+    batch = torch.from_numpy(pre.astype(np.float32) / np.float32(65535.0))
+    assert torch.equal(IO.adaptive_normalization(batch.clone()), rec["adaptive"])
+    images = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(rec["mix_seed"]))
+    m = rec["mixup"]
+    assert torch.equal(IO.mixup(images, m["index"], m["lam"]), m["out"])
+    c = rec["cutmix"]
+    box = IO.rand_bbox(images.shape, c["lam_drawn"], c["cx"], c["cy"])
+    out, lam = IO.cutmix(images, c["index"], box)
+    assert torch.equal(out, c["out"]) and abs(lam - c["lam"]) < 1e-12

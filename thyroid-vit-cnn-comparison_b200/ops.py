@@ -331,3 +331,49 @@ def binary_auroc(scores, score_labels, count, scratch=None, out=None):
     check(_lib.load().vitk_binary_auroc(scores.data_ptr(), score_labels.data_ptr(), count.data_ptr(), scores.numel(),
                                         scratch.data_ptr(), out.data_ptr(), _stream()), "binary_auroc")
     return out
+
+
+# --------------------------------------------------------------------------- GPU-side input pipeline
+def resize_u16(raw, H: int, W: int, out=None):
+    """raw uint16 [B, Hs, Ws] (CUDA) -> gray fp32 [B, H, W] in [0, 1] (cv2.resize INTER_LINEAR semantics, / 65535)."""
+    if raw.dtype != torch.uint16 or not raw.is_cuda or raw.dim() != 3 or not raw.is_contiguous():
+        raise TypeError("resize_u16: raw must be a contiguous CUDA uint16 tensor [B, Hs, Ws]")
+    B, Hs, Ws = raw.shape
+    out = torch.empty(B, H, W, dtype=f32, device=raw.device) if out is None else out
+    check(_lib.load().vitk_resize_u16(raw.data_ptr(), out.data_ptr(), B, Hs, Ws, H, W, _stream()), "resize_u16")
+    return out
+
+
+def percentile_bounds(x, q_lo: float, q_hi: float, out=None):
+    """x fp32 [B, ...] -> fp32 [B, 2] = per-image (torch.quantile(q_lo), torch.quantile(q_hi))."""
+    _req(x, f32, "percentile x")
+    B = x.shape[0]
+    n = x.numel() // B
+    out = torch.empty(B, 2, dtype=f32, device=x.device) if out is None else out
+    check(_lib.load().vitk_percentile_bounds(x.data_ptr(), B, n, float(q_lo), float(q_hi), out.data_ptr(), _stream()),
+          "percentile_bounds")
+    return out
+
+
+def finish_tiles(gray, C: int, *, bounds=None, mean=None, std=None, perm=None, cutmix: bool = False, lam: float = 1.0,
+                 box=(0, 0, 0, 0), out=None):
+    """gray fp32 [B, H, W] -> fp32 [B, C, H, W]: optional percentile clamp-normalise, channel replicate + Normalize, MixUp/CutMix.
+    box = (x1, y1, x2, y2) in the reference's CutMix naming (columns x, rows y)."""
+    _req(gray, f32, "finish gray")
+    B, H, W = gray.shape
+    out = torch.empty(B, C, H, W, dtype=f32, device=gray.device) if out is None else out
+    if (mean is None) != (std is None):
+        raise ValueError("finish_tiles: mean and std come together")
+    marr = sarr = None
+    if mean is not None:
+        if len(mean) != C or len(std) != C:
+            raise ValueError("finish_tiles: one mean / std per output channel")
+        import ctypes
+        marr = (ctypes.c_float * C)(*[float(v) for v in mean])
+        sarr = (ctypes.c_float * C)(*[float(v) for v in std])
+    if perm is not None and (perm.dtype != torch.int32 or not perm.is_cuda or perm.numel() != B):
+        raise TypeError("finish_tiles: perm must be a CUDA int32 tensor [B]")
+    x1, y1, x2, y2 = (int(v) for v in box)
+    check(_lib.load().vitk_finish_tiles(gray.data_ptr(), _p(bounds), out.data_ptr(), B, C, H, W, marr, sarr, _p(perm),
+                                        int(bool(cutmix)), float(lam), x1, y1, x2, y2, _stream()), "finish_tiles")
+    return out
