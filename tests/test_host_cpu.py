@@ -210,3 +210,28 @@ def test_cfg_get_and_label_handling():
     assert training.cfg_get(C(), "x") == 3 and training.cfg_get(C(), "y") == 4 and training.cfg_get(C(), "z", 9) == 9
     assert training._labels(torch.tensor([[1], [0]], dtype=torch.int32)).tolist() == [1, 0]
     assert parallel.shard_folds(5, 1, 8) == [1] and parallel.shard_folds(5, 0, 2) == [0, 2, 4]
+
+
+def test_lightning_checkpoint_key_remapping():
+    """run_ensemble_kfold_evaluation.py:98-101: `model.model.<key>` of a Lightning .ckpt -> wrapper / bare-network keys."""
+    class Cfg:
+        def __init__(self, **k):
+            self.__dict__.update(k)
+
+        def get(self, k, d=None):
+            return getattr(self, k, d)
+    w = registry.ModelRegistry.create_model(Cfg(name="deit_tiny", pretrained=False, num_classes=2, img_size=224))
+    inner = {k: torch.randn_like(v) for k, v in w.model.state_dict().items()}
+    ckpt = {"state_dict": {"model.model." + k: v for k, v in inner.items()}, "epoch": 3}
+    registry.load_lightning_checkpoint(w, ckpt, strict=True)
+    assert all(torch.equal(w.model.state_dict()[k], v) for k, v in inner.items())
+    import copy
+    bare = copy.deepcopy(w.model)
+    for t in bare.state_dict().values():
+        t.zero_()
+    distill = {"student.model." + k: v for k, v in inner.items()}
+    distill["teacher.features.conv0.weight"] = torch.zeros(1)
+    registry.load_lightning_checkpoint(bare, distill, strict=True)
+    assert all(torch.equal(bare.state_dict()[k], v) for k, v in inner.items())
+    with pytest.raises(RuntimeError):
+        registry.load_lightning_checkpoint(bare, {"state_dict": {"model.model.cls_token": inner["cls_token"]}}, strict=True)

@@ -146,3 +146,40 @@ def install_into(ref_registry) -> None:
     """Overwrite the reference registry's vit_* / deit_* entries with the B200 wrappers."""
     ref_registry.register(["deit_tiny", "deit_small", "deit_base"], "vit")(DeiT)
     ref_registry.register(["vit_tiny", "vit_small", "vit_base"], "vit")(VisionTransformer)
+
+
+# --------------------------------------------------------------------------- checkpoint interop (SURVEY.md section 8 f2)
+_CKPT_PREFIXES = ("model.model.", "student.model.", "model.", "student.")
+
+
+def lightning_state_dict(checkpoint, target: nn.Module) -> dict:
+    """Key remapping for checkpoints written by the reference's Lightning modules.
+
+    `ThyroidViTModule` stores the wrapper as `self.model` and the wrapper stores the network as `self.model`, so a `.ckpt`
+    holds `model.model.<key>`; `scripts/run_ensemble_kfold_evaluation.py:98-101` rewrites that to `model.<key>` before
+    `load_state_dict(strict=True)` on the wrapper.  `ThyroidDistillationModule` writes `student.model.<key>` (plus
+    `teacher.*`, which is dropped).  `checkpoint` is the loaded dict (with or without the 'state_dict' level); the result
+    is keyed for `target`, which may be a registry wrapper (keys `model.<key>`) or the bare network (keys `<key>`)."""
+    sd = checkpoint.get("state_dict", checkpoint) if isinstance(checkpoint, dict) else checkpoint
+    want = set(target.state_dict().keys())
+    wrapper = isinstance(target, ModelBase)
+    out = {}
+    for key, value in sd.items():
+        if key.startswith("teacher."):
+            continue
+        inner = key
+        for pre in _CKPT_PREFIXES:
+            if key.startswith(pre):
+                inner = key[len(pre):]
+                break
+        new_key = ("model." + inner) if wrapper else inner
+        if new_key in want:
+            out[new_key] = value
+        elif key in want:
+            out[key] = value
+    return out
+
+
+def load_lightning_checkpoint(target: nn.Module, checkpoint, strict: bool = True):
+    """load_model_for_fold's loading step (run_ensemble_kfold_evaluation.py:78-103) for an already-loaded checkpoint dict."""
+    return target.load_state_dict(lightning_state_dict(checkpoint, target), strict=strict)
