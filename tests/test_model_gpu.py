@@ -492,3 +492,15 @@ def test_eval_steps_accumulate_device_metrics():
         assert got["stat_scores"] == [tp, fp, tn, fn, tp + fn]
     assert abs(got["auc"] - O.binary_auroc(torch.softmax(logits, 1)[:, 1], ys)) < 0.02
     assert mod.split_metrics("test").compute()["stat_scores"] == got["stat_scores"]
+
+
+def test_training_converges_end_to_end():
+    """examples/train_synthetic.py: GPU ingest -> captured train step (dropout, stochastic depth, fp16 + dynamic loss scale,
+    clip, fused AdamW) -> on-device metrics.  A learnable two-class task must actually be learnt."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("train_synthetic", ROOT / "examples" / "train_synthetic.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    losses, res = mod.run(steps=120, batch=64, seed=0, verbose=False)
+    assert losses[-1] < 0.5 * losses[0], losses
+    assert res["acc"] > 0.95 and res["auc"] > 0.98, res
