@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 11
+#define VITK_ABI_VERSION 12
 
 typedef enum {
   VITK_OK = 0,
@@ -206,6 +206,26 @@ int vitk_head_bwd(const float* dlogits0, const float* dlogits1, const float* xha
                   float* dW0, float* db0, float* dW1, float* db1, float* dcolsum,
                   const float* loss_scale, const float* branch_scale, const vitk_dropout* branch_drop, int32_t B,
                   int32_t tokens_per_img, int32_t dim, int32_t C, int32_t n_heads, void* stream);
+
+/* General classification tail -- vision_transformer_base.py:468-486 for the constructor options the fused head kernels above
+ * do not cover: pool_type 'gap' (mean of norm(x)[:, 1:], or of all tokens without a class token, :471-474), and
+ * `pre_logits` = Linear + Tanh when representation_size is set (:380-386, :477).
+ * pool_norm_fwd: pooled[b, :] = mean over tokens t in [t0, t1) of LayerNorm(x[b, t, :]) (fp32 [B, dim]); mean / rstd
+ *   (fp32 [B, tokens_per_img]) are written for those rows.
+ * pool_norm_bwd: takes the TRUE dpooled; writes dx / dx16 = S * d(loss)/dx for every row (zero outside the range) with the
+ *   same loss_scale / branch_scale / branch_drop meaning as vitk_head_bwd; accumulates dgamma, dbeta, dcolsum.
+ * dense_fwd: y = act(x W^T + bias), x fp32 [B, in_dim], W [out_dim, in_dim]; act 0 identity, 1 tanh.
+ * dense_bwd: dz = dy * act'(y) (scratch fp32 [B, out_dim]); dx = dz W (optional); dW += dz^T x; db += column sums (optional). */
+int vitk_pool_norm_fwd(const float* x, const float* gamma, const float* beta, float* pooled, float* mean, float* rstd,
+                       int32_t B, int32_t tokens_per_img, int32_t dim, int32_t t0, int32_t t1, float eps, void* stream);
+int vitk_pool_norm_bwd(const float* dpooled, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       float* dx, void* dx16, int32_t dx16_dtype, float* dgamma, float* dbeta, float* dcolsum,
+                       const float* loss_scale, const float* branch_scale, const vitk_dropout* branch_drop, int32_t B,
+                       int32_t tokens_per_img, int32_t dim, int32_t t0, int32_t t1, void* stream);
+int vitk_dense_fwd(const float* x, const float* W, const float* bias, float* y, int32_t B, int32_t in_dim, int32_t out_dim,
+                   int32_t act, void* stream);
+int vitk_dense_bwd(const float* dy, const float* y, const float* x, const float* W, float* dz, float* dx, float* dW,
+                   float* db, int32_t B, int32_t in_dim, int32_t out_dim, int32_t act, void* stream);
 
 /* Stochastic depth (DropPath.forward, vision_transformer_base.py:56-64): scale[br, b*T + t] = floor(keep + u[br,b]) / keep
  * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */

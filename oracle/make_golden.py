@@ -47,7 +47,14 @@ def build_reference(cfg: O.VitConfig, seed: int):
     if cfg.is_deit:
         model = deit.DeiT(distilled=cfg.distilled, **kw)
     else:
-        model = vitm.VisionTransformer(drop_path_rate=0.0, **kw)
+        opt = {}
+        if not cfg.class_token:
+            opt["class_token"] = False
+        if cfg.pool_type != "cls":
+            opt["pool_type"] = cfg.pool_type
+        if cfg.representation_size:
+            opt["representation_size"] = cfg.representation_size
+        model = vitm.VisionTransformer(drop_path_rate=0.0, **kw, **opt)
     sd = O.seeded_state_dict(cfg, seed)
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not missing and not unexpected, (missing, unexpected)
@@ -85,6 +92,9 @@ def run_case(cfg: O.VitConfig, batch: int, seed: int, full: bool):
         with torch.no_grad():
             rec["eval_logits"] = model(x).detach().clone()
         rec["attn_layer0"] = model.blocks[0].attn.attention_maps.clone()                   # vision_transformer_base.py:187-188
+        if not cfg.is_deit:
+            with torch.no_grad():
+                rec["eval_features"] = model.extract_features(x).detach().clone()          # :494-497 (after pre_logits)
         model.train()
         # one optimizer step exactly as Lightning would run it: clip_grad_norm_(1.0) then AdamW
         params = [p for p in model.parameters() if p.grad is not None]
@@ -100,6 +110,13 @@ def run_case(cfg: O.VitConfig, batch: int, seed: int, full: bool):
     return rec
 
 
+# constructor options of the base class outside the default tail (vision_transformer_base.py:470-477, vit_models.py:97-106)
+GAP_REP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=128, depth=2, num_heads=2, distilled=False, is_deit=False,
+                          pool_type="gap", representation_size=128)
+NOCLS_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=1, embed_dim=64, depth=2, num_heads=1, distilled=False, is_deit=False,
+                        class_token=False)
+CLS_REP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=1, embed_dim=64, depth=1, num_heads=1, distilled=False, is_deit=False,
+                          representation_size=64)
 DROP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=128, depth=2, num_heads=2, distilled=False, is_deit=False)
 
 
@@ -208,6 +225,11 @@ def main():
     assert ref_loader.available(), "run this where /root/reference is mounted"
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    torch.save(run_case(GAP_REP_VIT, 3, 45, True), GOLD / "small_vit_gap_rep.pt")
+    torch.save(run_case(NOCLS_VIT, 2, 46, True), GOLD / "small_vit_nocls.pt")
+    torch.save(run_case(CLS_REP_VIT, 2, 47, True), GOLD / "small_vit_cls_rep.pt")
+    if "--tail-only" in sys.argv:
+        return
     torch.save(run_case(SMALL_DEIT, 3, 42, True), GOLD / "small_deit.pt")
     torch.save(run_case(SMALL_VIT, 2, 43, True), GOLD / "small_vit.pt")
     torch.save(run_dropout_case(DROP_VIT, 4, 44, 0.1), GOLD / "small_vit_dropout.pt")

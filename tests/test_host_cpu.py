@@ -117,8 +117,18 @@ def test_factories_registry_and_errors():
 
 def test_unsupported_options_fail_loudly():
     m = vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, pool_type="gap")
-    with pytest.raises(NotImplementedError):
-        m._check_supported()
+    m._check_supported()                                       # gap pooling / pre_logits: general tail (csrc/pool_head.cu)
+    assert m._pool_range() == (1, 17) and m._rep_size() == 0
+    m = vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, class_token=False)
+    assert m._pool_range() == (0, 16) and m._n_prefix() == 0 and not hasattr(m, "cls_token")
+    m = vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, representation_size=64)
+    assert m._pool_range() is None and m._rep_size() == 64
+    assert [n for n, _ in m.named_parameters() if n.startswith("pre_logits")] == ["pre_logits.0.weight", "pre_logits.0.bias"]
+    m = vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, representation_size=32)
+    with pytest.raises(RuntimeError):                          # head is Linear(embed_dim, classes): same failure as the reference
+        m._rep_size()
+    with pytest.raises(AttributeError):                        # deit_models.py:84-99 (Sequential has no .weight)
+        vit.DeiT(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, distilled=True, representation_size=64)
     m = vit.create_vit_tiny(img_size=64, in_chans=3)           # factory default drop_path_rate=0.1: stochastic depth is
     m.train()                                                  # served by the engine (GPU test test_stochastic_depth_*)
     m._check_supported()

@@ -624,6 +624,88 @@ def test_head_bwd_branch_dropout():
     assert rel_l2(res[1][2], (res[0][0] * mask).sum((0, 1))) < 1e-4
 
 
+# ------------------------------------------------------------------ general classification tail (gap pooling, pre_logits)
+@pytest.mark.parametrize("B,T,D,t0,t1", [(19, 197, 192, 1, 197), (5, 196, 768, 0, 196), (3, 17, 64, 0, 1), (2, 50, 384, 7, 31)])
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_pool_norm_fwd_bwd(B, T, D, t0, t1, dt):
+    """vitk_pool_norm_{fwd,bwd} against torch fp32: mean over tokens [t0,t1) of LayerNorm(x) (vision_transformer_base.py:469-474).
+    fp32 kernels: 1e-5; the 16-bit gradient copy: rounding of the format."""
+    x = _rand(B, T, D, seed=1)
+    g = _rand(D, seed=2) * 0.1 + 1; b = _rand(D, seed=3) * 0.1
+    pooled, mean, rstd = ops.pool_norm_fwd(x, g, b, t0, t1)
+    xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)[:, t0:t1].mean(1)
+    torch.cuda.synchronize()
+    assert (pooled - ref).abs().max().item() < 1e-5
+    dp = _rand(B, D, seed=4)
+    (ref * dp).sum().backward()
+    S = 512.0
+    bs = (torch.rand(B * T, device=DEV) > 0.3).float() / 0.7            # stochastic-depth factor of the last MLP branch
+    dx = torch.full((B, T, D), 7.0, device=DEV); dx16 = torch.full((B, T, D), 3.0, dtype=dt, device=DEV)
+    dg, db_, dcs = (torch.zeros(D, device=DEV) for _ in range(3))
+    ops.pool_norm_bwd(dp, x, mean, rstd, g, dx, dx16, dg, db_, dcs, t0, t1, loss_scale=torch.tensor([S], device=DEV),
+                      branch_scale=bs)
+    torch.cuda.synchronize()
+    assert rel_l2(dx / S, xr.grad) < 1e-5
+    outside = torch.ones(T, dtype=torch.bool); outside[t0:t1] = False
+    assert dx[:, outside].abs().sum().item() == 0 and dx16[:, outside].float().abs().sum().item() == 0
+    branch = xr.grad * bs.view(B, T, 1)
+    assert rel_l2(dx16.float() / S, branch) < OUT_TOL[dt] * 2
+    assert rel_l2(dg, gr.grad) < 1e-4 and rel_l2(db_, br.grad) < 1e-4
+    assert rel_l2(dcs, branch.sum((0, 1))) < 1e-4
+
+
+def test_pool_norm_bwd_branch_dropout():
+    B, T, D = 7, 65, 128
+    x = _rand(B, T, D, seed=1)
+    g = _rand(D, seed=2) * 0.1 + 1; b = _rand(D, seed=3) * 0.1
+    _, mean, rstd = ops.pool_norm_fwd(x, g, b, 1, T)
+    dp = _rand(B, D, seed=4)
+    seed = _seed(5)
+    res = []
+    for drop in (None, (seed, 0.25, 4)):
+        dx = torch.empty(B, T, D, device=DEV); dx16 = torch.empty(B, T, D, dtype=F16, device=DEV)
+        dcs = torch.zeros(D, device=DEV)
+        ops.pool_norm_bwd(dp, x, mean, rstd, g, dx, dx16, torch.zeros(D, device=DEV), torch.zeros(D, device=DEV), dcs, 1, T,
+                          branch_drop=drop)
+        res.append((dx.clone(), dx16.float(), dcs))
+    mask = ops.dropout_mask(seed, 0.25, 4, B * T, D).view(B, T, D)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][0], res[1][0])                 # the residual path is not masked
+    assert rel_l2(res[1][1], res[0][0] * mask) < 1e-3
+    assert rel_l2(res[1][2], (res[0][0] * mask).sum((0, 1))) < 1e-4
+
+
+@pytest.mark.parametrize("B,I,O_,act", [(19, 192, 192, 1), (256, 768, 768, 1), (33, 128, 2, 0), (5, 64, 10, 0)])
+def test_dense_fwd_bwd(B, I, O_, act):
+    """vitk_dense_{fwd,bwd} (pre_logits Linear+Tanh :380-386 and the head Linear) against torch fp32, gradients ACCUMULATE."""
+    x = _rand(B, I, seed=1); W = _rand(O_, I, scale=0.05, seed=2); bias = _rand(O_, seed=3) * 0.1
+    y = ops.dense_fwd(x, W, bias, act=act)
+    xr, Wr, br = (t.clone().requires_grad_(True) for t in (x, W, bias))
+    ref = xr @ Wr.t() + br
+    ref = torch.tanh(ref) if act == 1 else ref
+    torch.cuda.synchronize()
+    assert (y - ref).abs().max().item() < 1e-5           # fp32 dot products of up to 768 terms, different summation order
+    dy = _rand(B, O_, seed=4)
+    (ref * dy).sum().backward()
+    dW = torch.ones(O_, I, device=DEV); db = torch.ones(O_, device=DEV)
+    dx = ops.dense_bwd(dy, y if act == 1 else None, x, W, dW, db, act=act)
+    torch.cuda.synchronize()
+    assert rel_l2(dx, xr.grad) < 1e-5
+    assert rel_l2(dW - 1, Wr.grad) < 1e-5 and rel_l2(db - 1, br.grad) < 1e-5
+    assert ops.dense_bwd(dy, y if act == 1 else None, x, W, dW, None, act=act, need_dx=False) is None
+
+
+def test_general_tail_rejects_bad_arguments():
+    x = _rand(2, 9, 64, seed=1); g = torch.ones(64, device=DEV); b = torch.zeros(64, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.pool_norm_fwd(x, g, b, 3, 3)             # empty token range
+    with pytest.raises(RuntimeError):
+        ops.pool_norm_fwd(x, g, b, 0, 10)            # beyond the sequence
+    with pytest.raises(RuntimeError):
+        ops.dense_fwd(x[:, 0], torch.ones(4, 64, device=DEV), None, act=2)
+
+
 # ------------------------------------------------------------------ on-device validation / test metrics (SURVEY 8 f4)
 @pytest.mark.parametrize("quant", [None, 4])
 def test_metrics_counters_and_auroc_match_oracle(quant):

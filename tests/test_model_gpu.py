@@ -30,7 +30,15 @@ def rel_l2(a, b):
 def build(cfg: O.VitConfig, seed: int):
     kw = dict(img_size=cfg.img_size, patch_size=cfg.patch_size, in_chans=cfg.in_chans, num_classes=cfg.num_classes,
               embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio)
-    m = V.DeiT(distilled=cfg.distilled, **kw) if cfg.is_deit else V.VisionTransformer(drop_path_rate=0.0, **kw)
+    opt = {}
+    if not cfg.is_deit:
+        if not cfg.class_token:
+            opt["class_token"] = False
+        if cfg.pool_type != "cls":
+            opt["pool_type"] = cfg.pool_type
+        if cfg.representation_size:
+            opt["representation_size"] = cfg.representation_size
+    m = V.DeiT(distilled=cfg.distilled, **kw) if cfg.is_deit else V.VisionTransformer(drop_path_rate=0.0, **kw, **opt)
     sd = O.seeded_state_dict(cfg, seed)
     m.load_state_dict(sd, strict=True)          # state_dict keys are the reference's
     return m.cuda(), sd
@@ -48,7 +56,7 @@ def run_gpu(model, x, y):
     return loss.item(), [o.detach().cpu() for o in outs], grads
 
 
-@pytest.mark.parametrize("name", ["small_deit", "small_vit"])
+@pytest.mark.parametrize("name", ["small_deit", "small_vit", "small_vit_gap_rep", "small_vit_nocls", "small_vit_cls_rep"])
 def test_small_models_vs_golden(name):
     rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
     cfg = O.VitConfig(**rec["config"])
@@ -71,6 +79,12 @@ def test_small_models_vs_golden(name):
     assert maps.shape == rec["attn_layer0"].shape and not maps.is_cuda
     assert (maps - rec["attn_layer0"]).abs().max().item() < 5e-3
     assert (maps.sum(-1) - 1).abs().max().item() < 1e-5
+    if "eval_features" in rec:          # gap / no-class-token pooling and pre_logits (vision_transformer_base.py:470-477)
+        with torch.no_grad():
+            feats = model.extract_features(x.cuda())
+            ff, q = model.forward_features(x.cuda())
+        assert q is None and torch.equal(ff, feats)
+        assert (feats.cpu() - rec["eval_features"]).abs().max().item() < LOGIT_TOL
 
 
 @pytest.mark.parametrize("cfg,batch,gold", [(O.DEIT_TINY, 32, None), (O.DEIT_TINY, 4, "deit_tiny_b4"), (O.VIT_BASE, 2, "vit_base_b2")])
@@ -136,6 +150,33 @@ def test_train_step_matches_oracle_adamw(use_graph):
         diff = (p.detach().cpu() - params[n]).abs()
         assert diff.max().item() < 6.5e-3 and diff.mean().item() < 1.5e-3, (n, diff.max().item(), diff.mean().item())
     assert opt.dev_state[0].item() == 3.0 and eng.amp[3].item() == 0.0        # three clean steps, none skipped
+
+
+def test_train_step_general_tail_inside_captured_graph():
+    """gap pooling + pre_logits (csrc/pool_head.cu) through the captured TrainStep: losses of three replays follow the oracle."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2, is_deit=False, distilled=False, pool_type="gap",
+                      representation_size=128)
+    model, sd = build(cfg, 11)
+    model.train()
+    opt = OPT.FusedAdamW(model, _groups(model, 1e-3, 0.05), lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+    step = TR.TrainStep(model, opt, 8, mode="ce", use_graph=True)
+    names = list(O.param_shapes(cfg))
+    tbl = O.parameter_groups(names, cfg.depth, weight_decay=0.05)
+    wd = {g["name"]: g["weight_decay"] for g in tbl}
+    sc = {g["name"]: g["lr_scale"] for g in tbl}
+    params = {k: v.clone() for k, v in sd.items()}
+    state = {}
+    for it in range(3):
+        x, y = O.seeded_batch(cfg, 8, 200 + it)
+        stats = step(x.pin_memory(), y.pin_memory()).cpu()
+        ref_loss, _, ref_grads = O.train_step(params, x, y, cfg)
+        O.clip_and_adamw_step(params, ref_grads, state, lr=1e-3, weight_decay=wd, lr_scale=sc, max_grad_norm=1.0)
+        assert abs(stats[0].item() - ref_loss.item()) < 3e-3, (it, stats[0].item(), ref_loss.item())
+    torch.cuda.synchronize()
+    eng = model._engine
+    for n in ("pre_logits.0.weight", "pre_logits.0.bias", "head.weight", "norm.weight", "blocks.1.mlp.fc2.bias"):
+        m_gpu = eng.flat.view(opt.exp_avg, n).cpu()
+        assert rel_l2(m_gpu, state["m"][n]) < 2e-2, (n, rel_l2(m_gpu, state["m"][n]))
 
 
 def test_distillation_step_matches_oracle():
@@ -402,14 +443,15 @@ def _gpu_drop_masks(m, B):
     return [ops.dropout_mask(eng.drop_seed, eng.drop_rate, site, M, c).view(B, d.tokens, c).cpu() for site, c in enumerate(cols)]
 
 
-@pytest.mark.parametrize("deit", [False, True])
-def test_dropout_training_step_matches_oracle_with_replayed_masks(deit):
+@pytest.mark.parametrize("deit,tail", [(False, {}), (True, {}), (False, dict(pool_type="gap", representation_size=128)),
+                                       (False, dict(class_token=False))])
+def test_dropout_training_step_matches_oracle_with_replayed_masks(deit, tail):
     """drop_rate > 0 (configs/model/vit/vit_base.yaml, vit_small.yaml: 0.1): pos_drop, proj_drop and both Mlp.drop calls are
     fused into the GEMM epilogues and re-derived in backward.  The masks the GPU drew are replayed into the oracle (whose
     dropout placement is pinned to the reference by tests/golden/small_vit_dropout.pt)."""
-    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=3, num_heads=2, is_deit=deit, distilled=deit)
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=3, num_heads=2, is_deit=deit, distilled=deit, **tail)
     kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=3, num_heads=2, mlp_ratio=4.0)
-    m = V.DeiT(distilled=True, drop_rate=0.2, **kw) if deit else V.VisionTransformer(drop_rate=0.2, drop_path_rate=0.2, **kw)
+    m = V.DeiT(distilled=True, drop_rate=0.2, **kw) if deit else V.VisionTransformer(drop_rate=0.2, drop_path_rate=0.2, **kw, **tail)
     sd = O.seeded_state_dict(cfg, 9)
     m.load_state_dict(sd, strict=True)
     m = m.cuda()

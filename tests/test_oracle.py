@@ -26,7 +26,7 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
-@pytest.mark.parametrize("name", ["small_deit", "small_vit"])
+@pytest.mark.parametrize("name", ["small_deit", "small_vit", "small_vit_gap_rep", "small_vit_nocls", "small_vit_cls_rep"])
 def test_oracle_matches_golden_small_full_gradients(name):
     rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
     cfg = _cfg(rec["config"])
@@ -55,6 +55,9 @@ def test_oracle_matches_golden_small_full_gradients(name):
     ev = O.forward(p, x, cfg, training=False, attn_out=attn)
     assert (ev - rec["eval_logits"]).abs().max().item() < 1e-5
     assert (attn[0] - rec["attn_layer0"]).abs().max().item() < 1e-6
+    if "eval_features" in rec:      # extract_features: pooled (cls / gap) feature after pre_logits
+        feats = O.pooled_features(p, O.forward_tokens(p, x, cfg), cfg)
+        assert (feats - rec["eval_features"]).abs().max().item() < 1e-5
 
 
 @pytest.mark.parametrize("name,batch", [("deit_tiny_b4", 4), ("vit_base_b2", 2)])

@@ -49,6 +49,9 @@ class Dims:
     classes: int
     n_prefix: int      # 1 (cls) or 2 (cls + dist)
     n_out: int         # number of classification heads (2 for a distilled DeiT)
+    pool: Optional[Tuple[int, int]] = None   # token range [t0, t1) averaged after the final norm ('gap' / no class token);
+                                             # None = the fused class-token tail (vitk_head_fwd)
+    rep: int = 0       # representation_size of `pre_logits` = Linear + Tanh (0 = Identity)
 
     @property
     def n_patches(self) -> int:
@@ -66,7 +69,7 @@ class Dims:
 def execution_order(names: List[str], depth: int) -> List[str]:
     """Reverse execution order: the order in which backward finishes each tensor's gradient."""
     def key(n: str):
-        if n.startswith("head") or n.startswith("norm."):
+        if n.startswith("head") or n.startswith("norm.") or n.startswith("pre_logits."):
             return (0, 0)
         if n.startswith("blocks."):
             return (1, depth - 1 - int(n.split(".")[1]))
@@ -288,7 +291,7 @@ class VitEngine:
         ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
                  bias=self.p("patch_embed.proj.bias"), epilogue=_lib.EPI_TOKENS,
                  tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"), drop=self._site(0))
-        ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token"),
+        ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token") if d.n_prefix >= 1 else None,
                               self.p("dist_token") if d.n_prefix == 2 else None, self.p("pos_embed"), d.n_prefix,
                               drop=self._site(0))
         for l in range(d.depth):
@@ -320,6 +323,8 @@ class VitEngine:
             pooled = torch.empty(d.n_out, B, D, dtype=torch.float32, device=self.device)
             features["pooled"] = pooled
             features["x_last"] = x_last.view(B, T, D)
+        if d.pool is not None or d.rep:
+            return self._tail_fwd(ws, x_last.view(B, T, D), train, features), None
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
                                           self.p("head.weight"), self.p("head.bias"),
                                           self.p("head_dist.weight") if two else None,
@@ -327,6 +332,36 @@ class VitEngine:
         if train:
             ws.head_saved = (xhat, rstd)
         return l0, l1
+
+    # ------------------------------------------------------------------ general classification tail
+    def _tail_range(self) -> Tuple[int, int]:
+        return self.d.pool if self.d.pool is not None else (0, 1)
+
+    def _tail_fwd(self, ws: Workspace, x_last: torch.Tensor, train: bool, features: Optional[dict]) -> torch.Tensor:
+        """norm -> pool over a token range -> pre_logits -> head (vision_transformer_base.py:468-486) for the constructor
+        options outside the fused class-token kernel: fp32 throughout, a few hundred KB per step."""
+        t0, t1 = self._tail_range()
+        pooled, mean, rstd = ops.pool_norm_fwd(x_last, self.p("norm.weight"), self.p("norm.bias"), t0, t1)
+        z = pooled
+        if self.d.rep:
+            z = ops.dense_fwd(pooled, self.p("pre_logits.0.weight"), self.p("pre_logits.0.bias"), act=1)
+        logits = ops.dense_fwd(z, self.p("head.weight"), self.p("head.bias"), act=0)
+        if features is not None:
+            features["pooled"] = z.unsqueeze(0)       # forward_features returns the pre-head feature (after pre_logits)
+        if train:
+            ws.head_saved = (pooled, mean, rstd, z, x_last)
+        return logits
+
+    def _tail_bwd(self, ws: Workspace, dl0: torch.Tensor, dx: torch.Tensor, dcolsum, branch_scale, branch_drop) -> None:
+        pooled, mean, rstd, z, x_last = ws.head_saved
+        t0, t1 = self._tail_range()
+        dz = ops.dense_bwd(dl0, None, z, self.p("head.weight"), self.g("head.weight"), self.g("head.bias"), act=0)
+        if self.d.rep:
+            dz = ops.dense_bwd(dz, z, pooled, self.p("pre_logits.0.weight"), self.g("pre_logits.0.weight"),
+                               self.g("pre_logits.0.bias"), act=1)
+        ops.pool_norm_bwd(dz, x_last, mean, rstd, self.p("norm.weight"), dx.view_as(x_last), ws.dx16, self.g("norm.weight"),
+                          self.g("norm.bias"), dcolsum, t0, t1, loss_scale=self.loss_scale, branch_scale=branch_scale,
+                          branch_drop=branch_drop)
 
     # ------------------------------------------------------------------ backward
     def backward(self, B: int, dl0: torch.Tensor, dl1: Optional[torch.Tensor]) -> None:
@@ -338,8 +373,7 @@ class VitEngine:
         ws = self.workspace(B, True)
         if ws.head_saved is None:
             raise RuntimeError("backward() called without a preceding training forward()")
-        xhat, rstd = ws.head_saved
-        ws.head_saved = None
+        general_tail = d.pool is not None or bool(d.rep)
         two = d.n_out == 2
         u = self.grad_unscale
         dp = ws.dp if getattr(ws, "dp_active", False) else None
@@ -347,12 +381,17 @@ class VitEngine:
         rs = lambda i: dp[i] if (dp is not None and i >= 0 and self.drop_path[i] > 0.0) else None
         dx, dx_alt = ws.dx[0], ws.dx[1]
         last_fc2_bias = self.g(f"blocks.{d.depth - 1}.mlp.fc2.bias")
-        ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),
-                     self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dx16,
-                     self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
-                     self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
-                     last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale, branch_scale=rs(2 * d.depth - 1),
-                     branch_drop=self._site(3 + 3 * (d.depth - 1)))
+        if general_tail:
+            self._tail_bwd(ws, dl0.contiguous(), dx, last_fc2_bias, rs(2 * d.depth - 1), self._site(3 + 3 * (d.depth - 1)))
+        else:
+            xhat, rstd = ws.head_saved
+            ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),
+                         self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dx16,
+                         self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
+                         self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
+                         last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale, branch_scale=rs(2 * d.depth - 1),
+                         branch_drop=self._site(3 + 3 * (d.depth - 1)))
+        ws.head_saved = None
         self._notify("head")
         for l in range(d.depth - 1, -1, -1):
             pre = f"blocks.{l}."
@@ -382,7 +421,8 @@ class VitEngine:
                               branch_drop=self._site(3 * l) if l > 0 else None)
             dx, dx_alt = dx_alt, dx
             self._notify(pre)
-        ops.tokens_bwd(dx.view(B, T, D), None if "pos_embed" in self.frozen else self.g("pos_embed"), self.g("cls_token"),
+        ops.tokens_bwd(dx.view(B, T, D), None if "pos_embed" in self.frozen else self.g("pos_embed"),
+                       self.g("cls_token") if d.n_prefix >= 1 else None,
                        self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g("patch_embed.proj.bias"),
                        d.n_prefix, unscale=u, drop=self._site(0))
         self._wgrad(ws.dpatch, ws.patches, "patch_embed.proj.weight", B * d.n_patches)

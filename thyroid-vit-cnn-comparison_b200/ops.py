@@ -377,3 +377,46 @@ def finish_tiles(gray, C: int, *, bounds=None, mean=None, std=None, perm=None, c
     check(_lib.load().vitk_finish_tiles(gray.data_ptr(), _p(bounds), out.data_ptr(), B, C, H, W, marr, sarr, _p(perm),
                                         int(bool(cutmix)), float(lam), x1, y1, x2, y2, _stream()), "finish_tiles")
     return out
+
+
+# --------------------------------------------------------------------------- general classification tail (gap pooling, pre_logits)
+def pool_norm_fwd(x, gamma, beta, t0: int, t1: int, eps: float = 1e-5):
+    """x fp32 [B,T,D] -> (pooled [B,D] = mean over tokens [t0,t1) of LayerNorm(x), mean [B,T], rstd [B,T])."""
+    _req(x, f32, "pool x")
+    B, T, dim = x.shape
+    pooled = torch.empty(B, dim, dtype=f32, device=x.device)
+    mean = torch.empty(B, T, dtype=f32, device=x.device)
+    rstd = torch.empty(B, T, dtype=f32, device=x.device)
+    check(_lib.load().vitk_pool_norm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), pooled.data_ptr(), mean.data_ptr(),
+                                         rstd.data_ptr(), B, T, dim, t0, t1, eps, _stream()), "pool_norm_fwd")
+    return pooled, mean, rstd
+
+
+def pool_norm_bwd(dpooled, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, dcolsum, t0: int, t1: int, loss_scale=None,
+                  branch_scale=None, branch_drop=None):
+    B, T, dim = x.shape
+    check(_lib.load().vitk_pool_norm_bwd(dpooled.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                         dx.data_ptr(), _p(dx16), _DT[dx16.dtype] if dx16 is not None else 0, dgamma.data_ptr(),
+                                         dbeta.data_ptr(), _p(dcolsum), _p(loss_scale), _p(branch_scale), _drop(branch_drop),
+                                         B, T, dim, t0, t1, _stream()), "pool_norm_bwd")
+
+
+def dense_fwd(x, W, bias, act: int = 0):
+    _req(x, f32, "dense x")
+    B, in_dim = x.shape
+    out_dim = W.shape[0]
+    y = torch.empty(B, out_dim, dtype=f32, device=x.device)
+    check(_lib.load().vitk_dense_fwd(x.data_ptr(), W.data_ptr(), _p(bias), y.data_ptr(), B, in_dim, out_dim, act, _stream()),
+          "dense_fwd")
+    return y
+
+
+def dense_bwd(dy, y, x, W, dW, db, act: int = 0, need_dx: bool = True):
+    """Returns dx [B, in_dim] (or None); dW / db are accumulated."""
+    B, in_dim = x.shape
+    out_dim = W.shape[0]
+    dz = torch.empty(B, out_dim, dtype=f32, device=x.device)
+    dx = torch.empty(B, in_dim, dtype=f32, device=x.device) if need_dx else None
+    check(_lib.load().vitk_dense_bwd(dy.data_ptr(), _p(y), x.data_ptr(), W.data_ptr(), dz.data_ptr(), _p(dx), dW.data_ptr(),
+                                     _p(db), B, in_dim, out_dim, act, _stream()), "dense_bwd")
+    return dx

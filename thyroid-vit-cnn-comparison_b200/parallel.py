@@ -51,11 +51,12 @@ def completed_prefix(order: List[str], offsets: dict, pad: int, stage: str, dept
 
     if stage == "embed":
         return end_of(order[-1])
+    tail = ("head", "norm.", "pre_logits.")
     if stage == "head":
-        names = [n for n in order if n.startswith("head") or n.startswith("norm.")]
+        names = [n for n in order if n.startswith(tail)]
         return max(end_of(n) for n in names)
     blk = int(stage.split(".")[1])
-    names = [n for n in order if n.startswith("head") or n.startswith("norm.") or
+    names = [n for n in order if n.startswith(tail) or
              (n.startswith("blocks.") and int(n.split(".")[1]) >= blk)]
     return max(end_of(n) for n in names)
 

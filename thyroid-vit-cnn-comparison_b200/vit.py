@@ -298,17 +298,30 @@ class VisionTransformerBase(_Base):
 
     # ------------------------------------------------------------------ engine plumbing
     def _n_prefix(self) -> int:
-        return 1
+        return 1 if self.class_token else 0
 
     def _n_out(self) -> int:
         return 1
 
+    def _pool_range(self):
+        """Token range averaged after the final norm, or None for class-token pooling (vision_transformer_base.py:470-474:
+        'cls' needs a class token; anything else is the mean of x[:, 1:], or of every token without a class token)."""
+        if self.pool_type == "cls" and self.class_token:
+            return None
+        n = self.num_patches + self._n_prefix()
+        return (1, n) if self.class_token else (0, n)
+
+    def _rep_size(self) -> int:
+        if isinstance(self.pre_logits, nn.Identity):
+            return 0
+        rep = self.pre_logits[0].out_features
+        if rep != self.head.in_features:      # the reference's head is Linear(embed_dim, classes) whatever representation_size is
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied: pre_logits emits {rep} features, head expects "
+                               f"{self.head.in_features} (the reference fails the same way unless representation_size == embed_dim)")
+        return rep
+
     def _check_supported(self) -> None:
         hp = self._vitk_hparams
-        if not self.class_token or self.pool_type != "cls":
-            raise NotImplementedError("the sm_100a path implements class-token pooling (pool_type='cls')")
-        if not isinstance(self.pre_logits, nn.Identity):
-            raise NotImplementedError("representation_size / pre_logits is not implemented in the sm_100a path")
         if self.training and hp.get("attn_drop_rate", 0.0):
             raise NotImplementedError("attention-probability dropout > 0 is not implemented in the sm_100a training path "
                                       "(drop_rate and stochastic depth are; every ViT/DeiT config of the reference uses 0)")
@@ -336,7 +349,7 @@ class VisionTransformerBase(_Base):
             dims = Dims(img=self.patch_embed.img_size, patch=self.patch_embed.patch_size, chans=self.in_chans,
                         dim=self.embed_dim, depth=len(self.blocks), heads=blk.attn.num_heads,
                         hidden=blk.mlp.fc1.out_features, classes=self.num_classes, n_prefix=self._n_prefix(),
-                        n_out=self._n_out())
+                        n_out=self._n_out(), pool=self._pool_range(), rep=self._rep_size())
             eng = VitEngine(dims, OrderedDict((n, p.data) for n, p in named.items()), first.device,
                             dtype16=self._vitk_hparams.get("compute_dtype", torch.float16))
             for n, p in named.items():        # re-point the module's parameters at the flat buffers
@@ -605,7 +618,9 @@ class DeiT(VisionTransformer):
             self.num_tokens = 2
             self.head_dist = nn.Linear(self.embed_dim, num_classes)
             if self.representation_size:
-                raise NotImplementedError("representation_size is not implemented in the sm_100a path")
+                # deit_models.py:84-99 replaces head_dist by a Sequential and then initialises `.weight` of it
+                raise AttributeError("'Sequential' object has no attribute 'weight' (the reference's distilled DeiT cannot be "
+                                     "built with representation_size, deit_models.py:84-99)")
             self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + self.num_tokens, self.embed_dim))
             nn.init.trunc_normal_(self.dist_token, std=0.02)
             nn.init.trunc_normal_(self.head_dist.weight, std=0.02)
@@ -619,6 +634,9 @@ class DeiT(VisionTransformer):
 
     def _n_out(self) -> int:
         return 2 if self.distilled else 1
+
+    def _pool_range(self):
+        return None          # DeiT.forward reads x[:, 0] / x[:, 1] whatever pool_type says (deit_models.py:220-238)
 
     def load_pretrained_weights(self):
         """deit_models.py:109-139 pulls ImageNet weights through timm + network; neither exists here."""
