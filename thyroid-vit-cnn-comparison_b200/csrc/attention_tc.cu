@@ -346,9 +346,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   uint64_t* bar_o = bars + 2;       // O landed
   uint64_t* bar_s = bars + 3;       // S^T, dP^T of chunk t complete
   uint64_t* bar_ld = bars + 4;      // every math thread has S^T, dP^T of chunk t in registers
-  uint64_t* bar_p = bars + 5;       // P^T, dS^T (TMEM + staging) of chunk t written
-  uint64_t* bar_m2 = bars + 6;      // [2] dV / dK / dQ MMAs that read P/dS buffer (t & 1) complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // [2] P^T, dS^T (TMEM + staging) of chunk t written, one barrier per buffer (t & 1), phase t >> 1.  A SINGLE barrier with
+  // parity t & 1 deadlocks once in ~1e7 CTAs: S^T/dP^T of chunk t+1 are committed before the issuer consumes bar_p(t), so when
+  // chunk t+1 is the short tail chunk (16 of 208 queries) the math warps can complete phase t+1 within a few hundred ns of
+  // phase t, and an issuer that has not yet polled sees the parity of phase t+2 and waits for ever.  With one barrier per
+  // buffer the next phase of the same barrier belongs to chunk t+2, whose operands are only issued after bar_p(t) was seen.
+  uint64_t* bar_p = bars + 5;
+  uint64_t* bar_m2 = bars + 7;      // [2] dV / dK / dQ MMAs that read P/dS buffer (t & 1) complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -367,7 +372,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       mbar_init(bar_o, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_ld, 256);
-      mbar_init(bar_p, 256);
+      mbar_init(bar_p + 0, 256);
+      mbar_init(bar_p + 1, 256);
       mbar_init(bar_m2 + 0, 1);
       mbar_init(bar_m2 + 1, 1);
       mbar_init_fence();
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
             issue_dp(j1, c1);
             umma_commit(bar_s);
           }
-          mbar_wait(bar_p, t & 1, 4);
+          mbar_wait(bar_p + (t & 1), (t >> 1) & 1, 4);
           tc_fence_after();
           ASTAMP(5 + 4 * t);
           const int buf = t & 1;
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
-        mbar_arrive(bar_p);
+        mbar_arrive(bar_p + buf);
         if (tid == 0) ASTAMP(72 + 8 * t);
         if (c == NCH - 1) {
           // ---- key tile j is complete: dV_j (half 0) / dK_j (half 1) -> 16-bit -> staging -> TMA store

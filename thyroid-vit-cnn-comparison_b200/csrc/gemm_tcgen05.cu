@@ -122,17 +122,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  The budget is 8 s of
+// ACCUMULATED waiting, each sample clamped to 1 ms: %globaltimer is a wall clock, and a step of that clock must not be
+// mistaken for a hang.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-  unsigned long long t0 = 0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned long long prev = 0, waited = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prev));
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 4000000000ull) {  // 4 s
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      const unsigned long long d = now - prev;
+      prev = now;
+      waited += d < 1000000ull ? d : 1000000ull;
+      if (waited > 8000000000ull) {
         printf("vitk gemm: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
         __trap();
       }

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--json", default="")
+    ap.add_argument("--warm", type=int, default=2, help="untimed launches per case (0 under ncu --set full: one launch per case)")
     a = ap.parse_args()
     B = a.batch
     if a.model == "deit_tiny":
@@ -103,7 +104,7 @@ def main():
     for name, (fn, nbytes, flops) in cases.items():
         if only and name not in only:
             continue
-        for _ in range(2):
+        for _ in range(a.warm):
             fn()
         torch.cuda.synchronize()
         ts = []
