@@ -178,19 +178,27 @@ def workload_config(args, cpu: bool = False):
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, profiles/): label of the
-# live per-kernel profile -> case name of tools/kbench.py the capture was taken with (DeiT-tiny shapes, batch 256)
+# live per-kernel profile -> case name of tools/kbench.py the capture was taken with (same shapes, batch 256)
 NCU_CASES = {
-    "attention_bwd": "attn_bwd", "attention_fwd": "attn_fwd", "layernorm_bwd": "ln_bwd", "layernorm_fwd": "ln_fwd",
-    "gemm_tcgen05[fwd] 50688x768x192 epi1": "gemm_gelu", "gemm_tcgen05[fwd] 50688x576x192 epi0": "gemm_qkv",
-    "gemm_tcgen05[fwd] 50688x192x192 epi0": "gemm_proj", "gemm_tcgen05[dgrad] 50688x768x192 epi2": "dgrad_dgelu",
-    "gemm_tcgen05[wgrad] 768x192x50688 epi3": "wgrad_fc1",
+    "deit_tiny": {
+        "attention_bwd": "attn_bwd", "attention_fwd": "attn_fwd", "layernorm_bwd": "ln_bwd", "layernorm_fwd": "ln_fwd",
+        "gemm_tcgen05[fwd] 50688x768x192 epi1": "gemm_gelu", "gemm_tcgen05[fwd] 50688x576x192 epi0": "gemm_qkv",
+        "gemm_tcgen05[fwd] 50688x192x768 epi0": "gemm_fc2", "gemm_tcgen05[dgrad] 50688x192x768 epi0": "dgrad_fc1",
+        "gemm_tcgen05[wgrad] 768x192x50688 epi3": "wgrad_fc1",
+    },
+    "vit_base": {
+        "attention_bwd": "attn_bwd", "attention_fwd": "attn_fwd", "layernorm_bwd": "ln_bwd", "layernorm_fwd": "ln_fwd",
+        "gemm_tcgen05[fwd] 50432x3072x768 epi1": "gemm_gelu", "gemm_tcgen05[fwd] 50432x2304x768 epi0": "gemm_qkv",
+        "gemm_tcgen05[fwd] 50432x768x3072 epi0": "gemm_fc2", "gemm_tcgen05[dgrad] 50432x768x3072 epi0": "dgrad_fc1",
+        "gemm_tcgen05[wgrad] 3072x768x50432 epi3": "wgrad_fc1",
+    },
 }
 
 
 def ncu_traffic(model: str, label: str):
-    f = ROOT / "profiles" / "r01_ncu_traffic_deit_tiny.json"
-    case = NCU_CASES.get(label)
-    if model != "deit_tiny" or case is None or not f.exists():
+    f = ROOT / "profiles" / f"r01_ncu_traffic_{model}.json"
+    case = NCU_CASES.get(model, {}).get(label)
+    if case is None or not f.exists():
         return None, None
     ent = json.loads(f.read_text()).get(case)
     return (ent["dram_bytes"], f"profiles/{f.name}:{case}") if ent else (None, None)
