@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 12
+#define VITK_ABI_VERSION 13
 
 typedef enum {
   VITK_OK = 0,
@@ -165,6 +165,15 @@ int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, float* lse, fl
 int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                        float* delta, void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H,
                        float scale, void* stream);
+/* The same pair with nn.Dropout on the softmax output (Attention.attn_drop, vision_transformer_base.py:184), training mode
+ * only: out = (P o M) V, M[b,h,q,key] = 0 | 1/(1-p) from the counter-based generator at element
+ * ((b*H + h)*N + q)*Npad + key, Npad = N rounded up to 8 -- i.e. vitk_dropout_mask(seed, p, site, B*H*N, Npad)[:, :N];
+ * lse is that of the unmasked P; the backward re-derives M (nothing is stored).  0 < p < 1 required. */
+int vitk_attention_dropout_fwd(const void* qkv, void* out, int32_t dtype, float* lse, int32_t B, int32_t N,
+                               int32_t H, float scale, const vitk_dropout* attn_drop, void* stream);
+int vitk_attention_dropout_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                               float* delta, void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H,
+                               float scale, const vitk_dropout* attn_drop, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch / token plumbing -- vision_transformer_base.py:120-143 (PatchEmbed.forward),
@@ -174,6 +183,10 @@ int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const
  * the flattening order of Conv2d.weight[D,C,P,P]) */
 int vitk_patchify(const float* images, void* patches, int32_t patches_dtype, int32_t B, int32_t C,
                   int32_t H, int32_t W, int32_t P, void* stream);
+/* the same gather with channel-last patch vectors, k = (ky*P + kx)*C + c: PatchEmbed(projection_type='linear'),
+ * einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' followed by nn.Linear (vision_transformer_base.py:102-107, :140) */
+int vitk_patchify_hwc(const float* images, void* patches, int32_t patches_dtype, int32_t B, int32_t C,
+                      int32_t H, int32_t W, int32_t P, void* stream);
 /* x[b, t, :] = drop(tok_t + pos[t, :]) for t < n_prefix (cls, dist); drop = pos_drop (optional) */
 int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok, const float* pos,
                            int32_t B, int32_t tokens_per_img, int32_t dim, int32_t n_prefix,

@@ -10,6 +10,8 @@ Fixtures
                                  after one clip+AdamW step, eval-mode logits, attention maps of layer 0.
   deit_tiny_b4.pt / vit_base_b2.pt  full-size models: logits, loss, per-parameter gradient norm and the
                                  gradient's projection on a seeded random direction (compact but sensitive).
+  small_vit_attn_dropout.pt      the same with attn_drop_rate = 0.2 on top (Attention.attn_drop, :184): its keep masks [B,H,N,N] per block too.
+  small_vit_{gap_rep,nocls,cls_rep,linear_proj}.pt   constructor options outside the default tail / patch projection.
   small_vit_dropout.pt           ViT (embed 128, 2 heads, depth 2) with drop_rate = 0.1 in training mode: the keep masks every
                                  nn.Dropout call drew (forward hooks, site order pos_drop, then per block proj_drop, Mlp.drop #1,
                                  Mlp.drop #2), logits, loss, full gradients -- pins WHERE the reference applies dropout.
@@ -54,6 +56,8 @@ def build_reference(cfg: O.VitConfig, seed: int):
             opt["pool_type"] = cfg.pool_type
         if cfg.representation_size:
             opt["representation_size"] = cfg.representation_size
+        if cfg.projection_type != "conv":
+            opt["projection_type"] = cfg.projection_type
         model = vitm.VisionTransformer(drop_path_rate=0.0, **kw, **opt)
     sd = O.seeded_state_dict(cfg, seed)
     missing, unexpected = model.load_state_dict(sd, strict=False)
@@ -117,14 +121,17 @@ NOCLS_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=1, embed_dim=64, de
                         class_token=False)
 CLS_REP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=1, embed_dim=64, depth=1, num_heads=1, distilled=False, is_deit=False,
                           representation_size=64)
+LINEAR_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=64, depth=1, num_heads=1, distilled=False, is_deit=False,
+                         projection_type="linear")
 DROP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=128, depth=2, num_heads=2, distilled=False, is_deit=False)
+ATTN_DROP_VIT = O.VitConfig(img_size=64, patch_size=16, in_chans=3, embed_dim=128, depth=2, num_heads=2, distilled=False, is_deit=False)
 
 
-def run_dropout_case(cfg: O.VitConfig, batch: int, seed: int, drop_rate: float):
+def run_dropout_case(cfg: O.VitConfig, batch: int, seed: int, drop_rate: float, attn_drop_rate: float = 0.0):
     base, vitm, deit = ref_loader.load()
     kw = dict(img_size=cfg.img_size, patch_size=cfg.patch_size, in_chans=cfg.in_chans, num_classes=cfg.num_classes,
               embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads, mlp_ratio=cfg.mlp_ratio)
-    model = vitm.VisionTransformer(drop_path_rate=0.0, drop_rate=drop_rate, **kw)
+    model = vitm.VisionTransformer(drop_path_rate=0.0, drop_rate=drop_rate, attn_drop_rate=attn_drop_rate, **kw)
     sd = O.seeded_state_dict(cfg, seed)
     model.load_state_dict(sd, strict=True)
     calls = {}
@@ -138,6 +145,8 @@ def run_dropout_case(cfg: O.VitConfig, batch: int, seed: int, drop_rate: float):
     for i, blk in enumerate(model.blocks):
         blk.attn.proj_drop.register_forward_hook(hook(f"proj{i}"))
         blk.mlp.drop.register_forward_hook(hook(f"mlp{i}"))
+        if attn_drop_rate > 0:
+            blk.attn.attn_drop.register_forward_hook(hook(f"attn{i}"))                    # :184, input = softmax output (> 0)
     x, y = O.seeded_batch(cfg, batch, seed)
     torch.manual_seed(seed)
     model.train()
@@ -148,7 +157,9 @@ def run_dropout_case(cfg: O.VitConfig, batch: int, seed: int, drop_rate: float):
     for i in range(cfg.depth):
         assert len(calls[f"proj{i}"]) == 1 and len(calls[f"mlp{i}"]) == 2
         masks += [calls[f"proj{i}"][0], calls[f"mlp{i}"][0], calls[f"mlp{i}"][1]]
+    attn_masks = [calls[f"attn{i}"][0] for i in range(cfg.depth)] if attn_drop_rate > 0 else None
     return {"config": cfg.__dict__, "batch": batch, "seed": seed, "drop_rate": drop_rate, "keep_masks": masks,
+            "attn_drop_rate": attn_drop_rate, "attn_keep_masks": attn_masks,
             "loss": loss.item(), "logits": out.detach().clone(),
             "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}}
 
@@ -228,6 +239,8 @@ def main():
     torch.save(run_case(GAP_REP_VIT, 3, 45, True), GOLD / "small_vit_gap_rep.pt")
     torch.save(run_case(NOCLS_VIT, 2, 46, True), GOLD / "small_vit_nocls.pt")
     torch.save(run_case(CLS_REP_VIT, 2, 47, True), GOLD / "small_vit_cls_rep.pt")
+    torch.save(run_case(LINEAR_VIT, 2, 48, True), GOLD / "small_vit_linear_proj.pt")
+    torch.save(run_dropout_case(ATTN_DROP_VIT, 2, 49, 0.1, 0.2), GOLD / "small_vit_attn_dropout.pt")
     if "--tail-only" in sys.argv:
         return
     torch.save(run_case(SMALL_DEIT, 3, 42, True), GOLD / "small_deit.pt")

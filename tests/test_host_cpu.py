@@ -129,6 +129,11 @@ def test_unsupported_options_fail_loudly():
         m._rep_size()
     with pytest.raises(AttributeError):                        # deit_models.py:84-99 (Sequential has no .weight)
         vit.DeiT(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, distilled=True, representation_size=64)
+    m = vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, projection_type="linear")
+    assert [n for n, _ in m.named_parameters() if n.startswith("patch_embed.proj")] == ["patch_embed.proj.1.weight", "patch_embed.proj.1.bias"]
+    assert m.patch_embed.proj[1].weight.shape == (64, 16 * 16 * 3)      # vision_transformer_base.py:103-107
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=1, num_heads=1, in_chans=3, is_deit=False, distilled=False, projection_type="linear")
+    assert [n for n, _ in m.named_parameters()] == list(O.param_shapes(cfg))
     m = vit.create_vit_tiny(img_size=64, in_chans=3)           # factory default drop_path_rate=0.1: stochastic depth is
     m.train()                                                  # served by the engine (GPU test test_stochastic_depth_*)
     m._check_supported()
@@ -137,10 +142,10 @@ def test_unsupported_options_fail_loudly():
     m._check_supported()
     m = vit.create_vit_tiny(img_size=64, in_chans=3, attn_drop_rate=0.1)
     m.train()
-    with pytest.raises(NotImplementedError):                   # dropout on attention probabilities is not
-        m._check_supported()
-    m.eval()
-    m._check_supported()                                       # identity in eval
+    m._check_supported()                                       # attention-probability dropout: vitk_attention_dropout_{fwd,bwd}
+    assert m.blocks[0].attn.attn_drop.p == 0.1
+    with pytest.raises(NotImplementedError):                   # only the exact-erf GELU of the reference is fused
+        vit.VisionTransformer(img_size=64, embed_dim=64, depth=1, num_heads=1, act_layer=torch.nn.ReLU)
 
 
 def test_flat_layout_and_completed_prefix():

@@ -246,6 +246,39 @@ def test_attention_fwd_bwd(B, N, H, dt):
     assert rel_l2(dqkv, qr.grad) < 2 * tol
 
 
+@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (1, 64, 1), (2, 577, 3), (1, 17, 2)])
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_attention_dropout_fwd_bwd(B, N, H, dt):
+    """vitk_attention_dropout_{fwd,bwd}: nn.Dropout on the softmax output (vision_transformer_base.py:184).  The mask is the
+    library's counter-based one, exported with vitk_dropout_mask and replayed into an fp32 torch restatement."""
+    scale, p, site = 64 ** -0.5, 0.25, 1003
+    tol = {F16: 1e-3, BF16: 8e-3}[dt]
+    qkv = _rand(B, N, 3 * H * 64, dtype=dt, seed=1)
+    seed = torch.tensor([12345], dtype=torch.int64, device=DEV)
+    npad = (N + 7) // 8 * 8
+    mask = ops.dropout_mask(seed, p, site, B * H * N, npad).view(B, H, N, npad)[..., :N]
+    if mask.numel() > 50000:                              # drop frequency (the 17-token case is too small a sample)
+        assert abs((mask == 0).float().mean().item() - p) < 0.02
+    assert all(v == 0.0 or abs(v - 1.0 / (1.0 - p)) < 1e-6 for v in mask.unique().tolist())
+    out, lse = ops.attention_fwd(qkv, B, N, H, scale, drop=(seed, p, site))
+    qr = qkv.float().requires_grad_(True)
+    q, k, v = qr.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    sc = (q @ k.transpose(-2, -1)) * scale
+    o_ref = ((sc.softmax(-1) * mask) @ v).transpose(1, 2).reshape(B, N, H * 64)
+    torch.cuda.synchronize()
+    assert rel_l2(out, o_ref) < tol
+    assert (lse - torch.logsumexp(sc, -1)).abs().max().item() < 2e-3           # lse is that of the unmasked probabilities
+    dout = _rand(B, N, H * 64, dtype=dt, seed=2)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, scale, drop=(seed, p, site))
+    o_ref.backward(dout.float())
+    torch.cuda.synchronize()
+    assert rel_l2(dqkv, qr.grad) < 2 * tol
+    out2, _ = ops.attention_fwd(qkv, B, N, H, scale, drop=(seed + 1, p, site))  # another seed: another mask
+    assert not torch.equal(out2, out)
+    with pytest.raises(RuntimeError):
+        ops.attention_fwd(qkv, B, N, H, scale, drop=(seed, 1.0, site))
+
+
 def test_attention_probs_rows_sum_to_one():
     B, N, H = 2, 198, 3
     qkv = _rand(B, N, 3 * H * 64, dtype=F16, seed=1)
@@ -267,6 +300,12 @@ def test_patchify(B, C, S, P, dt):
     ref = torch.nn.functional.unfold(img, P, stride=P).transpose(1, 2).reshape(-1, C * P * P)
     torch.cuda.synchronize()
     assert torch.equal(out, ref.to(dt))
+    # channel-last patch vectors (PatchEmbed projection_type='linear'): einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'
+    out2 = ops.patchify(img, P, dtype=dt, channel_last=True)
+    g = S // P
+    ref2 = img.reshape(B, C, g, P, g, P).permute(0, 2, 4, 3, 5, 1).reshape(-1, P * P * C)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref2.to(dt))
 
 
 def test_prefix_and_tokens_bwd():

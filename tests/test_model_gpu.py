@@ -38,6 +38,8 @@ def build(cfg: O.VitConfig, seed: int):
             opt["pool_type"] = cfg.pool_type
         if cfg.representation_size:
             opt["representation_size"] = cfg.representation_size
+        if cfg.projection_type != "conv":
+            opt["projection_type"] = cfg.projection_type
     m = V.DeiT(distilled=cfg.distilled, **kw) if cfg.is_deit else V.VisionTransformer(drop_path_rate=0.0, **kw, **opt)
     sd = O.seeded_state_dict(cfg, seed)
     m.load_state_dict(sd, strict=True)          # state_dict keys are the reference's
@@ -56,7 +58,7 @@ def run_gpu(model, x, y):
     return loss.item(), [o.detach().cpu() for o in outs], grads
 
 
-@pytest.mark.parametrize("name", ["small_deit", "small_vit", "small_vit_gap_rep", "small_vit_nocls", "small_vit_cls_rep"])
+@pytest.mark.parametrize("name", ["small_deit", "small_vit", "small_vit_gap_rep", "small_vit_nocls", "small_vit_cls_rep", "small_vit_linear_proj"])
 def test_small_models_vs_golden(name):
     rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
     cfg = O.VitConfig(**rec["config"])
@@ -150,6 +152,32 @@ def test_train_step_matches_oracle_adamw(use_graph):
         diff = (p.detach().cpu() - params[n]).abs()
         assert diff.max().item() < 6.5e-3 and diff.mean().item() < 1.5e-3, (n, diff.max().item(), diff.mean().item())
     assert opt.dev_state[0].item() == 3.0 and eng.amp[3].item() == 0.0        # three clean steps, none skipped
+
+
+def test_layernorm_eps_follows_the_norm_layer():
+    """norm_layer=partial(nn.LayerNorm, eps=1e-6) (timm's convention) must reach every LayerNorm kernel: with eps = 1e-2 the
+    logits differ visibly from the eps = 1e-5 ones and must follow an fp32 torch restatement with that eps."""
+    from functools import partial
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=2, num_heads=1, is_deit=False, distilled=False)
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=64, depth=2, num_heads=1, mlp_ratio=4.0)
+    sd = O.seeded_state_dict(cfg, 21)
+    x, _ = O.seeded_batch(cfg, 4, 21)
+    outs = {}
+    for eps in (1e-5, 1e-2):
+        m = V.VisionTransformer(drop_path_rate=0.0, norm_layer=partial(torch.nn.LayerNorm, eps=eps), **kw)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            outs[eps] = m(x.cuda()).cpu()
+    assert (outs[1e-5] - O.forward(sd, x, cfg, training=False)).abs().max().item() < LOGIT_TOL
+    saved = O.LN_EPS
+    try:
+        O.LN_EPS = 1e-2            # the oracle's functions read the module constant at call time
+        ref = O.forward(sd, x, cfg, training=False)
+    finally:
+        O.LN_EPS = saved
+    assert (outs[1e-2] - ref).abs().max().item() < LOGIT_TOL
+    assert (outs[1e-2] - outs[1e-5]).abs().max().item() > 10 * LOGIT_TOL
 
 
 def test_train_step_general_tail_inside_captured_graph():
@@ -499,11 +527,44 @@ def test_dropout_inside_captured_graph_draws_fresh_masks():
     assert all(torch.isfinite(s).all() for s in stats)
 
 
-def test_attention_dropout_still_fails_loudly():
-    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=1, num_heads=2, mlp_ratio=4.0)
-    m = V.VisionTransformer(attn_drop_rate=0.1, **kw).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(2, 3, 64, 64, device="cuda"))
+def _gpu_attn_masks(model, B):
+    eng = model._engine
+    d = eng.d
+    npad = (d.tokens + 7) // 8 * 8
+    return [ops.dropout_mask(eng.drop_seed, eng.attn_drop_rate, eng.ATTN_SITE0 + l, B * d.heads * d.tokens, npad)
+            .view(B, d.heads, d.tokens, npad)[..., :d.tokens].cpu() for l in range(d.depth)]
+
+
+@pytest.mark.parametrize("drop_rate", [0.0, 0.1])
+def test_attention_dropout_training_step_matches_oracle_with_replayed_masks(drop_rate):
+    """attn_drop_rate > 0 (Attention.attn_drop, vision_transformer_base.py:184; no shipped config uses it): the masks the GPU
+    drew are replayed into the oracle, whose placement of that Dropout is pinned by tests/golden/small_vit_attn_dropout.pt."""
+    cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2, is_deit=False, distilled=False)
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4.0)
+    m = V.VisionTransformer(drop_rate=drop_rate, attn_drop_rate=0.2, drop_path_rate=0.0, **kw)
+    sd = O.seeded_state_dict(cfg, 13)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    B = 8
+    x, y = O.seeded_batch(cfg, B, 13)
+    torch.manual_seed(6)
+    loss, outs, grads = run_gpu(m, x, y)
+    amasks = _gpu_attn_masks(m, B)
+    for mk in amasks:
+        assert abs((mk == 0).float().mean().item() - 0.2) < 0.03
+    masks = _gpu_drop_masks(m, B) if drop_rate > 0 else None
+    ref_loss, ref_out, ref_grads = O.train_step(sd, x, y, cfg, drop_masks=masks, attn_masks=amasks)
+    assert (outs[0] - ref_out).abs().max().item() < LOGIT_TOL
+    assert abs(loss - ref_loss.item()) < 2e-3
+    for n, g in ref_grads.items():
+        if g is None or "quality_score" in n:
+            continue
+        assert rel_l2(grads[n], g) < GRAD_TOL, (n, rel_l2(grads[n], g))
+    m.eval()                                               # identity in eval mode, maps are the plain softmax
+    with torch.no_grad():
+        e = m(x.cuda()).cpu()
+    assert (e - O.forward(sd, x, cfg, training=False)).abs().max().item() < LOGIT_TOL
+    assert (m.blocks[0].attn.attention_maps.sum(-1) - 1).abs().max().item() < 1e-5
 
 
 def test_eval_steps_accumulate_device_metrics():

@@ -26,7 +26,7 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
-@pytest.mark.parametrize("name", ["small_deit", "small_vit", "small_vit_gap_rep", "small_vit_nocls", "small_vit_cls_rep"])
+@pytest.mark.parametrize("name", ["small_deit", "small_vit", "small_vit_gap_rep", "small_vit_nocls", "small_vit_cls_rep", "small_vit_linear_proj"])
 def test_oracle_matches_golden_small_full_gradients(name):
     rec = torch.load(GOLD / f"{name}.pt", weights_only=False)
     cfg = _cfg(rec["config"])
@@ -174,6 +174,24 @@ def test_oracle_dropout_sites_match_reference_with_replayed_masks():
     wrong = list(masks)
     wrong[1], wrong[3] = wrong[3], wrong[1]
     assert (O.forward(sd, x, cfg, drop_masks=wrong) - rec["logits"]).abs().max().item() > 1e-4
+
+
+def test_oracle_attention_dropout_site_matches_reference_with_replayed_masks():
+    """attn_drop_rate = 0.2 (+ drop_rate 0.1): Attention.attn_drop acts on the softmax output before attn @ v
+    (vision_transformer_base.py:183-191); the masks the REFERENCE drew, replayed, must reproduce its logits / loss / gradients."""
+    rec = torch.load(GOLD / "small_vit_attn_dropout.pt", weights_only=False)
+    cfg = _cfg(rec["config"])
+    sd = O.seeded_state_dict(cfg, rec["seed"])
+    x, y = O.seeded_batch(cfg, rec["batch"], rec["seed"])
+    masks = [m.float() / (1.0 - rec["drop_rate"]) for m in rec["keep_masks"]]
+    amasks = [m.float() / (1.0 - rec["attn_drop_rate"]) for m in rec["attn_keep_masks"]]
+    assert len(amasks) == cfg.depth and amasks[0].shape == (rec["batch"], cfg.num_heads, cfg.num_tokens, cfg.num_tokens)
+    loss, out, grads = O.train_step(sd, x, y, cfg, drop_masks=masks, attn_masks=amasks)
+    assert abs(loss.item() - rec["loss"]) < 1e-6
+    assert (out - rec["logits"]).abs().max().item() < 1e-5
+    for n, g in rec["grads"].items():
+        assert _rel(grads[n], g) < 1e-5, n
+    assert (O.forward(sd, x, cfg, drop_masks=masks) - rec["logits"]).abs().max().item() > 1e-4     # without the attention masks: visible
 
 
 def test_oracle_metrics_match_sklearn():

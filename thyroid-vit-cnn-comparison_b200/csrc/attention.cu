@@ -151,9 +151,13 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 }
 
 // ------------------------------------------------------------------ forward
-template <bool H16>
+// DROP: nn.Dropout on the softmax output (Attention.attn_drop, vision_transformer_base.py:184): O = (P o M) V with the
+// counter-based factors M[b,h,q,key] = 0 | 1/(1-p) of element (((b*H + h)*N + q)*Npad + key) at `drop.site`; the row sum and
+// lse stay those of the unmasked P.  The backward kernels re-derive M from the same counters.
+template <bool H16, bool DROP>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                       float* __restrict__ lse, int N, int H, float scale_log2) {
+                                                       float* __restrict__ lse, int N, int H, float scale_log2, DropSpec drop,
+                                                       int Npad) {
   __shared__ __align__(128) bf16 sQ[TILE * DH];
   __shared__ __align__(128) bf16 sK[2][TILE * DH];
   __shared__ __align__(128) bf16 sV[2][TILE * DH];
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
   float o[8][4];
   zero_acc(o);
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
 
   for (int j = 0; j < nkv; ++j) {
     const int buf = j & 1;
@@ -228,6 +233,20 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rsum[r];
+    if (DROP) {   // this thread's two adjacent keys of every 8-key group share one counter block
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long q = q0 + warp * 16 + g + r * 8;
+        const unsigned long long rowblk = ((unsigned long long)(((long long)b * H + h) * N + q) * Npad + j * TILE) >> 3;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint4 bits = drop_bits8(dseed, drop.site, rowblk + nt);
+          const float2 f = drop_pair(t == 0 ? bits.x : t == 1 ? bits.y : t == 2 ? bits.z : bits.w, drop.thresh, drop.inv_keep);
+          s[nt][2 * r] *= f.x;
+          s[nt][2 * r + 1] *= f.y;
+        }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       o[nt][0] *= corr[0]; o[nt][1] *= corr[0]; o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
@@ -287,11 +306,11 @@ struct BwdSmem {
   float delta[2][TILE];
 };
 
-template <bool H16>
+template <bool H16, bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                             const float* __restrict__ lse, const float* __restrict__ delta,
                                                             bf16* __restrict__ dqkv, int N, int H, float scale,
-                                                            float scale_log2) {
+                                                            float scale_log2, DropSpec drop, int Npad) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int k0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -354,9 +373,37 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
         st[nt][e] = ok ? exp2f(st[nt][e] * scale_log2 - sm.lse2[buf][ql]) : 0.f;
       }
     }
-    // dV += P^T dO
-    gemm_p_x<H16>(dv, st, sm.d[buf], lane);
-    // dP^T = V_w dO^T
+    // dropout factors of this thread's (query, key) elements: transposed walk, so one counter block per element
+    float mk[DROP ? 8 : 1][4];
+    if (DROP) {
+      const unsigned long long dseed = __ldg(drop.seed);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long q = (long long)i * TILE + nt * 8 + 2 * t + (e & 1);
+          const int key = k0 + warp * 16 + g + (e >> 1) * 8;
+          const unsigned long long el = (unsigned long long)(((long long)b * H + h) * N + q) * Npad + key;
+          const uint4 bits = drop_bits8(dseed, drop.site, el >> 3);
+          const int jj = int(el & 7);
+          const uint32_t w = jj < 2 ? bits.x : jj < 4 ? bits.y : jj < 6 ? bits.z : bits.w;
+          mk[nt][e] = (((jj & 1) ? (w >> 16) : (w & 0xffffu)) >= drop.thresh) ? drop.inv_keep : 0.f;
+        }
+      }
+    }
+    // dV += (P o M)^T dO
+    if (DROP) {
+      float pm[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pm[nt][e] = st[nt][e] * mk[DROP ? nt : 0][e];
+      }
+      gemm_p_x<H16>(dv, pm, sm.d[buf], lane);
+    } else {
+      gemm_p_x<H16>(dv, st, sm.d[buf], lane);
+    }
+    // dP^T = V_w dO^T (o M)
     float dp[8][4];
     zero_acc(dp);
     gemm_a_xt<H16>(dp, vf, sm.d[buf], lane);
@@ -366,7 +413,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int ql = nt * 8 + 2 * t + (e & 1);
-        dp[nt][e] = st[nt][e] * (dp[nt][e] - sm.delta[buf][ql]);
+        const float dpe = DROP ? dp[nt][e] * mk[DROP ? nt : 0][e] : dp[nt][e];
+        dp[nt][e] = st[nt][e] * (dpe - sm.delta[buf][ql]);
       }
     }
     // dK += dS^T Q
@@ -389,11 +437,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const bf16* __restri
 }
 
 // ------------------------------------------------------------------ backward: dQ
-template <bool H16>
+template <bool H16, bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                           const float* __restrict__ lse, const float* __restrict__ delta,
                                                           bf16* __restrict__ dqkv, int N, int H, float scale,
-                                                          float scale_log2) {
+                                                          float scale_log2, DropSpec drop, int Npad) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // reuse BwdSmem: k/v fields hold Q and dO of this CTA, q/d double buffers hold K and V blocks
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -454,6 +502,21 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
     float dp[8][4];
     zero_acc(dp);
     gemm_a_xt<H16>(dp, dof, sm.d[buf], lane);  // dP = dO V^T
+    if (DROP) {                                // dP o M (same counter walk as the forward)
+      const unsigned long long dseed = __ldg(drop.seed);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long q = q0 + warp * 16 + g + r * 8;
+        const unsigned long long rowblk = ((unsigned long long)(((long long)b * H + h) * N + q) * Npad + j * TILE) >> 3;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint4 bits = drop_bits8(dseed, drop.site, rowblk + nt);
+          const float2 f = drop_pair(t == 0 ? bits.x : t == 1 ? bits.y : t == 2 ? bits.z : bits.w, drop.thresh, drop.inv_keep);
+          dp[nt][2 * r] *= f.x;
+          dp[nt][2 * r + 1] *= f.y;
+        }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -540,8 +603,8 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* pro
     if (rc != VITK_OK) return rc;
   } else {
     dim3 grid((N + TILE - 1) / TILE, H, B);
-    attn_fwd_kernel<H16><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse, N, H,
-                                               scale * LOG2E);
+    attn_fwd_kernel<H16, false><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse, N, H,
+                                                      scale * LOG2E, make_drop_spec(nullptr, 0.f, 0), 0);
     VITK_LAUNCH_CHECK();
   }
   if (probs != nullptr) {
@@ -563,28 +626,29 @@ extern "C" int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, flo
                             : attention_fwd_impl<false>(qkv, out, lse, probs, B, N, H, scale, st);
 }
 
-template <bool H16>
+template <bool H16, bool DROP>
 static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
-                              int B, int N, int H, float scale, cudaStream_t st) {
+                              int B, int N, int H, float scale, DropSpec drop, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<H16, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<H16, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
     configured = true;
   }
-  if (N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, H16, st);  // delta fused
+  const int Npad = (N + 7) & ~7;
+  if (!DROP && N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, H16, st);  // delta fused
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
                                                                      reinterpret_cast<const bf16*>(dout), delta, B, N, H);
   VITK_LAUNCH_CHECK();
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  attn_bwd_dkdv_kernel<H16><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
-                                                                reinterpret_cast<const bf16*>(dout), lse, delta,
-                                                                reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E);
+  attn_bwd_dkdv_kernel<H16, DROP><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                                      reinterpret_cast<const bf16*>(dout), lse, delta,
+                                                                      reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E, drop, Npad);
   VITK_LAUNCH_CHECK();
-  attn_bwd_dq_kernel<H16><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
-                                                              reinterpret_cast<const bf16*>(dout), lse, delta,
-                                                              reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E);
+  attn_bwd_dq_kernel<H16, DROP><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
+                                                                    reinterpret_cast<const bf16*>(dout), lse, delta,
+                                                                    reinterpret_cast<bf16*>(dqkv), N, H, scale, scale * LOG2E, drop, Npad);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -596,6 +660,42 @@ extern "C" int vitk_attention_bwd(const void* qkv, const void* out, const void* 
   VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_bwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_bwd: grid limit");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return dtype == VITK_FP16 ? attention_bwd_impl<true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st)
-                            : attention_bwd_impl<false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st);
+  const DropSpec none = make_drop_spec(nullptr, 0.f, 0);
+  return dtype == VITK_FP16 ? attention_bwd_impl<true, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, none, st)
+                            : attention_bwd_impl<false, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, none, st);
+}
+
+// ---- training-mode dropout on the attention probabilities (Attention.attn_drop, vision_transformer_base.py:184).  Every
+// ViT / DeiT configuration of the reference sets the rate to 0, so this option runs on the mma.sync kernels for any N.
+extern "C" int vitk_attention_dropout_fwd(const void* qkv, void* out, int32_t dtype, float* lse, int32_t B, int32_t N, int32_t H,
+                                          float scale, const vitk_dropout* attn_drop, void* stream) {
+  VITK_CHECK_ARG(qkv && out && lse && attn_drop && attn_drop->seed, "vitk_attention_dropout_fwd: null pointer");
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_dropout_fwd: dtype must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "vitk_attention_dropout_fwd: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_CHECK_ARG(attn_drop->p > 0.f && attn_drop->p < 1.f, "vitk_attention_dropout_fwd: need 0 < p < 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const DropSpec ds = make_drop_spec(attn_drop->seed, attn_drop->p, attn_drop->site);
+  const int Npad = (N + 7) & ~7;
+  dim3 grid((N + TILE - 1) / TILE, H, B);
+  if (dtype == VITK_FP16)
+    attn_fwd_kernel<true, true><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse, N, H,
+                                                      scale * LOG2E, ds, Npad);
+  else
+    attn_fwd_kernel<false, true><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse, N, H,
+                                                       scale * LOG2E, ds, Npad);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_attention_dropout_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                                          void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H, float scale,
+                                          const vitk_dropout* attn_drop, void* stream) {
+  VITK_CHECK_ARG(qkv && out && dout && lse && delta && dqkv && attn_drop && attn_drop->seed, "vitk_attention_dropout_bwd: null pointer");
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_dropout_bwd: dtype must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "vitk_attention_dropout_bwd: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_CHECK_ARG(attn_drop->p > 0.f && attn_drop->p < 1.f, "vitk_attention_dropout_bwd: need 0 < p < 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const DropSpec ds = make_drop_spec(attn_drop->seed, attn_drop->p, attn_drop->site);
+  return dtype == VITK_FP16 ? attention_bwd_impl<true, true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, ds, st)
+                            : attention_bwd_impl<false, true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, ds, st);
 }

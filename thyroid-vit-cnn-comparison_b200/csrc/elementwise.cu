@@ -109,6 +109,34 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   }
 }
 
+// channel-last patch vectors (projection_type='linear'): one thread writes two adjacent 16-bit outputs k, k+1 of
+// k = (ky*P + kx)*C + c -- coalesced 4-byte stores; the loads walk C image planes (L1/L2 absorb the reuse)
+__global__ void patchify_hwc_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int fp16, int B, int C, int H, int W,
+                                    int P) {
+  const int gw = W / P, gh = H / P;
+  const int Kdim = C * P * P;          // even: P % 8 == 0
+  const int kpairs = Kdim >> 1;
+  const long long total = (long long)B * gh * gw * kpairs;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int kp = int(i % kpairs);
+    long long r = i / kpairs;
+    const int px = int(r % gw);
+    r /= gw;
+    const int py = int(r % gh);
+    const int b = int(r / gh);
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = 2 * kp + e;
+      const int c = k % C, pix = k / C;
+      const int ky = pix / P, kx = pix - ky * P;
+      v[e] = __ldg(img + (((long long)b * C + c) * H + py * P + ky) * W + px * P + kx);
+    }
+    reinterpret_cast<uint32_t*>(patches)[i] = pack16(v[0], v[1], fp16);
+  }
+}
+
 // ------------------------------------------------------------------ cls / dist token rows
 __global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls_tok, const float* __restrict__ dist_tok,
                                      const float* __restrict__ pos, int B, int T, int dim, int n_prefix, DropSpec drop) {
@@ -424,6 +452,19 @@ extern "C" int vitk_patchify(const float* images, void* patches, int32_t patches
                  "vitk_patchify: need P %% 8 == 0 and H, W divisible by P (B=%d C=%d H=%d W=%d P=%d)", B, C, H, W, P);
   const long long total = (long long)B * C * H * (W / 8);
   patchify_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      images, reinterpret_cast<bf16*>(patches), int(patches_dtype == VITK_FP16), B, C, H, W, P);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_patchify_hwc(const float* images, void* patches, int32_t patches_dtype, int32_t B, int32_t C, int32_t H,
+                                 int32_t W, int32_t P, void* stream) {
+  VITK_CHECK_ARG(images && patches, "vitk_patchify_hwc: null pointer");
+  VITK_CHECK_ARG(patches_dtype == VITK_BF16 || patches_dtype == VITK_FP16, "vitk_patchify_hwc: patches must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && C > 0 && P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0,
+                 "vitk_patchify_hwc: need P %% 8 == 0 and H, W divisible by P (B=%d C=%d H=%d W=%d P=%d)", B, C, H, W, P);
+  const long long total = (long long)B * (H / P) * (W / P) * ((long long)C * P * P / 2);
+  patchify_hwc_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       images, reinterpret_cast<bf16*>(patches), int(patches_dtype == VITK_FP16), B, C, H, W, P);
   VITK_LAUNCH_CHECK();
   return VITK_OK;

@@ -52,6 +52,8 @@ class Dims:
     pool: Optional[Tuple[int, int]] = None   # token range [t0, t1) averaged after the final norm ('gap' / no class token);
                                              # None = the fused class-token tail (vitk_head_fwd)
     rep: int = 0       # representation_size of `pre_logits` = Linear + Tanh (0 = Identity)
+    patch_linear: bool = False   # PatchEmbed(projection_type='linear'): channel-last patch vectors, proj = Sequential[1]
+    eps: float = 1e-5  # LayerNorm epsilon of every norm layer (nn.LayerNorm default; a partial(nn.LayerNorm, eps=...) changes it)
 
     @property
     def n_patches(self) -> int:
@@ -201,8 +203,11 @@ class VitEngine:
         # nn.Dropout(drop_rate) sites (pos_drop, proj_drop, Mlp.drop x2): counter-based masks recomputed from one device
         # seed per step (include/vitk.h `vitk_dropout`); site 0 = pos_drop, block l: 1+3l proj, 2+3l after GELU, 3+3l after fc2
         self.drop_rate = 0.0
+        self.attn_drop_rate = 0.0       # Attention.attn_drop (:184): site ATTN_SITE0 + l, element ((b*H + h)*T + q)*Tpad + key
         self.drop_seed = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.frozen = set()             # flat-buffer entries that are not trained (a sinusoidal pos_embed buffer)
+        proj = "patch_embed.proj.1." if dims.patch_linear else "patch_embed.proj."
+        self.patch_w, self.patch_b = proj + "weight", proj + "bias"
 
     def set_drop_path(self, per_block_rates) -> None:
         rates = [float(r) for r in per_block_rates]
@@ -216,9 +221,19 @@ class VitEngine:
             raise ValueError("set_dropout: rate in [0, 1) expected")
         self.drop_rate = float(rate)
 
+    ATTN_SITE0 = 1000
+
+    def set_attn_dropout(self, rate: float) -> None:
+        if not (0.0 <= float(rate) < 1.0):
+            raise ValueError("set_attn_dropout: rate in [0, 1) expected")
+        self.attn_drop_rate = float(rate)
+
+    def _attn_site(self, l: int):
+        return (self.drop_seed, self.attn_drop_rate, self.ATTN_SITE0 + l) if (self._drop_on and self.attn_drop_rate > 0.0) else None
+
     def _site(self, site: int):
         """(seed, p, site) of one Dropout call, or None when dropout is off for this pass."""
-        return (self.drop_seed, self.drop_rate, site) if self._drop_on else None
+        return (self.drop_seed, self.drop_rate, site) if (self._drop_on and self.drop_rate > 0.0) else None
 
     # ------------------------------------------------------------------ helpers
     def w(self, name: str) -> torch.Tensor:      # 16-bit shadow view
@@ -281,15 +296,15 @@ class VitEngine:
             dp = ws.dp
             self.last_drop_scale = ws.dp[:, ::T]
         ws.dp_active = dp is not None
-        self._drop_on = bool(train and self.drop_rate > 0.0)
+        self._drop_on = bool(train and (self.drop_rate > 0.0 or self.attn_drop_rate > 0.0))
         ws.drop_on = self._drop_on
         if self._drop_on:
             self.drop_seed.random_(0, 1 << 62)      # torch's CUDA generator: seedable and CUDA-graph safe (fresh per replay)
         rs = lambda i: dp[i] if (dp is not None and self.drop_path[i] > 0.0) else None
-        ops.patchify(images, d.patch, out=ws.patches)
+        ops.patchify(images, d.patch, out=ws.patches, channel_last=d.patch_linear)
         x0 = ws.x[0]
-        ops.gemm(ws.patches, self.w("patch_embed.proj.weight"), B * d.n_patches, D, d.kpatch, out=x0,
-                 bias=self.p("patch_embed.proj.bias"), epilogue=_lib.EPI_TOKENS,
+        ops.gemm(ws.patches, self.w(self.patch_w), B * d.n_patches, D, d.kpatch, out=x0,
+                 bias=self.p(self.patch_b), epilogue=_lib.EPI_TOKENS,
                  tokens=(d.n_patches, T, d.n_prefix), pos=self.p("pos_embed"), drop=self._site(0))
         ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token") if d.n_prefix >= 1 else None,
                               self.p("dist_token") if d.n_prefix == 2 else None, self.p("pos_embed"), d.n_prefix,
@@ -302,16 +317,16 @@ class VitEngine:
             else:
                 x_in, x_mid, x_out = ws.x[(2 * l) % 3], ws.x[(2 * l + 1) % 3], ws.x[(2 * l + 2) % 3]
             st = ws.stats[s]
-            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), y=ws.xn1[s], mean=st[0], rstd=st[1])
+            ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), eps=d.eps, y=ws.xn1[s], mean=st[0], rstd=st[1])
             ops.gemm(ws.xn1[s], self.w(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
             probs = None
             if attn_probs is not None:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
-            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs)
+            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs, drop=self._attn_site(l))
             ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in,
                      row_scale=rs(2 * l), drop=self._site(1 + 3 * l))
-            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), y=ws.xn2[s], mean=st[2], rstd=st[3])
+            ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), eps=d.eps, y=ws.xn2[s], mean=st[2], rstd=st[3])
             ops.gemm(ws.xn2[s], self.w(pre + "mlp.fc1.weight"), M, d.hidden, D, out=ws.dact[s], out2=ws.act[s],
                      bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU, drop=self._site(2 + 3 * l))
             ops.gemm(ws.act[s], self.w(pre + "mlp.fc2.weight"), M, D, d.hidden, out=x_out, bias=self.p(pre + "mlp.fc2.bias"), residual=x_mid,
@@ -328,7 +343,7 @@ class VitEngine:
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
                                           self.p("head.weight"), self.p("head.bias"),
                                           self.p("head_dist.weight") if two else None,
-                                          self.p("head_dist.bias") if two else None, d.n_out, pooled=pooled)
+                                          self.p("head_dist.bias") if two else None, d.n_out, eps=d.eps, pooled=pooled)
         if train:
             ws.head_saved = (xhat, rstd)
         return l0, l1
@@ -341,7 +356,7 @@ class VitEngine:
         """norm -> pool over a token range -> pre_logits -> head (vision_transformer_base.py:468-486) for the constructor
         options outside the fused class-token kernel: fp32 throughout, a few hundred KB per step."""
         t0, t1 = self._tail_range()
-        pooled, mean, rstd = ops.pool_norm_fwd(x_last, self.p("norm.weight"), self.p("norm.bias"), t0, t1)
+        pooled, mean, rstd = ops.pool_norm_fwd(x_last, self.p("norm.weight"), self.p("norm.bias"), t0, t1, eps=self.d.eps)
         z = pooled
         if self.d.rep:
             z = ops.dense_fwd(pooled, self.p("pre_logits.0.weight"), self.p("pre_logits.0.bias"), act=1)
@@ -411,7 +426,8 @@ class VitEngine:
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(norm1(x_in))))
             self._wgrad(ws.dx16, ws.ao[l], pre + "attn.proj.weight", M)
             ops.gemm(ws.dx16, self.w(pre + "attn.proj.weight"), M, D, D, b_mn=True, out=ws.d_ao)
-            ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta)
+            ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta,
+                              drop=self._attn_site(l))
             self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M, bias_name=pre + "attn.qkv.bias")
             ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
             prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
@@ -423,9 +439,9 @@ class VitEngine:
             self._notify(pre)
         ops.tokens_bwd(dx.view(B, T, D), None if "pos_embed" in self.frozen else self.g("pos_embed"),
                        self.g("cls_token") if d.n_prefix >= 1 else None,
-                       self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g("patch_embed.proj.bias"),
+                       self.g("dist_token") if d.n_prefix == 2 else None, ws.dpatch, self.g(self.patch_b),
                        d.n_prefix, unscale=u, drop=self._site(0))
-        self._wgrad(ws.dpatch, ws.patches, "patch_embed.proj.weight", B * d.n_patches)
+        self._wgrad(ws.dpatch, ws.patches, self.patch_w, B * d.n_patches)
         self._notify("embed")
 
     def _notify(self, what: str) -> None:

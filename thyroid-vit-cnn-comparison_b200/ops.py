@@ -144,34 +144,49 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None
 
 
 # --------------------------------------------------------------------------- attention
-def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None):
+def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None, drop=None):
+    """drop = (seed, p, site): training-mode dropout on the attention probabilities (Attention.attn_drop)."""
     _req16(qkv, "attention qkv")
     out = torch.empty(B, N, H * 64, dtype=qkv.dtype, device=qkv.device) if out is None else out
     if out.dtype != qkv.dtype:
         raise RuntimeError("attention: qkv and out must share one element type")
     lse = torch.empty(B, H, N, dtype=f32, device=qkv.device) if lse is None else lse
+    if drop is not None:
+        if probs is not None:
+            raise RuntimeError("attention: probability maps are an eval-mode output; dropout is training-mode only")
+        check(_lib.load().vitk_attention_dropout_fwd(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], lse.data_ptr(), B, N, H, scale,
+                                                     _drop(drop), _stream()), "attention_dropout_fwd")
+        return out, lse
     check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], lse.data_ptr(), _p(probs), B, N, H,
                                          scale, _stream()), "attention_fwd")
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqkv=None, delta=None):
+def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqkv=None, delta=None, drop=None):
     _req16(qkv, "attention qkv")
     _req(out, qkv.dtype, "attention out"); _req(dout, qkv.dtype, "attention dout")
     dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
     delta = torch.empty(B, H, N, dtype=f32, device=qkv.device) if delta is None else delta
+    if drop is not None:
+        check(_lib.load().vitk_attention_dropout_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                                     dqkv.data_ptr(), _DT[qkv.dtype], B, N, H, scale, _drop(drop), _stream()),
+              "attention_dropout_bwd")
+        return dqkv
     check(_lib.load().vitk_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
                                          dqkv.data_ptr(), _DT[qkv.dtype], B, N, H, scale, _stream()), "attention_bwd")
     return dqkv
 
 
 # --------------------------------------------------------------------------- tokens
-def patchify(images, P: int, out=None, dtype=f16):
+def patchify(images, P: int, out=None, dtype=f16, channel_last: bool = False):
+    """[B,C,H,W] fp32 -> 16-bit patch matrix [B*gh*gw, C*P*P]; k = c*P*P + ky*P + kx (Conv2d weight order), or with
+    channel_last k = (ky*P + kx)*C + c (the Rearrange + Linear projection)."""
     _req(images, f32, "patchify images")
     B, Cc, H, W = images.shape
     rows = B * (H // P) * (W // P)
     out = torch.empty(rows, Cc * P * P, dtype=dtype, device=images.device) if out is None else out
-    check(_lib.load().vitk_patchify(images.data_ptr(), out.data_ptr(), _DT[out.dtype], B, Cc, H, W, P, _stream()), "patchify")
+    fn = _lib.load().vitk_patchify_hwc if channel_last else _lib.load().vitk_patchify
+    check(fn(images.data_ptr(), out.data_ptr(), _DT[out.dtype], B, Cc, H, W, P, _stream()), "patchify")
     return out
 
 

@@ -80,15 +80,18 @@ class PatchEmbed(nn.Module):
                  norm_layer=None, flatten: bool = True, bias: bool = True, strict_img_size: bool = True,
                  projection_type: str = "conv", quality_aware: bool = True):
         super().__init__()
-        if projection_type != "conv":
-            raise NotImplementedError("only projection_type='conv' is implemented in the sm_100a path")
         self.img_size, self.patch_size = img_size, patch_size
         self.grid_size = img_size // patch_size
         self.num_patches = self.grid_size ** 2
         self.flatten, self.projection_type = flatten, projection_type
         self.strict_img_size, self.quality_aware = strict_img_size, quality_aware
         self.in_chans, self.embed_dim = in_chans, embed_dim
-        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+        if projection_type == "conv":
+            self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias)
+        else:   # 'linear' (:102-107): channel-last patch vectors + nn.Linear; index 0 holds no parameters, as in the reference
+            from einops.layers.torch import Rearrange
+            self.proj = nn.Sequential(Rearrange("b c (h p1) (w p2) -> b (h w) (p1 p2 c)", p1=patch_size, p2=patch_size),
+                                      nn.Linear(patch_size * patch_size * in_chans, embed_dim, bias=bias))
         self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
         if quality_aware:
             self.quality_score = nn.Sequential(nn.Conv2d(in_chans, 32, kernel_size=3, padding=1), nn.ReLU(inplace=True),
@@ -101,11 +104,13 @@ class PatchEmbed(nn.Module):
             assert H == self.img_size and W == self.img_size, \
                 f"Input size ({H}x{W}) doesn't match expected size ({self.img_size}x{self.img_size})"
         _require_cuda(x, "PatchEmbed")
-        patches = ops.patchify(x.float().contiguous(), self.patch_size)
-        w16 = ops.cast_fp16(self.proj.weight.detach().reshape(self.embed_dim, -1).contiguous())
+        linear = self.projection_type != "conv"
+        lin = self.proj[1] if linear else self.proj
+        patches = ops.patchify(x.float().contiguous(), self.patch_size, channel_last=linear)
+        w16 = ops.cast_fp16(lin.weight.detach().reshape(self.embed_dim, -1).contiguous())
         out = torch.empty(patches.shape[0], self.embed_dim, dtype=torch.float32, device=x.device)
         ops.gemm(patches, w16, patches.shape[0], self.embed_dim, patches.shape[1], out=out,
-                 bias=self.proj.bias.detach() if self.proj.bias is not None else None)
+                 bias=lin.bias.detach() if lin.bias is not None else None)
         return out.view(B, -1, self.embed_dim), None
 
 
@@ -166,13 +171,13 @@ class Block(nn.Module):
                  store_attention: bool = True):
         super().__init__()
         norm_layer = get_layer_from_string(norm_layer) or nn.LayerNorm
-        if norm_layer is not nn.LayerNorm:
+        if getattr(norm_layer, "func", norm_layer) is not nn.LayerNorm:     # functools.partial(nn.LayerNorm, eps=...) is fine
             raise NotImplementedError("only nn.LayerNorm is implemented in the sm_100a path")
-        self.norm1 = nn.LayerNorm(dim)
+        self.norm1 = norm_layer(dim)
         self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop,
                               store_attention=store_attention)
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
-        self.norm2 = nn.LayerNorm(dim)
+        self.norm2 = norm_layer(dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
 
@@ -311,6 +316,17 @@ class VisionTransformerBase(_Base):
         n = self.num_patches + self._n_prefix()
         return (1, n) if self.class_token else (0, n)
 
+    def _ln_eps(self) -> float:
+        """One epsilon for every LayerNorm of the model (norm_layer is a single factory in the reference, :263,273,377)."""
+        norms = [self.norm] + [n for b in self.blocks for n in (b.norm1, b.norm2)]
+        bad = [type(n).__name__ for n in norms if not isinstance(n, nn.LayerNorm)]
+        if bad:
+            raise NotImplementedError(f"the sm_100a path implements nn.LayerNorm norm layers only (got {sorted(set(bad))})")
+        eps = {float(n.eps) for n in norms}
+        if len(eps) != 1:
+            raise NotImplementedError(f"all LayerNorm layers must share one eps (got {sorted(eps)})")
+        return eps.pop()
+
     def _rep_size(self) -> int:
         if isinstance(self.pre_logits, nn.Identity):
             return 0
@@ -321,10 +337,7 @@ class VisionTransformerBase(_Base):
         return rep
 
     def _check_supported(self) -> None:
-        hp = self._vitk_hparams
-        if self.training and hp.get("attn_drop_rate", 0.0):
-            raise NotImplementedError("attention-probability dropout > 0 is not implemented in the sm_100a training path "
-                                      "(drop_rate and stochastic depth are; every ViT/DeiT config of the reference uses 0)")
+        pass        # every constructor option of the reference classes is served
 
     def _engine_params(self) -> "OrderedDict[str, nn.Parameter]":
         skip = ("patch_embed.quality_score",)
@@ -349,7 +362,8 @@ class VisionTransformerBase(_Base):
             dims = Dims(img=self.patch_embed.img_size, patch=self.patch_embed.patch_size, chans=self.in_chans,
                         dim=self.embed_dim, depth=len(self.blocks), heads=blk.attn.num_heads,
                         hidden=blk.mlp.fc1.out_features, classes=self.num_classes, n_prefix=self._n_prefix(),
-                        n_out=self._n_out(), pool=self._pool_range(), rep=self._rep_size())
+                        n_out=self._n_out(), pool=self._pool_range(), rep=self._rep_size(),
+                        patch_linear=self.patch_embed.projection_type != "conv", eps=self._ln_eps())
             eng = VitEngine(dims, OrderedDict((n, p.data) for n, p in named.items()), first.device,
                             dtype16=self._vitk_hparams.get("compute_dtype", torch.float16))
             for n, p in named.items():        # re-point the module's parameters at the flat buffers
@@ -358,6 +372,7 @@ class VisionTransformerBase(_Base):
                     p.grad = None
             eng.set_drop_path([float(getattr(b.drop_path, "drop_prob", 0.0)) for b in self.blocks])
             eng.set_dropout(float(self.pos_drop.p))       # pos_drop, proj_drop and Mlp.drop all carry drop_rate
+            eng.set_attn_dropout(float(self.blocks[0].attn.attn_drop.p))
             if not isinstance(self.pos_embed, nn.Parameter):
                 eng.frozen.add("pos_embed")
             self._engine = eng
@@ -682,7 +697,7 @@ class DeiT(VisionTransformer):
         """deit_models.py:190-218: the normalised token sequence [B, T, D] (inference-only here)."""
         x_last = self._features(x)["x_last"]
         B, T, D = x_last.shape
-        y, _, _ = ops.layernorm_fwd(x_last.reshape(B * T, D), self.norm.weight.detach(), self.norm.bias.detach(),
+        y, _, _ = ops.layernorm_fwd(x_last.reshape(B * T, D), self.norm.weight.detach(), self.norm.bias.detach(), eps=self.norm.eps,
                                     dtype=self._engine.dt16)
         return y.float().view(B, T, D)       # 16-bit rounding of the normalised tokens (operand precision of the path)
 
