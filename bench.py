@@ -303,6 +303,8 @@ def run_ours(args):
     import thyroid_vit_cnn_comparison_b200  # noqa: F401
     from thyroid_vit_cnn_comparison_b200 import ops, optim, parallel, training, vit
 
+    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = parallel.init_distributed()
     dev = torch.device("cuda", local)
     torch.manual_seed(42)
