@@ -1,6 +1,7 @@
 """Tiny end-to-end workload for `compute-sanitizer --tool memcheck|racecheck python tools/sanitize_step.py`:
 one DeiT-tiny train step at batch 4 (every kernel of the hot path at its real shapes, ragged last tiles included) and one
-small ViT step with dropout + stochastic depth, then an eval forward with attention maps and feature extraction."""
+small ViT step with dropout + stochastic depth, then an eval forward with attention maps and feature extraction, then two
+steps of the non-default constructor options (gap pooling, pre_logits, linear patch projection, attention dropout, no class token)."""
 import sys
 from pathlib import Path
 
@@ -37,6 +38,18 @@ def main():
         feats = v.extract_features(x2)
     torch.cuda.synchronize()
     print("eval", tuple(out.shape), tuple(feats.shape), v.get_attention_maps().shape)
+    # the non-default constructor options: gap pooling + pre_logits (pool_head.cu), linear patch projection (patchify_hwc),
+    # attention-probability dropout (mma.sync attention kernels with masks), no class token
+    for kw in (dict(pool_type="gap", representation_size=128, projection_type="linear", attn_drop_rate=0.1, drop_rate=0.1),
+               dict(class_token=False, attn_drop_rate=0.2)):
+        g = vit.VisionTransformer(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=2, num_heads=2,
+                                  drop_path_rate=0.1, **kw).cuda().train()
+        opt3 = optim.FusedAdamW(g, lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
+        step3 = training.TrainStep(g, opt3, 8, mode="ce", use_graph=False)
+        for _ in range(2):
+            st = step3(x2, y2)
+        torch.cuda.synchronize()
+        print("options", sorted(kw), "loss", float(st[0]))
 
 
 if __name__ == "__main__":
