@@ -402,6 +402,9 @@ def run_ours(args):
         saved_graph, step.use_graph = step.use_graph, False
         with KernelProfile(ops, by_shape=True) as prof:
             for _ in range(nprof):
+                # ~30 ms of device-side spinning first: the host enqueues the whole eager step behind it, so every event
+                # pair brackets device time only (no launch gaps of a host-bound eager step inside the per-kernel numbers)
+                torch.cuda._sleep(60_000_000)
                 step.run()
             tab_shape = prof.table()
         step.use_graph = saved_graph

@@ -24,7 +24,7 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <int LPR, int CHUNKS>
+template <int LPR, int CHUNKS, bool PF = false>
 __global__ void __launch_bounds__(LN_WARPS * 32)
     ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   __nv_bfloat16* __restrict__ y, int y_fp16, float* __restrict__ mean, float* __restrict__ rstd, long long rows,
@@ -44,18 +44,33 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     bt[c] = i < nvec ? ldg_f4(beta + 4 * i) : make_float4(0, 0, 0, 0);
   }
   const long long stride = (long long)gridDim.x * LN_WARPS * RPW;
-  for (long long row0 = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * RPW; row0 < rows; row0 += stride) {
-    const long long row = row0 + sub;
+  // PF: the next row's loads are in flight while this row is reduced and stored (a lane group walks only a few rows, so the
+  // exposed DRAM latency per row is what bounds the short-row case)
+  float4 nv[CHUNKS];
+  auto issue = [&](long long r0) {
+    const long long row = r0 + sub;
     const bool ok = row < rows;
     const float* xr = x + (ok ? row : 0) * dim;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int i = gl + LPR * c;
+      nv[c] = (ok && i < nvec) ? ldg_f4(xr + 4 * i) : make_float4(0, 0, 0, 0);
+    }
+  };
+  const long long first = ((long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * RPW;
+  if (PF && first < rows) issue(first);
+  for (long long row0 = first; row0 < rows; row0 += stride) {
+    const long long row = row0 + sub;
+    const bool ok = row < rows;
+    if (!PF) issue(row0);
     float4 v[CHUNKS];
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-      const int i = gl + LPR * c;
-      v[c] = (ok && i < nvec) ? ldg_f4(xr + 4 * i) : make_float4(0, 0, 0, 0);
+      v[c] = nv[c];
       s += v[c].x + v[c].y + v[c].z + v[c].w;
     }
+    if (PF && row0 + stride < rows) issue(row0 + stride);
     const float mu = group_sum<LPR>(s) * inv_dim;
     float q = 0.f;
 #pragma unroll
@@ -198,8 +213,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 // registers instead of 12 per chunk per lane, and R rows per thread are in flight at once (R x 40 bytes of loads per
 // thread, 24+ resident warps per SM).  Row statistics are reduced inside G-lane groups by shuffles and across groups
 // through a double-buffered shared-memory table (one __syncthreads per batch of R x slots rows).
-template <int V, int R, bool DROP>
-__global__ void __launch_bounds__(192, 5)
+template <int V, int R, bool DROP, bool PF = false, int MINB = 5>
+__global__ void __launch_bounds__(192, MINB)
     ln_bwd_cols_kernel(const __nv_bfloat16* __restrict__ dy, int dy_fp16, const float* __restrict__ x, const float* __restrict__ mean,
                        const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                        float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int dx_fp16, float* __restrict__ dgamma,
@@ -223,21 +238,40 @@ __global__ void __launch_bounds__(192, 5)
   float4 dg = make_float4(0, 0, 0, 0), db = dg, dc = dg;
   const long long batch = (long long)SLOTS * R;
   int it = 0;
-  for (long long base = (long long)blockIdx.x * batch; base < rows; base += (long long)gridDim.x * batch, ++it) {
-    float4 xv[R], rv[R];
-    uint2 dyu[R];
-    float mu[R], rs[R];
+  // PF: the loads of the CTA's NEXT batch are issued before this batch is reduced, so a batch's DRAM latency hides behind
+  // the previous batch's shuffles / barrier / stores instead of adding to them (short rows: ~9 dependent batches per CTA)
+  float4 nxv[R], nrv[R];
+  uint2 ndyu[R];
+  float nmu[R], nrs[R];
+  auto issue = [&](long long base) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {  // every load of the batch in flight before any arithmetic
       const long long row = base + r * SLOTS + slot;
       const bool ok = row < rows;
       const long long rr = ok ? row : 0;
-      xv[r] = ok ? ldg_f4(x + rr * DIM + 4 * cv) : make_float4(0, 0, 0, 0);
-      dyu[r] = ok ? ldg_u2(dy + rr * DIM + 4 * cv) : make_uint2(0, 0);
-      rv[r] = (ok && dres != nullptr) ? ldg_f4(dres + rr * DIM + 4 * cv) : make_float4(0, 0, 0, 0);
-      mu[r] = __ldg(mean + rr);
-      rs[r] = __ldg(rstd + rr);
+      nxv[r] = ok ? ldg_f4(x + rr * DIM + 4 * cv) : make_float4(0, 0, 0, 0);
+      ndyu[r] = ok ? ldg_u2(dy + rr * DIM + 4 * cv) : make_uint2(0, 0);
+      nrv[r] = (ok && dres != nullptr) ? ldg_f4(dres + rr * DIM + 4 * cv) : make_float4(0, 0, 0, 0);
+      nmu[r] = __ldg(mean + rr);
+      nrs[r] = __ldg(rstd + rr);
     }
+  };
+  const long long step = (long long)gridDim.x * batch;
+  if (PF && (long long)blockIdx.x * batch < rows) issue((long long)blockIdx.x * batch);
+  for (long long base = (long long)blockIdx.x * batch; base < rows; base += step, ++it) {
+    float4 xv[R], rv[R];
+    uint2 dyu[R];
+    float mu[R], rs[R];
+    if (!PF) issue(base);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      xv[r] = nxv[r];
+      dyu[r] = ndyu[r];
+      rv[r] = nrv[r];
+      mu[r] = nmu[r];
+      rs[r] = nrs[r];
+    }
+    if (PF && base + step < rows) issue(base + step);
     float4 xh[R], g[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -359,9 +393,18 @@ extern "C" int vitk_layernorm_fwd(const float* x, const float* gamma, const floa
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const LnCfg cfg = ln_config(dim);
   const int rpb = LN_WARPS * (32 / cfg.lpr);
-  LN_DISPATCH(VITK_CUDA(launch_pdl(ln_fwd_kernel<L_, C_>, dim3(ln_grid(rows, rpb, 8)), dim3(LN_WARPS * 32), 0, st, x, gamma, beta,
-                                   reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, (long long)rows, dim,
-                                   eps)));
+  // long rows (>= 4 float4 per lane, e.g. D = 768) prefetch the next row: 51 -> 45 us on ViT-B/16 batch 256; short rows gain
+  // nothing (measured) and keep the smaller-register kernel.  VITK_LN_FWD_VARIANT=0|1 forces one of them (A/B runs).
+  static const int variant = [] { const char* e = getenv("VITK_LN_FWD_VARIANT"); return e != nullptr ? atoi(e) : -1; }();
+  if (variant == 1 || (variant < 0 && cfg.chunks >= 4)) {
+    LN_DISPATCH(VITK_CUDA(launch_pdl(ln_fwd_kernel<L_, C_, true>, dim3(ln_grid(rows, rpb, 6)), dim3(LN_WARPS * 32), 0, st, x, gamma,
+                                     beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, (long long)rows,
+                                     dim, eps)));
+  } else {
+    LN_DISPATCH(VITK_CUDA(launch_pdl(ln_fwd_kernel<L_, C_, false>, dim3(ln_grid(rows, rpb, 8)), dim3(LN_WARPS * 32), 0, st, x, gamma,
+                                     beta, reinterpret_cast<__nv_bfloat16*>(y), int(y_dtype == VITK_FP16), mean, rstd, (long long)rows,
+                                     dim, eps)));
+  }
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -384,26 +427,34 @@ extern "C" int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float*
     const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
     __nv_bfloat16* dx16p = reinterpret_cast<__nv_bfloat16*>(dx16);
     const int f_dy = int(dy_dtype == VITK_FP16), f_dx = int(dx16_dtype == VITK_FP16);
-#define LN_COLS(V_, R_)                                                                                                    \
+#define LN_LAUNCH(K_)                                                                                                       \
+  VITK_CUDA(launch_pdl(K_, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, gamma, dres, dx, dx16p, f_dx, \
+                       dgamma, dbeta, dcolsum, grad_unscale, branch_scale, drop, (long long)rows))
+#define LN_COLS(V_, R_, PF_, MINB_)                                                                                        \
   {                                                                                                                        \
     const long long batch = (long long)(192 / V_) * R_;                                                                    \
     long long blocks = (rows + batch - 1) / batch;                                                                         \
-    const long long cap = (long long)num_sms() * 5;                                                                        \
+    const long long cap = (long long)num_sms() * MINB_;                                                                    \
     if (blocks > cap) blocks = cap;                                                                                        \
     if (drop.seed != nullptr)                                                                                              \
-      VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_, true>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, \
-                           gamma, dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, branch_scale, drop, (long long)rows)); \
+      LN_LAUNCH((ln_bwd_cols_kernel<V_, R_, true, PF_, MINB_>));                                                           \
     else                                                                                                                   \
-      VITK_CUDA(launch_pdl(ln_bwd_cols_kernel<V_, R_, false>, dim3((unsigned)blocks), dim3(192), 0, st, dyp, f_dy, x, mean, rstd, \
-                           gamma, dres, dx, dx16p, f_dx, dgamma, dbeta, dcolsum, grad_unscale, branch_scale, drop, (long long)rows)); \
+      LN_LAUNCH((ln_bwd_cols_kernel<V_, R_, false, PF_, MINB_>));                                                          \
     VITK_LAUNCH_CHECK();                                                                                                   \
     return VITK_OK;                                                                                                        \
   }
-    if (dim == 768) LN_COLS(192, 2)
-    if (dim == 384) LN_COLS(96, 2)
-    if (dim == 192) LN_COLS(48, 2)
-    if (dim == 128) LN_COLS(32, 2)
+    // D = 192 (DeiT-tiny / ViT-tiny): prefetching variant on 2 CTAs per SM -- 43.0 -> 38.9 us at batch 256 (fewer CTAs also
+    // means fewer same-address atomics on the 3 x 192 column sums); measured alternatives: prefetch on 4 CTAs/SM 41.0, on 3
+    // CTAs/SM 45.1, four rows in flight without prefetch 47.2.  D = 768 is at 0.91 of its HBM floor and does not move with
+    // prefetching (104.4 vs 104.5 us).  VITK_LN_BWD_VARIANT=0 restores the non-prefetching kernel for A/B runs.
+    static const int variant = [] { const char* e = getenv("VITK_LN_BWD_VARIANT"); return e != nullptr ? atoi(e) : -1; }();
+    if (dim == 768) LN_COLS(192, 2, false, 5)
+    if (dim == 384) LN_COLS(96, 2, false, 5)
+    if (dim == 192 && variant == 0) LN_COLS(48, 2, false, 5)
+    if (dim == 192) LN_COLS(48, 2, true, 2)
+    if (dim == 128) LN_COLS(32, 2, false, 5)
 #undef LN_COLS
+#undef LN_LAUNCH
   }
   const LnCfg cfg = ln_config(dim);
   const size_t smem = 3 * (size_t)dim * sizeof(float);
