@@ -172,16 +172,25 @@ __global__ void tokens_bwd_kernel(const float* __restrict__ dx, float* __restric
   const int rows_per_img = T - n_prefix;
   for (int v = threadIdx.x; v < (dim >> 2); v += blockDim.x) {
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int b = b0; b < b1; ++b) {
-      float4 g = ldg_f4(dx + ((long long)b * T + t) * dim + 4 * v);
-      if (drop.seed != nullptr) {   // gradient through pos_drop: the mask the forward applied to this token element
-        const float4 m = drop_factors4(drop, dseed, (((unsigned long long)b * T + t) * dim + 4 * v) >> 2);
-        g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+    for (int bb = b0; bb < b1; bb += 8) {   // 8 independent 16-byte loads in flight per thread (one at a time: ~1.1 TB/s)
+      float4 gs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        gs[k] = (bb + k < b1) ? ldg_f4(dx + ((long long)(bb + k) * T + t) * dim + 4 * v) : make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int b = bb + k;
+        if (b >= b1) break;
+        float4 g = gs[k];
+        if (drop.seed != nullptr) {   // gradient through pos_drop: the mask the forward applied to this token element
+          const float4 m = drop_factors4(drop, dseed, (((unsigned long long)b * T + t) * dim + 4 * v) >> 2);
+          g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+        }
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        if (t >= n_prefix && dpatch != nullptr)
+          *reinterpret_cast<uint2*>(dpatch + ((long long)b * rows_per_img + (t - n_prefix)) * dim + 4 * v) =
+              make_uint2(pack16(g.x, g.y, fp16), pack16(g.z, g.w, fp16));
       }
-      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-      if (t >= n_prefix && dpatch != nullptr)
-        *reinterpret_cast<uint2*>(dpatch + ((long long)b * rows_per_img + (t - n_prefix)) * dim + 4 * v) =
-            make_uint2(pack16(g.x, g.y, fp16), pack16(g.z, g.w, fp16));
     }
     acc.x *= u; acc.y *= u; acc.z *= u; acc.w *= u;
     if (dpos != nullptr) {
