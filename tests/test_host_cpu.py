@@ -162,6 +162,21 @@ def test_flat_layout_and_completed_prefix():
         total += (torch.Size(shapes[n]).numel() + engine.PAD - 1) // engine.PAD * engine.PAD
     ends = [parallel.completed_prefix(order, offsets, engine.PAD, s, cfg.depth) for s in ("head", "blocks.2.", "blocks.1.", "blocks.0.", "embed")]
     assert ends == sorted(ends) and ends[-1] == total and ends[0] > 0
+    # the optional tail / projection tensors: pre_logits completes with the head, the linear patch projection with the embeddings
+    cfg2 = O.VitConfig(img_size=64, embed_dim=64, depth=2, num_heads=1, is_deit=False, distilled=False, representation_size=64,
+                       projection_type="linear")
+    shapes2 = O.param_shapes(cfg2)
+    names2 = [n for n in shapes2 if "quality" not in n]
+    order2 = engine.execution_order(names2, cfg2.depth)
+    tail = [n for n in order2 if n.startswith(("head", "norm.", "pre_logits."))]
+    assert order2[:len(tail)] == tail and len(tail) == 6
+    assert all(n.startswith(("patch_embed.proj.1.", "pos_embed", "cls_token")) for n in order2[-4:])
+    offsets2, total2 = {}, 0
+    for n in order2:
+        offsets2[n] = (total2, torch.Size(shapes2[n]))
+        total2 += (torch.Size(shapes2[n]).numel() + engine.PAD - 1) // engine.PAD * engine.PAD
+    head_end = parallel.completed_prefix(order2, offsets2, engine.PAD, "head", cfg2.depth)
+    assert head_end == offsets2[order2[len(tail)]][0]              # exactly the head / norm / pre_logits tensors
 
 
 def _dp_worker(rank, world, port, tmp):
