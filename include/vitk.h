@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 13
+#define VITK_ABI_VERSION 14
 
 typedef enum {
   VITK_OK = 0,
@@ -239,6 +239,14 @@ int vitk_dense_fwd(const float* x, const float* W, const float* bias, float* y, 
                    int32_t act, void* stream);
 int vitk_dense_bwd(const float* dy, const float* y, const float* x, const float* W, float* dz, float* dx, float* dW,
                    float* db, int32_t B, int32_t in_dim, int32_t out_dim, int32_t act, void* stream);
+
+/* Frozen-teacher fast path (lightning_modules.py:943-947: `self.teacher(images)`, eval mode, no_grad): eval-mode BatchNorm
+ * + ReLU over the first C channels of an NHWC feature buffer whose pixels are x_ld elements apart (the dense block's
+ * preallocated concatenation buffer) -> y (pixel pitch y_ld): y[p, c] = max(0, x[p, c] * scale[c] + shift[c]) (relu = 0: affine
+ * only), scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale.  Replaces torch.cat + batch_norm + relu of
+ * torchvision's _DenseLayer / _Transition (three read+write passes) by one.  C, x_ld, y_ld multiples of 8; 16-byte aligned. */
+int vitk_affine_relu_nhwc(const void* x, int64_t x_ld, void* y, int64_t y_ld, const float* scale, const float* shift,
+                          int64_t pixels, int32_t C, int32_t dtype, int32_t relu, void* stream);
 
 /* Stochastic depth (DropPath.forward, vision_transformer_base.py:56-64): scale[br, b*T + t] = floor(keep + u[br,b]) / keep
  * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */

@@ -265,3 +265,41 @@ def test_lightning_checkpoint_key_remapping():
     assert all(torch.equal(bare.state_dict()[k], v) for k, v in inner.items())
     with pytest.raises(RuntimeError):
         registry.load_lightning_checkpoint(bare, {"state_dict": {"model.model.cls_token": inner["cls_token"]}}, strict=True)
+
+
+def test_frozen_densenet_rewrites_match_torchvision_eval_forward():
+    """teacher.FrozenDenseNet's three rewrites (preallocated NHWC block buffer instead of torch.cat, eval BatchNorm + ReLU as one
+    affine pass, norm2 / norm0 folded into the preceding convolution) against torchvision's own eval forward, in fp32 on the
+    CPU with the CUDA kernel replaced by a torch restatement of its contract (the product default has no CPU path)."""
+    import torchvision
+    from thyroid_vit_cnn_comparison_b200 import teacher as T
+    torch.manual_seed(0)
+    m = torchvision.models.densenet169(weights=None, num_classes=2).eval()
+    g = torch.Generator().manual_seed(1)
+    for mod in m.modules():                                   # non-trivial running statistics and affine terms
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.weight.data.copy_(1 + 0.2 * torch.randn(mod.num_features, generator=g))
+            mod.bias.data.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+    assert T.is_supported(m) and not T.is_supported(torch.nn.Linear(4, 2))
+
+    def affine_relu_double(x, C, scale, shift, out=None, relu=True):      # contract of vitk_affine_relu_nhwc (include/vitk.h)
+        y = x[..., :C].float() * scale + shift
+        y = (torch.relu(y) if relu else y).to(x.dtype)
+        if out is None:
+            return y.contiguous()
+        out[..., :C] = y
+        return out
+
+    fast = T.FrozenDenseNet(m, dtype=torch.float32, affine_relu=affine_relu_double)
+    x = torch.rand(2, 3, 64, 64, generator=g)
+    with torch.no_grad():
+        ref = m(x)
+    out = fast(x)
+    assert out.shape == ref.shape == (2, 2)
+    assert (out - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    with pytest.raises(RuntimeError):                         # the default op is the CUDA kernel: loud on CPU tensors
+        T.FrozenDenseNet(m, dtype=torch.bfloat16)(x)
+    with pytest.raises(TypeError):
+        T.FrozenDenseNet(torch.nn.Linear(4, 2))

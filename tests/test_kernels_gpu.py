@@ -891,3 +891,30 @@ def test_finish_tiles_pipeline_and_mixing_match_reference_fixture():
     x = torch.stack([IO.preprocess_image(t, 224) for t in tiles])
     x = IO.to_channels_and_normalize(IO.adaptive_normalization(x), 3, ING.IMAGENET_MEAN, ING.IMAGENET_STD)
     assert (out - IO.mixup(x, perm, 0.3)).abs().max().item() < 5e-6
+
+
+# ------------------------------------------------------------------ frozen-teacher fast path
+@pytest.mark.parametrize("pixels,Ct,C,Co", [(2 * 56 * 56, 256, 64, 64), (3 * 14 * 14, 1280, 1248, 1248), (5 * 7 * 7, 1664, 1664, 1664),
+                                            (100, 96, 32, 64)])
+@pytest.mark.parametrize("dt", [F16, BF16])
+@pytest.mark.parametrize("relu", [True, False])
+def test_affine_relu_nhwc(pixels, Ct, C, Co, dt, relu):
+    """vitk_affine_relu_nhwc: eval BatchNorm (+ ReLU) over the first C channels of an NHWC buffer with pixel pitch Ct, written with
+    pixel pitch Co -- against torch fp32 rounded once to the 16-bit format (bit-exact: one fma + one rounding per element)."""
+    x = _rand(pixels, Ct, dtype=dt, seed=1)
+    scale = _rand(C, seed=2) * 0.3 + 1.0
+    shift = _rand(C, seed=3) * 0.5
+    out = torch.full((pixels, Co), 7.0, dtype=dt, device=DEV)
+    ops.affine_relu_nhwc(x, C, scale, shift, out=out, relu=relu)
+    ref = torch.addcmul(shift.double(), x[:, :C].double(), scale.double())
+    ref = (ref.clamp_min(0) if relu else ref)
+    torch.cuda.synchronize()
+    got = out[:, :C].double()
+    ulp = 2.0 ** -10 if dt == F16 else 2.0 ** -7
+    assert ((got - ref).abs() <= ulp * ref.abs().clamp_min(1e-3)).all()
+    if Co > C:
+        assert (out[:, C:] == 7.0).all()                      # channels beyond C are not touched
+    y = ops.affine_relu_nhwc(x.view(1, pixels, 1, Ct), C, scale, shift, relu=relu)
+    assert y.shape == (1, pixels, 1, C) and torch.equal(y.view(pixels, C), out[:, :C])
+    with pytest.raises(RuntimeError):
+        ops.affine_relu_nhwc(x, C - 4, scale, shift)          # C must be a multiple of 8

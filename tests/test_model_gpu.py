@@ -607,3 +607,58 @@ def test_training_converges_end_to_end():
     losses, res = mod.run(steps=120, batch=64, seed=0, verbose=False)
     assert losses[-1] < 0.5 * losses[0], losses
     assert res["acc"] > 0.95 and res["auc"] > 0.98, res
+
+
+def test_frozen_densenet_teacher_fast_path_matches_module():
+    """teacher.FrozenDenseNet (bf16, vitk_affine_relu_nhwc + cuDNN) against the torchvision module itself: its error versus the
+    module's fp32 forward must be of the size of the module's own bf16 eager error (same operand precision, fewer roundings)."""
+    import torchvision
+    from thyroid_vit_cnn_comparison_b200 import teacher as T
+    torch.manual_seed(0)
+    m = torchvision.models.densenet169(weights=None, num_classes=2).cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_((torch.randn(mod.num_features, generator=g) * 0.1).cuda())
+            mod.running_var.copy_((torch.rand(mod.num_features, generator=g) + 0.5).cuda())
+            mod.weight.data.copy_((1 + 0.2 * torch.randn(mod.num_features, generator=g)).cuda())
+            mod.bias.data.copy_((0.1 * torch.randn(mod.num_features, generator=g)).cuda())
+    x = torch.rand(8, 3, 224, 224, generator=g).cuda()
+    with torch.no_grad():
+        ref = m(x)
+        import copy
+        mb = copy.deepcopy(m).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        eager = mb(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)).float()
+    fast = T.FrozenDenseNet(m, dtype=torch.bfloat16)
+    out = fast(x)
+    torch.cuda.synchronize()
+    assert out.shape == (8, 2) and out.dtype == torch.float32
+    scale = ref.abs().max().item()
+    err_fast, err_eager = (out - ref).abs().max().item(), (eager - ref).abs().max().item()
+    assert err_fast < max(2.0 * err_eager, 0.02 * scale), (err_fast, err_eager, scale)
+    assert torch.equal(out.argmax(1), ref.argmax(1)) or err_eager > 0.02 * scale
+    assert torch.equal(fast(x), out)                                  # deterministic
+
+
+def test_distill_step_uses_fast_teacher_and_matches_plain_teacher_call():
+    """TrainStep(mode='distill') routes a torchvision DenseNet teacher through FrozenDenseNet; the step statistics must agree
+    with the same step driven by the plain module call (teacher_fast=False) within the bf16 teacher's own noise."""
+    import torchvision
+    from thyroid_vit_cnn_comparison_b200 import teacher as T
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=1, num_heads=1)
+    x, y = O.seeded_batch(cfg, 8, 31)
+    stats = []
+    for fast in (True, False):
+        torch.manual_seed(0)
+        teacher = torchvision.models.densenet121(weights=None, num_classes=2).cuda().eval().to(torch.bfloat16).to(memory_format=torch.channels_last)
+        model, _ = build(cfg, 31)
+        model.train()
+        opt = OPT.FusedAdamW(model, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+        step = TR.TrainStep(model, opt, 8, mode="distill", teacher=teacher, use_graph=fast, teacher_fast=fast)
+        assert isinstance(step._teacher_fn, T.FrozenDenseNet) == fast
+        for _ in range(2):
+            st = step(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        stats.append(st.cpu().clone())
+    assert torch.isfinite(stats[0]).all()
+    assert abs(stats[0][0].item() - stats[1][0].item()) < 2e-2, (stats[0], stats[1])

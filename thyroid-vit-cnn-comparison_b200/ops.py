@@ -435,3 +435,20 @@ def dense_bwd(dy, y, x, W, dW, db, act: int = 0, need_dx: bool = True):
     check(_lib.load().vitk_dense_bwd(dy.data_ptr(), _p(y), x.data_ptr(), W.data_ptr(), dz.data_ptr(), _p(dx), dW.data_ptr(),
                                      _p(db), B, in_dim, out_dim, act, _stream()), "dense_bwd")
     return dx
+
+
+# --------------------------------------------------------------------------- frozen-teacher fast path
+def affine_relu_nhwc(x, C: int, scale, shift, out=None, relu: bool = True):
+    """x: contiguous 16-bit NHWC tensor [..., C_total]; its first C channels go through y = max(0, x * scale + shift) into the first
+    C channels of `out` (contiguous [..., C_out_total >= C]; default: a new compact [..., C])."""
+    _req16(x, "affine_relu x")
+    pixels = x.numel() // x.shape[-1]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], C, dtype=x.dtype, device=x.device)
+    _req(out, x.dtype, "affine_relu out")
+    if out.numel() // out.shape[-1] != pixels:
+        raise RuntimeError("affine_relu_nhwc: out must have the pixel count of x")
+    _req(scale, f32, "affine_relu scale"); _req(shift, f32, "affine_relu shift")
+    check(_lib.load().vitk_affine_relu_nhwc(x.data_ptr(), x.shape[-1], out.data_ptr(), out.shape[-1], scale.data_ptr(),
+                                            shift.data_ptr(), pixels, C, _DT[x.dtype], int(relu), _stream()), "affine_relu_nhwc")
+    return out

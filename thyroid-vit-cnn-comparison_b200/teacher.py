@@ -1,0 +1,151 @@
+"""Frozen-teacher fast path for the distillation step (reference:
+`ThyroidDistillationModule.get_teacher_outputs`, lightning_modules.py:943-947 -- `self.teacher(images)` in eval mode under
+no_grad, teacher = DenseNet169, src/models/cnn/densenet.py:24-45).
+
+PyTorch eager spends 78 % of the DenseNet169 forward in memory-bound glue (measured on B200, batch 256, bf16 channels_last,
+tools/teacher_profile.py: batch_norm 37 %, torch.cat / copies 29 %, relu 11 %; the cuDNN convolutions are 16 %).  A frozen
+eval-mode network allows three exact rewrites:
+  * the features of a dense block live in ONE preallocated NHWC buffer: a layer's 32 new channels are written next to the
+    existing ones, so `torch.cat` (a copy of everything so far, every layer) disappears;
+  * norm1 + relu1 over that concatenation is one pass of `vitk_affine_relu_nhwc` (eval BatchNorm is a per-channel affine map);
+  * norm2 (and the stem's norm0) directly follow a convolution: they fold into its weights and bias, and the ReLU behind them
+    rides on cuDNN's fused conv + bias + relu.
+The convolutions stay cuDNN calls (library GEMMs on a frozen network); parameters are snapshotted at construction, which is
+what "frozen" means in the reference (`freeze_teacher`, lightning_modules.py:771-773).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _bn_affine(bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm as y = x * scale + shift (fp32)."""
+    if not isinstance(bn, nn.BatchNorm2d) or bn.running_mean is None:
+        raise TypeError("expected an nn.BatchNorm2d with running statistics")
+    w = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(bn.running_mean, dtype=torch.float32)
+    b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(bn.running_mean, dtype=torch.float32)
+    scale = w / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = b - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """conv followed by eval BatchNorm -> (weight, bias) of the equivalent convolution (fp32)."""
+    scale, shift = _bn_affine(bn)
+    w = conv.weight.detach().float() * scale[:, None, None, None]
+    b = shift if conv.bias is None else shift + conv.bias.detach().float() * scale
+    return w, b
+
+
+def is_supported(module: nn.Module) -> bool:
+    """torchvision-style DenseNet: features.{conv0,norm0,pool0,denseblockN.denselayerM.{norm1,conv1,norm2,conv2},transitionN,norm5}
+    + classifier."""
+    f = getattr(module, "features", None)
+    return (f is not None and all(hasattr(f, n) for n in ("conv0", "norm0", "pool0", "denseblock1", "norm5"))
+            and isinstance(getattr(module, "classifier", None), nn.Linear))
+
+
+class FrozenDenseNet:
+    """Callable replacement for `teacher(images)` of a frozen torchvision-style DenseNet (see module docstring)."""
+
+    def __init__(self, module: nn.Module, dtype=torch.bfloat16, affine_relu: Optional[Callable] = None):
+        if not is_supported(module):
+            raise TypeError("FrozenDenseNet expects a torchvision-style DenseNet (features.denseblockN.denselayerM, classifier)")
+        self.dtype = dtype
+        self._affine_relu = affine_relu if affine_relu is not None else ops.affine_relu_nhwc
+        f = module.features
+        cl = lambda w: w.to(dtype).contiguous(memory_format=torch.channels_last)
+        w0, b0 = _fold(f.conv0, f.norm0)
+        self.stem = (cl(w0), b0.to(dtype), f.conv0.stride, f.conv0.padding)
+        p = f.pool0
+        self.stem_pool = (p.kernel_size, p.stride, p.padding)
+        self.blocks: List[dict] = []
+        i = 1
+        while hasattr(f, f"denseblock{i}"):
+            layers = []
+            for layer in getattr(f, f"denseblock{i}").children():
+                if float(getattr(layer, "drop_rate", 0.0)) > 0 and module.training:
+                    raise RuntimeError("FrozenDenseNet runs the eval-mode forward")
+                s1, h1 = _bn_affine(layer.norm1)
+                w1, b1 = _fold(layer.conv1, layer.norm2)
+                layers.append({"s1": s1, "h1": h1, "w1": cl(w1), "b1": b1.to(dtype), "w2": cl(layer.conv2.weight.detach().float()),
+                               "growth": layer.conv2.out_channels, "pad2": layer.conv2.padding})
+            blk = {"layers": layers, "transition": None}
+            tr = getattr(f, f"transition{i}", None)
+            if tr is not None:
+                s, h = _bn_affine(tr.norm)
+                blk["transition"] = {"s": s, "h": h, "w": cl(tr.conv.weight.detach().float()),
+                                     "pool": (tr.pool.kernel_size, tr.pool.stride)}
+            self.blocks.append(blk)
+            i += 1
+        self.s5, self.h5 = _bn_affine(f.norm5)
+        self.wc = module.classifier.weight.detach().float().contiguous()
+        self.bc = module.classifier.bias.detach().float().contiguous() if module.classifier.bias is not None else None
+        self._fused_conv_relu = None      # decided on the first CUDA call
+
+    # ------------------------------------------------------------------ pieces
+    def _conv_bias_relu(self, x, w, b, stride, padding):
+        """cuDNN conv + bias + relu in one call where the build supports it for this dtype, else conv2d + in-place relu."""
+        if x.is_cuda and self._fused_conv_relu is None:
+            try:
+                y = torch.cudnn_convolution_relu(x, w, b, list(stride), list(padding), [1, 1], 1)
+                ref = F.relu(F.conv2d(x, w, b, stride, padding))
+                self._fused_conv_relu = bool(y.shape == ref.shape and torch.allclose(y.float(), ref.float(), rtol=2e-2, atol=2e-2))
+            except Exception:           # noqa: BLE001 -- any refusal (dtype, layout, build) selects the two-call form
+                self._fused_conv_relu = False
+        if x.is_cuda and self._fused_conv_relu:
+            return torch.cudnn_convolution_relu(x, w, b, list(stride), list(padding), [1, 1], 1)
+        return F.relu_(F.conv2d(x, w, b, stride, padding))
+
+    @staticmethod
+    def _nchw(t_nhwc):           # [B,H,W,C] contiguous -> NCHW-logical view with channels_last strides (no copy)
+        return t_nhwc.permute(0, 3, 1, 2)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        x = images.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        w0, b0, stride0, pad0 = self.stem
+        y = self._conv_bias_relu(x, w0, b0, stride0, pad0)
+        y = F.max_pool2d(y, *self.stem_pool)
+        buf = None
+        for blk in self.blocks:
+            B, c0, H, W = y.shape
+            ct = c0 + sum(l["growth"] for l in blk["layers"])
+            buf = torch.empty(B, H, W, ct, dtype=self.dtype, device=y.device)         # the block's concatenation, NHWC
+            buf[..., :c0].copy_(y.permute(0, 2, 3, 1))
+            c = c0
+            for l in blk["layers"]:
+                a = self._affine_relu(buf, c, l["s1"], l["h1"])                        # norm1 + relu1 over channels [0, c)
+                t = self._conv_bias_relu(self._nchw(a), l["w1"], l["b1"], (1, 1), (0, 0))   # conv1 (+ norm2 + relu2)
+                o = F.conv2d(t, l["w2"], None, 1, l["pad2"])                           # conv2: the layer's new features
+                buf[..., c:c + l["growth"]].copy_(o.permute(0, 2, 3, 1))
+                c += l["growth"]
+            tr = blk["transition"]
+            if tr is not None:
+                a = self._affine_relu(buf, ct, tr["s"], tr["h"])
+                y = F.avg_pool2d(F.conv2d(self._nchw(a), tr["w"]), *tr["pool"])
+        a = self._affine_relu(buf, buf.shape[-1], self.s5, self.h5)                    # norm5 + the forward()'s F.relu
+        pooled = a.float().mean(dim=(1, 2))                                            # adaptive_avg_pool2d((1, 1)) + flatten
+        return F.linear(pooled, self.wc, self.bc)
+
+    def to(self, device):
+        """Move the snapshotted parameters (used when the step is built before the module reaches the GPU)."""
+        mv = lambda t: t.to(device) if isinstance(t, torch.Tensor) else t
+        self.stem = tuple(mv(t) for t in self.stem)
+        for blk in self.blocks:
+            for l in blk["layers"]:
+                for k, v in l.items():
+                    l[k] = mv(v)
+            if blk["transition"] is not None:
+                for k, v in blk["transition"].items():
+                    blk["transition"][k] = mv(v)
+        self.s5, self.h5, self.wc = mv(self.s5), mv(self.h5), mv(self.wc)
+        self.bc = mv(self.bc)
+        return self

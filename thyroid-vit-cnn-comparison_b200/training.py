@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import teacher as _teacher
 from .optim import FusedAdamW
 
 try:
@@ -388,7 +389,7 @@ class TrainStep:
 
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, *, mode: str = "ce", teacher: Optional[nn.Module] = None,
                  alpha: float = 0.7, temperature: float = 3.0, distillation_type: str = "soft", label_smoothing: float = 0.0,
-                 reducer=None, use_graph: bool = False, teacher_dtype=torch.bfloat16):
+                 reducer=None, use_graph: bool = False, teacher_dtype=torch.bfloat16, teacher_fast: bool = True):
         self.model, self.opt, self.B, self.mode = model, optimizer, batch_size, mode
         self.teacher, self.alpha, self.T = teacher, alpha, temperature
         self.distillation_type, self.ls = distillation_type, label_smoothing
@@ -412,6 +413,13 @@ class TrainStep:
         self._pending_copy = False
         if mode == "distill" and teacher is None:
             raise ValueError("mode='distill' needs a teacher module")
+        # a frozen torchvision-style DenseNet teacher runs through the fused eval-mode executor (teacher.py): no torch.cat, one
+        # pass for BatchNorm + ReLU, BatchNorm folded into the convolutions; any other teacher module is called as it is
+        self._teacher_fn = teacher
+        if (teacher is not None and teacher_fast and teacher_dtype in (torch.bfloat16, torch.float16)
+                and _teacher.is_supported(teacher)):
+            teacher.eval()                                                                   # lightning_modules.py:944
+            self._teacher_fn = _teacher.FrozenDenseNet(teacher, dtype=teacher_dtype).to(dev)
         if reducer is not None:
             reducer.attach(self.eng)
 
@@ -437,7 +445,7 @@ class TrainStep:
                 x = self.images
                 if self.teacher_dtype is not None and self.teacher_dtype != torch.float32:
                     x = x.to(self.teacher_dtype).contiguous(memory_format=torch.channels_last)
-                teacher_logits = self.teacher(x).float().contiguous()
+                teacher_logits = self._teacher_fn(x).float().contiguous()
         eng.zero_grad()
         l0, l1 = eng.forward(self.images, train=True)
         eng.generation += 1
