@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 14
+#define VITK_ABI_VERSION 15
 
 typedef enum {
   VITK_OK = 0,
@@ -247,6 +247,11 @@ int vitk_dense_bwd(const float* dy, const float* y, const float* x, const float*
  * torchvision's _DenseLayer / _Transition (three read+write passes) by one.  C, x_ld, y_ld multiples of 8; 16-byte aligned. */
 int vitk_affine_relu_nhwc(const void* x, int64_t x_ld, void* y, int64_t y_ld, const float* scale, const float* shift,
                           int64_t pixels, int32_t C, int32_t dtype, int32_t relu, void* stream);
+/* MaxPool2d(kernel, stride, pad) (is_max = 1, -inf padding) / AvgPool2d(kernel, stride, pad) (is_max = 0, count_include_pad) of a
+ * compact NHWC tensor x [B,H,W,C], ceil_mode False, written with pixel pitch y_ld into y [B,OH,OW,y_ld]: the DenseNet stem's
+ * pool0 and the transitions' pool (torchvision densenet.py) store straight into the next dense block's buffer. */
+int vitk_pool_nhwc(const void* x, void* y, int64_t y_ld, int32_t B, int32_t H, int32_t W, int32_t C, int32_t kernel,
+                   int32_t stride, int32_t pad, int32_t is_max, int32_t dtype, void* stream);
 
 /* Stochastic depth (DropPath.forward, vision_transformer_base.py:56-64): scale[br, b*T + t] = floor(keep + u[br,b]) / keep
  * with keep = 1 - drop_prob[br]; `uniform` fp32 [branches, B] in [0,1), `scale` fp32 [branches, B*T]. */

@@ -292,7 +292,14 @@ def test_frozen_densenet_rewrites_match_torchvision_eval_forward():
         out[..., :C] = y
         return out
 
-    fast = T.FrozenDenseNet(m, dtype=torch.float32, affine_relu=affine_relu_double)
+    def pool_double(x, out, kernel, stride, pad, is_max):                  # contract of vitk_pool_nhwc
+        import torch.nn.functional as F
+        xn = x.permute(0, 3, 1, 2)
+        y = F.max_pool2d(xn, kernel, stride, pad) if is_max else F.avg_pool2d(xn, kernel, stride, pad)
+        out[..., :x.shape[-1]] = y.permute(0, 2, 3, 1)
+        return out
+
+    fast = T.FrozenDenseNet(m, dtype=torch.float32, affine_relu=affine_relu_double, pool=pool_double)
     x = torch.rand(2, 3, 64, 64, generator=g)
     with torch.no_grad():
         ref = m(x)

@@ -918,3 +918,28 @@ def test_affine_relu_nhwc(pixels, Ct, C, Co, dt, relu):
     assert y.shape == (1, pixels, 1, C) and torch.equal(y.view(pixels, C), out[:, :C])
     with pytest.raises(RuntimeError):
         ops.affine_relu_nhwc(x, C - 4, scale, shift)          # C must be a multiple of 8
+
+
+@pytest.mark.parametrize("B,H,W,C,Ct,k,s,p,is_max", [(2, 112, 112, 64, 256, 3, 2, 1, True), (2, 56, 56, 128, 512, 2, 2, 0, False),
+                                                     (3, 14, 14, 640, 1664, 2, 2, 0, False), (1, 9, 7, 8, 8, 3, 2, 1, True)])
+@pytest.mark.parametrize("dt", [F16, BF16])
+def test_pool_nhwc(B, H, W, C, Ct, k, s, p, is_max, dt):
+    """vitk_pool_nhwc against torch's pooling of the same 16-bit tensor (max: bit-exact; average: one rounding of the exact
+    mean), stored with the block buffer's pitch."""
+    import torch.nn.functional as F
+    x = _rand(B, H, W, C, dtype=dt, seed=1)
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    out = torch.full((B, OH, OW, Ct), 5.0, dtype=dt, device=DEV)
+    ops.pool_nhwc(x, out, k, s, p, is_max)
+    xn = x.permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    if is_max:
+        assert torch.equal(out[..., :C], F.max_pool2d(xn, k, s, p).permute(0, 2, 3, 1))
+    else:                                                     # fp32 sum, one rounding to the 16-bit format
+        ref = F.avg_pool2d(xn.double(), k, s, p).permute(0, 2, 3, 1)
+        ulp = 2.0 ** -10 if dt == F16 else 2.0 ** -7
+        assert ((out[..., :C].double() - ref).abs() <= ulp * ref.abs().clamp_min(1e-3)).all()
+    if Ct > C:
+        assert (out[..., C:] == 5.0).all()
+    with pytest.raises(RuntimeError):
+        ops.pool_nhwc(x, out[:, :-1].contiguous(), k, s, p, is_max)

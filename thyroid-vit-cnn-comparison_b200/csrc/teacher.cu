@@ -36,10 +36,71 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// k x k / stride s / zero- or -inf-padded pooling of an NHWC tensor, 8 channels per thread, written with pixel pitch y_ld:
+// the stem's MaxPool2d(3, 2, 1) and the transitions' AvgPool2d(2, 2) store straight into channels [0, C) of the NEXT dense
+// block's concatenation buffer (no separate copy).  Sums in fp32, one rounding (what ATen does for 16-bit pooling).
+__global__ void __launch_bounds__(256)
+    pool_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long y_ld8, int B, int H, int W, int cv, int OH, int OW,
+                     int k, int s, int pad, int is_max, int fp16) {
+  const long long total = (long long)B * OH * OW * cv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float inv = 1.f / float(k * k);          // count_include_pad = True (AvgPool2d default)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = int(i % cv);
+    long long r = i / cv;
+    const int ow = int(r % OW);
+    r /= OW;
+    const int oh = int(r % OH);
+    const int b = int(r / OH);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = is_max ? -INFINITY : 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oh * s - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ow * s - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 in = __ldg(x + (((long long)b * H + iy) * W + ix) * cv + v);
+        const float2 p0 = unpack16(in.x, fp16), p1 = unpack16(in.y, fp16), p2 = unpack16(in.z, fp16), p3 = unpack16(in.w, fp16);
+        const float f[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = is_max ? fmaxf(acc[e], f[e]) : acc[e] + f[e];
+      }
+    }
+    if (!is_max) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    }
+    y[(((long long)b * OH + oh) * OW + ow) * y_ld8 + v] =
+        make_uint4(pack16(acc[0], acc[1], fp16), pack16(acc[2], acc[3], fp16), pack16(acc[4], acc[5], fp16), pack16(acc[6], acc[7], fp16));
+  }
+}
+
 }  // namespace
 }  // namespace vitk
 
 using namespace vitk;
+
+extern "C" int vitk_pool_nhwc(const void* x, void* y, int64_t y_ld, int32_t B, int32_t H, int32_t W, int32_t C, int32_t kernel,
+                              int32_t stride, int32_t pad, int32_t is_max, int32_t dtype, void* stream) {
+  VITK_CHECK_ARG(x && y, "vitk_pool_nhwc: null pointer");
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_pool_nhwc: dtype must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && y_ld >= C && y_ld % 8 == 0, "vitk_pool_nhwc: C=%d, pitch must be multiples of 8", C);
+  VITK_CHECK_ARG(kernel > 0 && stride > 0 && pad >= 0 && 2 * pad <= kernel && H + 2 * pad >= kernel && W + 2 * pad >= kernel,
+                 "vitk_pool_nhwc: bad window (kernel=%d stride=%d pad=%d)", kernel, stride, pad);
+  VITK_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "vitk_pool_nhwc: 16-byte aligned pointers required");
+  const int OH = (H + 2 * pad - kernel) / stride + 1, OW = (W + 2 * pad - kernel) / stride + 1;   // ceil_mode = False
+  const long long total = (long long)B * OH * OW * (C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  pool_nhwc_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), y_ld / 8, B, H, W, C / 8, OH, OW, kernel, stride, pad, is_max,
+      int(dtype == VITK_FP16));
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
 
 extern "C" int vitk_affine_relu_nhwc(const void* x, int64_t x_ld, void* y, int64_t y_ld, const float* scale, const float* shift,
                                      int64_t pixels, int32_t C, int32_t dtype, int32_t relu, void* stream) {

@@ -452,3 +452,15 @@ def affine_relu_nhwc(x, C: int, scale, shift, out=None, relu: bool = True):
     check(_lib.load().vitk_affine_relu_nhwc(x.data_ptr(), x.shape[-1], out.data_ptr(), out.shape[-1], scale.data_ptr(),
                                             shift.data_ptr(), pixels, C, _DT[x.dtype], int(relu), _stream()), "affine_relu_nhwc")
     return out
+
+
+def pool_nhwc(x, out, kernel: int, stride: int, pad: int, is_max: bool):
+    """x: contiguous 16-bit [B,H,W,C]; out: contiguous [B,OH,OW,C_total >= C] whose first C channels receive the pooled map."""
+    _req16(x, "pool x"); _req(out, x.dtype, "pool out")
+    B, H, W, Cc = x.shape
+    OH, OW = (H + 2 * pad - kernel) // stride + 1, (W + 2 * pad - kernel) // stride + 1
+    if tuple(out.shape[:3]) != (B, OH, OW) or out.shape[3] < Cc:
+        raise RuntimeError(f"pool_nhwc: out must be [B={B},{OH},{OW},>= {Cc}], got {tuple(out.shape)}")
+    check(_lib.load().vitk_pool_nhwc(x.data_ptr(), out.data_ptr(), out.shape[3], B, H, W, Cc, kernel, stride, pad, int(is_max),
+                                     _DT[x.dtype], _stream()), "pool_nhwc")
+    return out

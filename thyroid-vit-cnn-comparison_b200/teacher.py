@@ -9,7 +9,9 @@ eval-mode network allows three exact rewrites:
     existing ones, so `torch.cat` (a copy of everything so far, every layer) disappears;
   * norm1 + relu1 over that concatenation is one pass of `vitk_affine_relu_nhwc` (eval BatchNorm is a per-channel affine map);
   * norm2 (and the stem's norm0) directly follow a convolution: they fold into its weights and bias, and the ReLU behind them
-    rides on cuDNN's fused conv + bias + relu.
+    rides on cuDNN's fused conv + bias + relu;
+  * the stem's max pool and the transitions' average pools (`vitk_pool_nhwc`) store straight into the first channels of the next
+    block's buffer.
 The convolutions stay cuDNN calls (library GEMMs on a frozen network); parameters are snapshotted at construction, which is
 what "frozen" means in the reference (`freeze_teacher`, lightning_modules.py:771-773).
 """
@@ -54,17 +56,18 @@ def is_supported(module: nn.Module) -> bool:
 class FrozenDenseNet:
     """Callable replacement for `teacher(images)` of a frozen torchvision-style DenseNet (see module docstring)."""
 
-    def __init__(self, module: nn.Module, dtype=torch.bfloat16, affine_relu: Optional[Callable] = None):
+    def __init__(self, module: nn.Module, dtype=torch.bfloat16, affine_relu: Optional[Callable] = None,
+                 pool: Optional[Callable] = None):
         if not is_supported(module):
             raise TypeError("FrozenDenseNet expects a torchvision-style DenseNet (features.denseblockN.denselayerM, classifier)")
         self.dtype = dtype
         self._affine_relu = affine_relu if affine_relu is not None else ops.affine_relu_nhwc
+        self._pool = pool if pool is not None else ops.pool_nhwc
         f = module.features
         cl = lambda w: w.to(dtype).contiguous(memory_format=torch.channels_last)
         w0, b0 = _fold(f.conv0, f.norm0)
         self.stem = (cl(w0), b0.to(dtype), f.conv0.stride, f.conv0.padding)
-        p = f.pool0
-        self.stem_pool = (p.kernel_size, p.stride, p.padding)
+        self.stem_pool = self._pool_spec(f.pool0, True)
         self.blocks: List[dict] = []
         i = 1
         while hasattr(f, f"denseblock{i}"):
@@ -80,8 +83,7 @@ class FrozenDenseNet:
             tr = getattr(f, f"transition{i}", None)
             if tr is not None:
                 s, h = _bn_affine(tr.norm)
-                blk["transition"] = {"s": s, "h": h, "w": cl(tr.conv.weight.detach().float()),
-                                     "pool": (tr.pool.kernel_size, tr.pool.stride)}
+                blk["transition"] = {"s": s, "h": h, "w": cl(tr.conv.weight.detach().float()), "pool": self._pool_spec(tr.pool, False)}
             self.blocks.append(blk)
             i += 1
         self.s5, self.h5 = _bn_affine(f.norm5)
@@ -90,6 +92,18 @@ class FrozenDenseNet:
         self._fused_conv_relu = None      # decided on the first CUDA call
 
     # ------------------------------------------------------------------ pieces
+    @staticmethod
+    def _pool_spec(p: nn.Module, is_max: bool):
+        one = lambda v: v[0] if isinstance(v, (tuple, list)) else v
+        if isinstance(p, nn.MaxPool2d) != is_max or not isinstance(p, (nn.MaxPool2d, nn.AvgPool2d)) or getattr(p, "ceil_mode", False):
+            raise TypeError(f"unexpected pooling layer {p}")
+        return (int(one(p.kernel_size)), int(one(p.stride)), int(one(p.padding)), is_max)
+
+    @staticmethod
+    def _nhwc(t):                # NCHW-logical conv output -> contiguous [B,H,W,C] (a view when the tensor is channels_last)
+        t = t.permute(0, 2, 3, 1)
+        return t if t.is_contiguous() else t.contiguous()
+
     def _conv_bias_relu(self, x, w, b, stride, padding):
         """cuDNN conv + bias + relu in one call where the build supports it for this dtype, else conv2d + in-place relu."""
         if x.is_cuda and self._fused_conv_relu is None:
@@ -112,14 +126,16 @@ class FrozenDenseNet:
     def __call__(self, images: torch.Tensor) -> torch.Tensor:
         x = images.to(self.dtype).contiguous(memory_format=torch.channels_last)
         w0, b0, stride0, pad0 = self.stem
-        y = self._conv_bias_relu(x, w0, b0, stride0, pad0)
-        y = F.max_pool2d(y, *self.stem_pool)
+        src = self._nhwc(self._conv_bias_relu(x, w0, b0, stride0, pad0))               # [B,H,W,64]
+        pool = self.stem_pool
         buf = None
         for blk in self.blocks:
-            B, c0, H, W = y.shape
+            B, H, W, c0 = src.shape
+            k, st, pd, is_max = pool
+            OH, OW = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
             ct = c0 + sum(l["growth"] for l in blk["layers"])
-            buf = torch.empty(B, H, W, ct, dtype=self.dtype, device=y.device)         # the block's concatenation, NHWC
-            buf[..., :c0].copy_(y.permute(0, 2, 3, 1))
+            buf = torch.empty(B, OH, OW, ct, dtype=self.dtype, device=src.device)     # the block's concatenation, NHWC
+            self._pool(src, buf, k, st, pd, is_max)                                    # pooled input -> channels [0, c0)
             c = c0
             for l in blk["layers"]:
                 a = self._affine_relu(buf, c, l["s1"], l["h1"])                        # norm1 + relu1 over channels [0, c)
@@ -130,7 +146,8 @@ class FrozenDenseNet:
             tr = blk["transition"]
             if tr is not None:
                 a = self._affine_relu(buf, ct, tr["s"], tr["h"])
-                y = F.avg_pool2d(F.conv2d(self._nchw(a), tr["w"]), *tr["pool"])
+                src = self._nhwc(F.conv2d(self._nchw(a), tr["w"]))
+                pool = tr["pool"]
         a = self._affine_relu(buf, buf.shape[-1], self.s5, self.h5)                    # norm5 + the forward()'s F.relu
         pooled = a.float().mean(dim=(1, 2))                                            # adaptive_avg_pool2d((1, 1)) + flatten
         return F.linear(pooled, self.wc, self.bc)
