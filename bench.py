@@ -142,16 +142,35 @@ def gpu_eager_reference_run(model_name: str, steps: int, warmup: int, batch: int
     return batch / sec, sec
 
 
+# stdout carries exactly ONE JSON line: the process's fd 1 is pointed at stderr for the whole run (library banners such as
+# "NCCL version ..." are C-level printf to fd 1) and the result line is written to a duplicate of the original stdout.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if args.ref_device == "cuda":
         ips, sec = gpu_eager_reference_run(args.model, args.steps, max(3, args.warmup), args.batch, args.ref_precision)
-        print(json.dumps({"impl": "reference", "reference_device": "cuda (PyTorch eager, oracle port)", "precision": args.ref_precision,
-                          "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": sec * 1e3, "higher_is_better": True, "data": "synthetic",
-                          "config": workload_config(args, cpu=True)}), flush=True)
+        emit({"impl": "reference", "reference_device": "cuda (PyTorch eager, oracle port)", "precision": args.ref_precision,
+              "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": sec * 1e3, "higher_is_better": True, "data": "synthetic",
+              "config": workload_config(args, cpu=True)})
         return
     batch = 32 if args.model == "deit_tiny" else 8
     ips, sec, cores = cpu_reference_run(args.model, args.steps, max(1, args.warmup), batch)
@@ -164,7 +183,7 @@ def run_reference(args):
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cpu: bool = False):
@@ -303,8 +322,6 @@ def run_ours(args):
     import thyroid_vit_cnn_comparison_b200  # noqa: F401
     from thyroid_vit_cnn_comparison_b200 import ops, optim, parallel, training, vit
 
-    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = parallel.init_distributed()
     dev = torch.device("cuda", local)
     torch.manual_seed(42)
@@ -467,7 +484,7 @@ def run_ours(args):
             "cuda_graph": bool(use_graph), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "kernels": kernels,
             "loss": loss_val, "loss_scale": float(step.eng.amp[0].item()), "skipped_steps": float(step.eng.amp[3].item()),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # teardown must never hold the box: drop captured graphs (they pin NCCL work), then leave; a watchdog ends the
         # process if the communicator teardown itself blocks (the result line is already out)
@@ -503,6 +520,7 @@ def main():
     ap.add_argument("--ref-precision", default="fp32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--by-shape", action="store_true", help="split the GEMM rows of the kernel profile by shape")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
