@@ -7,8 +7,13 @@ the evidence for which of its passes a fused kernel would remove.
 import argparse
 import collections
 
+import sys
+from pathlib import Path
+
 import torch
 import torchvision
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
 def main():
@@ -29,6 +34,19 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         print(f"eager forward: {e0.elapsed_time(e1) / 5:.2f} ms / batch {a.batch}")
+        # the same network through the frozen-teacher executor (teacher.py: block buffer, fused BatchNorm + ReLU, folded convs)
+        import thyroid_vit_cnn_comparison_b200  # noqa: F401
+        from thyroid_vit_cnn_comparison_b200 import teacher as T
+        fast = T.FrozenDenseNet(m, dtype=torch.bfloat16)
+        for _ in range(3):
+            fast(x)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fast(x)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"FrozenDenseNet forward: {e0.elapsed_time(e1) / 5:.2f} ms / batch {a.batch} (fused conv+bias+relu: {fast._fused_conv_relu})")
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
             m(x)
             torch.cuda.synchronize()
