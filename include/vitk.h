@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 15
+#define VITK_ABI_VERSION 16
 
 typedef enum {
   VITK_OK = 0,
@@ -277,6 +277,16 @@ int vitk_percentile_bounds(const float* x, int32_t B, int64_t n, float q_lo, flo
 int vitk_finish_tiles(const float* gray, const float* bounds, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
                       const float* mean, const float* stdv, const int32_t* perm, int32_t cutmix, float lam, int32_t x1,
                       int32_t y1, int32_t x2, int32_t y2, void* stream);
+/* Single-channel tiles straight to the 16-bit patch matrix the patch-embedding GEMM reads -- the input side of
+ * PatchEmbed.proj (vision_transformer_base.py:95-101,136-138) fused with `x.repeat(3,1,1)` + T.Normalize
+ * (vit_transforms.py:381-393) and, optionally, the percentile clamp-normalise (:314-316):
+ *   patches[(b,py,px), c*P*P + ky*P + kx] = 16-bit((norm(tile[b, py*P+ky, px*P+kx]) - mean[c]) / std[c])
+ * tiles [B,H,W]: tiles_kind 0 = fp32 in [0,1], 1 = raw uint16 (value / 65535, dataset.py:549), 2 = fp16, 3 = bf16.
+ * The fp32 value before the 16-bit rounding is bit-identical to vitk_finish_tiles' output, so the result equals
+ * vitk_finish_tiles + vitk_patchify; the fp32 [B,C,H,W] batch is never materialised.  mean/std: HOST arrays [C] or NULL. */
+int vitk_tiles_to_patches(const void* tiles, int32_t tiles_kind, const float* bounds, const float* mean,
+                          const float* stdv, void* patches, int32_t patches_dtype, int32_t B, int32_t C,
+                          int32_t H, int32_t W, int32_t P, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * On-device classification metrics -- the torchmetrics objects of lightning_modules.py:358-374 and their per-step
@@ -303,7 +313,9 @@ int vitk_binary_auroc(const float* scores, const uint8_t* score_labels, const in
  * mode 0: w_cls*CE(cls,y) [+ w_dist*CE(dist,y) if dist given]
  * mode 1: w_cls*CE(cls,y) + w_dist*KL_soft(dist, teacher, T)
  * mode 2: w_cls*CE(cls,y) + w_dist*CE(dist, argmax teacher)
- * out_scalars fp32[8]: {loss, cls_loss, dist_loss, n_correct(cls vs y), n_agree(cls vs teacher), ...}
+ * out_scalars fp32[8]: {loss, cls_loss, dist_loss, n_correct(cls vs y), n_agree(cls vs teacher), B, n_invalid_labels, 0}.
+ * A label outside [0, C) never indexes a row (torch's CE device-asserts): it is counted in out[6], the loss and that
+ * row's gradient become NaN, so the optimizer skips the step.
  * dcls/ddist: fp32 [B,C] gradient of `loss` (already divided by B*grad_div; grad_div = world size
  * under data parallel so that an all-reduce SUM yields the global-batch mean).
  * ------------------------------------------------------------------------------------------ */

@@ -328,3 +328,40 @@ def test_bench_traffic_table_points_at_committed_ncu_captures():
             nbytes, src = bench.ncu_traffic(model, label)
             assert nbytes > 0 and src.endswith(f":{case}")
     assert bench.ncu_traffic("deit_tiny", "no such kernel") == (None, None)
+
+
+def test_product_side_kfold_reproduces_reference_fixture_and_pins_5fold(tmp_path):
+    """generate_kfold_splits (scripts/prepare_kfold_data.py:30-73) in the PRODUCT package: all 21 index lists of the
+    reference's committed 7-fold files bit-exactly, the JSON files it writes, and the 5-fold variant of BASELINE.json
+    config 5 pinned against the oracle's restatement + its partition / stratification invariants."""
+    import json
+    from thyroid_vit_cnn_comparison_b200 import kfold
+    from oracle import vit_oracle as O
+    rec = json.loads((ROOT / "tests" / "golden" / "kfold_splits_7.json").read_text())
+    labels = kfold.cars_labels(225, 225)
+    assert labels.tolist() == rec["labels"] if "labels" in rec and isinstance(rec["labels"], list) else True
+    runs = kfold.generate_kfold_splits(labels, 7, random_state=42, splits_dir=tmp_path)
+    assert runs == rec["folds"]                                              # 7 folds x {train, val, test}
+    for i in range(1, 8):
+        on_disk = json.loads((tmp_path / f"split_fold_{i}.json").read_text())
+        assert on_disk == rec["folds"][i - 1] and list(on_disk) == ["train", "val", "test"]
+        assert kfold.load_fold_split(tmp_path, i) == rec["folds"][i - 1]
+    five = kfold.generate_kfold_splits(labels, 5)
+    assert five == O.kfold_splits(labels.tolist(), k=5, seed=42)
+    tests = [set(r["test"]) for r in five]
+    assert sorted(x for t in tests for x in t) == list(range(450))           # the test folds partition the dataset
+    for i, r in enumerate(five):
+        assert sorted(r["train"] + r["val"] + r["test"]) == list(range(450))
+        assert r["val"] == five[(i + 1) % 5]["test"]                          # rotation rule
+        assert abs(sum(int(labels[j]) for j in r["test"]) - len(r["test"]) / 2) <= 1
+    # the reference's calling convention: a raw-data directory with normal/ and cancerous/ sub-directories
+    raw = tmp_path / "raw"
+    for cls, n in (("normal", 12), ("cancerous", 9)):
+        (raw / cls).mkdir(parents=True)
+        for j in range(n):
+            (raw / cls / f"{j}.tif").write_bytes(b"")
+    by_dir = kfold.generate_kfold_splits(raw, 3)
+    assert by_dir == kfold.generate_kfold_splits(kfold.cars_labels(12, 9), 3)
+    assert (tmp_path / "splits" / "split_fold_3.json").exists()
+    with pytest.raises(ValueError):
+        kfold.generate_kfold_splits(labels, 2)

@@ -654,7 +654,8 @@ def test_distill_step_uses_fast_teacher_and_matches_plain_teacher_call():
         model, _ = build(cfg, 31)
         model.train()
         opt = OPT.FusedAdamW(model, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
-        step = TR.TrainStep(model, opt, 8, mode="distill", teacher=teacher, use_graph=fast, teacher_fast=fast)
+        step = TR.TrainStep(model, opt, 8, mode="distill", teacher=teacher, use_graph=fast, teacher_fast=fast,
+                            teacher_dtype=torch.bfloat16)          # the 16-bit teacher is opt-in (default: fp32, as the reference)
         assert isinstance(step._teacher_fn, T.FrozenDenseNet) == fast
         for _ in range(2):
             st = step(x.cuda(), y.cuda())

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -75,6 +75,7 @@ SIGNATURES = {
     "vitk_resize_u16": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "vitk_percentile_bounds": (c_int, [c_void_p, c_int, c_int64, c_float, c_float, c_void_p, c_void_p]),
     "vitk_finish_tiles": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 3 + [c_int, c_float] + [c_int] * 4 + [c_void_p]),
+    "vitk_tiles_to_patches": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "vitk_metrics_update": (c_int, [c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int64, c_void_p]),
     "vitk_binary_auroc": (c_int, [c_void_p] * 3 + [c_int64] + [c_void_p] * 3),
     "vitk_loss_fwd_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int] + [c_float] * 5 + [c_void_p]),

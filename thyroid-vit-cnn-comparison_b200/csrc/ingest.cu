@@ -255,6 +255,70 @@ __global__ void __launch_bounds__(256) finish_tiles_kernel(FinishParams p) {
   }
 }
 
+// ------------------------------------------------------------------ gray tiles -> 16-bit patch matrix (no NCHW round trip)
+// patches[(b, py, px), c*P*P + ky*P + kx] = 16-bit( (norm(tile[b, py*P+ky, px*P+kx]) - mean[c]) / std[c] )
+// i.e. finish_tiles (gray -> C replicated channels + T.Normalize, same operation order: the fp32 values are bit-identical)
+// followed by the patch gather of PatchEmbed.proj (vision_transformer_base.py:95-101,136-138), in ONE pass: the fp32
+// [B,C,H,W] batch never exists, the step's input is the single-channel tile (2 bytes/pixel over PCIe / from HBM), and
+// the patch GEMM reads what this kernel wrote.  8 pixels per thread: one 16-byte load (u16 / 16-bit) or two (fp32),
+// one 16-byte store per channel.
+struct TilePatchParams {
+  const void* tiles;
+  const float* bounds;   // [B,2] or nullptr
+  void* patches;
+  int src_kind;          // 0 fp32 [0,1], 1 uint16 (/65535), 2 fp16, 3 bf16
+  int fp16_out;
+  int B, C, H, W, P;
+  float mean[4], stdv[4];
+  int has_norm;
+};
+__global__ void __launch_bounds__(256) tiles_to_patches_kernel(TilePatchParams p) {
+  const int wv = p.W >> 3;
+  const long long total = (long long)p.B * p.H * wv;
+  const int gw = p.W / p.P, gh = p.H / p.P;
+  const int PP = p.P * p.P;
+  const int Kdim = p.C * PP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xv = int(i % wv);
+    const int y = int((i / wv) % p.H);
+    const long long b = i / ((long long)wv * p.H);
+    const long long off = (b * p.H + y) * (long long)p.W + 8 * xv;
+    float g[8];
+    if (p.src_kind == 0) {
+      const float4 a0 = ldg_f4(reinterpret_cast<const float*>(p.tiles) + off), a1 = ldg_f4(reinterpret_cast<const float*>(p.tiles) + off + 4);
+      g[0] = a0.x; g[1] = a0.y; g[2] = a0.z; g[3] = a0.w; g[4] = a1.x; g[5] = a1.y; g[6] = a1.z; g[7] = a1.w;
+    } else {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.tiles) + off));
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.src_kind == 1) {   // _preprocess_image: astype(float32) / 65535
+          g[2 * j] = __fdiv_rn((float)(w4[j] & 0xffffu), 65535.f);
+          g[2 * j + 1] = __fdiv_rn((float)(w4[j] >> 16), 65535.f);
+        } else {
+          const float2 f = unpack16(w4[j], p.src_kind == 2);
+          g[2 * j] = f.x;
+          g[2 * j + 1] = f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = adapt(g[j], p.bounds, b);
+    const int x = 8 * xv;
+    const int py = y / p.P, ky = y - py * p.P, px = x / p.P, kx = x - px * p.P;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.patches) + ((b * gh + py) * gw + px) * (long long)Kdim + ky * p.P + kx;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= p.C) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = p.has_norm ? __fdiv_rn(g[j] - p.mean[c], p.stdv[c]) : g[j];
+      *reinterpret_cast<uint4*>(dst + c * PP) = make_uint4(pack16(o[0], o[1], p.fp16_out), pack16(o[2], o[3], p.fp16_out),
+                                                           pack16(o[4], o[5], p.fp16_out), pack16(o[6], o[7], p.fp16_out));
+    }
+  }
+}
+
 }  // namespace
 }  // namespace vitk
 
@@ -305,6 +369,30 @@ extern "C" int vitk_finish_tiles(const float* gray, const float* bounds, float* 
   p.x1 = x1; p.y1 = y1; p.x2 = x2; p.y2 = y2;
   const long long total = (long long)B * H * (W / 4);
   finish_tiles_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_tiles_to_patches(const void* tiles, int32_t tiles_kind, const float* bounds, const float* mean,
+                                     const float* stdv, void* patches, int32_t patches_dtype, int32_t B, int32_t C,
+                                     int32_t H, int32_t W, int32_t P, void* stream) {
+  VITK_CHECK_ARG(tiles && patches && B > 0 && C >= 1 && C <= 4, "vitk_tiles_to_patches: bad args (1 <= C <= 4)");
+  VITK_CHECK_ARG(tiles_kind >= 0 && tiles_kind <= 3, "vitk_tiles_to_patches: tiles_kind 0 fp32, 1 uint16, 2 fp16, 3 bf16");
+  VITK_CHECK_ARG(patches_dtype == VITK_BF16 || patches_dtype == VITK_FP16, "vitk_tiles_to_patches: patches must be bf16 or fp16");
+  VITK_CHECK_ARG(P > 0 && P % 8 == 0 && H % P == 0 && W % P == 0,
+                 "vitk_tiles_to_patches: need P %% 8 == 0 and H, W divisible by P (H=%d W=%d P=%d)", H, W, P);
+  VITK_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "vitk_tiles_to_patches: mean and std come together");
+  TilePatchParams p;
+  p.tiles = tiles; p.bounds = bounds; p.patches = patches;
+  p.src_kind = tiles_kind; p.fp16_out = int(patches_dtype == VITK_FP16);
+  p.B = B; p.C = C; p.H = H; p.W = W; p.P = P;
+  p.has_norm = mean != nullptr;
+  for (int c = 0; c < 4; ++c) {
+    p.mean[c] = (mean != nullptr && c < C) ? mean[c] : 0.f;      // HOST arrays, as in vitk_finish_tiles
+    p.stdv[c] = (stdv != nullptr && c < C) ? stdv[c] : 1.f;
+  }
+  const long long total = (long long)B * H * (W / 8);
+  tiles_to_patches_kernel<<<capped_grid(total, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -56,14 +56,19 @@ __global__ void __launch_bounds__(LOSS_THREADS)
                 const long long* __restrict__ labels, float* __restrict__ out, float* __restrict__ dcls,
                 float* __restrict__ ddist, int B, int C, int mode, float w_cls, float w_dist, float T, float eps,
                 float grad_div) {
-  __shared__ float red[4][LOSS_THREADS / 32];
-  float acc_cls = 0.f, acc_dist = 0.f, n_correct = 0.f, n_agree = 0.f;
+  __shared__ float red[5][LOSS_THREADS / 32];
+  float acc_cls = 0.f, acc_dist = 0.f, n_correct = 0.f, n_agree = 0.f, n_bad = 0.f;
   const float gscale_cls = w_cls / (float(B) * grad_div);
   const float gscale_dist = w_dist / (float(B) * grad_div);
   for (int b = threadIdx.x; b < B; b += LOSS_THREADS) {
     const float* rc = cls + (long long)b * C;
-    const int y = (int)labels[b];
-    acc_cls += ce_row(rc, C, y, eps, gscale_cls, dcls + (long long)b * C);
+    // a label outside [0, C) must not index the row (torch's CE raises a device assert): it is counted in out[6], the
+    // loss becomes NaN and so do this row's gradients, which makes the optimizer skip the step (non-finite norm)
+    const long long yl = labels[b];
+    const bool bad = yl < 0 || yl >= (long long)C;
+    const int y = bad ? 0 : (int)yl;
+    n_bad += bad ? 1.f : 0.f;
+    acc_cls += ce_row(rc, C, y, eps, bad ? __int_as_float(0x7fc00000) : gscale_cls, dcls + (long long)b * C);
     const int pred = row_argmax(rc, C);
     n_correct += (pred == y) ? 1.f : 0.f;
     if (teacher != nullptr) n_agree += (pred == row_argmax(teacher + (long long)b * C, C)) ? 1.f : 0.f;
@@ -94,26 +99,26 @@ __global__ void __launch_bounds__(LOSS_THREADS)
       }
     }
   }
-  float vals[4] = {acc_cls, acc_dist, n_correct, n_agree};
+  float vals[5] = {acc_cls, acc_dist, n_correct, n_agree, n_bad};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) {
     const float v = warp_sum(vals[k]);
     if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < 4; ++k)
+    float tot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 5; ++k)
       for (int w = 0; w < LOSS_THREADS / 32; ++w) tot[k] += red[k][w];
     const float cls_loss = tot[0] / float(B);
     const float dist_loss = tot[1] / float(B);
-    out[0] = w_cls * cls_loss + (dist != nullptr ? w_dist * dist_loss : 0.f);
+    out[0] = tot[4] > 0.f ? __int_as_float(0x7fc00000) : w_cls * cls_loss + (dist != nullptr ? w_dist * dist_loss : 0.f);
     out[1] = cls_loss;
     out[2] = dist_loss;
     out[3] = tot[2];
     out[4] = tot[3];
     out[5] = float(B);
-    out[6] = 0.f;
+    out[6] = tot[4];   // number of labels outside [0, C)
     out[7] = 0.f;
   }
 }

@@ -79,6 +79,15 @@ def execution_order(names: List[str], depth: int) -> List[str]:
     return sorted(names, key=lambda n: (key(n), names.index(n)))
 
 
+@dataclass
+class GraySpec:
+    """How single-channel tiles become the model's `chans` input channels: optional per-image clamp-normalise bounds
+    (fp32 CUDA [B,2], ingest percentile stage) and optional T.Normalize statistics (one per channel)."""
+    bounds: Optional[torch.Tensor] = None
+    mean: Optional[Tuple[float, ...]] = None
+    std: Optional[Tuple[float, ...]] = None
+
+
 class FlatParams:
     """One fp32 buffer for all trainable tensors + same-layout gradient and 16-bit shadow buffers."""
 
@@ -189,6 +198,7 @@ class VitEngine:
         self.scale = 64 ** -0.5
         self.sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.grad_ready_hook = None   # callable(stage) used by the data-parallel bucket launcher
+        self.fused_optimizer = None   # weakref to the FusedAdamW that owns the loss-scale bookkeeping (None: external optimizer)
         self.generation = 0
         self._drop_on = False
         s0 = self.INIT_LOSS_SCALE if dtype16 == torch.float16 else 1.0
@@ -272,19 +282,30 @@ class VitEngine:
                  colsum_out=self.g(bias_name) if bias_name is not None else None)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, images: torch.Tensor, train: bool, attn_probs: Optional[List[torch.Tensor]] = None,
-                features: Optional[dict] = None):
-        """features (inference only): a dict that receives 'pooled' = norm(x)[:, :n_out] as fp32 [n_out,B,D] and
+    def forward(self, images: torch.Tensor, train: bool, attn_probs=None, features: Optional[dict] = None,
+                gray: Optional["GraySpec"] = None):
+        """gray: when given, `images` are single-channel tiles [B,H,W] / [B,1,H,W] (fp32 in [0,1], raw uint16, fp16 or
+        bf16) that the loader would have replicated to `chans` channels and normalised (vit_transforms.py:381-393).
+        attn_probs (inference only): a list that receives one fp32 [B,H,T,T] tensor per block, or a preallocated
+        contiguous fp32 [L,B,H,T,T] tensor the blocks write into.
+        features (inference only): a dict that receives 'pooled' = norm(x)[:, :n_out] as fp32 [n_out,B,D] and
         'x_last' = the final residual stream fp32 [B,T,D] (a workspace view: copy or consume before the next call)."""
         d = self.d
-        if images.dim() != 4 or images.shape[1] != d.chans:
+        if gray is None and (images.dim() != 4 or images.shape[1] != d.chans):
             raise ValueError(f"expected images [B,{d.chans},H,W], got {tuple(images.shape)}")
+        if gray is not None:
+            if d.patch_linear:
+                raise NotImplementedError("gray tile input is implemented for projection_type='conv' only")
+            if images.dim() == 4 and images.shape[1] == 1:
+                images = images[:, 0]
+            if images.dim() != 3 or images.shape[1] != d.img or images.shape[2] != d.img:
+                raise ValueError(f"expected gray tiles [B,{d.img},{d.img}] (or [B,1,H,W]), got {tuple(images.shape)}")
         B = images.shape[0]
         T, D = d.tokens, d.dim
         M = B * T
         ws = self.workspace(B, train)
         images = images.contiguous()
-        if images.dtype != torch.float32:
+        if gray is None and images.dtype != torch.float32:
             images = images.float()
         dp = None
         if train and any(r > 0.0 for r in self.drop_path):
@@ -301,7 +322,12 @@ class VitEngine:
         if self._drop_on:
             self.drop_seed.random_(0, 1 << 62)      # torch's CUDA generator: seedable and CUDA-graph safe (fresh per replay)
         rs = lambda i: dp[i] if (dp is not None and self.drop_path[i] > 0.0) else None
-        ops.patchify(images, d.patch, out=ws.patches, channel_last=d.patch_linear)
+        if gray is not None:
+            # single-channel tiles (fp32 | uint16 | 16-bit) -> replicated + normalised channels, written straight into the
+            # 16-bit patch matrix: the fp32 [B,C,H,W] batch of the reference's loader never exists on this path
+            ops.tiles_to_patches(images, d.chans, d.patch, bounds=gray.bounds, mean=gray.mean, std=gray.std, out=ws.patches)
+        else:
+            ops.patchify(images, d.patch, out=ws.patches, channel_last=d.patch_linear)
         x0 = ws.x[0]
         ops.gemm(ws.patches, self.w(self.patch_w), B * d.n_patches, D, d.kpatch, out=x0,
                  bias=self.p(self.patch_b), epilogue=_lib.EPI_TOKENS,
@@ -320,7 +346,9 @@ class VitEngine:
             ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), eps=d.eps, y=ws.xn1[s], mean=st[0], rstd=st[1])
             ops.gemm(ws.xn1[s], self.w(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
             probs = None
-            if attn_probs is not None:
+            if isinstance(attn_probs, torch.Tensor):       # caller-owned [L,B,H,T,T] buffer (ensemble rollout): no stacking copy later
+                probs = attn_probs[l]
+            elif attn_probs is not None:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
             ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs, drop=self._attn_site(l))

@@ -7,6 +7,7 @@ tensors that merely own the memory.  No function here computes anything with tor
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as C_
 from typing import Optional
 
 import torch
@@ -391,6 +392,37 @@ def finish_tiles(gray, C: int, *, bounds=None, mean=None, std=None, perm=None, c
     x1, y1, x2, y2 = (int(v) for v in box)
     check(_lib.load().vitk_finish_tiles(gray.data_ptr(), _p(bounds), out.data_ptr(), B, C, H, W, marr, sarr, _p(perm),
                                         int(bool(cutmix)), float(lam), x1, y1, x2, y2, _stream()), "finish_tiles")
+    return out
+
+
+_TILE_KIND = {f32: 0, torch.uint16: 1, f16: 2, bf16: 3}
+
+
+def tiles_to_patches(tiles, C: int, P: int, *, bounds=None, mean=None, std=None, out=None, dtype=f16):
+    """single-channel tiles [B,H,W] or [B,1,H,W] (fp32 in [0,1] | raw uint16 | fp16 | bf16, CUDA) -> 16-bit patch matrix
+    [B*(H/P)*(W/P), C*P*P] (channel-first patch vectors): vitk_finish_tiles + vitk_patchify in one pass."""
+    if tiles.dim() == 4 and tiles.shape[1] == 1:
+        tiles = tiles[:, 0]
+    if tiles.dim() != 3 or not tiles.is_cuda or not tiles.is_contiguous() or tiles.dtype not in _TILE_KIND:
+        raise TypeError("tiles_to_patches: tiles must be a contiguous CUDA [B,H,W] tensor of fp32 / uint16 / fp16 / bf16")
+    B, H, W = tiles.shape
+    if (mean is None) != (std is None):
+        raise ValueError("tiles_to_patches: mean and std come together")
+    marr = sarr = None
+    if mean is not None:
+        if len(mean) != C or len(std) != C:
+            raise ValueError("tiles_to_patches: one mean / std per output channel")
+        marr = (C_.c_float * C)(*[float(v) for v in mean])
+        sarr = (C_.c_float * C)(*[float(v) for v in std])
+    if bounds is not None:
+        _req(bounds, f32, "tiles_to_patches bounds")
+    rows, kdim = B * (H // P) * (W // P), C * P * P
+    out = torch.empty(rows, kdim, dtype=dtype, device=tiles.device) if out is None else out
+    _req16(out, "tiles_to_patches out")
+    if out.numel() != rows * kdim:
+        raise ValueError("tiles_to_patches: out has the wrong size")
+    check(_lib.load().vitk_tiles_to_patches(tiles.data_ptr(), _TILE_KIND[tiles.dtype], _p(bounds), marr, sarr, out.data_ptr(),
+                                            _DT[out.dtype], B, C, H, W, P, _stream()), "tiles_to_patches")
     return out
 
 

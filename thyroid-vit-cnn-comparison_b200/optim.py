@@ -27,6 +27,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self.model = model
         eng = model._ensure_engine()
         self.engine = eng
+        import weakref
+        eng.fused_optimizer = weakref.ref(self)      # this optimizer owns the fp16 loss-scale bookkeeping from now on
         if params is None:
             params = [p for p in model.parameters()]
         params = list(params)
@@ -42,6 +44,12 @@ class FusedAdamW(torch.optim.Optimizer):
         # state = {step, lr(base, fixed 1.0: per-chunk table carries the real lr), grad_sqnorm, clip_coef}
         self.dev_state = torch.tensor([0.0, 1.0, 0.0, 1.0], dtype=torch.float32, device=dev)
         ptr_to_name = {p.data_ptr(): n for n, p in model._engine_params().items()}
+        self._name_of = {}                      # id(parameter) -> flat-buffer entry (parameters the engine owns)
+        for g in self.param_groups:
+            for p in g["params"]:
+                n = ptr_to_name.get(p.data_ptr())
+                if n is not None:
+                    self._name_of[id(p)] = n
         self._chunk_group: List[int] = []       # group index of every chunk (-1: not optimised -> lr 0)
         offs, lens = [], []
         group_of: Dict[str, int] = {}
@@ -102,6 +110,53 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.engine.zero_grad()
+
+    # ------------------------------------------------------------------ checkpointing
+    # The moments live in two flat buffers and the step count / loss scale on the device, none of which torch's default
+    # Optimizer.state_dict() would see.  state_dict() therefore emits exactly torch.optim.AdamW's layout -- per-parameter
+    # {'step', 'exp_avg', 'exp_avg_sq'} under the packed parameter index -- so a Lightning checkpoint written by the
+    # reference (torch AdamW, lightning_modules.py:599-604) resumes here and vice versa, plus one extra key `vitk` with the
+    # device-side scalars torch has no slot for (dynamic loss scale, skipped-step counters).
+    def state_dict(self):
+        sd = super().state_dict()                    # param_groups with packed indices; `state` is empty (nothing lives there)
+        flat = self.engine.flat
+        step = self.dev_state[0:1].detach().clone().cpu().reshape(())
+        state, idx = {}, 0
+        for g in self.param_groups:
+            for p in g["params"]:
+                n = self._name_of.get(id(p))
+                if n is not None and float(step) > 0:
+                    state[idx] = {"step": step.clone(), "exp_avg": flat.view(self.exp_avg, n).detach().clone(),
+                                  "exp_avg_sq": flat.view(self.exp_avg_sq, n).detach().clone()}
+                idx += 1
+        sd["state"] = state
+        sd["vitk"] = {"amp": self.engine.amp.detach().clone().cpu(), "dev_state": self.dev_state.detach().clone().cpu(),
+                      "max_grad_norm": self.max_grad_norm}
+        return sd
+
+    def load_state_dict(self, state_dict) -> None:
+        sd = dict(state_dict)
+        extra = sd.pop("vitk", None)
+        super().load_state_dict(sd)                  # validates the group structure, restores lr / weight_decay / ...
+        flat = self.engine.flat
+        step = None
+        for g in self.param_groups:
+            for p in g["params"]:
+                st = self.state.get(p)
+                n = self._name_of.get(id(p))
+                if st is None or n is None:
+                    continue
+                flat.view(self.exp_avg, n).copy_(st["exp_avg"].to(self.exp_avg.device, torch.float32).view_as(p))
+                flat.view(self.exp_avg_sq, n).copy_(st["exp_avg_sq"].to(self.exp_avg.device, torch.float32).view_as(p))
+                step = float(st["step"]) if step is None else step
+        self.state.clear()                           # the flat buffers are the only copy
+        if extra is not None:
+            self.dev_state.copy_(extra["dev_state"].to(self.dev_state.device))
+            self.engine.amp.copy_(extra["amp"].to(self.engine.amp.device))
+        elif step is not None:                       # a plain torch.optim.AdamW checkpoint: only the step count carries over
+            self.dev_state[0] = step
+        self._hyper_cache = None
+        self._refresh_hyper()
 
     @property
     def last_clip_coef(self) -> float:

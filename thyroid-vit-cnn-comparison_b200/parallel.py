@@ -64,10 +64,14 @@ def completed_prefix(order: List[str], offsets: dict, pad: int, stage: str, dept
 class BucketedAllReduce:
     """Gradient reducer attached to a VitEngine (see module docstring)."""
 
-    def __init__(self, process_group=None, bucket_mb: float = 25.0):
+    def __init__(self, process_group=None, bucket_mb: float = 25.0, min_buckets: int = 6):
+        """bucket_mb caps a bucket; min_buckets shrinks it for small models (DeiT-tiny's whole gradient is 22 MB: one
+        25 MB bucket would only leave after backward has ended, i.e. nothing would overlap) -- the bucket size is
+        min(bucket_mb, total / min_buckets), cut at tensor boundaries."""
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.min_buckets = max(1, int(min_buckets))
         self.engine = None
         self.buckets: List[Tuple[int, int]] = []
         self._next = 0
@@ -78,7 +82,9 @@ class BucketedAllReduce:
         from .engine import PAD
         self.engine = engine
         self._pad = PAD
-        self.buckets = engine.flat.bucket_slices(self.bucket_bytes)
+        total_bytes = 4 * sum((shape.numel() + PAD - 1) // PAD * PAD for _, shape in engine.flat.offsets.values())
+        per_bucket = min(self.bucket_bytes, max(4 * PAD, -(-total_bytes // self.min_buckets)))
+        self.buckets = engine.flat.bucket_slices(per_bucket)
         engine.grad_ready_hook = self.on_stage_done
         self._next = 0
 
@@ -90,7 +96,8 @@ class BucketedAllReduce:
         while self._next < len(self.buckets) and self.buckets[self._next][1] <= done:
             s, e = self.buckets[self._next]
             self._works.append(dist.all_reduce(flat.grads[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-            self.launched_log.append((stage, self._next))
+            if len(self.launched_log) < 4096:
+                self.launched_log.append((stage, self._next))
             self._next += 1
 
     def finish(self) -> None:

@@ -83,29 +83,55 @@ def _get(cfg: Any, key: str, default=None):
     return getattr(cfg, key, default)
 
 
-def _common_kwargs(cfg) -> dict:
-    """Top-level keys the reference wrappers read (deit.py:26-32, vision_transformer.py:27-40) plus the YAML
-    `params:` block the hand-written constructors take (configs/model/vit/deit_tiny.yaml:11-33)."""
-    extra = _get(cfg, "extra_params", {}) or {}
-    in_chans = _get(extra, "in_chans", None) or _get(cfg, "in_channels", None) or _get(cfg, "channels", None) or 3
+def _in_chans(cfg) -> int:
+    """deit.py:29-32 / vision_transformer.py:31-35: extra_params['in_chans'], else config.channels, else 1 -- each tested
+    with `is not None`, so an explicit value is never skipped."""
+    extra = getattr(cfg, "extra_params", None) if hasattr(cfg, "extra_params") else None
+    if extra is None and isinstance(cfg, dict):
+        extra = cfg.get("extra_params")
+    v = _get(extra, "in_chans", None) if extra is not None else None
+    if v is None:
+        v = _get(cfg, "channels", None)
+    return 1 if v is None else int(v)
+
+
+_TIMM_LN_EPS = 1e-6      # timm's VisionTransformer builds its norms as partial(nn.LayerNorm, eps=1e-6)
+
+
+def _wrapper_kwargs(cfg) -> dict:
+    """What the reference wrappers pass on (deit.py:26-53, vision_transformer.py:27-69): num_classes (default 2), img_size
+    (224), patch_size (16, ViT wrapper only), in_chans.  The wrappers hand these to timm's plain ViT/DeiT variants --
+    non-distilled, stochastic depth 0, LayerNorm eps 1e-6, no quality branch -- and never look at the YAML `params:` block,
+    so the same holds here: the module tree (and therefore the state_dict key set a reference checkpoint was written
+    with) is that of the timm model.
+
+    `extra_params.handwritten: true` opts into the reference's HAND-WRITTEN constructors instead (deit_models.py /
+    vit_models.py, which the YAML `params:` block -- embed_dim, depth, distilled, drop rates, quality_aware ... -- describes)."""
+    import functools
     kw = dict(img_size=int(_get(cfg, "img_size", 224)), patch_size=int(_get(cfg, "patch_size", 16)),
-              in_chans=int(in_chans), num_classes=int(_get(cfg, "num_classes", 2)))
-    params = _get(cfg, "params", {}) or {}
-    for k in ("embed_dim", "depth", "num_heads", "mlp_ratio", "qkv_bias", "drop_rate", "attn_drop_rate", "drop_path_rate",
-              "distilled", "quality_aware", "store_attention"):
-        v = _get(params, k, None)
-        if v is not None:
-            kw[k] = v
+              in_chans=_in_chans(cfg), num_classes=int(_get(cfg, "num_classes", 2)))
+    extra = _get(cfg, "extra_params", {}) or {}
+    if _get(extra, "handwritten", False):
+        params = _get(cfg, "params", {}) or {}
+        for k in ("embed_dim", "depth", "num_heads", "mlp_ratio", "qkv_bias", "drop_rate", "attn_drop_rate", "drop_path_rate",
+                  "distilled", "quality_aware", "store_attention", "representation_size", "pos_embed_type", "pool_type",
+                  "class_token"):
+            v = _get(params, k, None)
+            if v is not None:
+                kw[k] = v
+        return kw
+    kw.update(drop_path_rate=0.0, quality_aware=False, norm_layer=functools.partial(nn.LayerNorm, eps=_TIMM_LN_EPS))
     return kw
 
 
 @ModelRegistry.register(["deit_tiny", "deit_small", "deit_base"], "vit")
 class DeiT(ModelBase):
-    """src/models/vit/deit.py:10-72.  The reference maps these names to timm's NON-distilled deit_*_patch16_224
-    (single logits tensor); `params.distilled: true` in the model YAML selects the hand-written distilled variant."""
+    """src/models/vit/deit.py:10-72.  The reference maps these names to timm's NON-distilled deit_*_patch16_224 (one
+    logits tensor; `lightning_modules.py:954-957` then uses it for both loss terms); see `_wrapper_kwargs`."""
 
     def __init__(self, config):
         super().__init__(config)
+        self.variant = config.name
         self._build_model()
 
     def _build_model(self):
@@ -113,7 +139,7 @@ class DeiT(ModelBase):
         factory = {"deit_tiny": V.create_deit_tiny, "deit_small": V.create_deit_small, "deit_base": V.create_deit_base}.get(name)
         if factory is None:
             raise ValueError(f"Unsupported DeiT model name: {name}")
-        kw = _common_kwargs(self.config)
+        kw = _wrapper_kwargs(self.config)
         kw.setdefault("distilled", False)
         kw.setdefault("drop_path_rate", 0.0)
         self.model = factory(pretrained=False, **kw)
@@ -128,13 +154,14 @@ class VisionTransformer(ModelBase):
 
     def __init__(self, config):
         super().__init__(config)
+        self.variant = config.name
         self._build_model()
 
     def _build_model(self):
         name = self.config.name
         if name not in V.VIT_MODEL_REGISTRY:
             raise ValueError(f"Unsupported ViT model name: {name}")
-        kw = _common_kwargs(self.config)
+        kw = _wrapper_kwargs(self.config)
         kw.setdefault("drop_path_rate", 0.0)
         self.model = V.VIT_MODEL_REGISTRY[name](**kw)
 

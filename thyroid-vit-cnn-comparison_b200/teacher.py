@@ -49,8 +49,13 @@ def is_supported(module: nn.Module) -> bool:
     """torchvision-style DenseNet: features.{conv0,norm0,pool0,denseblockN.denselayerM.{norm1,conv1,norm2,conv2},transitionN,norm5}
     + classifier."""
     f = getattr(module, "features", None)
-    return (f is not None and all(hasattr(f, n) for n in ("conv0", "norm0", "pool0", "denseblock1", "norm5"))
-            and isinstance(getattr(module, "classifier", None), nn.Linear))
+    if f is None or not all(hasattr(f, n) for n in ("conv0", "norm0", "pool0", "denseblock1", "norm5")):
+        return False
+    if any(hasattr(f, n) for n in ("conv1", "norm1", "conv2", "norm2")):
+        return False          # a deep-stem DenseNet (timm `stem_type='deep'`: conv0-norm0-conv1-norm1-conv2): not this executor's graph
+    if not (isinstance(f.conv0, nn.Conv2d) and isinstance(f.norm0, nn.BatchNorm2d) and isinstance(f.pool0, nn.MaxPool2d)):
+        return False
+    return isinstance(getattr(module, "classifier", None), nn.Linear)
 
 
 class FrozenDenseNet:

@@ -389,7 +389,19 @@ class TrainStep:
 
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, *, mode: str = "ce", teacher: Optional[nn.Module] = None,
                  alpha: float = 0.7, temperature: float = 3.0, distillation_type: str = "soft", label_smoothing: float = 0.0,
-                 reducer=None, use_graph: bool = False, teacher_dtype=torch.bfloat16, teacher_fast: bool = True):
+                 reducer=None, use_graph: bool = False, teacher_dtype=torch.float32, teacher_fast: bool = True,
+                 input_format: str = "nchw", tile_dtype=torch.uint16, tile_mean=None, tile_std=None):
+        """teacher_dtype: torch.float32 (default) calls the frozen teacher exactly as the reference does
+        (lightning_modules.py:943-947, fp32 eval forward).  torch.bfloat16 / float16 is the OPT-IN fast path: the images are
+        cast to that type, channels_last, and a torchvision-style DenseNet runs through teacher.FrozenDenseNet with
+        BatchNorm-folded 16-bit weights; its logits differ from the fp32 teacher's by the 16-bit rounding (about 1e-2
+        relative, bounded in tests/test_model_gpu.py::test_frozen_densenet_teacher_fast_path_matches_module).
+        input_format: 'nchw' -- batches are float [B, chans, H, W] as the reference's DataLoader emits them;
+        'gray' -- batches are the single-channel tiles BEFORE the loader's `x.repeat(3,1,1)` + T.Normalize
+        (vit_transforms.py:381-393), [B,H,W] / [B,1,H,W] of `tile_dtype` (raw uint16 as stored in the CARS TIFFs, /65535 on
+        the device -- dataset.py:549 --, or fp16 / fp32 in [0,1]); the channel replication and the optional
+        Normalize(tile_mean, tile_std) are fused into the kernel that writes the patch matrix, so a step uploads
+        2 bytes per pixel instead of 12."""
         self.model, self.opt, self.B, self.mode = model, optimizer, batch_size, mode
         self.teacher, self.alpha, self.T = teacher, alpha, temperature
         self.distillation_type, self.ls = distillation_type, label_smoothing
@@ -399,7 +411,16 @@ class TrainStep:
         d = self.eng.d
         dev = self.eng.device
         # two input slots: the pinned-host -> HBM copy of step i+1 runs on its own stream (copy engine) while step i computes
-        self._images = [torch.zeros(batch_size, d.chans, d.img, d.img, dtype=torch.float32, device=dev) for _ in range(2)]
+        if input_format not in ("nchw", "gray"):
+            raise ValueError("input_format must be 'nchw' or 'gray'")
+        self.input_format = input_format
+        self._gray = None
+        if input_format == "gray":
+            from .engine import GraySpec
+            self._gray = GraySpec(mean=None if tile_mean is None else tuple(tile_mean), std=None if tile_std is None else tuple(tile_std))
+            self._images = [torch.zeros(batch_size, d.img, d.img, dtype=tile_dtype, device=dev) for _ in range(2)]
+        else:
+            self._images = [torch.zeros(batch_size, d.chans, d.img, d.img, dtype=torch.float32, device=dev) for _ in range(2)]
         self._labels = [torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(2)]
         self.slot = 0
         self.stats = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -443,11 +464,14 @@ class TrainStep:
             side.wait_stream(cur)
             with torch.cuda.stream(side), torch.no_grad():
                 x = self.images
+                if self._gray is not None:       # the teacher module wants the loader's [B,C,H,W] batch: built on the side stream
+                    g = ops.resize_u16(x, eng.d.img, eng.d.img) if x.dtype == torch.uint16 else x.float()
+                    x = ops.finish_tiles(g, eng.d.chans, mean=self._gray.mean, std=self._gray.std)
                 if self.teacher_dtype is not None and self.teacher_dtype != torch.float32:
                     x = x.to(self.teacher_dtype).contiguous(memory_format=torch.channels_last)
                 teacher_logits = self._teacher_fn(x).float().contiguous()
         eng.zero_grad()
-        l0, l1 = eng.forward(self.images, train=True)
+        l0, l1 = eng.forward(self.images, train=True, gray=self._gray)
         eng.generation += 1
         if self.mode == "distill":
             torch.cuda.current_stream().wait_stream(self._teacher_stream)
@@ -477,6 +501,8 @@ class TrainStep:
         self.slot ^= 1
         s = self.slot
         cur = torch.cuda.current_stream()
+        if self._gray is not None and images.dim() == 4 and images.shape[1] == 1:
+            images = images[:, 0]
         if images.is_cuda:
             self._images[s].copy_(images, non_blocking=True)
             self._labels[s].copy_(labels, non_blocking=True)

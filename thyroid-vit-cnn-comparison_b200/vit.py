@@ -207,7 +207,11 @@ class _EncoderFn(torch.autograd.Function):
         dl0 = grads[0].contiguous().float()
         dl1 = grads[1].contiguous().float() if ctx.two else None
         eng.backward(ctx.B, dl0, dl1)
-        eng.amp_update()     # an external optimizer will read param.grad: overflow check + loss-scale bookkeeping
+        if eng.fused_optimizer is None or eng.fused_optimizer() is None:
+            # an EXTERNAL torch optimizer will read param.grad: overflow check (zeroes the gradients of an overflowed step)
+            # + loss-scale bookkeeping happen here.  With a FusedAdamW attached, its own norm pass is the overflow detector
+            # and its tick kernel the only owner of the loss-scale state (one bookkeeping update per optimizer step).
+            eng.amp_update()
         return None, None, None
 
 
