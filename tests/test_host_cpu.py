@@ -313,15 +313,16 @@ def test_frozen_densenet_rewrites_match_torchvision_eval_forward():
 
 
 def test_bench_traffic_table_points_at_committed_ncu_captures():
-    """bench.py's roofline.traffic comes from profiles/r01_ncu_traffic_<model>.json: every kernel label it maps must exist in
-    the committed capture, with a positive per-launch DRAM byte count."""
+    """bench.py's roofline.traffic comes from the newest profiles/rNN_ncu_traffic_<model>.json: every kernel label it maps must
+    exist in the committed capture, with a positive per-launch DRAM byte count."""
     import importlib.util
     import json
     spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     for model, table in bench.NCU_CASES.items():
-        f = ROOT / "profiles" / f"r01_ncu_traffic_{model}.json"
+        f = bench.ncu_traffic_file(model)
+        assert f is not None and f.parent == ROOT / "profiles"
         rec = json.loads(f.read_text())
         for label, case in table.items():
             assert case in rec, (model, label, case)

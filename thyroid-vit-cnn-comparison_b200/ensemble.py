@@ -102,7 +102,7 @@ class EnsembleInference:
             shape = [int(v) for v in t.tolist()]
         self._num_classes, self._grid = shape
 
-    def _member_forward(self, model: nn.Module, images: torch.Tensor, want_maps: bool):
+    def _member_forward(self, model: nn.Module, images: torch.Tensor, want_maps: bool, gray=None):
         net = _inner(model)
         eng = net._ensure_engine()
         net._sync_shadow()
@@ -114,13 +114,15 @@ class EnsembleInference:
             if maps is None:                       # one [L,B,H,T,T] buffer, reused by every member of that shape
                 maps = torch.empty(d.depth, images.shape[0], d.heads, d.tokens, d.tokens, dtype=torch.float32, device=images.device)
                 self._maps[key] = maps
-        l0, l1 = eng.forward(images, train=False, attn_probs=maps)
+        l0, l1 = eng.forward(images, train=False, attn_probs=maps, gray=gray)
         if l1 is not None:                         # DeiT eval: mean of the cls and dist heads (deit_models.py:233-238)
             l0 = (l0 + l1) / 2
         return l0, maps, eng.d.n_prefix
 
     @torch.no_grad()
-    def __call__(self, images: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def __call__(self, images: torch.Tensor, gray=None) -> Dict[str, torch.Tensor]:
+        """gray (engine.GraySpec, optional): `images` are single-channel tiles [B,H,W] (raw uint16 / fp16 / fp32) that every
+        member replicates + normalises on the device while writing its patch matrix (see VitEngine.forward)."""
         if not images.is_cuda:
             raise RuntimeError("EnsembleInference runs on a CUDA device through libvitk.so (no CPU fallback)")
         dev = images.device
@@ -128,7 +130,7 @@ class EnsembleInference:
             self._weights = self._weights_host.to(dev)
         logits, grids = [], []
         for m in self.models:
-            lg, maps, n_prefix = self._member_forward(m, images, self.rollout)
+            lg, maps, n_prefix = self._member_forward(m, images, self.rollout, gray)
             logits.append(lg.float())
             if self.rollout:
                 grids.append(cls_attention_grid(ops.attention_rollout(maps, self.head_fusion), n_prefix))

@@ -68,7 +68,13 @@ class DropPath(nn.Module):
         # (VitEngine.set_drop_path); called stand-alone on a tensor only the identity cases are served
         if self.drop_prob == 0.0 or not self.training:
             return x
-        raise NotImplementedError("DropPath with drop_prob > 0 in training mode is not implemented in the sm_100a path yet")
+        # stand-alone call (outside a model): the per-sample factors floor(keep + u) / keep come from the same kernel the
+        # engine uses (vitk_droppath_scale); only the broadcast multiply -- differentiable, off the hot path -- is torch's
+        _require_cuda(x, "DropPath")
+        u = torch.rand(1, x.shape[0], dtype=torch.float32, device=x.device)
+        prob = torch.tensor([float(self.drop_prob)], dtype=torch.float32, device=x.device)
+        scale = ops.droppath_scale(u, prob, 1)[0]
+        return x * scale.view((x.shape[0],) + (1,) * (x.ndim - 1)).to(x.dtype)
 
 
 class PatchEmbed(nn.Module):
@@ -98,7 +104,10 @@ class PatchEmbed(nn.Module):
                                                nn.Conv2d(32, 1, kernel_size=1), nn.Sigmoid())
 
     def forward(self, x: torch.Tensor):
-        """Standalone (inference-only) patch projection -> ([B, num_patches, D] fp32, None)."""
+        """Standalone (inference-only) patch projection -> ([B, num_patches, D] fp32, quality scores [B, num_patches] | None).
+        The quality branch (vision_transformer_base.py:126-132) is dead code inside the model's forward -- its scores never
+        reach the tokens -- so the engine skips it; a stand-alone call evaluates it with torch's convolutions (two tiny
+        convs + pooling, not on the training path) so callers of the reference's PatchEmbed API get the same tuple."""
         B, C, H, W = x.shape
         if self.strict_img_size:
             assert H == self.img_size and W == self.img_size, \
@@ -111,7 +120,11 @@ class PatchEmbed(nn.Module):
         out = torch.empty(patches.shape[0], self.embed_dim, dtype=torch.float32, device=x.device)
         ops.gemm(patches, w16, patches.shape[0], self.embed_dim, patches.shape[1], out=out,
                  bias=lin.bias.detach() if lin.bias is not None else None)
-        return out.view(B, -1, self.embed_dim), None
+        quality = None
+        if self.quality_aware and hasattr(self, "quality_score"):
+            with torch.no_grad():
+                quality = torch.nn.functional.avg_pool2d(self.quality_score(x.float()), self.patch_size).flatten(1)
+        return out.view(B, -1, self.embed_dim), quality
 
 
 class Attention(nn.Module):
@@ -657,40 +670,22 @@ class DeiT(VisionTransformer):
     def _pool_range(self):
         return None          # DeiT.forward reads x[:, 0] / x[:, 1] whatever pool_type says (deit_models.py:220-238)
 
-    def load_pretrained_weights(self):
-        """deit_models.py:109-139 pulls ImageNet weights through timm + network; neither exists here."""
-        import warnings
-        warnings.warn("pretrained weights are not available offline; keeping random init "
-                      "(use load_state_dict with a timm/Lightning checkpoint instead)")
+    def load_pretrained_weights(self, source=None):
+        """deit_models.py:109-139.  The reference pulls ImageNet weights through timm + the network; here `source` (or
+        `pretrained_cfg['file']`) names a local checkpoint / state_dict, adapted by the same three rules (pretrained.py)."""
+        from . import pretrained
+        return pretrained.load_into(self, source)
 
     def _adapt_pretrained_weights(self, state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """deit_models.py:141-164: skip mismatching heads, interpolate pos_embed, average RGB patch filters to gray."""
-        adapted = {}
-        for key, value in state_dict.items():
-            if "head" in key and value.shape[0] != self.num_classes:
-                continue
-            if "pos_embed" in key and value.shape != self.pos_embed.shape:
-                value = self._interpolate_pos_embed(value)
-            if "patch_embed.proj.weight" in key and self.in_chans != 3:
-                if value.shape[1] == 3 and self.in_chans == 1:
-                    value = value.mean(dim=1, keepdim=True)
-            adapted[key] = value
-        return adapted
+        """deit_models.py:141-164."""
+        from . import pretrained
+        return pretrained.adapt_state_dict(self, state_dict)
 
     def _interpolate_pos_embed(self, pos_embed: torch.Tensor) -> torch.Tensor:
-        """deit_models.py:166-188 (host-side, checkpoint-load time only)."""
-        import torch.nn.functional as F
-        npatch = self.patch_embed.num_patches
-        ntok = self.num_tokens if self.distilled else 1
-        N = pos_embed.shape[1] - ntok
-        if npatch == N:
-            return pos_embed
-        class_pos, patch_pos = pos_embed[:, :ntok], pos_embed[:, ntok:]
-        gs_old, gs_new = int(math.sqrt(N)), int(math.sqrt(npatch))
-        patch_pos = patch_pos.reshape(1, gs_old, gs_old, -1).permute(0, 3, 1, 2)
-        patch_pos = F.interpolate(patch_pos, size=(gs_new, gs_new), mode="bicubic", align_corners=False)
-        patch_pos = patch_pos.permute(0, 2, 3, 1).reshape(1, -1, self.embed_dim)
-        return torch.cat((class_pos, patch_pos), dim=1)
+        """deit_models.py:166-188.  (The reference reads `self.num_tokens`, which only a distilled model defines; a
+        non-distilled model keeps its single class-token row here instead of raising AttributeError.)"""
+        from . import pretrained
+        return pretrained.resize_position_table(pos_embed, self._n_prefix(), self.patch_embed.num_patches)
 
     def get_attention_maps(self):
         """The reference's DeiT override forgets to fill the storage and returns None (SURVEY.md section 3.5);
