@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 16
+#define VITK_ABI_VERSION 17
 
 typedef enum {
   VITK_OK = 0,
@@ -365,6 +365,11 @@ int vitk_ensemble_probs(const float* logits /*[F,B,C]*/, const float* weights /*
 /* probs fp32 [L,B,H,N,N] -> rollout fp32 [B,N,N]; fusion 0 mean, 1 max, 2 min */
 int vitk_attention_rollout(const float* probs, float* rollout, float* scratch, int32_t L,
                            int32_t B, int32_t H, int32_t N, int32_t fusion, void* stream);
+/* Row `row` of the same rollout matrix (row 0 = the class token's map, the only row config 5 / the visualisation code
+ * uses, attention_utils.py:49-62): L vector-matrix products per image, the maps are read once, no [B,N,N] scratch.
+ * probs fp32 [L,B,H,N,N] -> out fp32 [B,N]. */
+int vitk_attention_rollout_row(const float* probs, float* out, int32_t L, int32_t B, int32_t H, int32_t N,
+                               int32_t row, int32_t fusion, void* stream);
 
 #ifdef __cplusplus
 }

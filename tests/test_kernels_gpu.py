@@ -512,6 +512,9 @@ def test_ensemble_and_rollout():
             R = a @ R
         torch.cuda.synchronize()
         assert (r - R).abs().max().item() < 1e-5
+        for row in (0, 7):      # one row by vector-matrix products (the class-token map of config 5): same numbers
+            rr = ops.attention_rollout_row(p, row, fusion)
+            assert rr.shape == (B, N) and (rr - R[:, row]).abs().max().item() < 1e-5
 
 
 # ------------------------------------------------------------------ nn.Dropout (drop_rate > 0): counter-based masks

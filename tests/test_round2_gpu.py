@@ -56,9 +56,10 @@ def test_tiles_to_patches_equals_finish_tiles_plus_patchify(kind, norm):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_train_step_from_gray_tiles_is_bit_identical_to_the_replicated_batch(use_graph):
+def test_train_step_from_gray_tiles_equals_the_replicated_batch(use_graph):
     """TrainStep(input_format='gray') on raw uint16 tiles == TrainStep on the loader's fp32 [B,3,H,W] batch (tile/65535
-    replicated to 3 channels): same loss, same gradients, same updated parameters, bit for bit."""
+    replicated to 3 channels): bit-identical step statistics (the forward is deterministic); gradients / parameters equal up to
+    the summation order of the split-K / atomic weight-gradient accumulation (1e-5 relative)."""
     cfg = O.VitConfig(img_size=64, embed_dim=128, depth=2, num_heads=2)
     g = torch.Generator().manual_seed(9)
     tiles = torch.randint(0, 65536, (8, 64, 64), generator=g, dtype=torch.int32).to(torch.uint16)
@@ -76,7 +77,8 @@ def test_train_step_from_gray_tiles_is_bit_identical_to_the_replicated_batch(use
         eng = model._engine
         results.append((stats.clone(), eng.flat.grads.clone(), eng.flat.params.clone()))
     (s0, g0, p0), (s1, g1, p1) = results
-    assert torch.equal(s0, s1) and torch.equal(g0, g1) and torch.equal(p0, p1)
+    assert torch.equal(s0, s1)
+    assert rel_l2(g0, g1) < 1e-5 and (p0 - p1).abs().max().item() < 1e-6
     assert torch.isfinite(s0).all() and g0.abs().sum().item() > 0
 
 

@@ -410,6 +410,61 @@ __global__ void rollout_matmul_kernel(const float* __restrict__ a, const float* 
   for (int k = 0; k < N; ++k) acc += ar[k] * r[(long long)k * N + j];
   rout[((long long)b * N + i) * N + j] = acc;
 }
+// One ROW of the rollout without ever forming an N x N product: R = A_L ... A_1, so row r of R is
+//   v_L = e_r^T A_L,  v_{l} = v_{l+1} A_l   (l = L-1 .. 1),   A_l[i,:] = 0.5 (fuse_h P_l[i,:] + e_i) / rowsum_i
+// i.e. L vector-matrix products per image: the attention maps (the only large operand, L*H*N*N floats per image) are
+// read exactly once, 198x fewer flops than the matrix chain.  One CTA per image; warp w owns rows i = w, w+W, ...; lanes
+// stride over the columns (coalesced 128-byte row segments); per-warp partial accumulators live in shared memory.
+constexpr int ROLL_WARPS = 16;
+__global__ void __launch_bounds__(ROLL_WARPS * 32)
+    rollout_row_kernel(const float* __restrict__ probs, float* __restrict__ out, int L, int B, int H, int N, int row, int fusion) {
+  extern __shared__ float roll_smem[];
+  float* v = roll_smem;                 // [N] current row vector
+  float* part = roll_smem + N;          // [ROLL_WARPS][N] per-warp partial sums of the next vector
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) v[j] = j == row ? 1.f : 0.f;
+  __syncthreads();
+  for (int l = L - 1; l >= 0; --l) {
+    float* mine = part + warp * N;
+    for (int j = lane; j < N; j += 32) mine[j] = 0.f;
+    const float* base = probs + (((long long)l * B + b) * H) * (long long)N * N;
+    for (int i = warp; i < N; i += ROLL_WARPS) {
+      const float vi = v[i];
+      if (vi == 0.f) continue;          // warp-uniform: the first product only touches row `row`
+      float sum = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        float f = fusion == 0 ? 0.f : (fusion == 1 ? -INFINITY : INFINITY);
+        for (int h = 0; h < H; ++h) {
+          const float p = __ldg(base + ((long long)h * N + i) * N + j);
+          f = fusion == 0 ? f + p : (fusion == 1 ? fmaxf(f, p) : fminf(f, p));
+        }
+        if (fusion == 0) f /= float(H);
+        sum += 0.5f * (f + (i == j ? 1.f : 0.f));
+      }
+      sum = warp_sum(sum);
+      const float w = vi / sum;
+      for (int j = lane; j < N; j += 32) {     // second visit of the same row: served by L1/L2
+        float f = fusion == 0 ? 0.f : (fusion == 1 ? -INFINITY : INFINITY);
+        for (int h = 0; h < H; ++h) {
+          const float p = __ldg(base + ((long long)h * N + i) * N + j);
+          f = fusion == 0 ? f + p : (fusion == 1 ? fmaxf(f, p) : fminf(f, p));
+        }
+        if (fusion == 0) f /= float(H);
+        mine[j] += w * 0.5f * (f + (i == j ? 1.f : 0.f));
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROLL_WARPS; ++w) acc += part[w * N + j];
+      v[j] = acc;
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) out[(long long)b * N + j] = v[j];
+}
 __global__ void rollout_eye_kernel(float* __restrict__ r, int B, int N) {
   const long long total = (long long)B * N * N;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -605,5 +660,21 @@ extern "C" int vitk_attention_rollout(const float* probs, float* rollout, float*
     VITK_LAUNCH_CHECK();
     float* tmp = cur; cur = nxt; nxt = tmp;
   }
+  return VITK_OK;
+}
+
+extern "C" int vitk_attention_rollout_row(const float* probs, float* out, int32_t L, int32_t B, int32_t H, int32_t N,
+                                          int32_t row, int32_t fusion, void* stream) {
+  VITK_CHECK_ARG(probs && out && L > 0 && B > 0 && H > 0 && N > 0 && row >= 0 && row < N && fusion >= 0 && fusion <= 2,
+                 "vitk_attention_rollout_row: bad args");
+  const size_t smem = (size_t)(ROLL_WARPS + 1) * N * sizeof(float);
+  VITK_CHECK_ARG(smem <= 200 * 1024, "vitk_attention_rollout_row: sequence too long (N=%d)", N);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && configured < smem) {
+    VITK_CUDA(cudaFuncSetAttribute(rollout_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  rollout_row_kernel<<<B, ROLL_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(probs, out, L, B, H, N, row, fusion);
+  VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -133,7 +133,9 @@ class EnsembleInference:
             lg, maps, n_prefix = self._member_forward(m, images, self.rollout, gray)
             logits.append(lg.float())
             if self.rollout:
-                grids.append(cls_attention_grid(ops.attention_rollout(maps, self.head_fusion), n_prefix))
+                row = ops.attention_rollout_row(maps, 0, self.head_fusion)          # class-token row of the rollout, [B,N]
+                g = int(math.isqrt(row.shape[1] - n_prefix))
+                grids.append(row[:, n_prefix:].reshape(-1, g, g))
         B = images.shape[0]
         if logits:
             local = torch.stack(logits, dim=0)

@@ -328,6 +328,17 @@ def attention_rollout(probs, fusion: str = "mean"):
     return out
 
 
+def attention_rollout_row(probs, row: int = 0, fusion: str = "mean"):
+    """Row `row` of attention_rollout(probs, fusion) as fp32 [B,N], by L vector-matrix products (maps read once)."""
+    _req(probs, f32, "rollout probs")
+    L, B, H, N, _ = probs.shape
+    fus = {"mean": 0, "max": 1, "min": 2}[fusion]
+    out = torch.empty(B, N, dtype=f32, device=probs.device)
+    check(_lib.load().vitk_attention_rollout_row(probs.data_ptr(), out.data_ptr(), L, B, H, N, int(row), fus, _stream()),
+          "attention_rollout_row")
+    return out
+
+
 # --------------------------------------------------------------------------- on-device metrics
 def metrics_update(logits, labels, confusion, scores=None, score_labels=None, count=None):
     """confusion (int64 [C*C+1]) += this batch; optionally appends softmax(logits)[:, 1] / labels at *count (binary AUROC)."""
