@@ -573,7 +573,7 @@ def measure_train(args, model_name, steps, rank, world, local, dev, primary):
     if reducer is not None:
         log = list(reducer.launched_log)
         dp = {"buckets": len(reducer.buckets), "bucket_bytes": [4 * (e - s) for s, e in reducer.buckets],
-              "payload": "fp32", "launched_before_backward_ended": sum(1 for stage, _ in log if stage != "embed"),
+              "payload": "fp32", "nccl_max_ctas": args.nccl_max_ctas or None, "launched_before_backward_ended": sum(1 for stage, _ in log if stage != "embed"),
               "launch_stages": [stage for stage, _ in log]}
 
     with ClockSampler(local) as clk:
@@ -748,6 +748,8 @@ def run_ours(args):
     import thyroid_vit_cnn_comparison_b200  # noqa: F401
     from thyroid_vit_cnn_comparison_b200 import parallel
 
+    if args.nccl_max_ctas > 0:
+        os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
     rank, world, local = parallel.init_distributed()
     dev = torch.device("cuda", local)
     primary = args.model or "deit_tiny"
@@ -791,6 +793,9 @@ def main():
                     help="gray: single-channel uint16 tiles, replicated on device; nchw: fp32 [B,3,H,W] batches")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--min-buckets", type=int, default=6)
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="N > 1: cap the CTAs NCCL may use per collective (NCCL_MAX_CTAS) so that the overlapped all-reduces leave "
+                         "the SMs to the persistent GEMM / attention kernels; 0 = NCCL's default")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--dp-graph", action="store_true", help="(default) N > 1: the step, NCCL all-reduces included, is one CUDA graph")
     ap.add_argument("--dp-eager", action="store_true", help="N > 1: launch the step eagerly instead of replaying a captured graph")

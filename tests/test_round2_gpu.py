@@ -71,14 +71,17 @@ def test_train_step_from_gray_tiles_equals_the_replicated_batch(use_graph):
         model.train()
         opt = OPT.FusedAdamW(model, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
         step = TR.TrainStep(model, opt, 8, mode="ce", use_graph=use_graph, input_format=fmt)
-        for _ in range(2):
-            stats = step((tiles if fmt == "gray" else x).pin_memory(), y.pin_memory()).cpu()
+        first = step((tiles if fmt == "gray" else x).pin_memory(), y.pin_memory()).cpu().clone()
+        stats = step((tiles if fmt == "gray" else x).pin_memory(), y.pin_memory()).cpu()
         torch.cuda.synchronize()
         eng = model._engine
-        results.append((stats.clone(), eng.flat.grads.clone(), eng.flat.params.clone()))
-    (s0, g0, p0), (s1, g1, p1) = results
-    assert torch.equal(s0, s1)
-    assert rel_l2(g0, g1) < 1e-5 and (p0 - p1).abs().max().item() < 1e-6
+        results.append((first, stats.clone(), eng.flat.grads.clone(), eng.flat.params.clone()))
+    (f0, s0, g0, p0), (f1, s1, g1, p1) = results
+    assert torch.equal(f0, f1)                                   # the forward is deterministic: same patch matrix, same loss
+    # step 2 starts from parameters equal up to the summation order of step 1's atomically accumulated gradients; a last-bit
+    # difference in a master weight can flip the rounding of its fp16 shadow, so step 2 agrees to ~1e-3 of the gradient norm
+    assert (s0 - s1).abs().max().item() < 1e-4
+    assert rel_l2(g0, g1) < 2e-3 and (p0 - p1).abs().max().item() < 1e-5
     assert torch.isfinite(s0).all() and g0.abs().sum().item() > 0
 
 
@@ -208,8 +211,9 @@ def test_fused_adamw_state_dict_roundtrip_and_torch_adamw_interop():
     sa(x.cuda(), y.cuda())
     sb(x.cuda(), y.cuda())
     torch.cuda.synchronize()
-    assert torch.equal(ma._engine.flat.params, mb._engine.flat.params)                      # resumed run == uninterrupted run
-    assert torch.equal(oa.exp_avg, ob.exp_avg) and oa.dev_state[0].item() == 4.0 == ob.dev_state[0].item()
+    # resumed run == uninterrupted run, up to the summation order of the atomically accumulated weight gradients
+    assert (ma._engine.flat.params - mb._engine.flat.params).abs().max().item() < 1e-6
+    assert rel_l2(oa.exp_avg, ob.exp_avg) < 1e-5 and oa.dev_state[0].item() == 4.0 == ob.dev_state[0].item()
     # a checkpoint written by torch.optim.AdamW (what the reference's Lightning run saves) resumes here
     mc, oc, _ = make()
     ref_opt = torch.optim.AdamW([p for p in mc.parameters()], lr=1e-3, weight_decay=0.05)

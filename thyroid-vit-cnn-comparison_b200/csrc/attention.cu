@@ -589,6 +589,7 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 constexpr int TC_MAX_TOKENS = 256;      // forward
 constexpr int TC_MAX_TOKENS_BWD = 240;  // backward (shared-memory budget of the pipelined kernel)
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
+int attention_probs_tc(const void* qkv, const float* lse, float* probs, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
                      int H, float scale, bool fp16, cudaStream_t st);
 }  // namespace vitk
@@ -608,6 +609,7 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* pro
     VITK_LAUNCH_CHECK();
   }
   if (probs != nullptr) {
+    if (N <= TC_MAX_TOKENS) return attention_probs_tc(qkv, lse, probs, B, N, H, scale, H16, st);   // tensor-core S + the forward's lse
     const long long rows = (long long)B * H * N;
     attn_probs_kernel<H16><<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), probs, B, N, H, scale);
     VITK_LAUNCH_CHECK();

@@ -275,6 +275,122 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   if (warp == 4) tmem_dealloc<256>(tb);
 }
 
+// ================================================================================================ eval-mode attention maps
+// probs[b,h,q,:] = softmax(q k^T * scale) in fp32 -- the `attention_maps` the reference keeps in eval mode
+// (vision_transformer_base.py:186-188).  The forward above already left lse[b,h,q] = log sum_j exp(s_qj * scale), so
+// the map is exp2(s * c - lse * log2e): one S = Q K^T on the tensor core (bit-identical to the forward's S), one pass over
+// the TMEM row per thread, no max / sum / P / V.  HBM-bound on the B*H*N*N*4 bytes it writes (120 MB per DeiT-tiny layer at
+// batch 256): each thread streams its row as 16-byte stores, two consecutive store instructions completing every 32-byte
+// sector.  CTA per (128-query tile, head, image), 2 CTAs / SM like the forward.
+template <bool H16>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+    attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                         const float* __restrict__ lse, float* __restrict__ probs, int N, int H, int KP, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                       // [128][64] 16-bit
+  uint8_t* sK = sQ + 128 * 128;             // [KP][64]
+  float* sT = reinterpret_cast<float*>(sK + KP * 128);           // 4 x [32][33] fp32 transpose tiles (one per warp)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 4 * 32 * 33);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_s = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmKV);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_s, 1);
+      mbar_init_fence();
+      pdl_wait();
+      mbar_expect_tx(bar_qk, (128 + KP) * 128);
+      tma_load_3d(sQ, &tmQ, bar_qk, h * DH, q0, b);
+      tma_load_3d(sK, &tmKV, bar_qk, (H + h) * DH, 0, b);
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  pdl_trigger();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_wait(bar_qk, 0, 31);
+      tc_fence_after();
+      const uint32_t idesc_s = idesc_f16(KP, false, false, H16);
+      const uint64_t adesc = smem_desc_kmajor(smem_u32(sQ));
+      const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(tb, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+  } else {
+    const int row = warp * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t trow = tb + (uint32_t(warp * 32) << 16);
+    const bool warp_valid = q0 + warp * 32 < N;
+    const long long rowid = ((long long)b * H + h) * N + q;
+    const float nl2 = q < N ? -lse[rowid] * LOG2E : 0.f;
+    mbar_wait(bar_s, 0, 32);
+    tc_fence_after();
+    if (warp_valid) {
+      const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(nl2, nl2);
+      // A thread owns a row, but a row-per-lane store touches 32 different 128-byte lines per instruction (the LSU then
+      // needs ~32 cycles for it: measured 168 us per 120 MB layer).  Each warp therefore transposes its 32 x 32 block through
+      // a padded shared-memory tile and stores it row by row: one fully coalesced 128-byte segment per instruction.
+      float* tile = sT + warp * (32 * 33);
+      const int r0 = q0 + warp * 32;                       // first query row of this warp
+      float* pbase = probs + (((long long)b * H + h) * N + r0) * N;
+      uint32_t va[32], vb[32];
+      const int nch = (KP + 31) >> 5;
+      auto load_chunk = [&](int c, uint32_t (&v)[32]) {
+        if (KP - 32 * c >= 32) tmem_ld32_nowait(trow + uint32_t(32 * c), v);
+        else tmem_ld16_nowait(trow + uint32_t(32 * c), v);
+      };
+      auto emit_chunk = [&](int c, const uint32_t (&v)[32]) {
+        const int c0 = 32 * c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, nm2);
+          tile[lane * 33 + j] = ex2_approx(x.x);
+          tile[lane * 33 + j + 1] = ex2_approx(x.y);
+        }
+        __syncwarp();
+        const int col = c0 + lane;
+        if (col < N) {
+          const int nrows = min(32, N - r0);
+          for (int rr = 0; rr < nrows; ++rr) pbase[(long long)rr * N + col] = tile[rr * 33 + lane];
+        }
+        __syncwarp();
+      };
+      load_chunk(0, va);
+      for (int c = 0; c < nch; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nch) load_chunk(c + 1, vb);
+        emit_chunk(c, va);
+        if (c + 1 < nch) {
+          tmem_ld_wait();
+          if (c + 2 < nch) load_chunk(c + 2, va);
+          emit_chunk(c + 1, vb);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tb);
+}
+
 // ================================================================================================ backward
 constexpr int BWD_THREADS = 288;  // 8 math warps + 1 control warp
 // TMEM map (all 512 columns).  S^T / dP^T hold one 64-query chunk (fp32, lane = key); P^T / dS^T are their 16-bit
@@ -718,6 +834,31 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
 #ifdef VITK_GEMM_KNOBS
 extern "C" int vitk_debug_read_attn(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_attn_dbg, sizeof(g_attn_dbg)); }
 #endif
+
+// Eval-mode attention maps for N <= 256 (needs the lse the forward just wrote).
+template <bool H16>
+int attention_probs_tc_impl(const void* qkv, const float* lse, float* probs, int B, int N, int H, float scale, cudaStream_t st) {
+  const int KP = (N + 15) & ~15;
+  CUtensorMap tmQ, tmKV;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KP, H16)) != VITK_OK) return rc;
+  const int smem = 128 * 128 + KP * 128 + 4 * 32 * 33 * 4 + 64 + 1024;
+  auto kfn = attn_probs_tc_kernel<H16>;
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 + 256 * 128 + 4 * 32 * 33 * 4 + 64 + 1024));
+    configured = true;
+  }
+  dim3 grid((N + 127) / 128, H, B);
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, lse, probs, N, H, KP, scale * LOG2E));
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+int attention_probs_tc(const void* qkv, const float* lse, float* probs, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {
+  return fp16 ? attention_probs_tc_impl<true>(qkv, lse, probs, B, N, H, scale, st)
+              : attention_probs_tc_impl<false>(qkv, lse, probs, B, N, H, scale, st);
+}
 
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {
   return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, st)

@@ -416,6 +416,7 @@ __global__ void rollout_matmul_kernel(const float* __restrict__ a, const float* 
 // read exactly once, 198x fewer flops than the matrix chain.  One CTA per image; warp w owns rows i = w, w+W, ...; lanes
 // stride over the columns (coalesced 128-byte row segments); per-warp partial accumulators live in shared memory.
 constexpr int ROLL_WARPS = 16;
+template <int NJ>   // NJ = ceil(N / 32) for N <= 256 (row segments held in registers), 0 = any N (two passes over the row)
 __global__ void __launch_bounds__(ROLL_WARPS * 32)
     rollout_row_kernel(const float* __restrict__ probs, float* __restrict__ out, int L, int B, int H, int N, int row, int fusion) {
   extern __shared__ float roll_smem[];
@@ -432,6 +433,38 @@ __global__ void __launch_bounds__(ROLL_WARPS * 32)
     for (int i = warp; i < N; i += ROLL_WARPS) {
       const float vi = v[i];
       if (vi == 0.f) continue;          // warp-uniform: the first product only touches row `row`
+      if (NJ > 0) {
+        // row i of every head in registers (NJ * 32 >= N columns per lane-stripe): all H * NJ loads of the row are in flight
+        // together, the fused row and its sum are formed once
+        float f[NJ > 0 ? NJ : 1];
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) f[jj] = fusion == 0 ? 0.f : (fusion == 1 ? -INFINITY : INFINITY);
+        for (int h = 0; h < H; ++h) {
+          const float* prow = base + ((long long)h * N + i) * N;
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) {
+            const int j = lane + 32 * jj;
+            const float p = j < N ? __ldg(prow + j) : 0.f;
+            f[jj] = fusion == 0 ? f[jj] + p : (fusion == 1 ? fmaxf(f[jj], p) : fminf(f[jj], p));
+          }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          const int j = lane + 32 * jj;
+          if (fusion == 0) f[jj] /= float(H);
+          f[jj] = j < N ? 0.5f * (f[jj] + (i == j ? 1.f : 0.f)) : 0.f;
+          sum += f[jj];
+        }
+        sum = warp_sum(sum);
+        const float w = vi / sum;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          const int j = lane + 32 * jj;
+          if (j < N) mine[j] += w * f[jj];
+        }
+        continue;
+      }
       float sum = 0.f;
       for (int j = lane; j < N; j += 32) {
         float f = fusion == 0 ? 0.f : (fusion == 1 ? -INFINITY : INFINITY);
@@ -669,12 +702,20 @@ extern "C" int vitk_attention_rollout_row(const float* probs, float* out, int32_
                  "vitk_attention_rollout_row: bad args");
   const size_t smem = (size_t)(ROLL_WARPS + 1) * N * sizeof(float);
   VITK_CHECK_ARG(smem <= 200 * 1024, "vitk_attention_rollout_row: sequence too long (N=%d)", N);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
-    VITK_CUDA(cudaFuncSetAttribute(rollout_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nj = (N + 31) / 32;
+  if (nj <= 7) {
+    rollout_row_kernel<7><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, L, B, H, N, row, fusion);
+  } else if (nj == 8) {
+    rollout_row_kernel<8><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, L, B, H, N, row, fusion);
+  } else {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && configured < smem) {
+      VITK_CUDA(cudaFuncSetAttribute(rollout_row_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = 200 * 1024;
+    }
+    rollout_row_kernel<0><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, L, B, H, N, row, fusion);
   }
-  rollout_row_kernel<<<B, ROLL_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(probs, out, L, B, H, N, row, fusion);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
