@@ -792,7 +792,10 @@ def main():
     ap.add_argument("--input", default="gray", choices=["gray", "nchw"],
                     help="gray: single-channel uint16 tiles, replicated on device; nchw: fp32 [B,3,H,W] batches")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
-    ap.add_argument("--min-buckets", type=int, default=6)
+    ap.add_argument("--min-buckets", type=int, default=1,
+                    help="N > 1: lower bound on the number of all-reduce buckets (a model smaller than --bucket-mb otherwise reduces "
+                         "in ONE bucket after backward).  Measured on 8 B200 (profiles/r02_dp_scan_8gpu.txt): for DeiT-tiny's 22 MB "
+                         "of gradients 1 bucket is fastest -- overlapped NCCL kernels take SMs from the persistent GEMMs")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
                     help="N > 1: cap the CTAs NCCL may use per collective (NCCL_MAX_CTAS) so that the overlapped all-reduces leave "
                          "the SMs to the persistent GEMM / attention kernels; 0 = NCCL's default")

@@ -64,10 +64,13 @@ def completed_prefix(order: List[str], offsets: dict, pad: int, stage: str, dept
 class BucketedAllReduce:
     """Gradient reducer attached to a VitEngine (see module docstring)."""
 
-    def __init__(self, process_group=None, bucket_mb: float = 25.0, min_buckets: int = 6):
-        """bucket_mb caps a bucket; min_buckets shrinks it for small models (DeiT-tiny's whole gradient is 22 MB: one
-        25 MB bucket would only leave after backward has ended, i.e. nothing would overlap) -- the bucket size is
-        min(bucket_mb, total / min_buckets), cut at tensor boundaries."""
+    def __init__(self, process_group=None, bucket_mb: float = 25.0, min_buckets: int = 1):
+        """bucket_mb caps a bucket; min_buckets > 1 shrinks it for small models so that their all-reduce also overlaps backward
+        (bucket size = min(bucket_mb, total / min_buckets), cut at tensor boundaries).  The default keeps a model smaller
+        than one bucket in ONE all-reduce after backward: measured on 8 B200 with DeiT-tiny (22 MB of fp32 gradients) the
+        overlapped variants are 0.6-1.0 % SLOWER (6 buckets: 6.23 ms / step, 3: 6.21, 1: 6.17) -- a 22 MB NVLS all-reduce costs
+        ~0.1 ms, less than what its kernels take from the persistent GEMM / attention CTAs they run beside.  ViT-B/16 (343 MB)
+        splits into 14 buckets by bucket_mb alone and does overlap."""
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
