@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 17
+#define VITK_ABI_VERSION 18
 
 typedef enum {
   VITK_OK = 0,
@@ -247,6 +247,15 @@ int vitk_dense_bwd(const float* dy, const float* y, const float* x, const float*
  * torchvision's _DenseLayer / _Transition (three read+write passes) by one.  C, x_ld, y_ld multiples of 8; 16-byte aligned. */
 int vitk_affine_relu_nhwc(const void* x, int64_t x_ld, void* y, int64_t y_ld, const float* scale, const float* shift,
                           int64_t pixels, int32_t C, int32_t dtype, int32_t relu, void* stream);
+/* The 1x1 bottleneck convolution of a frozen dense layer with everything around it (torchvision densenet.py _DenseLayer:
+ * norm1 -> relu1 -> conv1 -> norm2 -> relu2, eval mode, norm2 folded into conv1):
+ *   out[p, 0:128] = relu( relu(x[p, 0:C] * scale + shift) @ w^T + bias )
+ * x: 16-bit NHWC concatenation buffer, pixel pitch x_ld elements; w: 16-bit [128, C] (row-major); scale / shift fp32 [C],
+ * bias fp32 [128]; out: 16-bit [pixels, 128].  tcgen05 GEMM whose A tile gets the affine + ReLU in shared memory between
+ * the TMA load and the MMA: the concatenation is read once per layer (vitk_affine_relu_nhwc + a library convolution read
+ * and wrote it three times). */
+int vitk_dense_bottleneck(const void* x, int64_t x_ld, const float* scale, const float* shift, const void* w,
+                          const float* bias, void* out, int64_t pixels, int32_t C, int32_t dtype, void* stream);
 /* MaxPool2d(kernel, stride, pad) (is_max = 1, -inf padding) / AvgPool2d(kernel, stride, pad) (is_max = 0, count_include_pad) of a
  * compact NHWC tensor x [B,H,W,C], ceil_mode False, written with pixel pitch y_ld into y [B,OH,OW,y_ld]: the DenseNet stem's
  * pool0 and the transitions' pool (torchvision densenet.py) store straight into the next dense block's buffer. */

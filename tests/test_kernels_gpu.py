@@ -946,3 +946,27 @@ def test_pool_nhwc(B, H, W, C, Ct, k, s, p, is_max, dt):
         assert (out[..., C:] == 5.0).all()
     with pytest.raises(RuntimeError):
         ops.pool_nhwc(x, out[:, :-1].contiguous(), k, s, p, is_max)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("P,Ct,C", [(1000, 256, 64), (128 * 3 + 5, 512, 96), (4096, 1664, 1632), (70, 64, 64), (20000, 224, 224)])
+def test_dense_bottleneck_matches_affine_relu_conv1x1(P, Ct, C, dt):
+    """vitk_dense_bottleneck = relu(relu(x[:, :C] * s + h) @ W^T + b): against vitk_affine_relu_nhwc (whose 16-bit output is
+    the bit-exact A operand) followed by an fp32 matmul; ragged pixel counts, C not a multiple of 64, pitch > C."""
+    g = torch.Generator().manual_seed(P + C)
+    x = (torch.randn(P, Ct, generator=g)).to(DEV).to(dt)
+    s = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    h = (torch.randn(C, generator=g) * 0.3).to(DEV)
+    w = (torch.randn(128, C, generator=g) / C ** 0.5).to(DEV).to(dt)
+    b = (torch.randn(128, generator=g) * 0.2).to(DEV)
+    out = ops.dense_bottleneck(x, C, s, h, w, b)
+    a = ops.affine_relu_nhwc(x.view(1, 1, P, Ct), C, s, h).view(P, C)
+    ref = torch.relu(a.float() @ w.float().t() + b)
+    torch.cuda.synchronize()
+    assert out.shape == (P, 128) and out.dtype == dt
+    err = (out.float() - ref).abs().max().item()
+    tol = (2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11) * max(1.0, ref.abs().max().item()) * 1.5
+    assert err <= tol, (err, tol)
+    assert torch.equal(ops.dense_bottleneck(x, C, s, h, w, b), out)          # deterministic
+    with pytest.raises(TypeError):
+        ops.dense_bottleneck(x, C, s, h, w[:, :-8].contiguous(), b)

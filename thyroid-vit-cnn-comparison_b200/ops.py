@@ -481,9 +481,9 @@ def dense_bwd(dy, y, x, W, dW, db, act: int = 0, need_dx: bool = True):
 
 
 # --------------------------------------------------------------------------- frozen-teacher fast path
-def affine_relu_nhwc(x, C: int, scale, shift, out=None, relu: bool = True):
-    """x: contiguous 16-bit NHWC tensor [..., C_total]; its first C channels go through y = max(0, x * scale + shift) into the first
-    C channels of `out` (contiguous [..., C_out_total >= C]; default: a new compact [..., C])."""
+def affine_relu_nhwc(x, C: int, scale, shift, out=None, relu: bool = True, out_channel_offset: int = 0):
+    """x: contiguous 16-bit NHWC tensor [..., C_total]; its first C channels go through y = max(0, x * scale + shift) into
+    channels [out_channel_offset, out_channel_offset + C) of `out` (contiguous [..., C_out_total]; default: a new compact [..., C])."""
     _req16(x, "affine_relu x")
     pixels = x.numel() // x.shape[-1]
     if out is None:
@@ -491,9 +491,30 @@ def affine_relu_nhwc(x, C: int, scale, shift, out=None, relu: bool = True):
     _req(out, x.dtype, "affine_relu out")
     if out.numel() // out.shape[-1] != pixels:
         raise RuntimeError("affine_relu_nhwc: out must have the pixel count of x")
+    off = int(out_channel_offset)
+    if off < 0 or off % 8 or off + C > out.shape[-1]:
+        raise ValueError("affine_relu_nhwc: out_channel_offset must be a multiple of 8 with offset + C <= channels of out")
     _req(scale, f32, "affine_relu scale"); _req(shift, f32, "affine_relu shift")
-    check(_lib.load().vitk_affine_relu_nhwc(x.data_ptr(), x.shape[-1], out.data_ptr(), out.shape[-1], scale.data_ptr(),
-                                            shift.data_ptr(), pixels, C, _DT[x.dtype], int(relu), _stream()), "affine_relu_nhwc")
+    check(_lib.load().vitk_affine_relu_nhwc(x.data_ptr(), x.shape[-1], out.data_ptr() + off * out.element_size(), out.shape[-1],
+                                            scale.data_ptr(), shift.data_ptr(), pixels, C, _DT[x.dtype], int(relu), _stream()),
+          "affine_relu_nhwc")
+    return out
+
+
+def dense_bottleneck(x, C: int, scale, shift, w, bias, out=None):
+    """x: 16-bit NHWC [..., Ct] (the first C channels are read), w: 16-bit [128, C], scale / shift fp32 [C], bias fp32 [128]
+    -> relu(relu(x[..., :C] * scale + shift) @ w^T + bias) as 16-bit [..., 128]."""
+    _req16(x, "bottleneck x")
+    ct = x.shape[-1]
+    pixels = x.numel() // ct
+    if w.dtype != x.dtype or not w.is_cuda or not w.is_contiguous() or tuple(w.shape) != (128, C):
+        raise TypeError("dense_bottleneck: w must be a contiguous CUDA [128, C] tensor of x's dtype")
+    _req(scale, f32, "bottleneck scale"); _req(shift, f32, "bottleneck shift"); _req(bias, f32, "bottleneck bias")
+    if scale.numel() != C or shift.numel() != C or bias.numel() != 128:
+        raise ValueError("dense_bottleneck: scale / shift need C entries, bias 128")
+    out = torch.empty(*x.shape[:-1], 128, dtype=x.dtype, device=x.device) if out is None else out
+    check(_lib.load().vitk_dense_bottleneck(x.data_ptr(), ct, scale.data_ptr(), shift.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                            out.data_ptr(), pixels, C, _DT[x.dtype], _stream()), "dense_bottleneck")
     return out
 
 

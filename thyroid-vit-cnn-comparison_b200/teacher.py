@@ -62,15 +62,20 @@ class FrozenDenseNet:
     """Callable replacement for `teacher(images)` of a frozen torchvision-style DenseNet (see module docstring)."""
 
     def __init__(self, module: nn.Module, dtype=torch.bfloat16, affine_relu: Optional[Callable] = None,
-                 pool: Optional[Callable] = None):
+                 pool: Optional[Callable] = None, bottleneck: Optional[Callable] = None):
         if not is_supported(module):
             raise TypeError("FrozenDenseNet expects a torchvision-style DenseNet (features.denseblockN.denselayerM, classifier)")
         self.dtype = dtype
         self._affine_relu = affine_relu if affine_relu is not None else ops.affine_relu_nhwc
         self._pool = pool if pool is not None else ops.pool_nhwc
+        # norm1 + relu1 + conv1 (1x1) + norm2 + relu2 of every dense layer as ONE tcgen05 GEMM over the block buffer
+        # (ops.dense_bottleneck); with an injected affine_relu (the CPU restatement used by the tests) the two-step form runs
+        self._bottleneck = bottleneck if bottleneck is not None else (ops.dense_bottleneck if affine_relu is None else None)
         f = module.features
         cl = lambda w: w.to(dtype).contiguous(memory_format=torch.channels_last)
         w0, b0 = _fold(f.conv0, f.norm0)
+        # (the 3-channel stem runs on a pre-tensor-core cuDNN kernel, 1.8 ms at batch 256; zero-padding it to 8 channels was
+        # measured: the library then picks a 2.8 ms tensor-core kernel -- left as it is)
         self.stem = (cl(w0), b0.to(dtype), f.conv0.stride, f.conv0.padding)
         self.stem_pool = self._pool_spec(f.pool0, True)
         self.blocks: List[dict] = []
@@ -83,7 +88,11 @@ class FrozenDenseNet:
                 s1, h1 = _bn_affine(layer.norm1)
                 w1, b1 = _fold(layer.conv1, layer.norm2)
                 layers.append({"s1": s1, "h1": h1, "w1": cl(w1), "b1": b1.to(dtype), "w2": cl(layer.conv2.weight.detach().float()),
-                               "growth": layer.conv2.out_channels, "pad2": layer.conv2.padding})
+                               "growth": layer.conv2.out_channels, "pad2": layer.conv2.padding,
+                               # GEMM form of conv1: [128, C] row-major weights, fp32 bias (None when conv1 is not 1x1 / 128 wide)
+                               "w1m": (w1.reshape(w1.shape[0], -1).to(dtype).contiguous()
+                                       if tuple(layer.conv1.kernel_size) == (1, 1) and w1.shape[0] == 128 else None),
+                               "b1f": b1.float().contiguous()})
             blk = {"layers": layers, "transition": None}
             tr = getattr(f, f"transition{i}", None)
             if tr is not None:
@@ -95,6 +104,7 @@ class FrozenDenseNet:
         self.wc = module.classifier.weight.detach().float().contiguous()
         self.bc = module.classifier.bias.detach().float().contiguous() if module.classifier.bias is not None else None
         self._fused_conv_relu = None      # decided on the first CUDA call
+        self._ident = {}                  # growth -> (ones, zeros) of the identity affine used by _put_channels
 
     # ------------------------------------------------------------------ pieces
     @staticmethod
@@ -122,6 +132,20 @@ class FrozenDenseNet:
             return torch.cudnn_convolution_relu(x, w, b, list(stride), list(padding), [1, 1], 1)
         return F.relu_(F.conv2d(x, w, b, stride, padding))
 
+    def _put_channels(self, buf, c, o):
+        """The layer's new features o (NCHW-logical, channels_last) -> channels [c, c + growth) of the block buffer.  ATen's
+        generic strided copy needs 0.9 ms per forward for these 64-byte segments; the 16-byte-vectorised NHWC pass of
+        libvitk (identity affine, no ReLU) writes them with the buffer's pixel pitch directly."""
+        g = o.shape[1]
+        o_nhwc = o.permute(0, 2, 3, 1)
+        if buf.is_cuda and self._affine_relu is ops.affine_relu_nhwc and o_nhwc.is_contiguous() and g % 8 == 0 and c % 8 == 0:
+            if g not in self._ident:
+                self._ident[g] = (torch.ones(g, dtype=torch.float32, device=buf.device), torch.zeros(g, dtype=torch.float32, device=buf.device))
+            one, zero = self._ident[g]
+            ops.affine_relu_nhwc(o_nhwc, g, one, zero, out=buf, out_channel_offset=c, relu=False)
+        else:
+            buf[..., c:c + g].copy_(o_nhwc)
+
     @staticmethod
     def _nchw(t_nhwc):           # [B,H,W,C] contiguous -> NCHW-logical view with channels_last strides (no copy)
         return t_nhwc.permute(0, 3, 1, 2)
@@ -143,10 +167,13 @@ class FrozenDenseNet:
             self._pool(src, buf, k, st, pd, is_max)                                    # pooled input -> channels [0, c0)
             c = c0
             for l in blk["layers"]:
-                a = self._affine_relu(buf, c, l["s1"], l["h1"])                        # norm1 + relu1 over channels [0, c)
-                t = self._conv_bias_relu(self._nchw(a), l["w1"], l["b1"], (1, 1), (0, 0))   # conv1 (+ norm2 + relu2)
+                if self._bottleneck is not None and l["w1m"] is not None and buf.is_cuda:
+                    t = self._nchw(self._bottleneck(buf, c, l["s1"], l["h1"], l["w1m"], l["b1f"]))   # one GEMM, buffer read once
+                else:
+                    a = self._affine_relu(buf, c, l["s1"], l["h1"])                    # norm1 + relu1 over channels [0, c)
+                    t = self._conv_bias_relu(self._nchw(a), l["w1"], l["b1"], (1, 1), (0, 0))   # conv1 (+ norm2 + relu2)
                 o = F.conv2d(t, l["w2"], None, 1, l["pad2"])                           # conv2: the layer's new features
-                buf[..., c:c + l["growth"]].copy_(o.permute(0, 2, 3, 1))
+                self._put_channels(buf, c, o)
                 c += l["growth"]
             tr = blk["transition"]
             if tr is not None:
