@@ -13,9 +13,10 @@
 //
 //   warp 0     TMA producer: A block [128 pixels x 64 channels] + W block [128 x 64] per stage, 4-stage ring
 //   warp 1     MMA issuer (one elected thread): tcgen05.mma M=128 N=128 K=16 x 4 per block, fp32 accumulator in TMEM
-//   warps 2-5  one thread per pixel row: transform the landed A block in place (16-bit -> fp32 fma + max(0) -> 16-bit,
-//              one rounding: bit-identical to vitk_affine_relu_nhwc)
-//   warps 6-9  tile epilogue (TMEM -> bias + ReLU -> 16-bit -> swizzled staging -> TMA store) of tile t while the other
+//   warps 2-9  two threads per pixel row (32 channels each): transform the landed A block in place (16-bit -> fp32 fma +
+//              max(0) -> 16-bit, one rounding: bit-identical to vitk_affine_relu_nhwc).  ~55 instructions per 16-byte cell:
+//              with one warp per SM sub-partition this pass, not HBM, set the pace (measured 1.5 k cycles per k-block)
+//   warps 10-13 tile epilogue (TMEM -> bias + ReLU -> 16-bit -> swizzled staging -> TMA store) of tile t while the other
 //              warps already work on tile t+1 (two accumulator stages in TMEM)
 // HBM-bound by construction: per k-block a CTA moves 16 KB of activations (W comes from L2) against 256 cycles of MMA.
 #include <cudaTypedefs.h>
@@ -27,7 +28,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int BT_THREADS = 320;   // TMA warp, MMA warp, 4 transform warps, 4 epilogue warps
+constexpr int BT_THREADS = 448;   // TMA warp, MMA warp, 8 transform warps, 4 epilogue warps
 constexpr int BT_STAGES = 4;
 constexpr int BT_N = 128;                 // bottleneck width (bn_size * growth_rate = 4 * 32 in every torchvision DenseNet)
 constexpr int BT_KMAX = 2048;             // channels of the widest concatenation served (DenseNet169: 1664, 201: 1920)
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   float* sBias = sShift + BT_KMAX;                                // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BT_N);
   uint64_t* full = bars;                     // [S] A and W block landed
-  uint64_t* ready = bars + BT_STAGES;        // [S] A block transformed (128 arrivals)
+  uint64_t* ready = bars + BT_STAGES;        // [S] A block transformed (256 arrivals)
   uint64_t* empty = bars + 2 * BT_STAGES;    // [S] the block's MMAs have completed
   uint64_t* tfull = bars + 3 * BT_STAGES;    // [2] accumulator of the tile complete
   uint64_t* tempty = tfull + 2;              // [2] accumulator read out (128 arrivals)
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       prefetch_tmap(&tmOut);
       for (int s = 0; s < BT_STAGES; ++s) {
         mbar_init(full + s, 1);
-        mbar_init(ready + s, 128);
+        mbar_init(ready + s, 256);
         mbar_init(empty + s, 1);
       }
       for (int a = 0; a < 2; ++a) {
@@ -134,9 +135,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
-    // ===================== transform: one thread per pixel row =====================
-    const int row = (warp - 2) * 32 + lane;
+  } else if (warp < 10) {
+    // ===================== transform: two threads per pixel row =====================
+    const int row = ((warp - 2) & 3) * 32 + lane;
+    const int half = (warp - 2) >> 2;              // 16-byte cells [4 * half, 4 * half + 4) of the row
     int g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -146,7 +148,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
         const float* sc = sScale + kb * 64;
         const float* sh = sShift + kb * 64;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = 4 * half + cc;
           uint4* cell = reinterpret_cast<uint4*>(a + swz128(row, c));
           const uint4 in = *cell;
           const float4 s0 = *reinterpret_cast<const float4*>(sc + 8 * c), s1 = *reinterpret_cast<const float4*>(sc + 8 * c + 4);
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     const int quad = warp & 3;                       // TMEM lane quadrant of this warp (warp id % 4)
     const int row = quad * 32 + lane;
     const uint32_t trow = tb + (uint32_t(quad * 32) << 16);
-    const bool leader = warp == 6;
+    const bool leader = warp == 10;
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;

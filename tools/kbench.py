@@ -98,6 +98,28 @@ def main():
         "colsum_h": (lambda: ops.colsum16(h16, cs_h, unscale=one), R * E, 0),
         "colsum_3d": (lambda: ops.colsum16(qkv, cs_3d, unscale=one), 3 * E, 0),
     }
+    # round-2 kernels around the encoder (input tiles, eval attention maps + rollout, the frozen teacher's bottleneck GEMM)
+    want = set(s for s in a.only.split(",") if s)
+    if a.model == "deit_tiny" and (not want or want & {"tiles_to_patches", "attn_probs", "rollout_row", "bottleneck_b1", "bottleneck_b3"}):
+        BF = torch.bfloat16
+        tiles = torch.randint(0, 65536, (B, 224, 224), dtype=torch.int32).to(torch.uint16).to(DEV)
+        patches = torch.empty(B * 196, 768, dtype=F16, device=DEV)
+        cases["tiles_to_patches"] = (lambda: ops.tiles_to_patches(tiles, 3, 16, out=patches), tiles.numel() * 2 + patches.numel() * 2, 0)
+        probs = torch.empty(B, H, T, T, device=DEV)
+        cases["attn_probs"] = (lambda: ops.attention_fwd(qkv, B, T, H, scale, out=o16b, lse=lse, probs=probs), 4 * E + probs.numel() * 4,
+                               6 * B * H * T * T * 64)
+        if not want or "rollout_row" in want:
+            maps = torch.rand(12, B, H, T, T, device=DEV)
+            cases["rollout_row"] = (lambda: ops.attention_rollout_row(maps, 0, "mean"), maps.numel() * 4, 0)
+        for nm, (P_, Ct_, C_) in {"bottleneck_b1": (B * 56 * 56, 256, 128), "bottleneck_b3": (B * 14 * 14, 1280, 768)}.items():
+            if want and nm not in want:
+                continue
+            xb = torch.randn(P_, Ct_, generator=g).to(DEV).to(BF)
+            wb = (torch.randn(128, C_, generator=g) * 0.05).to(DEV).to(BF)
+            sb_, hb_, bb_ = torch.rand(C_, device=DEV) + 0.5, torch.randn(C_, device=DEV) * 0.1, torch.randn(128, device=DEV) * 0.1
+            ob_ = torch.empty(P_, 128, dtype=BF, device=DEV)
+            cases[nm] = ((lambda xb=xb, C_=C_, sb_=sb_, hb_=hb_, wb=wb, bb_=bb_, ob_=ob_: ops.dense_bottleneck(xb, C_, sb_, hb_, wb, bb_, out=ob_)),
+                         P_ * C_ * 2 + P_ * 128 * 2 + 128 * C_ * 2, 2 * P_ * C_ * 128)
     only = [s for s in a.only.split(",") if s]
     flush = None if a.no_flush else torch.empty(256 * 1024 * 1024 // 4, device=DEV)
     res = {}

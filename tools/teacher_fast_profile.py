@@ -27,3 +27,7 @@ tot = sum(v[1] for v in agg.values())
 print(f"total kernel time {tot / 1e3:.2f} ms")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
     print(f"{v[1] / 1e3:7.2f} ms  {v[0]:4d}x  {k}")
+durs = [(ev.time_range.start, ev.device_time if hasattr(ev, "device_time") else ev.cuda_time) for ev in prof.events()
+        if ev.device_type == torch.autograd.DeviceType.CUDA and "dense_bottleneck" in ev.name]
+durs.sort()
+print("bottleneck launches in order (us):", " ".join(f"{d:.0f}" for _, d in durs))
