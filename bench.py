@@ -396,7 +396,7 @@ class KernelProfile:
         self._wrap("head_bwd", generic("head_bwd", lambda *a, **k: a[8].numel() * 6))
         self._wrap("loss_fwd_bwd", generic("loss", lambda *a, **k: 0))
         self._wrap("prefix_tokens_fwd", generic("prefix_tokens", lambda *a, **k: 0))
-        self._wrap("grad_sqnorm", generic("grad_sqnorm", lambda g, s: g.numel() * 4))
+        self._wrap("grad_sqnorm", generic("grad_sqnorm", lambda g, *a, **k: g.numel() * 4))
         self._wrap("adamw_step", generic("adamw", lambda p, *a, **k: p.numel() * 30))
         return self
 

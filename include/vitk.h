@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 18
+#define VITK_ABI_VERSION 19
 
 typedef enum {
   VITK_OK = 0,
@@ -340,7 +340,10 @@ int vitk_loss_fwd_bwd(const float* cls_logits, const float* dist_logits, const f
  * [chunk_off[c], chunk_off[c]+chunk_len[c]) and uses lr*lr_scale[c], wd[c].
  * state fp32[4] on device: {step, lr, grad_sqnorm, clip_coef}.
  * ------------------------------------------------------------------------------------------ */
-int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, void* stream);
+/* state[2] += ||grads||^2, summed in a FIXED order (bit-identical from launch to launch and across data-parallel ranks that
+ * hold identical gradients).  scratch: vitk_sqnorm_scratch_floats() floats, zero-initialised once by the caller. */
+int vitk_sqnorm_scratch_floats(void);
+int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, float* scratch, void* stream);
 /* If state[2] (the squared norm) is not finite the step is SKIPPED (fp16 overflow): nothing is written, and --
  * when amp_state is given -- S is halved; otherwise S doubles after `growth_interval` clean steps. */
 int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
@@ -350,8 +353,8 @@ int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                     float max_grad_norm, int32_t growth_interval, void* stream);
 /* Loss-scale bookkeeping for callers that run their OWN optimizer on the fp32 gradients (torch.optim.*):
  * checks grads for inf/nan; on overflow zeroes them and halves S, else counts towards the next doubling. */
-int vitk_amp_update(float* grads, int64_t n, float* amp_state, float* scratch4, int32_t growth_interval,
-                    void* stream);
+int vitk_amp_update(float* grads, int64_t n, float* amp_state, float* scratch4, float* sqnorm_scratch,
+                    int32_t growth_interval, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small memory-bound helpers

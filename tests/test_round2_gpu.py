@@ -211,8 +211,10 @@ def test_fused_adamw_state_dict_roundtrip_and_torch_adamw_interop():
     sa(x.cuda(), y.cuda())
     sb(x.cuda(), y.cuda())
     torch.cuda.synchronize()
-    # resumed run == uninterrupted run, up to the summation order of the atomically accumulated weight gradients
-    assert (ma._engine.flat.params - mb._engine.flat.params).abs().max().item() < 1e-6
+    # resumed run == uninterrupted run, up to the summation order of the atomically accumulated weight gradients: where a
+    # gradient element is itself rounding noise (|g| ~ eps) Adam's normalised update moves by a fraction of lr = 1e-3
+    assert (ma._engine.flat.params - mb._engine.flat.params).abs().max().item() < 2.5e-4
+    assert (ma._engine.flat.params - mb._engine.flat.params).abs().mean().item() < 1e-6
     assert rel_l2(oa.exp_avg, ob.exp_avg) < 1e-5 and oa.dev_state[0].item() == 4.0 == ob.dev_state[0].item()
     # a checkpoint written by torch.optim.AdamW (what the reference's Lightning run saves) resumes here
     mc, oc, _ = make()
@@ -336,6 +338,20 @@ def _two_rank_worker(rank, world, port, tmp, graph):
         torch.cuda.synchronize()
         res.update(ens_logits=out["logits"].cpu(), ens_preds=out["preds"].cpu(), ens_rollout=out["rollout"].cpu(), folds=mine)
         torch.save(res, Path(tmp) / f"r{rank}.pt")
+        # teardown as in bench.py: captured graphs pin NCCL work, so they go first; a watchdog ends the process should the
+        # communicator teardown itself block (the results are already on disk)
+        import threading
+        import time
+
+        def _bail():
+            time.sleep(15)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        step.graphs = [None, None]
+        del step
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
     finally:
         dist.destroy_process_group()
 

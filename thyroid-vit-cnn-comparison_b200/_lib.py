@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -80,9 +80,10 @@ SIGNATURES = {
     "vitk_metrics_update": (c_int, [c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int64, c_void_p]),
     "vitk_binary_auroc": (c_int, [c_void_p] * 3 + [c_int64] + [c_void_p] * 3),
     "vitk_loss_fwd_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int] + [c_float] * 5 + [c_void_p]),
-    "vitk_grad_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "vitk_sqnorm_scratch_floats": (c_int, []),
+    "vitk_grad_sqnorm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "vitk_adamw_step": (c_int, [c_void_p] * 10 + [c_int, c_void_p, c_void_p] + [c_float] * 4 + [c_int, c_void_p]),
-    "vitk_amp_update": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "vitk_amp_update": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vitk_cast_f32_to_16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "vitk_colsum16": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vitk_ensemble_probs": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),

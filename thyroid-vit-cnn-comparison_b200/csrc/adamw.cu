@@ -22,8 +22,15 @@
 namespace vitk {
 namespace {
 
-__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ state) {
+// ||g||^2 with a FIXED summation order: every block writes its partial sum, the last block to finish adds the partials in
+// index order.  (A float atomicAdd per block is shorter, but its order differs from launch to launch; the clip coefficient
+// -- and with it every updated parameter -- would then differ in the last bits between data-parallel ranks that hold
+// bit-identical all-reduced gradients, and the replicas would drift apart.)  scratch: uint counter at [0] (its place must not
+// depend on the grid size: the buffer is shared by launches of different sizes), float partials from [1].
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ state,
+                                                     float* __restrict__ scratch) {
   __shared__ float red[8];
+  __shared__ bool is_last;
   float acc = 0.f;
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -35,12 +42,30 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float v = red[threadIdx.x];
-    v += __shfl_xor_sync(0xffu, v, 4);
-    v += __shfl_xor_sync(0xffu, v, 2);
-    v += __shfl_xor_sync(0xffu, v, 1);
-    if (threadIdx.x == 0) atomicAdd(state + 2, v);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  float* partial = scratch + 1;
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w];
+    partial[blockIdx.x] = v;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t += __ldcg(partial + i);   // thread-strided, then a fixed tree
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w];
+    state[2] += v;          // the accumulator is cleared by the optimizer's tick kernel
+    *counter = 0u;          // ready for the next launch
   }
 }
 
@@ -152,10 +177,12 @@ int sq_grid(long long n) {
 
 using namespace vitk;
 
-extern "C" int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, void* stream) {
-  VITK_CHECK_ARG(grads && state && n > 0, "vitk_grad_sqnorm: bad args");
+extern "C" int vitk_sqnorm_scratch_floats(void) { return num_sms() * 8 + 4; }
+
+extern "C" int vitk_grad_sqnorm(const float* grads, int64_t n, float* state, float* scratch, void* stream) {
+  VITK_CHECK_ARG(grads && state && scratch && n > 0, "vitk_grad_sqnorm: bad args");
   VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "vitk_grad_sqnorm: grads must be 16-byte aligned");
-  sqnorm_kernel<<<sq_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(grads, n, state);
+  sqnorm_kernel<<<sq_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(grads, n, state, scratch);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -178,11 +205,11 @@ extern "C" int vitk_adamw_step(float* params, const float* grads, float* exp_avg
   return VITK_OK;
 }
 
-extern "C" int vitk_amp_update(float* grads, int64_t n, float* amp_state, float* scratch4, int32_t growth_interval,
-                               void* stream) {
-  VITK_CHECK_ARG(grads && amp_state && scratch4 && n > 0, "vitk_amp_update: bad args");
+extern "C" int vitk_amp_update(float* grads, int64_t n, float* amp_state, float* scratch4, float* sq_scratch,
+                               int32_t growth_interval, void* stream) {
+  VITK_CHECK_ARG(grads && amp_state && scratch4 && sq_scratch && n > 0, "vitk_amp_update: bad args");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  sqnorm_kernel<<<sq_grid(n), 256, 0, st>>>(grads, n, scratch4);
+  sqnorm_kernel<<<sq_grid(n), 256, 0, st>>>(grads, n, scratch4, sq_scratch);
   VITK_LAUNCH_CHECK();
   amp_zero_if_overflow_kernel<<<sq_grid(n), 256, 0, st>>>(grads, n, scratch4);
   VITK_LAUNCH_CHECK();

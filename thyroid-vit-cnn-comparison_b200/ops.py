@@ -267,8 +267,22 @@ def loss_fwd_bwd(cls_logits, dist_logits, teacher_logits, labels, *, mode: int, 
 
 
 # --------------------------------------------------------------------------- optimizer / loss scale
-def grad_sqnorm(grads, state):
-    check(_lib.load().vitk_grad_sqnorm(grads.data_ptr(), grads.numel(), state.data_ptr(), _stream()), "grad_sqnorm")
+_SQ_SCRATCH = {}
+
+
+def sqnorm_scratch(device) -> torch.Tensor:
+    """Per-device partial-sum buffer of the fixed-order gradient norm (zeroed once; the kernel resets its counter itself)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    buf = _SQ_SCRATCH.get(key)
+    if buf is None:
+        buf = torch.zeros(int(_lib.load().vitk_sqnorm_scratch_floats()), dtype=f32, device=torch.device("cuda", key))
+        _SQ_SCRATCH[key] = buf
+    return buf
+
+
+def grad_sqnorm(grads, state, scratch=None):
+    scratch = sqnorm_scratch(grads.device) if scratch is None else scratch
+    check(_lib.load().vitk_grad_sqnorm(grads.data_ptr(), grads.numel(), state.data_ptr(), scratch.data_ptr(), _stream()), "grad_sqnorm")
 
 
 def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, params_fp16, chunk_off, chunk_len, chunk_lr_scale, chunk_wd,
@@ -281,10 +295,9 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, params_fp16, chu
 
 def amp_update(grads, amp_state, scratch4, growth_interval: int = 2000):
     check(_lib.load().vitk_amp_update(grads.data_ptr(), grads.numel(), amp_state.data_ptr(), scratch4.data_ptr(),
-                                      growth_interval, _stream()), "amp_update")
+                                      sqnorm_scratch(grads.device).data_ptr(), int(growth_interval), _stream()), "amp_update")
 
 
-# --------------------------------------------------------------------------- helpers
 def cast_bf16(src, dst=None):
     _req(src, f32, "cast src")
     dst = torch.empty(src.shape, dtype=bf16, device=src.device) if dst is None else dst

@@ -43,6 +43,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(flat.params)
         # state = {step, lr(base, fixed 1.0: per-chunk table carries the real lr), grad_sqnorm, clip_coef}
         self.dev_state = torch.tensor([0.0, 1.0, 0.0, 1.0], dtype=torch.float32, device=dev)
+        # partial sums of the fixed-order gradient norm: owned by this optimizer (two optimizers may run on different streams)
+        from . import _lib
+        self._sq_scratch = torch.zeros(int(_lib.load().vitk_sqnorm_scratch_floats()), dtype=torch.float32, device=dev)
         ptr_to_name = {p.data_ptr(): n for n, p in model._engine_params().items()}
         self._name_of = {}                      # id(parameter) -> flat-buffer entry (parameters the engine owns)
         for g in self.param_groups:
@@ -100,7 +103,7 @@ class FusedAdamW(torch.optim.Optimizer):
         """Enqueue norm + update kernels (CUDA-graph capturable: no host reads, hyper-parameters on device)."""
         flat = self.engine.flat
         # the squared norm doubles as the fp16 overflow detector, so it is always computed
-        ops.grad_sqnorm(flat.grads, self.dev_state)
+        ops.grad_sqnorm(flat.grads, self.dev_state, self._sq_scratch)
         eng = self.engine
         fp16 = flat.dtype16 == torch.float16
         ops.adamw_step(flat.params, flat.grads, self.exp_avg, self.exp_avg_sq, None if fp16 else flat.w16,

@@ -519,7 +519,10 @@ class TrainStep:
     def run(self) -> None:
         """Enqueue one step on the current stream (no host sync)."""
         model = self.model
-        model._shadow_version = model._param_version()
+        # parameters edited through torch since the last step (load_state_dict, manual copy_) invalidate the 16-bit shadow the
+        # kernels read; the fused optimizer itself keeps it in sync without bumping tensor versions, so this is a no-op in
+        # the steady state
+        model._sync_shadow()
         self.opt._refresh_hyper()
         cur = torch.cuda.current_stream()
         if self._pending_copy:
