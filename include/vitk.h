@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 19
+#define VITK_ABI_VERSION 20
 
 typedef enum {
   VITK_OK = 0,
@@ -256,6 +256,11 @@ int vitk_affine_relu_nhwc(const void* x, int64_t x_ld, void* y, int64_t y_ld, co
  * and wrote it three times). */
 int vitk_dense_bottleneck(const void* x, int64_t x_ld, const float* scale, const float* shift, const void* w,
                           const float* bias, void* out, int64_t pixels, int32_t C, int32_t dtype, void* stream);
+/* Patch rows of a k x k / stride / zero-padded convolution over a 16-bit NHWC tensor with few channels (the teacher's 7x7
+ * 3-channel stem, densenet.py features.conv0): patches[(b,oy,ox), (ky*k + kx)*C + c], row pitch ld (multiple of 8, the tail
+ * is zero-filled) -- the A operand of vitk_gemm against the filters reshaped to [Cout, ky, kx, c]. */
+int vitk_im2col_rows(const void* x, void* patches, int32_t B, int32_t H, int32_t W, int32_t C, int32_t kernel,
+                     int32_t stride, int32_t pad, int64_t ld, void* stream);
 /* MaxPool2d(kernel, stride, pad) (is_max = 1, -inf padding) / AvgPool2d(kernel, stride, pad) (is_max = 0, count_include_pad) of a
  * compact NHWC tensor x [B,H,W,C], ceil_mode False, written with pixel pitch y_ld into y [B,OH,OW,y_ld]: the DenseNet stem's
  * pool0 and the transitions' pool (torchvision densenet.py) store straight into the next dense block's buffer. */

@@ -970,3 +970,27 @@ def test_dense_bottleneck_matches_affine_relu_conv1x1(P, Ct, C, dt):
     assert torch.equal(ops.dense_bottleneck(x, C, s, h, w, b), out)          # deterministic
     with pytest.raises(TypeError):
         ops.dense_bottleneck(x, C, s, h, w[:, :-8].contiguous(), b)
+
+
+def test_im2col_rows_plus_gemm_is_the_stem_convolution():
+    """vitk_im2col_rows (7x7 / stride 2 / pad 3 over a 3-channel NHWC tensor, element order ky, kx, c) + vitk_gemm against
+    the filters reshaped the same way == F.conv2d."""
+    g = torch.Generator().manual_seed(4)
+    B, H, W, C, Co = 3, 38, 42, 3, 64
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(Co, C, 7, 7, generator=g) * 0.1).to(DEV).to(torch.bfloat16)
+    b = torch.randn(Co, generator=g).to(DEV)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    patches = ops.im2col_rows(xn, 7, 2, 3)
+    OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    assert patches.shape == (B * OH * OW, 152)
+    ref_p = torch.nn.functional.unfold(x.float(), 7, padding=3, stride=2)                    # [B, C*49, L], order (c, ky, kx)
+    ref_p = ref_p.view(B, C, 49, OH * OW).permute(0, 3, 2, 1).reshape(B * OH * OW, 147)      # -> (ky*7+kx, c)
+    torch.cuda.synchronize()
+    assert torch.equal(patches[:, :147].float(), ref_p) and patches[:, 147:].abs().max().item() == 0
+    wm = torch.nn.functional.pad(w.permute(0, 2, 3, 1).reshape(Co, 147), (0, 5)).contiguous()
+    out = torch.empty(B * OH * OW, Co, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(patches, wm, patches.shape[0], Co, 152, out=out, bias=b)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), b, stride=2, padding=3).permute(0, 2, 3, 1).reshape(-1, Co)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < 2.0 ** -7 * max(1.0, ref.abs().max().item())

@@ -77,6 +77,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// Patch rows of a k x k / stride s / zero-padded convolution over an NHWC tensor with FEW channels (the 3-channel 7x7 stem):
+// row (b, oy, ox) = [ky][kx][c] -> k*k*C elements, padded with zeros to `ld` columns (a multiple of 8).  One thread gathers
+// the 8 elements of one 16-byte cell of a row (the input is small and cached; a per-block shared table turns the column
+// index into (ky, kx, input offset)) and writes it with a single coalesced 16-byte store: the kernel is bound by the
+// ld * 2 bytes per output pixel it writes.  Feeds vitk_gemm: cuDNN runs this 3-channel convolution on a pre-tensor-core
+// implicit-GEMM kernel (1.8 ms at batch 256).
+__global__ void __launch_bounds__(256)
+    im2col_rows_kernel(const uint16_t* __restrict__ x, uint4* __restrict__ patches, int B, int H, int W, int C, int k, int s, int pad,
+                       int OH, int OW, int ld) {
+  extern __shared__ int im2col_tab[];            // [ld] input offset (ky*W + kx)*C + c, [ld] (ky << 8) | kx, -1 beyond k*k*C
+  int* t_off = im2col_tab;
+  int* t_kk = im2col_tab + ld;
+  for (int e = threadIdx.x; e < ld; e += blockDim.x) {
+    if (e < k * k * C) {
+      const int ky = e / (k * C), rem = e - ky * (k * C), kx = rem / C, c = rem - kx * C;
+      t_off[e] = (ky * W + kx) * C + c;
+      t_kk[e] = (ky << 8) | kx;
+    } else {
+      t_off[e] = 0;
+      t_kk[e] = -1;
+    }
+  }
+  __syncthreads();
+  const int cells = ld >> 3;
+  const long long total = (long long)B * OH * OW * cells;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cell = int(i % cells);
+    const long long r = i / cells;
+    const int ox = int(r % OW);
+    const long long r2 = r / OW;
+    const int oy = int(r2 % OH);
+    const int b = int(r2 / OH);
+    const int iy0 = oy * s - pad, ix0 = ox * s - pad;
+    const uint16_t* base = x + (((long long)b * H + iy0) * W + ix0) * C;       // may point before the image: only valid taps are read
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint32_t v2 = 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = cell * 8 + 2 * h + q;
+        const int kk = t_kk[e];
+        uint32_t v = 0;
+        if (kk >= 0) {
+          const int iy = iy0 + (kk >> 8), ix = ix0 + (kk & 255);
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(base + t_off[e]);
+        }
+        v2 |= v << (16 * q);
+      }
+      w[h] = v2;
+    }
+    patches[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 }  // namespace
 }  // namespace vitk
 
@@ -117,6 +173,23 @@ extern "C" int vitk_affine_relu_nhwc(const void* x, int64_t x_ld, void* y, int64
   affine_relu_nhwc_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(x), x_ld / 8, reinterpret_cast<uint4*>(y), y_ld / 8, scale, shift, (long long)pixels, cv,
       int(dtype == VITK_FP16), relu);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_im2col_rows(const void* x, void* patches, int32_t B, int32_t H, int32_t W, int32_t C, int32_t kernel,
+                                int32_t stride, int32_t pad, int64_t ld, void* stream) {
+  VITK_CHECK_ARG(x && patches && B > 0 && H > 0 && W > 0 && C > 0 && kernel > 0 && stride > 0 && pad >= 0, "vitk_im2col_rows: bad args");
+  VITK_CHECK_ARG(ld >= (int64_t)kernel * kernel * C && ld % 8 == 0, "vitk_im2col_rows: ld must be a multiple of 8, >= k*k*C");
+  const int OH = (H + 2 * pad - kernel) / stride + 1, OW = (W + 2 * pad - kernel) / stride + 1;
+  VITK_CHECK_ARG(OH > 0 && OW > 0, "vitk_im2col_rows: empty output");
+  const long long total = (long long)B * OH * OW * (ld / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  VITK_CHECK_ARG(kernel < 256 && ld <= 4096 && ((uintptr_t)patches % 16 == 0), "vitk_im2col_rows: kernel < 256, ld <= 4096, 16-byte aligned output");
+  im2col_rows_kernel<<<(unsigned)blocks, 256, 2 * (size_t)ld * sizeof(int), reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint16_t*>(x), reinterpret_cast<uint4*>(patches), B, H, W, C, kernel, stride, pad, OH, OW, (int)ld);
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -514,6 +514,17 @@ def affine_relu_nhwc(x, C: int, scale, shift, out=None, relu: bool = True, out_c
     return out
 
 
+def im2col_rows(x_nhwc, kernel: int, stride: int, pad: int, out=None):
+    """16-bit NHWC [B,H,W,C] -> patch rows [B*OH*OW, ld] (ld = k*k*C rounded up to 8), element order (ky, kx, c)."""
+    _req16(x_nhwc, "im2col x")
+    B, H, W, Cc = x_nhwc.shape
+    OH, OW = (H + 2 * pad - kernel) // stride + 1, (W + 2 * pad - kernel) // stride + 1
+    ld = (kernel * kernel * Cc + 7) // 8 * 8
+    out = torch.empty(B * OH * OW, ld, dtype=x_nhwc.dtype, device=x_nhwc.device) if out is None else out
+    check(_lib.load().vitk_im2col_rows(x_nhwc.data_ptr(), out.data_ptr(), B, H, W, Cc, kernel, stride, pad, ld, _stream()), "im2col_rows")
+    return out
+
+
 def dense_bottleneck(x, C: int, scale, shift, w, bias, out=None):
     """x: 16-bit NHWC [..., Ct] (the first C channels are read), w: 16-bit [128, C], scale / shift fp32 [C], bias fp32 [128]
     -> relu(relu(x[..., :C] * scale + shift) @ w^T + bias) as 16-bit [..., 128]."""

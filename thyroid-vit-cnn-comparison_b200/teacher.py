@@ -74,9 +74,17 @@ class FrozenDenseNet:
         f = module.features
         cl = lambda w: w.to(dtype).contiguous(memory_format=torch.channels_last)
         w0, b0 = _fold(f.conv0, f.norm0)
-        # (the 3-channel stem runs on a pre-tensor-core cuDNN kernel, 1.8 ms at batch 256; zero-padding it to 8 channels was
-        # measured: the library then picks a 2.8 ms tensor-core kernel -- left as it is)
+        # The 3-channel stem runs on a pre-tensor-core cuDNN kernel (1.8 ms at batch 256; zero-padding it to 8 channels was
+        # measured: the library then picks a 2.8 ms kernel).  GEMM form: patch rows (vitk_im2col_rows, element order ky, kx, c)
+        # against the filters reshaped the same way; the ReLU moves behind the max-pool (max and ReLU commute).
         self.stem = (cl(w0), b0.to(dtype), f.conv0.stride, f.conv0.padding)
+        k0 = f.conv0.kernel_size
+        self.stem_gemm = None
+        if k0[0] == k0[1] and f.conv0.stride[0] == f.conv0.stride[1] and f.conv0.padding[0] == f.conv0.padding[1] and w0.shape[0] % 8 == 0:
+            wm = w0.permute(0, 2, 3, 1).reshape(w0.shape[0], -1)                       # [Cout, ky*kx*c]
+            ld = (wm.shape[1] + 7) // 8 * 8
+            wm = F.pad(wm, (0, ld - wm.shape[1])).to(dtype).contiguous()
+            self.stem_gemm = {"w": wm, "b": b0.float().contiguous(), "k": int(k0[0]), "s": int(f.conv0.stride[0]), "p": int(f.conv0.padding[0])}
         self.stem_pool = self._pool_spec(f.pool0, True)
         self.blocks: List[dict] = []
         i = 1
@@ -155,7 +163,19 @@ class FrozenDenseNet:
     def __call__(self, images: torch.Tensor) -> torch.Tensor:
         x = images.to(self.dtype).contiguous(memory_format=torch.channels_last)
         w0, b0, stride0, pad0 = self.stem
-        src = self._nhwc(self._conv_bias_relu(x, w0, b0, stride0, pad0))               # [B,H,W,64]
+        relu_after_pool = False
+        sg = self.stem_gemm
+        if sg is not None and self._bottleneck is not None and x.is_cuda and self.stem_pool[3]:
+            xn = self._nhwc(x)                                                          # [B,H,W,3] view of the channels_last batch
+            patches = ops.im2col_rows(xn, sg["k"], sg["s"], sg["p"])
+            Bn, Hn, Wn, _ = xn.shape
+            OHs, OWs = (Hn + 2 * sg["p"] - sg["k"]) // sg["s"] + 1, (Wn + 2 * sg["p"] - sg["k"]) // sg["s"] + 1
+            cout = sg["w"].shape[0]
+            src = torch.empty(Bn, OHs, OWs, cout, dtype=self.dtype, device=x.device)
+            ops.gemm(patches, sg["w"], patches.shape[0], cout, patches.shape[1], out=src, bias=sg["b"])   # conv0 + norm0, no ReLU yet
+            relu_after_pool = True
+        else:
+            src = self._nhwc(self._conv_bias_relu(x, w0, b0, stride0, pad0))           # [B,H,W,64]
         pool = self.stem_pool
         buf = None
         for blk in self.blocks:
@@ -165,6 +185,11 @@ class FrozenDenseNet:
             ct = c0 + sum(l["growth"] for l in blk["layers"])
             buf = torch.empty(B, OH, OW, ct, dtype=self.dtype, device=src.device)     # the block's concatenation, NHWC
             self._pool(src, buf, k, st, pd, is_max)                                    # pooled input -> channels [0, c0)
+            if relu_after_pool:                                                        # relu0 behind pool0: in place over [0, c0)
+                if c0 not in self._ident:
+                    self._ident[c0] = (torch.ones(c0, dtype=torch.float32, device=buf.device), torch.zeros(c0, dtype=torch.float32, device=buf.device))
+                ops.affine_relu_nhwc(buf, c0, self._ident[c0][0], self._ident[c0][1], out=buf, relu=True)
+                relu_after_pool = False
             c = c0
             for l in blk["layers"]:
                 if self._bottleneck is not None and l["w1m"] is not None and buf.is_cuda:
@@ -188,6 +213,8 @@ class FrozenDenseNet:
         """Move the snapshotted parameters (used when the step is built before the module reaches the GPU)."""
         mv = lambda t: t.to(device) if isinstance(t, torch.Tensor) else t
         self.stem = tuple(mv(t) for t in self.stem)
+        if self.stem_gemm is not None:
+            self.stem_gemm = {k: mv(v) for k, v in self.stem_gemm.items()}
         for blk in self.blocks:
             for l in blk["layers"]:
                 for k, v in l.items():
