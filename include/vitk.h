@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 20
+#define VITK_ABI_VERSION 21
 
 typedef enum {
   VITK_OK = 0,
@@ -162,6 +162,10 @@ int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const f
  * ------------------------------------------------------------------------------------------ */
 int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, float* lse, float* probs, int32_t B,
                        int32_t N, int32_t H, float scale, void* stream);
+/* The maps alone, from the lse a preceding vitk_attention_fwd wrote: probs + b * probs_batch_stride holds image b's
+ * [H,N,N] maps (stride in elements; H*N*N = the contiguous [B,H,N,N] layout). */
+int vitk_attention_probs(const void* qkv, int32_t dtype, const float* lse, float* probs, int64_t probs_batch_stride,
+                         int32_t B, int32_t N, int32_t H, float scale, void* stream);
 int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                        float* delta, void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H,
                        float scale, void* stream);
@@ -384,9 +388,11 @@ int vitk_attention_rollout(const float* probs, float* rollout, float* scratch, i
                            int32_t B, int32_t H, int32_t N, int32_t fusion, void* stream);
 /* Row `row` of the same rollout matrix (row 0 = the class token's map, the only row config 5 / the visualisation code
  * uses, attention_utils.py:49-62): L vector-matrix products per image, the maps are read once, no [B,N,N] scratch.
- * probs fp32 [L,B,H,N,N] -> out fp32 [B,N]. */
-int vitk_attention_rollout_row(const float* probs, float* out, int32_t L, int32_t B, int32_t H, int32_t N,
-                               int32_t row, int32_t fusion, void* stream);
+ * The [H,N,N] maps of (layer l, image b) start at probs + l * layer_stride + b * batch_stride (elements): [L,B,H,N,N] is
+ * (B*H*N*N, H*N*N); the image-major layout [B,L,H,N,N] = (H*N*N, L*H*N*N) keeps one image's maps contiguous, which is what
+ * the one-CTA-per-image walk wants (measured: 1.31 ms -> see profiles/ for DeiT-tiny, batch 256).  out fp32 [B,N]. */
+int vitk_attention_rollout_row(const float* probs, float* out, int64_t layer_stride, int64_t batch_stride, int32_t L,
+                               int32_t B, int32_t H, int32_t N, int32_t row, int32_t fusion, void* stream);
 
 #ifdef __cplusplus
 }

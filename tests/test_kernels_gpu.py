@@ -279,6 +279,18 @@ def test_attention_dropout_fwd_bwd(B, N, H, dt):
         ops.attention_fwd(qkv, B, N, H, scale, drop=(seed, 1.0, site))
 
 
+def test_attention_probs_with_batch_stride_equal_the_contiguous_maps():
+    B, N, H = 5, 198, 3
+    qkv = _rand(B, N, 3 * H * 64, seed=8).to(torch.float16)
+    ref = torch.empty(B, H, N, N, device=DEV)
+    out, lse = ops.attention_fwd(qkv, B, N, H, 0.125, probs=ref)
+    L = 4
+    im = torch.zeros(B, L, H, N, N, device=DEV)
+    ops.attention_probs(qkv, lse, B, N, H, 0.125, im[:, 2], batch_stride=L * H * N * N)
+    torch.cuda.synchronize()
+    assert torch.equal(im[:, 2], ref) and im[:, 1].abs().max().item() == 0 and im[:, 3].abs().max().item() == 0
+
+
 def test_attention_probs_rows_sum_to_one():
     B, N, H = 2, 198, 3
     qkv = _rand(B, N, 3 * H * 64, dtype=F16, seed=1)
@@ -515,6 +527,8 @@ def test_ensemble_and_rollout():
         for row in (0, 7):      # one row by vector-matrix products (the class-token map of config 5): same numbers
             rr = ops.attention_rollout_row(p, row, fusion)
             assert rr.shape == (B, N) and (rr - R[:, row]).abs().max().item() < 1e-5
+            rim = ops.attention_rollout_row(p.transpose(0, 1).contiguous(), row, fusion, image_major=True)   # [B,L,H,N,N] layout
+            assert torch.equal(rim, rr)
 
 
 # ------------------------------------------------------------------ nn.Dropout (drop_rate > 0): counter-based masks

@@ -541,7 +541,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
 // probs[b,h,q,:] = softmax(q.k^T*scale) in fp32 -- the `attention_maps` the reference stores in
 // eval mode (vision_transformer_base.py:186-188).  One warp per (b,h,q) row; not on the train path.
 template <bool H16>
-__global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restrict__ probs, int B, int N, int H, float scale) {
+__global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restrict__ probs, long long batch_stride, int B, int N, int H,
+                                  float scale) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b,h,q)
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * H * N) return;
@@ -555,7 +556,7 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
     const float2 f = upk<H16>(*reinterpret_cast<const uint32_t*>(qp + d));
     qv[d] = f.x; qv[d + 1] = f.y;
   }
-  float* prow = probs + row * N;
+  float* prow = probs + (long long)b * batch_stride + ((long long)h * N + q) * N;
   float mx = -INFINITY;
   for (int k = lane; k < N; k += 32) {
     const bf16* kp = qkv + (((long long)(b * N + k) * 3 + 1) * H + h) * DH;
@@ -589,12 +590,24 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 constexpr int TC_MAX_TOKENS = 256;      // forward
 constexpr int TC_MAX_TOKENS_BWD = 240;  // backward (shared-memory budget of the pipelined kernel)
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
-int attention_probs_tc(const void* qkv, const float* lse, float* probs, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
+int attention_probs_tc(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H, float scale,
+                       bool fp16, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
                      int H, float scale, bool fp16, cudaStream_t st);
 }  // namespace vitk
 
 using namespace vitk;
+
+template <bool H16>
+static int attention_probs_impl(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H,
+                                float scale, cudaStream_t st) {
+  if (N <= TC_MAX_TOKENS) return attention_probs_tc(qkv, lse, probs, batch_stride, B, N, H, scale, H16, st);   // tensor-core S + lse
+  const long long rows = (long long)B * H * N;
+  attn_probs_kernel<H16><<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), probs, batch_stride, B, N, H,
+                                                                     scale);
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
 
 template <bool H16>
 static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* probs, int B, int N, int H, float scale,
@@ -608,12 +621,7 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* pro
                                                       scale * LOG2E, make_drop_spec(nullptr, 0.f, 0), 0);
     VITK_LAUNCH_CHECK();
   }
-  if (probs != nullptr) {
-    if (N <= TC_MAX_TOKENS) return attention_probs_tc(qkv, lse, probs, B, N, H, scale, H16, st);   // tensor-core S + the forward's lse
-    const long long rows = (long long)B * H * N;
-    attn_probs_kernel<H16><<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), probs, B, N, H, scale);
-    VITK_LAUNCH_CHECK();
-  }
+  if (probs != nullptr) return attention_probs_impl<H16>(qkv, lse, probs, (long long)H * N * N, B, N, H, scale, st);
   return VITK_OK;
 }
 
@@ -626,6 +634,17 @@ extern "C" int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, flo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == VITK_FP16 ? attention_fwd_impl<true>(qkv, out, lse, probs, B, N, H, scale, st)
                             : attention_fwd_impl<false>(qkv, out, lse, probs, B, N, H, scale, st);
+}
+
+extern "C" int vitk_attention_probs(const void* qkv, int32_t dtype, const float* lse, float* probs, int64_t probs_batch_stride,
+                                    int32_t B, int32_t N, int32_t H, float scale, void* stream) {
+  VITK_CHECK_ARG(qkv && lse && probs, "vitk_attention_probs: null pointer");
+  VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_probs: dtype must be bf16 or fp16");
+  VITK_CHECK_ARG(B > 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "vitk_attention_probs: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_CHECK_ARG(probs_batch_stride >= (int64_t)H * N * N, "vitk_attention_probs: batch stride smaller than one image's maps");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == VITK_FP16 ? attention_probs_impl<true>(qkv, lse, probs, probs_batch_stride, B, N, H, scale, st)
+                            : attention_probs_impl<false>(qkv, lse, probs, probs_batch_stride, B, N, H, scale, st);
 }
 
 template <bool H16, bool DROP>

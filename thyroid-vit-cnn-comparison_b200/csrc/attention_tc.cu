@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
 template <bool H16>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
     attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                         const float* __restrict__ lse, float* __restrict__ probs, int N, int H, int KP, float scale_log2) {
+                         const float* __restrict__ lse, float* __restrict__ probs, long long batch_stride, int N, int H, int KP,
+                         float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       // a padded shared-memory tile and stores it row by row: one fully coalesced 128-byte segment per instruction.
       float* tile = sT + warp * (32 * 33);
       const int r0 = q0 + warp * 32;                       // first query row of this warp
-      float* pbase = probs + (((long long)b * H + h) * N + r0) * N;
+      float* pbase = probs + (long long)b * batch_stride + ((long long)h * N + r0) * N;   // image b's maps start at b * batch_stride
       uint32_t va[32], vb[32];
       const int nch = (KP + 31) >> 5;
       auto load_chunk = [&](int c, uint32_t (&v)[32]) {
@@ -837,7 +838,8 @@ extern "C" int vitk_debug_read_attn(long long* dst) { return (int)cudaMemcpyFrom
 
 // Eval-mode attention maps for N <= 256 (needs the lse the forward just wrote).
 template <bool H16>
-int attention_probs_tc_impl(const void* qkv, const float* lse, float* probs, int B, int N, int H, float scale, cudaStream_t st) {
+int attention_probs_tc_impl(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H, float scale,
+                            cudaStream_t st) {
   const int KP = (N + 15) & ~15;
   CUtensorMap tmQ, tmKV;
   int rc;
@@ -851,13 +853,14 @@ int attention_probs_tc_impl(const void* qkv, const float* lse, float* probs, int
     configured = true;
   }
   dim3 grid((N + 127) / 128, H, B);
-  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, lse, probs, N, H, KP, scale * LOG2E));
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, lse, probs, batch_stride, N, H, KP, scale * LOG2E));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
-int attention_probs_tc(const void* qkv, const float* lse, float* probs, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {
-  return fp16 ? attention_probs_tc_impl<true>(qkv, lse, probs, B, N, H, scale, st)
-              : attention_probs_tc_impl<false>(qkv, lse, probs, B, N, H, scale, st);
+int attention_probs_tc(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H, float scale,
+                       bool fp16, cudaStream_t st) {
+  return fp16 ? attention_probs_tc_impl<true>(qkv, lse, probs, batch_stride, B, N, H, scale, st)
+              : attention_probs_tc_impl<false>(qkv, lse, probs, batch_stride, B, N, H, scale, st);
 }
 
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {

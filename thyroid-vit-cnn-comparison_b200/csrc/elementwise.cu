@@ -416,9 +416,13 @@ __global__ void rollout_matmul_kernel(const float* __restrict__ a, const float* 
 // read exactly once, 198x fewer flops than the matrix chain.  One CTA per image; warp w owns rows i = w, w+W, ...; lanes
 // stride over the columns (coalesced 128-byte row segments); per-warp partial accumulators live in shared memory.
 constexpr int ROLL_WARPS = 16;
-template <int NJ>   // NJ = ceil(N / 32) for N <= 256 (row segments held in registers), 0 = any N (two passes over the row)
+// NJ = ceil(N / 32) for N <= 256 (row segments held in registers), 0 = any N (two passes over the row); HT = number of heads
+// when it is one of the reference's (3 / 6 / 12: the head loop unrolls and all HT * NJ loads of a row are in flight at once --
+// with a run-time head count each head's 7 loads waited for the previous head's, ~3 us per row), 0 = run-time H
+template <int NJ, int HT>
 __global__ void __launch_bounds__(ROLL_WARPS * 32)
-    rollout_row_kernel(const float* __restrict__ probs, float* __restrict__ out, int L, int B, int H, int N, int row, int fusion) {
+    rollout_row_kernel(const float* __restrict__ probs, float* __restrict__ out, long long layer_stride, long long batch_stride, int L,
+                       int B, int H, int N, int row, int fusion) {
   extern __shared__ float roll_smem[];
   float* v = roll_smem;                 // [N] current row vector
   float* part = roll_smem + N;          // [ROLL_WARPS][N] per-warp partial sums of the next vector
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(ROLL_WARPS * 32)
   for (int l = L - 1; l >= 0; --l) {
     float* mine = part + warp * N;
     for (int j = lane; j < N; j += 32) mine[j] = 0.f;
-    const float* base = probs + (((long long)l * B + b) * H) * (long long)N * N;
+    const float* base = probs + (long long)l * layer_stride + (long long)b * batch_stride;   // [H][N][N] maps of (layer l, image b)
     for (int i = warp; i < N; i += ROLL_WARPS) {
       const float vi = v[i];
       if (vi == 0.f) continue;          // warp-uniform: the first product only touches row `row`
@@ -439,13 +443,32 @@ __global__ void __launch_bounds__(ROLL_WARPS * 32)
         float f[NJ > 0 ? NJ : 1];
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) f[jj] = fusion == 0 ? 0.f : (fusion == 1 ? -INFINITY : INFINITY);
-        for (int h = 0; h < H; ++h) {
-          const float* prow = base + ((long long)h * N + i) * N;
+        if (HT > 0) {
+          float pv[HT > 0 ? HT : 1][NJ > 0 ? NJ : 1];
 #pragma unroll
-          for (int jj = 0; jj < NJ; ++jj) {
-            const int j = lane + 32 * jj;
-            const float p = j < N ? __ldg(prow + j) : 0.f;
-            f[jj] = fusion == 0 ? f[jj] + p : (fusion == 1 ? fmaxf(f[jj], p) : fminf(f[jj], p));
+          for (int h = 0; h < HT; ++h) {
+            const float* prow = base + ((long long)h * N + i) * N;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+              const int j = lane + 32 * jj;
+              pv[h][jj] = j < N ? __ldg(prow + j) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < HT; ++h) {
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj)
+              f[jj] = fusion == 0 ? f[jj] + pv[h][jj] : (fusion == 1 ? fmaxf(f[jj], pv[h][jj]) : fminf(f[jj], pv[h][jj]));
+          }
+        } else {
+          for (int h = 0; h < H; ++h) {
+            const float* prow = base + ((long long)h * N + i) * N;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+              const int j = lane + 32 * jj;
+              const float p = j < N ? __ldg(prow + j) : 0.f;
+              f[jj] = fusion == 0 ? f[jj] + p : (fusion == 1 ? fmaxf(f[jj], p) : fminf(f[jj], p));
+            }
           }
         }
         float sum = 0.f;
@@ -696,26 +719,34 @@ extern "C" int vitk_attention_rollout(const float* probs, float* rollout, float*
   return VITK_OK;
 }
 
-extern "C" int vitk_attention_rollout_row(const float* probs, float* out, int32_t L, int32_t B, int32_t H, int32_t N,
-                                          int32_t row, int32_t fusion, void* stream) {
+extern "C" int vitk_attention_rollout_row(const float* probs, float* out, int64_t layer_stride, int64_t batch_stride, int32_t L,
+                                          int32_t B, int32_t H, int32_t N, int32_t row, int32_t fusion, void* stream) {
+  VITK_CHECK_ARG(layer_stride >= (int64_t)H * N * N && batch_stride >= (int64_t)H * N * N, "vitk_attention_rollout_row: bad strides");
   VITK_CHECK_ARG(probs && out && L > 0 && B > 0 && H > 0 && N > 0 && row >= 0 && row < N && fusion >= 0 && fusion <= 2,
                  "vitk_attention_rollout_row: bad args");
   const size_t smem = (size_t)(ROLL_WARPS + 1) * N * sizeof(float);
   VITK_CHECK_ARG(smem <= 200 * 1024, "vitk_attention_rollout_row: sequence too long (N=%d)", N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nj = (N + 31) / 32;
+#define VITK_ROLL(NJ_, HT_) rollout_row_kernel<NJ_, HT_><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, layer_stride, batch_stride, L, B, H, N, row, fusion)
   if (nj <= 7) {
-    rollout_row_kernel<7><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, L, B, H, N, row, fusion);
+    if (H == 3) VITK_ROLL(7, 3);
+    else if (H == 6) VITK_ROLL(7, 6);
+    else if (H == 12) VITK_ROLL(7, 12);
+    else VITK_ROLL(7, 0);
   } else if (nj == 8) {
-    rollout_row_kernel<8><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, L, B, H, N, row, fusion);
+    if (H == 3) VITK_ROLL(8, 3);
+    else if (H == 12) VITK_ROLL(8, 12);
+    else VITK_ROLL(8, 0);
   } else {
     static size_t configured = 0;
     if (smem > 48 * 1024 && configured < smem) {
-      VITK_CUDA(cudaFuncSetAttribute(rollout_row_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      VITK_CUDA(cudaFuncSetAttribute(rollout_row_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = 200 * 1024;
     }
-    rollout_row_kernel<0><<<B, ROLL_WARPS * 32, smem, st>>>(probs, out, L, B, H, N, row, fusion);
+    VITK_ROLL(0, 0);
   }
+#undef VITK_ROLL
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -346,12 +346,18 @@ class VitEngine:
             ops.layernorm_fwd(x_in, self.p(pre + "norm1.weight"), self.p(pre + "norm1.bias"), eps=d.eps, y=ws.xn1[s], mean=st[0], rstd=st[1])
             ops.gemm(ws.xn1[s], self.w(pre + "attn.qkv.weight"), M, 3 * D, D, out=ws.qkv[s], bias=self.p(pre + "attn.qkv.bias"))
             probs = None
-            if isinstance(attn_probs, torch.Tensor):       # caller-owned [L,B,H,T,T] buffer (ensemble rollout): no stacking copy later
+            probs_im = None
+            if isinstance(attn_probs, torch.Tensor):       # caller-owned [L,B,H,T,T] buffer: no stacking copy later
                 probs = attn_probs[l]
+            elif isinstance(attn_probs, tuple):            # ("image_major", [B,L,H,T,T]): one image's maps contiguous (ensemble rollout)
+                probs_im = attn_probs[1]
             elif attn_probs is not None:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
             ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs, drop=self._attn_site(l))
+            if probs_im is not None:
+                ops.attention_probs(ws.qkv[s], ws.lse[s], B, T, d.heads, self.scale, probs_im[:, l],
+                                    batch_stride=d.depth * d.heads * T * T)
             ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in,
                      row_scale=rs(2 * l), drop=self._site(1 + 3 * l))
             ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), eps=d.eps, y=ws.xn2[s], mean=st[2], rstd=st[3])

@@ -111,10 +111,11 @@ class EnsembleInference:
             d = eng.d
             key = (images.shape[0], d.depth, d.heads, d.tokens)
             maps = self._maps.get(key)
-            if maps is None:                       # one [L,B,H,T,T] buffer, reused by every member of that shape
-                maps = torch.empty(d.depth, images.shape[0], d.heads, d.tokens, d.tokens, dtype=torch.float32, device=images.device)
+            if maps is None:                       # one image-major [B,L,H,T,T] buffer, reused by every member of that shape:
+                # the rollout walks one image's L*H maps per CTA, so they are kept contiguous
+                maps = torch.empty(images.shape[0], d.depth, d.heads, d.tokens, d.tokens, dtype=torch.float32, device=images.device)
                 self._maps[key] = maps
-        l0, l1 = eng.forward(images, train=False, attn_probs=maps, gray=gray)
+        l0, l1 = eng.forward(images, train=False, attn_probs=None if maps is None else ("image_major", maps), gray=gray)
         if l1 is not None:                         # DeiT eval: mean of the cls and dist heads (deit_models.py:233-238)
             l0 = (l0 + l1) / 2
         return l0, maps, eng.d.n_prefix
@@ -133,7 +134,7 @@ class EnsembleInference:
             lg, maps, n_prefix = self._member_forward(m, images, self.rollout, gray)
             logits.append(lg.float())
             if self.rollout:
-                row = ops.attention_rollout_row(maps, 0, self.head_fusion)          # class-token row of the rollout, [B,N]
+                row = ops.attention_rollout_row(maps, 0, self.head_fusion, image_major=True)   # class-token row of the rollout, [B,N]
                 g = int(math.isqrt(row.shape[1] - n_prefix))
                 grids.append(row[:, n_prefix:].reshape(-1, g, g))
         B = images.shape[0]

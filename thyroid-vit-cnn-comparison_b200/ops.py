@@ -341,15 +341,33 @@ def attention_rollout(probs, fusion: str = "mean"):
     return out
 
 
-def attention_rollout_row(probs, row: int = 0, fusion: str = "mean"):
-    """Row `row` of attention_rollout(probs, fusion) as fp32 [B,N], by L vector-matrix products (maps read once)."""
+def attention_rollout_row(probs, row: int = 0, fusion: str = "mean", image_major: bool = False):
+    """Row `row` of attention_rollout(probs, fusion) as fp32 [B,N], by L vector-matrix products (maps read once).
+    probs: contiguous fp32 [L,B,H,N,N], or [B,L,H,N,N] with image_major=True (one image's maps contiguous)."""
     _req(probs, f32, "rollout probs")
-    L, B, H, N, _ = probs.shape
+    if image_major:
+        B, L, H, N, _ = probs.shape
+        sl, sb = H * N * N, L * H * N * N
+    else:
+        L, B, H, N, _ = probs.shape
+        sl, sb = B * H * N * N, H * N * N
     fus = {"mean": 0, "max": 1, "min": 2}[fusion]
     out = torch.empty(B, N, dtype=f32, device=probs.device)
-    check(_lib.load().vitk_attention_rollout_row(probs.data_ptr(), out.data_ptr(), L, B, H, N, int(row), fus, _stream()),
+    check(_lib.load().vitk_attention_rollout_row(probs.data_ptr(), out.data_ptr(), sl, sb, L, B, H, N, int(row), fus, _stream()),
           "attention_rollout_row")
     return out
+
+
+def attention_probs(qkv, lse, B: int, N: int, H: int, scale: float, probs, batch_stride: int = 0):
+    """Eval-mode attention maps from the lse of a preceding attention_fwd: image b's [H,N,N] maps are written at
+    probs.data_ptr() + b * batch_stride elements (0: contiguous [B,H,N,N])."""
+    _req16(qkv, "attention qkv")
+    if probs.dtype != f32 or not probs.is_cuda:
+        raise TypeError("attention_probs: probs must be a CUDA fp32 tensor")
+    stride = int(batch_stride) if batch_stride else H * N * N
+    check(_lib.load().vitk_attention_probs(qkv.data_ptr(), _DT[qkv.dtype], lse.data_ptr(), probs.data_ptr(), stride, B, N, H, scale,
+                                           _stream()), "attention_probs")
+    return probs
 
 
 # --------------------------------------------------------------------------- on-device metrics

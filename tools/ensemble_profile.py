@@ -16,7 +16,7 @@ m = (vit.create_deit_tiny(img_size=224, in_chans=3, distilled=True) if name == "
 eng = m._ensure_engine()
 d = eng.d
 tiles = torch.randint(0, 65536, (B, 224, 224), dtype=torch.int32).to(torch.uint16).cuda()
-maps = torch.empty(d.depth, B, d.heads, d.tokens, d.tokens, device="cuda")
+maps = torch.empty(B, d.depth, d.heads, d.tokens, d.tokens, device="cuda")   # image-major
 
 
 def timed(fn, n=5):
@@ -34,10 +34,10 @@ def timed(fn, n=5):
 
 with torch.no_grad():
     t_plain = timed(lambda: eng.forward(tiles, train=False, gray=GraySpec()))
-    t_maps = timed(lambda: eng.forward(tiles, train=False, attn_probs=maps, gray=GraySpec()))
-    t_roll = timed(lambda: ops.attention_rollout_row(maps, 0, "mean"))
+    t_maps = timed(lambda: eng.forward(tiles, train=False, attn_probs=("image_major", maps), gray=GraySpec()))
+    t_roll = timed(lambda: ops.attention_rollout_row(maps, 0, "mean", image_major=True))
     qkv = torch.randn(B, d.tokens, 3 * d.dim, device="cuda").to(torch.float16)
-    pr = maps[0]
+    pr = torch.empty(B, d.heads, d.tokens, d.tokens, device="cuda")
     t_attn_maps = timed(lambda: ops.attention_fwd(qkv, B, d.tokens, d.heads, 0.125, probs=pr))
     t_attn = timed(lambda: ops.attention_fwd(qkv, B, d.tokens, d.heads, 0.125))
 print(f"{name} B={B}: eval forward {t_plain:.2f} ms | with map emission {t_maps:.2f} ms | rollout row {t_roll:.2f} ms | "

@@ -109,8 +109,8 @@ def main():
         cases["attn_probs"] = (lambda: ops.attention_fwd(qkv, B, T, H, scale, out=o16b, lse=lse, probs=probs), 4 * E + probs.numel() * 4,
                                6 * B * H * T * T * 64)
         if not want or "rollout_row" in want:
-            maps = torch.rand(12, B, H, T, T, device=DEV)
-            cases["rollout_row"] = (lambda: ops.attention_rollout_row(maps, 0, "mean"), maps.numel() * 4, 0)
+            maps = torch.rand(B, 12, H, T, T, device=DEV)       # image-major, as ensemble.EnsembleInference keeps them
+            cases["rollout_row"] = (lambda: ops.attention_rollout_row(maps, 0, "mean", image_major=True), maps.numel() * 4, 0)
         for nm, (P_, Ct_, C_) in {"bottleneck_b1": (B * 56 * 56, 256, 128), "bottleneck_b3": (B * 14 * 14, 1280, 768)}.items():
             if want and nm not in want:
                 continue
