@@ -26,8 +26,9 @@ if has newfull; then
 fi
 if has distill_launches; then
   CMD="python bench.py --mode distill --steps 1 --warmup 1 --no-graph --no-cpu-baseline"
-  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_distill.csv $CMD > $OUT/ncu_launches_distill.log 2>&1
-  python tools/ncu_summary.py launches $OUT/launches_distill.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv $CMD" > $OUT/ncu_launch_summary_distill.csv
+  # the timed region only (bench.py brackets it with the NVTX range "timed"): the teacher's set-up casts ~1500 tensors first
+  timeout 300 ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_distill.csv $CMD > $OUT/ncu_launches_distill.log 2>&1
+  python tools/ncu_summary.py launches $OUT/launches_distill.csv "ncu --nvtx --nvtx-include timed/ --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv $CMD" > $OUT/ncu_launch_summary_distill.csv
   rm -f $OUT/launches_distill.csv
 fi
 if has kbench; then
