@@ -366,3 +366,57 @@ def test_product_side_kfold_reproduces_reference_fixture_and_pins_5fold(tmp_path
     assert (tmp_path / "splits" / "split_fold_3.json").exists()
     with pytest.raises(ValueError):
         kfold.generate_kfold_splits(labels, 2)
+
+
+def _ens_worker(rank, world, port, tmp):
+    """EnsembleInference host logic on gloo: fold sharding, the shape hint for a rank that owns no fold, gather order.
+    The member forward and the probability mix are replaced by CPU stand-ins (the real ones are CUDA kernels)."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from thyroid_vit_cnn_comparison_b200 import ensemble, ops as _ops
+
+    class Net(torch.nn.Module):                       # what _inner() / the shape hint read
+        num_classes, num_patches = 2, 16
+
+        def __init__(self, fold):
+            super().__init__()
+            self.fold = fold
+
+        def _ensure_engine(self):
+            return None
+
+    class Ens(ensemble.EnsembleInference):
+        def _member_forward(self, model, images, want_maps, gray=None):
+            B = images.shape[0]
+            logits = torch.full((B, 2), float(model.fold)) + torch.arange(B).view(-1, 1) * torch.tensor([0.5, -0.5])
+            maps = torch.full((B, 17), float(model.fold)) if want_maps else None
+            return logits, maps, 1
+
+    _ops.ensemble_probs = lambda full, w: ((full.softmax(-1) * w.view(-1, 1, 1)).sum(0), (full.softmax(-1) * w.view(-1, 1, 1)).sum(0).argmax(1))
+    _ops.attention_rollout_row = lambda maps, row, fusion, image_major=False: maps
+    out = {}
+    for F in (5, 1):                                  # F = 1 with two ranks: rank 1 owns nothing and only joins the gather
+        mine = parallel.shard_folds(F, rank, world)
+        ens = Ens([Net(f) for f in mine], num_folds=F, rollout=True)
+        images = torch.zeros(3, 1, 8, 8)
+        images.__class__ = type("FakeCuda", (torch.Tensor,), {"is_cuda": property(lambda self: True)})
+        res = ens(images)
+        out[F] = (res["logits"].clone(), res["preds"].clone(), res["rollout"].clone(), mine)
+    torch.save(out, Path(tmp) / f"e{rank}.pt")
+    dist.destroy_process_group()
+
+
+def test_ensemble_inference_fold_sharding_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_ens_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"e{r}.pt", weights_only=False) for r in range(2))
+    for F in (5, 1):
+        l0, p0, g0, m0 = r0[F]
+        l1, p1, g1, m1 = r1[F]
+        assert torch.equal(l0, l1) and torch.equal(p0, p1) and torch.equal(g0, g1)          # identical on every rank
+        assert l0.shape == (F, 3, 2) and g0.shape == (F, 3, 4, 4)
+        for f in range(F):                                                                  # fold order restored after the gather
+            assert torch.all(l0[f, 0] == float(f)) and torch.all(g0[f] == float(f))
+    assert r0[5][3] == [0, 2, 4] and r1[5][3] == [1, 3] and r0[1][3] == [0] and r1[1][3] == []
