@@ -1025,15 +1025,30 @@ bool pair_mode_enabled() {
   return on;
 }
 
-// Pick the N tile: the widest of {256,192,128,64} that tiles N with the least padding.
-int pick_bn(int N, bool with_colsum) {
+// Pick the N tile.  A persistent grid of `units` CTAs walks m_tiles x n_tiles tiles in rounds, and the time of a tile is
+// ~(50 + BN) column-units (fitted on B200 at K = 192: 1.44 / 2.12 / 3.07 us per round for BN = 64 / 128 / 192 -- a fixed
+// hand-off cost plus an epilogue proportional to the width), so the candidate with the smallest rounds x (50 + BN) wins:
+// e.g. N = 768 at M = 50688 takes 9 rounds of BN = 256 (1188 tiles on 148 SMs: the 9th round runs 4 tiles) but 11 fuller
+// rounds of BN = 192 -- measured 56.4 -> 52.3 us (fc1 + GELU) and 52.3 -> 48.2 us (dGELU dgrad).  Ties go to the wider tile.
+// Without M (split-K accumulate GEMMs pick their split afterwards) the widest tile with the least padding is taken.
+int pick_bn(int N, int M, bool balance) {
+  static const int forced = [] {            // VITK_GEMM_BN=64|128|192|256: experiments only
+    const char* e = getenv("VITK_GEMM_BN");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced == 64 || forced == 128 || forced == 192 || forced == 256) return forced;
   const int cands[4] = {256, 192, 128, 64};
   int best = 64;
   long best_cost = -1;
+  const long units = num_sms();
+  const long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   for (int c : cands) {
-    (void)with_colsum;  // BN = 256 with the 16 column-sum columns runs on a single accumulator stage (272 of 512 columns)
-    const long tiles = (N + c - 1) / c;
-    const long cost = tiles * c;  // padded width; ties -> wider tile (listed first)
+    const long n_tiles = (N + c - 1) / c;
+    long cost = n_tiles * c;  // padded width
+    if (balance) {
+      const long rounds = (m_tiles * n_tiles + units - 1) / units;
+      cost = rounds * (50 + c);
+    }
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = c;
@@ -1092,7 +1107,7 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
     VITK_CHECK_ARG(a->epilogue == VITK_EPI_ATOMIC_ADD && out_fp32 && a->bias == nullptr && a->residual == nullptr && a->ldo % 4 == 0,
                    "vitk_gemm: colsum_out needs the split-K accumulate epilogue (fp32 out, no bias / residual)");
 
-  const int bn = pick_bn(a->N, a->colsum_out != nullptr);
+  const int bn = pick_bn(a->N, a->M, a->epilogue != VITK_EPI_ATOMIC_ADD && a->M > 4 * BLOCK_M);
   const int num_kblocks = (a->K + BLOCK_K - 1) / BLOCK_K;
   int split_k = a->split_k;
   bool pair_ok = pair_mode_enabled() && (bn == 256 || bn == 128) && a->M > BLOCK_M && (num_sms() % 2 == 0);
