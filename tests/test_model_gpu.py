@@ -458,8 +458,12 @@ def test_forward_features_matches_oracle(name):
     assert rel_l2(e.cpu(), ref[:, 0]) < 2e-3
     assert model.blocks[0].attn.attention_maps is not None                   # eval-mode maps are stored here too (:455-466)
     model.train()
-    with pytest.raises(NotImplementedError):
-        model.forward_features(x.cuda())                                     # training goes through forward()
+    if cfg.is_deit:
+        with pytest.raises(NotImplementedError):
+            model.forward_features(x.cuda())                                 # the token sequence is inference-only
+    else:
+        tf, _ = model.forward_features(x.cuda())                             # the base class's feature trains (test_round2_gpu)
+        assert tf.requires_grad and rel_l2(tf.detach().cpu(), ref[:, 0]) < 2e-3
 
 
 def _gpu_drop_masks(m, B):

@@ -484,3 +484,33 @@ def test_drop_path_and_patch_embed_stand_alone():
     assert tok.shape == (2, 16, 64) and q.shape == (2, 16) and (q >= 0).all() and (q <= 1).all()
     tok2, q2 = V.PatchEmbed(img_size=64, patch_size=16, in_chans=1, embed_dim=64, quality_aware=False).cuda()(torch.rand(2, 1, 64, 64, device=DEV))
     assert q2 is None
+
+
+@pytest.mark.parametrize("variant", ["cls", "gap_rep"])
+def test_forward_features_trains_with_autograd(variant):
+    """vision_transformer_base.py:440-479 in training mode: the pre-head feature carries gradients into the encoder (a custom
+    head on top of forward_features); every encoder gradient against the oracle's autograd through the same feature."""
+    kw = dict(pool_type="gap", representation_size=64) if variant == "gap_rep" else {}
+    cfg = O.VitConfig(img_size=64, embed_dim=64, depth=2, num_heads=1, is_deit=False, distilled=False,
+                      pool_type=kw.get("pool_type", "cls"), representation_size=kw.get("representation_size", 0))
+    model, sd = build(cfg, 13)
+    model.train()
+    x, _ = O.seeded_batch(cfg, 6, 13)
+    # a feature gradient of the size a mean-reduced loss produces (an O(1) gradient times the initial loss scale 65536 would
+    # overflow fp16 and -- GradScaler semantics -- zero this step's gradients while the scale halves)
+    proj = torch.randn(64, generator=torch.Generator().manual_seed(1)) * 1e-3
+    model.zero_grad()
+    feats, q = model.forward_features(x.cuda())
+    assert q is None and feats.shape == (6, 64) and feats.requires_grad
+    (feats * proj.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.pooled_features(leaves, O.forward_tokens(leaves, x, cfg), cfg)
+    (ref * proj).sum().backward()
+    assert (feats.detach().cpu() - ref.detach()).abs().max().item() < LOGIT_TOL
+    for n, p in model.named_parameters():
+        g = leaves[n].grad
+        if g is None:
+            assert p.grad is None or n.startswith("head") or p.grad.abs().sum().item() == 0, n    # the head is not on this path
+            continue
+        assert rel_l2(p.grad, g) < GRAD_TOL, (n, rel_l2(p.grad, g))

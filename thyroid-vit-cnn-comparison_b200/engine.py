@@ -283,7 +283,7 @@ class VitEngine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, images: torch.Tensor, train: bool, attn_probs=None, features: Optional[dict] = None,
-                gray: Optional["GraySpec"] = None):
+                gray: Optional["GraySpec"] = None, features_only: bool = False):
         """gray: when given, `images` are single-channel tiles [B,H,W] / [B,1,H,W] (fp32 in [0,1], raw uint16, fp16 or
         bf16) that the loader would have replicated to `chans` channels and normalised (vit_transforms.py:381-393).
         attn_probs (inference only): a list that receives one fp32 [B,H,T,T] tensor per block, or a preallocated
@@ -372,6 +372,10 @@ class VitEngine:
             pooled = torch.empty(d.n_out, B, D, dtype=torch.float32, device=self.device)
             features["pooled"] = pooled
             features["x_last"] = x_last.view(B, T, D)
+        if features_only:
+            # training-mode forward_features (vision_transformer_base.py:440-479): stop before the head; the saved state lets
+            # backward_features() start from the gradient of the pre-head feature (norm -> pool -> pre_logits, fp32 tail kernels)
+            return self._tail_fwd(ws, x_last.view(B, T, D), train, features, with_head=False), None
         if d.pool is not None or d.rep:
             return self._tail_fwd(ws, x_last.view(B, T, D), train, features), None
         l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
@@ -386,7 +390,7 @@ class VitEngine:
     def _tail_range(self) -> Tuple[int, int]:
         return self.d.pool if self.d.pool is not None else (0, 1)
 
-    def _tail_fwd(self, ws: Workspace, x_last: torch.Tensor, train: bool, features: Optional[dict]) -> torch.Tensor:
+    def _tail_fwd(self, ws: Workspace, x_last: torch.Tensor, train: bool, features: Optional[dict], with_head: bool = True) -> torch.Tensor:
         """norm -> pool over a token range -> pre_logits -> head (vision_transformer_base.py:468-486) for the constructor
         options outside the fused class-token kernel: fp32 throughout, a few hundred KB per step."""
         t0, t1 = self._tail_range()
@@ -394,17 +398,19 @@ class VitEngine:
         z = pooled
         if self.d.rep:
             z = ops.dense_fwd(pooled, self.p("pre_logits.0.weight"), self.p("pre_logits.0.bias"), act=1)
-        logits = ops.dense_fwd(z, self.p("head.weight"), self.p("head.bias"), act=0)
         if features is not None:
             features["pooled"] = z.unsqueeze(0)       # forward_features returns the pre-head feature (after pre_logits)
         if train:
             ws.head_saved = (pooled, mean, rstd, z, x_last)
-        return logits
+        if not with_head:
+            return z
+        return ops.dense_fwd(z, self.p("head.weight"), self.p("head.bias"), act=0)
 
-    def _tail_bwd(self, ws: Workspace, dl0: torch.Tensor, dx: torch.Tensor, dcolsum, branch_scale, branch_drop) -> None:
+    def _tail_bwd(self, ws: Workspace, dl0: torch.Tensor, dx: torch.Tensor, dcolsum, branch_scale, branch_drop,
+                  from_features: bool = False) -> None:
         pooled, mean, rstd, z, x_last = ws.head_saved
         t0, t1 = self._tail_range()
-        dz = ops.dense_bwd(dl0, None, z, self.p("head.weight"), self.g("head.weight"), self.g("head.bias"), act=0)
+        dz = dl0 if from_features else ops.dense_bwd(dl0, None, z, self.p("head.weight"), self.g("head.weight"), self.g("head.bias"), act=0)
         if self.d.rep:
             dz = ops.dense_bwd(dz, z, pooled, self.p("pre_logits.0.weight"), self.g("pre_logits.0.weight"),
                                self.g("pre_logits.0.bias"), act=1)
@@ -413,7 +419,11 @@ class VitEngine:
                           branch_drop=branch_drop)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, B: int, dl0: torch.Tensor, dl1: Optional[torch.Tensor]) -> None:
+    def backward_features(self, B: int, dz: torch.Tensor) -> None:
+        """Backward of a `features_only` training forward: dz = TRUE gradient of the pre-head feature [B, D | rep]."""
+        self.backward(B, dz, None, from_features=True)
+
+    def backward(self, B: int, dl0: torch.Tensor, dl1: Optional[torch.Tensor], from_features: bool = False) -> None:
         """Takes TRUE dlogits; accumulates every TRUE parameter gradient into flat.grads (no input gradient).
         Activation gradients in between are S-scaled 16-bit tensors."""
         d = self.d
@@ -422,7 +432,7 @@ class VitEngine:
         ws = self.workspace(B, True)
         if ws.head_saved is None:
             raise RuntimeError("backward() called without a preceding training forward()")
-        general_tail = d.pool is not None or bool(d.rep)
+        general_tail = d.pool is not None or bool(d.rep) or from_features
         two = d.n_out == 2
         u = self.grad_unscale
         dp = ws.dp if getattr(ws, "dp_active", False) else None
@@ -431,7 +441,8 @@ class VitEngine:
         dx, dx_alt = ws.dx[0], ws.dx[1]
         last_fc2_bias = self.g(f"blocks.{d.depth - 1}.mlp.fc2.bias")
         if general_tail:
-            self._tail_bwd(ws, dl0.contiguous(), dx, last_fc2_bias, rs(2 * d.depth - 1), self._site(3 + 3 * (d.depth - 1)))
+            self._tail_bwd(ws, dl0.contiguous(), dx, last_fc2_bias, rs(2 * d.depth - 1), self._site(3 + 3 * (d.depth - 1)),
+                           from_features=from_features)
         else:
             xhat, rstd = ws.head_saved
             ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),

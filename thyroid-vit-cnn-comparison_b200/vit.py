@@ -228,6 +228,31 @@ class _EncoderFn(torch.autograd.Function):
         return None, None, None
 
 
+class _FeaturesFn(torch.autograd.Function):
+    """Autograd node of a training-mode forward_features(): encoder + final norm + pooling + pre_logits, no head."""
+
+    @staticmethod
+    def forward(ctx, model, images, anchor):
+        eng = model._engine
+        z, _ = eng.forward(images, train=True, features_only=True)
+        eng.generation += 1
+        ctx.model, ctx.B, ctx.gen = model, images.shape[0], eng.generation
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        model = ctx.model
+        eng = model._engine
+        if ctx.gen != eng.generation:
+            raise RuntimeError("backward through a stale forward: the activation workspace holds a later forward "
+                               "(run forward/backward pairs in order)")
+        model._bind_grads()
+        eng.backward_features(ctx.B, dz.contiguous().float())
+        if eng.fused_optimizer is None or eng.fused_optimizer() is None:
+            eng.amp_update()
+        return None, None, None
+
+
 class VisionTransformerBase(_Base):
     """Same constructor surface as the reference base class (vision_transformer_base.py:288-402)."""
 
@@ -453,8 +478,9 @@ class VisionTransformerBase(_Base):
     def _features(self, x: torch.Tensor) -> dict:
         """Inference-only encoder pass that also returns the pre-head features (no autograd graph)."""
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("forward_features is inference-only in the sm_100a path (call it under "
-                                      "torch.no_grad() or model.eval()); training goes through forward()")
+            raise NotImplementedError("DeiT.forward_features (the normalised token sequence) and extract_features are "
+                                      "inference-only in the sm_100a path (call them under torch.no_grad() or model.eval()); "
+                                      "the base class's forward_features() and forward() train")
         self._check_supported()
         eng = self._ensure_engine()
         _require_cuda(x, type(self).__name__)
@@ -470,7 +496,18 @@ class VisionTransformerBase(_Base):
 
     def forward_features(self, x: torch.Tensor):
         """vision_transformer_base.py:440-479: (norm(x)[:, 0] as [B, D], quality_scores).  The quality branch is dead
-        code in the reference's forward (its scores never reach the tokens), so None is returned for it."""
+        code in the reference's forward (its scores never reach the tokens), so None is returned for it.  In training mode
+        with gradients enabled the feature carries an autograd edge into the encoder (a custom head can be trained on top)."""
+        if self.training and torch.is_grad_enabled() and type(self).forward_features is VisionTransformerBase.forward_features:
+            B, C, H, W = x.shape
+            if self.patch_embed.strict_img_size:
+                assert H == self.patch_embed.img_size and W == self.patch_embed.img_size, \
+                    f"Input size ({H}x{W}) doesn't match expected size ({self.patch_embed.img_size}x{self.patch_embed.img_size})"
+            eng = self._ensure_engine()
+            _require_cuda(x, type(self).__name__)
+            self._sync_shadow()
+            anchor = eng.flat.params.new_zeros((), requires_grad=True)
+            return _FeaturesFn.apply(self, x, anchor), None
         return self._features(x)["pooled"][0], None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
