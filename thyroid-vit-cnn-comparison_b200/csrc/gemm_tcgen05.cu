@@ -41,8 +41,21 @@ __device__ long long g_vitk_dbg2[8 * 4 * 8];  // [tile][unit][event] of epilogue
   do {                                                                                                       \
     if (KNOB(64) && blockIdx.x == 0 && warp == 2 && lane == 0 && (t) < 8 && (u) < 4) g_vitk_dbg2[((t) * 4 + (u)) * 8 + (ev)] = clock64(); \
   } while (0)
+// per-CTA wall-clock stamps (globaltimer ns): 0 kernel entry, 1 set-up done, 2 last epilogue done, 3 exit
+__device__ unsigned long long g_vitk_dbg3[256 * 4];
+#define DBG_G(ev)                                                                  \
+  do {                                                                             \
+    if (KNOB(64) && blockIdx.x < 256) {                                            \
+      unsigned long long t_;                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+      g_vitk_dbg3[blockIdx.x * 4 + (ev)] = t_;                                     \
+    }                                                                              \
+  } while (0)
 #else
 #define KNOB(x) false
+#define DBG_G(ev) \
+  do {            \
+  } while (0)
 #define DBG_UNIT(t, u, ev) \
   do {                     \
   } while (0)
@@ -510,6 +523,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DBG_G(0);
   const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
   const int total_tiles = tiles_mn * p.num_splits;
 
@@ -549,6 +563,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_G(1);
 
   // tile -> (m, n, split): n fastest (CTAs running together share the A rows through L2), split slowest.  Every role
   // walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...: the (split, mt, nt) counter advances in mixed radix by the
@@ -927,6 +942,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
       if (warp == 2 && lane == 0) DBG_STAMP(2, tcount, 2);
     }
+    if (warp == 2 && lane == 0) DBG_G(2);
     if (elect_one()) tma_store_wait_all();  // outstanding TMA stores must complete before the CTA (and its smem) goes away
   }
 
@@ -937,6 +953,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (CTA2) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
     else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (threadIdx.x == 0) DBG_G(3);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1066,6 +1083,9 @@ using namespace vitk;
 #ifdef VITK_GEMM_KNOBS
 extern "C" int vitk_debug_read(long long* dst) {
   return (int)cudaMemcpyFromSymbol(dst, g_vitk_dbg, sizeof(g_vitk_dbg));
+}
+extern "C" int vitk_debug_read3(long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, g_vitk_dbg3, sizeof(g_vitk_dbg3));
 }
 extern "C" int vitk_debug_read2(long long* dst) {
   return (int)cudaMemcpyFromSymbol(dst, g_vitk_dbg2, sizeof(g_vitk_dbg2));

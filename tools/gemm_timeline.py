@@ -39,6 +39,14 @@ else:
 for _ in range(3):
     fn()
 torch.cuda.synchronize()
+ts = []
+for _ in range(8):   # event-timed duration of the same launch (operands hot in L2), for the cycles -> time conversion
+    torch.cuda._sleep(400000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+ts.sort()
+print(f"event-timed launch (hot L2): min {ts[0]:.1f} med {ts[4]:.1f} us")
 lib = _lib.load()
 buf = (C.c_longlong * (3 * 64 * 4))()
 lib.vitk_debug_read.argtypes = [C.c_void_p]
@@ -63,3 +71,17 @@ for t in range(2, 6):
         e = [w[((t * 4 + u) * 8) + i] for i in range(6)]
         if e[0] == 0 or e[5] == 0: continue
         print(f"  tile {t} unit {u}: start {e[0]-t0:8d} | {e[1]-e[0]:5d} | {e[2]-e[1]:5d} | {e[3]-e[2]:5d} | {e[4]-e[3]:5d} | {e[5]-e[4]:5d}")
+
+buf3 = (C.c_longlong * (256 * 4))()
+lib.vitk_debug_read3.argtypes = [C.c_void_p]
+assert lib.vitk_debug_read3(buf3) == 0
+g3 = [[buf3[c * 4 + e] for e in range(4)] for c in range(256) if buf3[c * 4] != 0]
+t_first = min(r[0] for r in g3)
+t_last = max(r[3] for r in g3)
+import statistics as st
+print(f"wall clock over {len(g3)} CTAs (globaltimer ns): first entry -> last exit {t_last - t_first}")
+for name, f in (("entry skew (entry - first entry)", lambda r: r[0] - t_first), ("set-up (entry -> set-up done)", lambda r: r[1] - r[0]),
+                ("tile loop (set-up done -> last epilogue)", lambda r: r[2] - r[1]), ("teardown (last epilogue -> exit)", lambda r: r[3] - r[2]),
+                ("exit slack (last exit - exit)", lambda r: t_last - r[3])):
+    v = sorted(f(r) for r in g3)
+    print(f"  {name:44s} min {v[0]:6d}  med {v[len(v)//2]:6d}  max {v[-1]:6d}")
