@@ -286,6 +286,10 @@ def workload_config(args, model: str):
             "input": ("single-channel uint16 tiles [B,224,224]; /65535 + replication to 3 channels fused into the patch-matrix kernel"
                       if args.input == "gray" else "fp32 [B,3,224,224]"),
             "parallelism": f"dp{n}", "mode": args.mode, "drop_rate": args.drop_rate, "drop_path_rate": args.drop_path_rate,
+            "last_block": ("dense (VITK_DENSE_LAST_BLOCK=1)" if os.environ.get("VITK_DENSE_LAST_BLOCK", "0") == "1" or args.drop_rate > 0
+                           or args.drop_path_rate > 0 else
+                           "attn.proj / norm2 / Mlp of block L-1 run on the rows the classifier reads (cls, dist): same logits, loss and "
+                           "gradients as the dense form, which VITK_DENSE_LAST_BLOCK=1 selects"),
             "l2": "no flush needed: the step's working set (activations > 3 GB) is far larger than the 126 MB L2"}
 
 
@@ -392,6 +396,8 @@ class KernelProfile:
         self._wrap("tiles_to_patches", generic("tiles_to_patches",
                                                lambda tiles, C, P, **k: tiles.numel() * (tiles.element_size() + 2 * C)))
         self._wrap("tokens_bwd", generic("tokens_bwd", lambda dx, *a, **k: dx.numel() * 6))
+        self._wrap("gather_rows", generic("gather_rows", lambda src, n, out, **k: 2 * out.numel() * out.element_size()))
+        self._wrap("expand_rows", generic("expand_rows", lambda src, n, out, **k: out.numel() * out.element_size()))
         self._wrap("head_fwd", generic("head_fwd", lambda x, *a, **k: 0))
         self._wrap("head_bwd", generic("head_bwd", lambda *a, **k: a[8].numel() * 6))
         self._wrap("loss_fwd_bwd", generic("loss", lambda *a, **k: 0))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 21
+#define VITK_ABI_VERSION 22
 
 typedef enum {
   VITK_OK = 0,
@@ -202,6 +202,15 @@ int vitk_prefix_tokens_fwd(float* x, const float* cls_tok, const float* dist_tok
 int vitk_tokens_bwd(const float* dx, float* dpos, float* dcls, float* ddist, void* dpatch16,
                     int32_t dpatch_dtype, float* dbias_patch, const float* grad_unscale, int32_t B,
                     int32_t tokens_per_img, int32_t dim, int32_t n_prefix, const vitk_dropout* drop, void* stream);
+
+/* Leading rows of every image, compact <-> dense.  The classifier reads x[:, 0] (and x[:, 1] for the distillation head) of the
+ * last block's output only (vision_transformer_base.py:474-479, deit_models.py:224-235), so that block's attn.proj, norm2 and Mlp
+ * (vision_transformer_base.py:274-285) need the first n tokens of each image and nothing else: the engine runs them on B*n rows.
+ * gather: dst[b, j, :] = src[b, j, :] for j < n (src is [B, T, row_bytes], dst is [B, n, row_bytes]);
+ * expand: dst[b, j, :] = j < n ? src[b, j, :] : 0 (src [B, n, row_bytes], dst [B, T, row_bytes]) -- the gradient of those rows
+ * placed back into the dense tensor the rest of the backward continues from.  row_bytes % 16 == 0, 16-byte aligned bases. */
+int vitk_gather_rows(const void* src, void* dst, int32_t B, int32_t tokens_per_img, int32_t n, int64_t row_bytes, void* stream);
+int vitk_expand_rows(const void* src, void* dst, int32_t B, int32_t tokens_per_img, int32_t n, int64_t row_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Final norm + classification heads on the pooled rows only --

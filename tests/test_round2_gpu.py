@@ -514,3 +514,54 @@ def test_forward_features_trains_with_autograd(variant):
             assert p.grad is None or n.startswith("head") or p.grad.abs().sum().item() == 0, n    # the head is not on this path
             continue
         assert rel_l2(p.grad, g) < GRAD_TOL, (n, rel_l2(p.grad, g))
+
+
+# ------------------------------------------------------------------ last block on the classifier's rows
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,n,dt", [(5, 198, 2, torch.float16), (3, 197, 1, torch.float32), (256, 198, 2, torch.float32)])
+def test_gather_and_expand_rows(B, T, n, dt):
+    """vitk_gather_rows / vitk_expand_rows: leading token rows of every image, compact <-> dense (bit-exact copies)."""
+    D = 192
+    x = torch.randn(B, T, D, device="cuda").to(dt)
+    c = torch.empty(B, n, D, dtype=dt, device="cuda")
+    ops.gather_rows(x, n, c)
+    assert torch.equal(c, x[:, :n])
+    dense = torch.full((B, T, D), 7.0, dtype=dt, device="cuda")
+    ops.expand_rows(c, n, dense)
+    assert torch.equal(dense[:, :n], x[:, :n]) and dense[:, n:].abs().max().item() == 0.0
+    with pytest.raises(ValueError):
+        ops.gather_rows(x, n, torch.empty(B, n + 1, D, dtype=dt, device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deit", [True, False])
+def test_last_block_on_classifier_rows_equals_dense(deit):
+    """engine.cls_rows_last_block: the last block's attn.proj / norm2 / Mlp on tokens 0..n_out-1 only gives the logits and
+    every parameter gradient of the dense computation (vision_transformer_base.py:274-285,474-479; deit_models.py:224-235)."""
+    from thyroid_vit_cnn_comparison_b200 import vit
+    kw = dict(img_size=64, patch_size=16, in_chans=3, num_classes=6, embed_dim=128, depth=3, num_heads=2, mlp_ratio=4.0)
+    outs = {}
+    for mode in ("rows", "dense"):
+        torch.manual_seed(11)
+        m = (vit.DeiT(distilled=True, **kw) if deit else vit.VisionTransformer(**kw)).cuda().train()
+        eng = m._ensure_engine()
+        eng.cls_rows_last_block = mode == "rows"
+        x = torch.randn(7, 3, 64, 64, generator=torch.Generator().manual_seed(5)).cuda()
+        out = m(x)
+        logits = torch.cat([o for o in out], 1) if isinstance(out, tuple) else out
+        w = torch.randn(logits.shape, generator=torch.Generator().manual_seed(6)).cuda() * 1e-2
+        (logits * w).sum().backward()
+        torch.cuda.synchronize()
+        assert eng.workspace(7, True).pruned == (mode == "rows")
+        outs[mode] = (logits.detach().float().cpu(), {n_: p.grad.detach().float().cpu().clone() for n_, p in m.named_parameters()
+                                                       if p.grad is not None})
+    la, ga = outs["rows"]
+    lb, gb = outs["dense"]
+    assert torch.equal(la, lb)                                      # the same rows through the same kernels: bit-identical logits
+    assert set(ga) == set(gb)
+    for n_ in gb:
+        den = gb[n_].norm().item()
+        if den == 0.0:
+            assert ga[n_].abs().max().item() == 0.0, n_
+        else:
+            assert (ga[n_] - gb[n_]).norm().item() / den < 2e-3, (n_, (ga[n_] - gb[n_]).norm().item() / den)

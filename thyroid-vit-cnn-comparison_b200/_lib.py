@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 21
+ABI_VERSION = 22
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -62,6 +62,8 @@ SIGNATURES = {
     "vitk_patchify_hwc": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "vitk_prefix_tokens_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p]),
     "vitk_tokens_bwd": (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 2 + [c_int] * 4 + [c_void_p, c_void_p]),
+    "vitk_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.c_int64, c_void_p]),
+    "vitk_expand_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.c_int64, c_void_p]),
     "vitk_head_fwd": (c_int, [c_void_p] * 12 + [c_int] * 5 + [c_float, c_void_p]),
     "vitk_head_bwd": (c_int, [c_void_p] * 10 + [c_int] + [c_void_p] * 10 + [c_int] * 5 + [c_void_p]),
     "vitk_pool_norm_fwd": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_float, c_void_p]),

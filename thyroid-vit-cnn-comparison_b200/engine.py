@@ -30,6 +30,7 @@ from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
+import os
 import torch
 
 from . import _lib, ops
@@ -165,6 +166,15 @@ class Workspace:
             self.delta = e(B, H, T, dt=f32)
             self.dpatch = e(B * d.n_patches, D)
         self.head_saved = None
+        # the last block's attn.proj / norm2 / Mlp on the rows the classifier reads (tokens 0..n_out-1 of every image)
+        R = B * d.n_out
+        self.c_ao, self.c_xin, self.c_xmid, self.c_xout = e(R, D), e(R, D, dt=f32), e(R, D, dt=f32), e(R, D, dt=f32)
+        self.c_xn2, self.c_stats = e(R, D), e(2, R, dt=f32)
+        self.c_dact, self.c_act = e(R, d.hidden), e(R, d.hidden)
+        self.pruned = False
+        if train:
+            self.c_dx = [e(R, D, dt=f32) for _ in range(2)]
+            self.c_dx16, self.c_dxn, self.c_dao, self.c_dpre = e(R, D), e(R, D), e(R, D), e(R, d.hidden)
 
     def nbytes(self) -> int:
         tot = 0
@@ -216,6 +226,13 @@ class VitEngine:
         self.attn_drop_rate = 0.0       # Attention.attn_drop (:184): site ATTN_SITE0 + l, element ((b*H + h)*T + q)*Tpad + key
         self.drop_seed = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.frozen = set()             # flat-buffer entries that are not trained (a sinusoidal pos_embed buffer)
+        # The classifier reads x[:, 0] (and x[:, 1] for the distillation head) of the last block's output and nothing else
+        # (vision_transformer_base.py:474-479, deit_models.py:224-235), so with class-token pooling the last block's attn.proj,
+        # norm2 and Mlp -- forward and backward -- only matter on those rows: they run on B*n_out rows instead of B*T.  Logits,
+        # loss and every parameter gradient are unchanged (the other rows' outputs are never read, their gradients are exactly
+        # zero).  Off whenever something does read the other rows or indexes them: token pooling ('gap'), pre_logits tails,
+        # forward_features / `features`, dropout and stochastic depth (their masks are indexed by dense row).
+        self.cls_rows_last_block = os.environ.get("VITK_DENSE_LAST_BLOCK", "0") != "1"
         proj = "patch_embed.proj.1." if dims.patch_linear else "patch_embed.proj."
         self.patch_w, self.patch_b = proj + "weight", proj + "bias"
 
@@ -335,6 +352,11 @@ class VitEngine:
         ops.prefix_tokens_fwd(x0.view(B, T, D), self.p("cls_token") if d.n_prefix >= 1 else None,
                               self.p("dist_token") if d.n_prefix == 2 else None, self.p("pos_embed"), d.n_prefix,
                               drop=self._site(0))
+        prune = (self.cls_rows_last_block and d.pool is None and not d.rep and features is None and not features_only
+                 and dp is None and not self._drop_on and d.n_prefix >= d.n_out)
+        ws.pruned = prune
+        nr = d.n_out
+        R = B * nr
         for l in range(d.depth):
             s = l if train else 0
             pre = f"blocks.{l}."
@@ -358,6 +380,18 @@ class VitEngine:
             if probs_im is not None:
                 ops.attention_probs(ws.qkv[s], ws.lse[s], B, T, d.heads, self.scale, probs_im[:, l],
                                     batch_stride=d.depth * d.heads * T * T)
+            if prune and l == d.depth - 1:
+                ops.gather_rows(ws.ao[s].view(B, T, D), nr, ws.c_ao)
+                ops.gather_rows(x_in.view(B, T, D), nr, ws.c_xin)
+                ops.gemm(ws.c_ao, self.w(pre + "attn.proj.weight"), R, D, D, out=ws.c_xmid, bias=self.p(pre + "attn.proj.bias"),
+                         residual=ws.c_xin)
+                ops.layernorm_fwd(ws.c_xmid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), eps=d.eps, y=ws.c_xn2,
+                                  mean=ws.c_stats[0], rstd=ws.c_stats[1])
+                ops.gemm(ws.c_xn2, self.w(pre + "mlp.fc1.weight"), R, d.hidden, D, out=ws.c_dact, out2=ws.c_act,
+                         bias=self.p(pre + "mlp.fc1.bias"), epilogue=_lib.EPI_GELU)
+                ops.gemm(ws.c_act, self.w(pre + "mlp.fc2.weight"), R, D, d.hidden, out=ws.c_xout, bias=self.p(pre + "mlp.fc2.bias"),
+                         residual=ws.c_xmid)
+                continue
             ops.gemm(ws.ao[s], self.w(pre + "attn.proj.weight"), M, D, D, out=x_mid, bias=self.p(pre + "attn.proj.bias"), residual=x_in,
                      row_scale=rs(2 * l), drop=self._site(1 + 3 * l))
             ops.layernorm_fwd(x_mid, self.p(pre + "norm2.weight"), self.p(pre + "norm2.bias"), eps=d.eps, y=ws.xn2[s], mean=st[2], rstd=st[3])
@@ -378,7 +412,8 @@ class VitEngine:
             return self._tail_fwd(ws, x_last.view(B, T, D), train, features, with_head=False), None
         if d.pool is not None or d.rep:
             return self._tail_fwd(ws, x_last.view(B, T, D), train, features), None
-        l0, l1, xhat, rstd = ops.head_fwd(x_last.view(B, T, D), self.p("norm.weight"), self.p("norm.bias"),
+        l0, l1, xhat, rstd = ops.head_fwd(ws.c_xout.view(B, nr, D) if prune else x_last.view(B, T, D),
+                                          self.p("norm.weight"), self.p("norm.bias"),
                                           self.p("head.weight"), self.p("head.bias"),
                                           self.p("head_dist.weight") if two else None,
                                           self.p("head_dist.bias") if two else None, d.n_out, eps=d.eps, pooled=pooled)
@@ -445,18 +480,48 @@ class VitEngine:
                            from_features=from_features)
         else:
             xhat, rstd = ws.head_saved
+            pruned = bool(ws.pruned)
             ops.head_bwd(dl0.contiguous(), dl1.contiguous() if two else None, xhat, rstd, self.p("norm.weight"), self.p("norm.bias"),
-                         self.p("head.weight"), self.p("head_dist.weight") if two else None, dx, ws.dx16,
+                         self.p("head.weight"), self.p("head_dist.weight") if two else None,
+                         ws.c_dx[0] if pruned else dx, ws.c_dx16 if pruned else ws.dx16,
                          self.g("norm.weight"), self.g("norm.bias"), self.g("head.weight"), self.g("head.bias"),
                          self.g("head_dist.weight") if two else None, self.g("head_dist.bias") if two else None,
-                         last_fc2_bias, T, d.n_out, loss_scale=self.loss_scale, branch_scale=rs(2 * d.depth - 1),
-                         branch_drop=self._site(3 + 3 * (d.depth - 1)))
+                         last_fc2_bias, d.n_out if pruned else T, d.n_out, loss_scale=self.loss_scale,
+                         branch_scale=rs(2 * d.depth - 1), branch_drop=self._site(3 + 3 * (d.depth - 1)))
         ws.head_saved = None
         self._notify("head")
         for l in range(d.depth - 1, -1, -1):
             pre = f"blocks.{l}."
             st = ws.stats[l]
             x_in, x_mid = ws.x[2 * l], ws.x[2 * l + 1]
+            if l == d.depth - 1 and not general_tail and ws.pruned:
+                # the last block's MLP and attn.proj on the classifier's rows only (see cls_rows_last_block); the gradient of
+                # those rows then goes back into dense, otherwise-zero tensors for the attention backward and norm1
+                nr = d.n_out
+                R = B * nr
+                self._wgrad(ws.c_dx16, ws.c_act, pre + "mlp.fc2.weight", R)
+                ops.gemm(ws.c_dx16, self.w(pre + "mlp.fc2.weight"), R, d.hidden, D, b_mn=True, out=ws.c_dpre, aux=ws.c_dact,
+                         epilogue=_lib.EPI_DGELU)
+                self._wgrad(ws.c_dpre, ws.c_xn2, pre + "mlp.fc1.weight", R, bias_name=pre + "mlp.fc1.bias")
+                ops.gemm(ws.c_dpre, self.w(pre + "mlp.fc1.weight"), R, D, d.hidden, b_mn=True, out=ws.c_dxn)
+                ops.layernorm_bwd(ws.c_dxn, ws.c_xmid, ws.c_stats[0], ws.c_stats[1], self.p(pre + "norm2.weight"),
+                                  self.g(pre + "norm2.weight"), self.g(pre + "norm2.bias"), dres=ws.c_dx[0], dx=ws.c_dx[1],
+                                  dx16=ws.c_dx16, dcolsum=self.g(pre + "attn.proj.bias"), unscale=u)
+                self._wgrad(ws.c_dx16, ws.c_ao, pre + "attn.proj.weight", R)
+                ops.gemm(ws.c_dx16, self.w(pre + "attn.proj.weight"), R, D, D, b_mn=True, out=ws.c_dao)
+                ops.expand_rows(ws.c_dao.view(B, nr, D), nr, ws.d_ao.view(B, T, D))
+                ops.expand_rows(ws.c_dx[1].view(B, nr, D), nr, dx.view(B, T, D))
+                ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta,
+                                  drop=self._attn_site(l))
+                self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M, bias_name=pre + "attn.qkv.bias")
+                ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
+                prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None
+                ops.layernorm_bwd(ws.dxn, x_in, st[0], st[1], self.p(pre + "norm1.weight"), self.g(pre + "norm1.weight"),
+                                  self.g(pre + "norm1.bias"), dres=dx, dx=dx_alt, dx16=ws.dx16 if l > 0 else None,
+                                  dcolsum=prev_bias, unscale=u)
+                dx, dx_alt = dx_alt, dx
+                self._notify(pre)
+                continue
             # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(norm2(x_mid))))
             self._wgrad(ws.dx16, ws.act[l], pre + "mlp.fc2.weight", M)
             ops.gemm(ws.dx16, self.w(pre + "mlp.fc2.weight"), M, d.hidden, D, b_mn=True, out=ws.d_pre, aux=ws.dact[l],

@@ -205,6 +205,24 @@ def tokens_bwd(dx, dpos, dcls, ddist, dpatch16, dbias, n_prefix: int, unscale=No
                                       n_prefix, _drop(drop), _stream()), "tokens_bwd")
 
 
+def gather_rows(src, n: int, out):
+    """out[b, j, :] = src[b, j, :] for j < n: the leading n token rows of every image ([B,T,D] -> [B,n,D], any 16/32-bit dtype)."""
+    B, T, D = src.shape
+    if not (src.is_contiguous() and out.is_contiguous() and out.dtype == src.dtype and out.numel() == B * n * D):
+        raise ValueError("gather_rows: contiguous [B,T,D] source and a same-dtype [B,n,D] destination expected")
+    check(_lib.load().vitk_gather_rows(src.data_ptr(), out.data_ptr(), B, T, n, D * src.element_size(), _stream()), "gather_rows")
+    return out
+
+
+def expand_rows(src, n: int, out):
+    """out[b, j, :] = src[b, j, :] for j < n, zero for the other token rows ([B,n,D] -> dense [B,T,D])."""
+    B, T, D = out.shape
+    if not (src.is_contiguous() and out.is_contiguous() and out.dtype == src.dtype and src.numel() == B * n * D):
+        raise ValueError("expand_rows: contiguous [B,n,D] source and a same-dtype dense [B,T,D] destination expected")
+    check(_lib.load().vitk_expand_rows(src.data_ptr(), out.data_ptr(), B, T, n, D * out.element_size(), _stream()), "expand_rows")
+    return out
+
+
 # --------------------------------------------------------------------------- heads
 def head_fwd(x, gamma, beta, W0, b0, W1, b1, n_heads: int, eps: float = 1e-5, pooled=None):
     """pooled (optional, fp32 [n_heads,B,dim]) receives norm(x)[:, h] -- the reference's forward_features output."""
