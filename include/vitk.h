@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 22
+#define VITK_ABI_VERSION 23
 
 typedef enum {
   VITK_OK = 0,
@@ -159,16 +159,20 @@ int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const f
  * bwd recomputes P from q,k and lse; delta = rowsum(dout*out) is computed internally into
  * `delta` (fp32 [B,H,N] scratch).
  * probs (optional, eval only): fp32 [B,H,N,N] attention maps (:186-188 `attention_maps`).
+ * q_rows (0 = every row): the caller needs only query rows 0..q_rows-1 of `out` / `lse` (forward; the other rows may be left
+ *   unwritten) resp. guarantees that `dout` is zero from row q_rows on (backward; dqkv is still complete: dQ is zero there and
+ *   dK / dV sum over the leading rows).  The last block of a class-token model: the classifier reads x[:, 0] (and x[:, 1]) only
+ *   (vision_transformer_base.py:474-479, deit_models.py:224-235).  Ignored when `probs` is requested.
  * ------------------------------------------------------------------------------------------ */
 int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, float* lse, float* probs, int32_t B,
-                       int32_t N, int32_t H, float scale, void* stream);
+                       int32_t N, int32_t H, float scale, int32_t q_rows, void* stream);
 /* The maps alone, from the lse a preceding vitk_attention_fwd wrote: probs + b * probs_batch_stride holds image b's
  * [H,N,N] maps (stride in elements; H*N*N = the contiguous [B,H,N,N] layout). */
 int vitk_attention_probs(const void* qkv, int32_t dtype, const float* lse, float* probs, int64_t probs_batch_stride,
                          int32_t B, int32_t N, int32_t H, float scale, void* stream);
 int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                        float* delta, void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H,
-                       float scale, void* stream);
+                       float scale, int32_t q_rows, void* stream);
 /* The same pair with nn.Dropout on the softmax output (Attention.attn_drop, vision_transformer_base.py:184), training mode
  * only: out = (P o M) V, M[b,h,q,key] = 0 | 1/(1-p) from the counter-based generator at element
  * ((b*H + h)*N + q)*Npad + key, Npad = N rounded up to 8 -- i.e. vitk_dropout_mask(seed, p, site, B*H*N, Npad)[:, :N];

@@ -565,3 +565,26 @@ def test_last_block_on_classifier_rows_equals_dense(deit):
             assert ga[n_].abs().max().item() == 0.0, n_
         else:
             assert (ga[n_] - gb[n_]).norm().item() / den < 2e-3, (n_, (ga[n_] - gb[n_]).norm().item() / den)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,q_rows", [(198, 3, 2), (197, 12, 1), (64, 2, 2), (198, 3, 70), (198, 3, 130)])
+def test_attention_leading_query_rows(N, H, q_rows):
+    """vitk_attention_fwd / _bwd with q_rows: the leading rows of out / lse equal the full forward's, and with dout zero from
+    row q_rows on the backward's dqkv equals the full backward's (bit-exact: the skipped chunks only ever add zeros)."""
+    B = 5
+    g = torch.Generator().manual_seed(N + H)
+    qkv = (torch.randn(B, N, 3 * H * 64, generator=g) * 0.5).cuda().half()
+    scale = 64 ** -0.5
+    out_f, lse_f = ops.attention_fwd(qkv, B, N, H, scale)
+    out_p = torch.full_like(out_f, float("nan"))
+    lse_p = torch.full_like(lse_f, float("nan"))
+    ops.attention_fwd(qkv, B, N, H, scale, out=out_p, lse=lse_p, q_rows=q_rows)
+    assert torch.equal(out_p[:, :q_rows], out_f[:, :q_rows]) and torch.equal(lse_p[:, :, :q_rows], lse_f[:, :, :q_rows])
+    dout = torch.zeros_like(out_f)
+    dout[:, :q_rows] = (torch.randn(B, q_rows, H * 64, generator=g) * 0.1).cuda().half()
+    full = ops.attention_bwd(qkv, out_f, dout, lse_f, B, N, H, scale)
+    part = ops.attention_bwd(qkv, out_p, dout, lse_p, B, N, H, scale, q_rows=q_rows)   # unwritten rows of out / lse hold NaNs
+    torch.cuda.synchronize()
+    assert torch.isfinite(part.float()).all()
+    assert torch.equal(part, full)

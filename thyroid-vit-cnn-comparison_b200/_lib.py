@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 22
+ABI_VERSION = 23
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -54,8 +54,8 @@ SIGNATURES = {
     "vitk_gemm": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "vitk_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 2 + [c_int64, c_int, c_float, c_void_p]),
     "vitk_layernorm_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 7 + [c_int] + [c_void_p] * 6 + [c_int64, c_int, c_void_p]),
-    "vitk_attention_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int, c_int, c_int, c_float, c_void_p]),
-    "vitk_attention_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]),
+    "vitk_attention_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "vitk_attention_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "vitk_attention_dropout_fwd": (c_int, [c_void_p] * 2 + [c_int] + [c_void_p] + [c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "vitk_attention_dropout_bwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p, c_void_p]),
     "vitk_patchify": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

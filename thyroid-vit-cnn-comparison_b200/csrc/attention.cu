@@ -589,11 +589,11 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 // tcgen05 / TMEM kernels for sequences of up to 256 tokens (attention_tc.cu)
 constexpr int TC_MAX_TOKENS = 256;      // forward
 constexpr int TC_MAX_TOKENS_BWD = 240;  // backward (shared-memory budget of the pipelined kernel)
-int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st);
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, cudaStream_t st);
 int attention_probs_tc(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H, float scale,
                        bool fp16, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
-                     int H, float scale, bool fp16, cudaStream_t st);
+                     int H, float scale, int q_rows, bool fp16, cudaStream_t st);
 }  // namespace vitk
 
 using namespace vitk;
@@ -610,10 +610,10 @@ static int attention_probs_impl(const void* qkv, const float* lse, float* probs,
 }
 
 template <bool H16>
-static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* probs, int B, int N, int H, float scale,
+static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* probs, int B, int N, int H, float scale, int q_rows,
                               cudaStream_t st) {
   if (N <= TC_MAX_TOKENS) {
-    const int rc = attention_fwd_tc(qkv, out, lse, B, N, H, scale, H16, st);
+    const int rc = attention_fwd_tc(qkv, out, lse, B, N, H, scale, probs != nullptr ? 0 : q_rows, H16, st);  // maps need every lse
     if (rc != VITK_OK) return rc;
   } else {
     dim3 grid((N + TILE - 1) / TILE, H, B);
@@ -626,14 +626,15 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* pro
 }
 
 extern "C" int vitk_attention_fwd(const void* qkv, void* out, int32_t dtype, float* lse, float* probs, int32_t B, int32_t N,
-                                  int32_t H, float scale, void* stream) {
+                                  int32_t H, float scale, int32_t q_rows, void* stream) {
+  VITK_CHECK_ARG(q_rows >= 0, "vitk_attention_fwd: q_rows must be >= 0 (0: every query row)");
   VITK_CHECK_ARG(qkv && out && lse, "vitk_attention_fwd: null pointer");
   VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_fwd: dtype must be bf16 or fp16");
   VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_fwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_fwd: grid limit");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return dtype == VITK_FP16 ? attention_fwd_impl<true>(qkv, out, lse, probs, B, N, H, scale, st)
-                            : attention_fwd_impl<false>(qkv, out, lse, probs, B, N, H, scale, st);
+  return dtype == VITK_FP16 ? attention_fwd_impl<true>(qkv, out, lse, probs, B, N, H, scale, q_rows, st)
+                            : attention_fwd_impl<false>(qkv, out, lse, probs, B, N, H, scale, q_rows, st);
 }
 
 extern "C" int vitk_attention_probs(const void* qkv, int32_t dtype, const float* lse, float* probs, int64_t probs_batch_stride,
@@ -649,7 +650,7 @@ extern "C" int vitk_attention_probs(const void* qkv, int32_t dtype, const float*
 
 template <bool H16, bool DROP>
 static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
-                              int B, int N, int H, float scale, DropSpec drop, cudaStream_t st) {
+                              int B, int N, int H, float scale, DropSpec drop, cudaStream_t st, int q_rows = 0) {
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<H16, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
@@ -657,7 +658,7 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     configured = true;
   }
   const int Npad = (N + 7) & ~7;
-  if (!DROP && N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, H16, st);  // delta fused
+  if (!DROP && N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, H16, st);  // delta fused
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
                                                                      reinterpret_cast<const bf16*>(dout), delta, B, N, H);
@@ -675,15 +676,17 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
 }
 
 extern "C" int vitk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
-                                  void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H, float scale, void* stream) {
+                                  void* dqkv, int32_t dtype, int32_t B, int32_t N, int32_t H, float scale, int32_t q_rows,
+                                  void* stream) {
   VITK_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "vitk_attention_bwd: null pointer");
+  VITK_CHECK_ARG(q_rows >= 0, "vitk_attention_bwd: q_rows must be >= 0 (0: every query row)");
   VITK_CHECK_ARG(dtype == VITK_BF16 || dtype == VITK_FP16, "vitk_attention_bwd: dtype must be bf16 or fp16");
   VITK_CHECK_ARG(B > 0 && N > 0 && H > 0, "vitk_attention_bwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_CHECK_ARG(H <= 65535 && B <= 65535, "vitk_attention_bwd: grid limit");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const DropSpec none = make_drop_spec(nullptr, 0.f, 0);
-  return dtype == VITK_FP16 ? attention_bwd_impl<true, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, none, st)
-                            : attention_bwd_impl<false, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, none, st);
+  return dtype == VITK_FP16 ? attention_bwd_impl<true, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, none, st, q_rows)
+                            : attention_bwd_impl<false, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, none, st, q_rows);
 }
 
 // ---- training-mode dropout on the attention probabilities (Attention.attn_drop, vision_transformer_base.py:184).  Every

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQKV,
                        const float* __restrict__ lse, float* __restrict__ delta, int N, int H, int QP, float scale,
-                       float scale_log2, int wave_ctas) {
+                       float scale_log2, int wave_ctas, int q_chunks) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -475,7 +475,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
   const int NJ = (N + 127) >> 7;    // 128-key tiles
-  const int NCH = (QP + 63) >> 6;   // 64-query chunks
+  const int NCH_ALL = (QP + 63) >> 6;   // 64-query chunks
+  // q_chunks > 0: dO is zero from query row 64 * q_chunks on (the caller's guarantee), so those chunks contribute nothing to dK /
+  // dV and their dQ rows are zero: only the leading chunks are walked (the last block of a class-token model: 1 chunk of 4)
+  const int NCH = q_chunks > 0 ? min(q_chunks, NCH_ALL) : NCH_ALL;
   const int T = NJ * NCH;
 
   if (warp == 8) {
@@ -710,23 +713,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       }
     }
     // ---- dQ tiles (accumulated over all key tiles; every MMA is complete: the last bar_m2 wait above covered them)
-    const int NQT = (NCH + 1) >> 1;
+    const int NQT = (NCH + 1) >> 1;           // tiles with an accumulator
+    const int NQT_ALL = (NCH_ALL + 1) >> 1;   // tiles of the output (rows outside the walked chunks are stored as zeros)
     if (warp == 0 && elect_one()) tma_store_wait_read();
     named_bar_sync(1, 256);
-    if (half < NQT) {
+    if (half < NQT_ALL) {
       uint8_t* dst = sOut + half * 16384;
+      const bool have = half < NQT;                              // warp-uniform
+      const bool live = have && keyrow < 64 * (NCH - 2 * half);  // this thread's query row lies inside a walked chunk
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
-        tmem_ld32_nowait(trow + uint32_t(TM_DQ + 64 * half + 32 * hh), v);
-        tmem_ld_wait();
+        if (have) {
+          tmem_ld32_nowait(trow + uint32_t(TM_DQ + 64 * half + 32 * hh), v);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          uint4 o;
-          o.x = pk16<H16>(__uint_as_float(v[8 * cc + 0]) * scale, __uint_as_float(v[8 * cc + 1]) * scale);
-          o.y = pk16<H16>(__uint_as_float(v[8 * cc + 2]) * scale, __uint_as_float(v[8 * cc + 3]) * scale);
-          o.z = pk16<H16>(__uint_as_float(v[8 * cc + 4]) * scale, __uint_as_float(v[8 * cc + 5]) * scale);
-          o.w = pk16<H16>(__uint_as_float(v[8 * cc + 6]) * scale, __uint_as_float(v[8 * cc + 7]) * scale);
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (live) {
+            o.x = pk16<H16>(__uint_as_float(v[8 * cc + 0]) * scale, __uint_as_float(v[8 * cc + 1]) * scale);
+            o.y = pk16<H16>(__uint_as_float(v[8 * cc + 2]) * scale, __uint_as_float(v[8 * cc + 3]) * scale);
+            o.z = pk16<H16>(__uint_as_float(v[8 * cc + 4]) * scale, __uint_as_float(v[8 * cc + 5]) * scale);
+            o.w = pk16<H16>(__uint_as_float(v[8 * cc + 6]) * scale, __uint_as_float(v[8 * cc + 7]) * scale);
+          }
           *reinterpret_cast<uint4*>(dst + swz128(keyrow, 4 * hh + cc)) = o;
         }
       }
@@ -735,7 +745,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
     fence_proxy_async();
     named_bar_sync(1, 256);
     if (warp == 0 && elect_one()) {
-      for (int qt = 0; qt < NQT; ++qt) tma_store_3d(&tmDQKV, sOut + qt * 16384, h * DH, qt * 128, b);
+      for (int qt = 0; qt < NQT_ALL; ++qt) tma_store_3d(&tmDQKV, sOut + qt * 16384, h * DH, qt * 128, b);
       tma_store_commit();
       tma_store_wait_read();   // shared memory must outlive the reads; the writes themselves complete asynchronously
     }
@@ -786,7 +796,7 @@ int make_tmap_3d(CUtensorMap* tm, const void* base, int width, int N, int B, int
 
 // Forward for N <= 256.  Returns VITK_OK or an error; the caller (attention.cu) owns argument validation.
 template <bool H16>
-int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t st) {
+int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, cudaStream_t st) {
   const int KP = (N + 15) & ~15;
   CUtensorMap tmQ, tmKV, tmO;
   int rc;
@@ -800,7 +810,9 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 + 2 * 256 * 128 + 64 + 1024));
     configured = 128 * 128 + 2 * 256 * 128 + 64 + 1024;
   }
-  dim3 grid((N + 127) / 128, H, B);
+  // q_rows > 0: only the first q_rows query rows of out / lse are needed -> only the 128-query tiles that hold them are launched
+  const int q_need = q_rows > 0 && q_rows < N ? q_rows : N;
+  dim3 grid((q_need + 127) / 128, H, B);
   VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, lse, N, H, KP, scale, scale * LOG2E,
                        2 * num_sms()));
   VITK_LAUNCH_CHECK();
@@ -809,7 +821,7 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
 
 template <bool H16>
 int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
-                          int H, float scale, cudaStream_t st) {
+                          int H, float scale, int q_rows, cudaStream_t st) {
   const int QP = (N + 15) & ~15;
   CUtensorMap tmQKV, tmDO, tmO, tmDQKV;
   int rc;
@@ -826,8 +838,9 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
     configured = true;
   }
   dim3 grid(H, B);
+  const int q_chunks = q_rows > 0 && q_rows < N ? (q_rows + 63) / 64 : 0;
   VITK_CUDA(launch_pdl(kfn, grid, dim3(BWD_THREADS), (size_t)smem, st, tmQKV, tmDO, tmO, tmDQKV, lse, delta, N, H, QP, scale,
-                       scale * LOG2E, num_sms()));
+                       scale * LOG2E, num_sms(), q_chunks));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -863,14 +876,14 @@ int attention_probs_tc(const void* qkv, const float* lse, float* probs, long lon
               : attention_probs_tc_impl<false>(qkv, lse, probs, batch_stride, B, N, H, scale, st);
 }
 
-int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, bool fp16, cudaStream_t st) {
-  return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, st)
-              : attention_fwd_tc_impl<false>(qkv, out, lse, B, N, H, scale, st);
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, cudaStream_t st) {
+  return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, q_rows, st)
+              : attention_fwd_tc_impl<false>(qkv, out, lse, B, N, H, scale, q_rows, st);
 }
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
-                     int H, float scale, bool fp16, cudaStream_t st) {
-  return fp16 ? attention_bwd_tc_impl<true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st)
-              : attention_bwd_tc_impl<false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, st);
+                     int H, float scale, int q_rows, bool fp16, cudaStream_t st) {
+  return fp16 ? attention_bwd_tc_impl<true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, st)
+              : attention_bwd_tc_impl<false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, st);
 }
 
 }  // namespace vitk

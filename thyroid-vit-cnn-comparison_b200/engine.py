@@ -376,7 +376,10 @@ class VitEngine:
             elif attn_probs is not None:
                 probs = torch.empty(B, d.heads, T, T, dtype=torch.float32, device=self.device)
                 attn_probs.append(probs)
-            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs, drop=self._attn_site(l))
+            # last block of a class-token model: only the classifier's query rows are consumed (and the maps need every lse)
+            q_rows = nr if (prune and l == d.depth - 1 and attn_probs is None) else 0
+            ops.attention_fwd(ws.qkv[s], B, T, d.heads, self.scale, out=ws.ao[s], lse=ws.lse[s], probs=probs, drop=self._attn_site(l),
+                              q_rows=q_rows)
             if probs_im is not None:
                 ops.attention_probs(ws.qkv[s], ws.lse[s], B, T, d.heads, self.scale, probs_im[:, l],
                                     batch_stride=d.depth * d.heads * T * T)
@@ -512,7 +515,7 @@ class VitEngine:
                 ops.expand_rows(ws.c_dao.view(B, nr, D), nr, ws.d_ao.view(B, T, D))
                 ops.expand_rows(ws.c_dx[1].view(B, nr, D), nr, dx.view(B, T, D))
                 ops.attention_bwd(ws.qkv[l], ws.ao[l], ws.d_ao, ws.lse[l], B, T, d.heads, self.scale, dqkv=ws.dqkv, delta=ws.delta,
-                                  drop=self._attn_site(l))
+                                  drop=self._attn_site(l), q_rows=nr)       # d_ao is zero from row nr on
                 self._wgrad(ws.dqkv, ws.xn1[l], pre + "attn.qkv.weight", M, bias_name=pre + "attn.qkv.bias")
                 ops.gemm(ws.dqkv, self.w(pre + "attn.qkv.weight"), M, D, 3 * D, b_mn=True, out=ws.dxn)
                 prev_bias = self.g(f"blocks.{l - 1}.mlp.fc2.bias") if l > 0 else None

@@ -145,8 +145,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dres=None, dx=None
 
 
 # --------------------------------------------------------------------------- attention
-def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None, drop=None):
-    """drop = (seed, p, site): training-mode dropout on the attention probabilities (Attention.attn_drop)."""
+def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None, probs=None, drop=None, q_rows: int = 0):
+    """drop = (seed, p, site): training-mode dropout on the attention probabilities (Attention.attn_drop).
+    q_rows > 0: only query rows 0..q_rows-1 of out / lse are needed (the other rows may stay unwritten)."""
     _req16(qkv, "attention qkv")
     out = torch.empty(B, N, H * 64, dtype=qkv.dtype, device=qkv.device) if out is None else out
     if out.dtype != qkv.dtype:
@@ -159,11 +160,12 @@ def attention_fwd(qkv, B: int, N: int, H: int, scale: float, out=None, lse=None,
                                                      _drop(drop), _stream()), "attention_dropout_fwd")
         return out, lse
     check(_lib.load().vitk_attention_fwd(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], lse.data_ptr(), _p(probs), B, N, H,
-                                         scale, _stream()), "attention_fwd")
+                                         scale, int(q_rows), _stream()), "attention_fwd")
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqkv=None, delta=None, drop=None):
+def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqkv=None, delta=None, drop=None, q_rows: int = 0):
+    """q_rows > 0: the caller guarantees dout is zero from query row q_rows on (dqkv is still complete)."""
     _req16(qkv, "attention qkv")
     _req(out, qkv.dtype, "attention out"); _req(dout, qkv.dtype, "attention dout")
     dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
@@ -174,7 +176,7 @@ def attention_bwd(qkv, out, dout, lse, B: int, N: int, H: int, scale: float, dqk
               "attention_dropout_bwd")
         return dqkv
     check(_lib.load().vitk_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-                                         dqkv.data_ptr(), _DT[qkv.dtype], B, N, H, scale, _stream()), "attention_bwd")
+                                         dqkv.data_ptr(), _DT[qkv.dtype], B, N, H, scale, int(q_rows), _stream()), "attention_bwd")
     return dqkv
 
 
