@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 23
+#define VITK_ABI_VERSION 24
 
 typedef enum {
   VITK_OK = 0,
@@ -278,6 +278,13 @@ int vitk_dense_bottleneck(const void* x, int64_t x_ld, const float* scale, const
  * is zero-filled) -- the A operand of vitk_gemm against the filters reshaped to [Cout, ky, kx, c]. */
 int vitk_im2col_rows(const void* x, void* patches, int32_t B, int32_t H, int32_t W, int32_t C, int32_t kernel,
                      int32_t stride, int32_t pad, int64_t ld, void* stream);
+/* The same stem without the patch matrix: 7x7 / stride 2 / padding 3 convolution of a 3-channel NHWC batch as an implicit GEMM
+ * (torchvision densenet.py features.conv0 with norm0 folded into w / bias; relu != 0 applies relu0 -- ReLU and the max pool
+ * behind it commute).  x [B,H,W,3], out [B,H/2,W/2,64], one 16-bit type for x / w / out; w [64,192] with
+ * w[o][ky*24 + 1 + kx*3 + c] = filter[o][c][ky][kx] and zeros in slots 0, 22, 23 of every ky segment and from column 168 on;
+ * bias fp32 [64].  H even, W % 8 == 0. */
+int vitk_stem_conv7(const void* x, const void* w, const float* bias, void* out, int32_t B, int32_t H, int32_t W,
+                    int32_t relu, int32_t dtype, void* stream);
 /* MaxPool2d(kernel, stride, pad) (is_max = 1, -inf padding) / AvgPool2d(kernel, stride, pad) (is_max = 0, count_include_pad) of a
  * compact NHWC tensor x [B,H,W,C], ceil_mode False, written with pixel pitch y_ld into y [B,OH,OW,y_ld]: the DenseNet stem's
  * pool0 and the transitions' pool (torchvision densenet.py) store straight into the next dense block's buffer. */

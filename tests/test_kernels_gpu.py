@@ -1008,3 +1008,26 @@ def test_im2col_rows_plus_gemm_is_the_stem_convolution():
     ref = torch.nn.functional.conv2d(x.float(), w.float(), b, stride=2, padding=3).permute(0, 2, 3, 1).reshape(-1, Co)
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() < 2.0 ** -7 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,dt,relu", [(3, 224, 224, torch.float16, True), (2, 64, 64, torch.bfloat16, True),
+                                          (1, 40, 72, torch.float16, False), (9, 224, 224, torch.bfloat16, True)])
+def test_stem_conv7_matches_conv2d(B, H, W, dt, relu):
+    """vitk_stem_conv7 (implicit GEMM, zero padding by TMA fill, ragged tiles clipped) vs F.conv2d on the same 16-bit operands
+    (torchvision densenet.py features.conv0 + folded norm0 + relu0)."""
+    g = torch.Generator().manual_seed(B * H + W)
+    x = torch.randn(B, 3, H, W, generator=g).cuda().to(dt)
+    w = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).cuda().to(dt)
+    bias = torch.randn(64, generator=g).cuda()
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, stride=2, padding=3)
+    if relu:
+        ref = ref.relu()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    out = ops.stem_conv7(xn, ops.stem_conv7_weights(w, dt), bias, relu=relu)
+    torch.cuda.synchronize()
+    assert out.shape == (B, H // 2, W // 2, 64)
+    got = out.permute(0, 3, 1, 2).float()
+    tol = 2e-2 if dt == torch.bfloat16 else 3e-3       # one rounding of the 16-bit output (|values| up to ~4)
+    assert (got - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item()), (got - ref).abs().max().item()
+    assert rel_l2(got, ref) < (4e-3 if dt == torch.bfloat16 else 5e-4)

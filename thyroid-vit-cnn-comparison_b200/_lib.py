@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 23
+ABI_VERSION = 24
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -72,6 +72,7 @@ SIGNATURES = {
     "vitk_dense_bwd": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_void_p]),
     "vitk_affine_relu_nhwc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "vitk_im2col_rows": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_int64, c_void_p]),
+    "vitk_stem_conv7": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "vitk_dense_bottleneck": (c_int, [c_void_p, c_int64] + [c_void_p] * 5 + [c_int64, c_int, c_int, c_void_p]),
     "vitk_pool_nhwc": (c_int, [c_void_p, c_void_p, c_int64] + [c_int] * 9 + [c_void_p]),
     "vitk_dropout_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),

@@ -18,7 +18,7 @@ CSRC = HERE / "csrc"
 OBJ_DIR = HERE / "build"
 LIB = HERE / "libvitk.so"
 
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "elementwise.cu", "loss.cu", "adamw.cu", "metrics.cu", "ingest.cu", "pool_head.cu", "teacher.cu", "bottleneck_tc.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "elementwise.cu", "loss.cu", "adamw.cu", "metrics.cu", "ingest.cu", "pool_head.cu", "teacher.cu", "bottleneck_tc.cu", "stem_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -563,6 +563,32 @@ def im2col_rows(x_nhwc, kernel: int, stride: int, pad: int, out=None):
     return out
 
 
+def stem_conv7_weights(weight, dtype):
+    """Conv2d weight [64, 3, 7, 7] (norm0 already folded in) -> the [64, 192] filter matrix of vitk_stem_conv7:
+    column ky*24 + 1 + kx*3 + c, zeros in slots 0, 22, 23 of every ky segment and from column 168 on."""
+    if tuple(weight.shape) != (64, 3, 7, 7):
+        raise ValueError("stem_conv7_weights: a [64, 3, 7, 7] filter bank expected")
+    w = weight.detach().float().permute(0, 2, 3, 1).reshape(64, 7, 21)
+    w = torch.nn.functional.pad(w, (1, 2)).reshape(64, 168)
+    return torch.nn.functional.pad(w, (0, 24)).to(dtype).contiguous()
+
+
+def stem_conv7(x_nhwc, w, bias, relu: bool = True, out=None):
+    """7x7 / stride 2 / padding 3 convolution of a 16-bit NHWC [B,H,W,3] batch (implicit GEMM, no patch matrix):
+    -> [B,H/2,W/2,64]; w from stem_conv7_weights, bias fp32 [64]."""
+    _req16(x_nhwc, "stem x")
+    B, H, W, Cc = x_nhwc.shape
+    if Cc != 3 or not x_nhwc.is_contiguous():
+        raise ValueError("stem_conv7: a contiguous NHWC batch with 3 channels expected")
+    if w.dtype != x_nhwc.dtype or not w.is_cuda or not w.is_contiguous() or tuple(w.shape) != (64, 192):
+        raise TypeError("stem_conv7: w must be a contiguous CUDA [64, 192] tensor of x's dtype (stem_conv7_weights)")
+    _req(bias, f32, "stem bias")
+    out = torch.empty(B, H // 2, W // 2, 64, dtype=x_nhwc.dtype, device=x_nhwc.device) if out is None else out
+    check(_lib.load().vitk_stem_conv7(x_nhwc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, int(bool(relu)),
+                                      _DT[x_nhwc.dtype], _stream()), "stem_conv7")
+    return out
+
+
 def dense_bottleneck(x, C: int, scale, shift, w, bias, out=None):
     """x: 16-bit NHWC [..., Ct] (the first C channels are read), w: 16-bit [128, C], scale / shift fp32 [C], bias fp32 [128]
     -> relu(relu(x[..., :C] * scale + shift) @ w^T + bias) as 16-bit [..., 128]."""

@@ -80,11 +80,15 @@ class FrozenDenseNet:
         self.stem = (cl(w0), b0.to(dtype), f.conv0.stride, f.conv0.padding)
         k0 = f.conv0.kernel_size
         self.stem_gemm = None
+        self.stem_fused = True      # False: patch rows + vitk_gemm (the first GEMM form; kept for other stem shapes and for A/B runs)
         if k0[0] == k0[1] and f.conv0.stride[0] == f.conv0.stride[1] and f.conv0.padding[0] == f.conv0.padding[1] and w0.shape[0] % 8 == 0:
             wm = w0.permute(0, 2, 3, 1).reshape(w0.shape[0], -1)                       # [Cout, ky*kx*c]
             ld = (wm.shape[1] + 7) // 8 * 8
             wm = F.pad(wm, (0, ld - wm.shape[1])).to(dtype).contiguous()
             self.stem_gemm = {"w": wm, "b": b0.float().contiguous(), "k": int(k0[0]), "s": int(f.conv0.stride[0]), "p": int(f.conv0.padding[0])}
+            # the torchvision stem itself (7x7 / 2 / 3 on 3 channels, 64 filters): implicit GEMM, the patch rows never reach HBM
+            if tuple(w0.shape) == (64, 3, 7, 7) and self.stem_gemm["s"] == 2 and self.stem_gemm["p"] == 3:
+                self.stem_gemm["w7"] = ops.stem_conv7_weights(w0, dtype)
         self.stem_pool = self._pool_spec(f.pool0, True)
         self.blocks: List[dict] = []
         i = 1
@@ -167,13 +171,16 @@ class FrozenDenseNet:
         sg = self.stem_gemm
         if sg is not None and self._bottleneck is not None and x.is_cuda and self.stem_pool[3]:
             xn = self._nhwc(x)                                                          # [B,H,W,3] view of the channels_last batch
-            patches = ops.im2col_rows(xn, sg["k"], sg["s"], sg["p"])
             Bn, Hn, Wn, _ = xn.shape
-            OHs, OWs = (Hn + 2 * sg["p"] - sg["k"]) // sg["s"] + 1, (Wn + 2 * sg["p"] - sg["k"]) // sg["s"] + 1
-            cout = sg["w"].shape[0]
-            src = torch.empty(Bn, OHs, OWs, cout, dtype=self.dtype, device=x.device)
-            ops.gemm(patches, sg["w"], patches.shape[0], cout, patches.shape[1], out=src, bias=sg["b"])   # conv0 + norm0, no ReLU yet
-            relu_after_pool = True
+            if "w7" in sg and self.stem_fused and Hn % 2 == 0 and Wn % 8 == 0 and Hn >= 8:
+                src = ops.stem_conv7(xn, sg["w7"], sg["b"], relu=True)                 # conv0 + norm0 + relu0 (relu and max pool commute)
+            else:
+                patches = ops.im2col_rows(xn, sg["k"], sg["s"], sg["p"])
+                OHs, OWs = (Hn + 2 * sg["p"] - sg["k"]) // sg["s"] + 1, (Wn + 2 * sg["p"] - sg["k"]) // sg["s"] + 1
+                cout = sg["w"].shape[0]
+                src = torch.empty(Bn, OHs, OWs, cout, dtype=self.dtype, device=x.device)
+                ops.gemm(patches, sg["w"], patches.shape[0], cout, patches.shape[1], out=src, bias=sg["b"])   # conv0 + norm0, no ReLU yet
+                relu_after_pool = True
         else:
             src = self._nhwc(self._conv_bias_relu(x, w0, b0, stride0, pad0))           # [B,H,W,64]
         pool = self.stem_pool

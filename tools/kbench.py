@@ -100,7 +100,7 @@ def main():
     }
     # round-2 kernels around the encoder (input tiles, eval attention maps + rollout, the frozen teacher's bottleneck GEMM)
     want = set(s for s in a.only.split(",") if s)
-    if a.model == "deit_tiny" and (not want or want & {"tiles_to_patches", "attn_probs", "rollout_row", "bottleneck_b1", "bottleneck_b3"}):
+    if a.model == "deit_tiny" and (not want or want & {"tiles_to_patches", "attn_probs", "rollout_row", "bottleneck_b1", "bottleneck_b3", "stem_conv7"}):
         BF = torch.bfloat16
         tiles = torch.randint(0, 65536, (B, 224, 224), dtype=torch.int32).to(torch.uint16).to(DEV)
         patches = torch.empty(B * 196, 768, dtype=F16, device=DEV)
@@ -120,6 +120,12 @@ def main():
             ob_ = torch.empty(P_, 128, dtype=BF, device=DEV)
             cases[nm] = ((lambda xb=xb, C_=C_, sb_=sb_, hb_=hb_, wb=wb, bb_=bb_, ob_=ob_: ops.dense_bottleneck(xb, C_, sb_, hb_, wb, bb_, out=ob_)),
                          P_ * C_ * 2 + P_ * 128 * 2 + 128 * C_ * 2, 2 * P_ * C_ * 128)
+        if not want or "stem_conv7" in want:
+            xs = torch.randn(B, 224, 224, 3, generator=g).to(DEV).to(BF)
+            ws = ops.stem_conv7_weights(torch.randn(64, 3, 7, 7, generator=g) * 0.1, BF).to(DEV)
+            bs_ = torch.randn(64, device=DEV)
+            os_ = torch.empty(B, 112, 112, 64, dtype=BF, device=DEV)
+            cases["stem_conv7"] = (lambda: ops.stem_conv7(xs, ws, bs_, out=os_), xs.numel() * 2 + os_.numel() * 2, 2 * B * 112 * 112 * 64 * 147)
     only = [s for s in a.only.split(",") if s]
     flush = None if a.no_flush else torch.empty(256 * 1024 * 1024 // 4, device=DEV)
     res = {}
