@@ -965,8 +965,10 @@ def test_pool_nhwc(B, H, W, C, Ct, k, s, p, is_max, dt):
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("P,Ct,C", [(1000, 256, 64), (128 * 3 + 5, 512, 96), (4096, 1664, 1632), (70, 64, 64), (20000, 224, 224)])
 def test_dense_bottleneck_matches_affine_relu_conv1x1(P, Ct, C, dt):
-    """vitk_dense_bottleneck = relu(relu(x[:, :C] * s + h) @ W^T + b): against vitk_affine_relu_nhwc (whose 16-bit output is
-    the bit-exact A operand) followed by an fp32 matmul; ragged pixel counts, C not a multiple of 64, pitch > C."""
+    """vitk_dense_bottleneck = relu(relu(x[:, :C] * s + h) @ W^T + b) with the affine map in packed 16-bit fma.rn.relu (scale and
+    shift rounded to the operand type, the product-sum rounded once): against that arithmetic restated in torch followed by an
+    fp32 matmul, and against the fp32-parameter form (vitk_affine_relu_nhwc) within the rounding of s and h; ragged pixel
+    counts, C not a multiple of 64, pitch > C."""
     g = torch.Generator().manual_seed(P + C)
     x = (torch.randn(P, Ct, generator=g)).to(DEV).to(dt)
     s = (torch.rand(C, generator=g) + 0.5).to(DEV)
@@ -974,13 +976,17 @@ def test_dense_bottleneck_matches_affine_relu_conv1x1(P, Ct, C, dt):
     w = (torch.randn(128, C, generator=g) / C ** 0.5).to(DEV).to(dt)
     b = (torch.randn(128, generator=g) * 0.2).to(DEV)
     out = ops.dense_bottleneck(x, C, s, h, w, b)
-    a = ops.affine_relu_nhwc(x.view(1, 1, P, Ct), C, s, h).view(P, C)
+    a = torch.relu((x[:, :C].float() * s.to(dt).float() + h.to(dt).float()).to(dt))    # products of two 16-bit values are exact in fp32
     ref = torch.relu(a.float() @ w.float().t() + b)
+    a32 = ops.affine_relu_nhwc(x.view(1, 1, P, Ct), C, s, h).view(P, C)              # fp32 scale / shift, one rounding
+    ref32 = torch.relu(a32.float() @ w.float().t() + b)
     torch.cuda.synchronize()
     assert out.shape == (P, 128) and out.dtype == dt
     err = (out.float() - ref).abs().max().item()
-    tol = (2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11) * max(1.0, ref.abs().max().item()) * 1.5
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    tol = ulp * max(1.0, ref.abs().max().item()) * 1.5
     assert err <= tol, (err, tol)
+    assert (out.float() - ref32).abs().max().item() <= 4 * tol                        # rounding s and h costs a few output ulps at most
     assert torch.equal(ops.dense_bottleneck(x, C, s, h, w, b), out)          # deterministic
     with pytest.raises(TypeError):
         ops.dense_bottleneck(x, C, s, h, w[:, :-8].contiguous(), b)

@@ -13,9 +13,10 @@
 //
 //   warp 0     TMA producer: A block [128 pixels x 64 channels] + W block [128 x 64] per stage, 4-stage ring
 //   warp 1     MMA issuer (one elected thread): tcgen05.mma M=128 N=128 K=16 x 4 per block, fp32 accumulator in TMEM
-//   warps 2-9  two threads per pixel row (32 channels each): transform the landed A block in place (16-bit -> fp32 fma +
-//              max(0) -> 16-bit, one rounding: bit-identical to vitk_affine_relu_nhwc).  ~55 instructions per 16-byte cell:
-//              with one warp per SM sub-partition this pass, not HBM, set the pace (measured 1.5 k cycles per k-block)
+//   warps 2-9  two threads per pixel row (32 channels each): transform the landed A block in place with packed 16-bit
+//              fma.rn.relu (scale and shift rounded to the operand type once at start-up; the first version unpacked to
+//              fp32 -- bit-identical to vitk_affine_relu_nhwc, but ~55 instructions per 16-byte cell made this pass, not HBM,
+//              set the pace at 1.5 k cycles per k-block)
 //   warps 10-13 tile epilogue (TMEM -> bias + ReLU -> 16-bit -> swizzled staging -> TMA store) of tile t while the other
 //              warps already work on tile t+1 (two accumulator stages in TMEM)
 // HBM-bound by construction: per k-block a CTA moves 16 KB of activations (W comes from L2) against 256 cycles of MMA.
@@ -35,6 +36,19 @@ constexpr int BT_KMAX = 2048;             // channels of the widest concatenatio
 constexpr int BT_STAGE_BYTES = 2 * 128 * 128;   // A block + W block, [128 rows][64 x 16-bit], 128B swizzle
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+template <bool H16>
+__device__ __forceinline__ uint16_t to_bits16(float v) {
+  if (H16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+// max(x * s + h, 0) on a pair of 16-bit values (fma.rn.relu: the product-sum is exact, rounded once)
+template <bool H16>
+__device__ __forceinline__ uint32_t fma_relu2(uint32_t x, uint32_t s, uint32_t h) {
+  uint32_t d;
+  if (H16) asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
+  else asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
+  return d;
+}
 
 template <bool H16>
 __global__ void __launch_bounds__(BT_THREADS, 1)
@@ -46,9 +60,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sStage = smem;                                         // BT_STAGES x (A 16 KB + W 16 KB)
   uint8_t* sOut = sStage + BT_STAGES * BT_STAGE_BYTES;            // 2 x [128][64 x 16-bit] output halves
-  float* sScale = reinterpret_cast<float*>(sOut + 2 * 16384);     // [KP]
-  float* sShift = sScale + BT_KMAX;
-  float* sBias = sShift + BT_KMAX;                                // [128]
+  uint16_t* sScale = reinterpret_cast<uint16_t*>(sOut + 2 * 16384);   // [KP] norm1 scale in the operand's 16-bit type
+  uint16_t* sShift = sScale + BT_KMAX;                               // [KP] norm1 shift
+  float* sBias = reinterpret_cast<float*>(sShift + BT_KMAX);         // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BT_N);
   uint64_t* full = bars;                     // [S] A and W block landed
   uint64_t* ready = bars + BT_STAGES;        // [S] A block transformed (256 arrivals)
@@ -83,8 +97,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   }
   // per-channel affine of norm1 (zero beyond C: the W columns there are zero-filled by TMA, the products vanish) and bias
   for (int i = threadIdx.x; i < KP; i += BT_THREADS) {
-    sScale[i] = i < C ? __ldg(scale + i) : 0.f;
-    sShift[i] = i < C ? __ldg(shift + i) : 0.f;
+    sScale[i] = i < C ? to_bits16<H16>(__ldg(scale + i)) : uint16_t(0);
+    sShift[i] = i < C ? to_bits16<H16>(__ldg(shift + i)) : uint16_t(0);
   }
   for (int i = threadIdx.x; i < BT_N; i += BT_THREADS) sBias[i] = __ldg(bias + i);
   tc_fence_before();
@@ -145,21 +159,20 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
         const int s = g % BT_STAGES;
         mbar_wait(full + s, (g / BT_STAGES) & 1, 43);
         uint8_t* a = sStage + s * BT_STAGE_BYTES;
-        const float* sc = sScale + kb * 64;
-        const float* sh = sShift + kb * 64;
+        const uint16_t* sc = sScale + kb * 64;
+        const uint16_t* sh = sShift + kb * 64;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c = 4 * half + cc;
           uint4* cell = reinterpret_cast<uint4*>(a + swz128(row, c));
           const uint4 in = *cell;
-          const float4 s0 = *reinterpret_cast<const float4*>(sc + 8 * c), s1 = *reinterpret_cast<const float4*>(sc + 8 * c + 4);
-          const float4 h0 = *reinterpret_cast<const float4*>(sh + 8 * c), h1 = *reinterpret_cast<const float4*>(sh + 8 * c + 4);
-          const float2 x0 = unpack16(in.x, H16), x1 = unpack16(in.y, H16), x2 = unpack16(in.z, H16), x3 = unpack16(in.w, H16);
-          uint4 o;
-          o.x = pack16(fmaxf(fmaf(x0.x, s0.x, h0.x), 0.f), fmaxf(fmaf(x0.y, s0.y, h0.y), 0.f), H16);
-          o.y = pack16(fmaxf(fmaf(x1.x, s0.z, h0.z), 0.f), fmaxf(fmaf(x1.y, s0.w, h0.w), 0.f), H16);
-          o.z = pack16(fmaxf(fmaf(x2.x, s1.x, h1.x), 0.f), fmaxf(fmaf(x2.y, s1.y, h1.y), 0.f), H16);
-          o.w = pack16(fmaxf(fmaf(x3.x, s1.z, h1.z), 0.f), fmaxf(fmaf(x3.y, s1.w, h1.w), 0.f), H16);
+          const uint4 s4 = *reinterpret_cast<const uint4*>(sc + 8 * c);
+          const uint4 h4 = *reinterpret_cast<const uint4*>(sh + 8 * c);
+          uint4 o;   // packed fma + relu: two channels per instruction, one rounding of the exact x * s + h
+          o.x = fma_relu2<H16>(in.x, s4.x, h4.x);
+          o.y = fma_relu2<H16>(in.y, s4.y, h4.y);
+          o.z = fma_relu2<H16>(in.z, s4.z, h4.z);
+          o.w = fma_relu2<H16>(in.w, s4.w, h4.w);
           *cell = o;
         }
         fence_proxy_async();          // the generic-proxy writes above must be visible to the tensor core's smem reads
@@ -256,7 +269,7 @@ int launch_bottleneck(const void* x, long long x_ld, const float* scale, const f
   if ((rc = bt_tmap(&tmX, x, C, pixels, x_ld, H16)) != VITK_OK) return rc;
   if ((rc = bt_tmap(&tmW, w, C, BT_N, C, H16)) != VITK_OK) return rc;
   if ((rc = bt_tmap(&tmOut, out, BT_N, pixels, BT_N, H16)) != VITK_OK) return rc;
-  const int smem = BT_STAGES * BT_STAGE_BYTES + 2 * 16384 + (2 * BT_KMAX + BT_N) * 4 + (3 * BT_STAGES + 4) * 8 + 16 + 1024;
+  const int smem = BT_STAGES * BT_STAGE_BYTES + 2 * 16384 + 2 * BT_KMAX * 2 + BT_N * 4 + (3 * BT_STAGES + 4) * 8 + 16 + 1024;
   auto kfn = dense_bottleneck_kernel<H16>;
   static bool configured = false;
   if (!configured) {
