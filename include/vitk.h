@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 24
+#define VITK_ABI_VERSION 25
 
 typedef enum {
   VITK_OK = 0,
@@ -413,6 +413,15 @@ int vitk_attention_rollout(const float* probs, float* rollout, float* scratch, i
  * the one-CTA-per-image walk wants (measured: 1.31 ms -> see profiles/ for DeiT-tiny, batch 256).  out fp32 [B,N]. */
 int vitk_attention_rollout_row(const float* probs, float* out, int64_t layer_stride, int64_t batch_stride, int32_t L,
                                int32_t B, int32_t H, int32_t N, int32_t row, int32_t fusion, void* stream);
+
+/* Class-token heat map of the visualisation code (src/models/vit/attention_utils.py:50-67: `attn.mean(dim=0)[0, 1:]` ->
+ * sqrt grid -> F.interpolate(size=image, mode='bilinear', align_corners=False)), for every image of the batch.
+ * Element j of head h of image b is src[b * batch_stride + h * head_stride + j]: one layer's maps [B,H,N,N] are
+ * (H*N*N, N*N) -- row 0 of each head --, a rollout row [B,N] or a grid [B,g*g] is H = 1 with batch_stride = N / g*g.
+ * The g*g patch columns start at n_prefix (1 class token; 2 for a distilled DeiT).  out fp32 [B,out_h,out_w]. */
+int vitk_cls_attention_heatmap(const float* src, float* out, int64_t batch_stride, int64_t head_stride,
+                               int32_t B, int32_t H, int32_t n_prefix, int32_t grid, int32_t out_h,
+                               int32_t out_w, void* stream);
 
 #ifdef __cplusplus
 }

@@ -232,10 +232,29 @@ def run_ingest_case():
     return rec
 
 
+def run_heatmap_case():
+    """Class-token heat maps drawn by the reference's own visualize_attention_maps (attention_utils.py:14-81, run unmodified
+    with a recording matplotlib stand-in, oracle/ref_loader.py) for seeded attention maps: grid 4 -> 32x32 and 24x40 images
+    (layer -1 and layer 0), grid 14 -> 224x224 (DeiT-tiny's shape, ViT-style single class token)."""
+    rec = {}
+    g = torch.Generator().manual_seed(11)
+    small = torch.randn(2, 3, 3, 17, 17, generator=g).softmax(-1)
+    rec["small_maps"] = small
+    rec["small_32x32_last"] = ref_loader.reference_cls_heatmaps(small, (32, 32), -1)
+    rec["small_24x40_first"] = ref_loader.reference_cls_heatmaps(small, (24, 40), 0)
+    full = torch.randn(1, 1, 3, 197, 197, generator=g).softmax(-1)
+    rec["full_maps"] = full.to(torch.float32)
+    rec["full_224"] = ref_loader.reference_cls_heatmaps(full, (224, 224), -1)
+    return rec
+
+
 def main():
     assert ref_loader.available(), "run this where /root/reference is mounted"
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    torch.save(run_heatmap_case(), GOLD / "cls_heatmap.pt")
+    if "--heatmap-only" in sys.argv:
+        return
     torch.save(run_case(GAP_REP_VIT, 3, 45, True), GOLD / "small_vit_gap_rep.pt")
     torch.save(run_case(NOCLS_VIT, 2, 46, True), GOLD / "small_vit_nocls.pt")
     torch.save(run_case(CLS_REP_VIT, 2, 47, True), GOLD / "small_vit_cls_rep.pt")

@@ -243,3 +243,30 @@ def test_ingest_oracle_matches_reference_fixture():
     box = IO.rand_bbox(images.shape, c["lam_drawn"], c["cx"], c["cy"])
     out, lam = IO.cutmix(images, c["index"], box)
     assert torch.equal(out, c["out"]) and abs(lam - c["lam"]) < 1e-12
+
+
+def test_cls_heatmap_oracle_matches_reference_fixture():
+    """attention_utils.py:50-67 restated (O.cls_attention_heatmap) against the maps the reference's own
+    visualize_attention_maps drew (tests/golden/cls_heatmap.pt, made by oracle/make_golden.py::run_heatmap_case)."""
+    rec = torch.load(GOLD / "cls_heatmap.pt")
+    assert torch.equal(O.cls_attention_heatmap(rec["small_maps"], (32, 32), -1), rec["small_32x32_last"])
+    assert torch.equal(O.cls_attention_heatmap(rec["small_maps"], (24, 40), 0), rec["small_24x40_first"])
+    assert torch.equal(O.cls_attention_heatmap(rec["full_maps"], (224, 224), -1), rec["full_224"])
+    # bilinear weights sum to one: the map stays inside the grid's range and keeps its mean on an integer upscale
+    grid = O.cls_attention_map(rec["full_maps"], -1, 1)
+    heat = rec["full_224"]
+    assert heat.min() >= grid.min() - 1e-7 and heat.max() <= grid.max() + 1e-7
+    assert abs(heat.mean().item() - grid.mean().item()) < 1e-4 * grid.mean().item() + 1e-7
+    # a distilled DeiT (198 tokens) with the reference's hard-wired `[0, 1:]` cannot be reshaped: recorded, n_prefix=2 works
+    deit_maps = torch.rand(1, 1, 3, 198, 198).softmax(-1)
+    with pytest.raises(RuntimeError):
+        O.cls_attention_heatmap(deit_maps, (224, 224), -1, n_prefix=1)
+    assert O.cls_attention_heatmap(deit_maps, (224, 224), -1, n_prefix=2).shape == (1, 224, 224)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_cls_heatmap_oracle_vs_live_reference():
+    g = torch.Generator().manual_seed(5)
+    maps = torch.randn(3, 2, 4, 26, 26, generator=g).softmax(-1)       # 25 patches -> 5 x 5 grid
+    for hw, layer in (((40, 40), -1), ((37, 53), 1)):
+        assert torch.equal(O.cls_attention_heatmap(maps, hw, layer), ref_loader.reference_cls_heatmaps(maps, hw, layer))

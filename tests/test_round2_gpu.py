@@ -588,3 +588,64 @@ def test_attention_leading_query_rows(N, H, q_rows):
     torch.cuda.synchronize()
     assert torch.isfinite(part.float()).all()
     assert torch.equal(part, full)
+
+
+# ------------------------------------------------------------------ class-token heat map (attention_utils.py:50-67)
+HEAT_TOL = 2e-6   # fp32 bilinear blend of values <= 1: summation order / fma contraction only
+
+
+def test_cls_attention_heatmap_matches_reference_fixture_and_oracle():
+    """vitk_cls_attention_heatmap against (a) the maps the reference's own visualize_attention_maps drew
+    (tests/golden/cls_heatmap.pt) and (b) the oracle on other shapes: 5-D / 4-D maps, a strided view of the image-major
+    buffer the ensemble keeps, a rollout matrix, a rollout row with two prefix tokens, a ready grid, odd output widths."""
+    rec = torch.load(ROOT / "tests" / "golden" / "cls_heatmap.pt")
+    small, full = rec["small_maps"].cuda(), rec["full_maps"].cuda()
+    assert (ENS.cls_attention_heatmap(small, 32).cpu() - rec["small_32x32_last"]).abs().max().item() < HEAT_TOL
+    assert (ENS.cls_attention_heatmap(small, (24, 40), layer_idx=0).cpu() - rec["small_24x40_first"]).abs().max().item() < HEAT_TOL
+    assert (ENS.cls_attention_heatmap(full, (224, 224)).cpu() - rec["full_224"]).abs().max().item() < HEAT_TOL
+    g = torch.Generator().manual_seed(9)
+    maps = torch.randn(3, 5, 6, 38, 38, generator=g).softmax(-1)                # 36 patches + 2 prefix tokens (DeiT layout)
+    for hw, layer in (((96, 96), -1), ((45, 67), 1), ((7, 9), 0)):               # up, odd sizes (scalar stores), down
+        want = O.cls_attention_heatmap(maps, hw, layer, n_prefix=2)
+        got = ENS.cls_attention_heatmap(maps.cuda(), hw, layer_idx=layer, n_prefix=2)
+        assert got.shape == want.shape and (got.cpu() - want).abs().max().item() < HEAT_TOL
+        got4 = ENS.cls_attention_heatmap(maps[layer].cuda(), hw, n_prefix=2)     # one layer's [B,H,N,N]
+        assert torch.equal(got4, got)
+        im = maps.transpose(0, 1).contiguous().cuda()                            # [B,L,H,N,N]: the ensemble's buffer
+        assert torch.equal(ops.cls_attention_heatmap(im[:, layer], hw, n_prefix=2), got)   # strided batch, no copy
+    # rollout matrix [B,N,N] -> its class-token row; a row [B,N]; a grid [B,g,g]
+    roll = ops.attention_rollout(maps.cuda().contiguous(), "mean")
+    want = torch.nn.functional.interpolate(roll[:, 0, 2:].reshape(5, 1, 6, 6).cpu(), size=(48, 48), mode="bilinear",
+                                           align_corners=False)[:, 0]
+    for src in (roll, roll[:, 0, :].contiguous()):
+        assert (ENS.cls_attention_heatmap(src, 48, n_prefix=2).cpu() - want).abs().max().item() < HEAT_TOL
+    assert (ENS.cls_attention_heatmap(roll[:, 0, 2:].reshape(5, 6, 6), 48).cpu() - want).abs().max().item() < HEAT_TOL
+    # the reference's hard-wired `[0, 1:]` on a 38-token sequence leaves 37 columns: not a square grid -> ValueError here
+    with pytest.raises(ValueError):
+        ENS.cls_attention_heatmap(maps.cuda(), 48, n_prefix=1)
+    with pytest.raises(RuntimeError):
+        ENS.cls_attention_heatmap(maps, 48, n_prefix=2)                          # CPU tensor: no fallback
+
+
+def test_cls_attention_heatmap_from_the_model_api_batch_256():
+    """DeiT-tiny eval forward -> blocks[-1].attn.attention_maps -> heat maps for 256 images in one launch; properties that hold at
+    any size: inside the grid's range, mean preserved by the 16x integer upscale, identical images give identical maps."""
+    cfg = O.DEIT_TINY
+    m, _ = build(cfg, 42)
+    m.eval()
+    m.store_attention = True
+    x, _ = O.seeded_batch(cfg, 4, 42)
+    x = x.repeat(64, 1, 1, 1)                                                    # 256 images, 64 copies of 4
+    with torch.no_grad():
+        m(x.cuda())
+    last = m.blocks[-1].attn.attention_maps                                      # [B,H,N,N], still on the device
+    assert last.is_cuda and tuple(last.shape) == (256, 3, 198, 198)
+    heat = ENS.cls_attention_heatmap(last, 224, n_prefix=2)
+    torch.cuda.synchronize()
+    assert heat.shape == (256, 224, 224)
+    grid = last.float().mean(1)[:, 0, 2:].reshape(256, 14, 14)
+    assert (heat.amin((1, 2)) >= grid.amin((1, 2)) - 1e-7).all() and (heat.amax((1, 2)) <= grid.amax((1, 2)) + 1e-7).all()
+    assert ((heat.mean((1, 2)) - grid.mean((1, 2))).abs() < 1e-4 * grid.mean((1, 2))).all()
+    assert (heat[:4] - heat[4:8]).abs().max().item() < 1e-6 and (heat[:4] - heat[252:]).abs().max().item() < 1e-6
+    want = O.cls_attention_heatmap(last[:4].float().cpu().unsqueeze(0), (224, 224), -1, n_prefix=2)
+    assert (heat[:4].cpu() - want).abs().max().item() < HEAT_TOL

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "libvitk.so"
 
 c_void_p, c_int, c_int64, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
-ABI_VERSION = 24
+ABI_VERSION = 25
 DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_ADD, EPI_TOKENS = 0, 1, 2, 3, 4
 
@@ -93,6 +93,7 @@ SIGNATURES = {
     "vitk_ensemble_probs": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "vitk_attention_rollout_row": (c_int, [c_void_p] * 2 + [c_int64] * 2 + [c_int] * 6 + [c_void_p]),
     "vitk_attention_probs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p]),
+    "vitk_cls_attention_heatmap": (c_int, [c_void_p] * 2 + [c_int64] * 2 + [c_int] * 6 + [c_void_p]),
     "vitk_attention_rollout": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
 }
 

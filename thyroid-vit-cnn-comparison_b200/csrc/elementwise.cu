@@ -573,6 +573,53 @@ __global__ void rollout_eye_kernel(float* __restrict__ r, int B, int N) {
   }
 }
 
+// Class-token heat map (attention_utils.py:50-67): mean over heads of row 0 of an attention map, patch columns only,
+// as the sqrt-grid, bilinearly upsampled to the image (F.interpolate(mode='bilinear', align_corners=False) restated:
+// src = scale * (dst + 0.5) - 0.5 clamped at 0, the upper neighbour clamped at the border).  One CTA per (row band, image):
+// the g x g grid (a few hundred floats) is rebuilt per CTA in shared memory, the band is written as 16-byte stores.
+__global__ void __launch_bounds__(256) cls_heatmap_kernel(const float* __restrict__ src, float* __restrict__ out, long long batch_stride,
+                                                          long long head_stride, int H, int n_prefix, int g, int OH, int OW,
+                                                          int band, float sh, float sw) {
+  extern __shared__ float s_grid[];   // [g*g]
+  const int b = blockIdx.y;
+  const float* row0 = src + (long long)b * batch_stride + n_prefix;
+  const float invH = 1.f / float(H);
+  for (int j = threadIdx.x; j < g * g; j += blockDim.x) {
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) acc += row0[(long long)h * head_stride + j];
+    s_grid[j] = H > 1 ? acc * invH : acc;
+  }
+  __syncthreads();
+  const int y_lo = blockIdx.x * band, y_hi = min(OH, y_lo + band);
+  float* ob = out + (long long)b * OH * OW;
+  auto sample = [&](int oy, int ox) {
+    const float fy = fmaxf(sh * (float(oy) + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * (float(ox) + 0.5f) - 0.5f, 0.f);
+    const int y0 = int(fy), x0 = int(fx);
+    const int yp = y0 < g - 1 ? g : 0, xp = x0 < g - 1 ? 1 : 0;
+    const float ly1 = fy - float(y0), lx1 = fx - float(x0);
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* r = s_grid + y0 * g + x0;
+    return ly0 * (lx0 * r[0] + lx1 * r[xp]) + ly1 * (lx0 * r[yp] + lx1 * r[yp + xp]);
+  };
+  if ((OW & 3) == 0) {
+    const int vw = OW >> 2;
+    for (int i = threadIdx.x; i < (y_hi - y_lo) * vw; i += blockDim.x) {
+      const int oy = y_lo + i / vw, ox = (i % vw) << 2;
+      float4 v;
+      v.x = sample(oy, ox);
+      v.y = sample(oy, ox + 1);
+      v.z = sample(oy, ox + 2);
+      v.w = sample(oy, ox + 3);
+      *reinterpret_cast<float4*>(ob + (long long)oy * OW + ox) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < (y_hi - y_lo) * OW; i += blockDim.x) {
+      const int oy = y_lo + i / OW, ox = i % OW;
+      ob[(long long)oy * OW + ox] = sample(oy, ox);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace vitk
 
@@ -814,6 +861,25 @@ extern "C" int vitk_attention_rollout_row(const float* probs, float* out, int64_
     VITK_ROLL(0, 0);
   }
 #undef VITK_ROLL
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+extern "C" int vitk_cls_attention_heatmap(const float* src, float* out, int64_t batch_stride, int64_t head_stride, int32_t B,
+                                          int32_t H, int32_t n_prefix, int32_t grid, int32_t out_h, int32_t out_w, void* stream) {
+  VITK_CHECK_ARG(src && out && B > 0 && H > 0 && n_prefix >= 0 && grid > 0 && out_h > 0 && out_w > 0,
+                 "vitk_cls_attention_heatmap: bad args");
+  VITK_CHECK_ARG(grid <= 96, "vitk_cls_attention_heatmap: grid %d x %d too large", grid, grid);
+  VITK_CHECK_ARG(batch_stride >= (int64_t)n_prefix + (int64_t)grid * grid && (H == 1 || head_stride > 0),
+                 "vitk_cls_attention_heatmap: bad strides");
+  VITK_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "vitk_cls_attention_heatmap: out must be 16-byte aligned");
+  // bands sized so that the launch covers the SMs a few times over while every CTA still amortises its grid rebuild
+  int band = 32;
+  while (band > 4 && (long long)B * ((out_h + band - 1) / band) < 4LL * num_sms()) band >>= 1;
+  const dim3 g3((out_h + band - 1) / band, B);
+  cls_heatmap_kernel<<<g3, 256, (size_t)grid * grid * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, out, batch_stride, head_stride, H, n_prefix, grid, out_h, out_w, band, float(grid) / float(out_h),
+      float(grid) / float(out_w));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }

@@ -6,6 +6,8 @@
   EnsembleTeacher           src/utils/models.py:231-283: normalised weights, weighted sum of LOGITS (distillation teacher)
   create_attention_rollout  src/models/vit/attention_utils.py:129-145 (the reference body is `pass`; spec = Abnar & Zuidema 2020)
   cls_attention_grid        visualize_attention_maps' CLS-row map (attention_utils.py:49-62) without the matplotlib part
+  cls_attention_heatmap     the same map upsampled to the image (attention_utils.py:50-67: mean over heads, CLS row, sqrt grid,
+                            bilinear F.interpolate) for every image of the batch, one `vitk_cls_attention_heatmap` launch
 
 Every forward is the libvitk eval path of the member model (`engine.forward(train=False)`); the probability mix and
 the rollout are `vitk_ensemble_probs` / `vitk_attention_rollout`; torch only averages DeiT's two [B,classes] heads
@@ -23,7 +25,7 @@ import torch.nn as nn
 from . import ops
 from .parallel import gather_fold_logits, shard_folds
 
-__all__ = ["EnsembleInference", "EnsembleTeacher", "create_attention_rollout", "cls_attention_grid"]
+__all__ = ["EnsembleInference", "EnsembleTeacher", "create_attention_rollout", "cls_attention_grid", "cls_attention_heatmap"]
 
 
 def _inner(model: nn.Module) -> nn.Module:
@@ -50,6 +52,29 @@ def cls_attention_grid(rollout_or_map: torch.Tensor, n_prefix: int) -> torch.Ten
     if g * g != a.shape[-1]:
         raise ValueError("patch count is not a square grid")
     return a.reshape(-1, g, g)
+
+
+def cls_attention_heatmap(attention: torch.Tensor, image_size, layer_idx: int = -1, n_prefix: int = 1) -> torch.Tensor:
+    """The numeric part of `visualize_attention_maps` (attention_utils.py:50-67) for the whole batch -> fp32 [B,H_img,W_img].
+
+    attention   [L,B,H,N,N] (what `get_attention_maps()` returns; `layer_idx` picks the layer, default the last one like
+                the reference's `layer_indices=[-1]`), one layer's [B,H,N,N], a rollout matrix [B,N,N] (its class-token
+                row is used), a rollout row [B,N] or a grid [B,g,g] as `EnsembleInference(rollout=True)` returns per fold.
+    image_size  `original_image.shape[:2]` (int or (h, w)).
+    n_prefix    tokens before the patches: the reference slices `attn[0, 1:]`, i.e. 1 -- with a distilled DeiT's 198 tokens
+                that leaves 197 columns and its `reshape(14, 14)` raises; pass 2 there.
+    """
+    if not attention.is_cuda:
+        raise RuntimeError("cls_attention_heatmap runs on a CUDA device through libvitk.so (no CPU fallback)")
+    hw = (int(image_size), int(image_size)) if isinstance(image_size, int) else (int(image_size[0]), int(image_size[1]))
+    a = attention.float()
+    if a.dim() == 5:
+        a = a[layer_idx]
+    elif a.dim() == 3 and a.shape[-1] == a.shape[-2] and math.isqrt(a.shape[-1] - n_prefix) ** 2 == a.shape[-1] - n_prefix:
+        a = a[:, 0, :]                               # [B,N,N] rollout: the class token's row
+    if a.dim() == 4 and a.stride(3) != 1:
+        a = a.contiguous()
+    return ops.cls_attention_heatmap(a, hw, n_prefix)
 
 
 class EnsembleInference:

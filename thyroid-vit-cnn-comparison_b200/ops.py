@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import ctypes as C_
+import math
 from typing import Optional
 
 import torch
@@ -615,4 +616,33 @@ def pool_nhwc(x, out, kernel: int, stride: int, pad: int, is_max: bool):
         raise RuntimeError(f"pool_nhwc: out must be [B={B},{OH},{OW},>= {Cc}], got {tuple(out.shape)}")
     check(_lib.load().vitk_pool_nhwc(x.data_ptr(), out.data_ptr(), out.shape[3], B, H, W, Cc, kernel, stride, pad, int(is_max),
                                      _DT[x.dtype], _stream()), "pool_nhwc")
+    return out
+
+
+def cls_attention_heatmap(src, out_hw, n_prefix: int = 1):
+    """Class-token heat maps fp32 [B,out_h,out_w] (attention_utils.py:50-67, every image of the batch).
+    src: one layer's maps fp32 [B,H,N,N] (any batch / head strides, rows contiguous), a rollout row [B,N] (then n_prefix
+    patch-prefix columns are skipped) or a grid [B,g,g] (n_prefix is ignored)."""
+    _req(src, f32, "heat-map source")
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if src.dim() == 4:
+        B, H, N, N2 = src.shape
+        if N != N2 or src.stride(3) != 1:
+            raise ValueError("attention maps must be [B,H,N,N] with contiguous rows")
+        sb, sh, cols = src.stride(0), src.stride(1), N - n_prefix
+    elif src.dim() == 2:
+        if src.stride(1) != 1:
+            raise ValueError("rollout rows must be contiguous")
+        B, H, sb, sh, cols = src.shape[0], 1, src.stride(0), 0, src.shape[1] - n_prefix
+    elif src.dim() == 3:
+        src = src.contiguous()
+        B, H, sb, sh, cols, n_prefix = src.shape[0], 1, src.shape[1] * src.shape[2], 0, src.shape[1] * src.shape[2], 0
+    else:
+        raise ValueError("heat-map source must be [B,H,N,N], [B,N] or [B,g,g]")
+    g = math.isqrt(max(cols, 0))
+    if g == 0 or g * g != cols:
+        raise ValueError(f"{cols} patch columns are not a square grid (n_prefix={n_prefix}; a distilled DeiT has 2 prefix tokens)")
+    out = torch.empty(B, oh, ow, dtype=f32, device=src.device)
+    check(_lib.load().vitk_cls_attention_heatmap(src.data_ptr(), out.data_ptr(), sb, sh, B, H, int(n_prefix), g, oh, ow, _stream()),
+          "cls_attention_heatmap")
     return out
