@@ -638,8 +638,9 @@ def test_cls_attention_heatmap_from_the_model_api_batch_256():
     x = x.repeat(64, 1, 1, 1)                                                    # 256 images, 64 copies of 4
     with torch.no_grad():
         m(x.cuda())
-    last = m.blocks[-1].attn.attention_maps                                      # [B,H,N,N], still on the device
-    assert last.is_cuda and tuple(last.shape) == (256, 3, 198, 198)
+    last = m.blocks[-1].attn.attention_maps                                      # [B,H,N,N]; on the host like the reference's (:187-188)
+    assert tuple(last.shape) == (256, 3, 198, 198)
+    last = last.cuda()
     heat = ENS.cls_attention_heatmap(last, 224, n_prefix=2)
     torch.cuda.synchronize()
     assert heat.shape == (256, 224, 224)

@@ -587,13 +587,15 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 }  // namespace
 
 // tcgen05 / TMEM kernels for sequences of up to 256 tokens (attention_tc.cu)
-constexpr int TC_MAX_TOKENS = 256;      // forward
+constexpr int TC_MAX_TOKENS = 256;      // eval-mode maps (one S tile)
+constexpr int TC_MAX_TOKENS_FWD = 816;  // forward: one S tile up to 256 tokens, 2..4 key tiles beyond (384x384 images: 577; patch 8: 785)
 constexpr int TC_MAX_TOKENS_BWD = 240;  // backward (shared-memory budget of the pipelined kernel)
-int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, cudaStream_t st);
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, const DropSpec* drop,
+                     cudaStream_t st);
 int attention_probs_tc(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H, float scale,
                        bool fp16, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
-                     int H, float scale, int q_rows, bool fp16, cudaStream_t st);
+                     int H, float scale, int q_rows, bool fp16, const DropSpec* drop, cudaStream_t st);
 }  // namespace vitk
 
 using namespace vitk;
@@ -612,8 +614,8 @@ static int attention_probs_impl(const void* qkv, const float* lse, float* probs,
 template <bool H16>
 static int attention_fwd_impl(const void* qkv, void* out, float* lse, float* probs, int B, int N, int H, float scale, int q_rows,
                               cudaStream_t st) {
-  if (N <= TC_MAX_TOKENS) {
-    const int rc = attention_fwd_tc(qkv, out, lse, B, N, H, scale, probs != nullptr ? 0 : q_rows, H16, st);  // maps need every lse
+  if (N <= TC_MAX_TOKENS_FWD) {
+    const int rc = attention_fwd_tc(qkv, out, lse, B, N, H, scale, probs != nullptr ? 0 : q_rows, H16, nullptr, st);  // maps need every lse
     if (rc != VITK_OK) return rc;
   } else {
     dim3 grid((N + TILE - 1) / TILE, H, B);
@@ -658,7 +660,7 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     configured = true;
   }
   const int Npad = (N + 7) & ~7;
-  if (!DROP && N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, H16, st);  // delta fused
+  if (N <= TC_MAX_TOKENS_BWD) return attention_bwd_tc(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, H16, DROP ? &drop : nullptr, st);  // delta fused
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
                                                                      reinterpret_cast<const bf16*>(dout), delta, B, N, H);
@@ -690,7 +692,8 @@ extern "C" int vitk_attention_bwd(const void* qkv, const void* out, const void* 
 }
 
 // ---- training-mode dropout on the attention probabilities (Attention.attn_drop, vision_transformer_base.py:184).  Every
-// ViT / DeiT configuration of the reference sets the rate to 0, so this option runs on the mma.sync kernels for any N.
+// ViT / DeiT configuration of the reference sets the rate to 0.  Forward: tcgen05 kernels up to 816 tokens; backward: the tcgen05
+// kernel up to 240 tokens (DROP instantiation), the mma.sync kernels beyond.
 extern "C" int vitk_attention_dropout_fwd(const void* qkv, void* out, int32_t dtype, float* lse, int32_t B, int32_t N, int32_t H,
                                           float scale, const vitk_dropout* attn_drop, void* stream) {
   VITK_CHECK_ARG(qkv && out && lse && attn_drop && attn_drop->seed, "vitk_attention_dropout_fwd: null pointer");
@@ -699,6 +702,7 @@ extern "C" int vitk_attention_dropout_fwd(const void* qkv, void* out, int32_t dt
   VITK_CHECK_ARG(attn_drop->p > 0.f && attn_drop->p < 1.f, "vitk_attention_dropout_fwd: need 0 < p < 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const DropSpec ds = make_drop_spec(attn_drop->seed, attn_drop->p, attn_drop->site);
+  if (N <= TC_MAX_TOKENS_FWD) return attention_fwd_tc(qkv, out, lse, B, N, H, scale, 0, dtype == VITK_FP16, &ds, st);
   const int Npad = (N + 7) & ~7;
   dim3 grid((N + TILE - 1) / TILE, H, B);
   if (dtype == VITK_FP16)

@@ -65,11 +65,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 // ================================================================================================ forward
 constexpr int FWD_THREADS = 160;
 
-template <bool H16>
+// DROP: nn.Dropout on the softmax output (Attention.attn_drop, vision_transformer_base.py:184): O = (P o M) V with the
+// counter-based factors M[b,h,q,key] = 0 | 1/(1-p) of element (((b*H + h)*N + q)*Npad + key) at `drop.site` (the same function
+// vitk_dropout_mask exports); the row sum and lse stay those of the unmasked P.
+template <bool H16, bool DROP>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
     attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                        const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KP, float scale,
-                       float scale_log2, int wave_ctas) {
+                       float scale_log2, int wave_ctas, DropSpec drop, int Npad) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -199,6 +202,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
     if (threadIdx.x == 0) FSTAMP(4);
     const float msc = mx * scale_log2;
     float2 sum2 = make_float2(0.f, 0.f), sum2b = make_float2(0.f, 0.f);
+    // DROP: counter block of this query row's first 8 keys (Npad % 8 == 0); block + k covers keys [8k, 8k + 8)
+    const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
+    const unsigned long long rowblk = DROP ? ((((unsigned long long)b * H + h) * N + (q < N ? q : 0)) * (unsigned long long)Npad) >> 3 : 0ull;
     for (int c0 = 0; warp_valid && c0 < KP; c0 += 32) {
       uint32_t v[32];
       const bool full = KP - c0 >= 32;
@@ -208,6 +214,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
         tmem_ld16_nowait(trow + uint32_t(c0), v);
 #pragma unroll
         for (int j = 16; j < 32; ++j) v[j] = 0u;
+      }
+      uint32_t dw[16];   // DROP: the 16-bit uniforms of the chunk's 32 keys, two per word
+      if constexpr (DROP) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint4 bits = drop_bits8(dseed, drop.site, rowblk + (unsigned long long)((c0 >> 3) + t));
+          dw[4 * t + 0] = bits.x;
+          dw[4 * t + 1] = bits.y;
+          dw[4 * t + 2] = bits.z;
+          dw[4 * t + 3] = bits.w;
+        }
       }
       tmem_ld_wait();
       uint32_t ph[16];
@@ -219,7 +236,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
           const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
           if (j & 2) sum2b = __fadd2_rn(sum2b, pp);
           else sum2 = __fadd2_rn(sum2, pp);
-          ph[j >> 1] = pk16<H16>(pp.x, pp.y);
+          if constexpr (DROP) {
+            const float2 f = drop_pair(dw[j >> 1], drop.thresh, drop.inv_keep);
+            ph[j >> 1] = pk16<H16>(pp.x * f.x, pp.y * f.y);
+          } else {
+            ph[j >> 1] = pk16<H16>(pp.x, pp.y);
+          }
         }
       } else {
 #pragma unroll
@@ -228,7 +250,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
           const float p0 = (c0 + j < N) ? ex2_approx(x.x) : 0.f;
           const float p1 = (c0 + j + 1 < N) ? ex2_approx(x.y) : 0.f;
           sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
-          ph[j >> 1] = pk16<H16>(p0, p1);
+          if constexpr (DROP) {
+            const float2 f = drop_pair(dw[j >> 1], drop.thresh, drop.inv_keep);
+            ph[j >> 1] = pk16<H16>(p0 * f.x, p1 * f.y);
+          } else {
+            ph[j >> 1] = pk16<H16>(p0, p1);
+          }
         }
       }
       if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
@@ -273,6 +300,246 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<256>(tb);
+}
+
+// ================================================================================================ forward, 257 .. 816 tokens
+// 384x384 images (577 tokens) and patch 8 at 224 (785): the keys no longer fit one S tile, so they are walked as NKT <= 4 tiles
+// of KT <= 256 keys.  All of K and V still sits in shared memory (one CTA per SM), S_j reuses TMEM columns [0, KT), and every key
+// tile gets ITS OWN 64-column O accumulator (columns 256 + 64 j) with its own row maximum m_j and row sum l_j: no accumulator is
+// ever rescaled in TMEM; the epilogue merges the partial results in registers,
+//   m = max_j m_j,  w_j = exp2((m_j - m) c),  O = sum_j w_j O_j / sum_j w_j l_j,  lse = m * scale + log(sum_j w_j l_j)
+// (the split-KV form of the online softmax).  The issuer only starts S_{j+1} after P_j V_j has completed (P_j lives in S's columns).
+constexpr int FWDL_MAX_TILES = 4;
+constexpr int OL_COL = 256;   // first O accumulator
+
+template <bool H16, bool DROP>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+    attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                            const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KT, int NKT, float scale,
+                            float scale_log2, DropSpec drop, int Npad) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int tile_bytes = KT * 128;
+  uint8_t* sQ = smem;                            // [128][64] 16-bit, later the output staging tile
+  uint8_t* sK = sQ + 128 * 128;                  // NKT x [KT][64]
+  uint8_t* sV = sK + NKT * tile_bytes;           // NKT x [KT][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NKT * tile_bytes);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;                    // [4] S_j complete
+  uint64_t* bar_p = bars + 6;                    // [4] P_j written (128 arrivals)
+  uint64_t* bar_o = bars + 10;                   // [4] P_j V_j complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmKV);
+      prefetch_tmap(&tmO);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+        mbar_init(bar_s + j, 1);
+        mbar_init(bar_p + j, 128);
+        mbar_init(bar_o + j, 1);
+      }
+      mbar_init_fence();
+      pdl_wait();  // qkv is the previous kernel's output
+      mbar_expect_tx(bar_qk, 128 * 128 + NKT * tile_bytes);
+      tma_load_3d(sQ, &tmQ, bar_qk, h * DH, q0, b);
+      for (int j = 0; j < NKT; ++j) tma_load_3d(sK + j * tile_bytes, &tmKV, bar_qk, (H + h) * DH, j * KT, b);
+      mbar_expect_tx(bar_v, NKT * tile_bytes);
+      for (int j = 0; j < NKT; ++j) tma_load_3d(sV + j * tile_bytes, &tmKV, bar_v, (2 * H + h) * DH, j * KT, b);
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  pdl_trigger();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== MMA issuer (one elected thread) =====================
+    if (elect_one()) {
+      mbar_wait(bar_qk, 0, 1);
+      tc_fence_after();
+      const uint32_t idesc_s = idesc_f16(KT, false, false, H16);
+      const uint32_t idesc_o = idesc_f16(DH, false, true, H16);
+      const uint64_t adesc = smem_desc_kmajor(smem_u32(sQ));
+      const int steps = KT >> 4;
+      for (int j = 0; j < NKT; ++j) {
+        if (j > 0) {                               // P_{j-1} (in S's columns) has been consumed
+          mbar_wait(bar_o + (j - 1), 0, 2);
+          tc_fence_after();
+        }
+        const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK + j * tile_bytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tb, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s + j);
+        mbar_wait(bar_p + j, 0, 3);
+        if (j == 0) mbar_wait(bar_v, 0, 4);
+        tc_fence_after();
+        const uint64_t vdesc = smem_desc_mnmajor(smem_u32(sV + j * tile_bytes), 8192);
+        for (int st = 0; st < steps; ++st)
+          umma_ts(tb + uint32_t(OL_COL + 64 * j), tb + uint32_t(8 * st), vdesc + uint64_t(st * (2048 >> 4)), idesc_o, st > 0 ? 1u : 0u);
+        umma_commit(bar_o + j);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue: one thread per query row =====================
+    const int row = warp * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t trow = tb + (uint32_t(warp * 32) << 16);
+    const bool warp_valid = q0 + warp * 32 < N;
+    const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
+    const unsigned long long rowblk = DROP ? ((((unsigned long long)b * H + h) * N + (q < N ? q : 0)) * (unsigned long long)Npad) >> 3 : 0ull;
+    float mj[FWDL_MAX_TILES], lj[FWDL_MAX_TILES];
+#pragma unroll
+    for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+      mj[j] = -INFINITY;
+      lj[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+      if (j < NKT) {
+        const int key0 = j * KT;
+        const int nv = min(KT, N - key0);          // valid keys of this tile (>= 1)
+        mbar_wait(bar_s + j, 0, 5);
+        tc_fence_after();
+        if (warp_valid) {
+          // pass 1: row maximum over the tile's valid keys
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          for (int c0 = 0; c0 < nv; c0 += 32) {
+            uint32_t v[32];
+            if (KT - c0 >= 32) {
+              tmem_ld32_nowait(trow + uint32_t(c0), v);
+            } else {
+              tmem_ld16_nowait(trow + uint32_t(c0), v);
+#pragma unroll
+              for (int i = 16; i < 32; ++i) v[i] = 0u;
+            }
+            tmem_ld_wait();
+            if (c0 + 32 <= nv) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], (c0 + i < nv) ? __uint_as_float(v[i]) : -INFINITY);
+            }
+          }
+          const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          // pass 2: P = exp2((S - max) * scale * log2e), 16-bit, in place; every column of the tile is written (0 beyond nv)
+          const float msc = mx * scale_log2;
+          const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-msc, -msc);
+          float2 sum2 = make_float2(0.f, 0.f);
+          for (int c0 = 0; c0 < KT; c0 += 32) {
+            uint32_t v[32];
+            const bool full = KT - c0 >= 32;
+            if (full) {
+              tmem_ld32_nowait(trow + uint32_t(c0), v);
+            } else {
+              tmem_ld16_nowait(trow + uint32_t(c0), v);
+#pragma unroll
+              for (int i = 16; i < 32; ++i) v[i] = 0u;
+            }
+            uint32_t dw[16];
+            if constexpr (DROP) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const uint4 bits = drop_bits8(dseed, drop.site, rowblk + (unsigned long long)(((key0 + c0) >> 3) + t));
+                dw[4 * t + 0] = bits.x;
+                dw[4 * t + 1] = bits.y;
+                dw[4 * t + 2] = bits.z;
+                dw[4 * t + 3] = bits.w;
+              }
+            }
+            tmem_ld_wait();
+            uint32_t ph[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+              const float p0 = (c0 + i < nv) ? ex2_approx(x.x) : 0.f;
+              const float p1 = (c0 + i + 1 < nv) ? ex2_approx(x.y) : 0.f;
+              sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
+              if constexpr (DROP) {
+                const float2 f = drop_pair(dw[i >> 1], drop.thresh, drop.inv_keep);
+                ph[i >> 1] = pk16<H16>(p0 * f.x, p1 * f.y);
+              } else {
+                ph[i >> 1] = pk16<H16>(p0, p1);
+              }
+            }
+            if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
+            else tmem_st8_nowait(trow + uint32_t(c0 >> 1), ph);
+          }
+          mj[j] = mx;
+          lj[j] = sum2.x + sum2.y;
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(bar_p + j);
+      }
+    }
+    // merge the key tiles' partial results
+    float m = mj[0];
+#pragma unroll
+    for (int j = 1; j < FWDL_MAX_TILES; ++j) m = fmaxf(m, mj[j]);
+    float wj[FWDL_MAX_TILES], L = 0.f;
+#pragma unroll
+    for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+      wj[j] = (j < NKT && warp_valid) ? ex2_approx((mj[j] - m) * scale_log2) : 0.f;
+      L = fmaf(wj[j], lj[j], L);
+    }
+    if (q < N) lse[((long long)b * H + h) * N + q] = fmaf(m, scale, logf(L));
+    const float inv = 1.f / L;
+#pragma unroll
+    for (int j = 0; j < FWDL_MAX_TILES; ++j) wj[j] *= inv;
+    mbar_wait(bar_o + (NKT - 1), 0, 6);            // commits are ordered: every earlier P_j V_j is complete as well
+    tc_fence_after();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (!warp_valid) break;
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+        if (j < NKT) {
+          uint32_t v[32];
+          tmem_ld32_nowait(trow + uint32_t(OL_COL + 64 * j + 32 * hh), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = fmaf(__uint_as_float(v[i]), wj[j], acc[i]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o;
+        o.x = pk16<H16>(acc[8 * c + 0], acc[8 * c + 1]);
+        o.y = pk16<H16>(acc[8 * c + 2], acc[8 * c + 3]);
+        o.z = pk16<H16>(acc[8 * c + 4], acc[8 * c + 5]);
+        o.w = pk16<H16>(acc[8 * c + 6], acc[8 * c + 7]);
+        *reinterpret_cast<uint4*>(sQ + swz128(row, 4 * hh + c)) = o;
+      }
+    }
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (warp == 0 && elect_one()) {
+      tma_store_3d(&tmO, sQ, h * DH, q0, b);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tb);
 }
 
 // ================================================================================================ eval-mode attention maps
@@ -399,12 +666,22 @@ constexpr int BWD_THREADS = 288;  // 8 math warps + 1 control warp
 constexpr int TM_S = 0, TM_DP = 64, TM_PT = 128 /* +64*buf */, TM_DS = 160 /* +64*buf */, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
 
 // Math of one chunk for one thread: W (32 or 16) query columns starting at column g0 of the chunk, key lane = this thread.
-template <bool H16, int W>
+// DROP (attention-probability dropout, see the forward): with the factors m = M[q,key], dV += (P o M)^T dO and
+// dS = P o (M o dP - delta) (delta = rowsum(dO o O) is unchanged: sum_k P_k M_k dP_k = dO . O).  The walk is transposed (this
+// thread = one key, W queries), so every element needs its own counter block: dblk0 = block of (query qbase + g0, this key),
+// dstep = blocks per query row (Npad / 8), dhalf = which 16-bit uniform of the block belongs to this key.
+template <bool H16, int W, bool DROP>
 __device__ __forceinline__ void bwd_math(const uint32_t (&sv)[32], const uint32_t (&dv)[32], uint32_t trow, int g0, int buf,
                                          const float* __restrict__ s_lse2, const float* __restrict__ s_delta, int qbase,
-                                         float scale_log2, bool keyvalid, uint8_t* sDSblk, int keyrow) {
+                                         float scale_log2, bool keyvalid, uint8_t* sDSblk, int keyrow, const DropSpec& drop,
+                                         unsigned long long dseed, unsigned long long dblk0, unsigned long long dstep, int dhalf) {
   uint32_t ph[W / 2], dh[W / 2];
   const float2 sc2 = make_float2(scale_log2, scale_log2);
+  auto dfac = [&](int i) -> float {   // dropout factor of query (qbase + g0 + i) x this key
+    const uint4 bits = drop_bits8(dseed, drop.site, dblk0 + (unsigned long long)i * dstep);
+    const uint32_t w = (dhalf >> 1) == 0 ? bits.x : (dhalf >> 1) == 1 ? bits.y : (dhalf >> 1) == 2 ? bits.z : bits.w;
+    return (((dhalf & 1) ? (w >> 16) : (w & 0xffffu)) >= drop.thresh) ? drop.inv_keep : 0.f;
+  };
 #pragma unroll
   for (int e = 0; e < W; e += 4) {
     // s_lse2 / s_delta hold the NEGATED statistics (-lse*log2e, -delta): everything below is packed fp32x2 math
@@ -414,11 +691,21 @@ __device__ __forceinline__ void bwd_math(const uint32_t (&sv)[32], const uint32_
     const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sc2, make_float2(l4.z, l4.w));
     const float2 p01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
     const float2 p23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
-    const float2 t01 = __fadd2_rn(make_float2(__uint_as_float(dv[e + 0]), __uint_as_float(dv[e + 1])), make_float2(d4.x, d4.y));
-    const float2 t23 = __fadd2_rn(make_float2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), make_float2(d4.z, d4.w));
+    float2 t01, t23;
+    if constexpr (DROP) {
+      const float2 m01 = make_float2(dfac(e + 0), dfac(e + 1)), m23 = make_float2(dfac(e + 2), dfac(e + 3));
+      t01 = __ffma2_rn(make_float2(__uint_as_float(dv[e + 0]), __uint_as_float(dv[e + 1])), m01, make_float2(d4.x, d4.y));
+      t23 = __ffma2_rn(make_float2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), m23, make_float2(d4.z, d4.w));
+      const float2 q01 = __fmul2_rn(p01, m01), q23 = __fmul2_rn(p23, m23);
+      ph[(e >> 1) + 0] = pk16<H16>(q01.x, q01.y);
+      ph[(e >> 1) + 1] = pk16<H16>(q23.x, q23.y);
+    } else {
+      t01 = __fadd2_rn(make_float2(__uint_as_float(dv[e + 0]), __uint_as_float(dv[e + 1])), make_float2(d4.x, d4.y));
+      t23 = __fadd2_rn(make_float2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), make_float2(d4.z, d4.w));
+      ph[(e >> 1) + 0] = pk16<H16>(p01.x, p01.y);
+      ph[(e >> 1) + 1] = pk16<H16>(p23.x, p23.y);
+    }
     const float2 s01 = __fmul2_rn(p01, t01), s23 = __fmul2_rn(p23, t23);
-    ph[(e >> 1) + 0] = pk16<H16>(p01.x, p01.y);
-    ph[(e >> 1) + 1] = pk16<H16>(p23.x, p23.y);
     dh[(e >> 1) + 0] = pk16<H16>(s01.x, s01.y);
     dh[(e >> 1) + 1] = pk16<H16>(s23.x, s23.y);
   }
@@ -439,12 +726,12 @@ __device__ __forceinline__ void bwd_math(const uint32_t (&sv)[32], const uint32_
     *reinterpret_cast<uint4*>(sDSblk + swz128(keyrow, (g0 >> 3) + ch)) = make_uint4(dh[4 * ch], dh[4 * ch + 1], dh[4 * ch + 2], dh[4 * ch + 3]);
 }
 
-template <bool H16>
+template <bool H16, bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
     attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQKV,
                        const float* __restrict__ lse, float* __restrict__ delta, int N, int H, int QP, float scale,
-                       float scale_log2, int wave_ctas, int q_chunks) {
+                       float scale_log2, int wave_ctas, int q_chunks, DropSpec drop, int Npad) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -640,9 +927,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
       named_bar_sync(1, 256);
     }
     if (tid == 0) ASTAMP(64);
+    const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
+    const unsigned long long dstep = (unsigned long long)(Npad >> 3);
+    const unsigned long long drow0 = ((unsigned long long)b * H + h) * N;   // first query row of this (image, head)
     int t = 0;
     for (int j = 0; j < NJ; ++j) {
       const bool keyvalid = (j * 128 + keyrow) < N;
+      const int dkey = j * 128 + keyrow;
       for (int c = 0; c < NCH; ++c, ++t) {
         const int QC = min(64, QP - 64 * c);
         const int g0 = half * 32;                       // this warp's columns: [g0, min(g0 + 32, QC))
@@ -670,8 +961,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
         if (t >= 2) mbar_wait(bar_m2 + buf, ((t >> 1) - 1) & 1, 8);
         tc_fence_after();
         if (tid == 0) ASTAMP(71 + 8 * t);
-        if (w == 32) bwd_math<H16, 32>(sv, dv, trow, g0, buf, s_lse2, s_delta, c * 64, scale_log2, keyvalid, sDSblk, keyrow);
-        else if (w == 16) bwd_math<H16, 16>(sv, dv, trow, g0, buf, s_lse2, s_delta, c * 64, scale_log2, keyvalid, sDSblk, keyrow);
+        // DROP: counter block of (query c*64 + g0, key dkey); padded queries / keys produce P = 0 whatever the factor
+        const unsigned long long dblk0 = DROP ? (drow0 + (unsigned long long)(c * 64 + g0)) * dstep + (unsigned long long)(dkey >> 3) : 0ull;
+        if (w == 32)
+          bwd_math<H16, 32, DROP>(sv, dv, trow, g0, buf, s_lse2, s_delta, c * 64, scale_log2, keyvalid, sDSblk, keyrow, drop, dseed, dblk0,
+                                  dstep, dkey & 7);
+        else if (w == 16)
+          bwd_math<H16, 16, DROP>(sv, dv, trow, g0, buf, s_lse2, s_delta, c * 64, scale_log2, keyvalid, sDSblk, keyrow, drop, dseed, dblk0,
+                                  dstep, dkey & 7);
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
@@ -795,8 +1092,9 @@ int make_tmap_3d(CUtensorMap* tm, const void* base, int width, int N, int B, int
 }  // namespace
 
 // Forward for N <= 256.  Returns VITK_OK or an error; the caller (attention.cu) owns argument validation.
-template <bool H16>
-int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, cudaStream_t st) {
+template <bool H16, bool DROP>
+int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, DropSpec drop,
+                          cudaStream_t st) {
   const int KP = (N + 15) & ~15;
   CUtensorMap tmQ, tmKV, tmO;
   int rc;
@@ -804,7 +1102,7 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
   if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KP, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
   const int smem = 128 * 128 + 2 * KP * 128 + 64 + 1024;
-  auto kfn = attn_fwd_tc_kernel<H16>;
+  auto kfn = attn_fwd_tc_kernel<H16, DROP>;
   static int configured = 0;
   if (configured < smem) {
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 + 2 * 256 * 128 + 64 + 1024));
@@ -814,14 +1112,48 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
   const int q_need = q_rows > 0 && q_rows < N ? q_rows : N;
   dim3 grid((q_need + 127) / 128, H, B);
   VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, lse, N, H, KP, scale, scale * LOG2E,
-                       2 * num_sms()));
+                       2 * num_sms(), drop, (N + 7) & ~7));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
 
-template <bool H16>
+// Forward for 256 < N <= 816 (key tiles, see attn_fwd_tc_long_kernel).
+template <bool H16, bool DROP>
+int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, DropSpec drop,
+                               cudaStream_t st) {
+  const int NKT = (N + 255) / 256;
+  const int KT = (((N + NKT - 1) / NKT) + 15) & ~15;
+  if (NKT > FWDL_MAX_TILES || KT > 256 || (NKT - 1) * KT >= N) {
+    set_error("attention_fwd_tc_long: N=%d out of range", N);
+    return VITK_ERR_INVALID;
+  }
+  CUtensorMap tmQ, tmKV, tmO;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KT, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  const int smem = 128 * 128 + 2 * NKT * KT * 128 + 128 + 1024;
+  if (smem > 227 * 1024) {
+    set_error("attention_fwd_tc_long: N=%d needs %d bytes of shared memory", N, smem);
+    return VITK_ERR_INVALID;
+  }
+  auto kfn = attn_fwd_tc_long_kernel<H16, DROP>;
+  static int configured = 0;
+  if (configured < smem) {
+    VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  const int q_need = q_rows > 0 && q_rows < N ? q_rows : N;
+  dim3 grid((q_need + 127) / 128, H, B);
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, lse, N, H, KT, NKT, scale, scale * LOG2E, drop,
+                       (N + 7) & ~7));
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+template <bool H16, bool DROP>
 int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
-                          int H, float scale, int q_rows, cudaStream_t st) {
+                          int H, float scale, int q_rows, DropSpec drop, cudaStream_t st) {
   const int QP = (N + 15) & ~15;
   CUtensorMap tmQKV, tmDO, tmO, tmDQKV;
   int rc;
@@ -831,7 +1163,7 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
   if ((rc = make_tmap_3d(&tmDQKV, dqkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
   const int smem = 4 * QP * 128 + 98304 + 2048 + 128 + 1024;
   const int smem_max = 4 * 240 * 128 + 98304 + 2048 + 128 + 1024;
-  auto kfn = attn_bwd_tc_kernel<H16>;
+  auto kfn = attn_bwd_tc_kernel<H16, DROP>;
   static bool configured = false;
   if (!configured) {
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
@@ -840,7 +1172,7 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
   dim3 grid(H, B);
   const int q_chunks = q_rows > 0 && q_rows < N ? (q_rows + 63) / 64 : 0;
   VITK_CUDA(launch_pdl(kfn, grid, dim3(BWD_THREADS), (size_t)smem, st, tmQKV, tmDO, tmO, tmDQKV, lse, delta, N, H, QP, scale,
-                       scale * LOG2E, num_sms(), q_chunks));
+                       scale * LOG2E, num_sms(), q_chunks, drop, (N + 7) & ~7));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -876,14 +1208,32 @@ int attention_probs_tc(const void* qkv, const float* lse, float* probs, long lon
               : attention_probs_tc_impl<false>(qkv, lse, probs, batch_stride, B, N, H, scale, st);
 }
 
-int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, cudaStream_t st) {
-  return fp16 ? attention_fwd_tc_impl<true>(qkv, out, lse, B, N, H, scale, q_rows, st)
-              : attention_fwd_tc_impl<false>(qkv, out, lse, B, N, H, scale, q_rows, st);
+// drop == nullptr: no attention-probability dropout (every configuration the reference ships)
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, const DropSpec* drop,
+                     cudaStream_t st) {
+  const DropSpec none = make_drop_spec(nullptr, 0.f, 0);
+  const bool dropping = drop != nullptr && drop->seed != nullptr;
+  if (N > 256) {
+    if (dropping)
+      return fp16 ? attention_fwd_tc_long_impl<true, true>(qkv, out, lse, B, N, H, scale, q_rows, *drop, st)
+                  : attention_fwd_tc_long_impl<false, true>(qkv, out, lse, B, N, H, scale, q_rows, *drop, st);
+    return fp16 ? attention_fwd_tc_long_impl<true, false>(qkv, out, lse, B, N, H, scale, q_rows, none, st)
+                : attention_fwd_tc_long_impl<false, false>(qkv, out, lse, B, N, H, scale, q_rows, none, st);
+  }
+  if (dropping)
+    return fp16 ? attention_fwd_tc_impl<true, true>(qkv, out, lse, B, N, H, scale, q_rows, *drop, st)
+                : attention_fwd_tc_impl<false, true>(qkv, out, lse, B, N, H, scale, q_rows, *drop, st);
+  return fp16 ? attention_fwd_tc_impl<true, false>(qkv, out, lse, B, N, H, scale, q_rows, none, st)
+              : attention_fwd_tc_impl<false, false>(qkv, out, lse, B, N, H, scale, q_rows, none, st);
 }
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
-                     int H, float scale, int q_rows, bool fp16, cudaStream_t st) {
-  return fp16 ? attention_bwd_tc_impl<true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, st)
-              : attention_bwd_tc_impl<false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, st);
+                     int H, float scale, int q_rows, bool fp16, const DropSpec* drop, cudaStream_t st) {
+  const DropSpec none = make_drop_spec(nullptr, 0.f, 0);
+  if (drop != nullptr && drop->seed != nullptr)
+    return fp16 ? attention_bwd_tc_impl<true, true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, *drop, st)
+                : attention_bwd_tc_impl<false, true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, *drop, st);
+  return fp16 ? attention_bwd_tc_impl<true, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, none, st)
+              : attention_bwd_tc_impl<false, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, none, st);
 }
 
 }  // namespace vitk

@@ -623,7 +623,10 @@ def cls_attention_heatmap(src, out_hw, n_prefix: int = 1):
     """Class-token heat maps fp32 [B,out_h,out_w] (attention_utils.py:50-67, every image of the batch).
     src: one layer's maps fp32 [B,H,N,N] (any batch / head strides, rows contiguous), a rollout row [B,N] (then n_prefix
     patch-prefix columns are skipped) or a grid [B,g,g] (n_prefix is ignored)."""
-    _req(src, f32, "heat-map source")
+    if not src.is_cuda:
+        raise RuntimeError("heat-map source: expected a CUDA tensor (libvitk has no CPU path)")
+    if src.dtype != f32:
+        raise RuntimeError(f"heat-map source: expected dtype {f32}, got {src.dtype}")
     oh, ow = int(out_hw[0]), int(out_hw[1])
     if src.dim() == 4:
         B, H, N, N2 = src.shape
