@@ -227,7 +227,8 @@ def _attn_ref(qkv, B, N, H, scale):
     return o, p, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (3, 197, 12), (1, 64, 1), (2, 577, 3), (1, 17, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (3, 197, 12), (1, 64, 1), (2, 577, 3), (1, 17, 2), (2, 257, 2), (1, 785, 2),
+                                   (2, 1025, 1), (1, 2305, 1)])
 @pytest.mark.parametrize("dt", [F16, BF16])
 def test_attention_fwd_bwd(B, N, H, dt):
     scale = 64 ** -0.5
@@ -246,7 +247,7 @@ def test_attention_fwd_bwd(B, N, H, dt):
     assert rel_l2(dqkv, qr.grad) < 2 * tol
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (1, 64, 1), (2, 577, 3), (1, 17, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (1, 64, 1), (2, 577, 3), (1, 17, 2), (1, 1025, 2)])
 @pytest.mark.parametrize("dt", [F16, BF16])
 def test_attention_dropout_fwd_bwd(B, N, H, dt):
     """vitk_attention_dropout_{fwd,bwd}: nn.Dropout on the softmax output (vision_transformer_base.py:184).  The mask is the

@@ -568,7 +568,8 @@ def test_last_block_on_classifier_rows_equals_dense(deit):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,H,q_rows", [(198, 3, 2), (197, 12, 1), (64, 2, 2), (198, 3, 70), (198, 3, 130)])
+@pytest.mark.parametrize("N,H,q_rows", [(198, 3, 2), (197, 12, 1), (64, 2, 2), (198, 3, 70), (198, 3, 130), (577, 3, 2), (577, 2, 130),
+                                         (1025, 1, 1)])
 def test_attention_leading_query_rows(N, H, q_rows):
     """vitk_attention_fwd / _bwd with q_rows: the leading rows of out / lse equal the full forward's, and with dout zero from
     row q_rows on the backward's dqkv equals the full backward's (bit-exact: the skipped chunks only ever add zeros)."""

@@ -15,6 +15,8 @@
 // Round-1 implementation: warp-level mma.sync m16n8k16 (HMMA) with ldmatrix from
 // XOR-swizzled shared tiles.  The tcgen05/TMEM version (S and P resident in TMEM, N<=256 in a
 // single tile) is the planned replacement; the C-ABI below is already the one it will keep.
+#include <cstdlib>
+
 #include "vitk_common.cuh"
 
 namespace vitk {
@@ -588,7 +590,7 @@ __global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restric
 
 // tcgen05 / TMEM kernels for sequences of up to 256 tokens (attention_tc.cu)
 constexpr int TC_MAX_TOKENS = 256;      // eval-mode maps (one S tile)
-constexpr int TC_MAX_TOKENS_FWD = 816;  // forward: one S tile up to 256 tokens, 2..4 key tiles beyond (384x384 images: 577; patch 8: 785)
+constexpr int TC_MAX_TOKENS_FWD = 1 << 30;  // forward: one S tile up to 256 tokens, key tiles beyond (384x384 images: 577; patch 8: 785 / 1025)
 constexpr int TC_MAX_TOKENS_BWD = 240;  // backward (shared-memory budget of the pipelined kernel)
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, const DropSpec* drop,
                      cudaStream_t st);
@@ -596,6 +598,8 @@ int attention_probs_tc(const void* qkv, const float* lse, float* probs, long lon
                        bool fp16, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B, int N,
                      int H, float scale, int q_rows, bool fp16, const DropSpec* drop, cudaStream_t st);
+int attention_bwd_tc_long(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
+                          float scale, int q_rows, bool fp16, const DropSpec* drop, cudaStream_t st);
 }  // namespace vitk
 
 using namespace vitk;
@@ -650,6 +654,14 @@ extern "C" int vitk_attention_probs(const void* qkv, int32_t dtype, const float*
                             : attention_probs_impl<false>(qkv, lse, probs, probs_batch_stride, B, N, H, scale, st);
 }
 
+static bool tc_long_bwd_enabled() {     // VITK_ATTN_LEGACY_BWD=1: the mma.sync kernels (A/B measurements only)
+  static const bool on = [] {
+    const char* e = getenv("VITK_ATTN_LEGACY_BWD");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
+
 template <bool H16, bool DROP>
 static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                               int B, int N, int H, float scale, DropSpec drop, cudaStream_t st, int q_rows = 0) {
@@ -665,6 +677,8 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
   attn_delta_kernel<H16><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(out),
                                                                      reinterpret_cast<const bf16*>(dout), delta, B, N, H);
   VITK_LAUNCH_CHECK();
+  if (tc_long_bwd_enabled())
+    return attention_bwd_tc_long(qkv, dout, lse, delta, dqkv, B, N, H, scale, q_rows, H16, DROP ? &drop : nullptr, st);
   dim3 grid((N + TILE - 1) / TILE, H, B);
   attn_bwd_dkdv_kernel<H16, DROP><<<grid, 128, sizeof(BwdSmem), st>>>(reinterpret_cast<const bf16*>(qkv),
                                                                       reinterpret_cast<const bf16*>(dout), lse, delta,

@@ -302,38 +302,43 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   if (warp == 4) tmem_dealloc<256>(tb);
 }
 
-// ================================================================================================ forward, 257 .. 816 tokens
-// 384x384 images (577 tokens) and patch 8 at 224 (785): the keys no longer fit one S tile, so they are walked as NKT <= 4 tiles
-// of KT <= 256 keys.  All of K and V still sits in shared memory (one CTA per SM), S_j reuses TMEM columns [0, KT), and every key
-// tile gets ITS OWN 64-column O accumulator (columns 256 + 64 j) with its own row maximum m_j and row sum l_j: no accumulator is
-// ever rescaled in TMEM; the epilogue merges the partial results in registers,
-//   m = max_j m_j,  w_j = exp2((m_j - m) c),  O = sum_j w_j O_j / sum_j w_j l_j,  lse = m * scale + log(sum_j w_j l_j)
-// (the split-KV form of the online softmax).  The issuer only starts S_{j+1} after P_j V_j has completed (P_j lives in S's columns).
+// ================================================================================================ forward, > 256 tokens
+// 384x384 images (577 tokens), patch 8 (785 / 1025 / 2305 tokens): the keys no longer fit one S tile, so they are walked as tiles
+// of KT <= 256 keys, in groups of TPG <= 4 tiles whose K and V sit in shared memory together (one CTA per SM; up to 816 tokens
+// that is ONE group, i.e. K and V are loaded once, exactly like the short kernel).  S_j reuses TMEM columns [0, KT); every tile of
+// a group gets ITS OWN 64-column O accumulator (columns 256 + 64 j) with its own row maximum m_j and row sum l_j, so no
+// accumulator is ever rescaled in TMEM: at the end of a group the softmax threads merge the partial results into a
+// register-resident running (m, L, O[64]) -- the split-KV form of the online softmax,
+//   m' = max(m, max_j m_j),  O' = O 2^((m - m') c) + sum_j 2^((m_j - m') c) O_j,  L' likewise,  out = O / L,  lse = m scale + log L.
+// The issuer starts S_{j+1} only after P_j V_j has completed (P_j lives in S's columns) and the next group's loads only after the
+// group's last MMA; the group's first P V waits until the previous group's accumulators have been read (bar_free).
 constexpr int FWDL_MAX_TILES = 4;
 constexpr int OL_COL = 256;   // first O accumulator
 
 template <bool H16, bool DROP>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
     attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                            const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KT, int NKT, float scale,
-                            float scale_log2, DropSpec drop, int Npad) {
+                            const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KT, int NKT, int TPG,
+                            float scale, float scale_log2, DropSpec drop, int Npad) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int tile_bytes = KT * 128;
   uint8_t* sQ = smem;                            // [128][64] 16-bit, later the output staging tile
-  uint8_t* sK = sQ + 128 * 128;                  // NKT x [KT][64]
-  uint8_t* sV = sK + NKT * tile_bytes;           // NKT x [KT][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NKT * tile_bytes);
-  uint64_t* bar_qk = bars + 0;
+  uint8_t* sK = sQ + 128 * 128;                  // TPG x [KT][64]
+  uint8_t* sV = sK + TPG * tile_bytes;           // TPG x [KT][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + TPG * tile_bytes);
+  uint64_t* bar_qk = bars + 0;                   // phase = group
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_s = bars + 2;                    // [4] S_j complete
   uint64_t* bar_p = bars + 6;                    // [4] P_j written (128 arrivals)
   uint64_t* bar_o = bars + 10;                   // [4] P_j V_j complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_free = bars + 14;                // the group's O accumulators have been read (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int NG = (NKT + TPG - 1) / TPG;
 
   if (warp == 4) {
     if (elect_one()) {
@@ -347,13 +352,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
         mbar_init(bar_p + j, 128);
         mbar_init(bar_o + j, 1);
       }
+      mbar_init(bar_free, 128);
       mbar_init_fence();
       pdl_wait();  // qkv is the previous kernel's output
-      mbar_expect_tx(bar_qk, 128 * 128 + NKT * tile_bytes);
+      const int nt0 = min(TPG, NKT);
+      mbar_expect_tx(bar_qk, 128 * 128 + nt0 * tile_bytes);
       tma_load_3d(sQ, &tmQ, bar_qk, h * DH, q0, b);
-      for (int j = 0; j < NKT; ++j) tma_load_3d(sK + j * tile_bytes, &tmKV, bar_qk, (H + h) * DH, j * KT, b);
-      mbar_expect_tx(bar_v, NKT * tile_bytes);
-      for (int j = 0; j < NKT; ++j) tma_load_3d(sV + j * tile_bytes, &tmKV, bar_v, (2 * H + h) * DH, j * KT, b);
+      for (int j = 0; j < nt0; ++j) tma_load_3d(sK + j * tile_bytes, &tmKV, bar_qk, (H + h) * DH, j * KT, b);
+      mbar_expect_tx(bar_v, nt0 * tile_bytes);
+      for (int j = 0; j < nt0; ++j) tma_load_3d(sV + j * tile_bytes, &tmKV, bar_v, (2 * H + h) * DH, j * KT, b);
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
@@ -368,28 +375,45 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
   if (warp == 4) {
     // ===================== MMA issuer (one elected thread) =====================
     if (elect_one()) {
-      mbar_wait(bar_qk, 0, 1);
-      tc_fence_after();
       const uint32_t idesc_s = idesc_f16(KT, false, false, H16);
       const uint32_t idesc_o = idesc_f16(DH, false, true, H16);
       const uint64_t adesc = smem_desc_kmajor(smem_u32(sQ));
       const int steps = KT >> 4;
-      for (int j = 0; j < NKT; ++j) {
-        if (j > 0) {                               // P_{j-1} (in S's columns) has been consumed
-          mbar_wait(bar_o + (j - 1), 0, 2);
-          tc_fence_after();
-        }
-        const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK + j * tile_bytes));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tb, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s + j);
-        mbar_wait(bar_p + j, 0, 3);
-        if (j == 0) mbar_wait(bar_v, 0, 4);
+      for (int g = 0; g < NG; ++g) {
+        const uint32_t par = uint32_t(g & 1);
+        const int ntg = min(TPG, NKT - g * TPG);
+        mbar_wait(bar_qk, par, 1);
         tc_fence_after();
-        const uint64_t vdesc = smem_desc_mnmajor(smem_u32(sV + j * tile_bytes), 8192);
-        for (int st = 0; st < steps; ++st)
-          umma_ts(tb + uint32_t(OL_COL + 64 * j), tb + uint32_t(8 * st), vdesc + uint64_t(st * (2048 >> 4)), idesc_o, st > 0 ? 1u : 0u);
-        umma_commit(bar_o + j);
+        for (int j = 0; j < ntg; ++j) {
+          if (j > 0) {                             // P_{j-1} (in S's columns) has been consumed
+            mbar_wait(bar_o + (j - 1), par, 2);
+            tc_fence_after();
+          }
+          const uint64_t bdesc = smem_desc_kmajor(smem_u32(sK + j * tile_bytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tb, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_s + j);
+          mbar_wait(bar_p + j, par, 3);
+          if (j == 0) {
+            mbar_wait(bar_v, par, 4);
+            if (g > 0) mbar_wait(bar_free, uint32_t((g - 1) & 1), 7);   // the previous group's accumulators have been merged
+          }
+          tc_fence_after();
+          const uint64_t vdesc = smem_desc_mnmajor(smem_u32(sV + j * tile_bytes), 8192);
+          for (int st = 0; st < steps; ++st)
+            umma_ts(tb + uint32_t(OL_COL + 64 * j), tb + uint32_t(8 * st), vdesc + uint64_t(st * (2048 >> 4)), idesc_o, st > 0 ? 1u : 0u);
+          umma_commit(bar_o + j);
+        }
+        if (g + 1 < NG) {                          // K / V of this group are dead once its last MMA has completed
+          mbar_wait(bar_o + (ntg - 1), par, 8);
+          tc_fence_after();
+          const int t0 = (g + 1) * TPG;
+          const int ntn = min(TPG, NKT - t0);
+          mbar_expect_tx(bar_qk, ntn * tile_bytes);
+          for (int j = 0; j < ntn; ++j) tma_load_3d(sK + j * tile_bytes, &tmKV, bar_qk, (H + h) * DH, (t0 + j) * KT, b);
+          mbar_expect_tx(bar_v, ntn * tile_bytes);
+          for (int j = 0; j < ntn; ++j) tma_load_3d(sV + j * tile_bytes, &tmKV, bar_v, (2 * H + h) * DH, (t0 + j) * KT, b);
+        }
       }
     }
     __syncwarp();
@@ -401,132 +425,145 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
     const bool warp_valid = q0 + warp * 32 < N;
     const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
     const unsigned long long rowblk = DROP ? ((((unsigned long long)b * H + h) * N + (q < N ? q : 0)) * (unsigned long long)Npad) >> 3 : 0ull;
-    float mj[FWDL_MAX_TILES], lj[FWDL_MAX_TILES];
+    float m_run = -INFINITY, L_run = 0.f;
+    float acc[64];
 #pragma unroll
-    for (int j = 0; j < FWDL_MAX_TILES; ++j) {
-      mj[j] = -INFINITY;
-      lj[j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < FWDL_MAX_TILES; ++j) {
-      if (j < NKT) {
-        const int key0 = j * KT;
-        const int nv = min(KT, N - key0);          // valid keys of this tile (>= 1)
-        mbar_wait(bar_s + j, 0, 5);
-        tc_fence_after();
-        if (warp_valid) {
-          // pass 1: row maximum over the tile's valid keys
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          for (int c0 = 0; c0 < nv; c0 += 32) {
-            uint32_t v[32];
-            if (KT - c0 >= 32) {
-              tmem_ld32_nowait(trow + uint32_t(c0), v);
-            } else {
-              tmem_ld16_nowait(trow + uint32_t(c0), v);
-#pragma unroll
-              for (int i = 16; i < 32; ++i) v[i] = 0u;
-            }
-            tmem_ld_wait();
-            if (c0 + 32 <= nv) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], (c0 + i < nv) ? __uint_as_float(v[i]) : -INFINITY);
-            }
-          }
-          const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          // pass 2: P = exp2((S - max) * scale * log2e), 16-bit, in place; every column of the tile is written (0 beyond nv)
-          const float msc = mx * scale_log2;
-          const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-msc, -msc);
-          float2 sum2 = make_float2(0.f, 0.f);
-          for (int c0 = 0; c0 < KT; c0 += 32) {
-            uint32_t v[32];
-            const bool full = KT - c0 >= 32;
-            if (full) {
-              tmem_ld32_nowait(trow + uint32_t(c0), v);
-            } else {
-              tmem_ld16_nowait(trow + uint32_t(c0), v);
-#pragma unroll
-              for (int i = 16; i < 32; ++i) v[i] = 0u;
-            }
-            uint32_t dw[16];
-            if constexpr (DROP) {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const uint4 bits = drop_bits8(dseed, drop.site, rowblk + (unsigned long long)(((key0 + c0) >> 3) + t));
-                dw[4 * t + 0] = bits.x;
-                dw[4 * t + 1] = bits.y;
-                dw[4 * t + 2] = bits.z;
-                dw[4 * t + 3] = bits.w;
-              }
-            }
-            tmem_ld_wait();
-            uint32_t ph[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
-              const float p0 = (c0 + i < nv) ? ex2_approx(x.x) : 0.f;
-              const float p1 = (c0 + i + 1 < nv) ? ex2_approx(x.y) : 0.f;
-              sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
-              if constexpr (DROP) {
-                const float2 f = drop_pair(dw[i >> 1], drop.thresh, drop.inv_keep);
-                ph[i >> 1] = pk16<H16>(p0 * f.x, p1 * f.y);
-              } else {
-                ph[i >> 1] = pk16<H16>(p0, p1);
-              }
-            }
-            if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
-            else tmem_st8_nowait(trow + uint32_t(c0 >> 1), ph);
-          }
-          mj[j] = mx;
-          lj[j] = sum2.x + sum2.y;
-          tmem_st_wait();
-        }
-        tc_fence_before();
-        mbar_arrive(bar_p + j);
-      }
-    }
-    // merge the key tiles' partial results
-    float m = mj[0];
-#pragma unroll
-    for (int j = 1; j < FWDL_MAX_TILES; ++j) m = fmaxf(m, mj[j]);
-    float wj[FWDL_MAX_TILES], L = 0.f;
-#pragma unroll
-    for (int j = 0; j < FWDL_MAX_TILES; ++j) {
-      wj[j] = (j < NKT && warp_valid) ? ex2_approx((mj[j] - m) * scale_log2) : 0.f;
-      L = fmaf(wj[j], lj[j], L);
-    }
-    if (q < N) lse[((long long)b * H + h) * N + q] = fmaf(m, scale, logf(L));
-    const float inv = 1.f / L;
-#pragma unroll
-    for (int j = 0; j < FWDL_MAX_TILES; ++j) wj[j] *= inv;
-    mbar_wait(bar_o + (NKT - 1), 0, 6);            // commits are ordered: every earlier P_j V_j is complete as well
-    tc_fence_after();
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      if (!warp_valid) break;
-      float acc[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int g = 0; g < NG; ++g) {
+      const uint32_t par = uint32_t(g & 1);
+      const int ntg = min(TPG, NKT - g * TPG);
+      float mj[FWDL_MAX_TILES], lj[FWDL_MAX_TILES];
 #pragma unroll
       for (int j = 0; j < FWDL_MAX_TILES; ++j) {
-        if (j < NKT) {
-          uint32_t v[32];
-          tmem_ld32_nowait(trow + uint32_t(OL_COL + 64 * j + 32 * hh), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] = fmaf(__uint_as_float(v[i]), wj[j], acc[i]);
-        }
+        mj[j] = -INFINITY;
+        lj[j] = 0.f;
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+        if (j < ntg) {
+          const int key0 = (g * TPG + j) * KT;
+          const int nv = min(KT, N - key0);          // valid keys of this tile (>= 1)
+          mbar_wait(bar_s + j, par, 5);
+          tc_fence_after();
+          if (warp_valid) {
+            // pass 1: row maximum over the tile's valid keys
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            for (int c0 = 0; c0 < nv; c0 += 32) {
+              uint32_t v[32];
+              if (KT - c0 >= 32) {
+                tmem_ld32_nowait(trow + uint32_t(c0), v);
+              } else {
+                tmem_ld16_nowait(trow + uint32_t(c0), v);
+#pragma unroll
+                for (int i = 16; i < 32; ++i) v[i] = 0u;
+              }
+              tmem_ld_wait();
+              if (c0 + 32 <= nv) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], (c0 + i < nv) ? __uint_as_float(v[i]) : -INFINITY);
+              }
+            }
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            // pass 2: P = exp2((S - max) * scale * log2e), 16-bit, in place; every column of the tile is written (0 beyond nv)
+            const float msc = mx * scale_log2;
+            const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-msc, -msc);
+            float2 sum2 = make_float2(0.f, 0.f);
+            for (int c0 = 0; c0 < KT; c0 += 32) {
+              uint32_t v[32];
+              const bool full = KT - c0 >= 32;
+              if (full) {
+                tmem_ld32_nowait(trow + uint32_t(c0), v);
+              } else {
+                tmem_ld16_nowait(trow + uint32_t(c0), v);
+#pragma unroll
+                for (int i = 16; i < 32; ++i) v[i] = 0u;
+              }
+              uint32_t dw[16];
+              if constexpr (DROP) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const uint4 bits = drop_bits8(dseed, drop.site, rowblk + (unsigned long long)(((key0 + c0) >> 3) + t));
+                  dw[4 * t + 0] = bits.x;
+                  dw[4 * t + 1] = bits.y;
+                  dw[4 * t + 2] = bits.z;
+                  dw[4 * t + 3] = bits.w;
+                }
+              }
+              tmem_ld_wait();
+              uint32_t ph[16];
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+                const float p0 = (c0 + i < nv) ? ex2_approx(x.x) : 0.f;
+                const float p1 = (c0 + i + 1 < nv) ? ex2_approx(x.y) : 0.f;
+                sum2 = __fadd2_rn(sum2, make_float2(p0, p1));
+                if constexpr (DROP) {
+                  const float2 f = drop_pair(dw[i >> 1], drop.thresh, drop.inv_keep);
+                  ph[i >> 1] = pk16<H16>(p0 * f.x, p1 * f.y);
+                } else {
+                  ph[i >> 1] = pk16<H16>(p0, p1);
+                }
+              }
+              if (full) tmem_st16_nowait(trow + uint32_t(c0 >> 1), ph);
+              else tmem_st8_nowait(trow + uint32_t(c0 >> 1), ph);
+            }
+            mj[j] = mx;
+            lj[j] = sum2.x + sum2.y;
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          mbar_arrive(bar_p + j);
+        }
+      }
+      // merge the group's partial results into the running (m, L, O)
+      float m_new = m_run;
+#pragma unroll
+      for (int j = 0; j < FWDL_MAX_TILES; ++j) m_new = fmaxf(m_new, mj[j]);
+      const float f_old = warp_valid ? ex2_approx((m_run - m_new) * scale_log2) : 0.f;   // 0 for the first group (m_run = -inf)
+      float wj[FWDL_MAX_TILES];
+      L_run *= f_old;
+#pragma unroll
+      for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+        wj[j] = (j < ntg && warp_valid) ? ex2_approx((mj[j] - m_new) * scale_log2) : 0.f;
+        L_run = fmaf(wj[j], lj[j], L_run);
+      }
+      m_run = m_new;
+      mbar_wait(bar_o + (ntg - 1), par, 6);          // commits are ordered: every earlier P_j V_j of the group is complete as well
+      tc_fence_after();
+      if (warp_valid) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] *= f_old;
+#pragma unroll
+        for (int j = 0; j < FWDL_MAX_TILES; ++j) {
+          if (j < ntg) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[32];
+              tmem_ld32_nowait(trow + uint32_t(OL_COL + 64 * j + 32 * hh), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[32 * hh + i] = fmaf(__uint_as_float(v[i]), wj[j], acc[32 * hh + i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_free);
+    }
+    if (q < N) lse[((long long)b * H + h) * N + q] = fmaf(m_run, scale, logf(L_run));
+    const float inv = 1.f / L_run;
+    if (warp_valid) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
         uint4 o;
-        o.x = pk16<H16>(acc[8 * c + 0], acc[8 * c + 1]);
-        o.y = pk16<H16>(acc[8 * c + 2], acc[8 * c + 3]);
-        o.z = pk16<H16>(acc[8 * c + 4], acc[8 * c + 5]);
-        o.w = pk16<H16>(acc[8 * c + 6], acc[8 * c + 7]);
-        *reinterpret_cast<uint4*>(sQ + swz128(row, 4 * hh + c)) = o;
+        o.x = pk16<H16>(acc[8 * c + 0] * inv, acc[8 * c + 1] * inv);
+        o.y = pk16<H16>(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv);
+        o.z = pk16<H16>(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv);
+        o.w = pk16<H16>(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv);
+        *reinterpret_cast<uint4*>(sQ + swz128(row, c)) = o;
       }
     }
     fence_proxy_async();
@@ -1053,6 +1090,433 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
   if (warp == 8) tmem_dealloc<512>(tb);
 }
 
+// ================================================================================================ backward, > 240 tokens
+// Longer sequences (384x384 images: 577 tokens; patch 8: 785 / 1025 ...) do not fit the single-CTA kernel above (it keeps Q, K, V,
+// dO and O of one (image, head) in shared memory).  Two streaming kernels replace it, each with 2 CTAs per SM (256 TMEM columns):
+//   dK/dV: CTA per (128-key tile, head, image); K_j, V_j resident, 64-query chunks of Q / dO through a 2-stage TMA ring:
+//          S^T = K_j Q_c^T, dP^T = V_j dO_c^T (SS) -> P^T, dS^T 16-bit IN PLACE (lane = key) -> dV += P^T dO_c, dK += dS^T Q_c (TS)
+//   dQ:    CTA per (128-query tile, head, image); Q, dO resident, 64-key chunks of K / V through the ring:
+//          S = Q K_c^T, dP = dO V_c^T (SS) -> dS 16-bit in place (lane = query) -> dQ += dS K_c (TS)
+// delta = rowsum(dO o O) comes from attn_delta_kernel (attention.cu).  The chunk steps of a CTA are serial (MMA -> math -> MMA);
+// the second CTA of the SM fills the gaps.  q_limit > 0: dO is zero from query row q_limit on (and out / lse / delta are not
+// valid there): the dK/dV kernel walks only the chunks below it, the dQ kernel writes zeros for those rows.
+constexpr int BL_THREADS = 160;
+constexpr int BL_S = 0, BL_DP = 64, BL_ACC0 = 128, BL_ACC1 = 192;
+
+// P^T / dS^T (or dS) of W columns for one TMEM lane: sv / dv = S and dP values, nl2[i] = -lse*log2e and nd[i] = -delta of column i's
+// query (dK/dV: lane = key, columns = queries) -- or one pair for every column (dQ: lane = query).  fac[i] = dropout factor.
+template <bool H16, int W>
+__device__ __forceinline__ void bl_pack(const uint32_t* sv, const uint32_t* dv, const float* nl2, const float* nd, const float* fac,
+                                        bool per_col, bool have_fac, float scale_log2, uint32_t valid_mask, uint32_t* ph, uint32_t* dh) {
+#pragma unroll
+  for (int i = 0; i < W; i += 2) {
+    const float l0 = per_col ? nl2[i] : nl2[0], l1 = per_col ? nl2[i + 1] : nl2[0];
+    const float d0 = per_col ? nd[i] : nd[0], d1 = per_col ? nd[i + 1] : nd[0];
+    float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, l0));
+    float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, l1));
+    if (!((valid_mask >> i) & 1u)) p0 = 0.f;
+    if (!((valid_mask >> (i + 1)) & 1u)) p1 = 0.f;
+    const float m0 = have_fac ? fac[i] : 1.f, m1 = have_fac ? fac[i + 1] : 1.f;
+    const float s0 = p0 * fmaf(__uint_as_float(dv[i]), m0, d0), s1 = p1 * fmaf(__uint_as_float(dv[i + 1]), m1, d1);
+    ph[i >> 1] = pk16<H16>(p0 * m0, p1 * m1);
+    dh[i >> 1] = pk16<H16>(s0, s1);
+  }
+}
+
+template <bool H16, bool DROP>
+__global__ void __launch_bounds__(BL_THREADS, 2)
+    attn_bwd_dkdv_long_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
+                              const __grid_constant__ CUtensorMap tmDO64, const __grid_constant__ CUtensorMap tmDQKV,
+                              const float* __restrict__ lse, const float* __restrict__ delta, int N, int H, float scale,
+                              float scale_log2, int q_limit, DropSpec drop, int Npad) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sK = smem;                 // [128][64]; dK staging at the end
+  uint8_t* sV = sK + 16384;           // [128][64]; dV staging at the end
+  uint8_t* sQc = sV + 16384;          // 2 x [64][64]
+  uint8_t* sDOc = sQc + 16384;        // 2 x [64][64]
+  float* s_nl2 = reinterpret_cast<float*>(sDOc + 16384);   // [2][64]  -lse * log2e of the chunk's queries
+  float* s_nd = s_nl2 + 128;                               // [2][64]  -delta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_nd + 128);
+  uint64_t* bar_kv = bars + 0;
+  uint64_t* bar_q = bars + 1;         // [2] ring stage filled
+  uint64_t* bar_s = bars + 3;         // S^T, dP^T of chunk c complete
+  uint64_t* bar_p = bars + 4;         // P^T, dS^T written (128 arrivals)
+  uint64_t* bar_m = bars + 5;         // dV / dK MMAs of chunk c complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int QP = (N + 15) & ~15;
+  const int q_end = q_limit > 0 && q_limit < QP ? ((q_limit + 15) & ~15) : QP;   // queries walked (multiple of 16)
+  const int NC = (q_end + 63) >> 6;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tmap(&tmKV128);
+      prefetch_tmap(&tmQ64);
+      prefetch_tmap(&tmDO64);
+      prefetch_tmap(&tmDQKV);
+      mbar_init(bar_kv, 1);
+      mbar_init(bar_q + 0, 1);
+      mbar_init(bar_q + 1, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_m, 1);
+      mbar_init_fence();
+      pdl_wait();
+      mbar_expect_tx(bar_kv, 2 * 16384);
+      tma_load_3d(sK, &tmKV128, bar_kv, (H + h) * DH, jt * 128, b);
+      tma_load_3d(sV, &tmKV128, bar_kv, (2 * H + h) * DH, jt * 128, b);
+      for (int c = 0; c < 2 && c < NC; ++c) {
+        mbar_expect_tx(bar_q + c, 2 * 8192);
+        tma_load_3d(sQc + c * 8192, &tmQ64, bar_q + c, h * DH, c * 64, b);
+        tma_load_3d(sDOc + c * 8192, &tmDO64, bar_q + c, h * DH, c * 64, b);
+      }
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  pdl_trigger();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const uint32_t idesc64_ts = idesc_f16(DH, false, true, H16);
+      const uint64_t kd = smem_desc_kmajor(smem_u32(sK)), vd = smem_desc_kmajor(smem_u32(sV));
+      mbar_wait(bar_kv, 0, 1);
+      for (int c = 0; c < NC; ++c) {
+        const int st = c & 1;
+        const int QC = min(64, q_end - 64 * c);
+        mbar_wait(bar_q + st, (c >> 1) & 1, 2);
+        tc_fence_after();
+        const uint32_t idesc_s = idesc_f16(QC, false, false, H16);
+        const uint64_t qd = smem_desc_kmajor(smem_u32(sQc + st * 8192)), dd = smem_desc_kmajor(smem_u32(sDOc + st * 8192));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tb + BL_S, kd + uint64_t(2 * k), qd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tb + BL_DP, vd + uint64_t(2 * k), dd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, c & 1, 3);
+        tc_fence_after();
+        const int qsteps = QC >> 4;
+        for (int s = 0; s < qsteps; ++s) {     // dV += P^T dO_c
+          const uint64_t bd = smem_desc_mnmajor(smem_u32(sDOc + st * 8192 + 16 * s * 128), 8192);
+          umma_ts(tb + BL_ACC0, tb + uint32_t(BL_S + 8 * s), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
+        }
+        for (int s = 0; s < qsteps; ++s) {     // dK += dS^T Q_c
+          const uint64_t bd = smem_desc_mnmajor(smem_u32(sQc + st * 8192 + 16 * s * 128), 8192);
+          umma_ts(tb + BL_ACC1, tb + uint32_t(BL_DP + 8 * s), bd, idesc64_ts, (c > 0 || s > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_m);
+        mbar_wait(bar_m, c & 1, 4);              // serial: S^T / dP^T columns and the ring stage are free again
+        tc_fence_after();
+        if (c + 2 < NC) {
+          mbar_expect_tx(bar_q + st, 2 * 8192);
+          tma_load_3d(sQc + st * 8192, &tmQ64, bar_q + st, h * DH, (c + 2) * 64, b);
+          tma_load_3d(sDOc + st * 8192, &tmDO64, bar_q + st, h * DH, (c + 2) * 64, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int keyrow = warp * 32 + lane;
+    const int key = jt * 128 + keyrow;
+    const bool keyvalid = key < N;
+    const uint32_t trow = tb + (uint32_t(warp * 32) << 16);
+    const int tid = threadIdx.x;   // 0..127
+    const long long bh = (long long)b * H + h;
+    const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
+    const unsigned long long dstep = (unsigned long long)(Npad >> 3);
+    for (int c = 0; c < NC; ++c) {
+      const int st = c & 1;
+      const int QC = min(64, q_end - 64 * c);
+      {   // the chunk's row statistics -> shared memory (the stage's previous readers finished two chunks ago)
+        const int qq = 64 * c + (tid & 63);
+        if (tid < 64) s_nl2[st * 64 + tid] = qq < N ? -lse[bh * N + qq] * LOG2E : -INFINITY;
+        else s_nd[st * 64 + (tid - 64)] = qq < N ? -delta[bh * N + qq] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(bar_s, c & 1, 5);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int g0 = 32 * half;
+        const int w = min(32, QC - g0);        // 32, 16 or <= 0 (warp-uniform)
+        if (w <= 0) break;
+        uint32_t sv[32], dv[32], ph[16], dh[16];
+        if (w == 32) {
+          tmem_ld32_nowait(trow + uint32_t(BL_S + g0), sv);
+          tmem_ld32_nowait(trow + uint32_t(BL_DP + g0), dv);
+        } else {
+          tmem_ld16_nowait(trow + uint32_t(BL_S + g0), sv);
+          tmem_ld16_nowait(trow + uint32_t(BL_DP + g0), dv);
+        }
+        float fac[32];
+        if constexpr (DROP) {
+          const unsigned long long blk0 = ((unsigned long long)bh * N + (unsigned long long)(64 * c + g0)) * dstep + (unsigned long long)(key >> 3);
+          const int dhalf = key & 7;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < w) {
+              const uint4 bits = drop_bits8(dseed, drop.site, blk0 + (unsigned long long)i * dstep);
+              const uint32_t wd = (dhalf >> 1) == 0 ? bits.x : (dhalf >> 1) == 1 ? bits.y : (dhalf >> 1) == 2 ? bits.z : bits.w;
+              fac[i] = (((dhalf & 1) ? (wd >> 16) : (wd & 0xffffu)) >= drop.thresh) ? drop.inv_keep : 0.f;
+            } else {
+              fac[i] = 0.f;
+            }
+          }
+        }
+        tmem_ld_wait();
+        const uint32_t vmask = keyvalid ? 0xffffffffu : 0u;
+        if (w == 32) bl_pack<H16, 32>(sv, dv, s_nl2 + st * 64 + g0, s_nd + st * 64 + g0, fac, true, DROP, scale_log2, vmask, ph, dh);
+        else bl_pack<H16, 16>(sv, dv, s_nl2 + st * 64 + g0, s_nd + st * 64 + g0, fac, true, DROP, scale_log2, vmask, ph, dh);
+        if (w == 32) {
+          tmem_st16_nowait(trow + uint32_t(BL_S + (g0 >> 1)), ph);
+          tmem_st16_nowait(trow + uint32_t(BL_DP + (g0 >> 1)), dh);
+        } else {
+          tmem_st8_nowait(trow + uint32_t(BL_S + (g0 >> 1)), ph);
+          tmem_st8_nowait(trow + uint32_t(BL_DP + (g0 >> 1)), dh);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // ---- dV (x 1) and dK (x scale) -> 16-bit -> staging (K / V are dead) -> TMA store (rows >= N clipped)
+    mbar_wait(bar_m, (NC - 1) & 1, 6);
+    tc_fence_after();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint8_t* dst = which == 0 ? sV : sK;
+      const float mul = which == 0 ? 1.f : scale;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32_nowait(trow + uint32_t((which == 0 ? BL_ACC0 : BL_ACC1) + 32 * hh), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 o;
+          o.x = pk16<H16>(__uint_as_float(v[8 * cc + 0]) * mul, __uint_as_float(v[8 * cc + 1]) * mul);
+          o.y = pk16<H16>(__uint_as_float(v[8 * cc + 2]) * mul, __uint_as_float(v[8 * cc + 3]) * mul);
+          o.z = pk16<H16>(__uint_as_float(v[8 * cc + 4]) * mul, __uint_as_float(v[8 * cc + 5]) * mul);
+          o.w = pk16<H16>(__uint_as_float(v[8 * cc + 6]) * mul, __uint_as_float(v[8 * cc + 7]) * mul);
+          *reinterpret_cast<uint4*>(dst + swz128(keyrow, 4 * hh + cc)) = o;
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (warp == 0 && elect_one()) {
+      tma_store_3d(&tmDQKV, sV, (2 * H + h) * DH, jt * 128, b);
+      tma_store_3d(&tmDQKV, sK, (H + h) * DH, jt * 128, b);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tb);
+}
+
+template <bool H16, bool DROP>
+__global__ void __launch_bounds__(BL_THREADS, 2)
+    attn_bwd_dq_long_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmDO128,
+                            const __grid_constant__ CUtensorMap tmKV64, const __grid_constant__ CUtensorMap tmDQKV,
+                            const float* __restrict__ lse, const float* __restrict__ delta, int N, int H, float scale,
+                            float scale_log2, int q_limit, DropSpec drop, int Npad) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                 // [128][64]; dQ staging at the end
+  uint8_t* sDO = sQ + 16384;          // [128][64]
+  uint8_t* sKc = sDO + 16384;         // 2 x [64][64]
+  uint8_t* sVc = sKc + 16384;         // 2 x [64][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sVc + 16384);
+  uint64_t* bar_qdo = bars + 0;
+  uint64_t* bar_kv = bars + 1;        // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_m = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int KP = (N + 15) & ~15;
+  const int NJ = (KP + 63) >> 6;
+  const int q_live = q_limit > 0 && q_limit < N ? q_limit : N;   // query rows with a gradient
+  const bool tile_live = q0 < q_live;                             // block-uniform
+
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tmap(&tmQ128);
+      prefetch_tmap(&tmDO128);
+      prefetch_tmap(&tmKV64);
+      prefetch_tmap(&tmDQKV);
+      mbar_init(bar_qdo, 1);
+      mbar_init(bar_kv + 0, 1);
+      mbar_init(bar_kv + 1, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_m, 1);
+      mbar_init_fence();
+      pdl_wait();
+      if (tile_live) {
+        mbar_expect_tx(bar_qdo, 2 * 16384);
+        tma_load_3d(sQ, &tmQ128, bar_qdo, h * DH, q0, b);
+        tma_load_3d(sDO, &tmDO128, bar_qdo, h * DH, q0, b);
+        for (int j = 0; j < 2 && j < NJ; ++j) {
+          mbar_expect_tx(bar_kv + j, 2 * 8192);
+          tma_load_3d(sKc + j * 8192, &tmKV64, bar_kv + j, (H + h) * DH, j * 64, b);
+          tma_load_3d(sVc + j * 8192, &tmKV64, bar_kv + j, (2 * H + h) * DH, j * 64, b);
+        }
+      }
+    }
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  pdl_trigger();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (warp == 4) {
+    if (tile_live && elect_one()) {
+      const uint32_t idesc64_ts = idesc_f16(DH, false, true, H16);
+      const uint64_t qd = smem_desc_kmajor(smem_u32(sQ)), dd = smem_desc_kmajor(smem_u32(sDO));
+      mbar_wait(bar_qdo, 0, 1);
+      for (int j = 0; j < NJ; ++j) {
+        const int st = j & 1;
+        const int KC = min(64, KP - 64 * j);
+        mbar_wait(bar_kv + st, (j >> 1) & 1, 2);
+        tc_fence_after();
+        const uint32_t idesc_s = idesc_f16(KC, false, false, H16);
+        const uint64_t kd = smem_desc_kmajor(smem_u32(sKc + st * 8192)), vd = smem_desc_kmajor(smem_u32(sVc + st * 8192));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tb + BL_S, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tb + BL_DP, dd + uint64_t(2 * k), vd + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, j & 1, 3);
+        tc_fence_after();
+        const int ksteps = KC >> 4;
+        for (int s = 0; s < ksteps; ++s) {     // dQ += dS K_c
+          const uint64_t bd = smem_desc_mnmajor(smem_u32(sKc + st * 8192 + 16 * s * 128), 8192);
+          umma_ts(tb + BL_ACC0, tb + uint32_t(BL_S + 8 * s), bd, idesc64_ts, (j > 0 || s > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_m);
+        mbar_wait(bar_m, j & 1, 4);
+        tc_fence_after();
+        if (j + 2 < NJ) {
+          mbar_expect_tx(bar_kv + st, 2 * 8192);
+          tma_load_3d(sKc + st * 8192, &tmKV64, bar_kv + st, (H + h) * DH, (j + 2) * 64, b);
+          tma_load_3d(sVc + st * 8192, &tmKV64, bar_kv + st, (2 * H + h) * DH, (j + 2) * 64, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int row = warp * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t trow = tb + (uint32_t(warp * 32) << 16);
+    const long long bh = (long long)b * H + h;
+    const bool rowlive = q < q_live;
+    if (tile_live) {
+      float nl2 = rowlive ? -lse[bh * N + q] * LOG2E : -INFINITY;
+      float nd = rowlive ? -delta[bh * N + q] : 0.f;
+      const unsigned long long dseed = DROP ? __ldg(drop.seed) : 0ull;
+      const unsigned long long rowblk = DROP ? (((unsigned long long)bh * N + (rowlive ? q : 0)) * (unsigned long long)Npad) >> 3 : 0ull;
+      for (int j = 0; j < NJ; ++j) {
+        const int KC = min(64, KP - 64 * j);
+        const int key0 = 64 * j;
+        mbar_wait(bar_s, j & 1, 5);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int g0 = 32 * half;
+          const int w = min(32, KC - g0);
+          if (w <= 0) break;
+          uint32_t sv[32], dv[32], ph[16], dh[16];
+          if (w == 32) {
+            tmem_ld32_nowait(trow + uint32_t(BL_S + g0), sv);
+            tmem_ld32_nowait(trow + uint32_t(BL_DP + g0), dv);
+          } else {
+            tmem_ld16_nowait(trow + uint32_t(BL_S + g0), sv);
+            tmem_ld16_nowait(trow + uint32_t(BL_DP + g0), dv);
+          }
+          float fac[32];
+          if constexpr (DROP) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint4 bits = drop_bits8(dseed, drop.site, rowblk + (unsigned long long)(((key0 + g0) >> 3) + t));
+              const uint32_t wd[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = drop_pair(wd[e], drop.thresh, drop.inv_keep);
+                fac[8 * t + 2 * e] = f.x;
+                fac[8 * t + 2 * e + 1] = f.y;
+              }
+            }
+          }
+          tmem_ld_wait();
+          const int nvalid = N - (key0 + g0);                        // keys of this half below N
+          const uint32_t vmask = !rowlive ? 0u : nvalid >= 32 ? 0xffffffffu : nvalid <= 0 ? 0u : ((1u << nvalid) - 1u);
+          if (w == 32) bl_pack<H16, 32>(sv, dv, &nl2, &nd, fac, false, DROP, scale_log2, vmask, ph, dh);
+          else bl_pack<H16, 16>(sv, dv, &nl2, &nd, fac, false, DROP, scale_log2, vmask, ph, dh);
+          // only dS is an operand here (dQ += dS K); it goes where S was
+          if (w == 32) tmem_st16_nowait(trow + uint32_t(BL_S + (g0 >> 1)), dh);
+          else tmem_st8_nowait(trow + uint32_t(BL_S + (g0 >> 1)), dh);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
+      mbar_wait(bar_m, (NJ - 1) & 1, 6);
+      tc_fence_after();
+    }
+    // ---- dQ x scale -> 16-bit -> staging (Q is dead) -> TMA store; rows without a gradient are written as zeros
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];
+      if (tile_live) {
+        tmem_ld32_nowait(trow + uint32_t(BL_ACC0 + 32 * hh), v);
+        tmem_ld_wait();
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (rowlive) {
+          o.x = pk16<H16>(__uint_as_float(v[8 * cc + 0]) * scale, __uint_as_float(v[8 * cc + 1]) * scale);
+          o.y = pk16<H16>(__uint_as_float(v[8 * cc + 2]) * scale, __uint_as_float(v[8 * cc + 3]) * scale);
+          o.z = pk16<H16>(__uint_as_float(v[8 * cc + 4]) * scale, __uint_as_float(v[8 * cc + 5]) * scale);
+          o.w = pk16<H16>(__uint_as_float(v[8 * cc + 6]) * scale, __uint_as_float(v[8 * cc + 7]) * scale);
+        }
+        *reinterpret_cast<uint4*>(sQ + swz128(row, 4 * hh + cc)) = o;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (warp == 0 && elect_one()) {
+      tma_store_3d(&tmDQKV, sQ, h * DH, q0, b);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<256>(tb);
+}
+
 // ------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -1117,13 +1581,19 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
   return VITK_OK;
 }
 
-// Forward for 256 < N <= 816 (key tiles, see attn_fwd_tc_long_kernel).
+// Forward for N > 256 (key tiles, see attn_fwd_tc_long_kernel).
 template <bool H16, bool DROP>
 int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, DropSpec drop,
                                cudaStream_t st) {
-  const int NKT = (N + 255) / 256;
-  const int KT = (((N + NKT - 1) / NKT) + 15) & ~15;
-  if (NKT > FWDL_MAX_TILES || KT > 256 || (NKT - 1) * KT >= N) {
+  int NKT = (N + 255) / 256, KT, TPG;
+  if (N <= 816) {          // one group: K and V are loaded once
+    KT = (((N + NKT - 1) / NKT) + 15) & ~15;
+    TPG = NKT;
+  } else {                 // groups of three 256-key tiles (16 + 192 KB of shared memory, 256 + 192 TMEM columns)
+    KT = 256;
+    TPG = 3;
+  }
+  if (TPG > FWDL_MAX_TILES || KT > 256 || (NKT - 1) * KT >= N) {
     set_error("attention_fwd_tc_long: N=%d out of range", N);
     return VITK_ERR_INVALID;
   }
@@ -1132,7 +1602,7 @@ int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, in
   if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KT, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
-  const int smem = 128 * 128 + 2 * NKT * KT * 128 + 128 + 1024;
+  const int smem = 128 * 128 + 2 * TPG * KT * 128 + 192 + 1024;
   if (smem > 227 * 1024) {
     set_error("attention_fwd_tc_long: N=%d needs %d bytes of shared memory", N, smem);
     return VITK_ERR_INVALID;
@@ -1145,8 +1615,8 @@ int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, in
   }
   const int q_need = q_rows > 0 && q_rows < N ? q_rows : N;
   dim3 grid((q_need + 127) / 128, H, B);
-  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, lse, N, H, KT, NKT, scale, scale * LOG2E, drop,
-                       (N + 7) & ~7));
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, tmO, lse, N, H, KT, NKT, TPG, scale, scale * LOG2E,
+                       drop, (N + 7) & ~7));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -1173,6 +1643,38 @@ int attention_bwd_tc_impl(const void* qkv, const void* out, const void* dout, co
   const int q_chunks = q_rows > 0 && q_rows < N ? (q_rows + 63) / 64 : 0;
   VITK_CUDA(launch_pdl(kfn, grid, dim3(BWD_THREADS), (size_t)smem, st, tmQKV, tmDO, tmO, tmDQKV, lse, delta, N, H, QP, scale,
                        scale * LOG2E, num_sms(), q_chunks, drop, (N + 7) & ~7));
+  VITK_LAUNCH_CHECK();
+  return VITK_OK;
+}
+
+// Backward for N > 240: delta must already hold rowsum(dO o O) (attn_delta_kernel).  q_rows as in attention_bwd_tc_impl.
+template <bool H16, bool DROP>
+int attention_bwd_tc_long_impl(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
+                               float scale, int q_rows, DropSpec drop, cudaStream_t st) {
+  CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64, tmDQKV;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQKV128, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmQKV64, qkv, 3 * H * DH, N, B, 64, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmDO128, dout, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmDO64, dout, H * DH, N, B, 64, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmDQKV, dqkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  const int smem_kv = 4 * 16384 + 1024 + 64 + 1024, smem_q = 4 * 16384 + 64 + 1024;
+  auto kkv = attn_bwd_dkdv_long_kernel<H16, DROP>;
+  auto kq = attn_bwd_dq_long_kernel<H16, DROP>;
+  static bool configured = false;
+  if (!configured) {
+    VITK_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
+    VITK_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q));
+    configured = true;
+  }
+  const int q_limit = q_rows > 0 && q_rows < N ? q_rows : 0;
+  const int Npad = (N + 7) & ~7;
+  dim3 grid((N + 127) / 128, H, B);
+  VITK_CUDA(launch_pdl(kkv, grid, dim3(BL_THREADS), (size_t)smem_kv, st, tmQKV128, tmQKV64, tmDO64, tmDQKV, lse, delta, N, H, scale,
+                       scale * LOG2E, q_limit, drop, Npad));
+  VITK_LAUNCH_CHECK();
+  VITK_CUDA(launch_pdl(kq, grid, dim3(BL_THREADS), (size_t)smem_q, st, tmQKV128, tmDO128, tmQKV64, tmDQKV, lse, delta, N, H, scale,
+                       scale * LOG2E, q_limit, drop, Npad));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
@@ -1234,6 +1736,16 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
                 : attention_bwd_tc_impl<false, true>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, *drop, st);
   return fp16 ? attention_bwd_tc_impl<true, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, none, st)
               : attention_bwd_tc_impl<false, false>(qkv, out, dout, lse, delta, dqkv, B, N, H, scale, q_rows, none, st);
+}
+
+int attention_bwd_tc_long(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int N, int H,
+                          float scale, int q_rows, bool fp16, const DropSpec* drop, cudaStream_t st) {
+  const DropSpec none = make_drop_spec(nullptr, 0.f, 0);
+  if (drop != nullptr && drop->seed != nullptr)
+    return fp16 ? attention_bwd_tc_long_impl<true, true>(qkv, dout, lse, delta, dqkv, B, N, H, scale, q_rows, *drop, st)
+                : attention_bwd_tc_long_impl<false, true>(qkv, dout, lse, delta, dqkv, B, N, H, scale, q_rows, *drop, st);
+  return fp16 ? attention_bwd_tc_long_impl<true, false>(qkv, dout, lse, delta, dqkv, B, N, H, scale, q_rows, none, st)
+              : attention_bwd_tc_long_impl<false, false>(qkv, dout, lse, delta, dqkv, B, N, H, scale, q_rows, none, st);
 }
 
 }  // namespace vitk
