@@ -1,6 +1,7 @@
 // attention_tc.cu -- fused softmax attention on the 5th-gen tensor cores (tcgen05.mma, S / P / O and every backward
-// accumulator resident in TMEM, operands staged by TMA), head_dim 64, sequences of up to 256 tokens
-// (every 224x224 / 256x256... configuration of the reference with N = 197 / 198; longer sequences use attention.cu).
+// accumulator resident in TMEM, operands staged by TMA), head_dim 64.  The first two kernels serve sequences of up to 256 / 240
+// tokens (every 224x224 / 256x256 configuration of the reference with N = 197 / 198 / 257 at patch 16); the key-tile forward
+// and the two streaming backward kernels further down serve every longer sequence (384x384: 577; patch 8: 785 / 1025 / 2305).
 //
 // Replaces Attention.forward's q@k^T*scale -> softmax -> attn@v (vision_transformer_base.py:182-191) and its autograd
 // backward.  Layouts are the reference's own: qkv [B,N,3,H,64] as nn.Linear(D,3D) emits it (:178), out [B,N,H,64] =
@@ -312,14 +313,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
 //   m' = max(m, max_j m_j),  O' = O 2^((m - m') c) + sum_j 2^((m_j - m') c) O_j,  L' likewise,  out = O / L,  lse = m scale + log L.
 // The issuer starts S_{j+1} only after P_j V_j has completed (P_j lives in S's columns) and the next group's loads only after the
 // group's last MMA; the group's first P V waits until the previous group's accumulators have been read (bar_free).
+// TCOLS = 512: S tile of up to 256 keys + up to 4 accumulators, one CTA per SM; TCOLS = 256: S tile of up to 128 keys + 2
+// accumulators, two CTAs per SM (one CTA's softmax runs under the other's MMAs and loads).
 constexpr int FWDL_MAX_TILES = 4;
-constexpr int OL_COL = 256;   // first O accumulator
 
-template <bool H16, bool DROP>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+template <bool H16, bool DROP, int TCOLS>
+__global__ void __launch_bounds__(FWD_THREADS, TCOLS == 256 ? 2 : 1)
     attn_fwd_tc_long_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                             const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse, int N, int H, int KT, int NKT, int TPG,
                             float scale, float scale_log2, DropSpec drop, int Npad) {
+  constexpr int OL_COL = TCOLS / 2;   // first O accumulator
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
       for (int j = 0; j < nt0; ++j) tma_load_3d(sV + j * tile_bytes, &tmKV, bar_v, (2 * H + h) * DH, j * KT, b);
     }
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    tmem_alloc<TCOLS>(tmem_slot);
   }
   pdl_trigger();
   pdl_wait();
@@ -576,7 +579,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tb);
+  if (warp == 4) tmem_dealloc<TCOLS>(tb);
 }
 
 // ================================================================================================ eval-mode attention maps
@@ -1582,32 +1585,15 @@ int attention_fwd_tc_impl(const void* qkv, void* out, float* lse, int B, int N, 
 }
 
 // Forward for N > 256 (key tiles, see attn_fwd_tc_long_kernel).
-template <bool H16, bool DROP>
-int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, DropSpec drop,
-                               cudaStream_t st) {
-  int NKT = (N + 255) / 256, KT, TPG;
-  if (N <= 816) {          // one group: K and V are loaded once
-    KT = (((N + NKT - 1) / NKT) + 15) & ~15;
-    TPG = NKT;
-  } else {                 // groups of three 256-key tiles (16 + 192 KB of shared memory, 256 + 192 TMEM columns)
-    KT = 256;
-    TPG = 3;
-  }
-  if (TPG > FWDL_MAX_TILES || KT > 256 || (NKT - 1) * KT >= N) {
-    set_error("attention_fwd_tc_long: N=%d out of range", N);
-    return VITK_ERR_INVALID;
-  }
-  CUtensorMap tmQ, tmKV, tmO;
-  int rc;
-  if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
-  if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KT, H16)) != VITK_OK) return rc;
-  if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+template <bool H16, bool DROP, int TCOLS>
+int attention_fwd_tc_long_launch(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const CUtensorMap& tmO, float* lse, int B, int N, int H,
+                                 int KT, int NKT, int TPG, float scale, int q_rows, DropSpec drop, cudaStream_t st) {
   const int smem = 128 * 128 + 2 * TPG * KT * 128 + 192 + 1024;
   if (smem > 227 * 1024) {
     set_error("attention_fwd_tc_long: N=%d needs %d bytes of shared memory", N, smem);
     return VITK_ERR_INVALID;
   }
-  auto kfn = attn_fwd_tc_long_kernel<H16, DROP>;
+  auto kfn = attn_fwd_tc_long_kernel<H16, DROP, TCOLS>;
   static int configured = 0;
   if (configured < smem) {
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1619,6 +1605,39 @@ int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, in
                        drop, (N + 7) & ~7));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
+}
+
+template <bool H16, bool DROP>
+int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, DropSpec drop,
+                               cudaStream_t st) {
+  // two CTAs per SM (128-key tiles in groups of two, 256 TMEM columns): 129 us against 190 us for the one-CTA configuration
+  // (256-key tiles, all of K / V resident) at 32 x 12 heads x 577 tokens -- one CTA's softmax runs under the other's MMAs
+  constexpr bool two = true;
+  int NKT, KT, TPG;
+  if (two) {
+    NKT = (N + 127) / 128;
+    KT = (((N + NKT - 1) / NKT) + 15) & ~15;
+    TPG = 2;
+  } else if (N <= 816) {   // one group: K and V are loaded once
+    NKT = (N + 255) / 256;
+    KT = (((N + NKT - 1) / NKT) + 15) & ~15;
+    TPG = NKT;
+  } else {                 // groups of three 256-key tiles (16 + 192 KB of shared memory, 256 + 192 TMEM columns)
+    NKT = (N + 255) / 256;
+    KT = 256;
+    TPG = 3;
+  }
+  if (TPG > FWDL_MAX_TILES || KT > (two ? 128 : 256) || (NKT - 1) * KT >= N) {
+    set_error("attention_fwd_tc_long: N=%d out of range", N);
+    return VITK_ERR_INVALID;
+  }
+  CUtensorMap tmQ, tmKV, tmO;
+  int rc;
+  if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KT, H16)) != VITK_OK) return rc;
+  if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
+  return two ? attention_fwd_tc_long_launch<H16, DROP, 256>(tmQ, tmKV, tmO, lse, B, N, H, KT, NKT, TPG, scale, q_rows, drop, st)
+             : attention_fwd_tc_long_launch<H16, DROP, 512>(tmQ, tmKV, tmO, lse, B, N, H, KT, NKT, TPG, scale, q_rows, drop, st);
 }
 
 template <bool H16, bool DROP>
