@@ -39,7 +39,7 @@ def main():
     torch.cuda.synchronize()
     print("eval", tuple(out.shape), tuple(feats.shape), v.get_attention_maps().shape)
     # the non-default constructor options: gap pooling + pre_logits (pool_head.cu), linear patch projection (patchify_hwc),
-    # attention-probability dropout (mma.sync attention kernels with masks), no class token
+    # attention-probability dropout (DROP instantiations of the tcgen05 attention kernels), no class token
     for kw in (dict(pool_type="gap", representation_size=128, projection_type="linear", attn_drop_rate=0.1, drop_rate=0.1),
                dict(class_token=False, attn_drop_rate=0.2)):
         g = vit.VisionTransformer(img_size=64, patch_size=16, in_chans=3, num_classes=2, embed_dim=128, depth=2, num_heads=2,
