@@ -1141,7 +1141,11 @@ extern "C" int vitk_gemm(const vitk_gemm_args* a, void* stream) {
       const int tile_rows = pair ? 2 * BLOCK_M : BLOCK_M;
       const long tiles = (long)((a->M + tile_rows - 1) / tile_rows) * ((a->N + bn - 1) / bn);
       const long units = pair ? num_sms() / 2 : num_sms();
-      long want = (2 * units) / tiles;   // floor: never a third, partial round of work units
+      // CTA pairs (long K, ViT-B): about two work units per pair, so that the epilogue of one overlaps the MMAs of the next.
+      // Single CTAs (DeiT-tiny's 192-wide gradients): ONE round -- the units are L2-bandwidth-bound, a second round only adds
+      // its 1.9-round tail and twice the reduce-add traffic (measured, tools/wgrad_scan.py: qkv 31.7 -> 29.7 us, fc1 33.8 ->
+      // 31.7, fc2 35.8 -> 33.8, proj 21.4 -> 19.5)
+      long want = pair ? (2 * units) / tiles : units / tiles;   // floor: never a partial extra round of work units
       const long cap = num_kblocks / 8 > 0 ? num_kblocks / 8 : 1;
       split_k = (int)(want < 1 ? 1 : want > cap ? cap : want);
     }
