@@ -651,3 +651,29 @@ def test_cls_attention_heatmap_from_the_model_api_batch_256():
     assert (heat[:4] - heat[4:8]).abs().max().item() < 1e-6 and (heat[:4] - heat[252:]).abs().max().item() < 1e-6
     want = O.cls_attention_heatmap(last[:4].float().cpu().unsqueeze(0), (224, 224), -1, n_prefix=2)
     assert (heat[:4].cpu() - want).abs().max().item() < HEAT_TOL
+
+
+# ------------------------------------------------------------------ long sequences through the whole model (tcgen05 key-tile kernels)
+@pytest.mark.parametrize("img,patch,deit,batch", [(384, 16, True, 3), (384, 16, False, 2), (224, 8, False, 2)])
+def test_long_sequence_models_vs_oracle(img, patch, deit, batch):
+    """384x384 images (577 / 578 tokens; tests/test_vision_transformer_base.py:309-319 exercises this size) and patch 8 at 224
+    (785 tokens): logits, loss and every parameter gradient of a 2-block model against the oracle.  These shapes run the
+    key-tile forward and the streaming dK/dV + dQ kernels, with the last block pruned to the classifier's rows (q_rows)."""
+    cfg = O.VitConfig(img_size=img, patch_size=patch, embed_dim=128, depth=2, num_heads=2, is_deit=deit, distilled=deit)
+    model, sd = build(cfg, 31)
+    x, y = O.seeded_batch(cfg, batch, 31)
+    loss, outs, grads = run_gpu(model, x, y)
+    ref_loss, ref_out, ref_grads = O.train_step(sd, x, y, cfg)
+    ref_outs = ref_out if isinstance(ref_out, tuple) else (ref_out,)
+    for o, ref in zip(outs, ref_outs):
+        assert (o - ref.detach()).abs().max().item() < LOGIT_TOL
+    assert abs(loss - ref_loss.item()) < 2e-3
+    worst = max((rel_l2(grads[n], g), n) for n, g in ref_grads.items() if g is not None)
+    assert worst[0] < GRAD_TOL, worst
+    model.eval()
+    with torch.no_grad():
+        ev = model(x.cuda())
+    ref_ev = O.forward(sd, x, cfg, training=False)
+    assert (ev.cpu() - ref_ev).abs().max().item() < LOGIT_TOL
+    maps = model.blocks[-1].attn.attention_maps                       # fp32 maps beyond one S tile: the CUDA-core row kernel
+    assert maps.shape[-1] == cfg.num_patches + cfg.num_prefix and (maps.sum(-1) - 1).abs().max().item() < 1e-5
