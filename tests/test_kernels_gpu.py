@@ -292,8 +292,9 @@ def test_attention_probs_with_batch_stride_equal_the_contiguous_maps():
     assert torch.equal(im[:, 2], ref) and im[:, 1].abs().max().item() == 0 and im[:, 3].abs().max().item() == 0
 
 
-def test_attention_probs_rows_sum_to_one():
-    B, N, H = 2, 198, 3
+@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (2, 257, 2), (2, 577, 3), (1, 785, 2), (1, 1025, 1)])
+def test_attention_probs_rows_sum_to_one(B, N, H):
+    """Eval-mode maps on the tensor core for every sequence length (one key tile up to 256 tokens, key tiles beyond)."""
     qkv = _rand(B, N, 3 * H * 64, dtype=F16, seed=1)
     probs = torch.empty(B, H, N, N, device=DEV)
     ops.attention_fwd(qkv, B, N, H, 0.125, probs=probs)

@@ -11,15 +11,13 @@
 //
 // Every matrix product runs on the tcgen05 / TMEM kernels of attention_tc.cu, for every sequence length and with or without
 // attention-probability dropout (the round-1 mma.sync kernels that used to serve long sequences and dropout are gone).  What
-// lives here: argument validation, delta = rowsum(dO o O) for the streaming long-sequence backward, and the fp32 eval-mode
-// attention maps for sequences longer than one S tile.
+// lives here: argument validation and delta = rowsum(dO o O) for the streaming long-sequence backward.
 #include "vitk_common.cuh"
 
 namespace vitk {
 namespace {
 
 constexpr int DH = 64;
-constexpr float LOG2E = 1.4426950408889634f;
 
 typedef __nv_bfloat16 bf16;
 
@@ -50,57 +48,9 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   }
 }
 
-// ------------------------------------------------------------------ eval-only attention maps
-// probs[b,h,q,:] = softmax(q.k^T*scale) in fp32 -- the `attention_maps` the reference stores in
-// eval mode (vision_transformer_base.py:186-188).  One warp per (b,h,q) row; not on the train path.
-template <bool H16>
-__global__ void attn_probs_kernel(const bf16* __restrict__ qkv, float* __restrict__ probs, long long batch_stride, int B, int N, int H,
-                                  float scale) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b,h,q)
-  const int lane = threadIdx.x & 31;
-  if (row >= (long long)B * H * N) return;
-  const int q = int(row % N);
-  const int h = int((row / N) % H);
-  const int b = int(row / ((long long)N * H));
-  const bf16* qp = qkv + (((long long)(b * N + q) * 3 + 0) * H + h) * DH;
-  float qv[DH];
-#pragma unroll
-  for (int d = 0; d < DH; d += 2) {
-    const float2 f = upk<H16>(*reinterpret_cast<const uint32_t*>(qp + d));
-    qv[d] = f.x; qv[d + 1] = f.y;
-  }
-  float* prow = probs + (long long)b * batch_stride + ((long long)h * N + q) * N;
-  float mx = -INFINITY;
-  for (int k = lane; k < N; k += 32) {
-    const bf16* kp = qkv + (((long long)(b * N + k) * 3 + 1) * H + h) * DH;
-    float acc = 0.f;
-#pragma unroll
-    for (int d = 0; d < DH; d += 8) {
-      const uint4 u = ldg_u4(kp + d);
-      const float2 f0 = upk<H16>(u.x), f1 = upk<H16>(u.y), f2 = upk<H16>(u.z), f3 = upk<H16>(u.w);
-      acc += qv[d] * f0.x + qv[d + 1] * f0.y + qv[d + 2] * f1.x + qv[d + 3] * f1.y + qv[d + 4] * f2.x +
-             qv[d + 5] * f2.y + qv[d + 6] * f3.x + qv[d + 7] * f3.y;
-    }
-    acc *= scale;
-    prow[k] = acc;
-    mx = fmaxf(mx, acc);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int k = lane; k < N; k += 32) {
-    const float e = __expf(prow[k] - mx);
-    prow[k] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
-  for (int k = lane; k < N; k += 32) prow[k] *= inv;
-}
-
 }  // namespace
 
 // tcgen05 / TMEM kernels (attention_tc.cu)
-constexpr int TC_MAX_TOKENS = 256;      // one S tile: the short forward kernel and the tensor-core eval-mode maps
 constexpr int TC_MAX_TOKENS_BWD = 240;  // the single-CTA pipelined backward (shared-memory budget); streaming kernels beyond
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, bool fp16, const DropSpec* drop,
                      cudaStream_t st);
@@ -117,12 +67,7 @@ using namespace vitk;
 template <bool H16>
 static int attention_probs_impl(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H,
                                 float scale, cudaStream_t st) {
-  if (N <= TC_MAX_TOKENS) return attention_probs_tc(qkv, lse, probs, batch_stride, B, N, H, scale, H16, st);   // tensor-core S + lse
-  const long long rows = (long long)B * H * N;
-  attn_probs_kernel<H16><<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(reinterpret_cast<const bf16*>(qkv), probs, batch_stride, B, N, H,
-                                                                     scale);
-  VITK_LAUNCH_CHECK();
-  return VITK_OK;
+  return attention_probs_tc(qkv, lse, probs, batch_stride, B, N, H, scale, H16, st);   // tensor-core S + the forward's lse
 }
 
 template <bool H16>

@@ -588,12 +588,14 @@ __global__ void __launch_bounds__(FWD_THREADS, TCOLS == 256 ? 2 : 1)
 // the map is exp2(s * c - lse * log2e): one S = Q K^T on the tensor core (bit-identical to the forward's S), one pass over
 // the TMEM row per thread, no max / sum / P / V.  HBM-bound on the B*H*N*N*4 bytes it writes (120 MB per DeiT-tiny layer at
 // batch 256): each thread streams its row as 16-byte stores, two consecutive store instructions completing every 32-byte
-// sector.  CTA per (128-query tile, head, image), 2 CTAs / SM like the forward.
+// sector.  CTA per (128-query tile x key tile, head, image), 2 CTAs / SM like the forward; up to 256 tokens there is one key
+// tile (KP = the padded sequence), longer sequences split the keys into tiles of KP <= 256 (blockIdx.x = key tile * NQT + query
+// tile) -- every map element depends on its own (q, k) pair and the row's lse only, so the tiles are independent.
 template <bool H16>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
     attn_probs_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const float* __restrict__ lse, float* __restrict__ probs, long long batch_stride, int N, int H, int KP,
-                         float scale_log2) {
+                         float scale_log2, int NQT) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (blockIdx.x % NQT) * 128, key0 = (blockIdx.x / NQT) * KP, h = blockIdx.y, b = blockIdx.z;
 
   if (warp == 4) {
     if (elect_one()) {
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
       pdl_wait();
       mbar_expect_tx(bar_qk, (128 + KP) * 128);
       tma_load_3d(sQ, &tmQ, bar_qk, h * DH, q0, b);
-      tma_load_3d(sK, &tmKV, bar_qk, (H + h) * DH, 0, b);
+      tma_load_3d(sK, &tmKV, bar_qk, (H + h) * DH, key0, b);
     }
     __syncwarp();
     tmem_alloc<256>(tmem_slot);
@@ -674,8 +676,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 2)
           tile[lane * 33 + j + 1] = ex2_approx(x.y);
         }
         __syncwarp();
-        const int col = c0 + lane;
-        if (col < N) {
+        const int col = key0 + c0 + lane;
+        if (col < N && c0 + lane < KP) {          // the tile's own keys only (a 16-wide last chunk leaves lanes 16.. without data)
           const int nrows = min(32, N - r0);
           for (int rr = 0; rr < nrows; ++rr) pbase[(long long)rr * N + col] = tile[rr * 33 + lane];
         }
@@ -1702,11 +1704,13 @@ int attention_bwd_tc_long_impl(const void* qkv, const void* dout, const float* l
 extern "C" int vitk_debug_read_attn(long long* dst) { return (int)cudaMemcpyFromSymbol(dst, g_attn_dbg, sizeof(g_attn_dbg)); }
 #endif
 
-// Eval-mode attention maps for N <= 256 (needs the lse the forward just wrote).
+// Eval-mode attention maps (needs the lse the forward just wrote).
 template <bool H16>
 int attention_probs_tc_impl(const void* qkv, const float* lse, float* probs, long long batch_stride, int B, int N, int H, float scale,
                             cudaStream_t st) {
-  const int KP = (N + 15) & ~15;
+  const int NKT = (N + 255) / 256;
+  const int KP = (((N + NKT - 1) / NKT) + 15) & ~15;       // keys per tile (<= 256); one tile up to 256 tokens
+  const int NQT = (N + 127) / 128;
   CUtensorMap tmQ, tmKV;
   int rc;
   if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
@@ -1718,8 +1722,8 @@ int attention_probs_tc_impl(const void* qkv, const float* lse, float* probs, lon
     VITK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 + 256 * 128 + 4 * 32 * 33 * 4 + 64 + 1024));
     configured = true;
   }
-  dim3 grid((N + 127) / 128, H, B);
-  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, lse, probs, batch_stride, N, H, KP, scale * LOG2E));
+  dim3 grid(NQT * NKT, H, B);
+  VITK_CUDA(launch_pdl(kfn, grid, dim3(FWD_THREADS), (size_t)smem, st, tmQ, tmKV, lse, probs, batch_stride, N, H, KP, scale * LOG2E, NQT));
   VITK_LAUNCH_CHECK();
   return VITK_OK;
 }
