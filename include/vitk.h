@@ -159,6 +159,8 @@ int vitk_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const f
  * bwd recomputes P from q,k and lse; delta = rowsum(dout*out) is computed internally into
  * `delta` (fp32 [B,H,N] scratch).
  * probs (optional, eval only): fp32 [B,H,N,N] attention maps (:186-188 `attention_maps`).
+ * Any sequence length: up to 256 (forward) / 240 (backward) tokens one CTA holds the whole key range, longer sequences
+ *   (384x384 images: 577 tokens; patch 8: 785 / 1025) walk key / query tiles; every product runs on tcgen05.
  * q_rows (0 = every row): the caller needs only query rows 0..q_rows-1 of `out` / `lse` (forward; the other rows may be left
  *   unwritten) resp. guarantees that `dout` is zero from row q_rows on (backward; dqkv is still complete: dQ is zero there and
  *   dK / dV sum over the leading rows).  The last block of a class-token model: the classifier reads x[:, 0] (and x[:, 1]) only

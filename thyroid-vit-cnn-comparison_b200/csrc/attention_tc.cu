@@ -1612,24 +1612,14 @@ int attention_fwd_tc_long_launch(const CUtensorMap& tmQ, const CUtensorMap& tmKV
 template <bool H16, bool DROP>
 int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, int N, int H, float scale, int q_rows, DropSpec drop,
                                cudaStream_t st) {
-  // two CTAs per SM (128-key tiles in groups of two, 256 TMEM columns): 129 us against 190 us for the one-CTA configuration
-  // (256-key tiles, all of K / V resident) at 32 x 12 heads x 577 tokens -- one CTA's softmax runs under the other's MMAs
-  constexpr bool two = true;
-  int NKT, KT, TPG;
-  if (two) {
-    NKT = (N + 127) / 128;
-    KT = (((N + NKT - 1) / NKT) + 15) & ~15;
-    TPG = 2;
-  } else if (N <= 816) {   // one group: K and V are loaded once
-    NKT = (N + 255) / 256;
-    KT = (((N + NKT - 1) / NKT) + 15) & ~15;
-    TPG = NKT;
-  } else {                 // groups of three 256-key tiles (16 + 192 KB of shared memory, 256 + 192 TMEM columns)
-    NKT = (N + 255) / 256;
-    KT = 256;
-    TPG = 3;
-  }
-  if (TPG > FWDL_MAX_TILES || KT > (two ? 128 : 256) || (NKT - 1) * KT >= N) {
+  // Two CTAs per SM: 128-key tiles in groups of two, 256 TMEM columns, 83 KB of shared memory -- one CTA's softmax runs under the
+  // other's MMAs and loads.  Measured at 32 x 12 heads x 577 tokens: 129 us, against 190 us for the one-CTA-per-SM
+  // configuration of the same kernel (TCOLS = 512: 256-key tiles, all of K / V resident up to 816 tokens) and 182 us for the
+  // round-1 mma.sync kernel (profiles/r02_attention_long_sequences.txt).
+  const int NKT = (N + 127) / 128;
+  const int KT = (((N + NKT - 1) / NKT) + 15) & ~15;
+  const int TPG = 2;
+  if (KT > 128 || (NKT - 1) * KT >= N) {
     set_error("attention_fwd_tc_long: N=%d out of range", N);
     return VITK_ERR_INVALID;
   }
@@ -1638,8 +1628,7 @@ int attention_fwd_tc_long_impl(const void* qkv, void* out, float* lse, int B, in
   if ((rc = make_tmap_3d(&tmQ, qkv, 3 * H * DH, N, B, 128, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmKV, qkv, 3 * H * DH, N, B, KT, H16)) != VITK_OK) return rc;
   if ((rc = make_tmap_3d(&tmO, out, H * DH, N, B, 128, H16)) != VITK_OK) return rc;
-  return two ? attention_fwd_tc_long_launch<H16, DROP, 256>(tmQ, tmKV, tmO, lse, B, N, H, KT, NKT, TPG, scale, q_rows, drop, st)
-             : attention_fwd_tc_long_launch<H16, DROP, 512>(tmQ, tmKV, tmO, lse, B, N, H, KT, NKT, TPG, scale, q_rows, drop, st);
+  return attention_fwd_tc_long_launch<H16, DROP, 256>(tmQ, tmKV, tmO, lse, B, N, H, KT, NKT, TPG, scale, q_rows, drop, st);
 }
 
 template <bool H16, bool DROP>
