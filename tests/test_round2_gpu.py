@@ -620,7 +620,9 @@ def test_cls_attention_heatmap_matches_reference_fixture_and_oracle():
                                            align_corners=False)[:, 0]
     for src in (roll, roll[:, 0, :].contiguous()):
         assert (ENS.cls_attention_heatmap(src, 48, n_prefix=2).cpu() - want).abs().max().item() < HEAT_TOL
-    assert (ENS.cls_attention_heatmap(roll[:, 0, 2:].reshape(5, 6, 6), 48).cpu() - want).abs().max().item() < HEAT_TOL
+    assert (ENS.cls_attention_heatmap(roll[:, 0, 2:].reshape(5, 6, 6), 48, grid=True).cpu() - want).abs().max().item() < HEAT_TOL
+    with pytest.raises(ValueError):
+        ENS.cls_attention_heatmap(roll[:, :5, :7], 48)                           # 3-D but not square: neither a rollout matrix nor a grid
     # the reference's hard-wired `[0, 1:]` on a 38-token sequence leaves 37 columns: not a square grid -> ValueError here
     with pytest.raises(ValueError):
         ENS.cls_attention_heatmap(maps.cuda(), 48, n_prefix=1)

@@ -54,25 +54,34 @@ def cls_attention_grid(rollout_or_map: torch.Tensor, n_prefix: int) -> torch.Ten
     return a.reshape(-1, g, g)
 
 
-def cls_attention_heatmap(attention: torch.Tensor, image_size, layer_idx: int = -1, n_prefix: int = 1) -> torch.Tensor:
+def cls_attention_heatmap(attention: torch.Tensor, image_size, layer_idx: int = -1, n_prefix: int = 1, grid: bool = False) -> torch.Tensor:
     """The numeric part of `visualize_attention_maps` (attention_utils.py:50-67) for the whole batch -> fp32 [B,H_img,W_img].
 
     attention   [L,B,H,N,N] (what `get_attention_maps()` returns; `layer_idx` picks the layer, default the last one like
                 the reference's `layer_indices=[-1]`), one layer's [B,H,N,N], a rollout matrix [B,N,N] (its class-token
-                row is used), a rollout row [B,N] or a grid [B,g,g] as `EnsembleInference(rollout=True)` returns per fold.
+                row is used) or a rollout row [B,N]; with grid=True a ready [B,g,g] grid, e.g. one fold of what
+                `EnsembleInference(rollout=True)` returns (a 3-D input is ambiguous otherwise: [B,10,10] could be either).
     image_size  `original_image.shape[:2]` (int or (h, w)).
     n_prefix    tokens before the patches: the reference slices `attn[0, 1:]`, i.e. 1 -- with a distilled DeiT's 198 tokens
-                that leaves 197 columns and its `reshape(14, 14)` raises; pass 2 there.
+                that leaves 197 columns and its `reshape(14, 14)` raises; pass 2 there.  Ignored with grid=True.
     """
     if not attention.is_cuda:
         raise RuntimeError("cls_attention_heatmap runs on a CUDA device through libvitk.so (no CPU fallback)")
     hw = (int(image_size), int(image_size)) if isinstance(image_size, int) else (int(image_size[0]), int(image_size[1]))
     a = attention.float()
+    if grid:
+        if a.dim() != 3 or a.shape[-1] != a.shape[-2]:
+            raise ValueError("grid=True expects [B,g,g]")
+        return ops.cls_attention_heatmap(a, hw, 0)
     if a.dim() == 5:
         a = a[layer_idx]
-    elif a.dim() == 3 and a.shape[-1] == a.shape[-2] and math.isqrt(a.shape[-1] - n_prefix) ** 2 == a.shape[-1] - n_prefix:
-        a = a[:, 0, :]                               # [B,N,N] rollout: the class token's row
-    if a.dim() == 4 and a.stride(3) != 1:
+    elif a.dim() == 3:
+        if a.shape[-1] != a.shape[-2]:
+            raise ValueError("a 3-D input must be a rollout matrix [B,N,N] (or a [B,g,g] grid with grid=True)")
+        a = a[:, 0, :]                               # the class token's row
+    elif a.dim() not in (2, 4):
+        raise ValueError("attention must be [L,B,H,N,N], [B,H,N,N], [B,N,N] or [B,N]")
+    if a.stride(-1) != 1:
         a = a.contiguous()
     return ops.cls_attention_heatmap(a, hw, n_prefix)
 
