@@ -305,6 +305,37 @@ def test_attention_probs_rows_sum_to_one(B, N, H):
     assert (probs - p_ref).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("B,N,H", [(2, 198, 3), (2, 577, 2), (1, 785, 1), (1, 1025, 1)])
+def test_attention_outputs_stay_inside_their_buffers(B, N, H):
+    """Canaries behind out / lse / delta / dqkv / probs: every attention kernel (short, key-tile forward, streaming backward,
+    tensor-core maps) writes ragged tails (N % 128 != 0) through clipped TMA boxes or guarded stores -- nothing may land past
+    the tensors.  (compute-sanitizer is not available on the GPU pool, so the bounds are checked this way.)"""
+    pad = 4096
+
+    def guarded(shape, dtype, fill):
+        n = 1
+        for d in shape:
+            n *= d
+        flat = torch.full((n + pad,), fill, dtype=dtype, device=DEV)
+        return flat, flat[:n].view(*shape)
+
+    qkv = _rand(B, N, 3 * H * 64, dtype=F16, seed=3)
+    f_out, out = guarded((B, N, H * 64), F16, 777.0)
+    f_lse, lse = guarded((B, H, N), torch.float32, 777.0)
+    f_pr, probs = guarded((B, H, N, N), torch.float32, 777.0)
+    ops.attention_fwd(qkv, B, N, H, 0.125, out=out, lse=lse, probs=probs)
+    dout = _rand(B, N, H * 64, dtype=F16, seed=4)
+    f_dq, dqkv = guarded((B, N, 3 * H * 64), F16, 777.0)
+    f_de, delta = guarded((B, H, N), torch.float32, 777.0)
+    ops.attention_bwd(qkv, out, dout, lse, B, N, H, 0.125, dqkv=dqkv, delta=delta)
+    torch.cuda.synchronize()
+    for name, flat in (("out", f_out), ("lse", f_lse), ("probs", f_pr), ("dqkv", f_dq), ("delta", f_de)):
+        assert (flat[-pad:] == 777.0).all(), name
+    for t in (out, lse, probs, dqkv):
+        assert torch.isfinite(t.float()).all() and not (t == 777.0).all()
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
+
+
 # ------------------------------------------------------------------ token plumbing
 @pytest.mark.parametrize("B,C,S,P", [(3, 3, 224, 16), (2, 1, 256, 16), (2, 3, 64, 8), (1, 3, 64, 32)])
 @pytest.mark.parametrize("dt", [F16, BF16])
